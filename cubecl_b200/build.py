@@ -1,0 +1,94 @@
+"""In-tree build of the native pieces (no JIT cache, no pip install):
+
+  csrc/*.cu  --nvcc -cubin, sm_100a-->  build/*.cubin  --.incbin-->  lib/libcubecl_b200.so  (host: g++, dlopen's libcuda)
+
+The cubins are PREBUILT images loaded with cuModuleLoadData at b200_init(); nothing is compiled at run time
+(the reference's NVRTC step, crates/cubecl-cuda/src/compute/context.rs:141-317, is what this replaces).
+
+`python -m cubecl_b200.build` or `__graft_entry__.build()` runs it; nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+BUILD = PKG / "build"
+LIBDIR = PKG / "lib"
+LIB = LIBDIR / "libcubecl_b200.so"
+
+CUBINS = {"gemm": "gemm_tcgen05.cu", "reduce": "reduce.cu", "aux": "aux_kernels.cu"}
+NVCC_FLAGS = ["-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA kernels cannot be built")
+
+
+def _cuda_include() -> str:
+    for cand in (os.environ.get("CUDA_HOME"), "/usr/local/cuda"):
+        if cand and (Path(cand) / "include" / "cuda.h").exists():
+            return str(Path(cand) / "include")
+    raise RuntimeError("cuda.h not found")
+
+
+def _digest(paths) -> str:
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def _run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError("build step failed: " + " ".join(map(str, cmd)) + "\n" + r.stdout)
+    return r.stdout
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Build lib/libcubecl_b200.so if sources changed. Returns the library path."""
+    BUILD.mkdir(exist_ok=True)
+    LIBDIR.mkdir(exist_ok=True)
+    sources = [p for p in CSRC.iterdir() if p.suffix in (".cu", ".cuh", ".cpp", ".h")]
+    sources.append(ROOT / "include" / "cubecl_b200.h")
+    stamp = BUILD / "stamp.txt"
+    digest = _digest(sources)
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+        return LIB
+    nvcc = _nvcc()
+    for tag, src in CUBINS.items():
+        out = BUILD / f"{tag}.cubin"
+        log = _run([nvcc, *NVCC_FLAGS, "-Xptxas", "-v", str(CSRC / src), "-o", str(out)])
+        (BUILD / f"{tag}.ptxas.log").write_text(log)
+        if verbose:
+            print(log)
+    # embed the cubins with .incbin (64-byte aligned, begin/end symbols)
+    asm = [".section .rodata\n"]
+    for tag in CUBINS:
+        asm.append(
+            f".global b200_cubin_{tag}\n.global b200_cubin_{tag}_end\n.balign 64\n"
+            f"b200_cubin_{tag}:\n.incbin \"{BUILD / (tag + '.cubin')}\"\nb200_cubin_{tag}_end:\n.byte 0\n"
+        )
+    asm.append('.section .note.GNU-stack,"",@progbits\n')
+    embed = BUILD / "embed.S"
+    embed.write_text("".join(asm))
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-I", _cuda_include(),
+          str(CSRC / "capi.cpp"), str(embed), "-ldl", "-lpthread", "-o", str(LIB)])
+    stamp.write_text(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

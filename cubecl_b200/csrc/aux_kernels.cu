@@ -1,0 +1,163 @@
+// Auxiliary sm_100a kernels (cubin):
+//  * counter-hash generators so host (numpy) and device produce bit-identical synthetic operands without PCIe traffic
+//  * a strided SIMT matmul for operands whose strides/alignment TMA cannot describe (still a CUDA path, never a CPU one);
+//    it accumulates in f32 over increasing k with separate mul/add roundings, i.e. exactly the reference's CPU order
+//    (crates/cubecl-core/src/runtime_tests/cmma.rs:695-721), so it is bit-comparable with the oracle
+//  * the two "what the reference would run on this GPU" probes, written by hand from CubeCL's emit rules:
+//      wmma_probe_f16            <- crates/cubecl-std/src/throughput/runners/compute_cmma.rs:47-91 lowered through
+//                                   crates/cubecl-cpp/src/shared/mma.rs:67-155 (nvcuda::wmma 16x16x16, f16 -> f16)
+//      memread_probe_vec4        <- crates/cubecl-std/src/throughput/runners/memory_read.rs:68-154 (float_4 loads)
+//  * 3xTF32 operand splitting (f32 matmul at near-f32 accuracy on the tf32 tensor pipe)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <mma.h>
+#include <cstdint>
+
+// ------------------------------------------------------------------------------------------------ generators
+// splitmix64 finaliser over (seed, index); the numpy mirror lives in cubecl_b200/synth.py.
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t i) {
+  uint64_t z = seed * 0x9E3779B97F4A7C15ull + i + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<uint32_t>(z >> 32);
+}
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i, float lo, float scale) {
+  // 24 random bits -> [0,1) exactly representable, then one multiply and one add, both rounded to nearest
+  const float u = static_cast<float>(hash_u32(seed, i) >> 8) * (1.0f / 16777216.0f);
+  return __fadd_rn(lo, __fmul_rn(u, scale));
+}
+
+struct FillParams {
+  uint64_t out, n, seed;
+  float lo, scale;     // value = lo + u * scale
+  uint32_t dtype;      // 0 f32, 1 f16, 2 bf16
+  uint32_t mode;       // 0 uniform hash, 1 (i % modulus) as a number
+  uint32_t modulus, pad;
+};
+
+extern "C" __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillParams p) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const float v = (p.mode == 0) ? hash_uniform(p.seed, i, p.lo, p.scale) : static_cast<float>(i % p.modulus);
+    if (p.dtype == 0) reinterpret_cast<float*>(p.out)[i] = v;
+    else if (p.dtype == 1) reinterpret_cast<__half*>(p.out)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(p.out)[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ strided SIMT matmul
+struct SimtGemmParams {
+  uint64_t a, b, out;
+  uint64_t a_sb, a_sm, a_sk;  // strides in elements: batch, m, k
+  uint64_t b_sb, b_sk, b_sn;
+  uint64_t o_sb, o_sm, o_sn;
+  uint32_t M, N, K, batch;
+  uint32_t in_dtype, out_dtype;  // 0 f32, 1 f16, 2 bf16
+};
+
+__device__ __forceinline__ float load_as_f32(uint64_t base, uint64_t idx, uint32_t dt) {
+  if (dt == 0) return reinterpret_cast<const float*>(base)[idx];
+  if (dt == 1) return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+__device__ __forceinline__ void store_from_f32(uint64_t base, uint64_t idx, uint32_t dt, float v) {
+  if (dt == 0) reinterpret_cast<float*>(base)[idx] = v;
+  else if (dt == 1) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid_constant__ SimtGemmParams p) {
+  __shared__ float sa[16][17];
+  __shared__ float sb[16][17];
+  const uint32_t tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const uint32_t m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx, bz = blockIdx.z;
+  float acc = 0.f;
+  for (uint32_t k0 = 0; k0 < p.K; k0 += 16) {
+    const uint32_t ka = k0 + tx, kb = k0 + ty;
+    sa[ty][tx] = (m < p.M && ka < p.K) ? load_as_f32(p.a, bz * p.a_sb + m * p.a_sm + ka * p.a_sk, p.in_dtype) : 0.f;
+    sb[ty][tx] = (kb < p.K && n < p.N) ? load_as_f32(p.b, bz * p.b_sb + kb * p.b_sk + n * p.b_sn, p.in_dtype) : 0.f;
+    __syncthreads();
+    const uint32_t kmax = min(16u, p.K - k0);
+    for (uint32_t k = 0; k < kmax; ++k) acc = __fadd_rn(acc, __fmul_rn(sa[ty][k], sb[k][tx]));  // no FMA: reference order
+    __syncthreads();
+  }
+  if (m < p.M && n < p.N) store_from_f32(p.out, bz * p.o_sb + m * p.o_sm + n * p.o_sn, p.out_dtype, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ 3xTF32 split
+// hi = x with the low 13 mantissa bits cleared (what the tf32 datapath reads anyway), lo = x - hi (exact in f32).
+// mode 0 (operand whose K is innermost, [rows, K]):  out[b][r][3K] = [hi | hi | lo]   (lhs)
+// mode 1 (same layout, the other operand)         :  out[b][r][3K] = [hi | lo | hi]   (rhs stored [N,K])
+// mode 2 (rhs stored row-major [K, N])            :  out[b][3K][N] = [hi ; lo ; hi] stacked along K
+// A tf32 GEMM over K' = 3K then computes hi*hi + hi*lo + lo*hi with f32 accumulation.
+struct SplitParams {
+  uint64_t in, out;
+  uint64_t batch, rows, cols;   // logical [batch, rows, cols], cols innermost (stride 1)
+  uint64_t in_bs, in_rs;        // input strides in elements
+  uint32_t mode, pad;
+};
+extern "C" __global__ void __launch_bounds__(256) split_tf32(const __grid_constant__ SplitParams p) {
+  const uint64_t per = p.rows * p.cols, total = p.batch * per;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t b = i / per, rem = i - b * per;
+    const uint64_t r = rem / p.cols, c = rem - r * p.cols;
+    const float x = reinterpret_cast<const float*>(p.in)[b * p.in_bs + r * p.in_rs + c];
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    const float lo = x - hi;
+    float* o = reinterpret_cast<float*>(p.out) + b * 3 * per;
+    if (p.mode == 2) {
+      o[rem] = hi; o[per + rem] = lo; o[2 * per + rem] = hi;
+    } else {
+      float* row = o + r * 3 * p.cols;
+      row[c] = hi;
+      row[p.cols + c] = (p.mode == 0) ? hi : lo;
+      row[2 * p.cols + c] = (p.mode == 0) ? lo : hi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ reference probes
+// compute_cmma_throughput: A,B = fill(1), acc = 0, n_iter x mma_sync(acc, a, b, acc), unit 0 of each plane-0 stores.
+// Launch exactly like compute_cmma.rs:20-42: grid = SMs*32, block = 256 (8 planes).
+extern "C" __global__ void __launch_bounds__(256) wmma_probe_f16(__half* out, uint32_t n_iter) {
+  using namespace nvcuda;
+  wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> a;
+  wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> b;
+  wmma::fragment<wmma::accumulator, 16, 16, 16, __half> acc;
+  wmma::fill_fragment(a, __float2half(1.0f));
+  wmma::fill_fragment(b, __float2half(1.0f));
+  wmma::fill_fragment(acc, __float2half(0.0f));
+  for (uint32_t i = 0; i < n_iter; ++i) wmma::mma_sync(acc, a, b, acc);
+  if (threadIdx.x < 32 && blockIdx.x == 0) wmma::store_matrix_sync(out, acc, 16, wmma::mem_row_major);
+}
+// bf16 -> f32 variant (what a cubek bf16 matmul would accumulate with: cuda_compiler.rs:27-31)
+extern "C" __global__ void __launch_bounds__(256) wmma_probe_bf16(float* out, uint32_t n_iter) {
+  using namespace nvcuda;
+  wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> a;
+  wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> b;
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+  wmma::fill_fragment(a, __float2bfloat16(1.0f));
+  wmma::fill_fragment(b, __float2bfloat16(1.0f));
+  wmma::fill_fragment(acc, 0.0f);
+  for (uint32_t i = 0; i < n_iter; ++i) wmma::mma_sync(acc, a, b, acc);
+  if (threadIdx.x < 32 && blockIdx.x == 0) wmma::store_matrix_sync(out, acc, 16, wmma::mem_row_major);
+}
+
+// memory_read_throughput: acc += input[ABSOLUTE_POS + step * stride] over `steps` coalesced float_4 lines,
+// one accumulator per unit (memory_read.rs:95-99), unit 0 writes one line.
+extern "C" __global__ void __launch_bounds__(256) memread_probe_vec4(const float4* __restrict__ in, float4* out,
+                                                                      uint64_t lines, uint32_t steps) {
+  const uint64_t pos = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t s = 0; s < steps; ++s) {
+    const uint64_t idx = pos + s * stride;
+    if (idx < lines) {
+      const float4 v = in[idx];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (pos == 0 || acc.x == -1.2345e33f) out[0] = acc;  // the data-dependent arm keeps every unit's loads alive
+}

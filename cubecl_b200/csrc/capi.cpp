@@ -1,0 +1,1167 @@
+// Host side of the C ABI declared in include/cubecl_b200.h.
+//
+// What this file is: the B200-native stand-in for the pieces of cubecl-cuda that sit between `ComputeClient::launch` and
+// `cuLaunchKernel` on the dense-LA hot path -- minus NVRTC.  It loads libcuda (and, lazily, libnccl) with dlopen exactly
+// like cudarc's dynamic loading does (reference Cargo.toml:179-187), retains the device's primary context, loads the
+// PREBUILT sm_100a cubins embedded in this library with cuModuleLoadData (the call the reference makes with NVRTC's PTX at
+// crates/cubecl-cuda/src/compute/context.rs:293), keeps a small exclusive-page memory pool + pinned staging
+// (semantics of crates/cubecl-runtime/src/memory_management, crates/cubecl-cuda/src/compute/storage/gpu.rs:174-207),
+// encodes TMA descriptors (same cuTensorMapEncodeTiled call as crates/cubecl-cuda/src/compute/server.rs:1210-1224) and
+// launches.  No kernels are generated, compiled or autotuned at run time and nothing here can run without a GPU.
+#include "../../include/cubecl_b200.h"
+
+#include <cuda.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+// ================================================================================================ embedded cubins
+extern "C" {
+extern const unsigned char b200_cubin_gemm[];
+extern const unsigned char b200_cubin_gemm_end[];
+extern const unsigned char b200_cubin_reduce[];
+extern const unsigned char b200_cubin_reduce_end[];
+extern const unsigned char b200_cubin_aux[];
+extern const unsigned char b200_cubin_aux_end[];
+}
+
+// ================================================================================================ errors
+static thread_local std::string g_last_error;
+
+static int fail(int status, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return status;
+}
+
+extern "C" const char* b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+// ================================================================================================ driver loading
+#define DRV_FUNCTIONS(X)                                                                                              \
+  X(cuInit) X(cuDeviceGetCount) X(cuDeviceGet) X(cuDeviceGetName) X(cuDeviceGetAttribute) X(cuDeviceTotalMem)        \
+  X(cuDevicePrimaryCtxRetain) X(cuDevicePrimaryCtxRelease) X(cuCtxSetCurrent) X(cuCtxSynchronize)                    \
+  X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuFuncSetAttribute) X(cuFuncGetAttribute)           \
+  X(cuLaunchKernelEx) X(cuLaunchKernel) X(cuOccupancyMaxActiveClusters)                                              \
+  X(cuMemAlloc) X(cuMemFree) X(cuMemAllocHost) X(cuMemFreeHost) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync)            \
+  X(cuMemcpyDtoDAsync) X(cuMemsetD32Async) X(cuMemGetInfo)                                                           \
+  X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent)                                   \
+  X(cuEventCreate) X(cuEventRecord) X(cuEventElapsedTime) X(cuEventDestroy) X(cuEventSynchronize)                    \
+  X(cuTensorMapEncodeTiled) X(cuGetErrorString) X(cuGetErrorName)
+
+struct Driver {
+  void* lib = nullptr;
+  bool ok = false;
+  std::string why;
+#define X(n) decltype(&n) n##_p = nullptr;
+  DRV_FUNCTIONS(X)
+#undef X
+};
+static Driver g_drv;
+static std::once_flag g_drv_once;
+
+static void load_driver() {
+  const char* names[] = {"libcuda.so.1", "libcuda.so"};
+  for (const char* n : names) {
+    g_drv.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_drv.lib) break;
+  }
+  if (!g_drv.lib) {
+    g_drv.why = "cannot dlopen libcuda.so.1 (no NVIDIA driver): this library has no CPU fallback";
+    return;
+  }
+  using GetProc = CUresult (*)(const char*, void**, int, cuuint64_t, CUdriverProcAddressQueryResult*);
+  GetProc get_proc = reinterpret_cast<GetProc>(dlsym(g_drv.lib, "cuGetProcAddress_v2"));
+  if (!get_proc) {
+    g_drv.why = "libcuda has no cuGetProcAddress_v2 (driver older than CUDA 12)";
+    return;
+  }
+#define X(n)                                                                                              \
+  {                                                                                                       \
+    void* fp = nullptr;                                                                                   \
+    CUdriverProcAddressQueryResult q;                                                                     \
+    CUresult r = get_proc(#n, &fp, 12080, CU_GET_PROC_ADDRESS_DEFAULT, &q);                               \
+    if (r != CUDA_SUCCESS || !fp) {                                                                       \
+      g_drv.why = std::string("driver symbol missing: ") + #n;                                            \
+      return;                                                                                             \
+    }                                                                                                     \
+    g_drv.n##_p = reinterpret_cast<decltype(&n)>(fp);                                                     \
+  }
+  DRV_FUNCTIONS(X)
+#undef X
+  CUresult r = g_drv.cuInit_p(0);
+  if (r != CUDA_SUCCESS) {
+    g_drv.why = "cuInit failed (" + std::to_string(static_cast<int>(r)) + "): no usable GPU";
+    return;
+  }
+  g_drv.ok = true;
+}
+
+static int ensure_driver() {
+  std::call_once(g_drv_once, load_driver);
+  if (!g_drv.ok) return fail(B200_ERR_NO_DEVICE, "%s", g_drv.why.c_str());
+  return B200_OK;
+}
+
+static const char* cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.cuGetErrorString_p && g_drv.cuGetErrorString_p(r, &s) == CUDA_SUCCESS && s) return s;
+  return "unknown CUDA error";
+}
+
+static int map_cu(CUresult r) {
+  switch (r) {
+    case CUDA_ERROR_OUT_OF_MEMORY: return B200_ERR_OUT_OF_MEMORY;
+    case CUDA_ERROR_LAUNCH_OUT_OF_RESOURCES: return B200_ERR_TOO_MANY_RESOURCES;
+    case CUDA_ERROR_INVALID_IMAGE:
+    case CUDA_ERROR_NO_BINARY_FOR_GPU:
+    case CUDA_ERROR_INVALID_SOURCE: return B200_ERR_COMPILATION;
+    case CUDA_ERROR_ILLEGAL_ADDRESS:
+    case CUDA_ERROR_LAUNCH_FAILED:
+    case CUDA_ERROR_ILLEGAL_INSTRUCTION:
+    case CUDA_ERROR_MISALIGNED_ADDRESS:
+    case CUDA_ERROR_HARDWARE_STACK_ERROR:
+    case CUDA_ERROR_LAUNCH_TIMEOUT: return B200_ERR_UNHEALTHY;
+    default: return B200_ERR_UNKNOWN;
+  }
+}
+
+#define CU_CHECK(call)                                                                               \
+  do {                                                                                               \
+    CUresult _r = (call);                                                                            \
+    if (_r != CUDA_SUCCESS) return fail(map_cu(_r), "%s failed: %s (%d)", #call, cu_err(_r), (int)_r); \
+  } while (0)
+
+// ================================================================================================ NCCL loading (lazy)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+// ncclDataType_t / ncclRedOp_t numeric values are ABI-stable across NCCL 2.x
+enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat16 = 6,
+       ncclFloat32 = 7, ncclFloat64 = 8, ncclBfloat16 = 9 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4 };
+
+struct Nccl {
+  void* lib = nullptr;
+  bool ok = false;
+  std::string why;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, CUstream) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+static std::once_flag g_nccl_once;
+
+static void load_nccl() {
+  // If torch already mapped its bundled libnccl.so.2 the soname lookup returns that copy; otherwise the system one.
+  g_nccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.lib) {
+    g_nccl.why = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+    return;
+  }
+#define L(field, sym)                                                        \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.lib, sym)); \
+  if (!g_nccl.field) { g_nccl.why = std::string("nccl symbol missing: ") + sym; return; }
+  L(GetUniqueId, "ncclGetUniqueId")
+  L(CommInitRank, "ncclCommInitRank")
+  L(CommDestroy, "ncclCommDestroy")
+  L(AllReduce, "ncclAllReduce")
+  L(GetErrorString, "ncclGetErrorString")
+#undef L
+  g_nccl.ok = true;
+}
+
+static int ensure_nccl() {
+  std::call_once(g_nccl_once, load_nccl);
+  if (!g_nccl.ok) return fail(B200_ERR_COMM, "%s", g_nccl.why.c_str());
+  return B200_OK;
+}
+
+#define NCCL_CHECK(call)                                                                                      \
+  do {                                                                                                        \
+    int _r = (call);                                                                                          \
+    if (_r != ncclSuccess) return fail(B200_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(_r));     \
+  } while (0)
+
+// ================================================================================================ kernel parameter blocks
+// (layouts mirror the structs in gemm_tcgen05.cu / reduce.cu / aux_kernels.cu)
+struct GemmParams {
+  uint64_t out, out_row_stride, out_batch_stride;
+  uint32_t M, N, K, batch;
+  uint32_t tiles_m, tiles_n, group_m;
+  uint32_t a_bmul, b_bmul, vec_store;
+};
+struct ReduceParams {
+  uint64_t in, out, ws;
+  uint64_t outer, len, inner;
+  float scale;
+  uint32_t pad;
+};
+struct FillParams {
+  uint64_t out, n, seed;
+  float lo, scale;
+  uint32_t dtype, mode, modulus, pad;
+};
+struct SimtGemmParams {
+  uint64_t a, b, out;
+  uint64_t a_sb, a_sm, a_sk, b_sb, b_sk, b_sn, o_sb, o_sm, o_sn;
+  uint32_t M, N, K, batch, in_dtype, out_dtype;
+};
+struct SplitParams {
+  uint64_t in, out, batch, rows, cols, in_bs, in_rs;
+  uint32_t mode, pad;
+};
+static constexpr uint32_t kWsMaxBlocks = 4096;
+static constexpr uint32_t kWsTicketOffset = kWsMaxBlocks * 4 + kWsMaxBlocks * 8;
+static constexpr size_t kWsBytes = kWsTicketOffset + 256;
+
+// ================================================================================================ context
+struct PoolBlock {
+  size_t size;
+  bool in_use;
+};
+
+struct CommState {
+  ncclComm_t comm = nullptr;
+  int rank = -1, n = 0;
+};
+
+struct b200_ctx {
+  int device = -1;
+  CUdevice dev{};
+  CUcontext cuctx = nullptr;
+  b200_props props{};
+  CUstream stream = nullptr;       // default compute stream
+  CUstream comm_stream = nullptr;  // dedicated NCCL stream (server.rs:944)
+  CUevent comm_event = nullptr;
+  std::vector<CUmodule> modules;
+  std::unordered_map<std::string, CUfunction> funcs;
+  // exclusive-page pool: exact-size free lists
+  std::map<size_t, std::vector<CUdeviceptr>> free_lists;
+  std::unordered_map<CUdeviceptr, PoolBlock> blocks;
+  uint64_t bytes_in_use = 0, bytes_reserved = 0;
+  std::unordered_map<void*, size_t> pinned;
+  std::unordered_map<CUstream, CUdeviceptr> reduce_ws;
+  std::map<std::string, CUtensorMap> tmap_cache;
+  std::map<std::vector<int>, CommState> comms;
+  std::unordered_map<std::string, std::string> options;
+  uint64_t launches = 0;
+};
+
+static inline CUstream resolve_stream(b200_ctx* c, b200_stream s) { return s ? static_cast<CUstream>(s) : c->stream; }
+
+#define CTX_ENTER(c)                                                  \
+  if (!(c)) return fail(B200_ERR_INVALID_ARG, "null context");        \
+  CU_CHECK(g_drv.cuCtxSetCurrent_p((c)->cuctx));
+
+static std::string opt(b200_ctx* c, const char* key, const char* dflt) {
+  auto it = c->options.find(key);
+  if (it != c->options.end()) return it->second;
+  std::string env = std::string("B200_") + key;
+  for (auto& ch : env) ch = (ch == '.') ? '_' : static_cast<char>(toupper(ch));
+  if (const char* e = getenv(env.c_str())) return e;
+  return dflt;
+}
+
+static int load_module(b200_ctx* c, const unsigned char* begin, const unsigned char* end, const char* what) {
+  if (end <= begin) return fail(B200_ERR_COMPILATION, "embedded cubin '%s' is empty (library was built without kernels)", what);
+  CUmodule m;
+  CUresult r = g_drv.cuModuleLoadData_p(&m, begin);
+  if (r != CUDA_SUCCESS)
+    return fail(B200_ERR_COMPILATION, "cuModuleLoadData(%s) failed: %s -- the cubins are sm_100a only", what, cu_err(r));
+  c->modules.push_back(m);
+  return B200_OK;
+}
+
+static int get_func(b200_ctx* c, const std::string& name, CUfunction* out) {
+  auto it = c->funcs.find(name);
+  if (it != c->funcs.end()) { *out = it->second; return B200_OK; }
+  for (CUmodule m : c->modules) {
+    CUfunction f;
+    if (g_drv.cuModuleGetFunction_p(&f, m, name.c_str()) == CUDA_SUCCESS) {
+      c->funcs[name] = f;
+      *out = f;
+      return B200_OK;
+    }
+  }
+  return fail(B200_ERR_COMPILATION, "kernel '%s' not found in the prebuilt cubins", name.c_str());
+}
+
+extern "C" int b200_device_count(int* count) {
+  if (!count) return fail(B200_ERR_INVALID_ARG, "null count");
+  int rc = ensure_driver();
+  if (rc) return rc;
+  CU_CHECK(g_drv.cuDeviceGetCount_p(count));
+  return B200_OK;
+}
+
+extern "C" int b200_init(int device, b200_ctx** out) {
+  if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
+  *out = nullptr;
+  int rc = ensure_driver();
+  if (rc) return rc;
+  int n = 0;
+  CU_CHECK(g_drv.cuDeviceGetCount_p(&n));
+  if (device < 0 || device >= n) return fail(B200_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, n);
+  b200_ctx* c = new b200_ctx();
+  c->device = device;
+  auto bail = [&](int code) { delete c; return code; };
+  CUresult r;
+  if ((r = g_drv.cuDeviceGet_p(&c->dev, device)) != CUDA_SUCCESS) return bail(fail(map_cu(r), "cuDeviceGet: %s", cu_err(r)));
+  if ((r = g_drv.cuDevicePrimaryCtxRetain_p(&c->cuctx, c->dev)) != CUDA_SUCCESS)
+    return bail(fail(map_cu(r), "cuDevicePrimaryCtxRetain: %s", cu_err(r)));
+  if ((r = g_drv.cuCtxSetCurrent_p(c->cuctx)) != CUDA_SUCCESS) return bail(fail(map_cu(r), "cuCtxSetCurrent: %s", cu_err(r)));
+  auto attr = [&](CUdevice_attribute a) { int v = 0; g_drv.cuDeviceGetAttribute_p(&v, a, c->dev); return v; };
+  c->props.device = device;
+  c->props.cc_major = attr(CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR);
+  c->props.cc_minor = attr(CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR);
+  c->props.num_sms = attr(CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT);
+  c->props.max_shared_per_block = attr(CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN);
+  c->props.clock_khz = attr(CU_DEVICE_ATTRIBUTE_CLOCK_RATE);
+  c->props.mem_clock_khz = attr(CU_DEVICE_ATTRIBUTE_MEMORY_CLOCK_RATE);
+  c->props.plane_size = 32;
+  size_t total = 0;
+  g_drv.cuDeviceTotalMem_p(&total, c->dev);
+  c->props.total_mem = total;
+  g_drv.cuDeviceGetName_p(c->props.name, sizeof(c->props.name), c->dev);
+  if (c->props.cc_major != 10) {
+    g_drv.cuDevicePrimaryCtxRelease_p(c->dev);
+    return bail(fail(B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library ships sm_100a cubins only (B200)", device,
+                     c->props.cc_major, c->props.cc_minor));
+  }
+  if ((rc = load_module(c, b200_cubin_gemm, b200_cubin_gemm_end, "gemm")) ||
+      (rc = load_module(c, b200_cubin_reduce, b200_cubin_reduce_end, "reduce")) ||
+      (rc = load_module(c, b200_cubin_aux, b200_cubin_aux_end, "aux"))) {
+    for (CUmodule m : c->modules) g_drv.cuModuleUnload_p(m);
+    g_drv.cuDevicePrimaryCtxRelease_p(c->dev);
+    return bail(rc);
+  }
+  if ((r = g_drv.cuStreamCreate_p(&c->stream, CU_STREAM_NON_BLOCKING)) != CUDA_SUCCESS ||
+      (r = g_drv.cuStreamCreate_p(&c->comm_stream, CU_STREAM_NON_BLOCKING)) != CUDA_SUCCESS ||
+      (r = g_drv.cuEventCreate_p(&c->comm_event, CU_EVENT_DISABLE_TIMING)) != CUDA_SUCCESS) {
+    g_drv.cuDevicePrimaryCtxRelease_p(c->dev);
+    return bail(fail(map_cu(r), "stream/event creation failed: %s", cu_err(r)));
+  }
+  *out = c;
+  return B200_OK;
+}
+
+extern "C" int b200_destroy(b200_ctx* c) {
+  if (!c) return B200_OK;
+  if (g_drv.ok && g_drv.cuCtxSetCurrent_p(c->cuctx) == CUDA_SUCCESS) {
+    g_drv.cuCtxSynchronize_p();
+    for (auto& kv : c->comms)
+      if (kv.second.comm && g_nccl.ok) g_nccl.CommDestroy(kv.second.comm);
+    for (auto& kv : c->blocks) g_drv.cuMemFree_p(kv.first);
+    for (auto& kv : c->reduce_ws) g_drv.cuMemFree_p(kv.second);
+    for (auto& kv : c->pinned) g_drv.cuMemFreeHost_p(kv.first);
+    if (c->comm_event) g_drv.cuEventDestroy_p(c->comm_event);
+    if (c->comm_stream) g_drv.cuStreamDestroy_p(c->comm_stream);
+    if (c->stream) g_drv.cuStreamDestroy_p(c->stream);
+    for (CUmodule m : c->modules) g_drv.cuModuleUnload_p(m);
+    g_drv.cuDevicePrimaryCtxRelease_p(c->dev);
+  }
+  delete c;
+  return B200_OK;
+}
+
+extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
+  if (!c || !out) return fail(B200_ERR_INVALID_ARG, "null argument");
+  *out = c->props;
+  return B200_OK;
+}
+
+extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
+  if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "reduce.variant", "reduce.threads",
+                                "reduce.blocks_per_sm"};
+  for (const char* k : known)
+    if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
+  return fail(B200_ERR_INVALID_ARG, "unknown option '%s'", key);
+}
+
+extern "C" int b200_launch_count(b200_ctx* c, uint64_t* count) {
+  if (!c || !count) return fail(B200_ERR_INVALID_ARG, "null argument");
+  *count = c->launches;
+  return B200_OK;
+}
+
+// ================================================================================================ memory
+static size_t pool_round(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  const size_t align = bytes >= (64u << 20) ? (2u << 20) : bytes >= (1u << 20) ? (64u << 10) : 512;
+  return (bytes + align - 1) / align * align;
+}
+
+static int pool_alloc(b200_ctx* c, size_t bytes, CUdeviceptr* out) {
+  const size_t sz = pool_round(bytes);
+  auto it = c->free_lists.find(sz);
+  if (it != c->free_lists.end() && !it->second.empty()) {
+    *out = it->second.back();
+    it->second.pop_back();
+    c->blocks[*out].in_use = true;
+    c->bytes_in_use += sz;
+    return B200_OK;
+  }
+  CUdeviceptr p = 0;
+  CUresult r = g_drv.cuMemAlloc_p(&p, sz);
+  if (r == CUDA_ERROR_OUT_OF_MEMORY) {
+    // release cached pages and retry once (memory_cleanup semantics)
+    for (auto& fl : c->free_lists) {
+      for (CUdeviceptr q : fl.second) { g_drv.cuMemFree_p(q); c->bytes_reserved -= fl.first; c->blocks.erase(q); }
+      fl.second.clear();
+    }
+    r = g_drv.cuMemAlloc_p(&p, sz);
+  }
+  if (r != CUDA_SUCCESS) return fail(map_cu(r), "cuMemAlloc(%zu bytes) failed: %s", sz, cu_err(r));
+  c->blocks[p] = PoolBlock{sz, true};
+  c->bytes_reserved += sz;
+  c->bytes_in_use += sz;
+  *out = p;
+  return B200_OK;
+}
+
+static int pool_free(b200_ctx* c, CUdeviceptr p) {
+  auto it = c->blocks.find(p);
+  if (it == c->blocks.end() || !it->second.in_use) return fail(B200_ERR_INVALID_ARG, "b200_free: pointer not owned by this context");
+  it->second.in_use = false;
+  c->bytes_in_use -= it->second.size;
+  c->free_lists[it->second.size].push_back(p);
+  return B200_OK;
+}
+
+extern "C" int b200_alloc(b200_ctx* c, size_t bytes, b200_dptr* out) {
+  CTX_ENTER(c);
+  if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
+  CUdeviceptr p;
+  int rc = pool_alloc(c, bytes, &p);
+  if (rc) return rc;
+  *out = static_cast<b200_dptr>(p);
+  return B200_OK;
+}
+
+extern "C" int b200_free(b200_ctx* c, b200_dptr ptr) {
+  CTX_ENTER(c);
+  return pool_free(c, static_cast<CUdeviceptr>(ptr));
+}
+
+extern "C" int b200_memory_usage(b200_ctx* c, uint64_t* in_use, uint64_t* reserved) {
+  if (!c) return fail(B200_ERR_INVALID_ARG, "null context");
+  if (in_use) *in_use = c->bytes_in_use;
+  if (reserved) *reserved = c->bytes_reserved;
+  return B200_OK;
+}
+
+extern "C" int b200_memory_cleanup(b200_ctx* c) {
+  CTX_ENTER(c);
+  CU_CHECK(g_drv.cuCtxSynchronize_p());
+  for (auto& fl : c->free_lists) {
+    for (CUdeviceptr q : fl.second) { g_drv.cuMemFree_p(q); c->bytes_reserved -= fl.first; c->blocks.erase(q); }
+    fl.second.clear();
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_host_alloc(b200_ctx* c, size_t bytes, void** out) {
+  CTX_ENTER(c);
+  if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
+  void* p = nullptr;
+  CU_CHECK(g_drv.cuMemAllocHost_p(&p, bytes ? bytes : 1));
+  c->pinned[p] = bytes;
+  *out = p;
+  return B200_OK;
+}
+
+extern "C" int b200_host_free(b200_ctx* c, void* ptr) {
+  CTX_ENTER(c);
+  auto it = c->pinned.find(ptr);
+  if (it == c->pinned.end()) return fail(B200_ERR_INVALID_ARG, "b200_host_free: pointer not owned by this context");
+  CU_CHECK(g_drv.cuMemFreeHost_p(ptr));
+  c->pinned.erase(it);
+  return B200_OK;
+}
+
+extern "C" int b200_write(b200_ctx* c, b200_stream s, b200_dptr dst, const void* src, size_t bytes) {
+  CTX_ENTER(c);
+  if (bytes == 0) return B200_OK;
+  CU_CHECK(g_drv.cuMemcpyHtoDAsync_p(static_cast<CUdeviceptr>(dst), src, bytes, resolve_stream(c, s)));
+  return B200_OK;
+}
+
+extern "C" int b200_read(b200_ctx* c, b200_stream s, void* dst, b200_dptr src, size_t bytes) {
+  CTX_ENTER(c);
+  if (bytes == 0) return B200_OK;
+  CU_CHECK(g_drv.cuMemcpyDtoHAsync_p(dst, static_cast<CUdeviceptr>(src), bytes, resolve_stream(c, s)));
+  return B200_OK;
+}
+
+extern "C" int b200_copy(b200_ctx* c, b200_stream s, b200_dptr dst, b200_dptr src, size_t bytes) {
+  CTX_ENTER(c);
+  if (bytes == 0) return B200_OK;
+  CU_CHECK(g_drv.cuMemcpyDtoDAsync_p(static_cast<CUdeviceptr>(dst), static_cast<CUdeviceptr>(src), bytes, resolve_stream(c, s)));
+  return B200_OK;
+}
+
+extern "C" int b200_memset32(b200_ctx* c, b200_stream s, b200_dptr dst, uint32_t value, size_t words) {
+  CTX_ENTER(c);
+  if (words == 0) return B200_OK;
+  CU_CHECK(g_drv.cuMemsetD32Async_p(static_cast<CUdeviceptr>(dst), value, words, resolve_stream(c, s)));
+  return B200_OK;
+}
+
+// ================================================================================================ streams / events
+extern "C" int b200_stream_create(b200_ctx* c, b200_stream* out) {
+  CTX_ENTER(c);
+  if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
+  CUstream s;
+  CU_CHECK(g_drv.cuStreamCreate_p(&s, CU_STREAM_NON_BLOCKING));
+  *out = s;
+  return B200_OK;
+}
+
+extern "C" int b200_stream_destroy(b200_ctx* c, b200_stream s) {
+  CTX_ENTER(c);
+  if (!s) return B200_OK;
+  auto it = c->reduce_ws.find(static_cast<CUstream>(s));
+  if (it != c->reduce_ws.end()) { g_drv.cuMemFree_p(it->second); c->reduce_ws.erase(it); }
+  CU_CHECK(g_drv.cuStreamDestroy_p(static_cast<CUstream>(s)));
+  return B200_OK;
+}
+
+extern "C" int b200_sync(b200_ctx* c, b200_stream s) {
+  CTX_ENTER(c);
+  CUresult r = g_drv.cuStreamSynchronize_p(resolve_stream(c, s));
+  if (r != CUDA_SUCCESS) return fail(B200_ERR_UNHEALTHY, "stream sync surfaced a device fault: %s (%d)", cu_err(r), (int)r);
+  return B200_OK;
+}
+
+extern "C" int b200_event_create(b200_ctx* c, b200_event* out) {
+  CTX_ENTER(c);
+  if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
+  CUevent e;
+  CU_CHECK(g_drv.cuEventCreate_p(&e, CU_EVENT_DEFAULT));
+  *out = e;
+  return B200_OK;
+}
+
+extern "C" int b200_event_record(b200_ctx* c, b200_event e, b200_stream s) {
+  CTX_ENTER(c);
+  CU_CHECK(g_drv.cuEventRecord_p(static_cast<CUevent>(e), resolve_stream(c, s)));
+  return B200_OK;
+}
+
+extern "C" int b200_event_elapsed_ms(b200_ctx* c, b200_event a, b200_event b, float* ms) {
+  CTX_ENTER(c);
+  if (!ms) return fail(B200_ERR_INVALID_ARG, "null ms");
+  CU_CHECK(g_drv.cuEventSynchronize_p(static_cast<CUevent>(b)));
+  CU_CHECK(g_drv.cuEventElapsedTime_p(ms, static_cast<CUevent>(a), static_cast<CUevent>(b)));
+  return B200_OK;
+}
+
+extern "C" int b200_event_destroy(b200_ctx* c, b200_event e) {
+  CTX_ENTER(c);
+  if (e) CU_CHECK(g_drv.cuEventDestroy_p(static_cast<CUevent>(e)));
+  return B200_OK;
+}
+
+// ================================================================================================ launch helper
+static int launch(b200_ctx* c, CUfunction f, unsigned grid_x, unsigned grid_y, unsigned grid_z, unsigned block,
+                  unsigned smem, unsigned cluster_x, CUstream st, void** args) {
+  CUlaunchConfig cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDimX = grid_x; cfg.gridDimY = grid_y; cfg.gridDimZ = grid_z;
+  cfg.blockDimX = block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+  cfg.sharedMemBytes = smem;
+  cfg.hStream = st;
+  CUlaunchAttribute at[1];
+  if (cluster_x > 1) {
+    at[0].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+    at[0].value.clusterDim.x = cluster_x; at[0].value.clusterDim.y = 1; at[0].value.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  CUresult r = g_drv.cuLaunchKernelEx_p(&cfg, f, args, nullptr);
+  if (r != CUDA_SUCCESS) return fail(map_cu(r), "cuLaunchKernelEx failed: %s (%d)", cu_err(r), (int)r);
+  c->launches++;
+  return B200_OK;
+}
+
+static size_t dtype_size(int dt) {
+  switch (dt) {
+    case B200_F32: case B200_U32: case B200_I32: return 4;
+    case B200_F16: case B200_BF16: return 2;
+    case B200_F64: case B200_I64: case B200_U64: return 8;
+    case B200_U8: case B200_I8: return 1;
+    default: return 0;
+  }
+}
+
+// ================================================================================================ matmul
+struct GemmVariant {
+  const char* tag;  // suffix in the kernel name
+  int cg, block_n, stages;
+};
+static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6}, {"2sm_n128", 2, 128, 8}, {"1sm_n128", 1, 128, 6}};
+
+static unsigned gemm_smem_bytes(const GemmVariant& v) { return v.stages * (16384 + (v.block_n / v.cg) * 128) + 1024 + 256; }
+
+static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, size_t esz, uint64_t base, uint64_t d0,
+                       uint64_t d1, uint64_t d2, uint64_t s1_elems, uint64_t s2_elems, uint32_t b0, uint32_t b1) {
+  char key[256];
+  snprintf(key, sizeof(key), "%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u", (int)dt, (unsigned long long)base,
+           (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_elems,
+           (unsigned long long)s2_elems, b0, b1);
+  auto it = c->tmap_cache.find(key);
+  if (it != c->tmap_cache.end()) { *out = it->second; return B200_OK; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_elems * esz, s2_elems * esz};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, dt, 3, reinterpret_cast<void*>(base), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200_ERR_INVALID_ARG, "cuTensorMapEncodeTiled failed: %s (dims %llu,%llu,%llu strides %llu,%llu box %u,%u)",
+                cu_err(r), (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                (unsigned long long)strides[0], (unsigned long long)strides[1], b0, b1);
+  if (c->tmap_cache.size() > 512) c->tmap_cache.clear();
+  c->tmap_cache[key] = *out;
+  return B200_OK;
+}
+
+// One batched problem with LINEAR batch strides (0 = broadcast).  Strides in elements.
+struct GemmProblem {
+  int in_dtype, out_dtype;
+  uint64_t a, b, out;
+  uint64_t M, N, K, batch;
+  uint64_t a_sm, a_sk, a_sb;
+  uint64_t b_sk, b_sn, b_sb;
+  uint64_t o_sm, o_sn, o_sb;
+};
+
+static int launch_simt(b200_ctx* c, CUstream st, const GemmProblem& g) {
+  CUfunction f;
+  int rc = get_func(c, "gemm_simt_strided", &f);
+  if (rc) return rc;
+  if (g.batch > 65535) return fail(B200_ERR_UNSUPPORTED, "simt matmul: batch %llu > 65535", (unsigned long long)g.batch);
+  SimtGemmParams p{g.a, g.b, g.out, g.a_sb, g.a_sm, g.a_sk, g.b_sb, g.b_sk, g.b_sn, g.o_sb, g.o_sm, g.o_sn,
+                   (uint32_t)g.M, (uint32_t)g.N, (uint32_t)g.K, (uint32_t)g.batch, (uint32_t)g.in_dtype, (uint32_t)g.out_dtype};
+  void* args[] = {&p};
+  return launch(c, f, (unsigned)((g.N + 15) / 16), (unsigned)((g.M + 15) / 16), (unsigned)g.batch, 256, 0, 1, st, args);
+}
+
+static bool tma_ok(const GemmProblem& g, bool* b_mn) {
+  const size_t esz = dtype_size(g.in_dtype);
+  auto al16 = [&](uint64_t elems) { return (elems * esz) % 16 == 0; };
+  if (g.M >= (1ull << 31) || g.N >= (1ull << 31) || g.K >= (1ull << 31) || g.batch >= (1ull << 31)) return false;
+  // lhs must be K-major
+  if (!(g.a_sk == 1 || g.K == 1)) return false;
+  if (g.a % 16 || !al16(g.a_sb)) return false;
+  if (g.M > 1 && (!al16(g.a_sm) || g.a_sm < g.K)) return false;
+  if (g.b % 16 || !al16(g.b_sb)) return false;
+  if ((g.b_sk == 1 || g.K == 1) && (g.N == 1 || (al16(g.b_sn) && g.b_sn >= g.K))) { *b_mn = false; }
+  else if ((g.b_sn == 1 || g.N == 1) && (g.K == 1 || (al16(g.b_sk) && g.b_sk >= g.N))) { *b_mn = true; }
+  else return false;
+  // a dimension of extent 1 still needs a 16-byte-multiple stride in the descriptor; encode_tmap substitutes one
+  if (!(g.o_sn == 1 || g.N == 1)) return false;
+  // TMA stride limit 2^40 bytes
+  if (g.a_sm * esz >= (1ull << 40) || g.a_sb * esz >= (1ull << 40) || g.b_sb * esz >= (1ull << 40)) return false;
+  return true;
+}
+
+static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool b_mn) {
+  const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
+  const char* in_tag = g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : "tf32";
+  const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : "f32";
+  const uint32_t block_k = static_cast<uint32_t>(128 / esz);
+
+  // pick the tile variant by padded work per wave (ties -> larger tile, less L2 traffic)
+  const std::string forced = opt(c, "gemm.variant", "auto");
+  const GemmVariant* best = nullptr;
+  double best_cost = 0;
+  for (const GemmVariant& v : kVariants) {
+    if (forced != "auto" && forced != v.tag) continue;
+    const uint64_t tm = (g.M + 128 * v.cg - 1) / (128 * v.cg), tn = (g.N + v.block_n - 1) / v.block_n;
+    const uint64_t tiles = tm * tn * g.batch;
+    const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
+    const uint64_t waves = (tiles + clusters - 1) / clusters;
+    const double cost = static_cast<double>(waves) * (128.0 * v.block_n);  // per-SM MMA work per wave
+    if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; }
+  }
+  if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant", forced.c_str());
+  const GemmVariant& v = *best;
+
+  const std::string name = std::string("gemm_") + in_tag + "_" + out_tag + "_" + v.tag + (b_mn ? "_bn" : "_bk");
+  CUfunction f;
+  int rc = get_func(c, name, &f);
+  if (rc) return rc;
+  const unsigned smem = gemm_smem_bytes(v);
+  CU_CHECK(g_drv.cuFuncSetAttribute_p(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+
+  const CUtensorMapDataType dt = g.in_dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : g.in_dtype == B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const bool a_bcast = (g.a_sb == 0 || g.batch == 1), b_bcast = (g.b_sb == 0 || g.batch == 1);
+  CUtensorMap ta, tb;
+  auto pad16 = [&](uint64_t elems) { const uint64_t q = 16 / esz; return (elems + q - 1) / q * q; };
+  const uint64_t a_sm = g.M > 1 ? g.a_sm : pad16(g.K);
+  rc = encode_tmap(c, &ta, dt, esz, g.a, g.K, g.M, a_bcast ? 1 : g.batch, a_sm, a_bcast ? a_sm * g.M : g.a_sb, block_k, 128);
+  if (rc) return rc;
+  const uint32_t n_local = v.block_n / v.cg;
+  if (!b_mn) {
+    const uint64_t b_sn = g.N > 1 ? g.b_sn : pad16(g.K);
+    rc = encode_tmap(c, &tb, dt, esz, g.b, g.K, g.N, b_bcast ? 1 : g.batch, b_sn, b_bcast ? b_sn * g.N : g.b_sb, block_k, n_local);
+  } else {
+    const uint64_t b_sk = g.K > 1 ? g.b_sk : pad16(g.N);
+    rc = encode_tmap(c, &tb, dt, esz, g.b, g.N, g.K, b_bcast ? 1 : g.batch, b_sk, b_bcast ? b_sk * g.K : g.b_sb,
+                     static_cast<uint32_t>(128 / esz), block_k);
+  }
+  if (rc) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = g.out;
+  p.out_row_stride = g.o_sm;
+  p.out_batch_stride = g.o_sb;
+  p.M = (uint32_t)g.M; p.N = (uint32_t)g.N; p.K = (uint32_t)g.K; p.batch = (uint32_t)g.batch;
+  p.tiles_m = (uint32_t)((g.M + 128 * v.cg - 1) / (128 * v.cg));
+  p.tiles_n = (uint32_t)((g.N + v.block_n - 1) / v.block_n);
+  p.group_m = (uint32_t)std::max(1, atoi(opt(c, "gemm.group_m", "8").c_str()));
+  p.a_bmul = a_bcast ? 0 : 1;
+  p.b_bmul = b_bcast ? 0 : 1;
+  p.vec_store = (g.out % 16 == 0 && (g.o_sm * osz) % 16 == 0 && (g.o_sb * osz) % 16 == 0) ? 1 : 0;
+
+  const uint64_t total_tiles = static_cast<uint64_t>(p.tiles_m) * p.tiles_n * p.batch;
+  if (total_tiles >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "too many tiles");
+  const unsigned clusters = (unsigned)std::min<uint64_t>(total_tiles, std::max(1, c->props.num_sms / v.cg));
+  void* args[] = {&ta, &tb, &p};
+  return launch(c, f, clusters * v.cg, 1, 1, 256, smem, v.cg, st, args);
+}
+
+static int launch_split(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uint64_t batch, uint64_t rows, uint64_t cols,
+                        uint64_t in_bs, uint64_t in_rs, uint32_t mode) {
+  CUfunction f;
+  int rc = get_func(c, "split_tf32", &f);
+  if (rc) return rc;
+  SplitParams p{in, out, batch, rows, cols, in_bs, in_rs, mode, 0};
+  const uint64_t total = batch * rows * cols;
+  const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->props.num_sms * 16);
+  void* args[] = {&p};
+  return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
+}
+
+static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
+  if (g.M == 0 || g.N == 0 || g.batch == 0) return B200_OK;
+  const std::string forced = opt(c, "gemm.variant", "auto");
+  bool b_mn = false;
+  const bool tma = g.K > 0 && tma_ok(g, &b_mn);
+  if (forced == "simt" || !tma) {
+    if (forced != "simt" && forced != "auto")
+      return fail(B200_ERR_UNSUPPORTED, "gemm.variant=%s forced but operands are not TMA-describable", forced.c_str());
+    return launch_simt(c, st, g);
+  }
+  if (g.in_dtype == B200_F32 && opt(c, "gemm.f32", "3xtf32") == "3xtf32") {
+    // split both operands into tf32 hi/lo along K and run one tf32 GEMM with K' = 3K
+    const uint64_t ab = (g.a_sb == 0) ? 1 : g.batch, bb = (g.b_sb == 0) ? 1 : g.batch;
+    CUdeviceptr a3 = 0, b3 = 0;
+    int rc = pool_alloc(c, ab * g.M * 3 * g.K * 4, &a3);
+    if (rc) return rc;
+    rc = pool_alloc(c, bb * g.N * 3 * g.K * 4, &b3);
+    if (rc) { pool_free(c, a3); return rc; }
+    rc = launch_split(c, st, g.a, a3, ab, g.M, g.K, g.a_sb, g.a_sm, 0);
+    if (!rc) {
+      if (!b_mn) rc = launch_split(c, st, g.b, b3, bb, g.N, g.K, g.b_sb, g.b_sn, 1);
+      else rc = launch_split(c, st, g.b, b3, bb, g.K, g.N, g.b_sb, g.b_sk, 2);
+    }
+    if (!rc) {
+      GemmProblem h = g;
+      h.a = a3; h.K = 3 * g.K; h.a_sm = 3 * g.K; h.a_sk = 1; h.a_sb = (g.a_sb == 0) ? 0 : g.M * 3 * g.K;
+      h.b = b3;
+      if (!b_mn) { h.b_sk = 1; h.b_sn = 3 * g.K; } else { h.b_sk = g.N; h.b_sn = 1; }
+      h.b_sb = (g.b_sb == 0) ? 0 : g.N * 3 * g.K;
+      rc = launch_tcgen05(c, st, h, b_mn);
+    }
+    // stream-ordered reuse: the pool hands these pages out again only to later work on this context
+    pool_free(c, a3);
+    pool_free(c, b3);
+    return rc;
+  }
+  return launch_tcgen05(c, st, g, b_mn);
+}
+
+// Collapse batch dims [0, nb) of one operand into a linear stride; false if the offsets are not linear in the flat index.
+static bool linear_batch(int nb, const uint64_t* out_shape, const uint64_t* shape, const uint64_t* strides, uint64_t* flat) {
+  uint64_t inner_stride = 0, inner_extent = 1;
+  bool have = false;
+  for (int i = nb - 1; i >= 0; --i) {
+    if (out_shape[i] == 1) continue;
+    const uint64_t st = (shape[i] == 1) ? 0 : strides[i];
+    if (!have) { inner_stride = st; inner_extent = out_shape[i]; have = true; *flat = st; continue; }
+    if (st != inner_stride * inner_extent) return false;
+    inner_extent *= out_shape[i];
+  }
+  if (!have) *flat = 0;
+  return true;
+}
+
+static int matmul_rec(b200_ctx* c, CUstream st, GemmProblem g, int nb, const uint64_t* ob, const uint64_t* ls,
+                      const uint64_t* lst, const uint64_t* rs, const uint64_t* rst, const uint64_t* ost) {
+  uint64_t fa = 0, fb = 0, fo = 0;
+  if (linear_batch(nb, ob, ls, lst, &fa) && linear_batch(nb, ob, rs, rst, &fb) && linear_batch(nb, ob, ob, ost, &fo)) {
+    uint64_t batch = 1;
+    for (int i = 0; i < nb; ++i) batch *= ob[i];
+    g.batch = batch; g.a_sb = fa; g.b_sb = fb; g.o_sb = fo;
+    if (batch == 1) { g.a_sb = g.b_sb = 0; g.o_sb = 0; }
+    return run_gemm(c, st, g);
+  }
+  // peel the outermost non-unit batch dim and recurse
+  int d = 0;
+  while (d < nb && ob[d] == 1) ++d;
+  const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
+  for (uint64_t i = 0; i < ob[d]; ++i) {
+    GemmProblem h = g;
+    h.a += (ls[d] == 1 ? 0 : i * lst[d]) * esz;
+    h.b += (rs[d] == 1 ? 0 : i * rst[d]) * esz;
+    h.out += i * ost[d] * osz;
+    int rc = matmul_rec(c, st, h, nb - d - 1, ob + d + 1, ls + d + 1, lst + d + 1, rs + d + 1, rst + d + 1, ost + d + 1);
+    if (rc) return rc;
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_matmul(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
+                           b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                           const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
+                           const uint64_t* strides_out) {
+  CTX_ENTER(c);
+  if (rank < 2 || rank > 8) return fail(B200_ERR_INVALID_ARG, "matmul: rank %d unsupported (need 2..8)", rank);
+  if (!shape_lhs || !strides_lhs || !shape_rhs || !strides_rhs || !shape_out || !strides_out)
+    return fail(B200_ERR_INVALID_ARG, "matmul: null shape/stride array");
+  if (in_dtype != B200_F32 && in_dtype != B200_F16 && in_dtype != B200_BF16)
+    return fail(B200_ERR_UNSUPPORTED, "matmul: input dtype %d unsupported (f32, f16, bf16)", (int)in_dtype);
+  if (out_dtype != in_dtype && out_dtype != B200_F32)
+    return fail(B200_ERR_UNSUPPORTED, "matmul: output dtype must equal the input dtype or be f32");
+  const int nb = rank - 2;
+  const uint64_t M = shape_lhs[rank - 2], K = shape_lhs[rank - 1], K2 = shape_rhs[rank - 2], N = shape_rhs[rank - 1];
+  // shape.rs:489-517: inner dims must agree, batch dims broadcast 1 vs d
+  if (K != K2) return fail(B200_ERR_INVALID_ARG, "matmul: inner dimensions differ (lhs k=%llu, rhs k=%llu)", (unsigned long long)K, (unsigned long long)K2);
+  if (shape_out[rank - 2] != M || shape_out[rank - 1] != N)
+    return fail(B200_ERR_INVALID_ARG, "matmul: output is [%llu,%llu], expected [%llu,%llu]", (unsigned long long)shape_out[rank - 2],
+                (unsigned long long)shape_out[rank - 1], (unsigned long long)M, (unsigned long long)N);
+  for (int i = 0; i < nb; ++i) {
+    const uint64_t l = shape_lhs[i], r = shape_rhs[i], o = shape_out[i];
+    const uint64_t expect = l == r ? l : (l == 1 ? r : (r == 1 ? l : 0));
+    if (expect == 0 && !(l == 0 && r == 0)) return fail(B200_ERR_INVALID_ARG, "matmul: batch dim %d cannot broadcast (%llu vs %llu)", i, (unsigned long long)l, (unsigned long long)r);
+    if (o != expect) return fail(B200_ERR_INVALID_ARG, "matmul: output batch dim %d is %llu, expected %llu", i, (unsigned long long)o, (unsigned long long)expect);
+  }
+  if (!lhs || !rhs || !out) {
+    uint64_t n = M * N;
+    for (int i = 0; i < nb; ++i) n *= shape_out[i];
+    if (n == 0) return B200_OK;
+    return fail(B200_ERR_INVALID_ARG, "matmul: null device pointer");
+  }
+  CUstream st = resolve_stream(c, s);
+  GemmProblem g{};
+  g.in_dtype = in_dtype; g.out_dtype = out_dtype;
+  g.a = lhs; g.b = rhs; g.out = out;
+  g.M = M; g.N = N; g.K = K; g.batch = 1;
+  g.a_sm = strides_lhs[rank - 2]; g.a_sk = strides_lhs[rank - 1];
+  g.b_sk = strides_rhs[rank - 2]; g.b_sn = strides_rhs[rank - 1];
+  g.o_sm = strides_out[rank - 2]; g.o_sn = strides_out[rank - 1];
+  for (int i = 0; i < nb; ++i)
+    if (shape_out[i] == 0) return B200_OK;
+  return matmul_rec(c, st, g, nb, shape_out, shape_lhs, strides_lhs, shape_rhs, strides_rhs, strides_out);
+}
+
+// ================================================================================================ reduce
+static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out) {
+  auto it = c->reduce_ws.find(st);
+  if (it != c->reduce_ws.end()) { *out = it->second; return B200_OK; }
+  CUdeviceptr p;
+  CUresult r = g_drv.cuMemAlloc_p(&p, kWsBytes);
+  if (r != CUDA_SUCCESS) return fail(map_cu(r), "reduce workspace allocation failed: %s", cu_err(r));
+  r = g_drv.cuMemsetD32Async_p(p, 0, kWsBytes / 4, st);  // ticket starts at 0; kernels reset it themselves
+  if (r != CUDA_SUCCESS) { g_drv.cuMemFree_p(p); return fail(map_cu(r), "reduce workspace memset failed: %s", cu_err(r)); }
+  c->reduce_ws[st] = p;
+  *out = p;
+  return B200_OK;
+}
+
+static const char* op_tag(int op) {
+  switch (op) {
+    case B200_REDUCE_SUM: case B200_REDUCE_MEAN: return "sum";
+    case B200_REDUCE_PROD: return "prod";
+    case B200_REDUCE_MAX: return "max";
+    case B200_REDUCE_MIN: return "min";
+    case B200_REDUCE_ARGMAX: return "argmax";
+    case B200_REDUCE_ARGMIN: return "argmin";
+    default: return nullptr;
+  }
+}
+static const char* dt_tag(int dt) { return dt == B200_F32 ? "f32" : dt == B200_F16 ? "f16" : dt == B200_BF16 ? "bf16" : nullptr; }
+
+static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, uint64_t in, uint64_t out, uint64_t n, float scale) {
+  std::string name = std::string("reduce_all_") + op_tag(op) + "_" + dt_tag(dt);
+  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
+  unsigned threads = 512, bps = 2;
+  if (!arg && op_tag(op) == std::string("sum") && dt == B200_F32) {
+    const std::string v = opt(c, "reduce.variant", "auto");
+    if (v != "auto" && v != "u8") name += "_" + v;
+  }
+  threads = (unsigned)std::min(512, std::max(32, atoi(opt(c, "reduce.threads", "512").c_str())));
+  threads = threads / 32 * 32;
+  bps = (unsigned)std::max(1, atoi(opt(c, "reduce.blocks_per_sm", "2").c_str()));
+  CUfunction f;
+  int rc = get_func(c, name, &f);
+  if (rc) return rc;
+  CUdeviceptr ws;
+  rc = reduce_workspace(c, st, &ws);
+  if (rc) return rc;
+  const uint64_t vec = 16 / dtype_size(dt);
+  uint64_t want = (n / vec + threads - 1) / threads;  // blocks that still get >= 1 vector per thread
+  unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)c->props.num_sms * bps, kWsMaxBlocks)));
+  ReduceParams p{in, out, ws, 1, n, 1, scale, 0};
+  void* args[] = {&p};
+  return launch(c, f, grid, 1, 1, threads, 0, 1, st, args);
+}
+
+static int launch_reduce_rows(b200_ctx* c, CUstream st, int op, int dt, uint64_t in, uint64_t out, uint64_t outer, uint64_t len, float scale) {
+  const std::string name = std::string("reduce_rows_") + op_tag(op) + "_" + dt_tag(dt);
+  CUfunction f;
+  int rc = get_func(c, name, &f);
+  if (rc) return rc;
+  const uint64_t vec = 16 / dtype_size(dt);
+  // threads per row: ~4 vectors per thread, power of two, 1..512
+  uint64_t tpr = 1;
+  while (tpr < 512 && tpr * vec * 4 < len) tpr <<= 1;
+  int tpr_log2 = 0;
+  while ((1ull << tpr_log2) < tpr) ++tpr_log2;
+  const unsigned threads = tpr > 32 ? (unsigned)tpr : 256;
+  const uint64_t rows_per_block = threads >> tpr_log2;
+  const uint64_t blocks = (outer + rows_per_block - 1) / rows_per_block;
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)c->props.num_sms * 16));
+  ReduceParams p{in, out, 0, outer, len, 1, scale, 0};
+  void* args[] = {&p, &tpr_log2};
+  return launch(c, f, grid, 1, 1, threads, 0, 1, st, args);
+}
+
+static int launch_reduce_cols(b200_ctx* c, CUstream st, int op, int dt, uint64_t in, uint64_t out, uint64_t outer, uint64_t len, uint64_t inner, float scale) {
+  const std::string name = std::string("reduce_cols_") + op_tag(op) + "_" + dt_tag(dt);
+  CUfunction f;
+  int rc = get_func(c, name, &f);
+  if (rc) return rc;
+  const uint64_t total = outer * inner;
+  const unsigned threads = 256;
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total + threads - 1) / threads, (uint64_t)c->props.num_sms * 16));
+  ReduceParams p{in, out, 0, outer, len, inner, scale, 0};
+  void* args[] = {&p};
+  return launch(c, f, grid, 1, 1, threads, 0, 1, st, args);
+}
+
+extern "C" int b200_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
+                           int rank, const uint64_t* shape, int axis) {
+  CTX_ENTER(c);
+  if (!op_tag(op)) return fail(B200_ERR_INVALID_ARG, "reduce: unknown op %d", (int)op);
+  if (!dt_tag(in_dtype)) return fail(B200_ERR_UNSUPPORTED, "reduce: input dtype %d unsupported (f32, f16, bf16)", (int)in_dtype);
+  if (rank < 1 || rank > 8 || !shape) return fail(B200_ERR_INVALID_ARG, "reduce: bad rank/shape");
+  if (axis < -1 || axis >= rank) return fail(B200_ERR_INVALID_ARG, "reduce: axis %d out of range for rank %d", axis, rank);
+  uint64_t outer = 1, len = 1, inner = 1;
+  if (axis == -1) {
+    for (int i = 0; i < rank; ++i) len *= shape[i];
+  } else {
+    for (int i = 0; i < axis; ++i) outer *= shape[i];
+    len = shape[axis];
+    for (int i = axis + 1; i < rank; ++i) inner *= shape[i];
+  }
+  if (outer * inner == 0) return B200_OK;  // empty output
+  if (len == 0) return fail(B200_ERR_INVALID_ARG, "reduce: reduced extent is 0 (identity-filled outputs are not defined by the reference)");
+  if (!in || !out) return fail(B200_ERR_INVALID_ARG, "reduce: null device pointer");
+  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
+  if (arg && len >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "arg-reduce: axis extent %llu does not fit u32 indices", (unsigned long long)len);
+  const float scale = (op == B200_REDUCE_MEAN) ? static_cast<float>(1.0 / static_cast<double>(len)) : 1.0f;
+  CUstream st = resolve_stream(c, s);
+  const uint64_t sms = c->props.num_sms;
+  const size_t esz = dtype_size(in_dtype);
+
+  if (outer == 1 && inner == 1) return launch_reduce_all(c, st, op, in_dtype, in, out, len, scale);
+
+  if (inner == 1) {
+    // few long rows: split every row into S segments, reduce [outer*S, len/S] to f32 partials, then reduce [outer, S]
+    if (!arg && outer < 2 * sms && len >= (1u << 16)) {
+      uint64_t S = 1;
+      while (outer * S < 4 * sms && len % (S * 2) == 0 && len / (S * 2) >= 4096 && ((len / (S * 2)) * esz) % 16 == 0) S *= 2;
+      if (S > 1) {
+        CUdeviceptr tmp;
+        int rc = pool_alloc(c, outer * S * 4, &tmp);
+        if (rc) return rc;
+        rc = launch_reduce_rows(c, st, op, in_dtype, in, tmp, outer * S, len / S, 1.0f);
+        if (!rc) rc = launch_reduce_rows(c, st, op, B200_F32, tmp, out, outer, S, scale);
+        pool_free(c, tmp);
+        return rc;
+      }
+    }
+    return launch_reduce_rows(c, st, op, in_dtype, in, out, outer, len, scale);
+  }
+
+  // inner > 1: few outputs but a long axis -> split the axis the same way
+  if (!arg && outer * inner < sms * 256 && len >= 64) {
+    uint64_t S = 1;
+    while (outer * S * inner < sms * 1024 && len % (S * 2) == 0 && len / (S * 2) >= 16) S *= 2;
+    if (S > 1) {
+      CUdeviceptr tmp;
+      int rc = pool_alloc(c, outer * S * inner * 4, &tmp);
+      if (rc) return rc;
+      rc = launch_reduce_cols(c, st, op, in_dtype, in, tmp, outer * S, len / S, inner, 1.0f);
+      if (!rc) rc = launch_reduce_cols(c, st, op, B200_F32, tmp, out, outer, S, inner, scale);
+      pool_free(c, tmp);
+      return rc;
+    }
+  }
+  return launch_reduce_cols(c, st, op, in_dtype, in, out, outer, len, inner, scale);
+}
+
+// ================================================================================================ collectives
+extern "C" int b200_comm_get_unique_id(b200_ctx* c, void* id128) {
+  CTX_ENTER(c);
+  if (!id128) return fail(B200_ERR_INVALID_ARG, "null id");
+  int rc = ensure_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NCCL_CHECK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return B200_OK;
+}
+
+static std::vector<int> sorted_ids(const int* ids, int n) {
+  std::vector<int> v(ids, ids + n);
+  std::sort(v.begin(), v.end());
+  return v;
+}
+
+extern "C" int b200_comm_init(b200_ctx* c, const int* device_ids, int n, const void* id128) {
+  CTX_ENTER(c);
+  if (!device_ids || n < 1 || !id128) return fail(B200_ERR_INVALID_ARG, "comm_init: bad arguments");
+  int rc = ensure_nccl();
+  if (rc) return rc;
+  std::vector<int> key = sorted_ids(device_ids, n);
+  if (c->comms.count(key)) return B200_OK;  // idempotent, like ensure_init_collective (client.rs:755-767)
+  auto it = std::find(key.begin(), key.end(), c->device);
+  if (it == key.end()) return fail(B200_ERR_INVALID_ARG, "comm_init: device %d is not in the device set", c->device);
+  CommState cs;
+  cs.rank = static_cast<int>(it - key.begin());
+  cs.n = n;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_CHECK(g_nccl.CommInitRank(&cs.comm, n, id, cs.rank));
+  c->comms[key] = cs;
+  return B200_OK;
+}
+
+extern "C" int b200_all_reduce(b200_ctx* c, b200_stream compute, b200_dptr src, b200_dptr dst, size_t bytes, b200_dtype dtype,
+                               b200_comm_op op, const int* device_ids, int n) {
+  CTX_ENTER(c);
+  if (!device_ids || n < 1) return fail(B200_ERR_INVALID_ARG, "all_reduce: bad device set");
+  int rc = ensure_nccl();
+  if (rc) return rc;
+  auto it = c->comms.find(sorted_ids(device_ids, n));
+  if (it == c->comms.end()) return fail(B200_ERR_COMM, "all_reduce: no communicator for this device set (call b200_comm_init)");
+  int nt;
+  switch (dtype) {  // communication.rs:34-108
+    case B200_F32: nt = ncclFloat32; break;
+    case B200_F16: nt = ncclFloat16; break;
+    case B200_BF16: nt = ncclBfloat16; break;
+    case B200_F64: nt = ncclFloat64; break;
+    case B200_I32: nt = ncclInt32; break;
+    case B200_U32: nt = ncclUint32; break;
+    case B200_I64: nt = ncclInt64; break;
+    case B200_U64: nt = ncclUint64; break;
+    case B200_I8: nt = ncclInt8; break;
+    case B200_U8: nt = ncclUint8; break;
+    default: return fail(B200_ERR_UNSUPPORTED, "all_reduce: dtype %d", (int)dtype);
+  }
+  const size_t esz = dtype_size(dtype);
+  if (bytes % esz) return fail(B200_ERR_INVALID_ARG, "all_reduce: %zu bytes is not a multiple of the element size", bytes);
+  CUstream cs = resolve_stream(c, compute);
+  // compute -> comm dependency, then the collective on the comm stream (server.rs:749)
+  CU_CHECK(g_drv.cuEventRecord_p(c->comm_event, cs));
+  CU_CHECK(g_drv.cuStreamWaitEvent_p(c->comm_stream, c->comm_event, 0));
+  NCCL_CHECK(g_nccl.AllReduce(reinterpret_cast<const void*>(src), reinterpret_cast<void*>(dst), bytes / esz, nt,
+                              op == B200_COMM_MEAN ? ncclAvg : ncclSum, it->second.comm, c->comm_stream));
+  return B200_OK;
+}
+
+extern "C" int b200_sync_collective(b200_ctx* c, b200_stream compute) {
+  CTX_ENTER(c);
+  CU_CHECK(g_drv.cuEventRecord_p(c->comm_event, c->comm_stream));
+  CU_CHECK(g_drv.cuStreamWaitEvent_p(resolve_stream(c, compute), c->comm_event, 0));
+  return B200_OK;
+}
+
+// ================================================================================================ generators / probes
+static int launch_fill(b200_ctx* c, b200_stream s, int dtype, uint64_t out, uint64_t n, FillParams p) {
+  if (!dt_tag(dtype)) return fail(B200_ERR_UNSUPPORTED, "fill: dtype %d unsupported", dtype);
+  if (n == 0) return B200_OK;
+  CUfunction f;
+  int rc = get_func(c, "fill_kernel", &f);
+  if (rc) return rc;
+  p.out = out; p.n = n; p.dtype = (uint32_t)dtype;
+  const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->props.num_sms * 32);
+  void* args[] = {&p};
+  return launch(c, f, grid, 1, 1, 256, 0, 1, resolve_stream(c, s), args);
+}
+
+extern "C" int b200_fill_uniform(b200_ctx* c, b200_stream s, b200_dtype dtype, b200_dptr out, uint64_t n, uint64_t seed, float lo, float hi) {
+  CTX_ENTER(c);
+  FillParams p{};
+  p.seed = seed; p.lo = lo; p.scale = hi - lo; p.mode = 0; p.modulus = 1;
+  return launch_fill(c, s, dtype, out, n, p);
+}
+
+extern "C" int b200_fill_modulo(b200_ctx* c, b200_stream s, b200_dtype dtype, b200_dptr out, uint64_t n, uint32_t modulus) {
+  CTX_ENTER(c);
+  if (modulus == 0) return fail(B200_ERR_INVALID_ARG, "fill_modulo: modulus 0");
+  FillParams p{};
+  p.mode = 1; p.modulus = modulus;
+  return launch_fill(c, s, dtype, out, n, p);
+}
+
+extern "C" int b200_probe_wmma(b200_ctx* c, b200_stream s, b200_dtype dtype, uint32_t n_iter, b200_dptr scratch, double* ops) {
+  CTX_ENTER(c);
+  CUfunction f;
+  int rc = get_func(c, dtype == B200_BF16 ? "wmma_probe_bf16" : "wmma_probe_f16", &f);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)c->props.num_sms * 32, block = 256;
+  uint64_t sp = scratch;
+  void* args[] = {&sp, &n_iter};
+  rc = launch(c, f, grid, 1, 1, block, 0, 1, resolve_stream(c, s), args);
+  if (!rc && ops) *ops = static_cast<double>(grid) * (block / 32) * 2.0 * 16 * 16 * 16 * n_iter;
+  return rc;
+}
+
+extern "C" int b200_probe_memread(b200_ctx* c, b200_stream s, b200_dptr buf, uint64_t bytes, b200_dptr scratch) {
+  CTX_ENTER(c);
+  CUfunction f;
+  int rc = get_func(c, "memread_probe_vec4", &f);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)c->props.num_sms * 32, block = 256;
+  uint64_t lines = bytes / 16;
+  const uint64_t per_pass = static_cast<uint64_t>(grid) * block;
+  uint32_t steps = (uint32_t)((lines + per_pass - 1) / per_pass);
+  uint64_t in = buf, out = scratch;
+  void* args[] = {&in, &out, &lines, &steps};
+  return launch(c, f, grid, 1, 1, block, 0, 1, resolve_stream(c, s), args);
+}

@@ -1,0 +1,313 @@
+// Hand-written sm_100a GEMM: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators in TMEM) -> tcgen05.ld epilogue.
+// Persistent, warp-specialised (1 TMA producer warp, 1 MMA issuer thread, 4 epilogue warps), optional CTA pair
+// (cta_group::2, UMMA M = 256) and double-buffered TMEM accumulators so the epilogue of tile i overlaps the
+// mainloop of tile i+1.
+//
+// Replaces: the (out-of-tree, cubek) `matmul::launch` kernel bodies that CubeCL lowers to nvcuda::wmma / mma.sync
+// through crates/cubecl-cpp/src/shared/mma.rs:48-174 and crates/cubecl-cpp/src/cuda/ptx/mma.rs:30-61.
+// Semantics follow the reference's CPU expectation `test_simple_cube_expected`
+// (crates/cubecl-core/src/runtime_tests/cmma.rs:695-721): inputs widened to f32, f32 accumulate over increasing k.
+// Shape / batch-broadcast rule: crates/cubecl-zspace/src/shape.rs:489-517 (resolved on the host, see capi.cpp).
+//
+// Compiled to a cubin (no host code here): nvcc -cubin -gencode arch=compute_100a,code=sm_100a
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+using namespace b200;
+
+struct GemmParams {
+  uint64_t out;               // device pointer of out[batch, M, N]
+  uint64_t out_row_stride;    // in elements
+  uint64_t out_batch_stride;  // in elements
+  uint32_t M, N, K, batch;
+  uint32_t tiles_m, tiles_n;  // tile grid per batch; a tile is (128*CG) x BLOCK_N
+  uint32_t group_m;           // rasterisation: tiles are walked in column strips of `group_m` tile-rows (L2 reuse)
+  uint32_t a_bmul, b_bmul;    // 0 = operand broadcast over batch (tensor map has batch extent 1), 1 = batched
+  uint32_t vec_store;         // 1 when every output row start is 16-byte aligned
+};
+
+enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2 };
+enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };
+
+constexpr int kNumThreads = 256;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
+
+template <int OUT>
+__device__ __forceinline__ void store_chunk32(uint64_t row_ptr, uint32_t n0, uint32_t N, bool vec, const uint32_t (&v)[32]) {
+  if constexpr (OUT == OUT_F32) {
+    float* dst = reinterpret_cast<float*>(row_ptr) + n0;
+    if (vec && n0 + 32 <= N) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+        reinterpret_cast<float4*>(dst)[j] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) dst[j] = __uint_as_float(v[j]);
+    }
+  } else {
+    uint16_t* dst = reinterpret_cast<uint16_t*>(row_ptr) + n0;
+    uint32_t packed[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
+      if constexpr (OUT == OUT_BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+      } else {
+        __half2 h = __floats2half2_rn(lo, hi);
+        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+    if (vec && n0 + 32 <= N) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<uint4*>(dst)[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) dst[j] = static_cast<uint16_t>((j & 1) ? (packed[j >> 1] >> 16) : (packed[j >> 1] & 0xFFFFu));
+    }
+  }
+}
+
+struct TileCoord {
+  uint32_t b, m_blk, n_blk;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(uint32_t t, const GemmParams& p) {
+  const uint32_t per_batch = p.tiles_m * p.tiles_n;
+  TileCoord c;
+  c.b = t / per_batch;
+  uint32_t r = t - c.b * per_batch;
+  const uint32_t strip = p.group_m * p.tiles_n;
+  const uint32_t g = r / strip;
+  const uint32_t first_m = g * p.group_m;
+  const uint32_t gsize = min(p.group_m, p.tiles_m - first_m);
+  const uint32_t in = r - g * strip;
+  c.m_blk = first_m + in % gsize;
+  c.n_blk = in / gsize;
+  return c;
+}
+
+template <int CG, int BLOCK_N, bool B_MN, int KIND, int OUT, int STAGES>
+__device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtensorMap* tma_b, const GemmParams& p) {
+  constexpr int ESZ = (KIND == KIND_TF32) ? 4 : 2;
+  constexpr int BLOCK_K = 128 / ESZ;  // one 128-byte swizzle row of K per stage
+  constexpr int UMMA_K = 32 / ESZ;
+  constexpr int UMMA_M = 128 * CG;
+  constexpr int N_LOCAL = BLOCK_N / CG;  // rows of the B tile this CTA stages
+  constexpr uint32_t A_BYTES = 128 * 128;
+  constexpr uint32_t B_BYTES = N_LOCAL * 128;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int CHUNK_N = 128 / ESZ;                 // MN-major B: N elements per 128-byte row
+  constexpr uint32_t CHUNK_BYTES = BLOCK_K * 128;    // MN-major B: one [BLOCK_K x 128 B] chunk
+  constexpr int NUM_CHUNKS = N_LOCAL / CHUNK_N;
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                               : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+  static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024-byte alignment for SWIZZLE_128B");
+  constexpr uint32_t IDESC = make_idesc(KIND, 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  const uint32_t cluster_id = (CG == 2) ? cluster_id_x() : blockIdx.x;
+  const uint32_t n_clusters = (CG == 2) ? num_clusters_x() : gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(tma_a);
+    tma_prefetch_desc(tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // one arrive.expect_tx by the leader's producer; bytes of both CTAs counted
+      mbar_init(empty_bar(s), 1);  // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);         // one tcgen05.commit
+      mbar_init(tempty_bar(a), 4 * CG);   // one elected lane per epilogue warp, both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+    tmem_relinquish<CG>();
+  }
+  tcgen05_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const uint32_t total_tiles = p.batch * p.tiles_m * p.tiles_n;
+  const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (one lane per CTA)
+    if (lane == 0) {
+      const uint32_t leader_full0 = (CG == 2) ? mapa_shared(full_bar(0), 0) : full_bar(0);
+      uint32_t s = 0, ph = 0;
+      for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
+        const TileCoord tc = tile_coord(t, p);
+        const int m0 = static_cast<int>((tc.m_blk * CG + rank) * 128);
+        const int n0 = static_cast<int>(tc.n_blk * BLOCK_N + rank * N_LOCAL);
+        const int ba = static_cast<int>(tc.b * p.a_bmul), bb = static_cast<int>(tc.b * p.b_bmul);
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          const int k0 = static_cast<int>(kb * BLOCK_K);
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+            tma_load_3d(sa, tma_a, full_bar(s), k0, m0, ba);
+            if constexpr (!B_MN) {
+              tma_load_3d(sb, tma_b, full_bar(s), k0, n0, bb);
+            } else {
+#pragma unroll
+              for (int c = 0; c < NUM_CHUNKS; ++c)
+                tma_load_3d(sb + c * CHUNK_BYTES, tma_b, full_bar(s), n0 + c * CHUNK_N, k0, bb);
+            }
+          } else {
+            const uint32_t fb = leader_full0 + 8u * s;
+            if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE_BYTES);
+            tma_load_3d_2sm(sa, tma_a, fb, k0, m0, ba);
+            if constexpr (!B_MN) {
+              tma_load_3d_2sm(sb, tma_b, fb, k0, n0, bb);
+            } else {
+#pragma unroll
+              for (int c = 0; c < NUM_CHUNKS; ++c)
+                tma_load_3d_2sm(sb + c * CHUNK_BYTES, tma_b, fb, n0 + c * CHUNK_N, k0, bb);
+            }
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread, leader CTA)
+    if (leader && lane == 0) {
+      uint32_t s = 0, ph = 0, as = 0, aph = 0;
+      for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
+        mbar_wait(tempty_bar(as), aph ^ 1);  // epilogue (both CTAs) drained this accumulator stage
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          // A is K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart.
+          const uint64_t a_desc = make_smem_desc_sw128(sa, 16, 1024);
+          // B K-major: same.  B MN-major: 128-byte rows run along N, 8 k-rows per atom (SBO 1024),
+          // next 128-byte N chunk CHUNK_BYTES further (LBO).
+          const uint64_t b_desc = B_MN ? make_smem_desc_sw128(sb, CHUNK_BYTES, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_k = a_desc + static_cast<uint64_t>((k * 32) >> 4);
+            const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
+            umma_ss<CG, KIND>(d_tmem, a_k, b_k, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<CG>(empty_bar(s));  // smem slot reusable once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit<CG>(tfull_bar(as));  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (4 warps, TMEM -> regs -> global)
+    const uint32_t q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t tempty_leader = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t osz = (OUT == OUT_F32) ? 4 : 2;
+    uint32_t as = 0, aph = 0;
+    for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
+      const TileCoord tc = tile_coord(t, p);
+      const uint32_t m = (tc.m_blk * CG + rank) * 128 + q * 32 + lane;
+      const uint32_t n_tile = tc.n_blk * BLOCK_N;
+      const uint64_t row_ptr = p.out + (static_cast<uint64_t>(tc.b) * p.out_batch_stride + static_cast<uint64_t>(m) * p.out_row_stride) * osz;
+      mbar_wait(tfull_bar(as), aph);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const uint32_t n0 = n_tile + c * 32;
+        if (m < p.M && n0 < p.N) store_chunk32<OUT>(row_ptr, n0, p.N, p.vec_store != 0, v);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+// Dynamic shared memory a variant needs (host mirrors this in capi.cpp: gemm_smem_bytes()).
+//   STAGES * (16384 + (BLOCK_N/CG)*128) + 1024 (alignment slack) + 256 (barriers)
+
+#define GEMM_KERNEL(NAME, CG, BN, BMN, KIND, OUT, STAGES)                                                        \
+  extern "C" __global__ void __launch_bounds__(kNumThreads, 1)                                                   \
+      NAME(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,                 \
+           const __grid_constant__ GemmParams p) {                                                               \
+    gemm_body<CG, BN, BMN, KIND, OUT, STAGES>(&tma_a, &tma_b, p);                                                \
+  }
+
+// name: gemm_<in>_<out>_<cg>sm_n<BLOCK_N>_<bk|bn>   (bk: rhs stored [N,K] K-major; bn: rhs stored [K,N] row-major)
+// 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
+GEMM_KERNEL(gemm_bf16_bf16_2sm_n256_bk, 2, 256, false, KIND_BF16, OUT_BF16, 6)
+GEMM_KERNEL(gemm_bf16_bf16_2sm_n256_bn, 2, 256, true, KIND_BF16, OUT_BF16, 6)
+GEMM_KERNEL(gemm_bf16_f32_2sm_n256_bk, 2, 256, false, KIND_BF16, OUT_F32, 6)
+GEMM_KERNEL(gemm_bf16_f32_2sm_n256_bn, 2, 256, true, KIND_BF16, OUT_F32, 6)
+GEMM_KERNEL(gemm_f16_f16_2sm_n256_bk, 2, 256, false, KIND_F16, OUT_F16, 6)
+GEMM_KERNEL(gemm_f16_f16_2sm_n256_bn, 2, 256, true, KIND_F16, OUT_F16, 6)
+GEMM_KERNEL(gemm_f16_f32_2sm_n256_bk, 2, 256, false, KIND_F16, OUT_F32, 6)
+GEMM_KERNEL(gemm_f16_f32_2sm_n256_bn, 2, 256, true, KIND_F16, OUT_F32, 6)
+GEMM_KERNEL(gemm_tf32_f32_2sm_n256_bk, 2, 256, false, KIND_TF32, OUT_F32, 6)
+GEMM_KERNEL(gemm_tf32_f32_2sm_n256_bn, 2, 256, true, KIND_TF32, OUT_F32, 6)
+// 2-SM, 256x128 tiles (better wave quantisation on mid-size problems): 24 KB/stage/CTA -> 8 stages = 192 KB
+GEMM_KERNEL(gemm_bf16_bf16_2sm_n128_bk, 2, 128, false, KIND_BF16, OUT_BF16, 8)
+GEMM_KERNEL(gemm_bf16_bf16_2sm_n128_bn, 2, 128, true, KIND_BF16, OUT_BF16, 8)
+GEMM_KERNEL(gemm_bf16_f32_2sm_n128_bk, 2, 128, false, KIND_BF16, OUT_F32, 8)
+GEMM_KERNEL(gemm_bf16_f32_2sm_n128_bn, 2, 128, true, KIND_BF16, OUT_F32, 8)
+GEMM_KERNEL(gemm_f16_f16_2sm_n128_bk, 2, 128, false, KIND_F16, OUT_F16, 8)
+GEMM_KERNEL(gemm_f16_f16_2sm_n128_bn, 2, 128, true, KIND_F16, OUT_F16, 8)
+GEMM_KERNEL(gemm_f16_f32_2sm_n128_bk, 2, 128, false, KIND_F16, OUT_F32, 8)
+GEMM_KERNEL(gemm_f16_f32_2sm_n128_bn, 2, 128, true, KIND_F16, OUT_F32, 8)
+GEMM_KERNEL(gemm_tf32_f32_2sm_n128_bk, 2, 128, false, KIND_TF32, OUT_F32, 8)
+GEMM_KERNEL(gemm_tf32_f32_2sm_n128_bn, 2, 128, true, KIND_TF32, OUT_F32, 8)
+// 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
+GEMM_KERNEL(gemm_bf16_bf16_1sm_n128_bk, 1, 128, false, KIND_BF16, OUT_BF16, 6)
+GEMM_KERNEL(gemm_bf16_bf16_1sm_n128_bn, 1, 128, true, KIND_BF16, OUT_BF16, 6)
+GEMM_KERNEL(gemm_bf16_f32_1sm_n128_bk, 1, 128, false, KIND_BF16, OUT_F32, 6)
+GEMM_KERNEL(gemm_bf16_f32_1sm_n128_bn, 1, 128, true, KIND_BF16, OUT_F32, 6)
+GEMM_KERNEL(gemm_f16_f16_1sm_n128_bk, 1, 128, false, KIND_F16, OUT_F16, 6)
+GEMM_KERNEL(gemm_f16_f16_1sm_n128_bn, 1, 128, true, KIND_F16, OUT_F16, 6)
+GEMM_KERNEL(gemm_f16_f32_1sm_n128_bk, 1, 128, false, KIND_F16, OUT_F32, 6)
+GEMM_KERNEL(gemm_f16_f32_1sm_n128_bn, 1, 128, true, KIND_F16, OUT_F32, 6)
+GEMM_KERNEL(gemm_tf32_f32_1sm_n128_bk, 1, 128, false, KIND_TF32, OUT_F32, 6)
+GEMM_KERNEL(gemm_tf32_f32_1sm_n128_bn, 1, 128, true, KIND_TF32, OUT_F32, 6)

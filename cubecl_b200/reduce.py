@@ -1,0 +1,53 @@
+"""`reduce::launch` surface (cubek's reduce is out of tree; in-tree semantics: examples/sum_things/src/lib.rs:6-33,
+cubecl-book/src/getting-started/src/bin/v1-cpu.rs:7-15).
+
+Reduces one axis (or every element with axis=None) of a contiguous tensor; f32 accumulation; output f32 (values) or
+u32 (indices for argmax/argmin: ties -> lowest index, first NaN wins).  Kernels: csrc/reduce.cu.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _ffi
+from ._ffi import B200Error
+from .client import ComputeClient, DTYPES, TensorHandle
+
+OPS = {"sum": _ffi.REDUCE_SUM, "prod": _ffi.REDUCE_PROD, "max": _ffi.REDUCE_MAX, "min": _ffi.REDUCE_MIN,
+       "argmax": _ffi.REDUCE_ARGMAX, "argmin": _ffi.REDUCE_ARGMIN, "mean": _ffi.REDUCE_MEAN}
+
+
+def output_shape(shape, axis) -> list[int]:
+    shape = list(shape)
+    if axis is None:
+        return [1]
+    if not -len(shape) <= axis < len(shape):
+        raise ValueError(f"axis {axis} out of range for rank {len(shape)}")
+    axis %= len(shape)
+    return shape[:axis] + shape[axis + 1:] or [1]
+
+
+def output_dtype(op: str) -> str:
+    return "u32" if op in ("argmax", "argmin") else "f32"
+
+
+def launch(client: ComputeClient, input: TensorHandle, output: TensorHandle, axis, op: str = "sum") -> None:
+    """Enqueue the reduction on the client's stream; errors are deferred to sync()/read_one()."""
+    try:
+        if op not in OPS:
+            raise B200Error(6, f"unknown reduce op {op!r}")
+        if not input.is_contiguous():
+            raise B200Error(7, "reduce: input must be contiguous (into_contiguous is outside this path)")
+        if output.dtype != output_dtype(op):
+            raise B200Error(6, f"reduce: output dtype must be {output_dtype(op)} for op {op}")
+        rank = len(input.shape)
+        ax = -1 if axis is None else axis % rank
+        _ffi.check(client._lib.b200_reduce(client._ctx, None, OPS[op], DTYPES[input.dtype], C.c_uint64(input.handle.ptr),
+                                           C.c_uint64(output.handle.ptr), rank, _ffi.u64_array(input.shape), ax))
+    except B200Error as e:
+        client._defer(e)
+
+
+def launch_alloc(client: ComputeClient, input: TensorHandle, axis, op: str = "sum") -> TensorHandle:
+    out = TensorHandle.empty_contiguous(client, output_shape(input.shape, axis), output_dtype(op))
+    launch(client, input, out, axis, op)
+    return out

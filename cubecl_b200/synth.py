@@ -1,0 +1,68 @@
+"""Host mirror of the device generators in csrc/aux_kernels.cu plus bf16 bit helpers.
+
+The counter hash lets bench/tests create operands directly in HBM and still know every value on the host
+("generator = counter-based hash so host and device can regenerate identically without PCIe traffic").
+Pure numpy; used by tests and bench only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def hash_u32(seed: int, idx: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser over (seed, index) -> high 32 bits; mirrors hash_u32() in aux_kernels.cu."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + idx.astype(np.uint64) + np.uint64(0x632BE59BD9B4E019))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(32)).astype(np.uint32)
+
+
+def uniform_f32(seed: int, n: int, lo: float, hi: float, start: int = 0) -> np.ndarray:
+    """lo + u * (hi - lo) with u = (hash >> 8) * 2^-24, each op rounded to f32 (no FMA) like the device kernel."""
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    u = (hash_u32(seed, idx) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    scale = np.float32(np.float32(hi) - np.float32(lo))
+    return (np.float32(lo) + (u * scale).astype(np.float32)).astype(np.float32)
+
+
+def uniform_at(seed: int, idx: np.ndarray, lo: float, hi: float) -> np.ndarray:
+    u = (hash_u32(seed, np.asarray(idx, dtype=np.uint64)) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    scale = np.float32(np.float32(hi) - np.float32(lo))
+    return (np.float32(lo) + (u * scale).astype(np.float32)).astype(np.float32)
+
+
+def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even f32 -> bf16 bit patterns (uint16); NaN stays NaN. Mirrors __float2bfloat16_rn."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    rounding = ((b >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    out = ((b + rounding) >> np.uint32(16)).astype(np.uint16)
+    nan = np.isnan(x)
+    if np.any(nan):
+        out = np.where(nan, np.uint16(0x7FC0), out)
+    return out
+
+
+def bf16_bits_to_f32(bits: np.ndarray) -> np.ndarray:
+    return (np.ascontiguousarray(bits, dtype=np.uint16).astype(np.uint32) << np.uint32(16)).view(np.float32)
+
+
+def to_device_dtype(x_f32: np.ndarray, dtype: str) -> np.ndarray:
+    """f32 values -> array in the device representation of `dtype` (bf16 as uint16 bits)."""
+    if dtype == "f32":
+        return np.ascontiguousarray(x_f32, dtype=np.float32)
+    if dtype == "f16":
+        return np.ascontiguousarray(x_f32, dtype=np.float32).astype(np.float16)
+    if dtype == "bf16":
+        return f32_to_bf16_bits(x_f32)
+    raise ValueError(dtype)
+
+
+def from_device_dtype(a: np.ndarray, dtype: str) -> np.ndarray:
+    """Device representation -> f32 values."""
+    if dtype == "bf16":
+        return bf16_bits_to_f32(a)
+    return np.asarray(a).astype(np.float32)

@@ -1,0 +1,166 @@
+/* cubecl_b200.h -- C ABI of the B200-native dense linear-algebra hot path (tcgen05 matmul + HBM-bound reduction).
+ *
+ * This is the drop-in boundary a CubeCL maintainer binds from Rust (see INTEGRATION.md for the `extern "C"` block and the
+ * `CudaServer` hook).  Plain pointers and sizes only; no torch / C++ types.  All device pointers are CUdeviceptr values
+ * carried as uint64_t, all streams are CUstream carried as void* (NULL = the context's own compute stream).
+ *
+ * Citations are into the reference tree (tracel-ai/cubecl @ 4057f39e), i.e. the interface each entry point replaces.
+ *
+ * Threading (crates/cubecl-common/src/device/handle/mod.rs:18-24): one thread per device at a time; distinct contexts
+ * are independent.  The only process-global state is the dlopen'ed driver/NCCL symbol tables and the last-error string,
+ * which is thread-local.
+ *
+ * Errors (crates/cubecl-runtime/src/server/base.rs:177-272): every call returns a b200_status; the message is available
+ * from b200_last_error() on the calling thread.  Asynchronous device faults surface at the next b200_sync()/b200_read(),
+ * like ServerError::ServerUnhealthy does at sync/read (crates/cubecl-cuda/src/compute/server.rs:981-1022).
+ *
+ * There is no CPU fallback anywhere behind this header: without a CUDA driver and an sm_100 device b200_init() fails.
+ */
+#ifndef CUBECL_B200_H
+#define CUBECL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+typedef struct b200_ctx b200_ctx;
+typedef uint64_t b200_dptr;   /* CUdeviceptr */
+typedef void* b200_stream;    /* CUstream; NULL = context compute stream */
+typedef void* b200_event;     /* CUevent */
+
+/* Mirrors LaunchError / ServerError variants (server/base.rs:177-272) so a Rust shim can map 1:1. */
+typedef enum b200_status {
+  B200_OK = 0,
+  B200_ERR_COMPILATION = 1,        /* LaunchError::CompilationError  -- here: cubin image failed to load */
+  B200_ERR_OUT_OF_MEMORY = 2,      /* LaunchError::OutOfMemory */
+  B200_ERR_TOO_MANY_RESOURCES = 3, /* LaunchError::TooManyResources (smem / units / cube dim) */
+  B200_ERR_UNKNOWN = 4,            /* LaunchError::Unknown */
+  B200_ERR_IO = 5,                 /* LaunchError::IoError / IoError::* */
+  B200_ERR_INVALID_ARG = 6,        /* shape/stride/dtype validation failed before launch */
+  B200_ERR_UNSUPPORTED = 7,        /* feature absent (dtype/layout not implemented) -- callers self-skip like runtime_tests do */
+  B200_ERR_NO_DEVICE = 8,          /* no driver / no sm_100 device: fail loudly, never fall back */
+  B200_ERR_COMM = 9,               /* NCCL failure -> ServerError::Generic (server.rs:773-776) */
+  B200_ERR_UNHEALTHY = 10          /* deferred device fault surfaced at sync -> ServerError::ServerUnhealthy */
+} b200_status;
+
+/* Element types.  Values double as the NCCL dtype selector of communication.rs:34-108 for all_reduce. */
+typedef enum b200_dtype {
+  B200_F32 = 0, B200_F16 = 1, B200_BF16 = 2, B200_U32 = 3, B200_I32 = 4, B200_F64 = 5, B200_I64 = 6, B200_U64 = 7,
+  B200_U8 = 8, B200_I8 = 9
+} b200_dtype;
+
+/* Reduction instructions of the `reduce::launch` surface (cubek); in-tree semantics: examples/sum_things/src/lib.rs:6-33,
+ * cubecl-book/.../v1-cpu.rs:7-15.  Arg ops: ties -> lowest index, NaN is the extreme and the first NaN wins. */
+typedef enum b200_reduce_op {
+  B200_REDUCE_SUM = 0, B200_REDUCE_PROD = 1, B200_REDUCE_MAX = 2, B200_REDUCE_MIN = 3,
+  B200_REDUCE_ARGMAX = 4, B200_REDUCE_ARGMIN = 5, B200_REDUCE_MEAN = 6
+} b200_reduce_op;
+
+/* ReduceOperation{Sum,Mean} -- crates/cubecl-runtime/src/server/base.rs:623-628 */
+typedef enum b200_comm_op { B200_COMM_SUM = 0, B200_COMM_MEAN = 1 } b200_comm_op;
+
+/* HardwareProperties subset -- crates/cubecl-ir/src/properties.rs:26-58, probed like cubecl-cuda/src/runtime.rs:52-350 */
+typedef struct b200_props {
+  int32_t device;
+  int32_t cc_major, cc_minor;
+  int32_t num_sms;                 /* num_streaming_multiprocessors */
+  int32_t max_shared_per_block;    /* opt-in maximum (max_shared_memory_size) */
+  int32_t clock_khz, mem_clock_khz;
+  int32_t plane_size;              /* 32 */
+  uint64_t total_mem;
+  char name[128];
+} b200_props;
+
+/* ---- lifecycle: R::client(device) -> DeviceService::init (cubecl-cuda/src/runtime.rs:52-350) ------------------------ */
+int b200_abi_version(void);
+int b200_device_count(int* count);
+int b200_init(int device, b200_ctx** out);   /* cuInit, primary ctx retain, load the embedded sm_100a cubins (context.rs:293) */
+int b200_destroy(b200_ctx* ctx);
+int b200_get_props(b200_ctx* ctx, b200_props* out);
+/* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
+ * (auto|2sm_n256|2sm_n128|1sm_n128|simt), "gemm.f32" (3xtf32|tf32), "gemm.group_m", "reduce.variant"
+ * (auto|u4|u8|u16|w2|w4), "reduce.threads", "reduce.blocks_per_sm". */
+int b200_set_option(b200_ctx* ctx, const char* key, const char* value);
+/* Number of device kernels this context has launched so far (bench.py reports it as gpu_launches). */
+int b200_launch_count(b200_ctx* ctx, uint64_t* count);
+
+/* ---- memory: ComputeClient::{empty,create_from_slice,read_one} (cubecl-runtime/src/client.rs:654,452,256) ----------- */
+/* Pooled device allocation, 512-byte aligned (mem_alignment, cubecl-cuda/src/runtime.rs:81). */
+int b200_alloc(b200_ctx* ctx, size_t bytes, b200_dptr* out);
+int b200_free(b200_ctx* ctx, b200_dptr ptr);
+int b200_memory_usage(b200_ctx* ctx, uint64_t* bytes_in_use, uint64_t* bytes_reserved);  /* MemoryUsage, memory_management/base.rs:7-28 */
+int b200_memory_cleanup(b200_ctx* ctx);                                                  /* client.memory_cleanup */
+/* Pinned host staging (compute/stream.rs:138-178 pinned pool). */
+int b200_host_alloc(b200_ctx* ctx, size_t bytes, void** out);
+int b200_host_free(b200_ctx* ctx, void* ptr);
+/* Stream-ordered copies.  b200_write/read are asynchronous when `host` is pinned; call b200_sync before reusing `host`. */
+int b200_write(b200_ctx* ctx, b200_stream s, b200_dptr dst, const void* host_src, size_t bytes);
+int b200_read(b200_ctx* ctx, b200_stream s, void* host_dst, b200_dptr src, size_t bytes);
+int b200_copy(b200_ctx* ctx, b200_stream s, b200_dptr dst, b200_dptr src, size_t bytes);
+int b200_memset32(b200_ctx* ctx, b200_stream s, b200_dptr dst, uint32_t value, size_t words);
+
+/* ---- streams / sync / timing: ComputeClient::sync (client.rs:1013), Fence = CUevent (compute/sync/fence.rs) ---------- */
+int b200_stream_create(b200_ctx* ctx, b200_stream* out);
+int b200_stream_destroy(b200_ctx* ctx, b200_stream s);
+int b200_sync(b200_ctx* ctx, b200_stream s);
+int b200_event_create(b200_ctx* ctx, b200_event* out);
+int b200_event_record(b200_ctx* ctx, b200_event e, b200_stream s);
+int b200_event_elapsed_ms(b200_ctx* ctx, b200_event start, b200_event end, float* ms);
+int b200_event_destroy(b200_ctx* ctx, b200_event e);
+
+/* ---- matmul::launch (cubek; shape rule crates/cubecl-zspace/src/shape.rs:489-517) ----------------------------------
+ * out[..,m,n] = sum_k lhs[..,m,k] * rhs[..,k,n]; equal rank >= 2, leading dims broadcast (1 vs d); shapes/strides in
+ * ELEMENTS (TensorHandle, cubecl-std/src/tensor/handle.rs:13-23).  f32 accumulation over k.  Inputs f16/bf16/f32;
+ * `out_dtype` is the input dtype or F32.  Row strides may be pitched (allocator.rs:21-72); rhs may be given transposed
+ * (stride_k == 1, MatrixBatchLayout::MildlyPermuted{transposed}, matrix_batch_layout.rs:8-19).  f32 inputs run on the tf32
+ * tensor pipe, by default with a 3-way split that restores ~f32 accuracy (see "gemm.f32").
+ * Returns B200_ERR_INVALID_ARG on shape mismatch -- the MatmulShapeError of shape.rs:489-517. */
+int b200_matmul(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype,
+                b200_dptr lhs, b200_dptr rhs, b200_dptr out, int rank,
+                const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                const uint64_t* shape_rhs, const uint64_t* strides_rhs,
+                const uint64_t* shape_out, const uint64_t* strides_out);
+
+/* ---- reduce::launch (cubek) -----------------------------------------------------------------------------------------
+ * Reduces `axis` (0..rank-1) of a CONTIGUOUS row-major input, or every element when axis == -1.  Output is contiguous
+ * with the reduced axis removed (one element for axis == -1): F32 values, or U32 indices along the axis for arg ops.
+ * Input dtype F32 / F16 / BF16, f32 accumulation.  Single launch, no host sync; uses a per-stream workspace owned by ctx. */
+int b200_reduce(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype,
+                b200_dptr in, b200_dptr out, int rank, const uint64_t* shape, int axis);
+
+/* ---- collectives: ServerCommunication (server/base.rs:632-739), CUDA impl cubecl-cuda/src/compute/server.rs:666-926 -- */
+#define B200_UNIQUE_ID_BYTES 128
+int b200_comm_get_unique_id(b200_ctx* ctx, void* id128);            /* ncclGetUniqueId (communication.rs:11-25 holds it per device set) */
+/* Communicator for the device set `device_ids` (keyed by the sorted set, CommunicationId server/base.rs:605-620);
+ * this context's rank is the position of its device in the sorted list (server.rs:669-703). */
+int b200_comm_init(b200_ctx* ctx, const int* device_ids, int n, const void* id128);
+/* src -> dst (may alias) of bytes/elem_size elements on the communicator's comm stream, after an event wait on
+ * `compute` (server.rs:705-780). */
+int b200_all_reduce(b200_ctx* ctx, b200_stream compute, b200_dptr src, b200_dptr dst, size_t bytes, b200_dtype dtype,
+                    b200_comm_op op, const int* device_ids, int n);
+/* Make `compute` wait for everything issued on the comm stream (server.rs:782-798). */
+int b200_sync_collective(b200_ctx* ctx, b200_stream compute);
+
+/* ---- synthetic operands + reference-equivalent probes (examples/throughput) ----------------------------------------- */
+/* out[i] = lo + u(seed,i) * (hi - lo), u in [0,1) from a counter hash the host can reproduce (cubecl_b200/synth.py);
+ * mode 1: out[i] = i % modulus. */
+int b200_fill_uniform(b200_ctx* ctx, b200_stream s, b200_dtype dtype, b200_dptr out, uint64_t n, uint64_t seed, float lo, float hi);
+int b200_fill_modulo(b200_ctx* ctx, b200_stream s, b200_dtype dtype, b200_dptr out, uint64_t n, uint32_t modulus);
+/* compute_cmma_throughput as CubeCL would JIT it today (wmma 16x16x16): launches grid = SMs*32, block = 256, `n_iter`
+ * dependent mma_sync per plane; *ops = cubes * planes * 2*m*n*k * n_iter (compute_cmma.rs:16,41-42). dtype F16 or BF16. */
+int b200_probe_wmma(b200_ctx* ctx, b200_stream s, b200_dtype dtype, uint32_t n_iter, b200_dptr scratch_1k, double* ops);
+/* memory_read_throughput with float_4 lines over `bytes` of `buf` (memory_read.rs:68-154): grid = SMs*32, block = 256. */
+int b200_probe_memread(b200_ctx* ctx, b200_stream s, b200_dptr buf, uint64_t bytes, b200_dptr scratch_16);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBECL_B200_H */
