@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the dense-LA hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: one bf16 matmul 8192^3 per GPU (BASELINE
+config 3; at N GPUs the batch axis [N, 8192, 8192] is sharded one batch per rank -- batched matmul over the batch axis,
+no data-path collective, weak scaling).  `value` = whole-job TFLOP/s with operands resident in HBM, timed with CUDA events
+on the launching stream, max over ranks.  `e2e` = the same metric through the public API with HOST buffers (pinned H2D of
+both operands + D2H of the result inside the timed region, every step).
+
+Secondary objects on the same JSON line cover the other BASELINE configs: `reduce` (f32 sum of 2^28, weak + strong
+sharding with an NCCL all-reduce), `matmul_f32_4096`, `batched_bf16_4096`, `reference_equivalent` (what CubeCL's own
+wmma / vec4 kernels reach on this GPU), plus `roofline`, `roofline_reduce`, `cpu_baseline`, `clocks`.
+
+--impl reference times the reference's CPU semantics (the oracle port; the Rust reference cannot be built here) on the
+host cores, on a bounded sample of the same workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_MM = 8192                      # BASELINE config 3
+FLOPS_MM = 2.0 * N_MM ** 3
+N_RED = 1 << 28                  # BASELINE config 4
+BYTES_RED = N_RED * 4
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return dict(FALLBACK_PEAKS, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def ncu_traffic():
+    """Per-launch DRAM traffic of the dominant kernels, from the committed ncu summary of this round (or None)."""
+    p = ROOT / "profiles" / "traffic.json"
+    return json.loads(p.read_text()) if p.exists() else {}
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile(prefix="clocks", suffix=".csv", delete=False).name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        try:
+            rows = [r.split(", ") for r in Path(self.path).read_text().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            out["samples"] = len(rows)
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, nm in enumerate(names):
+                    if any(r[5 + i].strip().lower().startswith("active") for r in rows if len(r) > 5 + i):
+                        out["reasons"].append(nm)
+        except Exception as e:  # noqa: BLE001
+            out["error"] = str(e)
+        return out
+
+
+def rejected(clocks) -> bool:
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if bad & set(clocks.get("reasons", [])):
+        return True
+    sm, mx = clocks.get("sm_mhz"), clocks.get("sm_max_mhz")
+    return bool(sm and mx and sm < 0.5 * mx and not clocks.get("reasons"))
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def cpu_matmul_sample(seconds_target=12.0):
+    """Reference-order CPU matmul (oracle port, all host threads) on a bounded row-slab of the 8192^3 problem."""
+    import oracle
+    from cubecl_b200 import synth
+    threads = oracle.num_threads()
+    K = Ncols = N_MM
+    b_nk = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(4, 512 * K, -1.0, 1.0))).reshape(512, K)  # 512 rhs columns
+    rows = 2 * threads
+    a = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(3, rows * K, -1.0, 1.0))).reshape(rows, K)
+    t0 = time.perf_counter()
+    oracle.matmul_blocked_f32(a, b_nk, threads)
+    dt = time.perf_counter() - t0
+    rate = 2.0 * rows * 512 * K / dt                       # FLOP/s on the probe
+    # size the sample: `rows_s` rows x 512 columns x K, ~seconds_target of work
+    rows_s = int(max(rows, min(8192, seconds_target * rate / (2.0 * 512 * K))))
+    rows_s = max(threads, rows_s // threads * threads)
+    a = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(3, rows_s * K, -1.0, 1.0))).reshape(rows_s, K)
+    t0 = time.perf_counter()
+    oracle.matmul_blocked_f32(a, b_nk, threads)
+    dt = time.perf_counter() - t0
+    flops = 2.0 * rows_s * 512 * K
+    return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+            "sample": f"{rows_s}x512 block of C of the bf16 8192^3 matmul (K=8192 full), reference-order f32 loops, {threads} threads, {dt:.1f} s",
+            "seconds": dt, "flops": flops}
+
+
+def cpu_reduce_sample():
+    import oracle
+    from cubecl_b200 import synth
+    threads = oracle.num_threads()
+    n = 1 << 26
+    x = synth.uniform_f32(5, n, 0.0, 1.0)
+    t0 = time.perf_counter(); oracle.sum_serial_f32(x); t_serial = time.perf_counter() - t0
+    t0 = time.perf_counter(); oracle.sum_blocked_f32(x, threads); t_blocked = time.perf_counter() - t0
+    return {"serial_gbs": n * 4 / t_serial / 1e9, "blocked_gbs": n * 4 / t_blocked / 1e9, "cores": threads,
+            "sample": "2^26 of the 2^28 f32 elements"}
+
+
+def run_reference(args):
+    e_rank = int(os.environ.get("RANK", "0"))
+    if e_rank != 0:
+        return
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_matmul_sample(seconds_target=max(1.0, 40.0 / (args.warmup + args.steps)))
+        if i >= args.warmup:
+            times.append(last)
+    flops = sum(t["flops"] for t in times)
+    secs = sum(t["seconds"] for t in times)
+    val = flops / secs / 1e12
+    line = {"impl": "reference", "metric": "bf16_matmul_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / len(times) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "bf16 matmul 8192x8192x8192 (f32 accumulate), bounded sample per step",
+                       "note": "reference = CPU restatement of cubecl's semantics (oracle port); the Rust reference cannot be built here"},
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+            "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline + reduce only")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from cubecl_b200 import ComputeClient, TensorHandle, matmul, reduce
+    from cubecl_b200 import distributed as D
+
+    e = D.env()
+    world = e.world_size
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    dist = None
+    tdev = None
+    if world > 1:
+        import torch
+        dist = D.init_process_group("nccl")
+        tdev = torch.device("cuda", e.local_rank)
+
+    c = ComputeClient.load(e.local_rank)
+    pk = peaks()
+    rank0 = e.rank == 0
+
+    def barrier():
+        c.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        """W untimed + exactly `steps` timed launches between barriers; CUDA events on the launching stream; max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = c.event(), c.event()
+        l0 = c.launch_count()
+        c.record(e0)
+        for _ in range(steps):
+            fn()
+        c.record(e1)
+        ms = c.elapsed_ms(e0, e1)
+        c.sync()
+        launches = c.launch_count() - l0
+        barrier()
+        if dist is not None:
+            ms = D.max_over_ranks(ms, dist, tdev)
+        c.event_destroy(e0); c.event_destroy(e1)
+        return ms, launches
+
+    # ------------------------------------------------------------------ headline: bf16 8192^3 per GPU, HBM-resident
+    a = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "bf16")
+    b = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "bf16")
+    o = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "bf16")
+    c.fill_uniform(a.handle, "bf16", N_MM * N_MM, 3 + 100 * e.rank, -1.0, 1.0)
+    c.fill_uniform(b.handle, "bf16", N_MM * N_MM, 4 + 100 * e.rank, -1.0, 1.0)
+
+    def mm_step():
+        matmul.launch(c, a, b, o)
+
+    clocks = None
+    for attempt in range(2):
+        with ClockSampler(e.local_rank) as cs:
+            ms, launches = timed(mm_step, args.steps, args.warmup)
+        clocks = cs.summary()
+        if not rejected(clocks):
+            break
+        clocks["remeasured"] = True
+    c.flush()
+    value = world * FLOPS_MM * args.steps / (ms * 1e-3) / 1e12
+    per_launch_ms = ms / args.steps
+    per_gpu_tflops = FLOPS_MM / (per_launch_ms * 1e-3) / 1e12
+    traffic = ncu_traffic()
+
+    line = {
+        "metric": "bf16_matmul_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"bf16 matmul 8192x8192x8192 per GPU (f32 accumulate, bf16 out), batch [{world},8192,8192] sharded over the batch axis",
+                   "parallelism": f"batch-shard x{world}, no data-path collective",
+                   "l2": "inputs_larger_than_L2 (A+B+C = 384 MiB per GPU vs 126 MB L2)", "rhs_layout": "row-major [K,N]"},
+        "gpu_launches": launches * world,
+        "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": per_gpu_tflops / pk["bf16_tflops"], "traffic": traffic.get("gemm_bf16_8192_dram_bytes"),
+                     "peak_source": pk["source"] + " (cuBLAS bf16 burst)", "kernel": "gemm_bf16_bf16_2sm_n256_bn",
+                     "algorithmic_flops_per_launch": FLOPS_MM},
+        "clocks": clocks,
+    }
+
+    # ------------------------------------------------------------------ e2e: host buffers through the public API
+    nbytes = N_MM * N_MM * 2
+    ha, hb, hc = c.host_alloc(nbytes), c.host_alloc(nbytes), c.host_alloc(nbytes)
+    ha.view(np.uint16)[:] = 0x3F80  # 1.0 in bf16 (contents do not change the work)
+    hb.view(np.uint16)[:] = 0x3F80
+
+    def e2e_step():
+        c.write_async(a.handle, ha)
+        c.write_async(b.handle, hb)
+        matmul.launch(c, a, b, o)
+        c.read_async(hc, o.handle)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e, _ = timed(e2e_step, e2e_steps, 3)
+    assert hc.view(np.uint16)[0] == 0x4600, "e2e result check failed"  # 8192 = sum of 8192 ones, exact in bf16
+    line["e2e"] = {"value": world * FLOPS_MM * e2e_steps / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
+                   "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps,
+                   "api": "ComputeClient.write_async x2 + matmul.launch + read_async, pinned host buffers"}
+    for h in (ha, hb, hc):
+        c.host_free(h)
+    c.fill_uniform(a.handle, "bf16", N_MM * N_MM, 3 + 100 * e.rank, -1.0, 1.0)
+    c.fill_uniform(b.handle, "bf16", N_MM * N_MM, 4 + 100 * e.rank, -1.0, 1.0)
+
+    # ------------------------------------------------------------------ reduce: f32 sum of 2^28 (1 GiB), weak + strong
+    red = {"metric": "f32_reduce_sum_gbs", "unit": "GB/s", "elements": N_RED}
+    nbuf = 3                                                 # rotate 3 x 1 GiB so nothing survives in the 126 MB L2
+    xs = [TensorHandle.empty_contiguous(c, [N_RED], "f32") for _ in range(nbuf)]
+    for i, x in enumerate(xs):
+        c.fill_uniform(x.handle, "f32", N_RED, 5 + i + 10 * e.rank, 0.0, 1.0)
+    r_out = TensorHandle.empty_contiguous(c, [1], "f32")
+    k = [0]
+    ids = list(range(world))
+    if world > 1:
+        uid = D.exchange_unique_id(c.get_unique_id, dist)
+        c.ensure_init_collective(ids, uid)
+
+    def red_local():
+        k[0] += 1
+        reduce.launch(c, xs[k[0] % nbuf], r_out, None, "sum")
+
+    rsteps = max(args.steps, 20)
+    ms_r, _ = timed(red_local, rsteps, args.warmup)
+    gbs = BYTES_RED / (ms_r / rsteps * 1e-3) / 1e9
+    red["kernel_only_per_gpu"] = gbs
+    line["roofline_reduce"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                               "traffic": traffic.get("reduce_sum_2p28_dram_bytes"), "peak_source": pk["source"] + " (copy, read+write)",
+                               "kernel": "reduce_all_sum_f32", "algorithmic_bytes_per_launch": BYTES_RED}
+    if world > 1:
+        def red_weak():                                       # 2^28 per GPU, local sum + all-reduce of one f32
+            red_local()
+            c.all_reduce(r_out.handle, r_out.handle, "f32", ids, "sum")
+            c.sync_collective()
+
+        ms_w, _ = timed(red_weak, rsteps, args.warmup)
+        red["weak"] = {"value": world * BYTES_RED / (ms_w / rsteps * 1e-3) / 1e9, "ms_per_step": ms_w / rsteps,
+                       "config": "2^28 f32 per GPU, outer-axis shard + NCCL all-reduce(4 B)"}
+        lo, hi = D.shard_range(N_RED, world, e.rank)
+        shard = TensorHandle(xs[0].handle.offset(lo * 4, (hi - lo) * 4), [hi - lo], [1], "f32")
+
+        def red_strong():                                     # 2^28 total, 2^28/N per GPU
+            reduce.launch(c, shard, r_out, None, "sum")
+            c.all_reduce(r_out.handle, r_out.handle, "f32", ids, "sum")
+            c.sync_collective()
+
+        ms_s, _ = timed(red_strong, rsteps, args.warmup)
+        red["strong"] = {"value": BYTES_RED / (ms_s / rsteps * 1e-3) / 1e9, "ms_per_step": ms_s / rsteps,
+                         "config": "2^28 f32 total, contiguous outer-axis shards + NCCL all-reduce(4 B); latency-bound"}
+        red["value"] = red["weak"]["value"]
+    else:
+        red["value"] = gbs
+    # reduce e2e at N=1 (1 GiB pinned H2D + 4 B D2H)
+    if world == 1 and not args.quick:
+        hx = c.host_alloc(BYTES_RED)
+        hr = c.host_alloc(4)
+        hx.view(np.float32)[:] = 1.0
+
+        def red_e2e():
+            c.write_async(xs[0].handle, hx)
+            reduce.launch(c, xs[0], r_out, None, "sum")
+            c.read_async(hr, r_out.handle)
+
+        ms_re, _ = timed(red_e2e, 3, 1)
+        assert hr.view(np.float32)[0] == float(N_RED)
+        red["e2e"] = {"value": BYTES_RED / (ms_re / 3 * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": BYTES_RED, "d2h_bytes_per_step": 4}
+        c.host_free(hx); c.host_free(hr)
+    del xs
+    c.memory_cleanup()
+    line["reduce"] = red
+
+    # ------------------------------------------------------------------ other BASELINE configs (N-independent per GPU)
+    if not args.quick:
+        extra_steps = max(5, min(args.steps, 10))
+        n4 = 4096
+        # config 5: batched bf16, 8 x 4096^3 per GPU (B = 8N sharded over the batch axis)
+        ab = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
+        bb = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
+        ob = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
+        c.fill_uniform(ab.handle, "bf16", 8 * n4 * n4, 6, -1.0, 1.0)
+        c.fill_uniform(bb.handle, "bf16", 8 * n4 * n4, 7, -1.0, 1.0)
+        ms_b, _ = timed(lambda: matmul.launch(c, ab, bb, ob), extra_steps, 3)
+        line["batched_bf16_4096"] = {"value": world * 8 * 2.0 * n4 ** 3 * extra_steps / (ms_b * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                     "config": f"B={8 * world} x 4096^3 bf16, 8 batches per GPU, batch-axis shard, no collective"}
+        del ab, bb, ob
+        # config 2: f32 4096^3 on the tf32 tensor pipe (both f32 modes)
+        af = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
+        bf = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
+        of = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
+        c.fill_uniform(af.handle, "f32", n4 * n4, 1, -1.0, 1.0)
+        c.fill_uniform(bf.handle, "f32", n4 * n4, 2, -1.0, 1.0)
+        f32res = {}
+        for mode in ("3xtf32", "tf32"):
+            c.set_option("gemm.f32", mode)
+            ms_f, _ = timed(lambda: matmul.launch(c, af, bf, of), extra_steps, 3)
+            f32res[mode] = world * 2.0 * n4 ** 3 * extra_steps / (ms_f * 1e-3) / 1e12
+        c.set_option("gemm.f32", "3xtf32")
+        line["matmul_f32_4096"] = {"unit": "TFLOP/s (f32-equivalent 2*N^3)", "3xtf32_default": f32res["3xtf32"], "tf32": f32res["tf32"]}
+        del af, bf, of
+        # what CubeCL's own kernels reach on this GPU (hand-written from its emit rules)
+        if world == 1:
+            scratch = c.empty(1024)
+            ops = [0.0]
+
+            def wm():
+                ops[0] = c.probe_wmma("bf16", 2048, scratch)
+
+            ms_p, _ = timed(wm, 5, 2)
+            buf = c.empty(512 << 20)
+            c.fill_modulo(buf, "f32", (512 << 20) // 4, 8)
+            ms_m, _ = timed(lambda: c.probe_memread(buf, 512 << 20, scratch), 10, 2)
+            line["reference_equivalent"] = {"wmma_bf16_probe_tflops": ops[0] * 5 / (ms_p * 1e-3) / 1e12,
+                                            "vec4_read_probe_gbs": (512 << 20) * 10 / (ms_m * 1e-3) / 1e9,
+                                            "note": "compute_cmma.rs / memory_read.rs kernels as CubeCL would JIT them for sm_100a (wmma, 128-bit loads)"}
+            del buf
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    if rank0 and world == 1:
+        try:
+            cb = cpu_matmul_sample(12.0)
+            cb.pop("flops"); cb.pop("seconds")
+            line["cpu_baseline"] = cb
+            line["reduce"]["cpu_baseline"] = cpu_reduce_sample()
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": str(ex)}
+    c.sync()
+    if rank0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -620,9 +620,10 @@ static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6}, {"2sm_n128", 2,
 static unsigned gemm_smem_bytes(const GemmVariant& v) { return v.stages * (16384 + (v.block_n / v.cg) * 128) + 1024 + 256; }
 
 static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, size_t esz, uint64_t base, uint64_t d0,
-                       uint64_t d1, uint64_t d2, uint64_t s1_elems, uint64_t s2_elems, uint32_t b0, uint32_t b1) {
+                       uint64_t d1, uint64_t d2, uint64_t s1_elems, uint64_t s2_elems, uint32_t b0, uint32_t b1,
+                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   char key[256];
-  snprintf(key, sizeof(key), "%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u", (int)dt, (unsigned long long)base,
+  snprintf(key, sizeof(key), "%d|%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u", (int)dt, (int)swz, (unsigned long long)base,
            (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_elems,
            (unsigned long long)s2_elems, b0, b1);
   auto it = c->tmap_cache.find(key);
@@ -632,7 +633,7 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, dt, 3, reinterpret_cast<void*>(base), dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(B200_ERR_INVALID_ARG, "cuTensorMapEncodeTiled failed: %s (dims %llu,%llu,%llu strides %llu,%llu box %u,%u)",
@@ -728,7 +729,9 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool b
   } else {
     const uint64_t b_sk = g.K > 1 ? g.b_sk : pad16(g.N);
     rc = encode_tmap(c, &tb, dt, esz, g.b, g.N, g.K, b_bcast ? 1 : g.batch, b_sk, b_bcast ? b_sk * g.K : g.b_sb,
-                     static_cast<uint32_t>(128 / esz), block_k);
+                     static_cast<uint32_t>(128 / esz), block_k,
+                     // MN-major 32-bit operands: 32-byte swizzle atoms (matches the SWIZZLE_128B_BASE32B smem descriptor)
+                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
   }
   if (rc) return rc;
 

@@ -199,6 +199,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
         }
       }
     }
+    __syncwarp();  // reconverge before the (warp-aligned) teardown barrier
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one thread, leader CTA)
     if (leader && lane == 0) {
@@ -216,7 +217,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
           const uint64_t a_desc = make_smem_desc_sw128(sa, 16, 1024);
           // B K-major: same.  B MN-major: 128-byte rows run along N, 8 k-rows per atom (SBO 1024),
           // next 128-byte N chunk CHUNK_BYTES further (LBO).
-          const uint64_t b_desc = B_MN ? make_smem_desc_sw128(sb, CHUNK_BYTES, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+          // 32-bit MN-major operands only exist in the 32-byte-atom swizzle: 4 k-rows per atom (SBO 512).
+          const uint64_t b_desc = !B_MN ? make_smem_desc_sw128(sb, 16, 1024)
+                                  : (KIND == KIND_TF32) ? make_smem_desc(sb, CHUNK_BYTES, 512, 1)
+                                                        : make_smem_desc_sw128(sb, CHUNK_BYTES, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t a_k = a_desc + static_cast<uint64_t>((k * 32) >> 4);
@@ -230,6 +234,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================================================================== epilogue (4 warps, TMEM -> regs -> global)
     const uint32_t q = warp & 3;  // TMEM lane quarter this warp may access

