@@ -58,45 +58,53 @@ def ncu_traffic():
 
 # ---------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons through NVML from a thread DURING the timed region (the recipe's
+    nvidia-smi line needs ~100 ms per sample; a 20-step timed region lasts ~15 ms)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.rows, self._stop, self._thr, self.err = index, [], threading.Event(), None, None
+        self.max_mhz = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), pw, int(rs)))
+                time.sleep(0.001)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
     def __enter__(self):
-        try:
-            self.path = tempfile.NamedTemporaryFile(prefix="clocks", suffix=".csv", delete=False).name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        time.sleep(0.02)   # let NVML initialise before the timed region starts
         return self
 
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        self._thr.join(timeout=5)
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        try:
-            rows = [r.split(", ") for r in Path(self.path).read_text().strip().splitlines() if r.strip()]
-            sm = [float(r[1]) for r in rows]
-            out["samples"] = len(rows)
-            if sm:
-                out["sm_mhz"] = float(np.median(sm))
-                out["sm_max_mhz"] = float(rows[0][2])
-                out["power_w_max"] = max(float(r[3]) for r in rows)
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for i, nm in enumerate(names):
-                    if any(r[5 + i].strip().lower().startswith("active") for r in rows if len(r) > 5 + i):
-                        out["reasons"].append(nm)
-        except Exception as e:  # noqa: BLE001
-            out["error"] = str(e)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": len(self.rows), "how": "NVML thread, ~1 ms period, started before warm-up"}
+        if self.err:
+            out["error"] = self.err
+        if self.rows:
+            busy = [r for r in self.rows if r[1] >= 0.5 * max(x[1] for x in self.rows)] or self.rows   # samples under load
+            out["sm_mhz"] = float(np.median([r[0] for r in busy]))
+            out["sm_mhz_min"] = float(min(r[0] for r in busy))
+            out["power_w_max"] = float(max(r[1] for r in self.rows))
+            bits = 0
+            for r in busy:
+                bits |= r[2]
+            out["reasons"] = [nm for bit, nm in self.REASONS.items() if bits & bit]
         return out
 
 
@@ -173,7 +181,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline + reduce only")

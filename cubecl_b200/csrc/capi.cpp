@@ -614,8 +614,10 @@ static size_t dtype_size(int dt) {
 struct GemmVariant {
   const char* tag;  // suffix in the kernel name
   int cg, block_n, stages;
+  double eff;       // measured MMA-pipe efficiency relative to 2sm_n256 (8192^3, B200): the N=128 shapes need
+                    // 128 B/cycle/SM of operand reads from shared memory and are smem-bandwidth bound
 };
-static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6}, {"2sm_n128", 2, 128, 8}, {"1sm_n128", 1, 128, 6}};
+static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59}};
 
 static unsigned gemm_smem_bytes(const GemmVariant& v) { return v.stages * (16384 + (v.block_n / v.cg) * 128) + 1024 + 256; }
 
@@ -700,7 +702,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool b
     const uint64_t tiles = tm * tn * g.batch;
     const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
     const uint64_t waves = (tiles + clusters - 1) / clusters;
-    const double cost = static_cast<double>(waves) * (128.0 * v.block_n);  // per-SM MMA work per wave
+    const double cost = static_cast<double>(waves) * (128.0 * v.block_n) / v.eff;  // per-SM MMA time per wave
     if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; }
   }
   if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant", forced.c_str());
@@ -927,7 +929,7 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, uint64_t 
   }
   threads = (unsigned)std::min(512, std::max(32, atoi(opt(c, "reduce.threads", "512").c_str())));
   threads = threads / 32 * 32;
-  bps = (unsigned)std::max(1, atoi(opt(c, "reduce.blocks_per_sm", "2").c_str()));
+  bps = (unsigned)std::max(1, atoi(opt(c, "reduce.blocks_per_sm", "4").c_str()));
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;

@@ -237,7 +237,9 @@ def test_f32_4096_sampled_points(client):
     b_cols = np.stack([synth.uniform_at(2, np.arange(n, dtype=np.uint64) * n + c, -1.0, 1.0) for c in ns])
     f64 = a_rows.astype(np.float64) @ b_cols.astype(np.float64).T
     fabs = np.abs(a_rows).astype(np.float64) @ np.abs(b_cols).astype(np.float64).T
-    for mode, tol in (("tf32", 1e-3), ("3xtf32", 2e-6)):
+    # 3xtf32 at K = 4096: f32 accumulation of 3K products dominates (measured 4e-6); the reference-order f32 loop itself
+    # is only good to ~K * 2^-24 = 2.4e-4 in the worst case
+    for mode, tol in (("tf32", 1e-3), ("3xtf32", 1e-5)):
         client.set_option("gemm.f32", mode)
         out = TensorHandle.empty_contiguous(client, [n, n], "f32")
         matmul.launch(client, a, b, out)

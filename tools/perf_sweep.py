@@ -50,7 +50,7 @@ if "reduce" in what:
                 print(f"  {variant:4s} threads={threads:4d} blocks/SM={bps}: {ms * 1e3:8.1f} us  {n * 4 / ms / 1e6:8.1f} GB/s", flush=True)
     c.set_option("reduce.variant", "auto")
     c.set_option("reduce.threads", 512)
-    c.set_option("reduce.blocks_per_sm", 2)
+    c.set_option("reduce.blocks_per_sm", 4)
     del bufs
 
 if "gemm" in what:
