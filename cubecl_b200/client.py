@@ -268,6 +268,23 @@ class ComputeClient:
         except B200Error as e:
             self._defer(e)
 
+    # -- peer-memory exchange (fused reduce + all-reduce over NVLink)
+    def p2p_export(self) -> tuple[int, bytes, int, int]:
+        """(device, ipc handle, mailbox pointer, pid) to be exchanged with the other ranks."""
+        h = (C.c_uint8 * _ffi.IPC_HANDLE_BYTES)()
+        ptr, pid = C.c_uint64(), C.c_int64()
+        _ffi.check(self._lib.b200_p2p_export(self._ctx, h, C.byref(ptr), C.byref(pid)))
+        return self.device, bytes(h), ptr.value, pid.value
+
+    def p2p_connect(self, exports) -> None:
+        """exports: list of p2p_export() tuples of every rank of the device set (any order)."""
+        exports = sorted(exports, key=lambda e: e[0])
+        ids = _ffi.int_array([e[0] for e in exports])
+        handles = (C.c_uint8 * (len(exports) * _ffi.IPC_HANDLE_BYTES)).from_buffer_copy(b"".join(e[1] for e in exports))
+        ptrs = _ffi.u64_array([e[2] for e in exports])
+        pids = (C.c_int64 * len(exports))(*[int(e[3]) for e in exports])
+        _ffi.check(self._lib.b200_p2p_connect(self._ctx, ids, len(exports), handles, ptrs, pids))
+
     # -- synthetic operands / probes
     def fill_uniform(self, handle: Handle, dtype: str, n: int, seed: int, lo: float, hi: float) -> None:
         _ffi.check(self._lib.b200_fill_uniform(self._ctx, None, DTYPES[dtype], C.c_uint64(handle.ptr), int(n), int(seed), float(lo), float(hi)))
@@ -278,6 +295,11 @@ class ComputeClient:
     def probe_wmma(self, dtype: str, n_iter: int, scratch: Handle) -> float:
         ops = C.c_double()
         _ffi.check(self._lib.b200_probe_wmma(self._ctx, None, DTYPES[dtype], int(n_iter), C.c_uint64(scratch.ptr), C.byref(ops)))
+        return ops.value
+
+    def probe_umma(self, n_iter: int, scratch: Handle) -> float:
+        ops = C.c_double()
+        _ffi.check(self._lib.b200_probe_umma(self._ctx, None, int(n_iter), C.c_uint64(scratch.ptr), C.byref(ops)))
         return ops.value
 
     def probe_memread(self, buf: Handle, nbytes: int, scratch: Handle) -> None:

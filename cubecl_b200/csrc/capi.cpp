@@ -60,7 +60,8 @@ extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
   X(cuMemcpyDtoDAsync) X(cuMemsetD32Async) X(cuMemGetInfo)                                                           \
   X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent)                                   \
   X(cuEventCreate) X(cuEventRecord) X(cuEventElapsedTime) X(cuEventDestroy) X(cuEventSynchronize)                    \
-  X(cuTensorMapEncodeTiled) X(cuGetErrorString) X(cuGetErrorName)
+  X(cuTensorMapEncodeTiled) X(cuGetErrorString) X(cuGetErrorName)                                                    \
+  X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuCtxEnablePeerAccess) X(cuDeviceCanAccessPeer)
 
 struct Driver {
   void* lib = nullptr;
@@ -226,6 +227,11 @@ struct SplitParams {
   uint64_t in, out, batch, rows, cols, in_bs, in_rs;
   uint32_t mode, pad;
 };
+struct XgpuParams {
+  uint64_t mailbox[8];
+  uint32_t rank, nranks, epoch, pad;
+};
+static constexpr size_t kMailboxBytes = 4096;
 static constexpr uint32_t kWsMaxBlocks = 4096;
 static constexpr uint32_t kWsTicketOffset = kWsMaxBlocks * 4 + kWsMaxBlocks * 8;
 static constexpr size_t kWsBytes = kWsTicketOffset + 256;
@@ -239,6 +245,14 @@ struct PoolBlock {
 struct CommState {
   ncclComm_t comm = nullptr;
   int rank = -1, n = 0;
+};
+
+// Peer-memory exchange state for one device set (fused reduce + all-reduce over NVLink).
+struct P2PState {
+  uint64_t mailbox[8] = {0};
+  int rank = -1, n = 0;
+  uint32_t epoch = 0;
+  std::vector<CUdeviceptr> opened;  // IPC mappings to close
 };
 
 struct b200_ctx {
@@ -259,6 +273,8 @@ struct b200_ctx {
   std::unordered_map<CUstream, CUdeviceptr> reduce_ws;
   std::map<std::string, CUtensorMap> tmap_cache;
   std::map<std::vector<int>, CommState> comms;
+  std::map<std::vector<int>, P2PState> p2p;
+  CUdeviceptr mailbox = 0;
   std::unordered_map<std::string, std::string> options;
   uint64_t launches = 0;
 };
@@ -367,6 +383,9 @@ extern "C" int b200_destroy(b200_ctx* c) {
     g_drv.cuCtxSynchronize_p();
     for (auto& kv : c->comms)
       if (kv.second.comm && g_nccl.ok) g_nccl.CommDestroy(kv.second.comm);
+    for (auto& kv : c->p2p)
+      for (CUdeviceptr q : kv.second.opened) g_drv.cuIpcCloseMemHandle_p(q);
+    if (c->mailbox) g_drv.cuMemFree_p(c->mailbox);
     for (auto& kv : c->blocks) g_drv.cuMemFree_p(kv.first);
     for (auto& kv : c->reduce_ws) g_drv.cuMemFree_p(kv.second);
     for (auto& kv : c->pinned) g_drv.cuMemFreeHost_p(kv.first);
@@ -1116,6 +1135,113 @@ extern "C" int b200_sync_collective(b200_ctx* c, b200_stream compute) {
   return B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ peer-memory exchange
+#include <unistd.h>
+
+static int ensure_mailbox(b200_ctx* c) {
+  if (c->mailbox) return B200_OK;
+  CU_CHECK(g_drv.cuMemAlloc_p(&c->mailbox, kMailboxBytes));
+  CU_CHECK(g_drv.cuMemsetD32Async_p(c->mailbox, 0, kMailboxBytes / 4, c->stream));
+  CU_CHECK(g_drv.cuStreamSynchronize_p(c->stream));
+  return B200_OK;
+}
+
+extern "C" int b200_p2p_export(b200_ctx* c, void* ipc_handle64, uint64_t* local_ptr, int64_t* pid) {
+  CTX_ENTER(c);
+  if (!ipc_handle64 || !local_ptr || !pid) return fail(B200_ERR_INVALID_ARG, "p2p_export: null argument");
+  int rc = ensure_mailbox(c);
+  if (rc) return rc;
+  CUipcMemHandle h;
+  static_assert(sizeof(CUipcMemHandle) == B200_IPC_HANDLE_BYTES, "IPC handle size");
+  CU_CHECK(g_drv.cuIpcGetMemHandle_p(&h, c->mailbox));
+  memcpy(ipc_handle64, &h, sizeof(h));
+  *local_ptr = c->mailbox;
+  *pid = static_cast<int64_t>(getpid());
+  return B200_OK;
+}
+
+extern "C" int b200_p2p_connect(b200_ctx* c, const int* device_ids, int n, const void* ipc_handles, const uint64_t* local_ptrs,
+                                const int64_t* pids) {
+  CTX_ENTER(c);
+  if (!device_ids || n < 1 || n > 8 || !ipc_handles || !local_ptrs || !pids)
+    return fail(B200_ERR_INVALID_ARG, "p2p_connect: bad arguments (1..8 devices)");
+  int rc = ensure_mailbox(c);
+  if (rc) return rc;
+  // the arrays are indexed like device_ids; ranks follow the SORTED device set (same keying as b200_comm_init)
+  std::vector<int> key = sorted_ids(device_ids, n);
+  if (c->p2p.count(key)) return B200_OK;
+  P2PState st;
+  st.n = n;
+  for (int r = 0; r < n; ++r) {
+    int src = -1;
+    for (int j = 0; j < n; ++j)
+      if (device_ids[j] == key[r]) src = j;
+    if (key[r] == c->device) {
+      st.rank = r;
+      st.mailbox[r] = c->mailbox;
+      continue;
+    }
+    if (pids[src] == static_cast<int64_t>(getpid())) {
+      // same process (the reference's one-process model): enable peer access to that device's primary context
+      CUdevice pd;
+      CUcontext pctx;
+      CU_CHECK(g_drv.cuDeviceGet_p(&pd, key[r]));
+      int can = 0;
+      CU_CHECK(g_drv.cuDeviceCanAccessPeer_p(&can, c->dev, pd));
+      if (!can) return fail(B200_ERR_UNSUPPORTED, "p2p_connect: device %d cannot access device %d", c->device, key[r]);
+      CU_CHECK(g_drv.cuDevicePrimaryCtxRetain_p(&pctx, pd));
+      CUresult r2 = g_drv.cuCtxEnablePeerAccess_p(pctx, 0);
+      g_drv.cuDevicePrimaryCtxRelease_p(pd);
+      if (r2 != CUDA_SUCCESS && r2 != CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED)
+        return fail(map_cu(r2), "cuCtxEnablePeerAccess(%d) failed: %s", key[r], cu_err(r2));
+      st.mailbox[r] = local_ptrs[src];
+    } else {
+      CUipcMemHandle h;
+      memcpy(&h, static_cast<const char*>(ipc_handles) + static_cast<size_t>(src) * B200_IPC_HANDLE_BYTES, sizeof(h));
+      CUdeviceptr mapped = 0;
+      CUresult r2 = g_drv.cuIpcOpenMemHandle_p(&mapped, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+      if (r2 != CUDA_SUCCESS) return fail(map_cu(r2), "cuIpcOpenMemHandle(device %d) failed: %s", key[r], cu_err(r2));
+      st.opened.push_back(mapped);
+      st.mailbox[r] = mapped;
+    }
+  }
+  if (st.rank < 0) return fail(B200_ERR_INVALID_ARG, "p2p_connect: device %d is not in the device set", c->device);
+  c->p2p[key] = st;
+  return B200_OK;
+}
+
+extern "C" int b200_reduce_all_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in,
+                                      b200_dptr out, uint64_t n, const int* device_ids, int ndev) {
+  CTX_ENTER(c);
+  if (op != B200_REDUCE_SUM) return fail(B200_ERR_UNSUPPORTED, "reduce_all_reduce: only SUM is fused");
+  if (in_dtype != B200_F32) return fail(B200_ERR_UNSUPPORTED, "reduce_all_reduce: only f32 input is fused");
+  if (!device_ids || ndev < 1) return fail(B200_ERR_INVALID_ARG, "reduce_all_reduce: bad device set");
+  if (!in || !out || n == 0) return fail(B200_ERR_INVALID_ARG, "reduce_all_reduce: null pointer or empty input");
+  auto it = c->p2p.find(sorted_ids(device_ids, ndev));
+  if (it == c->p2p.end()) return fail(B200_ERR_COMM, "reduce_all_reduce: device set not connected (call b200_p2p_connect)");
+  P2PState& st = it->second;
+  CUstream cs = resolve_stream(c, s);
+  CUfunction f;
+  int rc = get_func(c, "reduce_all_sum_f32_xgpu", &f);
+  if (rc) return rc;
+  CUdeviceptr ws;
+  rc = reduce_workspace(c, cs, &ws);
+  if (rc) return rc;
+  unsigned threads = (unsigned)std::min(512, std::max(32, atoi(opt(c, "reduce.threads", "512").c_str()))) / 32 * 32;
+  unsigned bps = (unsigned)std::max(1, atoi(opt(c, "reduce.blocks_per_sm", "4").c_str()));
+  const uint64_t want = (n / 4 + threads - 1) / threads;
+  unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)c->props.num_sms * bps, kWsMaxBlocks)));
+  ReduceParams p{in, out, ws, 1, n, 1, 1.0f, 0};
+  XgpuParams xg;
+  memset(&xg, 0, sizeof(xg));
+  for (int r = 0; r < st.n; ++r) xg.mailbox[r] = st.mailbox[r];
+  xg.rank = (uint32_t)st.rank;
+  xg.nranks = (uint32_t)st.n;
+  xg.epoch = ++st.epoch;  // every rank calls in the same order (collective semantics), so epochs agree
+  void* args[] = {&p, &xg};
+  return launch(c, f, grid, 1, 1, threads, 0, 1, cs, args);
+}
+
 // ================================================================================================ generators / probes
 static int launch_fill(b200_ctx* c, b200_stream s, int dtype, uint64_t out, uint64_t n, FillParams p) {
   if (!dt_tag(dtype)) return fail(B200_ERR_UNSUPPORTED, "fill: dtype %d unsupported", dtype);
@@ -1154,6 +1280,21 @@ extern "C" int b200_probe_wmma(b200_ctx* c, b200_stream s, b200_dtype dtype, uin
   void* args[] = {&sp, &n_iter};
   rc = launch(c, f, grid, 1, 1, block, 0, 1, resolve_stream(c, s), args);
   if (!rc && ops) *ops = static_cast<double>(grid) * (block / 32) * 2.0 * 16 * 16 * 16 * n_iter;
+  return rc;
+}
+
+extern "C" int b200_probe_umma(b200_ctx* c, b200_stream s, uint32_t n_iter, b200_dptr scratch, double* ops) {
+  CTX_ENTER(c);
+  CUfunction f;
+  int rc = get_func(c, "umma_probe_bf16_2sm", &f);
+  if (rc) return rc;
+  const unsigned smem = 32768 + 1024 + 64;
+  CU_CHECK(g_drv.cuFuncSetAttribute_p(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+  const unsigned clusters = (unsigned)std::max(1, c->props.num_sms / 2);
+  uint64_t sp = scratch;
+  void* args[] = {&sp, &n_iter};
+  rc = launch(c, f, clusters * 2, 1, 1, 256, smem, 2, resolve_stream(c, s), args);
+  if (!rc && ops) *ops = static_cast<double>(clusters) * n_iter * 4.0 * 2.0 * 256 * 256 * 16;
   return rc;
 }
 

@@ -316,3 +316,55 @@ GEMM_KERNEL(gemm_f16_f32_1sm_n128_bk, 1, 128, false, KIND_F16, OUT_F32, 6)
 GEMM_KERNEL(gemm_f16_f32_1sm_n128_bn, 1, 128, true, KIND_F16, OUT_F32, 6)
 GEMM_KERNEL(gemm_tf32_f32_1sm_n128_bk, 1, 128, false, KIND_TF32, OUT_F32, 6)
 GEMM_KERNEL(gemm_tf32_f32_1sm_n128_bn, 1, 128, true, KIND_TF32, OUT_F32, 6)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/
+// compute_cmma.rs:16,41-42: ops = cubes * planes * 2mnk * n_iter) moved to the 5th-gen tensor cores -- every CTA pair
+// issues n_iter x 4 back-to-back UMMA 256x256x16 (bf16 -> f32 in TMEM) on operands resident in shared memory (all ones),
+// so it measures the MMA pipe with no TMA / HBM in the loop.  out[cluster] = acc[0][0] = 64 * n_iter.
+extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_bf16_2sm(float* out, uint32_t n_iter) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sa = smem_base, sb = smem_base + 16384;
+  const uint32_t done_bar = smem_base + 32768, tmem_slot = done_bar + 8;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool leader = cluster_ctarank() == 0;
+  for (uint32_t i = threadIdx.x; i < 32768 / 4; i += blockDim.x)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_base + 4 * i), "r"(0x3F803F80u) : "memory");  // bf16 1.0 pairs
+  fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+  if (warp == 1 && lane == 0) {
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(tmem_slot, 256);
+    tmem_relinquish<2>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (warp == 1 && leader && lane == 0) {
+    const uint64_t a_desc = make_smem_desc_sw128(sa, 16, 1024), b_desc = make_smem_desc_sw128(sb, 16, 1024);
+    constexpr uint32_t idesc = make_idesc(KIND_BF16, 0, 0, 256, 256);
+    for (uint32_t i = 0; i < n_iter; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss<2, KIND_BF16>(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+    }
+    umma_commit<2>(done_bar);
+  }
+  __syncwarp();
+  mbar_wait(done_bar, 0);
+  tcgen05_fence_after();
+  if (warp == 4) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base, v);
+    tmem_ld_wait();
+    if (lane == 0 && leader) out[cluster_id_x()] = __uint_as_float(v[0]);
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, 256);
+}

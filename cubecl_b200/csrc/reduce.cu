@@ -25,6 +25,14 @@ struct ReduceParams {
   uint32_t pad;
 };
 
+// Cross-GPU exchange fused into the grid stage (one kernel = local reduce + all-reduce of the scalar over NVLink peer
+// memory).  Every rank owns a mailbox `uint64 slots[2][8]` (epoch parity x source rank) that its peers can write; an entry
+// is (epoch << 32) | f32 bits, stored with ONE 64-bit system-scope store so value and flag arrive together.
+struct XgpuParams {
+  uint64_t mailbox[8];   // device pointers of every rank's mailbox (own included), indexed by rank
+  uint32_t rank, nranks, epoch, pad;
+};
+
 enum : int { OP_SUM = 0, OP_PROD = 1, OP_MAX = 2, OP_MIN = 3, OP_ARGMAX = 4, OP_ARGMIN = 5 };
 enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
 
@@ -198,8 +206,22 @@ __device__ __forceinline__ float arg_identity(int op) { return op == OP_ARGMAX ?
 // Grid-stride over 128-bit (VEC elements) vectors, UNROLL independent loads in flight per thread, one accumulator per
 // load slot and vector lane.  Per-block partial -> workspace; the last block to finish (ticket) reduces the partials in
 // block order (deterministic for a fixed grid) and writes out[0] * scale.
-template <int OP, int DT, int UNROLL, bool WIDE /* 256-bit loads, f32 only */>
-__device__ __forceinline__ void reduce_all_body(const ReduceParams& p) {
+__device__ __forceinline__ void st_sys_u64(uint64_t addr, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_sys_u64(uint64_t addr) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int OP, int DT, int UNROLL, bool WIDE /* 256-bit loads, f32 only */, bool XGPU = false>
+__device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const XgpuParams* xg = nullptr) {
   using E = Elem<DT>;
   constexpr int VEC = WIDE ? 8 : E::VEC;
   __shared__ float s_red[kMaxWarps];
@@ -294,9 +316,37 @@ __device__ __forceinline__ void reduce_all_body(const ReduceParams& p) {
         d = (static_cast<int>(threadIdx.x) < nwarps) ? s_dred[threadIdx.x] : 0.0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) d += __shfl_down_sync(0xffffffffu, d, off);
-        if (threadIdx.x == 0) {
-          reinterpret_cast<float*>(p.out)[0] = static_cast<float>(d * static_cast<double>(p.scale));
-          *ticket = 0;  // ready for the next launch on this stream
+        if constexpr (!XGPU) {
+          if (threadIdx.x == 0) {
+            reinterpret_cast<float*>(p.out)[0] = static_cast<float>(d * static_cast<double>(p.scale));
+            *ticket = 0;  // ready for the next launch on this stream
+          }
+        } else {
+          // ---- fused all-reduce: publish this rank's scalar into every peer's mailbox, gather the others, sum in rank order
+          __shared__ float s_peer[8];
+          d = __shfl_sync(0xffffffffu, d, 0);
+          const float mine = static_cast<float>(d * static_cast<double>(p.scale));
+          const uint32_t slot_base = (xg->epoch & 1u) * 8u;
+          if (threadIdx.x < xg->nranks) {
+            const uint32_t peer = threadIdx.x;
+            st_sys_u64(xg->mailbox[peer] + (slot_base + xg->rank) * 8ull,
+                       (static_cast<uint64_t>(xg->epoch) << 32) | __float_as_uint(mine));
+            const uint64_t src = xg->mailbox[xg->rank] + (slot_base + peer) * 8ull;
+            const uint64_t t0 = globaltimer_ns();
+            uint64_t w = ld_sys_u64(src);
+            while (static_cast<uint32_t>(w >> 32) != xg->epoch) {
+              if (globaltimer_ns() - t0 > 4000000000ull) asm volatile("trap;");  // a peer never arrived: fail loudly
+              w = ld_sys_u64(src);
+            }
+            s_peer[peer] = __uint_as_float(static_cast<uint32_t>(w));
+          }
+          __syncwarp();
+          if (threadIdx.x == 0) {
+            double total = 0.0;
+            for (uint32_t r = 0; r < xg->nranks; ++r) total += static_cast<double>(s_peer[r]);  // same order on every rank
+            reinterpret_cast<float*>(p.out)[0] = static_cast<float>(total);
+            *ticket = 0;
+          }
         }
       }
     } else {
@@ -540,6 +590,12 @@ ALL_DTYPES(ALL_SHAPES, max, OP_MAX)
 ALL_DTYPES(ALL_SHAPES, min, OP_MIN)
 ALL_DTYPES(ALL_ARG_SHAPES, argmax, OP_ARGMAX)
 ALL_DTYPES(ALL_ARG_SHAPES, argmin, OP_ARGMIN)
+
+// local sum + cross-GPU all-reduce of the scalar in one launch (see XgpuParams)
+extern "C" __global__ void __launch_bounds__(512) reduce_all_sum_f32_xgpu(const __grid_constant__ ReduceParams p,
+                                                                          const __grid_constant__ XgpuParams xg) {
+  reduce_all_body<OP_SUM, DT_F32, 8, false, true>(p, &xg);
+}
 
 // tuning variants of the headline kernel (f32 sum over all elements); the host picks one by name.
 REDUCE_ALL(reduce_all_sum_f32_u4, OP_SUM, DT_F32, 4, false)

@@ -76,3 +76,14 @@ def max_over_ranks(value: float, dist=None, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def connect_p2p(client, dist=None) -> list[int]:
+    """Exchange every rank's mailbox export (all_gather_object) and connect; returns the device set."""
+    if dist is None:
+        import torch.distributed as dist  # type: ignore[no-redef]
+    mine = client.p2p_export()
+    everyone = [None] * dist.get_world_size()
+    dist.all_gather_object(everyone, mine)
+    client.p2p_connect(everyone)
+    return sorted(e[0] for e in everyone)

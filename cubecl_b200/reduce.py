@@ -51,3 +51,19 @@ def launch_alloc(client: ComputeClient, input: TensorHandle, axis, op: str = "su
     out = TensorHandle.empty_contiguous(client, output_shape(input.shape, axis), output_dtype(op))
     launch(client, input, out, axis, op)
     return out
+
+
+def launch_all_reduce(client: ComputeClient, input: TensorHandle, output: TensorHandle, device_ids) -> None:
+    """Sum of every element of `input` on every rank of `device_ids`, summed over ranks, written to output[0] on each rank:
+    `reduce::launch` followed by `client.all_reduce(.., Sum)` (client.rs:790) as ONE kernel -- the grid stage of the
+    reduce exchanges the per-rank scalar through NVLink peer memory (csrc/reduce.cu, XgpuParams).  Collective call."""
+    try:
+        if input.dtype != "f32" or output.dtype != "f32":
+            raise B200Error(7, "launch_all_reduce: f32 in, f32 out")
+        if not input.is_contiguous():
+            raise B200Error(7, "launch_all_reduce: input must be contiguous")
+        ids = sorted(int(d) for d in device_ids)
+        _ffi.check(client._lib.b200_reduce_all_reduce(client._ctx, None, _ffi.REDUCE_SUM, DTYPES["f32"], C.c_uint64(input.handle.ptr),
+                                                      C.c_uint64(output.handle.ptr), input.size(), _ffi.int_array(ids), len(ids)))
+    except B200Error as e:
+        client._defer(e)

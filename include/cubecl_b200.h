@@ -146,6 +146,22 @@ int b200_all_reduce(b200_ctx* ctx, b200_stream compute, b200_dptr src, b200_dptr
 /* Make `compute` wait for everything issued on the comm stream (server.rs:782-798). */
 int b200_sync_collective(b200_ctx* ctx, b200_stream compute);
 
+/* ---- fused reduce + all-reduce over NVLink peer memory (no NCCL on the data path) -----------------------------------
+ * The reduce path's exchange step is one f32 per rank.  Instead of reduce kernel -> event -> ncclAllReduce -> event
+ * (client.rs:790 + server.rs:705-798), the LAST block of the reduce kernel stores this rank's scalar (value+epoch in one
+ * 64-bit system-scope store) into every peer's mailbox and gathers theirs, so local reduce + exchange are ONE launch.
+ * Setup: every rank exports its mailbox, the handles are exchanged out of band, every rank connects.  Ranks = position in
+ * the sorted device set (as for b200_comm_init).  Works across processes (CUDA IPC) and inside one process (peer access). */
+#define B200_IPC_HANDLE_BYTES 64
+int b200_p2p_export(b200_ctx* ctx, void* ipc_handle64, uint64_t* local_ptr, int64_t* pid);
+/* arrays are indexed like device_ids: n x 64-byte handles, n pointers, n pids (as returned by b200_p2p_export on each rank) */
+int b200_p2p_connect(b200_ctx* ctx, const int* device_ids, int n, const void* ipc_handles, const uint64_t* local_ptrs,
+                     const int64_t* pids);
+/* out[0] (on every rank) = sum over ranks of sum(in[0..n)).  Collective: every rank of the set must call it, in the same
+ * order; a missing peer trips the kernel's 4 s deadline (device trap -> B200_ERR_UNHEALTHY at sync).  SUM of F32 only. */
+int b200_reduce_all_reduce(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
+                           uint64_t n, const int* device_ids, int ndev);
+
 /* ---- synthetic operands + reference-equivalent probes (examples/throughput) ----------------------------------------- */
 /* out[i] = lo + u(seed,i) * (hi - lo), u in [0,1) from a counter hash the host can reproduce (cubecl_b200/synth.py);
  * mode 1: out[i] = i % modulus. */
@@ -154,6 +170,10 @@ int b200_fill_modulo(b200_ctx* ctx, b200_stream s, b200_dtype dtype, b200_dptr o
 /* compute_cmma_throughput as CubeCL would JIT it today (wmma 16x16x16): launches grid = SMs*32, block = 256, `n_iter`
  * dependent mma_sync per plane; *ops = cubes * planes * 2*m*n*k * n_iter (compute_cmma.rs:16,41-42). dtype F16 or BF16. */
 int b200_probe_wmma(b200_ctx* ctx, b200_stream s, b200_dtype dtype, uint32_t n_iter, b200_dptr scratch_1k, double* ops);
+/* The same accounting on the 5th-gen tensor cores: every CTA pair issues n_iter x 4 dependent UMMA 256x256x16 (bf16->f32,
+ * TMEM accumulator) on smem-resident operands; *ops = pairs * n_iter * 4 * 2*256*256*16.  scratch: >= 4 * num_sms/2 bytes;
+ * scratch[pair] = 64 * n_iter afterwards. */
+int b200_probe_umma(b200_ctx* ctx, b200_stream s, uint32_t n_iter, b200_dptr scratch, double* ops);
 /* memory_read_throughput with float_4 lines over `bytes` of `buf` (memory_read.rs:68-154): grid = SMs*32, block = 256. */
 int b200_probe_memread(b200_ctx* ctx, b200_stream s, b200_dptr buf, uint64_t bytes, b200_dptr scratch_16);
 

@@ -4,7 +4,7 @@ import threading
 import numpy as np
 import pytest
 
-from cubecl_b200 import ComputeClient, TensorHandle, synth
+from cubecl_b200 import ComputeClient, TensorHandle, reduce, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -82,3 +82,30 @@ def test_all_reduce_sync_collective(golden):
         for j, h in enumerate(handles):
             got = np.frombuffer(c.read_one(h), dtype=np.float32)
             assert np.all(got == base + j * n)
+
+
+def test_fused_reduce_all_reduce_over_peer_memory():
+    # reduce::launch + client.all_reduce(Sum) as ONE kernel: the last block exchanges the scalar through NVLink mailboxes.
+    # Same single-process, one-client-per-device shape as runtime_tests/all_reduce.rs; exact-integer data so the float
+    # summation order cannot matter (sum over ranks of sum(i % 8) + rank offsets).
+    n_dev = ComputeClient.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 devices")
+    clients = [ComputeClient.load(d) for d in range(n_dev)]
+    exports = [c.p2p_export() for c in clients]
+    for c in clients:
+        c.p2p_connect(exports)
+    ids = list(range(n_dev))
+    n = (1 << 22) + 4
+    ins, outs, expect = [], [], 0.0
+    for r, c in enumerate(clients):
+        x = ((np.arange(n) + r) % 8).astype(np.float32)
+        expect += float(x.astype(np.float64).sum())
+        ins.append(TensorHandle.from_numpy(c, x, "f32"))
+        outs.append(TensorHandle.empty_contiguous(c, [1], "f32"))
+    for rounds in range(3):  # epochs advance in lockstep; parity double-buffering of the mailbox is exercised
+        threads = [threading.Thread(target=reduce.launch_all_reduce, args=(c, ins[r], outs[r], ids)) for r, c in enumerate(clients)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        for r, c in enumerate(clients):
+            assert float(outs[r].to_numpy(c)[0]) == expect
