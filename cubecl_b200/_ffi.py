@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200_sync": (C.c_int, [_vp, _vp]),
     "b200_event_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "b200_event_record": (C.c_int, [_vp, _vp, _vp]),
+    "b200_stream_wait_event": (C.c_int, [_vp, _vp, _vp]),
     "b200_event_elapsed_ms": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
     "b200_event_destroy": (C.c_int, [_vp, _vp]),
     "b200_matmul": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,

@@ -195,13 +195,29 @@ class ComputeClient:
         addr = self._pinned.pop(arr.ctypes.data)
         _ffi.check(self._lib.b200_host_free(self._ctx, C.c_void_p(addr)))
 
-    def write_async(self, handle: Handle, host: np.ndarray, nbytes: int | None = None) -> None:
+    def write_async(self, handle: Handle, host: np.ndarray, nbytes: int | None = None, stream=None) -> None:
         n = host.nbytes if nbytes is None else nbytes
-        _ffi.check(self._lib.b200_write(self._ctx, None, C.c_uint64(handle.ptr), host.ctypes.data_as(C.c_void_p), n))
+        _ffi.check(self._lib.b200_write(self._ctx, stream, C.c_uint64(handle.ptr), host.ctypes.data_as(C.c_void_p), n))
 
-    def read_async(self, host: np.ndarray, handle: Handle, nbytes: int | None = None) -> None:
+    def read_async(self, host: np.ndarray, handle: Handle, nbytes: int | None = None, stream=None) -> None:
         n = host.nbytes if nbytes is None else nbytes
-        _ffi.check(self._lib.b200_read(self._ctx, None, host.ctypes.data_as(C.c_void_p), C.c_uint64(handle.ptr), n))
+        _ffi.check(self._lib.b200_read(self._ctx, stream, host.ctypes.data_as(C.c_void_p), C.c_uint64(handle.ptr), n))
+
+    # -- extra streams (StreamId -> CUstream, cubecl-cuda/src/compute/stream.rs:24-44); None = the client's compute stream
+    def create_stream(self):
+        s = C.c_void_p()
+        _ffi.check(self._lib.b200_stream_create(self._ctx, C.byref(s)))
+        return s
+
+    def destroy_stream(self, stream) -> None:
+        _ffi.check(self._lib.b200_stream_destroy(self._ctx, stream))
+
+    def stream_wait_event(self, stream, event) -> None:
+        """Cross-stream dependency: work queued on `stream` after this call waits for `event` (MultiStream::resolve)."""
+        _ffi.check(self._lib.b200_stream_wait_event(self._ctx, stream, event))
+
+    def sync_stream(self, stream) -> None:
+        _ffi.check(self._lib.b200_sync(self._ctx, stream))
 
     # -- sync / deferred errors
     def _defer(self, err: Exception) -> None:
@@ -225,8 +241,8 @@ class ComputeClient:
         _ffi.check(self._lib.b200_event_create(self._ctx, C.byref(e)))
         return e
 
-    def record(self, e) -> None:
-        _ffi.check(self._lib.b200_event_record(self._ctx, e, None))
+    def record(self, e, stream=None) -> None:
+        _ffi.check(self._lib.b200_event_record(self._ctx, e, stream))
 
     def elapsed_ms(self, a, b) -> float:
         ms = C.c_float()

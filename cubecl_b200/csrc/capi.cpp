@@ -584,6 +584,12 @@ extern "C" int b200_event_record(b200_ctx* c, b200_event e, b200_stream s) {
   return B200_OK;
 }
 
+extern "C" int b200_stream_wait_event(b200_ctx* c, b200_stream s, b200_event e) {
+  CTX_ENTER(c);
+  CU_CHECK(g_drv.cuStreamWaitEvent_p(resolve_stream(c, s), static_cast<CUevent>(e), 0));
+  return B200_OK;
+}
+
 extern "C" int b200_event_elapsed_ms(b200_ctx* c, b200_event a, b200_event b, float* ms) {
   CTX_ENTER(c);
   if (!ms) return fail(B200_ERR_INVALID_ARG, "null ms");

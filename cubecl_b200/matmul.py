@@ -40,7 +40,7 @@ def calculate_matmul_output(shape_lhs, shape_rhs) -> list[int]:
     return out + [shape_lhs[-2], shape_rhs[-1]]
 
 
-def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: TensorHandle) -> None:
+def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: TensorHandle, stream=None) -> None:
     """Enqueue the matmul on the client's stream.  Never raises for launch problems: errors are deferred to
     client.sync()/read_one() like the reference's launch path."""
     try:
@@ -50,7 +50,7 @@ def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: Ten
         if len(rhs.shape) != rank or len(out.shape) != rank:
             raise B200Error(6, "matmul: lhs, rhs and out must have equal rank")
         _ffi.check(client._lib.b200_matmul(
-            client._ctx, None, DTYPES[lhs.dtype], DTYPES[out.dtype],
+            client._ctx, stream, DTYPES[lhs.dtype], DTYPES[out.dtype],
             C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(out.handle.ptr), rank,
             _ffi.u64_array(lhs.shape), _ffi.u64_array(lhs.strides), _ffi.u64_array(rhs.shape), _ffi.u64_array(rhs.strides),
             _ffi.u64_array(out.shape), _ffi.u64_array(out.strides)))

@@ -30,7 +30,7 @@ def output_dtype(op: str) -> str:
     return "u32" if op in ("argmax", "argmin") else "f32"
 
 
-def launch(client: ComputeClient, input: TensorHandle, output: TensorHandle, axis, op: str = "sum") -> None:
+def launch(client: ComputeClient, input: TensorHandle, output: TensorHandle, axis, op: str = "sum", stream=None) -> None:
     """Enqueue the reduction on the client's stream; errors are deferred to sync()/read_one()."""
     try:
         if op not in OPS:
@@ -41,7 +41,7 @@ def launch(client: ComputeClient, input: TensorHandle, output: TensorHandle, axi
             raise B200Error(6, f"reduce: output dtype must be {output_dtype(op)} for op {op}")
         rank = len(input.shape)
         ax = -1 if axis is None else axis % rank
-        _ffi.check(client._lib.b200_reduce(client._ctx, None, OPS[op], DTYPES[input.dtype], C.c_uint64(input.handle.ptr),
+        _ffi.check(client._lib.b200_reduce(client._ctx, stream, OPS[op], DTYPES[input.dtype], C.c_uint64(input.handle.ptr),
                                            C.c_uint64(output.handle.ptr), rank, _ffi.u64_array(input.shape), ax))
     except B200Error as e:
         client._defer(e)

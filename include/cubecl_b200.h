@@ -110,6 +110,7 @@ int b200_stream_destroy(b200_ctx* ctx, b200_stream s);
 int b200_sync(b200_ctx* ctx, b200_stream s);
 int b200_event_create(b200_ctx* ctx, b200_event* out);
 int b200_event_record(b200_ctx* ctx, b200_event e, b200_stream s);
+int b200_stream_wait_event(b200_ctx* ctx, b200_stream s, b200_event e);   /* cross-stream dependency (MultiStream::resolve, stream/event.rs:220) */
 int b200_event_elapsed_ms(b200_ctx* ctx, b200_event start, b200_event end, float* ms);
 int b200_event_destroy(b200_ctx* ctx, b200_event e);
 

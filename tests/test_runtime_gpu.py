@@ -46,6 +46,12 @@ def test_reference_probes_run(client):
     client.sync()
     assert ops == client.properties["num_streaming_multiprocessors"] * 32 * 8 * 2 * 16 ** 3 * 4
     assert np.all(np.frombuffer(client.read_one(scratch), dtype=np.float16)[:256] == 64.0)
+    # the same accounting on tcgen05: 4 UMMAs of K=16 per iteration on all-ones operands -> acc = 64 * n_iter
+    ops = client.probe_umma(16, scratch)
+    client.sync()
+    pairs = client.properties["num_streaming_multiprocessors"] // 2
+    assert ops == pairs * 16 * 4 * 2 * 256 * 256 * 16
+    assert np.all(np.frombuffer(client.read_one(scratch), dtype=np.float32)[:pairs] == 1024.0)
     buf = client.empty(1 << 24)
     client.fill_modulo(buf, "f32", 1 << 22, 2)
     client.probe_memread(buf, 1 << 24, scratch)

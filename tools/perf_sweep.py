@@ -93,6 +93,15 @@ if "probes" in what:
 
         ms = time_ms(c, run, iters=5, warm=2)
         print(f"reference-equivalent wmma probe ({dt}, 16x16x16, grid SMs*32 x 256): {ops[0] / ms / 1e9:8.1f} TFLOP/s")
+    ops = [0.0]
+
+    def run_u():
+        ops[0] = c.probe_umma(8192, scratch)
+
+    ms = time_ms(c, run_u, iters=5, warm=2)
+    import numpy as _np
+    vals = _np.frombuffer(c.read_one(scratch), dtype=_np.float32)[:4]
+    print(f"tcgen05 peak probe (UMMA 256x256x16 bf16, 74 CTA pairs, smem-resident): {ops[0] / ms / 1e9:8.1f} TFLOP/s  acc[0]={vals[0]} (expect {64 * 8192})")
     buf = c.empty(512 << 20)
     c.fill_modulo(buf, "f32", (512 << 20) // 4, 8)
     ms = time_ms(c, lambda: c.probe_memread(buf, 512 << 20, scratch), iters=10, warm=2)
