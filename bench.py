@@ -284,10 +284,21 @@ def main():
         "gpu_launches": launches * world,
         "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": per_gpu_tflops / pk["bf16_tflops"], "traffic": traffic.get("gemm_bf16_8192_dram_bytes"),
-                     "peak_source": pk["source"] + " (cuBLAS bf16 burst)", "kernel": "gemm_bf16_bf16_2sm_n256_bn",
+                     "peak_source": pk["source"] + " (cuBLAS bf16 burst)", "kernel": "gemm_bf16_bf16_2sm_n256_kn",
                      "algorithmic_flops_per_launch": FLOPS_MM},
         "clocks": clocks,
     }
+
+    # ------------------------------------------------------------------ context: the same kernel held for ~1 s (power-capped regime)
+    if not args.quick:
+        n_sus = max(200, int(1000.0 / per_launch_ms))
+        with ClockSampler(e.local_rank) as cs2:
+            ms_sus, _ = timed(mm_step, n_sus, 3)
+        cl2 = cs2.summary()
+        line["sustained"] = {"value": world * FLOPS_MM * n_sus / (ms_sus * 1e-3) / 1e12, "unit": "TFLOP/s", "launches": n_sus,
+                             "seconds": ms_sus * 1e-3, "frac_of_sustained_peak": FLOPS_MM * n_sus / (ms_sus * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                             "peak_sustained": pk["bf16_tflops_sustained"], "clocks": cl2,
+                             "note": "back-to-back launches for ~1 s: the 1 kW power cap pulls SM clocks to ~1.4 GHz (ncu: 1.41 GHz, tensor pipe 92 % active)"}
 
     # ------------------------------------------------------------------ e2e: host buffers through the public API
     nbytes = N_MM * N_MM * 2

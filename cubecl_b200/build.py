@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
     LIBDIR.mkdir(exist_ok=True)
     sources = [p for p in CSRC.iterdir() if p.suffix in (".cu", ".cuh", ".cpp", ".h")]
-    sources.append(ROOT / "include" / "cubecl_b200.h")
+    sources += [ROOT / "include" / "cubecl_b200.h", ROOT / "include" / "cubecl_b200.hpp", ROOT / "examples" / "sum_things.cpp"]
     stamp = BUILD / "stamp.txt"
     digest = _digest(sources)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
@@ -85,6 +85,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     embed.write_text("".join(asm))
     _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function", "-I", _cuda_include(),
           str(CSRC / "capi.cpp"), str(embed), "-ldl", "-lpthread", "-o", str(LIB)])
+    # C++ host-layer example (include/cubecl_b200.hpp): compiled here so the header cannot rot; run on the GPU box by
+    # tests/test_cpp_host_gpu.py
+    _run(["g++", "-O2", "-std=c++17", "-Wall", "-I", str(ROOT / "include"), str(ROOT / "examples" / "sum_things.cpp"),
+          "-L", str(LIBDIR), "-lcubecl_b200", f"-Wl,-rpath,{LIBDIR}", "-Wl,-rpath,$ORIGIN", "-o", str(LIBDIR / "sum_things_cpp")])
     stamp.write_text(digest)
     return LIB
 

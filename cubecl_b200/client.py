@@ -322,6 +322,13 @@ class ComputeClient:
         _ffi.check(self._lib.b200_probe_memread(self._ctx, None, C.c_uint64(buf.ptr), int(nbytes), C.c_uint64(scratch.ptr)))
 
 
+    def probe_memwrite(self, dst: Handle, nbytes: int) -> None:
+        _ffi.check(self._lib.b200_probe_memwrite(self._ctx, None, C.c_uint64(dst.ptr), int(nbytes)))
+
+    def probe_memcopy(self, dst: Handle, src: Handle, nbytes: int) -> None:
+        _ffi.check(self._lib.b200_probe_memcopy(self._ctx, None, C.c_uint64(dst.ptr), C.c_uint64(src.ptr), int(nbytes)))
+
+
 def contiguous_strides(shape: Sequence[int]) -> list[int]:
     strides, acc = [], 1
     for s in reversed(shape):

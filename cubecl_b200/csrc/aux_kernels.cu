@@ -90,6 +90,7 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
 // mode 0 (operand whose K is innermost, [rows, K]):  out[b][r][3K] = [hi | hi | lo]   (lhs)
 // mode 1 (same layout, the other operand)         :  out[b][r][3K] = [hi | lo | hi]   (rhs stored [N,K])
 // mode 2 (rhs stored row-major [K, N])            :  out[b][3K][N] = [hi ; lo ; hi] stacked along K
+// mode 3 (lhs stored [K, M], transposed view)     :  out[b][3K][M] = [hi ; hi ; lo] stacked along K
 // A tf32 GEMM over K' = 3K then computes hi*hi + hi*lo + lo*hi with f32 accumulation.
 struct SplitParams {
   uint64_t in, out;
@@ -109,6 +110,8 @@ extern "C" __global__ void __launch_bounds__(256) split_tf32(const __grid_consta
     float* o = reinterpret_cast<float*>(p.out) + b * 3 * per;
     if (p.mode == 2) {
       o[rem] = hi; o[per + rem] = lo; o[2 * per + rem] = hi;
+    } else if (p.mode == 3) {
+      o[rem] = hi; o[per + rem] = hi; o[2 * per + rem] = lo;
     } else {
       float* row = o + r * 3 * p.cols;
       row[c] = hi;
@@ -160,4 +163,28 @@ extern "C" __global__ void __launch_bounds__(256) memread_probe_vec4(const float
     }
   }
   if (pos == 0 || acc.x == -1.2345e33f) out[0] = acc;  // the data-dependent arm keeps every unit's loads alive
+}
+
+// memory_write_throughput (crates/cubecl-std/src/throughput/runners/memory_write.rs): the copy kernel with the load
+// removed -- every unit writes one constant float_4 line per step, coalesced, `steps` passes over `lines`.
+extern "C" __global__ void __launch_bounds__(256) memwrite_probe_vec4(float4* out, uint64_t lines, uint32_t steps) {
+  const uint64_t pos = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+  for (uint32_t s = 0; s < steps; ++s) {
+    const uint64_t idx = pos + s * stride;
+    if (idx < lines) out[idx] = v;
+  }
+}
+
+// memory_direct (runners/memory_direct.rs): a line in and a line back out; ops_count counts BOTH directions, which is
+// the convention of the copy roofline (and of MEASURED_PEAKS.json's hbm_gbs).
+extern "C" __global__ void __launch_bounds__(256) memcopy_probe_vec4(const float4* __restrict__ in, float4* out,
+                                                                      uint64_t lines, uint32_t steps) {
+  const uint64_t pos = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint32_t s = 0; s < steps; ++s) {
+    const uint64_t idx = pos + s * stride;
+    if (idx < lines) out[idx] = in[idx];
+  }
 }

@@ -692,26 +692,27 @@ static int launch_simt(b200_ctx* c, CUstream st, const GemmProblem& g) {
   return launch(c, f, (unsigned)((g.N + 15) / 16), (unsigned)((g.M + 15) / 16), (unsigned)g.batch, 256, 0, 1, st, args);
 }
 
-static bool tma_ok(const GemmProblem& g, bool* b_mn) {
+static bool tma_ok(const GemmProblem& g, bool* a_mn, bool* b_mn) {
   const size_t esz = dtype_size(g.in_dtype);
   auto al16 = [&](uint64_t elems) { return (elems * esz) % 16 == 0; };
   if (g.M >= (1ull << 31) || g.N >= (1ull << 31) || g.K >= (1ull << 31) || g.batch >= (1ull << 31)) return false;
-  // lhs must be K-major
-  if (!(g.a_sk == 1 || g.K == 1)) return false;
-  if (g.a % 16 || !al16(g.a_sb)) return false;
-  if (g.M > 1 && (!al16(g.a_sm) || g.a_sm < g.K)) return false;
-  if (g.b % 16 || !al16(g.b_sb)) return false;
+  if (g.a % 16 || !al16(g.a_sb) || g.b % 16 || !al16(g.b_sb)) return false;
+  // lhs: K-major ([M,K] rows) or MN-major ([K,M] rows, i.e. a transposed view)
+  if ((g.a_sk == 1 || g.K == 1) && (g.M == 1 || (al16(g.a_sm) && g.a_sm >= g.K))) { *a_mn = false; }
+  else if ((g.a_sm == 1 || g.M == 1) && (g.K == 1 || (al16(g.a_sk) && g.a_sk >= g.M))) { *a_mn = true; }
+  else return false;
+  // rhs: K-major ([N,K] rows, transposed view) or MN-major ([K,N] rows)
   if ((g.b_sk == 1 || g.K == 1) && (g.N == 1 || (al16(g.b_sn) && g.b_sn >= g.K))) { *b_mn = false; }
   else if ((g.b_sn == 1 || g.N == 1) && (g.K == 1 || (al16(g.b_sk) && g.b_sk >= g.N))) { *b_mn = true; }
   else return false;
-  // a dimension of extent 1 still needs a 16-byte-multiple stride in the descriptor; encode_tmap substitutes one
   if (!(g.o_sn == 1 || g.N == 1)) return false;
-  // TMA stride limit 2^40 bytes
-  if (g.a_sm * esz >= (1ull << 40) || g.a_sb * esz >= (1ull << 40) || g.b_sb * esz >= (1ull << 40)) return false;
+  // TMA stride limit 2^40 bytes; a dimension of extent 1 gets a substituted 16-byte-multiple stride in encode
+  const uint64_t lim = 1ull << 40;
+  if (g.a_sm * esz >= lim || g.a_sk * esz >= lim || g.a_sb * esz >= lim || g.b_sk * esz >= lim || g.b_sn * esz >= lim || g.b_sb * esz >= lim) return false;
   return true;
 }
 
-static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool b_mn) {
+static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
   const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
   const char* in_tag = g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : "tf32";
   const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : "f32";
@@ -733,7 +734,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool b
   if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant", forced.c_str());
   const GemmVariant& v = *best;
 
-  const std::string name = std::string("gemm_") + in_tag + "_" + out_tag + "_" + v.tag + (b_mn ? "_bn" : "_bk");
+  const std::string name = std::string("gemm_") + in_tag + "_" + out_tag + "_" + v.tag + (a_mn ? "_m" : "_k") + (b_mn ? "n" : "k");
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;
@@ -746,8 +747,15 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool b
   const bool a_bcast = (g.a_sb == 0 || g.batch == 1), b_bcast = (g.b_sb == 0 || g.batch == 1);
   CUtensorMap ta, tb;
   auto pad16 = [&](uint64_t elems) { const uint64_t q = 16 / esz; return (elems + q - 1) / q * q; };
-  const uint64_t a_sm = g.M > 1 ? g.a_sm : pad16(g.K);
-  rc = encode_tmap(c, &ta, dt, esz, g.a, g.K, g.M, a_bcast ? 1 : g.batch, a_sm, a_bcast ? a_sm * g.M : g.a_sb, block_k, 128);
+  const uint32_t chunk = static_cast<uint32_t>(128 / esz);  // MN-major operands: elements per 128-byte row
+  const CUtensorMapSwizzle mn_swz = esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  if (!a_mn) {
+    const uint64_t a_sm = g.M > 1 ? g.a_sm : pad16(g.K);
+    rc = encode_tmap(c, &ta, dt, esz, g.a, g.K, g.M, a_bcast ? 1 : g.batch, a_sm, a_bcast ? a_sm * g.M : g.a_sb, block_k, 128);
+  } else {
+    const uint64_t a_sk = g.K > 1 ? g.a_sk : pad16(g.M);
+    rc = encode_tmap(c, &ta, dt, esz, g.a, g.M, g.K, a_bcast ? 1 : g.batch, a_sk, a_bcast ? a_sk * g.K : g.a_sb, chunk, block_k, mn_swz);
+  }
   if (rc) return rc;
   const uint32_t n_local = v.block_n / v.cg;
   if (!b_mn) {
@@ -755,10 +763,8 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool b
     rc = encode_tmap(c, &tb, dt, esz, g.b, g.K, g.N, b_bcast ? 1 : g.batch, b_sn, b_bcast ? b_sn * g.N : g.b_sb, block_k, n_local);
   } else {
     const uint64_t b_sk = g.K > 1 ? g.b_sk : pad16(g.N);
-    rc = encode_tmap(c, &tb, dt, esz, g.b, g.N, g.K, b_bcast ? 1 : g.batch, b_sk, b_bcast ? b_sk * g.K : g.b_sb,
-                     static_cast<uint32_t>(128 / esz), block_k,
-                     // MN-major 32-bit operands: 32-byte swizzle atoms (matches the SWIZZLE_128B_BASE32B smem descriptor)
-                     esz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+    // MN-major 32-bit operands: 32-byte swizzle atoms (matches the SWIZZLE_128B_BASE32B smem descriptor)
+    rc = encode_tmap(c, &tb, dt, esz, g.b, g.N, g.K, b_bcast ? 1 : g.batch, b_sk, b_bcast ? b_sk * g.K : g.b_sb, chunk, block_k, mn_swz);
   }
   if (rc) return rc;
 
@@ -797,8 +803,8 @@ static int launch_split(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uin
 static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
   if (g.M == 0 || g.N == 0 || g.batch == 0) return B200_OK;
   const std::string forced = opt(c, "gemm.variant", "auto");
-  bool b_mn = false;
-  const bool tma = g.K > 0 && tma_ok(g, &b_mn);
+  bool a_mn = false, b_mn = false;
+  const bool tma = g.K > 0 && tma_ok(g, &a_mn, &b_mn);
   if (forced == "simt" || !tma) {
     if (forced != "simt" && forced != "auto")
       return fail(B200_ERR_UNSUPPORTED, "gemm.variant=%s forced but operands are not TMA-describable", forced.c_str());
@@ -812,25 +818,29 @@ static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
     if (rc) return rc;
     rc = pool_alloc(c, bb * g.N * 3 * g.K * 4, &b3);
     if (rc) { pool_free(c, a3); return rc; }
-    rc = launch_split(c, st, g.a, a3, ab, g.M, g.K, g.a_sb, g.a_sm, 0);
+    // lhs -> [M, 3K] = [hi|hi|lo] (K-major) or, for a transposed lhs, [3K, M] = [hi;hi;lo] stacked along K
+    rc = !a_mn ? launch_split(c, st, g.a, a3, ab, g.M, g.K, g.a_sb, g.a_sm, 0)
+               : launch_split(c, st, g.a, a3, ab, g.K, g.M, g.a_sb, g.a_sk, 3);
     if (!rc) {
       if (!b_mn) rc = launch_split(c, st, g.b, b3, bb, g.N, g.K, g.b_sb, g.b_sn, 1);
       else rc = launch_split(c, st, g.b, b3, bb, g.K, g.N, g.b_sb, g.b_sk, 2);
     }
     if (!rc) {
       GemmProblem h = g;
-      h.a = a3; h.K = 3 * g.K; h.a_sm = 3 * g.K; h.a_sk = 1; h.a_sb = (g.a_sb == 0) ? 0 : g.M * 3 * g.K;
+      h.a = a3; h.K = 3 * g.K;
+      if (!a_mn) { h.a_sm = 3 * g.K; h.a_sk = 1; } else { h.a_sm = 1; h.a_sk = g.M; }
+      h.a_sb = (g.a_sb == 0) ? 0 : g.M * 3 * g.K;
       h.b = b3;
       if (!b_mn) { h.b_sk = 1; h.b_sn = 3 * g.K; } else { h.b_sk = g.N; h.b_sn = 1; }
       h.b_sb = (g.b_sb == 0) ? 0 : g.N * 3 * g.K;
-      rc = launch_tcgen05(c, st, h, b_mn);
+      rc = launch_tcgen05(c, st, h, a_mn, b_mn);
     }
     // stream-ordered reuse: the pool hands these pages out again only to later work on this context
     pool_free(c, a3);
     pool_free(c, b3);
     return rc;
   }
-  return launch_tcgen05(c, st, g, b_mn);
+  return launch_tcgen05(c, st, g, a_mn, b_mn);
 }
 
 // Collapse batch dims [0, nb) of one operand into a linear stride; false if the offsets are not linear in the flat index.
@@ -1314,6 +1324,33 @@ extern "C" int b200_probe_memread(b200_ctx* c, b200_stream s, b200_dptr buf, uin
   const uint64_t per_pass = static_cast<uint64_t>(grid) * block;
   uint32_t steps = (uint32_t)((lines + per_pass - 1) / per_pass);
   uint64_t in = buf, out = scratch;
+  void* args[] = {&in, &out, &lines, &steps};
+  return launch(c, f, grid, 1, 1, block, 0, 1, resolve_stream(c, s), args);
+}
+
+// mode 0: write-only (memory_write.rs), mode 1: copy (memory_direct.rs); `bytes` per buffer
+extern "C" int b200_probe_memwrite(b200_ctx* c, b200_stream s, b200_dptr dst, uint64_t bytes) {
+  CTX_ENTER(c);
+  CUfunction f;
+  int rc = get_func(c, "memwrite_probe_vec4", &f);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)c->props.num_sms * 32, block = 256;
+  uint64_t lines = bytes / 16, out = dst;
+  const uint64_t per_pass = static_cast<uint64_t>(grid) * block;
+  uint32_t steps = (uint32_t)((lines + per_pass - 1) / per_pass);
+  void* args[] = {&out, &lines, &steps};
+  return launch(c, f, grid, 1, 1, block, 0, 1, resolve_stream(c, s), args);
+}
+
+extern "C" int b200_probe_memcopy(b200_ctx* c, b200_stream s, b200_dptr dst, b200_dptr src, uint64_t bytes) {
+  CTX_ENTER(c);
+  CUfunction f;
+  int rc = get_func(c, "memcopy_probe_vec4", &f);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)c->props.num_sms * 32, block = 256;
+  uint64_t lines = bytes / 16, in = src, out = dst;
+  const uint64_t per_pass = static_cast<uint64_t>(grid) * block;
+  uint32_t steps = (uint32_t)((lines + per_pass - 1) / per_pass);
   void* args[] = {&in, &out, &lines, &steps};
   return launch(c, f, grid, 1, 1, block, 0, 1, resolve_stream(c, s), args);
 }

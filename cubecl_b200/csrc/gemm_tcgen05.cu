@@ -94,7 +94,7 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, const GemmParams& p)
   return c;
 }
 
-template <int CG, int BLOCK_N, bool B_MN, int KIND, int OUT, int STAGES>
+template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtensorMap* tma_b, const GemmParams& p) {
   constexpr int ESZ = (KIND == KIND_TF32) ? 4 : 2;
   constexpr int BLOCK_K = 128 / ESZ;  // one 128-byte swizzle row of K per stage
@@ -104,14 +104,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
   constexpr uint32_t A_BYTES = 128 * 128;
   constexpr uint32_t B_BYTES = N_LOCAL * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int CHUNK_N = 128 / ESZ;                 // MN-major B: N elements per 128-byte row
-  constexpr uint32_t CHUNK_BYTES = BLOCK_K * 128;    // MN-major B: one [BLOCK_K x 128 B] chunk
-  constexpr int NUM_CHUNKS = N_LOCAL / CHUNK_N;
+  constexpr int CHUNK_N = 128 / ESZ;                 // MN-major operand: M/N elements per 128-byte row
+  constexpr uint32_t CHUNK_BYTES = BLOCK_K * 128;    // MN-major operand: one [BLOCK_K x 128 B] chunk
+  constexpr int NUM_CHUNKS = N_LOCAL / CHUNK_N;      // B chunks per CTA
+  constexpr int NUM_CHUNKS_A = 128 / CHUNK_N;        // A chunks per CTA (128 rows of M)
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                : (2 * BLOCK_N <= 256) ? 256 : 512;
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024-byte alignment for SWIZZLE_128B");
-  constexpr uint32_t IDESC = make_idesc(KIND, 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc(KIND, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -175,7 +176,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
           const int k0 = static_cast<int>(kb * BLOCK_K);
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
-            tma_load_3d(sa, tma_a, full_bar(s), k0, m0, ba);
+            if constexpr (!A_MN) {
+              tma_load_3d(sa, tma_a, full_bar(s), k0, m0, ba);
+            } else {
+#pragma unroll
+              for (int c = 0; c < NUM_CHUNKS_A; ++c)
+                tma_load_3d(sa + c * CHUNK_BYTES, tma_a, full_bar(s), m0 + c * CHUNK_N, k0, ba);
+            }
             if constexpr (!B_MN) {
               tma_load_3d(sb, tma_b, full_bar(s), k0, n0, bb);
             } else {
@@ -186,7 +193,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
           } else {
             const uint32_t fb = leader_full0 + 8u * s;
             if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE_BYTES);
-            tma_load_3d_2sm(sa, tma_a, fb, k0, m0, ba);
+            if constexpr (!A_MN) {
+              tma_load_3d_2sm(sa, tma_a, fb, k0, m0, ba);
+            } else {
+#pragma unroll
+              for (int c = 0; c < NUM_CHUNKS_A; ++c)
+                tma_load_3d_2sm(sa + c * CHUNK_BYTES, tma_a, fb, m0 + c * CHUNK_N, k0, ba);
+            }
             if constexpr (!B_MN) {
               tma_load_3d_2sm(sb, tma_b, fb, k0, n0, bb);
             } else {
@@ -213,17 +226,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
           tcgen05_fence_after();
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          // A is K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart.
-          const uint64_t a_desc = make_smem_desc_sw128(sa, 16, 1024);
-          // B K-major: same.  B MN-major: 128-byte rows run along N, 8 k-rows per atom (SBO 1024),
-          // next 128-byte N chunk CHUNK_BYTES further (LBO).
-          // 32-bit MN-major operands only exist in the 32-byte-atom swizzle: 4 k-rows per atom (SBO 512).
-          const uint64_t b_desc = !B_MN ? make_smem_desc_sw128(sb, 16, 1024)
-                                  : (KIND == KIND_TF32) ? make_smem_desc(sb, CHUNK_BYTES, 512, 1)
-                                                        : make_smem_desc_sw128(sb, CHUNK_BYTES, 1024);
+          // K-major operand: rows of 128 B along K, 8-row swizzle atoms 1024 B apart (SBO).
+          // MN-major operand: 128-byte rows run along M/N, 8 k-rows per atom (SBO 1024), next 128-byte M/N chunk
+          // CHUNK_BYTES further (LBO).  32-bit MN-major operands only exist in the 32-byte-atom swizzle: 4 k-rows per
+          // atom (SBO 512), layout type SWIZZLE_128B_BASE32B.
+          auto mn_desc = [](uint32_t addr) {
+            return (KIND == KIND_TF32) ? make_smem_desc(addr, CHUNK_BYTES, 512, 1) : make_smem_desc_sw128(addr, CHUNK_BYTES, 1024);
+          };
+          const uint64_t a_desc = A_MN ? mn_desc(sa) : make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t b_desc = B_MN ? mn_desc(sb) : make_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t a_k = a_desc + static_cast<uint64_t>((k * 32) >> 4);
+            const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
             const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
             umma_ss<CG, KIND>(d_tmem, a_k, b_k, IDESC, (kb | k) != 0 ? 1u : 0u);
           }
@@ -275,47 +289,34 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
 // Dynamic shared memory a variant needs (host mirrors this in capi.cpp: gemm_smem_bytes()).
 //   STAGES * (16384 + (BLOCK_N/CG)*128) + 1024 (alignment slack) + 256 (barriers)
 
-#define GEMM_KERNEL(NAME, CG, BN, BMN, KIND, OUT, STAGES)                                                        \
+#define GEMM_KERNEL(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES)                                                   \
   extern "C" __global__ void __launch_bounds__(kNumThreads, 1)                                                   \
       NAME(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,                 \
            const __grid_constant__ GemmParams p) {                                                               \
-    gemm_body<CG, BN, BMN, KIND, OUT, STAGES>(&tma_a, &tma_b, p);                                                \
+    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES>(&tma_a, &tma_b, p);                                           \
   }
 
-// name: gemm_<in>_<out>_<cg>sm_n<BLOCK_N>_<bk|bn>   (bk: rhs stored [N,K] K-major; bn: rhs stored [K,N] row-major)
+// name: gemm_<in>_<out>_<cg>sm_n<BLOCK_N>_<a><b>
+//   a: k = lhs stored [M,K] row-major (K-major), m = lhs stored [K,M] (transposed view, M contiguous)
+//   b: n = rhs stored [K,N] row-major (N contiguous), k = rhs stored [N,K] (transposed view, K contiguous)
+#define GEMM_LAYOUTS(PFX, CG, BN, KIND, OUT, STAGES)           \
+  GEMM_KERNEL(PFX##_kn, CG, BN, false, true, KIND, OUT, STAGES)  \
+  GEMM_KERNEL(PFX##_kk, CG, BN, false, false, KIND, OUT, STAGES) \
+  GEMM_KERNEL(PFX##_mn, CG, BN, true, true, KIND, OUT, STAGES)   \
+  GEMM_KERNEL(PFX##_mk, CG, BN, true, false, KIND, OUT, STAGES)
+#define GEMM_DTYPES(TILE, CG, BN, STAGES)                                      \
+  GEMM_LAYOUTS(gemm_bf16_bf16_##TILE, CG, BN, KIND_BF16, OUT_BF16, STAGES)      \
+  GEMM_LAYOUTS(gemm_bf16_f32_##TILE, CG, BN, KIND_BF16, OUT_F32, STAGES)        \
+  GEMM_LAYOUTS(gemm_f16_f16_##TILE, CG, BN, KIND_F16, OUT_F16, STAGES)          \
+  GEMM_LAYOUTS(gemm_f16_f32_##TILE, CG, BN, KIND_F16, OUT_F32, STAGES)          \
+  GEMM_LAYOUTS(gemm_tf32_f32_##TILE, CG, BN, KIND_TF32, OUT_F32, STAGES)
+
 // 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
-GEMM_KERNEL(gemm_bf16_bf16_2sm_n256_bk, 2, 256, false, KIND_BF16, OUT_BF16, 6)
-GEMM_KERNEL(gemm_bf16_bf16_2sm_n256_bn, 2, 256, true, KIND_BF16, OUT_BF16, 6)
-GEMM_KERNEL(gemm_bf16_f32_2sm_n256_bk, 2, 256, false, KIND_BF16, OUT_F32, 6)
-GEMM_KERNEL(gemm_bf16_f32_2sm_n256_bn, 2, 256, true, KIND_BF16, OUT_F32, 6)
-GEMM_KERNEL(gemm_f16_f16_2sm_n256_bk, 2, 256, false, KIND_F16, OUT_F16, 6)
-GEMM_KERNEL(gemm_f16_f16_2sm_n256_bn, 2, 256, true, KIND_F16, OUT_F16, 6)
-GEMM_KERNEL(gemm_f16_f32_2sm_n256_bk, 2, 256, false, KIND_F16, OUT_F32, 6)
-GEMM_KERNEL(gemm_f16_f32_2sm_n256_bn, 2, 256, true, KIND_F16, OUT_F32, 6)
-GEMM_KERNEL(gemm_tf32_f32_2sm_n256_bk, 2, 256, false, KIND_TF32, OUT_F32, 6)
-GEMM_KERNEL(gemm_tf32_f32_2sm_n256_bn, 2, 256, true, KIND_TF32, OUT_F32, 6)
-// 2-SM, 256x128 tiles (better wave quantisation on mid-size problems): 24 KB/stage/CTA -> 8 stages = 192 KB
-GEMM_KERNEL(gemm_bf16_bf16_2sm_n128_bk, 2, 128, false, KIND_BF16, OUT_BF16, 8)
-GEMM_KERNEL(gemm_bf16_bf16_2sm_n128_bn, 2, 128, true, KIND_BF16, OUT_BF16, 8)
-GEMM_KERNEL(gemm_bf16_f32_2sm_n128_bk, 2, 128, false, KIND_BF16, OUT_F32, 8)
-GEMM_KERNEL(gemm_bf16_f32_2sm_n128_bn, 2, 128, true, KIND_BF16, OUT_F32, 8)
-GEMM_KERNEL(gemm_f16_f16_2sm_n128_bk, 2, 128, false, KIND_F16, OUT_F16, 8)
-GEMM_KERNEL(gemm_f16_f16_2sm_n128_bn, 2, 128, true, KIND_F16, OUT_F16, 8)
-GEMM_KERNEL(gemm_f16_f32_2sm_n128_bk, 2, 128, false, KIND_F16, OUT_F32, 8)
-GEMM_KERNEL(gemm_f16_f32_2sm_n128_bn, 2, 128, true, KIND_F16, OUT_F32, 8)
-GEMM_KERNEL(gemm_tf32_f32_2sm_n128_bk, 2, 128, false, KIND_TF32, OUT_F32, 8)
-GEMM_KERNEL(gemm_tf32_f32_2sm_n128_bn, 2, 128, true, KIND_TF32, OUT_F32, 8)
+GEMM_DTYPES(2sm_n256, 2, 256, 6)
+// 2-SM, 256x128 tiles: 24 KB/stage/CTA -> 8 stages = 192 KB (smem-read bound: 128 B/cycle/SM of operands)
+GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
-GEMM_KERNEL(gemm_bf16_bf16_1sm_n128_bk, 1, 128, false, KIND_BF16, OUT_BF16, 6)
-GEMM_KERNEL(gemm_bf16_bf16_1sm_n128_bn, 1, 128, true, KIND_BF16, OUT_BF16, 6)
-GEMM_KERNEL(gemm_bf16_f32_1sm_n128_bk, 1, 128, false, KIND_BF16, OUT_F32, 6)
-GEMM_KERNEL(gemm_bf16_f32_1sm_n128_bn, 1, 128, true, KIND_BF16, OUT_F32, 6)
-GEMM_KERNEL(gemm_f16_f16_1sm_n128_bk, 1, 128, false, KIND_F16, OUT_F16, 6)
-GEMM_KERNEL(gemm_f16_f16_1sm_n128_bn, 1, 128, true, KIND_F16, OUT_F16, 6)
-GEMM_KERNEL(gemm_f16_f32_1sm_n128_bk, 1, 128, false, KIND_F16, OUT_F32, 6)
-GEMM_KERNEL(gemm_f16_f32_1sm_n128_bn, 1, 128, true, KIND_F16, OUT_F32, 6)
-GEMM_KERNEL(gemm_tf32_f32_1sm_n128_bk, 1, 128, false, KIND_TF32, OUT_F32, 6)
-GEMM_KERNEL(gemm_tf32_f32_1sm_n128_bn, 1, 128, true, KIND_TF32, OUT_F32, 6)
+GEMM_DTYPES(1sm_n128, 1, 128, 6)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/

@@ -50,6 +50,12 @@ def run(device: int = 0, clock: str = "host") -> None:
     c.fill_modulo(buf, "f32", nbytes // 4, 8)
     v = bench.measure(device_sampler(c, lambda: c.probe_memread(buf, nbytes, scratch), clock), nbytes)
     rows.append(("memory-read", "512 MiB float_4 (as CubeCL JITs it)", fmt(v.bytes_per_s() / 1e9, "Gbytes/s")))
+    buf2 = c.empty(nbytes)
+    v = bench.measure(device_sampler(c, lambda: c.probe_memwrite(buf2, nbytes), clock), nbytes)
+    rows.append(("memory-write", "512 MiB float_4 (as CubeCL JITs it)", fmt(v.bytes_per_s() / 1e9, "Gbytes/s")))
+    v = bench.measure(device_sampler(c, lambda: c.probe_memcopy(buf2, buf, nbytes), clock), 2 * nbytes)
+    rows.append(("memory", "512 MiB copy, read+write counted", fmt(v.bytes_per_s() / 1e9, "Gbytes/s")))
+    c.fill_modulo(buf, "f32", nbytes // 4, 8)
     t = TensorHandle.new_contiguous([nbytes // 4], buf, "f32")
     out = TensorHandle.empty_contiguous(c, [1], "f32")
     v = bench.measure(device_sampler(c, lambda: reduce.launch(c, t, out, None, "sum"), clock), nbytes)

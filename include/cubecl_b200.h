@@ -177,6 +177,9 @@ int b200_probe_wmma(b200_ctx* ctx, b200_stream s, b200_dtype dtype, uint32_t n_i
 int b200_probe_umma(b200_ctx* ctx, b200_stream s, uint32_t n_iter, b200_dptr scratch, double* ops);
 /* memory_read_throughput with float_4 lines over `bytes` of `buf` (memory_read.rs:68-154): grid = SMs*32, block = 256. */
 int b200_probe_memread(b200_ctx* ctx, b200_stream s, b200_dptr buf, uint64_t bytes, b200_dptr scratch_16);
+/* memory_write_throughput (memory_write.rs: writes only) and memory_direct (memory_direct.rs: copy, both directions counted). */
+int b200_probe_memwrite(b200_ctx* ctx, b200_stream s, b200_dptr dst, uint64_t bytes);
+int b200_probe_memcopy(b200_ctx* ctx, b200_stream s, b200_dptr dst, b200_dptr src, uint64_t bytes);
 
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char* b200_last_error(void);

@@ -21,10 +21,13 @@ def make_operand(shape, dtype, seed, lo=-1.0, hi=1.0, integer_mod=None):
     return dev, synth.from_device_dtype(dev, dtype).reshape(shape)
 
 
-def run_matmul(client, lhs_dev, rhs_dev, in_dtype, out_dtype, rhs_transposed=False, out_shape=None):
-    """lhs_dev [..,M,K]; rhs_dev is [..,K,N], or [..,N,K] when rhs_transposed (passed as a stride-swapped view)."""
+def run_matmul(client, lhs_dev, rhs_dev, in_dtype, out_dtype, rhs_transposed=False, out_shape=None, lhs_transposed=False):
+    """lhs_dev [..,M,K] (or [..,K,M] when lhs_transposed); rhs_dev is [..,K,N], or [..,N,K] when rhs_transposed.
+    Transposed operands are passed as stride-swapped views of the same buffer (MatrixBatchLayout::MildlyPermuted)."""
     lhs = TensorHandle.from_numpy(client, lhs_dev, in_dtype)
     rhs = TensorHandle.from_numpy(client, rhs_dev, in_dtype)
+    if lhs_transposed:
+        lhs = lhs.transposed()
     if rhs_transposed:
         rhs = rhs.transposed()
     shape = out_shape or matmul.calculate_matmul_output(lhs.shape, rhs.shape)

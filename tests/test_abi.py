@@ -28,7 +28,7 @@ def test_cubins_are_embedded_and_sm100a():
     # the prebuilt images are in .rodata of the .so; cuobjdump must list sm_100a ELF with tcgen05/TMA SASS
     cub = ROOT / "cubecl_b200" / "build" / "gemm.cubin"
     assert cub.exists() and cub.stat().st_size > 10000
-    r = subprocess.run(["cuobjdump", "-sass", "-fun", "gemm_bf16_bf16_2sm_n256_bn", str(cub)], capture_output=True, text=True)
+    r = subprocess.run(["cuobjdump", "-sass", "-fun", "gemm_bf16_bf16_2sm_n256_kn", str(cub)], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in r.stdout

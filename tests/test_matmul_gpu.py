@@ -103,6 +103,24 @@ def test_parity_f32(client, variant, rhs_t, mode, tol):
     check_against_oracle(got, a, b.T if rhs_t else b, "f32", tight=tol)
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
+@pytest.mark.parametrize("in_dtype,mode,tol", [("bf16", "-", 1e-5), ("f16", "-", 1e-5), ("f32", "tf32", 1e-3), ("f32", "3xtf32", 2e-6)])
+def test_parity_transposed_lhs(client, variant, rhs_t, in_dtype, mode, tol):
+    # lhs given as a transposed view of a [K, M] buffer (MildlyPermuted{transposed}, matrix_batch_layout.rs:8-19):
+    # MN-major A operand through TMA, no into_contiguous copy
+    client.set_option("gemm.variant", variant)
+    if in_dtype == "f32":
+        client.set_option("gemm.f32", mode)
+    M, N, K = 320, 384, 264
+    a_dev, a_km = make_operand((K, M), in_dtype, 71)
+    b_dev, b = make_operand((N, K) if rhs_t else (K, N), in_dtype, 72)
+    before = client.launch_count()
+    got = run_matmul(client, a_dev, b_dev, in_dtype, "f32", rhs_transposed=rhs_t, lhs_transposed=True)
+    assert client.launch_count() - before == (3 if mode == "3xtf32" else 1)   # tcgen05 path (+2 split kernels), not SIMT
+    check_against_oracle(got, np.ascontiguousarray(a_km.T), b.T if rhs_t else b, "f32", tight=tol)
+
+
 def test_simt_is_bit_exact_with_reference_order(client):
     # the strided SIMT kernel accumulates exactly like cmma.rs:695-721 (f32, ascending k, separate mul/add)
     client.set_option("gemm.variant", "simt")

@@ -55,6 +55,11 @@ def test_reference_probes_run(client):
     buf = client.empty(1 << 24)
     client.fill_modulo(buf, "f32", 1 << 22, 2)
     client.probe_memread(buf, 1 << 24, scratch)
+    dst = client.empty(1 << 24)
+    client.probe_memcopy(dst, buf, 1 << 24)
+    assert np.array_equal(np.frombuffer(client.read_one(dst), dtype=np.float32), (np.arange(1 << 22) % 2).astype(np.float32))
+    client.probe_memwrite(dst, 1 << 24)
+    assert np.array_equal(np.frombuffer(client.read_one(dst), dtype=np.float32)[:8], np.array([1, 2, 3, 4, 1, 2, 3, 4], dtype=np.float32))
     client.sync()
 
 
