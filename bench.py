@@ -131,12 +131,20 @@ def rejected(clocks) -> bool:
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise cap the CPU arm)."""
+    try:
+        return max(1, min(256, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        return max(1, min(256, os.cpu_count() or 1))
+
+
 def cpu_matmul_sample(seconds_target=12.0):
     """Reference-order CPU matmul (oracle port, all host threads) on a bounded row-slab of the 8192^3 problem."""
     import oracle
     from cubecl_b200 import synth
-    threads = oracle.num_threads()
-    K = Ncols = N_MM
+    threads = host_threads()
+    K = N_MM
     b_nk = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(4, 512 * K, -1.0, 1.0))).reshape(512, K)  # 512 rhs columns
     rows = 2 * threads
     a = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(3, rows * K, -1.0, 1.0))).reshape(rows, K)
@@ -160,7 +168,7 @@ def cpu_matmul_sample(seconds_target=12.0):
 def cpu_reduce_sample():
     import oracle
     from cubecl_b200 import synth
-    threads = oracle.num_threads()
+    threads = host_threads()
     n = 1 << 26
     x = synth.uniform_f32(5, n, 0.0, 1.0)
     t0 = time.perf_counter(); oracle.sum_serial_f32(x); t_serial = time.perf_counter() - t0

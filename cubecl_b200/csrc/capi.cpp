@@ -642,7 +642,8 @@ struct GemmVariant {
   double eff;       // measured MMA-pipe efficiency relative to 2sm_n256 (8192^3, B200): the N=128 shapes need
                     // 128 B/cycle/SM of operand reads from shared memory and are smem-bandwidth bound
 };
-static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59}};
+static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59},
+                                       {"2sm_n256s7", 2, 256, 7, 0.0 /* tuning only: never auto-selected */}};
 
 static unsigned gemm_smem_bytes(const GemmVariant& v) { return v.stages * (16384 + (v.block_n / v.cg) * 128) + 1024 + 256; }
 
@@ -724,11 +725,12 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   double best_cost = 0;
   for (const GemmVariant& v : kVariants) {
     if (forced != "auto" && forced != v.tag) continue;
+    if (forced == "auto" && v.eff <= 0.0) continue;
     const uint64_t tm = (g.M + 128 * v.cg - 1) / (128 * v.cg), tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
     const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
     const uint64_t waves = (tiles + clusters - 1) / clusters;
-    const double cost = static_cast<double>(waves) * (128.0 * v.block_n) / v.eff;  // per-SM MMA time per wave
+    const double cost = static_cast<double>(waves) * (128.0 * v.block_n) / (v.eff > 0 ? v.eff : 1.0);  // per-SM MMA time per wave
     if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; }
   }
   if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant", forced.c_str());

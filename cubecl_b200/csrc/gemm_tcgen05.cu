@@ -313,6 +313,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
 
 // 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
 GEMM_DTYPES(2sm_n256, 2, 256, 6)
+// tuning variant: 7 stages (224 KB of operand ring), bf16 only
+GEMM_LAYOUTS(gemm_bf16_bf16_2sm_n256s7, 2, 256, KIND_BF16, OUT_BF16, 7)
 // 2-SM, 256x128 tiles: 24 KB/stage/CTA -> 8 stages = 192 KB (smem-read bound: 128 B/cycle/SM of operands)
 GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages

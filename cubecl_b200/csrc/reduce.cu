@@ -220,7 +220,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
-template <int OP, int DT, int UNROLL, bool WIDE /* 256-bit loads, f32 only */, bool XGPU = false>
+template <int OP, int DT, int UNROLL, bool WIDE /* 256-bit loads, f32 only */, bool XGPU = false, bool BLOCKED = false>
 __device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const XgpuParams* xg = nullptr) {
   using E = Elem<DT>;
   constexpr int VEC = WIDE ? 8 : E::VEC;
@@ -240,6 +240,26 @@ __device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const Xgp
     for (int j = 0; j < VEC; ++j) acc[u][j] = ValOp<OP>::identity();
 
   uint64_t v = tid;
+  if constexpr (BLOCKED) {
+    // tile = blockDim * UNROLL consecutive vectors (64 KB for 512 threads x 8 x 16 B), tiles dealt round-robin to blocks:
+    // at any instant the whole grid reads ONE contiguous window instead of UNROLL windows nthreads apart
+    const uint64_t tile = static_cast<uint64_t>(blockDim.x) * UNROLL;
+    const uint64_t ntiles = nvec / tile;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const uint64_t base_v = t * tile + threadIdx.x;
+      uint4 r[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) r[u] = ldg_stream_u4(base + (base_v + static_cast<uint64_t>(u) * blockDim.x) * 16);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        float f[VEC];
+        E::unpack(r[u], f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[u][j] = ValOp<OP>::apply(acc[u][j], f[j]);
+      }
+    }
+    v = ntiles * tile + tid;  // leftover vectors: grid-stride below
+  } else
   // main: UNROLL vectors per thread per trip, all loads issued before any use
   for (; v + static_cast<uint64_t>(UNROLL - 1) * nthreads < nvec; v += static_cast<uint64_t>(UNROLL) * nthreads) {
     if constexpr (WIDE) {
@@ -597,8 +617,16 @@ extern "C" __global__ void __launch_bounds__(512) reduce_all_sum_f32_xgpu(const 
   reduce_all_body<OP_SUM, DT_F32, 8, false, true>(p, &xg);
 }
 
+#define REDUCE_ALL_BLOCKED(NAME, UNROLL)                                                           \
+  extern "C" __global__ void __launch_bounds__(512) NAME(const __grid_constant__ ReduceParams p) {  \
+    reduce_all_body<OP_SUM, DT_F32, UNROLL, false, false, true>(p);                                \
+  }
+REDUCE_ALL_BLOCKED(reduce_all_sum_f32_b4, 4)
+REDUCE_ALL_BLOCKED(reduce_all_sum_f32_b8, 8)
+
 // tuning variants of the headline kernel (f32 sum over all elements); the host picks one by name.
 REDUCE_ALL(reduce_all_sum_f32_u4, OP_SUM, DT_F32, 4, false)
 REDUCE_ALL(reduce_all_sum_f32_u16, OP_SUM, DT_F32, 16, false)
+REDUCE_ALL(reduce_all_sum_f32_u2, OP_SUM, DT_F32, 2, false)
 REDUCE_ALL(reduce_all_sum_f32_w2, OP_SUM, DT_F32, 2, true)
 REDUCE_ALL(reduce_all_sum_f32_w4, OP_SUM, DT_F32, 4, true)

@@ -84,7 +84,7 @@ int b200_destroy(b200_ctx* ctx);
 int b200_get_props(b200_ctx* ctx, b200_props* out);
 /* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
  * (auto|2sm_n256|2sm_n128|1sm_n128|simt), "gemm.f32" (3xtf32|tf32), "gemm.group_m", "reduce.variant"
- * (auto|u4|u8|u16|w2|w4), "reduce.threads", "reduce.blocks_per_sm". */
+ * (auto|u2|u4|u8|u16|b4|b8|w2|w4), "reduce.threads", "reduce.blocks_per_sm". */
 int b200_set_option(b200_ctx* ctx, const char* key, const char* value);
 /* Number of device kernels this context has launched so far (bench.py reports it as gpu_launches). */
 int b200_launch_count(b200_ctx* ctx, uint64_t* count);

@@ -77,6 +77,9 @@ class Handle {
     b200_ctx* ctx;
     uint64_t ptr;
     size_t size;
+    Rec(b200_ctx* c, uint64_t p, size_t s) : ctx(c), ptr(p), size(s) {}
+    Rec(const Rec&) = delete;
+    Rec& operator=(const Rec&) = delete;
     ~Rec() { if (ctx && ptr) b200_free(ctx, ptr); }
   };
   std::shared_ptr<Rec> rec_;
@@ -98,7 +101,7 @@ class ComputeClient {
     uint64_t p = 0;
     check(b200_alloc(ctx_, size, &p));
     Handle h;
-    h.rec_ = std::make_shared<Handle::Rec>(Handle::Rec{ctx_, p, size});
+    h.rec_ = std::shared_ptr<Handle::Rec>(new Handle::Rec{ctx_, p, size});  // in place: a temporary Rec would free the block
     return h;
   }
   Handle create_from_slice(const void* data, size_t bytes) {

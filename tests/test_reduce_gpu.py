@@ -22,7 +22,7 @@ def test_sum_things_kat(client, golden):
     assert got.tolist() == [golden["sum_things"]["expected_sum"]]
 
 
-@pytest.mark.parametrize("variant", ["auto", "u4", "u16", "w2", "w4"])
+@pytest.mark.parametrize("variant", ["auto", "u2", "u4", "u16", "b4", "b8", "w2", "w4"])
 @pytest.mark.parametrize("n", [1, 3, 4, 1000, (1 << 20) + 5])
 def test_sum_all_integer_pattern_exact(client, variant, n):
     # BASELINE config 1 pattern x[i] = i % 8: every partial is an exact integer, so the result must be exact

@@ -38,10 +38,10 @@ if "reduce" in what:
         reduce.launch(c, bufs[k[0] % 3], out, None, "sum")
 
     print("reduce-sum f32 2^28 (1 GiB), rotating 3 buffers (no L2 reuse):")
-    for variant in ("u4", "u8", "u16", "w2", "w4"):
+    for variant in ("u2", "u4", "u8", "b4", "b8", "w2"):
         for threads in (256, 512):
-            for bps in (1, 2, 4, 8):
-                if threads * bps > 2048:
+            for bps in (2, 4, 8, 16):
+                if threads * bps > 4096:
                     continue
                 c.set_option("reduce.variant", variant)
                 c.set_option("reduce.threads", threads)
@@ -66,7 +66,7 @@ if "gemm" in what:
         for mode in (("tf32", "3xtf32") if idt == "f32" else ("-",)):
             if idt == "f32":
                 c.set_option("gemm.f32", mode)
-            for variant in ("2sm_n256", "2sm_n128", "1sm_n128"):
+            for variant in (("2sm_n256", "2sm_n256s7", "2sm_n128", "1sm_n128") if (idt == "bf16" and batch == 1) else ("2sm_n256", "2sm_n128", "1sm_n128")):
                 for rhs_t in (False, True):
                     for gm in ((8, 4, 16) if (variant == "2sm_n256" and not rhs_t and idt == "bf16" and batch == 1) else (8,)):
                         c.set_option("gemm.variant", variant)
