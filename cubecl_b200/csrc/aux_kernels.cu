@@ -188,3 +188,29 @@ extern "C" __global__ void __launch_bounds__(256) memcopy_probe_vec4(const float
     if (idx < lines) out[idx] = in[idx];
   }
 }
+
+// ------------------------------------------------------------------------------------------------ into_contiguous
+// Gather a strided rank<=8 tensor into a compact row-major buffer (crates/cubecl-std/src/tensor/contiguous.rs is the
+// reference's generic version).  Only used in front of kernels that need contiguous input (reduce) when the caller
+// hands in a pitched / permuted TensorHandle; element size 1, 2, 4 or 8 bytes.
+struct GatherParams {
+  uint64_t in, out, n;
+  uint64_t shape[8], strides[8];
+  uint32_t rank, esz;
+};
+extern "C" __global__ void __launch_bounds__(256) gather_strided(const __grid_constant__ GatherParams p) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    uint64_t rem = i, off = 0;
+#pragma unroll 1
+    for (int d = static_cast<int>(p.rank) - 1; d >= 0; --d) {
+      const uint64_t q = rem / p.shape[d];
+      off += (rem - q * p.shape[d]) * p.strides[d];
+      rem = q;
+    }
+    if (p.esz == 4) reinterpret_cast<uint32_t*>(p.out)[i] = reinterpret_cast<const uint32_t*>(p.in)[off];
+    else if (p.esz == 2) reinterpret_cast<uint16_t*>(p.out)[i] = reinterpret_cast<const uint16_t*>(p.in)[off];
+    else if (p.esz == 8) reinterpret_cast<uint64_t*>(p.out)[i] = reinterpret_cast<const uint64_t*>(p.in)[off];
+    else reinterpret_cast<uint8_t*>(p.out)[i] = reinterpret_cast<const uint8_t*>(p.in)[off];
+  }
+}

@@ -12,6 +12,7 @@
 
 #include <cuda.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -1076,6 +1077,57 @@ extern "C" int b200_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_d
   return launch_reduce_cols(c, st, op, in_dtype, in, out, outer, len, inner, scale);
 }
 
+struct GatherParams {
+  uint64_t in, out, n;
+  uint64_t shape[8], strides[8];
+  uint32_t rank, esz;
+};
+
+extern "C" int b200_into_contiguous(b200_ctx* c, b200_stream s, b200_dtype dtype, b200_dptr in, b200_dptr out, int rank,
+                                    const uint64_t* shape, const uint64_t* strides) {
+  CTX_ENTER(c);
+  const size_t esz = dtype_size(dtype);
+  if (!esz) return fail(B200_ERR_INVALID_ARG, "into_contiguous: unknown dtype %d", (int)dtype);
+  if (rank < 1 || rank > 8 || !shape || !strides) return fail(B200_ERR_INVALID_ARG, "into_contiguous: bad rank/shape/strides");
+  GatherParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = in; p.out = out; p.rank = (uint32_t)rank; p.esz = (uint32_t)esz; p.n = 1;
+  for (int i = 0; i < rank; ++i) { p.shape[i] = shape[i]; p.strides[i] = strides[i]; p.n *= shape[i]; }
+  if (p.n == 0) return B200_OK;
+  if (!in || !out) return fail(B200_ERR_INVALID_ARG, "into_contiguous: null device pointer");
+  CUfunction f;
+  int rc = get_func(c, "gather_strided", &f);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)std::min<uint64_t>((p.n + 255) / 256, (uint64_t)c->props.num_sms * 32);
+  void* args[] = {&p};
+  return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, resolve_stream(c, s), args);
+}
+
+extern "C" int b200_reduce_strided(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
+                                   int rank, const uint64_t* shape, const uint64_t* strides, int axis) {
+  CTX_ENTER(c);
+  if (rank < 1 || rank > 8 || !shape) return fail(B200_ERR_INVALID_ARG, "reduce: bad rank/shape");
+  bool contiguous = true;
+  if (strides) {
+    uint64_t expect = 1;
+    for (int i = rank - 1; i >= 0; --i) {
+      if (shape[i] != 1 && strides[i] != expect) contiguous = false;
+      expect *= shape[i];
+    }
+  }
+  if (contiguous) return b200_reduce(c, s, op, in_dtype, in, out, rank, shape, axis);
+  uint64_t n = 1;
+  for (int i = 0; i < rank; ++i) n *= shape[i];
+  if (n == 0) return b200_reduce(c, s, op, in_dtype, in, out, rank, shape, axis);
+  CUdeviceptr tmp;
+  int rc = pool_alloc(c, n * dtype_size(in_dtype), &tmp);
+  if (rc) return rc;
+  rc = b200_into_contiguous(c, s, in_dtype, in, tmp, rank, shape, strides);
+  if (!rc) rc = b200_reduce(c, s, op, in_dtype, tmp, out, rank, shape, axis);
+  pool_free(c, tmp);
+  return rc;
+}
+
 // ================================================================================================ collectives
 extern "C" int b200_comm_get_unique_id(b200_ctx* c, void* id128) {
   CTX_ENTER(c);
@@ -1154,7 +1206,6 @@ extern "C" int b200_sync_collective(b200_ctx* c, b200_stream compute) {
 }
 
 // ------------------------------------------------------------------------------------------------ peer-memory exchange
-#include <unistd.h>
 
 static int ensure_mailbox(b200_ctx* c) {
   if (c->mailbox) return B200_OK;

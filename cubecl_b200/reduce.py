@@ -1,7 +1,7 @@
 """`reduce::launch` surface (cubek's reduce is out of tree; in-tree semantics: examples/sum_things/src/lib.rs:6-33,
 cubecl-book/src/getting-started/src/bin/v1-cpu.rs:7-15).
 
-Reduces one axis (or every element with axis=None) of a contiguous tensor; f32 accumulation; output f32 (values) or
+Reduces one axis (or every element with axis=None) of a tensor (any strides; non-contiguous inputs are compacted first); f32 accumulation; output f32 (values) or
 u32 (indices for argmax/argmin: ties -> lowest index, first NaN wins).  Kernels: csrc/reduce.cu.
 """
 from __future__ import annotations
@@ -35,14 +35,16 @@ def launch(client: ComputeClient, input: TensorHandle, output: TensorHandle, axi
     try:
         if op not in OPS:
             raise B200Error(6, f"unknown reduce op {op!r}")
-        if not input.is_contiguous():
-            raise B200Error(7, "reduce: input must be contiguous (into_contiguous is outside this path)")
         if output.dtype != output_dtype(op):
             raise B200Error(6, f"reduce: output dtype must be {output_dtype(op)} for op {op}")
         rank = len(input.shape)
         ax = -1 if axis is None else axis % rank
-        _ffi.check(client._lib.b200_reduce(client._ctx, stream, OPS[op], DTYPES[input.dtype], C.c_uint64(input.handle.ptr),
-                                           C.c_uint64(output.handle.ptr), rank, _ffi.u64_array(input.shape), ax))
+        if not output.is_contiguous():
+            raise B200Error(7, "reduce: output must be contiguous")
+        # pitched / permuted inputs are gathered into a compact temporary inside the library (into_contiguous)
+        _ffi.check(client._lib.b200_reduce_strided(client._ctx, stream, OPS[op], DTYPES[input.dtype], C.c_uint64(input.handle.ptr),
+                                                   C.c_uint64(output.handle.ptr), rank, _ffi.u64_array(input.shape),
+                                                   _ffi.u64_array(input.strides), ax))
     except B200Error as e:
         client._defer(e)
 

@@ -134,6 +134,15 @@ int b200_matmul(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dtype ou
 int b200_reduce(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype,
                 b200_dptr in, b200_dptr out, int rank, const uint64_t* shape, int axis);
 
+/* Same, for an input described by strides in elements (pitched rows from TensorHandle::empty, permuted views): a
+ * non-contiguous input is first gathered into a pooled compact temporary (into_contiguous, crates/cubecl-std/src/tensor/
+ * contiguous.rs), then reduced.  strides == NULL means contiguous. */
+int b200_reduce_strided(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype,
+                        b200_dptr in, b200_dptr out, int rank, const uint64_t* shape, const uint64_t* strides, int axis);
+/* out (compact row-major) = gather of the strided rank<=8 tensor `in`. */
+int b200_into_contiguous(b200_ctx* ctx, b200_stream s, b200_dtype dtype, b200_dptr in, b200_dptr out, int rank,
+                         const uint64_t* shape, const uint64_t* strides);
+
 /* ---- collectives: ServerCommunication (server/base.rs:632-739), CUDA impl cubecl-cuda/src/compute/server.rs:666-926 -- */
 #define B200_UNIQUE_ID_BYTES 128
 int b200_comm_get_unique_id(b200_ctx* ctx, void* id128);            /* ncclGetUniqueId (communication.rs:11-25 holds it per device set) */

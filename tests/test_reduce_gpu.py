@@ -129,3 +129,24 @@ def test_bad_axis_is_deferred(client):
     reduce.launch(client, t, out, 1, "sum")
     with pytest.raises(ServerError):
         client.sync()
+
+
+def test_pitched_and_permuted_inputs(client):
+    # TensorHandle::empty pitches rows (allocator.rs:21-72): [100, 72] f32 rows of 288 B pitch to 512 B; the reduce must
+    # see the logical tensor.  Also a transposed (stride-swapped) view.
+    rows, cols = 100, 72
+    x = synth.uniform_f32(12, rows * cols, -1.0, 1.0).reshape(rows, cols)
+    t = TensorHandle.empty(client, [rows, cols], "f32")
+    assert t.strides[0] > cols
+    host = np.zeros((rows, t.strides[0]), dtype=np.float32)
+    host[:, :cols] = x
+    host[:, cols:] = 1e30  # padding must never be read
+    client.write(t.handle, host)
+    for axis in (0, 1, None):
+        got = reduce.launch_alloc(client, t, axis, "sum").to_numpy(client)
+        assert np.allclose(got, oracle.reduce_f64(x, axis, "sum"), rtol=0, atol=1e-4)
+        got = reduce.launch_alloc(client, t, axis, "argmax").to_numpy(client)
+        assert np.array_equal(got, oracle.reduce(x, axis, "argmax"))
+    tt = TensorHandle.from_numpy(client, x, "f32").transposed()          # logical [cols, rows]
+    got = reduce.launch_alloc(client, tt, 1, "max").to_numpy(client)
+    assert np.array_equal(got, x.T.max(axis=1))
