@@ -480,6 +480,15 @@ def main():
         c.set_option("gemm.f32", "3xtf32")
         line["matmul_f32_4096"] = {"unit": "TFLOP/s (f32-equivalent 2*N^3)", "3xtf32_default": f32res["3xtf32"], "tf32": f32res["tf32"]}
         del af, bf, of
+        # widening row: fp8 e4m3 8192^3 -> bf16 on the same kernel (kind::f8f6f4)
+        a8 = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "f8e4m3")
+        b8 = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "f8e4m3")
+        c.fill_uniform(a8.handle, "f8e4m3", N_MM * N_MM, 8, -1.0, 1.0)
+        c.fill_uniform(b8.handle, "f8e4m3", N_MM * N_MM, 9, -1.0, 1.0)
+        ms_8, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
+        line["matmul_fp8_8192"] = {"value": world * FLOPS_MM * extra_steps / (ms_8 * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                   "config": "fp8 e4m3 x e4m3 -> bf16, f32 accumulate, 8192^3 per GPU"}
+        del a8, b8
         # what CubeCL's own kernels reach on this GPU (hand-written from its emit rules)
         if world == 1:
             scratch = c.empty(1024)

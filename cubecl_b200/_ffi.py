@@ -15,7 +15,7 @@ LIB_PATH = PKG / "lib" / "libcubecl_b200.so"
 HEADER_PATH = PKG.parent / "include" / "cubecl_b200.h"
 
 # enums (must match the header)
-F32, F16, BF16, U32, I32, F64, I64, U64, U8, I8 = range(10)
+F32, F16, BF16, U32, I32, F64, I64, U64, U8, I8, F8E4M3, F8E5M2 = range(12)
 REDUCE_SUM, REDUCE_PROD, REDUCE_MAX, REDUCE_MIN, REDUCE_ARGMAX, REDUCE_ARGMIN, REDUCE_MEAN = range(7)
 COMM_SUM, COMM_MEAN = 0, 1
 UNIQUE_ID_BYTES = 128

@@ -10,6 +10,7 @@
 //  * 3xTF32 operand splitting (f32 matmul at near-f32 accuracy on the tf32 tensor pipe)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <mma.h>
 #include <cstdint>
 
@@ -31,7 +32,7 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i, float l
 struct FillParams {
   uint64_t out, n, seed;
   float lo, scale;     // value = lo + u * scale
-  uint32_t dtype;      // 0 f32, 1 f16, 2 bf16
+  uint32_t dtype;      // b200_dtype: 0 f32, 1 f16, 2 bf16, 10 fp8 e4m3, 11 fp8 e5m2
   uint32_t mode;       // 0 uniform hash, 1 (i % modulus) as a number
   uint32_t modulus, pad;
 };
@@ -42,7 +43,8 @@ extern "C" __global__ void __launch_bounds__(256) fill_kernel(const __grid_const
     const float v = (p.mode == 0) ? hash_uniform(p.seed, i, p.lo, p.scale) : static_cast<float>(i % p.modulus);
     if (p.dtype == 0) reinterpret_cast<float*>(p.out)[i] = v;
     else if (p.dtype == 1) reinterpret_cast<__half*>(p.out)[i] = __float2half_rn(v);
-    else reinterpret_cast<__nv_bfloat16*>(p.out)[i] = __float2bfloat16_rn(v);
+    else if (p.dtype == 2) reinterpret_cast<__nv_bfloat16*>(p.out)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<uint8_t*>(p.out)[i] = __nv_cvt_float_to_fp8(v, __NV_SATFINITE, p.dtype == 10 ? __NV_E4M3 : __NV_E5M2);
   }
 }
 
@@ -53,13 +55,15 @@ struct SimtGemmParams {
   uint64_t b_sb, b_sk, b_sn;
   uint64_t o_sb, o_sm, o_sn;
   uint32_t M, N, K, batch;
-  uint32_t in_dtype, out_dtype;  // 0 f32, 1 f16, 2 bf16
+  uint32_t in_dtype, out_dtype;  // b200_dtype: 0 f32, 1 f16, 2 bf16; inputs also 10 fp8 e4m3, 11 fp8 e5m2
 };
 
 __device__ __forceinline__ float load_as_f32(uint64_t base, uint64_t idx, uint32_t dt) {
   if (dt == 0) return reinterpret_cast<const float*>(base)[idx];
   if (dt == 1) return __half2float(reinterpret_cast<const __half*>(base)[idx]);
-  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  if (dt == 2) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  const __half_raw h = __nv_cvt_fp8_to_halfraw(reinterpret_cast<const uint8_t*>(base)[idx], dt == 10 ? __NV_E4M3 : __NV_E5M2);
+  return __half2float(__half(h));
 }
 __device__ __forceinline__ void store_from_f32(uint64_t base, uint64_t idx, uint32_t dt, float v) {
   if (dt == 0) reinterpret_cast<float*>(base)[idx] = v;

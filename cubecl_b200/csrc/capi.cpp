@@ -631,7 +631,7 @@ static size_t dtype_size(int dt) {
     case B200_F32: case B200_U32: case B200_I32: return 4;
     case B200_F16: case B200_BF16: return 2;
     case B200_F64: case B200_I64: case B200_U64: return 8;
-    case B200_U8: case B200_I8: return 1;
+    case B200_U8: case B200_I8: case B200_F8E4M3: case B200_F8E5M2: return 1;
     default: return 0;
   }
 }
@@ -645,6 +645,12 @@ struct GemmVariant {
 };
 static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59},
                                        {"2sm_n256s7", 2, 256, 7, 0.0 /* tuning only: never auto-selected */}};
+static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
+  const bool fp8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2);
+  if (fp8) return !strcmp(v.tag, "2sm_n256") || !strcmp(v.tag, "1sm_n128");
+  if (!strcmp(v.tag, "2sm_n256s7")) return in_dtype == B200_BF16;
+  return true;
+}
 
 static unsigned gemm_smem_bytes(const GemmVariant& v) { return v.stages * (16384 + (v.block_n / v.cg) * 128) + 1024 + 256; }
 
@@ -716,7 +722,8 @@ static bool tma_ok(const GemmProblem& g, bool* a_mn, bool* b_mn) {
 
 static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
   const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
-  const char* in_tag = g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : "tf32";
+  const char* in_tag = g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
+                       : g.in_dtype == B200_F8E5M2 ? "e5m2" : "tf32";
   const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : "f32";
   const uint32_t block_k = static_cast<uint32_t>(128 / esz);
 
@@ -727,6 +734,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   for (const GemmVariant& v : kVariants) {
     if (forced != "auto" && forced != v.tag) continue;
     if (forced == "auto" && v.eff <= 0.0) continue;
+    if (!variant_has_dtype(v, g.in_dtype)) continue;
     const uint64_t tm = (g.M + 128 * v.cg - 1) / (128 * v.cg), tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
     const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
@@ -734,7 +742,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     const double cost = static_cast<double>(waves) * (128.0 * v.block_n) / (v.eff > 0 ? v.eff : 1.0);  // per-SM MMA time per wave
     if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; }
   }
-  if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant", forced.c_str());
+  if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant for this dtype", forced.c_str());
   const GemmVariant& v = *best;
 
   const std::string name = std::string("gemm_") + in_tag + "_" + out_tag + "_" + v.tag + (a_mn ? "_m" : "_k") + (b_mn ? "n" : "k");
@@ -746,7 +754,8 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
 
   const CUtensorMapDataType dt = g.in_dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                  : g.in_dtype == B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
-                                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+                                 : esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                            : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const bool a_bcast = (g.a_sb == 0 || g.batch == 1), b_bcast = (g.b_sb == 0 || g.batch == 1);
   CUtensorMap ta, tb;
   auto pad16 = [&](uint64_t elems) { const uint64_t q = 16 / esz; return (elems + q - 1) / q * q; };
@@ -894,10 +903,12 @@ extern "C" int b200_matmul(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200
   if (rank < 2 || rank > 8) return fail(B200_ERR_INVALID_ARG, "matmul: rank %d unsupported (need 2..8)", rank);
   if (!shape_lhs || !strides_lhs || !shape_rhs || !strides_rhs || !shape_out || !strides_out)
     return fail(B200_ERR_INVALID_ARG, "matmul: null shape/stride array");
-  if (in_dtype != B200_F32 && in_dtype != B200_F16 && in_dtype != B200_BF16)
-    return fail(B200_ERR_UNSUPPORTED, "matmul: input dtype %d unsupported (f32, f16, bf16)", (int)in_dtype);
-  if (out_dtype != in_dtype && out_dtype != B200_F32)
-    return fail(B200_ERR_UNSUPPORTED, "matmul: output dtype must equal the input dtype or be f32");
+  const bool fp8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2);
+  if (in_dtype != B200_F32 && in_dtype != B200_F16 && in_dtype != B200_BF16 && !fp8)
+    return fail(B200_ERR_UNSUPPORTED, "matmul: input dtype %d unsupported (f32, f16, bf16, f8e4m3, f8e5m2)", (int)in_dtype);
+  if (fp8 ? (out_dtype != B200_F32 && out_dtype != B200_BF16 && out_dtype != B200_F16)
+          : (out_dtype != in_dtype && out_dtype != B200_F32))
+    return fail(B200_ERR_UNSUPPORTED, "matmul: output dtype must equal the input dtype or be f32 (fp8 inputs: bf16, f16 or f32)");
   const int nb = rank - 2;
   const uint64_t M = shape_lhs[rank - 2], K = shape_lhs[rank - 1], K2 = shape_rhs[rank - 2], N = shape_rhs[rank - 1];
   // shape.rs:489-517: inner dims must agree, batch dims broadcast 1 vs d
@@ -956,6 +967,7 @@ static const char* op_tag(int op) {
   }
 }
 static const char* dt_tag(int dt) { return dt == B200_F32 ? "f32" : dt == B200_F16 ? "f16" : dt == B200_BF16 ? "bf16" : nullptr; }
+static bool fill_dtype_ok(int dt) { return dt_tag(dt) || dt == B200_F8E4M3 || dt == B200_F8E5M2; }
 
 static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, uint64_t in, uint64_t out, uint64_t n, float scale) {
   std::string name = std::string("reduce_all_") + op_tag(op) + "_" + dt_tag(dt);
@@ -1313,7 +1325,7 @@ extern "C" int b200_reduce_all_reduce(b200_ctx* c, b200_stream s, b200_reduce_op
 
 // ================================================================================================ generators / probes
 static int launch_fill(b200_ctx* c, b200_stream s, int dtype, uint64_t out, uint64_t n, FillParams p) {
-  if (!dt_tag(dtype)) return fail(B200_ERR_UNSUPPORTED, "fill: dtype %d unsupported", dtype);
+  if (!fill_dtype_ok(dtype)) return fail(B200_ERR_UNSUPPORTED, "fill: dtype %d unsupported", dtype);
   if (n == 0) return B200_OK;
   CUfunction f;
   int rc = get_func(c, "fill_kernel", &f);

@@ -28,7 +28,7 @@ struct GemmParams {
   uint32_t vec_store;         // 1 when every output row start is 16-byte aligned
 };
 
-enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2 };
+enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4 };
 enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };
 
 constexpr int kNumThreads = 256;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
@@ -96,7 +96,9 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, const GemmParams& p)
 
 template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtensorMap* tma_b, const GemmParams& p) {
-  constexpr int ESZ = (KIND == KIND_TF32) ? 4 : 2;
+  constexpr int ESZ = (KIND == KIND_TF32) ? 4 : (KIND >= KIND_E4M3) ? 1 : 2;
+  // operand format field of the instruction descriptor (meaning depends on the MMA kind)
+  constexpr uint32_t FMT = (KIND == KIND_E4M3) ? 0u : (KIND == KIND_E5M2) ? 1u : static_cast<uint32_t>(KIND);
   constexpr int BLOCK_K = 128 / ESZ;  // one 128-byte swizzle row of K per stage
   constexpr int UMMA_K = 32 / ESZ;
   constexpr int UMMA_M = 128 * CG;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
                                : (2 * BLOCK_N <= 256) ? 256 : 512;
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024-byte alignment for SWIZZLE_128B");
-  constexpr uint32_t IDESC = make_idesc(KIND, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc(FMT, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -310,15 +312,25 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
   GEMM_LAYOUTS(gemm_f16_f16_##TILE, CG, BN, KIND_F16, OUT_F16, STAGES)          \
   GEMM_LAYOUTS(gemm_f16_f32_##TILE, CG, BN, KIND_F16, OUT_F32, STAGES)          \
   GEMM_LAYOUTS(gemm_tf32_f32_##TILE, CG, BN, KIND_TF32, OUT_F32, STAGES)
+// fp8 (kind::f8f6f4, f32 accumulate): 128 elements of K per 128-byte row, UMMA K = 32
+#define GEMM_FP8(TILE, CG, BN, STAGES)                                          \
+  GEMM_LAYOUTS(gemm_e4m3_bf16_##TILE, CG, BN, KIND_E4M3, OUT_BF16, STAGES)       \
+  GEMM_LAYOUTS(gemm_e4m3_f16_##TILE, CG, BN, KIND_E4M3, OUT_F16, STAGES)         \
+  GEMM_LAYOUTS(gemm_e4m3_f32_##TILE, CG, BN, KIND_E4M3, OUT_F32, STAGES)         \
+  GEMM_LAYOUTS(gemm_e5m2_bf16_##TILE, CG, BN, KIND_E5M2, OUT_BF16, STAGES)       \
+  GEMM_LAYOUTS(gemm_e5m2_f16_##TILE, CG, BN, KIND_E5M2, OUT_F16, STAGES)         \
+  GEMM_LAYOUTS(gemm_e5m2_f32_##TILE, CG, BN, KIND_E5M2, OUT_F32, STAGES)
 
 // 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
 GEMM_DTYPES(2sm_n256, 2, 256, 6)
+GEMM_FP8(2sm_n256, 2, 256, 6)
 // tuning variant: 7 stages (224 KB of operand ring), bf16 only
 GEMM_LAYOUTS(gemm_bf16_bf16_2sm_n256s7, 2, 256, KIND_BF16, OUT_BF16, 7)
 // 2-SM, 256x128 tiles: 24 KB/stage/CTA -> 8 stages = 192 KB (smem-read bound: 128 B/cycle/SM of operands)
 GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
 GEMM_DTYPES(1sm_n128, 1, 128, 6)
+GEMM_FP8(1sm_n128, 1, 128, 6)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/
@@ -326,8 +338,8 @@ GEMM_DTYPES(1sm_n128, 1, 128, 6)
 // issues n_iter x 4 back-to-back UMMA 256x256x16 (bf16 -> f32 in TMEM) on operands resident in shared memory (all ones),
 // so it measures the MMA pipe with no TMA / HBM in the loop.  out[cluster] = acc[0][0] = 64 * n_iter.
 extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_bf16_2sm(float* out, uint32_t n_iter) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ uint8_t smem_probe_raw[];
+  const uint32_t smem_base = (smem_u32(smem_probe_raw) + 1023u) & ~1023u;
   const uint32_t sa = smem_base, sb = smem_base + 16384;
   const uint32_t done_bar = smem_base + 32768, tmem_slot = done_bar + 8;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -192,34 +192,23 @@ __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem].  KIND: 0 = kind::f16 (f16/bf16 inputs), 2 = kind::tf32.
+// D[tmem] (+)= A[smem] * B[smem].  KIND: 0/1 = kind::f16 (f16 / bf16 inputs), 2 = kind::tf32, 3/4 = kind::f8f6f4
+// (e4m3 / e5m2 inputs).  The operand formats themselves are encoded in the instruction descriptor.
+#define B200_UMMA_ASM(CGS, KINDS)                                                                             \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                            \
+               "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),       \
+               "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)                                          \
+               : "memory")
 template <int CG, int KIND>
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
-  if constexpr (CG == 1 && KIND != 2)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else if constexpr (CG == 2 && KIND != 2)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else if constexpr (CG == 1 && KIND == 2)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
+  if constexpr (KIND <= 1) {
+    if constexpr (CG == 1) B200_UMMA_ASM("1", "f16"); else B200_UMMA_ASM("2", "f16");
+  } else if constexpr (KIND == 2) {
+    if constexpr (CG == 1) B200_UMMA_ASM("1", "tf32"); else B200_UMMA_ASM("2", "tf32");
+  } else {
+    if constexpr (CG == 1) B200_UMMA_ASM("1", "f8f6f4"); else B200_UMMA_ASM("2", "f8f6f4");
+  }
 }
 
 // All previously issued tcgen05.mma of this thread arrive (once) on `bar` when they retire.
@@ -271,7 +260,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 }
 
 // Instruction descriptor for kind::f16 / kind::tf32, f32 accumulate.
-//   fmt: 0 = f16, 1 = bf16, 2 = tf32;  *_mn: 0 = K-major operand, 1 = MN-major operand.
+//   fmt: kind::f16 -> 0 = f16, 1 = bf16; kind::tf32 -> 2; kind::f8f6f4 -> 0 = e4m3, 1 = e5m2.
+//   *_mn: 0 = K-major operand, 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t a_mn, uint32_t b_mn, uint32_t umma_m,
                                                   uint32_t umma_n) {
   return (1u << 4)            // accumulator format f32

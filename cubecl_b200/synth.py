@@ -50,6 +50,44 @@ def bf16_bits_to_f32(bits: np.ndarray) -> np.ndarray:
     return (np.ascontiguousarray(bits, dtype=np.uint16).astype(np.uint32) << np.uint32(16)).view(np.float32)
 
 
+def _fp8_table(kind: str) -> np.ndarray:
+    """f32 value of every fp8 code (OCP e4m3fn: bias 7, no inf, NaN = 0x7F/0xFF; e5m2: bias 15, IEEE-like)."""
+    codes = np.arange(256, dtype=np.uint32)
+    sign = np.where(codes & 0x80, -1.0, 1.0)
+    with np.errstate(over="ignore", invalid="ignore"):
+        if kind == "f8e4m3":
+            e, m, bias = (codes >> 3) & 0xF, codes & 0x7, 7
+            val = np.where(e == 0, m / 8.0 * 2.0 ** (1 - bias), (1 + m / 8.0) * 2.0 ** (e.astype(np.float64) - bias))
+            val = np.where((e == 15) & (m == 7), np.nan, val)
+        else:
+            e, m, bias = (codes >> 2) & 0x1F, codes & 0x3, 15
+            val = np.where(e == 0, m / 4.0 * 2.0 ** (1 - bias), (1 + m / 4.0) * 2.0 ** (e.astype(np.float64) - bias))
+            val = np.where(e == 31, np.where(m == 0, np.inf, np.nan), val)
+    return (sign * val).astype(np.float32)
+
+
+def fp8_bits_to_f32(bits: np.ndarray, kind: str) -> np.ndarray:
+    return _fp8_table(kind)[np.ascontiguousarray(bits, dtype=np.uint8)]
+
+
+def f32_to_fp8_bits(x: np.ndarray, kind: str) -> np.ndarray:
+    """Round-to-nearest-even, saturating to the largest finite value (mirrors __nv_cvt_float_to_fp8(.., __NV_SATFINITE, ..))."""
+    table = _fp8_table(kind).astype(np.float64)
+    pos_codes = np.array([c for c in range(128) if np.isfinite(table[c])], dtype=np.int64)   # ascending magnitudes
+    pos_vals = table[pos_codes]
+    xf = np.ascontiguousarray(x, dtype=np.float32)
+    a = np.abs(xf.astype(np.float64))
+    hi = np.clip(np.searchsorted(pos_vals, a, side="left"), 0, len(pos_vals) - 1)
+    lo = np.clip(hi - 1, 0, len(pos_vals) - 1)
+    d_lo, d_hi = np.abs(a - pos_vals[lo]), np.abs(pos_vals[hi] - a)
+    pick_hi = (d_hi < d_lo) | ((d_hi == d_lo) & (pos_codes[hi] % 2 == 0))   # ties -> even mantissa
+    code = np.where(pick_hi, pos_codes[hi], pos_codes[lo])
+    code = np.where(a >= pos_vals[-1], pos_codes[-1], code)                     # saturate (incl. inf)
+    code = np.where(np.isnan(a), 0x7F, code)
+    sign = np.signbit(xf).astype(np.int64) << 7
+    return (code | sign).astype(np.uint8)
+
+
 def to_device_dtype(x_f32: np.ndarray, dtype: str) -> np.ndarray:
     """f32 values -> array in the device representation of `dtype` (bf16 as uint16 bits)."""
     if dtype == "f32":
@@ -58,6 +96,8 @@ def to_device_dtype(x_f32: np.ndarray, dtype: str) -> np.ndarray:
         return np.ascontiguousarray(x_f32, dtype=np.float32).astype(np.float16)
     if dtype == "bf16":
         return f32_to_bf16_bits(x_f32)
+    if dtype in ("f8e4m3", "f8e5m2"):
+        return f32_to_fp8_bits(x_f32, dtype)
     raise ValueError(dtype)
 
 
@@ -65,4 +105,6 @@ def from_device_dtype(a: np.ndarray, dtype: str) -> np.ndarray:
     """Device representation -> f32 values."""
     if dtype == "bf16":
         return bf16_bits_to_f32(a)
+    if dtype in ("f8e4m3", "f8e5m2"):
+        return fp8_bits_to_f32(a, dtype)
     return np.asarray(a).astype(np.float32)

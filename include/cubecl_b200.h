@@ -51,7 +51,8 @@ typedef enum b200_status {
 /* Element types.  Values double as the NCCL dtype selector of communication.rs:34-108 for all_reduce. */
 typedef enum b200_dtype {
   B200_F32 = 0, B200_F16 = 1, B200_BF16 = 2, B200_U32 = 3, B200_I32 = 4, B200_F64 = 5, B200_I64 = 6, B200_U64 = 7,
-  B200_U8 = 8, B200_I8 = 9
+  B200_U8 = 8, B200_I8 = 9,
+  B200_F8E4M3 = 10, B200_F8E5M2 = 11   /* fp8 matmul inputs (FloatKind::E4M3 / E5M2; manual-MMA dtypes of cuda/mma/manual.rs:108-186) */
 } b200_dtype;
 
 /* Reduction instructions of the `reduce::launch` surface (cubek); in-tree semantics: examples/sum_things/src/lib.rs:6-33,
@@ -116,8 +117,9 @@ int b200_event_destroy(b200_ctx* ctx, b200_event e);
 
 /* ---- matmul::launch (cubek; shape rule crates/cubecl-zspace/src/shape.rs:489-517) ----------------------------------
  * out[..,m,n] = sum_k lhs[..,m,k] * rhs[..,k,n]; equal rank >= 2, leading dims broadcast (1 vs d); shapes/strides in
- * ELEMENTS (TensorHandle, cubecl-std/src/tensor/handle.rs:13-23).  f32 accumulation over k.  Inputs f16/bf16/f32;
- * `out_dtype` is the input dtype or F32.  Row strides may be pitched (allocator.rs:21-72); rhs may be given transposed
+ * ELEMENTS (TensorHandle, cubecl-std/src/tensor/handle.rs:13-23).  f32 accumulation over k.  Inputs f16/bf16/f32 with
+ * `out_dtype` = the input dtype or F32; fp8 inputs (F8E4M3 / F8E5M2, both operands the same format, kind::f8f6f4) with
+ * `out_dtype` BF16, F16 or F32.  Row strides may be pitched (allocator.rs:21-72); rhs may be given transposed
  * (stride_k == 1, MatrixBatchLayout::MildlyPermuted{transposed}, matrix_batch_layout.rs:8-19).  f32 inputs run on the tf32
  * tensor pipe, by default with a 3-way split that restores ~f32 accuracy (see "gemm.f32").
  * Returns B200_ERR_INVALID_ARG on shape mismatch -- the MatmulShapeError of shape.rs:489-517. */

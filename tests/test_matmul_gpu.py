@@ -121,6 +121,45 @@ def test_parity_transposed_lhs(client, variant, rhs_t, in_dtype, mode, tol):
     check_against_oracle(got, np.ascontiguousarray(a_km.T), b.T if rhs_t else b, "f32", tight=tol)
 
 
+# ------------------------------------------------------------------------------------------------ fp8 (kind::f8f6f4)
+@pytest.mark.parametrize("dtype", ["f8e4m3", "f8e5m2"])
+def test_golden_cmma_manual_fp8(client, dtype):
+    # cmma.rs:1099-1196 instantiated (16, 8, 32) for e4m3 / e5m2 (cmma.rs:1856-1859): lhs[i,j]=2i+j, rhs[i,j]=3i+j.
+    # fp8 cannot hold every integer up to 100, which is why the reference allows 3 %; against the fp8-ROUNDED operands
+    # the f32-accumulated result is exact, and it is within the reference's 3 % of the integer expectation.
+    m, n, k = 16, 8, 32
+    lhs = np.array([[2 * i + j for j in range(k)] for i in range(m)], dtype=np.float32)
+    rhs = np.array([[3 * i + j for j in range(n)] for i in range(k)], dtype=np.float32)
+    l8, r8 = synth.to_device_dtype(lhs, dtype), synth.to_device_dtype(rhs, dtype)
+    got = run_matmul(client, l8, r8, dtype, "f32")
+    exp_rounded = synth.from_device_dtype(l8, dtype).astype(np.float64) @ synth.from_device_dtype(r8, dtype).astype(np.float64)
+    assert np.array_equal(got.astype(np.float64), exp_rounded)
+    exp_int = lhs.astype(np.float64) @ rhs.astype(np.float64)
+    assert np.all(np.abs(got - exp_int) <= 0.03 * exp_int + 1e-9)   # the reference's own criterion (cmma.rs:1180-1194)
+
+
+@pytest.mark.parametrize("variant", ["2sm_n256", "1sm_n128"])
+@pytest.mark.parametrize("lhs_t", [False, True], ids=["lhs_mk", "lhs_km"])
+@pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
+@pytest.mark.parametrize("dtype,out_dtype", [("f8e4m3", "f32"), ("f8e4m3", "bf16"), ("f8e5m2", "f16"), ("f8e5m2", "f32")])
+def test_parity_fp8(client, variant, lhs_t, rhs_t, dtype, out_dtype):
+    client.set_option("gemm.variant", variant)
+    M, N, K = 384, 512, 640   # 5 k-blocks of 128 fp8 elements
+    a_dev, a = make_operand((K, M) if lhs_t else (M, K), dtype, 81)
+    b_dev, b = make_operand((N, K) if rhs_t else (K, N), dtype, 82)
+    got = run_matmul(client, a_dev, b_dev, dtype, out_dtype, rhs_transposed=rhs_t, lhs_transposed=lhs_t)
+    check_against_oracle(got, np.ascontiguousarray(a.T) if lhs_t else a, b.T if rhs_t else b, out_dtype,
+                         tight=1e-5 if out_dtype == "f32" else None)
+
+
+def test_fp8_ragged_and_simt_fallback(client):
+    for (M, N, K) in ((1, 16, 16), (130, 48, 272), (33, 7, 5)):   # the last one is not TMA-describable -> SIMT kernel
+        a_dev, a = make_operand((M, K), "f8e4m3", 83)
+        b_dev, b = make_operand((K, N), "f8e4m3", 84)
+        got = run_matmul(client, a_dev, b_dev, "f8e4m3", "f32")
+        check_against_oracle(got, a, b, "f32", tight=1e-5)
+
+
 def test_simt_is_bit_exact_with_reference_order(client):
     # the strided SIMT kernel accumulates exactly like cmma.rs:695-721 (f32, ascending k, separate mul/add)
     client.set_option("gemm.variant", "simt")

@@ -170,3 +170,15 @@ def test_matmul_batch_broadcast_and_f64():
     pts, _ = oracle.matmul_points_f64(a[0, 0], b[1, 0], ms, ns)
     assert np.allclose(pts, f64[ms, ns])
     assert np.all(fabs >= np.abs(f64) - 1e-12)
+
+
+def test_fp8_codecs_match_torch():
+    # the numpy fp8 encode/decode used to build operands and expectations, pinned against torch's CPU conversion
+    import torch
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.standard_normal(5000).astype(np.float32) * s for s in (0.01, 1, 30, 500)]
+                       + [np.array([0, -0.0, 448, 449, 1e9, -1e9, 2 ** -9, 2 ** -10, 57344, 60000, 2 ** -16, 2 ** -17], dtype=np.float32)])
+    for kind, tdt in (("f8e4m3", torch.float8_e4m3fn), ("f8e5m2", torch.float8_e5m2)):
+        t = torch.from_numpy(x).clamp(-torch.finfo(tdt).max, torch.finfo(tdt).max).to(tdt)
+        assert np.array_equal(synth.f32_to_fp8_bits(x, kind), t.view(torch.uint8).numpy())
+        assert np.array_equal(synth.fp8_bits_to_f32(t.view(torch.uint8).numpy(), kind), t.float().numpy())

@@ -27,7 +27,7 @@ def test_props_and_pool(client):
     assert np.array_equal(np.frombuffer(client.read_one(h3), dtype=np.float32), data)
 
 
-@pytest.mark.parametrize("dtype", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("dtype", ["f32", "f16", "bf16", "f8e4m3", "f8e5m2"])
 def test_device_generator_matches_host_mirror(client, dtype):
     n = 100003
     t = TensorHandle.empty_contiguous(client, [n], dtype)

@@ -55,7 +55,7 @@ if "reduce" in what:
 
 if "gemm" in what:
     for (idt, odt, n, batch, label) in (("bf16", "bf16", 8192, 1, "bf16 8192^3"), ("bf16", "bf16", 4096, 8, "bf16 8x4096^3"),
-                                        ("f32", "f32", 4096, 1, "f32 4096^3")):
+                                        ("f32", "f32", 4096, 1, "f32 4096^3"), ("f8e4m3", "bf16", 8192, 1, "fp8 8192^3")):
         shape = [batch, n, n] if batch > 1 else [n, n]
         a = TensorHandle.empty_contiguous(c, shape, idt)
         b = TensorHandle.empty_contiguous(c, shape, idt)
@@ -66,7 +66,8 @@ if "gemm" in what:
         for mode in (("tf32", "3xtf32") if idt == "f32" else ("-",)):
             if idt == "f32":
                 c.set_option("gemm.f32", mode)
-            for variant in (("2sm_n256", "2sm_n256s7", "2sm_n128", "1sm_n128") if (idt == "bf16" and batch == 1) else ("2sm_n256", "2sm_n128", "1sm_n128")):
+            for variant in (("2sm_n256", "2sm_n256s7", "2sm_n128", "1sm_n128") if (idt == "bf16" and batch == 1) else
+                            ("2sm_n256", "1sm_n128") if idt.startswith("f8") else ("2sm_n256", "2sm_n128", "1sm_n128")):
                 for rhs_t in (False, True):
                     for gm in ((8, 4, 16) if (variant == "2sm_n256" and not rhs_t and idt == "bf16" and batch == 1) else (8,)):
                         c.set_option("gemm.variant", variant)
