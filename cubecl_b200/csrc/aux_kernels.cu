@@ -71,22 +71,44 @@ __device__ __forceinline__ void store_from_f32(uint64_t base, uint64_t idx, uint
   else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
 }
 
+__device__ __forceinline__ int load_as_i32(uint64_t base, uint64_t idx, uint32_t dt) {
+  return dt == 8 ? static_cast<int>(reinterpret_cast<const uint8_t*>(base)[idx]) : static_cast<int>(reinterpret_cast<const int8_t*>(base)[idx]);
+}
+
 extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid_constant__ SimtGemmParams p) {
   __shared__ float sa[16][17];
   __shared__ float sb[16][17];
   const uint32_t tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const uint32_t m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx, bz = blockIdx.z;
+  const bool integer = (p.in_dtype == 8 || p.in_dtype == 9);  // u8 / i8 -> exact s32 accumulation
   float acc = 0.f;
+  int iacc = 0;
   for (uint32_t k0 = 0; k0 < p.K; k0 += 16) {
     const uint32_t ka = k0 + tx, kb = k0 + ty;
-    sa[ty][tx] = (m < p.M && ka < p.K) ? load_as_f32(p.a, bz * p.a_sb + m * p.a_sm + ka * p.a_sk, p.in_dtype) : 0.f;
-    sb[ty][tx] = (kb < p.K && n < p.N) ? load_as_f32(p.b, bz * p.b_sb + kb * p.b_sk + n * p.b_sn, p.in_dtype) : 0.f;
+    const bool va = (m < p.M && ka < p.K), vb = (kb < p.K && n < p.N);
+    const uint64_t ia = bz * p.a_sb + static_cast<uint64_t>(m) * p.a_sm + static_cast<uint64_t>(ka) * p.a_sk;
+    const uint64_t ib = bz * p.b_sb + static_cast<uint64_t>(kb) * p.b_sk + static_cast<uint64_t>(n) * p.b_sn;
+    if (integer) {  // 8-bit integers are exact in f32, so the staging tiles stay float
+      sa[ty][tx] = va ? static_cast<float>(load_as_i32(p.a, ia, p.in_dtype)) : 0.f;
+      sb[ty][tx] = vb ? static_cast<float>(load_as_i32(p.b, ib, p.in_dtype)) : 0.f;
+    } else {
+      sa[ty][tx] = va ? load_as_f32(p.a, ia, p.in_dtype) : 0.f;
+      sb[ty][tx] = vb ? load_as_f32(p.b, ib, p.in_dtype) : 0.f;
+    }
     __syncthreads();
     const uint32_t kmax = min(16u, p.K - k0);
-    for (uint32_t k = 0; k < kmax; ++k) acc = __fadd_rn(acc, __fmul_rn(sa[ty][k], sb[k][tx]));  // no FMA: reference order
+    if (integer) {
+      for (uint32_t k = 0; k < kmax; ++k) iacc += static_cast<int>(sa[ty][k]) * static_cast<int>(sb[k][tx]);
+    } else {
+      for (uint32_t k = 0; k < kmax; ++k) acc = __fadd_rn(acc, __fmul_rn(sa[ty][k], sb[k][tx]));  // no FMA: reference order
+    }
     __syncthreads();
   }
-  if (m < p.M && n < p.N) store_from_f32(p.out, bz * p.o_sb + m * p.o_sm + n * p.o_sn, p.out_dtype, acc);
+  if (m < p.M && n < p.N) {
+    const uint64_t io = bz * p.o_sb + static_cast<uint64_t>(m) * p.o_sm + static_cast<uint64_t>(n) * p.o_sn;
+    if (integer) reinterpret_cast<int*>(p.out)[io] = iacc;
+    else store_from_f32(p.out, io, p.out_dtype, acc);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ 3xTF32 split

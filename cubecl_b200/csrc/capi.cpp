@@ -646,8 +646,8 @@ struct GemmVariant {
 static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59},
                                        {"2sm_n256s7", 2, 256, 7, 0.0 /* tuning only: never auto-selected */}};
 static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
-  const bool fp8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2);
-  if (fp8) return !strcmp(v.tag, "2sm_n256") || !strcmp(v.tag, "1sm_n128");
+  const bool bits8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2 || in_dtype == B200_U8 || in_dtype == B200_I8);
+  if (bits8) return !strcmp(v.tag, "2sm_n256") || !strcmp(v.tag, "1sm_n128");
   if (!strcmp(v.tag, "2sm_n256s7")) return in_dtype == B200_BF16;
   return true;
 }
@@ -723,8 +723,8 @@ static bool tma_ok(const GemmProblem& g, bool* a_mn, bool* b_mn) {
 static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
   const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
   const char* in_tag = g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
-                       : g.in_dtype == B200_F8E5M2 ? "e5m2" : "tf32";
-  const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : "f32";
+                       : g.in_dtype == B200_F8E5M2 ? "e5m2" : g.in_dtype == B200_U8 ? "u8" : g.in_dtype == B200_I8 ? "s8" : "tf32";
+  const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : g.out_dtype == B200_I32 ? "i32" : "f32";
   const uint32_t block_k = static_cast<uint32_t>(128 / esz);
 
   // pick the tile variant by padded work per wave (ties -> larger tile, less L2 traffic)
@@ -904,11 +904,13 @@ extern "C" int b200_matmul(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200
   if (!shape_lhs || !strides_lhs || !shape_rhs || !strides_rhs || !shape_out || !strides_out)
     return fail(B200_ERR_INVALID_ARG, "matmul: null shape/stride array");
   const bool fp8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2);
-  if (in_dtype != B200_F32 && in_dtype != B200_F16 && in_dtype != B200_BF16 && !fp8)
-    return fail(B200_ERR_UNSUPPORTED, "matmul: input dtype %d unsupported (f32, f16, bf16, f8e4m3, f8e5m2)", (int)in_dtype);
-  if (fp8 ? (out_dtype != B200_F32 && out_dtype != B200_BF16 && out_dtype != B200_F16)
-          : (out_dtype != in_dtype && out_dtype != B200_F32))
-    return fail(B200_ERR_UNSUPPORTED, "matmul: output dtype must equal the input dtype or be f32 (fp8 inputs: bf16, f16 or f32)");
+  const bool int8 = (in_dtype == B200_U8 || in_dtype == B200_I8);
+  if (in_dtype != B200_F32 && in_dtype != B200_F16 && in_dtype != B200_BF16 && !fp8 && !int8)
+    return fail(B200_ERR_UNSUPPORTED, "matmul: input dtype %d unsupported (f32, f16, bf16, f8e4m3, f8e5m2, u8, i8)", (int)in_dtype);
+  if (int8 ? (out_dtype != B200_I32)
+      : fp8 ? (out_dtype != B200_F32 && out_dtype != B200_BF16 && out_dtype != B200_F16)
+            : (out_dtype != in_dtype && out_dtype != B200_F32))
+    return fail(B200_ERR_UNSUPPORTED, "matmul: output dtype must equal the input dtype or be f32 (fp8 inputs: bf16/f16/f32; u8/i8 inputs: i32)");
   const int nb = rank - 2;
   const uint64_t M = shape_lhs[rank - 2], K = shape_lhs[rank - 1], K2 = shape_rhs[rank - 2], N = shape_rhs[rank - 1];
   // shape.rs:489-517: inner dims must agree, batch dims broadcast 1 vs d

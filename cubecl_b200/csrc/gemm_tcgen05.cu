@@ -28,8 +28,8 @@ struct GemmParams {
   uint32_t vec_store;         // 1 when every output row start is 16-byte aligned
 };
 
-enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4 };
-enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };
+enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6 };
+enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };  // OUT_F32 is a raw 32-bit store: it also carries the s32 accumulators of kind::i8
 
 constexpr int kNumThreads = 256;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 
@@ -98,7 +98,8 @@ template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAG
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtensorMap* tma_b, const GemmParams& p) {
   constexpr int ESZ = (KIND == KIND_TF32) ? 4 : (KIND >= KIND_E4M3) ? 1 : 2;
   // operand format field of the instruction descriptor (meaning depends on the MMA kind)
-  constexpr uint32_t FMT = (KIND == KIND_E4M3) ? 0u : (KIND == KIND_E5M2) ? 1u : static_cast<uint32_t>(KIND);
+  constexpr uint32_t FMT = (KIND == KIND_E4M3 || KIND == KIND_U8) ? 0u : (KIND == KIND_E5M2 || KIND == KIND_S8) ? 1u : static_cast<uint32_t>(KIND);
+  constexpr uint32_t C_FMT = (KIND >= KIND_U8) ? 2u : 1u;  // s32 accumulators for integer inputs, f32 otherwise
   constexpr int BLOCK_K = 128 / ESZ;  // one 128-byte swizzle row of K per stage
   constexpr int UMMA_K = 32 / ESZ;
   constexpr int UMMA_M = 128 * CG;
@@ -114,7 +115,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
                                : (2 * BLOCK_N <= 256) ? 256 : 512;
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024-byte alignment for SWIZZLE_128B");
-  constexpr uint32_t IDESC = make_idesc(FMT, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc(FMT, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N, C_FMT);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -312,14 +313,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
   GEMM_LAYOUTS(gemm_f16_f16_##TILE, CG, BN, KIND_F16, OUT_F16, STAGES)          \
   GEMM_LAYOUTS(gemm_f16_f32_##TILE, CG, BN, KIND_F16, OUT_F32, STAGES)          \
   GEMM_LAYOUTS(gemm_tf32_f32_##TILE, CG, BN, KIND_TF32, OUT_F32, STAGES)
-// fp8 (kind::f8f6f4, f32 accumulate): 128 elements of K per 128-byte row, UMMA K = 32
+// 8-bit inputs: fp8 (kind::f8f6f4, f32 accumulate) and u8 / s8 (kind::i8, s32 accumulate, exact): 128 elements of K per
+// 128-byte row, UMMA K = 32
 #define GEMM_FP8(TILE, CG, BN, STAGES)                                          \
   GEMM_LAYOUTS(gemm_e4m3_bf16_##TILE, CG, BN, KIND_E4M3, OUT_BF16, STAGES)       \
   GEMM_LAYOUTS(gemm_e4m3_f16_##TILE, CG, BN, KIND_E4M3, OUT_F16, STAGES)         \
   GEMM_LAYOUTS(gemm_e4m3_f32_##TILE, CG, BN, KIND_E4M3, OUT_F32, STAGES)         \
   GEMM_LAYOUTS(gemm_e5m2_bf16_##TILE, CG, BN, KIND_E5M2, OUT_BF16, STAGES)       \
   GEMM_LAYOUTS(gemm_e5m2_f16_##TILE, CG, BN, KIND_E5M2, OUT_F16, STAGES)         \
-  GEMM_LAYOUTS(gemm_e5m2_f32_##TILE, CG, BN, KIND_E5M2, OUT_F32, STAGES)
+  GEMM_LAYOUTS(gemm_e5m2_f32_##TILE, CG, BN, KIND_E5M2, OUT_F32, STAGES)        \
+  GEMM_LAYOUTS(gemm_u8_i32_##TILE, CG, BN, KIND_U8, OUT_F32, STAGES)             \
+  GEMM_LAYOUTS(gemm_s8_i32_##TILE, CG, BN, KIND_S8, OUT_F32, STAGES)
 
 // 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
 GEMM_DTYPES(2sm_n256, 2, 256, 6)

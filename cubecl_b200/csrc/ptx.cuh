@@ -193,7 +193,8 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 }
 
 // D[tmem] (+)= A[smem] * B[smem].  KIND: 0/1 = kind::f16 (f16 / bf16 inputs), 2 = kind::tf32, 3/4 = kind::f8f6f4
-// (e4m3 / e5m2 inputs).  The operand formats themselves are encoded in the instruction descriptor.
+// (e4m3 / e5m2 inputs), 5/6 = kind::i8 (u8 / s8 inputs, s32 accumulate).  The operand formats themselves are encoded in
+// the instruction descriptor.
 #define B200_UMMA_ASM(CGS, KINDS)                                                                             \
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                            \
                "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),       \
@@ -206,8 +207,10 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
     if constexpr (CG == 1) B200_UMMA_ASM("1", "f16"); else B200_UMMA_ASM("2", "f16");
   } else if constexpr (KIND == 2) {
     if constexpr (CG == 1) B200_UMMA_ASM("1", "tf32"); else B200_UMMA_ASM("2", "tf32");
-  } else {
+  } else if constexpr (KIND <= 4) {
     if constexpr (CG == 1) B200_UMMA_ASM("1", "f8f6f4"); else B200_UMMA_ASM("2", "f8f6f4");
+  } else {
+    if constexpr (CG == 1) B200_UMMA_ASM("1", "i8"); else B200_UMMA_ASM("2", "i8");
   }
 }
 
@@ -260,11 +263,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 }
 
 // Instruction descriptor for kind::f16 / kind::tf32, f32 accumulate.
-//   fmt: kind::f16 -> 0 = f16, 1 = bf16; kind::tf32 -> 2; kind::f8f6f4 -> 0 = e4m3, 1 = e5m2.
+//   fmt: kind::f16 -> 0 = f16, 1 = bf16; kind::tf32 -> 2; kind::f8f6f4 -> 0 = e4m3, 1 = e5m2; kind::i8 -> 0 = u8, 1 = s8.
 //   *_mn: 0 = K-major operand, 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t a_mn, uint32_t b_mn, uint32_t umma_m,
-                                                  uint32_t umma_n) {
-  return (1u << 4)            // accumulator format f32
+                                                  uint32_t umma_n, uint32_t c_fmt = 1 /* 1 = f32, 2 = s32 */) {
+  return (c_fmt << 4)         // accumulator format
          | (fmt << 7)         // A format
          | (fmt << 10)        // B format
          | (a_mn << 15)       // A major

@@ -119,7 +119,7 @@ int b200_event_destroy(b200_ctx* ctx, b200_event e);
  * out[..,m,n] = sum_k lhs[..,m,k] * rhs[..,k,n]; equal rank >= 2, leading dims broadcast (1 vs d); shapes/strides in
  * ELEMENTS (TensorHandle, cubecl-std/src/tensor/handle.rs:13-23).  f32 accumulation over k.  Inputs f16/bf16/f32 with
  * `out_dtype` = the input dtype or F32; fp8 inputs (F8E4M3 / F8E5M2, both operands the same format, kind::f8f6f4) with
- * `out_dtype` BF16, F16 or F32.  Row strides may be pitched (allocator.rs:21-72); rhs may be given transposed
+ * `out_dtype` BF16, F16 or F32; U8 / I8 inputs (kind::i8) with exact I32 accumulation and `out_dtype` I32.  Row strides may be pitched (allocator.rs:21-72); rhs may be given transposed
  * (stride_k == 1, MatrixBatchLayout::MildlyPermuted{transposed}, matrix_batch_layout.rs:8-19).  f32 inputs run on the tf32
  * tensor pipe, by default with a 3-way split that restores ~f32 accuracy (see "gemm.f32").
  * Returns B200_ERR_INVALID_ARG on shape mismatch -- the MatmulShapeError of shape.rs:489-517. */

@@ -160,6 +160,44 @@ def test_fp8_ragged_and_simt_fallback(client):
         check_against_oracle(got, a, b, "f32", tight=1e-5)
 
 
+# ------------------------------------------------------------------------------------------------ u8 / i8 -> i32 (kind::i8)
+@pytest.mark.parametrize("dtype", ["i8", "u8"])
+def test_golden_cmma_manual_int8(client, dtype):
+    # cmma.rs:1099-1196 instantiated test::<i8, i8, i32>(16, 8, 32) / <u8, u8, i32> (cmma.rs:1860-1863): exact integers
+    m, n, k = 16, 8, 32
+    lhs = np.array([[2 * i + j for j in range(k)] for i in range(m)], dtype=np.int64)
+    rhs = np.array([[3 * i + j for j in range(n)] for i in range(k)], dtype=np.int64)
+    npdt = np.int8 if dtype == "i8" else np.uint8
+    got = run_matmul_int(client, lhs.astype(npdt), rhs.astype(npdt), dtype)
+    assert np.array_equal(got.astype(np.int64), lhs @ rhs)
+
+
+@pytest.mark.parametrize("variant", ["auto", "2sm_n256", "1sm_n128", "simt"])
+@pytest.mark.parametrize("lhs_t", [False, True], ids=["lhs_mk", "lhs_km"])
+@pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
+@pytest.mark.parametrize("dtype", ["i8", "u8"])
+def test_parity_int8_exact(client, variant, lhs_t, rhs_t, dtype):
+    client.set_option("gemm.variant", variant)
+    M, N, K = 272, 320, 640
+    rng = np.random.default_rng(91)
+    lo, hi, npdt = (-128, 128, np.int8) if dtype == "i8" else (0, 256, np.uint8)
+    a = rng.integers(lo, hi, size=(K, M) if lhs_t else (M, K)).astype(npdt)
+    b = rng.integers(lo, hi, size=(N, K) if rhs_t else (K, N)).astype(npdt)
+    got = run_matmul_int(client, a, b, dtype, lhs_t=lhs_t, rhs_t=rhs_t)
+    exp = (a.T if lhs_t else a).astype(np.int64) @ (b.T if rhs_t else b).astype(np.int64)
+    assert np.array_equal(got.astype(np.int64), exp)   # integer work: bit-exact
+
+
+def run_matmul_int(client, a, b, dtype, lhs_t=False, rhs_t=False):
+    lhs = TensorHandle.from_numpy(client, a, dtype)
+    rhs = TensorHandle.from_numpy(client, b, dtype)
+    lhs = lhs.transposed() if lhs_t else lhs
+    rhs = rhs.transposed() if rhs_t else rhs
+    out = TensorHandle.empty_contiguous(client, matmul.calculate_matmul_output(lhs.shape, rhs.shape), "i32")
+    matmul.launch(client, lhs, rhs, out)
+    return out.to_numpy(client)
+
+
 def test_simt_is_bit_exact_with_reference_order(client):
     # the strided SIMT kernel accumulates exactly like cmma.rs:695-721 (f32, ascending k, separate mul/add)
     client.set_option("gemm.variant", "simt")
