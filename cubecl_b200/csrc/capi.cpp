@@ -231,6 +231,7 @@ struct SplitParams {
 struct XgpuParams {
   uint64_t mailbox[8];
   uint32_t rank, nranks, epoch, pad;
+  uint64_t index_offset;
 };
 static constexpr size_t kMailboxBytes = 4096;
 static constexpr uint32_t kWsMaxBlocks = 4096;
@@ -317,6 +318,18 @@ static int get_func(b200_ctx* c, const std::string& name, CUfunction* out) {
     }
   }
   return fail(B200_ERR_COMPILATION, "kernel '%s' not found in the prebuilt cubins", name.c_str());
+}
+
+extern "C" int b200_get_cubin(const char* name, const void** image, size_t* size) {
+  if (!name || !image || !size) return fail(B200_ERR_INVALID_ARG, "get_cubin: null argument");
+  const unsigned char *b = nullptr, *e = nullptr;
+  if (!strcmp(name, "gemm")) { b = b200_cubin_gemm; e = b200_cubin_gemm_end; }
+  else if (!strcmp(name, "reduce")) { b = b200_cubin_reduce; e = b200_cubin_reduce_end; }
+  else if (!strcmp(name, "aux")) { b = b200_cubin_aux; e = b200_cubin_aux_end; }
+  else return fail(B200_ERR_INVALID_ARG, "get_cubin: unknown image '%s' (gemm|reduce|aux)", name);
+  *image = b;
+  *size = static_cast<size_t>(e - b);
+  return B200_OK;
 }
 
 extern "C" int b200_device_count(int* count) {
@@ -1293,19 +1306,20 @@ extern "C" int b200_p2p_connect(b200_ctx* c, const int* device_ids, int n, const
   return B200_OK;
 }
 
-extern "C" int b200_reduce_all_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in,
-                                      b200_dptr out, uint64_t n, const int* device_ids, int ndev) {
-  CTX_ENTER(c);
-  if (op != B200_REDUCE_SUM) return fail(B200_ERR_UNSUPPORTED, "reduce_all_reduce: only SUM is fused");
+static int reduce_all_reduce_impl(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
+                                  uint64_t n, uint64_t index_offset, const int* device_ids, int ndev) {
+  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
+  if (op != B200_REDUCE_SUM && !arg) return fail(B200_ERR_UNSUPPORTED, "reduce_all_reduce: SUM, ARGMAX and ARGMIN are fused");
   if (in_dtype != B200_F32) return fail(B200_ERR_UNSUPPORTED, "reduce_all_reduce: only f32 input is fused");
   if (!device_ids || ndev < 1) return fail(B200_ERR_INVALID_ARG, "reduce_all_reduce: bad device set");
   if (!in || !out || n == 0) return fail(B200_ERR_INVALID_ARG, "reduce_all_reduce: null pointer or empty input");
+  if (arg && index_offset + n > (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "reduce_all_reduce: global indices must fit 32 bits");
   auto it = c->p2p.find(sorted_ids(device_ids, ndev));
   if (it == c->p2p.end()) return fail(B200_ERR_COMM, "reduce_all_reduce: device set not connected (call b200_p2p_connect)");
   P2PState& st = it->second;
   CUstream cs = resolve_stream(c, s);
   CUfunction f;
-  int rc = get_func(c, "reduce_all_sum_f32_xgpu", &f);
+  int rc = get_func(c, op == B200_REDUCE_SUM ? "reduce_all_sum_f32_xgpu" : op == B200_REDUCE_ARGMAX ? "reduce_all_argmax_f32_xgpu" : "reduce_all_argmin_f32_xgpu", &f);
   if (rc) return rc;
   CUdeviceptr ws;
   rc = reduce_workspace(c, cs, &ws);
@@ -1320,9 +1334,24 @@ extern "C" int b200_reduce_all_reduce(b200_ctx* c, b200_stream s, b200_reduce_op
   for (int r = 0; r < st.n; ++r) xg.mailbox[r] = st.mailbox[r];
   xg.rank = (uint32_t)st.rank;
   xg.nranks = (uint32_t)st.n;
+  xg.index_offset = index_offset;
   xg.epoch = ++st.epoch;  // every rank calls in the same order (collective semantics), so epochs agree
   void* args[] = {&p, &xg};
   return launch(c, f, grid, 1, 1, threads, 0, 1, cs, args);
+}
+
+extern "C" int b200_reduce_all_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in,
+                                      b200_dptr out, uint64_t n, const int* device_ids, int ndev) {
+  CTX_ENTER(c);
+  if (op != B200_REDUCE_SUM) return fail(B200_ERR_UNSUPPORTED, "reduce_all_reduce: SUM only (use b200_argreduce_all_reduce for arg ops)");
+  return reduce_all_reduce_impl(c, s, op, in_dtype, in, out, n, 0, device_ids, ndev);
+}
+
+extern "C" int b200_argreduce_all_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in,
+                                         b200_dptr out, uint64_t n, uint64_t index_offset, const int* device_ids, int ndev) {
+  CTX_ENTER(c);
+  if (op != B200_REDUCE_ARGMAX && op != B200_REDUCE_ARGMIN) return fail(B200_ERR_INVALID_ARG, "argreduce_all_reduce: ARGMAX or ARGMIN");
+  return reduce_all_reduce_impl(c, s, op, in_dtype, in, out, n, index_offset, device_ids, ndev);
 }
 
 // ================================================================================================ generators / probes

@@ -31,7 +31,10 @@ struct ReduceParams {
 struct XgpuParams {
   uint64_t mailbox[8];   // device pointers of every rank's mailbox (own included), indexed by rank
   uint32_t rank, nranks, epoch, pad;
+  uint64_t index_offset; // arg ops: global index of this rank's element 0 (outer-axis shard offset)
 };
+// mailbox layout: [0,128) value slots[2][8]; [128,256) index slots[2][8] (arg ops: second word, same epoch tag)
+constexpr uint32_t kMailboxIndexOffset = 128;
 
 enum : int { OP_SUM = 0, OP_PROD = 1, OP_MAX = 2, OP_MIN = 3, OP_ARGMAX = 4, OP_ARGMIN = 5 };
 enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
@@ -381,8 +384,8 @@ __device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const Xgp
   }
 }
 
-template <int OP, int DT>
-__device__ __forceinline__ void argreduce_all_body(const ReduceParams& p) {
+template <int OP, int DT, bool XGPU = false>
+__device__ __forceinline__ void argreduce_all_body(const ReduceParams& p, const XgpuParams* xg = nullptr) {
   using E = Elem<DT>;
   constexpr int VEC = E::VEC;
   __shared__ float s_v[kMaxWarps];
@@ -428,9 +431,45 @@ __device__ __forceinline__ void argreduce_all_body(const ReduceParams& p) {
       if (arg_better<OP>(v, i, ov, oi)) { v = ov; i = oi; }
     }
     block_arg_reduce<OP>(v, i, s_v, s_i);
-    if (threadIdx.x == 0) {
-      reinterpret_cast<uint32_t*>(p.out)[0] = static_cast<uint32_t>(i);
-      *ticket = 0;
+    if constexpr (!XGPU) {
+      if (threadIdx.x == 0) {
+        reinterpret_cast<uint32_t*>(p.out)[0] = static_cast<uint32_t>(i);
+        *ticket = 0;
+      }
+    } else if (threadIdx.x < 32) {
+      // ---- fused (value, index) exchange: NCCL has no arg-reduce; every rank publishes its pair, then selects in rank
+      // order with the same tie rule (lowest GLOBAL index), so all ranks agree.  Global indices must fit 32 bits.
+      __shared__ float s_pv[8];
+      __shared__ uint32_t s_pi[8];
+      v = __shfl_sync(0xffffffffu, v, 0);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      const uint32_t gi = static_cast<uint32_t>(i + xg->index_offset);
+      const uint32_t slot_base = (xg->epoch & 1u) * 8u;
+      const uint64_t tag = static_cast<uint64_t>(xg->epoch) << 32;
+      if (threadIdx.x < xg->nranks) {
+        const uint32_t peer = threadIdx.x;
+        st_sys_u64(xg->mailbox[peer] + (slot_base + xg->rank) * 8ull, tag | __float_as_uint(v));
+        st_sys_u64(xg->mailbox[peer] + kMailboxIndexOffset + (slot_base + xg->rank) * 8ull, tag | gi);
+        const uint64_t src = xg->mailbox[xg->rank] + (slot_base + peer) * 8ull;
+        const uint64_t t0 = globaltimer_ns();
+        uint64_t w0 = ld_sys_u64(src), w1 = ld_sys_u64(src + kMailboxIndexOffset);
+        while (static_cast<uint32_t>(w0 >> 32) != xg->epoch || static_cast<uint32_t>(w1 >> 32) != xg->epoch) {
+          if (globaltimer_ns() - t0 > 4000000000ull) asm volatile("trap;");
+          w0 = ld_sys_u64(src);
+          w1 = ld_sys_u64(src + kMailboxIndexOffset);
+        }
+        s_pv[peer] = __uint_as_float(static_cast<uint32_t>(w0));
+        s_pi[peer] = static_cast<uint32_t>(w1);
+      }
+      __syncwarp();
+      if (threadIdx.x == 0) {
+        float bv = s_pv[0];
+        uint64_t bi = s_pi[0];
+        for (uint32_t r = 1; r < xg->nranks; ++r)
+          if (arg_better<OP>(bv, bi, s_pv[r], s_pi[r])) { bv = s_pv[r]; bi = s_pi[r]; }
+        reinterpret_cast<uint32_t*>(p.out)[0] = static_cast<uint32_t>(bi);
+        *ticket = 0;
+      }
     }
   }
 }
@@ -623,6 +662,15 @@ extern "C" __global__ void __launch_bounds__(512) reduce_all_sum_f32_xgpu(const 
   }
 REDUCE_ALL_BLOCKED(reduce_all_sum_f32_b4, 4)
 REDUCE_ALL_BLOCKED(reduce_all_sum_f32_b8, 8)
+
+extern "C" __global__ void __launch_bounds__(1024) reduce_all_argmax_f32_xgpu(const __grid_constant__ ReduceParams p,
+                                                                              const __grid_constant__ XgpuParams xg) {
+  argreduce_all_body<OP_ARGMAX, DT_F32, true>(p, &xg);
+}
+extern "C" __global__ void __launch_bounds__(1024) reduce_all_argmin_f32_xgpu(const __grid_constant__ ReduceParams p,
+                                                                              const __grid_constant__ XgpuParams xg) {
+  argreduce_all_body<OP_ARGMIN, DT_F32, true>(p, &xg);
+}
 
 // tuning variants of the headline kernel (f32 sum over all elements); the host picks one by name.
 REDUCE_ALL(reduce_all_sum_f32_u4, OP_SUM, DT_F32, 4, false)

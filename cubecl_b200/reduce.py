@@ -69,3 +69,20 @@ def launch_all_reduce(client: ComputeClient, input: TensorHandle, output: Tensor
                                                       C.c_uint64(output.handle.ptr), input.size(), _ffi.int_array(ids), len(ids)))
     except B200Error as e:
         client._defer(e)
+
+
+def launch_arg_all_reduce(client: ComputeClient, input: TensorHandle, output: TensorHandle, device_ids, index_offset: int,
+                          op: str = "argmax") -> None:
+    """Global argmax/argmin over the concatenation of every rank's `input` (outer-axis shards): output[0] (u32) = global
+    index on every rank.  One kernel per rank; the (value, index) pairs travel through the NVLink mailboxes."""
+    try:
+        if op not in ("argmax", "argmin"):
+            raise B200Error(6, "launch_arg_all_reduce: op must be argmax or argmin")
+        if input.dtype != "f32" or output.dtype != "u32" or not input.is_contiguous():
+            raise B200Error(7, "launch_arg_all_reduce: contiguous f32 in, u32 out")
+        ids = sorted(int(d) for d in device_ids)
+        _ffi.check(client._lib.b200_argreduce_all_reduce(client._ctx, None, OPS[op], DTYPES["f32"], C.c_uint64(input.handle.ptr),
+                                                         C.c_uint64(output.handle.ptr), input.size(), int(index_offset),
+                                                         _ffi.int_array(ids), len(ids)))
+    except B200Error as e:
+        client._defer(e)

@@ -80,6 +80,9 @@ typedef struct b200_props {
 /* ---- lifecycle: R::client(device) -> DeviceService::init (cubecl-cuda/src/runtime.rs:52-350) ------------------------ */
 int b200_abi_version(void);
 int b200_device_count(int* count);
+/* The embedded prebuilt sm_100a images ("gemm" | "reduce" | "aux"), for a host that prefers to cuModuleLoadData them into
+ * its own module cache (CudaContext::modules, crates/cubecl-cuda/src/compute/context.rs:38-62,293). No GPU needed. */
+int b200_get_cubin(const char* name, const void** image, size_t* size);
 int b200_init(int device, b200_ctx** out);   /* cuInit, primary ctx retain, load the embedded sm_100a cubins (context.rs:293) */
 int b200_destroy(b200_ctx* ctx);
 int b200_get_props(b200_ctx* ctx, b200_props* out);
@@ -173,6 +176,12 @@ int b200_p2p_connect(b200_ctx* ctx, const int* device_ids, int n, const void* ip
  * order; a missing peer trips the kernel's 4 s deadline (device trap -> B200_ERR_UNHEALTHY at sync).  SUM of F32 only. */
 int b200_reduce_all_reduce(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
                            uint64_t n, const int* device_ids, int ndev);
+
+/* Arg-reduce across ranks (NCCL has no arg-reduce: SURVEY 8e "all-gather 8 pairs + local select", here inside the kernel):
+ * out[0] (u32, on every rank) = GLOBAL index of the extremum of the concatenation of all ranks' inputs, where this rank's
+ * element 0 has global index `index_offset`.  Same tie / NaN rule as b200_reduce.  Global indices must fit 32 bits. */
+int b200_argreduce_all_reduce(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
+                              uint64_t n, uint64_t index_offset, const int* device_ids, int ndev);
 
 /* ---- synthetic operands + reference-equivalent probes (examples/throughput) ----------------------------------------- */
 /* out[i] = lo + u(seed,i) * (hi - lo), u in [0,1) from a counter hash the host can reproduce (cubecl_b200/synth.py);

@@ -40,6 +40,18 @@ def test_cubins_are_embedded_and_sm100a():
     assert "SHFL.DOWN" in red
 
 
+def test_embedded_images_are_elf_cubins_for_sm100():
+    # "driver-API load of a prebuilt sm_100a .cubin": the images inside the .so are the nvcc -cubin outputs, byte for byte
+    lib = _ffi.load()
+    for name in ("gemm", "reduce", "aux"):
+        img, size = ctypes.c_void_p(), ctypes.c_size_t()
+        assert lib.b200_get_cubin(name.encode(), ctypes.byref(img), ctypes.byref(size)) == 0
+        blob = ctypes.string_at(img.value, size.value)
+        assert blob[:4] == b"\x7fELF"
+        assert blob == (ROOT / "cubecl_b200" / "build" / f"{name}.cubin").read_bytes()
+    assert lib.b200_get_cubin(b"nope", ctypes.byref(img), ctypes.byref(size)) == 6
+
+
 def test_no_gpu_fails_loudly_not_silently():
     import torch
     if torch.cuda.is_available():

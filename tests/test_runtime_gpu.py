@@ -27,6 +27,46 @@ def test_props_and_pool(client):
     assert np.array_equal(np.frombuffer(client.read_one(h3), dtype=np.float32), data)
 
 
+def test_error_paths_are_loud(client):
+    from cubecl_b200 import B200Error, _ffi
+    import ctypes as C
+    with pytest.raises(B200Error) as ei:
+        client.set_option("no.such.option", 1)
+    assert ei.value.kind == "InvalidArgument"
+    assert client._lib.b200_free(client._ctx, C.c_uint64(0xdead000)) == 6          # pointer not owned by the pool
+    h = client.empty(64)
+    assert client._lib.b200_free(client._ctx, C.c_uint64(h.ptr)) == 0
+    assert client._lib.b200_free(client._ctx, C.c_uint64(h.ptr)) == 6          # double free
+    h._owner = False
+    bad = C.c_void_p()
+    assert client._lib.b200_init(99, C.byref(bad)) == 8                            # no such device
+    with pytest.raises(B200Error):
+        client.set_option("gemm.variant", "2sm_n128")
+        try:
+            a = TensorHandle.empty_contiguous(client, [64, 128], "f8e4m3")
+            b = TensorHandle.empty_contiguous(client, [128, 64], "f8e4m3")
+            o = TensorHandle.empty_contiguous(client, [64, 64], "f32")
+            _ffi.check(client._lib.b200_matmul(client._ctx, None, 10, 0, C.c_uint64(a.handle.ptr), C.c_uint64(b.handle.ptr),
+                                               C.c_uint64(o.handle.ptr), 2, _ffi.u64_array([64, 128]), _ffi.u64_array([128, 1]),
+                                               _ffi.u64_array([128, 64]), _ffi.u64_array([64, 1]), _ffi.u64_array([64, 64]),
+                                               _ffi.u64_array([64, 1])))       # no fp8 2sm_n128 variant exists
+        finally:
+            client.set_option("gemm.variant", "auto")
+
+
+def test_pooled_handles_are_recycled_per_size_class(client):
+    before = client.memory_usage()
+    hs = [client.empty(3 << 20) for _ in range(4)]
+    ptrs = sorted(h.ptr for h in hs)
+    del hs
+    again = [client.empty(3 << 20) for _ in range(4)]
+    assert sorted(h.ptr for h in again) == ptrs                                    # exclusive pages come back
+    del again
+    assert client.memory_usage().bytes_in_use == before.bytes_in_use
+    client.memory_cleanup()
+    assert client.memory_usage().bytes_reserved <= before.bytes_reserved
+
+
 @pytest.mark.parametrize("dtype", ["f32", "f16", "bf16", "f8e4m3", "f8e5m2"])
 def test_device_generator_matches_host_mirror(client, dtype):
     n = 100003
@@ -120,3 +160,31 @@ def test_fused_reduce_all_reduce_over_peer_memory():
         [t.join() for t in threads]
         for r, c in enumerate(clients):
             assert float(outs[r].to_numpy(c)[0]) == expect
+
+
+def test_fused_argmax_all_reduce_over_peer_memory():
+    # outer-axis shards of one logical vector; ties across ranks resolve to the lowest GLOBAL index; first NaN wins
+    n_dev = ComputeClient.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 devices")
+    clients = [ComputeClient.load(d) for d in range(n_dev)]
+    exports = [c.p2p_export() for c in clients]
+    for c in clients:
+        c.p2p_connect(exports)
+    ids = list(range(n_dev))
+    per = (1 << 20) + 8
+    full = synth.uniform_f32(33, per * n_dev, -1.0, 1.0)
+    full[[5, per + 17, per * n_dev - 3]] = 7.0          # three equal maxima: global index 5 must win
+    cases = [("argmax", full.copy(), 5)]
+    mn = full.copy(); mn[per * (n_dev - 1) + 11] = -9.0
+    cases.append(("argmin", mn, per * (n_dev - 1) + 11))
+    nan = full.copy(); nan[per + 100] = np.nan; nan[per * (n_dev - 1) + 3] = np.nan
+    cases.append(("argmax", nan, per + 100))
+    for op, data, expect in cases:
+        ins = [TensorHandle.from_numpy(c, data[r * per:(r + 1) * per], "f32") for r, c in enumerate(clients)]
+        outs = [TensorHandle.empty_contiguous(c, [1], "u32") for c in clients]
+        threads = [threading.Thread(target=reduce.launch_arg_all_reduce, args=(c, ins[r], outs[r], ids, r * per, op)) for r, c in enumerate(clients)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        for r, c in enumerate(clients):
+            assert int(outs[r].to_numpy(c)[0]) == expect
