@@ -453,65 +453,75 @@ def main():
     line["reduce"] = red
 
     # ------------------------------------------------------------------ other BASELINE configs (N-independent per GPU)
-    if not args.quick:
-        extra_steps = max(5, min(args.steps, 10))
-        n4 = 4096
-        # config 5: batched bf16, 8 x 4096^3 per GPU (B = 8N sharded over the batch axis)
-        ab = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
-        bb = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
-        ob = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
-        c.fill_uniform(ab.handle, "bf16", 8 * n4 * n4, 6, -1.0, 1.0)
-        c.fill_uniform(bb.handle, "bf16", 8 * n4 * n4, 7, -1.0, 1.0)
-        ms_b, _ = timed(lambda: matmul.launch(c, ab, bb, ob), extra_steps, 3)
-        line["batched_bf16_4096"] = {"value": world * 8 * 2.0 * n4 ** 3 * extra_steps / (ms_b * 1e-3) / 1e12, "unit": "TFLOP/s",
-                                     "config": f"B={8 * world} x 4096^3 bf16, 8 batches per GPU, batch-axis shard, no collective"}
-        del ab, bb, ob
-        # config 2: f32 4096^3 on the tf32 tensor pipe (both f32 modes)
-        af = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
-        bf = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
-        of = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
-        c.fill_uniform(af.handle, "f32", n4 * n4, 1, -1.0, 1.0)
-        c.fill_uniform(bf.handle, "f32", n4 * n4, 2, -1.0, 1.0)
-        f32res = {}
-        for mode in ("3xtf32", "tf32"):
-            c.set_option("gemm.f32", mode)
-            ms_f, _ = timed(lambda: matmul.launch(c, af, bf, of), extra_steps, 3)
-            f32res[mode] = world * 2.0 * n4 ** 3 * extra_steps / (ms_f * 1e-3) / 1e12
-        c.set_option("gemm.f32", "3xtf32")
-        line["matmul_f32_4096"] = {"unit": "TFLOP/s (f32-equivalent 2*N^3)", "3xtf32_default": f32res["3xtf32"], "tf32": f32res["tf32"]}
-        del af, bf, of
-        # widening row: fp8 e4m3 8192^3 -> bf16 on the same kernel (kind::f8f6f4)
-        a8 = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "f8e4m3")
-        b8 = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "f8e4m3")
-        c.fill_uniform(a8.handle, "f8e4m3", N_MM * N_MM, 8, -1.0, 1.0)
-        c.fill_uniform(b8.handle, "f8e4m3", N_MM * N_MM, 9, -1.0, 1.0)
-        ms_8, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
-        line["matmul_fp8_8192"] = {"value": world * FLOPS_MM * extra_steps / (ms_8 * 1e-3) / 1e12, "unit": "TFLOP/s",
-                                   "config": "fp8 e4m3 x e4m3 -> bf16, f32 accumulate, 8192^3 per GPU"}
-        del a8, b8
-        # what CubeCL's own kernels reach on this GPU (hand-written from its emit rules)
-        if world == 1:
-            scratch = c.empty(1024)
-            ops = [0.0]
+    def other_configs():
+        if not args.quick:
+            extra_steps = max(5, min(args.steps, 10))
+            n4 = 4096
+            # config 5: batched bf16, 8 x 4096^3 per GPU (B = 8N sharded over the batch axis)
+            ab = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
+            bb = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
+            ob = TensorHandle.empty_contiguous(c, [8, n4, n4], "bf16")
+            c.fill_uniform(ab.handle, "bf16", 8 * n4 * n4, 6, -1.0, 1.0)
+            c.fill_uniform(bb.handle, "bf16", 8 * n4 * n4, 7, -1.0, 1.0)
+            ms_b, _ = timed(lambda: matmul.launch(c, ab, bb, ob), extra_steps, 3)
+            line["batched_bf16_4096"] = {"value": world * 8 * 2.0 * n4 ** 3 * extra_steps / (ms_b * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                         "config": f"B={8 * world} x 4096^3 bf16, 8 batches per GPU, batch-axis shard, no collective"}
+            del ab, bb, ob
+            # config 2: f32 4096^3 on the tf32 tensor pipe (both f32 modes)
+            af = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
+            bf = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
+            of = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
+            c.fill_uniform(af.handle, "f32", n4 * n4, 1, -1.0, 1.0)
+            c.fill_uniform(bf.handle, "f32", n4 * n4, 2, -1.0, 1.0)
+            f32res = {}
+            for mode in ("3xtf32", "tf32"):
+                c.set_option("gemm.f32", mode)
+                ms_f, _ = timed(lambda: matmul.launch(c, af, bf, of), extra_steps, 3)
+                f32res[mode] = world * 2.0 * n4 ** 3 * extra_steps / (ms_f * 1e-3) / 1e12
+            c.set_option("gemm.f32", "3xtf32")
+            line["matmul_f32_4096"] = {"unit": "TFLOP/s (f32-equivalent 2*N^3)", "3xtf32_default": f32res["3xtf32"], "tf32": f32res["tf32"]}
+            del af, bf, of
+            # widening row: fp8 e4m3 8192^3 -> bf16 on the same kernel (kind::f8f6f4)
+            a8 = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "f8e4m3")
+            b8 = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "f8e4m3")
+            c.fill_uniform(a8.handle, "f8e4m3", N_MM * N_MM, 8, -1.0, 1.0)
+            c.fill_uniform(b8.handle, "f8e4m3", N_MM * N_MM, 9, -1.0, 1.0)
+            ms_8, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
+            line["matmul_fp8_8192"] = {"value": world * FLOPS_MM * extra_steps / (ms_8 * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                       "config": "fp8 e4m3 x e4m3 -> bf16, f32 accumulate, 8192^3 per GPU"}
+            del a8, b8
+            # what CubeCL's own kernels reach on this GPU (hand-written from its emit rules)
+            if world == 1:
+                scratch = c.empty(1024)
+                ops = [0.0]
 
-            def wm():
-                ops[0] = c.probe_wmma("bf16", 2048, scratch)
+                def wm():
+                    ops[0] = c.probe_wmma("bf16", 2048, scratch)
 
-            ms_p, _ = timed(wm, 5, 2)
-            uops = [0.0]
+                ms_p, _ = timed(wm, 5, 2)
+                uops = [0.0]
 
-            def um():
-                uops[0] = c.probe_umma(8192, scratch)
+                def um():
+                    uops[0] = c.probe_umma(8192, scratch)
 
-            ms_u, _ = timed(um, 5, 2)
-            buf = c.empty(512 << 20)
-            c.fill_modulo(buf, "f32", (512 << 20) // 4, 8)
-            ms_m, _ = timed(lambda: c.probe_memread(buf, 512 << 20, scratch), 10, 2)
-            line["tcgen05_probe_tflops"] = uops[0] * 5 / (ms_u * 1e-3) / 1e12
-            line["reference_equivalent"] = {"wmma_bf16_probe_tflops": ops[0] * 5 / (ms_p * 1e-3) / 1e12,
-                                            "vec4_read_probe_gbs": (512 << 20) * 10 / (ms_m * 1e-3) / 1e9,
-                                            "note": "compute_cmma.rs / memory_read.rs kernels as CubeCL would JIT them for sm_100a (wmma, 128-bit loads)"}
-            del buf
+                ms_u, _ = timed(um, 5, 2)
+                buf = c.empty(512 << 20)
+                c.fill_modulo(buf, "f32", (512 << 20) // 4, 8)
+                ms_m, _ = timed(lambda: c.probe_memread(buf, 512 << 20, scratch), 10, 2)
+                line["tcgen05_probe_tflops"] = uops[0] * 5 / (ms_u * 1e-3) / 1e12
+                line["reference_equivalent"] = {"wmma_bf16_probe_tflops": ops[0] * 5 / (ms_p * 1e-3) / 1e12,
+                                                "vec4_read_probe_gbs": (512 << 20) * 10 / (ms_m * 1e-3) / 1e9,
+                                                "note": "compute_cmma.rs / memory_read.rs kernels as CubeCL would JIT them for sm_100a (wmma, 128-bit loads)"}
+                del buf
+
+    try:
+        other_configs()
+    except Exception as ex:  # noqa: BLE001  (secondary rows must never cost the headline line)
+        line["secondary_error"] = repr(ex)
+        try:
+            c.flush()
+        except Exception:  # noqa: BLE001
+            pass
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     if rank0 and world == 1:

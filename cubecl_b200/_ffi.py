@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200_get_cubin": (C.c_int, [C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "b200_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "b200_destroy": (C.c_int, [_vp]),
+    "b200_plan_begin": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "b200_plan_text": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200_get_props": (C.c_int, [_vp, C.POINTER(Props)]),
     "b200_set_option": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
     "b200_launch_count": (C.c_int, [_vp, _u64p]),

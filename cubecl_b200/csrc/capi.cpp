@@ -279,13 +279,24 @@ struct b200_ctx {
   CUdeviceptr mailbox = 0;
   std::unordered_map<std::string, std::string> options;
   uint64_t launches = 0;
+  // Dry-run planning context (no driver, no device): every launch / descriptor / pool request is RECORDED instead of
+  // executed, so the host logic (validation, batch collapse, variant choice, split plans) is testable on a CPU box.
+  // Mirrors the reference's DryRun mode (crates/cubecl-runtime/src/dry_run.rs:45,88,121).
+  bool dry = false;
+  std::string plan;
+  std::string pending_kernel;
+  uint64_t fake_next = 0x7000000000ull;
 };
 
 static inline CUstream resolve_stream(b200_ctx* c, b200_stream s) { return s ? static_cast<CUstream>(s) : c->stream; }
 
 #define CTX_ENTER(c)                                                  \
   if (!(c)) return fail(B200_ERR_INVALID_ARG, "null context");        \
-  CU_CHECK(g_drv.cuCtxSetCurrent_p((c)->cuctx));
+  if (!(c)->dry) CU_CHECK(g_drv.cuCtxSetCurrent_p((c)->cuctx));
+// entry points that talk to the driver directly (copies, streams, events, collectives) do not exist on a planning context
+#define CTX_ENTER_DEVICE(c)                                           \
+  CTX_ENTER(c);                                                       \
+  if ((c)->dry) return fail(B200_ERR_UNSUPPORTED, "%s is not available on a dry-run planning context", __func__);
 
 static std::string opt(b200_ctx* c, const char* key, const char* dflt) {
   auto it = c->options.find(key);
@@ -307,6 +318,7 @@ static int load_module(b200_ctx* c, const unsigned char* begin, const unsigned c
 }
 
 static int get_func(b200_ctx* c, const std::string& name, CUfunction* out) {
+  if (c->dry) { c->pending_kernel = name; *out = nullptr; return B200_OK; }
   auto it = c->funcs.find(name);
   if (it != c->funcs.end()) { *out = it->second; return B200_OK; }
   for (CUmodule m : c->modules) {
@@ -393,6 +405,7 @@ extern "C" int b200_init(int device, b200_ctx** out) {
 
 extern "C" int b200_destroy(b200_ctx* c) {
   if (!c) return B200_OK;
+  if (c->dry) { delete c; return B200_OK; }
   if (g_drv.ok && g_drv.cuCtxSetCurrent_p(c->cuctx) == CUDA_SUCCESS) {
     g_drv.cuCtxSynchronize_p();
     for (auto& kv : c->comms)
@@ -410,6 +423,31 @@ extern "C" int b200_destroy(b200_ctx* c) {
     g_drv.cuDevicePrimaryCtxRelease_p(c->dev);
   }
   delete c;
+  return B200_OK;
+}
+
+extern "C" int b200_plan_begin(int num_sms, b200_ctx** out) {
+  if (!out || num_sms < 1) return fail(B200_ERR_INVALID_ARG, "plan_begin: bad arguments");
+  b200_ctx* c = new b200_ctx();
+  c->dry = true;
+  c->device = 0;
+  c->props.num_sms = num_sms;
+  c->props.cc_major = 10;
+  c->props.plane_size = 32;
+  snprintf(c->props.name, sizeof(c->props.name), "dry-run (%d SMs)", num_sms);
+  *out = c;
+  return B200_OK;
+}
+
+extern "C" int b200_plan_text(b200_ctx* c, char* buf, size_t capacity, size_t* needed) {
+  if (!c || !c->dry) return fail(B200_ERR_INVALID_ARG, "plan_text: not a planning context");
+  if (needed) *needed = c->plan.size() + 1;
+  if (buf && capacity) {
+    const size_t n = std::min(capacity - 1, c->plan.size());
+    memcpy(buf, c->plan.data(), n);
+    buf[n] = 0;
+    if (capacity > c->plan.size()) c->plan.clear();
+  }
   return B200_OK;
 }
 
@@ -443,6 +481,14 @@ static size_t pool_round(size_t bytes) {
 
 static int pool_alloc(b200_ctx* c, size_t bytes, CUdeviceptr* out) {
   const size_t sz = pool_round(bytes);
+  if (c->dry) {
+    *out = c->fake_next;
+    c->fake_next += (sz + 511) / 512 * 512;
+    char line[96];
+    snprintf(line, sizeof(line), "alloc %zu\n", sz);
+    c->plan += line;
+    return B200_OK;
+  }
   auto it = c->free_lists.find(sz);
   if (it != c->free_lists.end() && !it->second.empty()) {
     *out = it->second.back();
@@ -470,6 +516,7 @@ static int pool_alloc(b200_ctx* c, size_t bytes, CUdeviceptr* out) {
 }
 
 static int pool_free(b200_ctx* c, CUdeviceptr p) {
+  if (c->dry) return B200_OK;
   auto it = c->blocks.find(p);
   if (it == c->blocks.end() || !it->second.in_use) return fail(B200_ERR_INVALID_ARG, "b200_free: pointer not owned by this context");
   it->second.in_use = false;
@@ -501,7 +548,7 @@ extern "C" int b200_memory_usage(b200_ctx* c, uint64_t* in_use, uint64_t* reserv
 }
 
 extern "C" int b200_memory_cleanup(b200_ctx* c) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   CU_CHECK(g_drv.cuCtxSynchronize_p());
   for (auto& fl : c->free_lists) {
     for (CUdeviceptr q : fl.second) { g_drv.cuMemFree_p(q); c->bytes_reserved -= fl.first; c->blocks.erase(q); }
@@ -511,7 +558,7 @@ extern "C" int b200_memory_cleanup(b200_ctx* c) {
 }
 
 extern "C" int b200_host_alloc(b200_ctx* c, size_t bytes, void** out) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
   void* p = nullptr;
   CU_CHECK(g_drv.cuMemAllocHost_p(&p, bytes ? bytes : 1));
@@ -521,7 +568,7 @@ extern "C" int b200_host_alloc(b200_ctx* c, size_t bytes, void** out) {
 }
 
 extern "C" int b200_host_free(b200_ctx* c, void* ptr) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   auto it = c->pinned.find(ptr);
   if (it == c->pinned.end()) return fail(B200_ERR_INVALID_ARG, "b200_host_free: pointer not owned by this context");
   CU_CHECK(g_drv.cuMemFreeHost_p(ptr));
@@ -530,28 +577,28 @@ extern "C" int b200_host_free(b200_ctx* c, void* ptr) {
 }
 
 extern "C" int b200_write(b200_ctx* c, b200_stream s, b200_dptr dst, const void* src, size_t bytes) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (bytes == 0) return B200_OK;
   CU_CHECK(g_drv.cuMemcpyHtoDAsync_p(static_cast<CUdeviceptr>(dst), src, bytes, resolve_stream(c, s)));
   return B200_OK;
 }
 
 extern "C" int b200_read(b200_ctx* c, b200_stream s, void* dst, b200_dptr src, size_t bytes) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (bytes == 0) return B200_OK;
   CU_CHECK(g_drv.cuMemcpyDtoHAsync_p(dst, static_cast<CUdeviceptr>(src), bytes, resolve_stream(c, s)));
   return B200_OK;
 }
 
 extern "C" int b200_copy(b200_ctx* c, b200_stream s, b200_dptr dst, b200_dptr src, size_t bytes) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (bytes == 0) return B200_OK;
   CU_CHECK(g_drv.cuMemcpyDtoDAsync_p(static_cast<CUdeviceptr>(dst), static_cast<CUdeviceptr>(src), bytes, resolve_stream(c, s)));
   return B200_OK;
 }
 
 extern "C" int b200_memset32(b200_ctx* c, b200_stream s, b200_dptr dst, uint32_t value, size_t words) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (words == 0) return B200_OK;
   CU_CHECK(g_drv.cuMemsetD32Async_p(static_cast<CUdeviceptr>(dst), value, words, resolve_stream(c, s)));
   return B200_OK;
@@ -559,7 +606,7 @@ extern "C" int b200_memset32(b200_ctx* c, b200_stream s, b200_dptr dst, uint32_t
 
 // ================================================================================================ streams / events
 extern "C" int b200_stream_create(b200_ctx* c, b200_stream* out) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
   CUstream s;
   CU_CHECK(g_drv.cuStreamCreate_p(&s, CU_STREAM_NON_BLOCKING));
@@ -568,7 +615,7 @@ extern "C" int b200_stream_create(b200_ctx* c, b200_stream* out) {
 }
 
 extern "C" int b200_stream_destroy(b200_ctx* c, b200_stream s) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!s) return B200_OK;
   auto it = c->reduce_ws.find(static_cast<CUstream>(s));
   if (it != c->reduce_ws.end()) { g_drv.cuMemFree_p(it->second); c->reduce_ws.erase(it); }
@@ -578,13 +625,14 @@ extern "C" int b200_stream_destroy(b200_ctx* c, b200_stream s) {
 
 extern "C" int b200_sync(b200_ctx* c, b200_stream s) {
   CTX_ENTER(c);
+  if (c->dry) return B200_OK;
   CUresult r = g_drv.cuStreamSynchronize_p(resolve_stream(c, s));
   if (r != CUDA_SUCCESS) return fail(B200_ERR_UNHEALTHY, "stream sync surfaced a device fault: %s (%d)", cu_err(r), (int)r);
   return B200_OK;
 }
 
 extern "C" int b200_event_create(b200_ctx* c, b200_event* out) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
   CUevent e;
   CU_CHECK(g_drv.cuEventCreate_p(&e, CU_EVENT_DEFAULT));
@@ -593,19 +641,19 @@ extern "C" int b200_event_create(b200_ctx* c, b200_event* out) {
 }
 
 extern "C" int b200_event_record(b200_ctx* c, b200_event e, b200_stream s) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   CU_CHECK(g_drv.cuEventRecord_p(static_cast<CUevent>(e), resolve_stream(c, s)));
   return B200_OK;
 }
 
 extern "C" int b200_stream_wait_event(b200_ctx* c, b200_stream s, b200_event e) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   CU_CHECK(g_drv.cuStreamWaitEvent_p(resolve_stream(c, s), static_cast<CUevent>(e), 0));
   return B200_OK;
 }
 
 extern "C" int b200_event_elapsed_ms(b200_ctx* c, b200_event a, b200_event b, float* ms) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!ms) return fail(B200_ERR_INVALID_ARG, "null ms");
   CU_CHECK(g_drv.cuEventSynchronize_p(static_cast<CUevent>(b)));
   CU_CHECK(g_drv.cuEventElapsedTime_p(ms, static_cast<CUevent>(a), static_cast<CUevent>(b)));
@@ -613,7 +661,7 @@ extern "C" int b200_event_elapsed_ms(b200_ctx* c, b200_event a, b200_event b, fl
 }
 
 extern "C" int b200_event_destroy(b200_ctx* c, b200_event e) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (e) CU_CHECK(g_drv.cuEventDestroy_p(static_cast<CUevent>(e)));
   return B200_OK;
 }
@@ -632,6 +680,14 @@ static int launch(b200_ctx* c, CUfunction f, unsigned grid_x, unsigned grid_y, u
     at[0].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
     at[0].value.clusterDim.x = cluster_x; at[0].value.clusterDim.y = 1; at[0].value.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  if (c->dry) {
+    char line[256];
+    snprintf(line, sizeof(line), "launch %s grid=(%u,%u,%u) block=%u smem=%u cluster=%u\n", c->pending_kernel.c_str(), grid_x,
+             grid_y, grid_z, block, smem, cluster_x);
+    c->plan += line;
+    c->launches++;
+    return B200_OK;
   }
   CUresult r = g_drv.cuLaunchKernelEx_p(&cfg, f, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(map_cu(r), "cuLaunchKernelEx failed: %s (%d)", cu_err(r), (int)r);
@@ -674,6 +730,15 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
   snprintf(key, sizeof(key), "%d|%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u", (int)dt, (int)swz, (unsigned long long)base,
            (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_elems,
            (unsigned long long)s2_elems, b0, b1);
+  if (c->dry) {
+    char line[256];
+    snprintf(line, sizeof(line), "tmap esz=%zu dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u) swizzle=%d\n", esz,
+             (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)(s1_elems * esz),
+             (unsigned long long)(s2_elems * esz), b0, b1, (int)swz);
+    c->plan += line;
+    memset(out, 0, sizeof(*out));
+    return B200_OK;
+  }
   auto it = c->tmap_cache.find(key);
   if (it != c->tmap_cache.end()) { *out = it->second; return B200_OK; }
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -748,6 +813,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (forced != "auto" && forced != v.tag) continue;
     if (forced == "auto" && v.eff <= 0.0) continue;
     if (!variant_has_dtype(v, g.in_dtype)) continue;
+    if (forced == "auto" && v.cg == 2 && g.M <= 128) continue;  // a CTA pair would idle its second half: one CTA per tile
     const uint64_t tm = (g.M + 128 * v.cg - 1) / (128 * v.cg), tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
     const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
@@ -763,7 +829,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   int rc = get_func(c, name, &f);
   if (rc) return rc;
   const unsigned smem = gemm_smem_bytes(v);
-  CU_CHECK(g_drv.cuFuncSetAttribute_p(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+  if (!c->dry) CU_CHECK(g_drv.cuFuncSetAttribute_p(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
 
   const CUtensorMapDataType dt = g.in_dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                  : g.in_dtype == B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -958,6 +1024,7 @@ extern "C" int b200_matmul(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200
 
 // ================================================================================================ reduce
 static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out) {
+  if (c->dry) { *out = 0x6000000000ull; return B200_OK; }
   auto it = c->reduce_ws.find(st);
   if (it != c->reduce_ws.end()) { *out = it->second; return B200_OK; }
   CUdeviceptr p;
@@ -1157,7 +1224,7 @@ extern "C" int b200_reduce_strided(b200_ctx* c, b200_stream s, b200_reduce_op op
 
 // ================================================================================================ collectives
 extern "C" int b200_comm_get_unique_id(b200_ctx* c, void* id128) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!id128) return fail(B200_ERR_INVALID_ARG, "null id");
   int rc = ensure_nccl();
   if (rc) return rc;
@@ -1174,7 +1241,7 @@ static std::vector<int> sorted_ids(const int* ids, int n) {
 }
 
 extern "C" int b200_comm_init(b200_ctx* c, const int* device_ids, int n, const void* id128) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!device_ids || n < 1 || !id128) return fail(B200_ERR_INVALID_ARG, "comm_init: bad arguments");
   int rc = ensure_nccl();
   if (rc) return rc;
@@ -1194,7 +1261,7 @@ extern "C" int b200_comm_init(b200_ctx* c, const int* device_ids, int n, const v
 
 extern "C" int b200_all_reduce(b200_ctx* c, b200_stream compute, b200_dptr src, b200_dptr dst, size_t bytes, b200_dtype dtype,
                                b200_comm_op op, const int* device_ids, int n) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!device_ids || n < 1) return fail(B200_ERR_INVALID_ARG, "all_reduce: bad device set");
   int rc = ensure_nccl();
   if (rc) return rc;
@@ -1226,7 +1293,7 @@ extern "C" int b200_all_reduce(b200_ctx* c, b200_stream compute, b200_dptr src, 
 }
 
 extern "C" int b200_sync_collective(b200_ctx* c, b200_stream compute) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   CU_CHECK(g_drv.cuEventRecord_p(c->comm_event, c->comm_stream));
   CU_CHECK(g_drv.cuStreamWaitEvent_p(resolve_stream(c, compute), c->comm_event, 0));
   return B200_OK;
@@ -1243,7 +1310,7 @@ static int ensure_mailbox(b200_ctx* c) {
 }
 
 extern "C" int b200_p2p_export(b200_ctx* c, void* ipc_handle64, uint64_t* local_ptr, int64_t* pid) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!ipc_handle64 || !local_ptr || !pid) return fail(B200_ERR_INVALID_ARG, "p2p_export: null argument");
   int rc = ensure_mailbox(c);
   if (rc) return rc;
@@ -1258,7 +1325,7 @@ extern "C" int b200_p2p_export(b200_ctx* c, void* ipc_handle64, uint64_t* local_
 
 extern "C" int b200_p2p_connect(b200_ctx* c, const int* device_ids, int n, const void* ipc_handles, const uint64_t* local_ptrs,
                                 const int64_t* pids) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   if (!device_ids || n < 1 || n > 8 || !ipc_handles || !local_ptrs || !pids)
     return fail(B200_ERR_INVALID_ARG, "p2p_connect: bad arguments (1..8 devices)");
   int rc = ensure_mailbox(c);
@@ -1396,7 +1463,7 @@ extern "C" int b200_probe_wmma(b200_ctx* c, b200_stream s, b200_dtype dtype, uin
 }
 
 extern "C" int b200_probe_umma(b200_ctx* c, b200_stream s, uint32_t n_iter, b200_dptr scratch, double* ops) {
-  CTX_ENTER(c);
+  CTX_ENTER_DEVICE(c);
   CUfunction f;
   int rc = get_func(c, "umma_probe_bf16_2sm", &f);
   if (rc) return rc;

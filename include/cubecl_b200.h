@@ -86,6 +86,12 @@ int b200_get_cubin(const char* name, const void** image, size_t* size);
 int b200_init(int device, b200_ctx** out);   /* cuInit, primary ctx retain, load the embedded sm_100a cubins (context.rs:293) */
 int b200_destroy(b200_ctx* ctx);
 int b200_get_props(b200_ctx* ctx, b200_props* out);
+/* Dry-run planning context (DryRun, crates/cubecl-runtime/src/dry_run.rs:45,88,121): needs no driver and no device.  Ops
+ * called on it (b200_matmul, b200_reduce*, b200_alloc, ...) validate and plan exactly like a real context but RECORD each
+ * pooled allocation, TMA descriptor and kernel launch as one text line instead of executing it.  b200_plan_text copies the
+ * log (and clears it when it fit); *needed = bytes required.  Device pointers passed to ops may be any non-zero values. */
+int b200_plan_begin(int num_sms, b200_ctx** out);
+int b200_plan_text(b200_ctx* ctx, char* buf, size_t capacity, size_t* needed);
 /* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
  * (auto|2sm_n256|2sm_n128|1sm_n128|simt), "gemm.f32" (3xtf32|tf32), "gemm.group_m", "reduce.variant"
  * (auto|u2|u4|u8|u16|b4|b8|w2|w4), "reduce.threads", "reduce.blocks_per_sm". */

@@ -1,0 +1,175 @@
+"""CPU: the C++ host logic of the library (validation, batch collapse, variant choice, TMA descriptor geometry, 3xTF32 and
+reduce split plans) exercised through a dry-run planning context -- no driver, no device (DryRun, dry_run.rs)."""
+import ctypes as C
+
+import pytest
+
+from cubecl_b200 import _ffi
+
+F32, F16, BF16, U32, I32, E4M3 = _ffi.F32, _ffi.F16, _ffi.BF16, _ffi.U32, _ffi.I32, _ffi.F8E4M3
+A, B, O = 0x10000000, 0x20000000, 0x30000000
+
+
+class Planner:
+    def __init__(self, sms=148):
+        self.lib = _ffi.load()
+        self.ctx = C.c_void_p()
+        _ffi.check(self.lib.b200_plan_begin(sms, C.byref(self.ctx)))
+
+    def close(self):
+        self.lib.b200_destroy(self.ctx)
+
+    def text(self):
+        need = C.c_size_t()
+        _ffi.check(self.lib.b200_plan_text(self.ctx, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _ffi.check(self.lib.b200_plan_text(self.ctx, buf, need.value, None))
+        return buf.value.decode()
+
+    def option(self, k, v):
+        _ffi.check(self.lib.b200_set_option(self.ctx, k.encode(), str(v).encode()))
+
+    def matmul(self, idt, odt, ls, lst, rs, rst, os_, ost, a=A, b=B, o=O):
+        rc = self.lib.b200_matmul(self.ctx, None, idt, odt, a, b, o, len(ls), _ffi.u64_array(ls), _ffi.u64_array(lst),
+                                  _ffi.u64_array(rs), _ffi.u64_array(rst), _ffi.u64_array(os_), _ffi.u64_array(ost))
+        return rc, self.text()
+
+    def reduce(self, op, dt, shape, axis, strides=None):
+        rc = self.lib.b200_reduce_strided(self.ctx, None, op, dt, A, O, len(shape), _ffi.u64_array(shape),
+                                          _ffi.u64_array(strides) if strides else None, axis)
+        return rc, self.text()
+
+
+@pytest.fixture
+def plan():
+    p = Planner()
+    yield p
+    p.close()
+
+
+def cs(shape):
+    out, acc = [], 1
+    for s in reversed(shape):
+        out.append(acc)
+        acc *= s
+    return out[::-1]
+
+
+def test_headline_plan_is_one_persistent_2sm_launch(plan):
+    n = 8192
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0
+    lines = t.strip().splitlines()
+    assert lines[-1] == "launch gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1) block=256 smem=197888 cluster=2"
+    # A: K-major box [64 k x 128 m]; B (row-major [K,N]): MN-major box [64 n x 64 k]; both SWIZZLE_128B (enum 3)
+    assert "tmap esz=2 dims=(8192,8192,1) strides=(16384,134217728) box=(64,128) swizzle=3" in lines[0]
+    assert "box=(64,64) swizzle=3" in lines[1]
+    assert len(lines) == 3
+
+
+def test_operand_major_combinations_pick_the_right_kernel(plan):
+    n = 1024
+    for lhs_t, rhs_t, suffix in ((False, False, "_kn"), (False, True, "_kk"), (True, False, "_mn"), (True, True, "_mk")):
+        rc, t = plan.matmul(F16, F32, [n, n], [1, n] if lhs_t else [n, 1], [n, n], [1, n] if rhs_t else [n, 1], [n, n], [n, 1])
+        assert rc == 0 and f"launch gemm_f16_f32_" in t and t.strip().endswith("cluster=2") and suffix + " grid" in t
+
+
+def test_f32_defaults_to_3xtf32_with_two_split_passes(plan):
+    n = 4096
+    rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0
+    launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
+    assert launches == ["split_tf32", "split_tf32", "gemm_tf32_f32_2sm_n256_kn"]
+    assert f"tmap esz=4 dims=({3 * n},{n},1)" in t                      # K' = 3K
+    assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
+    assert t.count("alloc ") == 2
+    plan.option("gemm.f32", "tf32")
+    rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gemm_tf32_f32_2sm_n256_kn"]
+
+
+def test_small_and_unaligned_problems(plan):
+    rc, t = plan.matmul(BF16, F32, [100, 64], [64, 1], [64, 72], [72, 1], [100, 72], [72, 1])
+    assert rc == 0 and "1sm_n128" in t and "cluster=1" in t               # M <= 128: one CTA per tile
+    rc, t = plan.matmul(BF16, F32, [9, 5], [5, 1], [5, 3], [3, 1], [9, 3], [3, 1])
+    assert rc == 0 and t.strip() == "launch gemm_simt_strided grid=(1,1,1) block=256 smem=0 cluster=1"   # 10-byte rows: no TMA
+    rc, t = plan.matmul(BF16, BF16, [0, 16], [16, 1], [16, 8], [8, 1], [0, 8], [8, 1])
+    assert rc == 0 and t == ""                                            # empty output: no launch
+
+
+def test_batch_broadcast_collapses_or_peels(plan):
+    M, N, K = 256, 256, 128
+    # fully batched: one launch over 5 batches (3-D descriptors)
+    rc, t = plan.matmul(BF16, BF16, [5, M, K], cs([5, M, K]), [5, K, N], cs([5, K, N]), [5, M, N], cs([5, M, N]))
+    assert rc == 0 and t.count("launch") == 1 and f"dims=({K},{M},5)" in t
+    # rhs broadcast over the batch: descriptor batch extent 1, still one launch
+    rc, t = plan.matmul(BF16, BF16, [5, M, K], cs([5, M, K]), [1, K, N], cs([1, K, N]), [5, M, N], cs([5, M, N]))
+    assert rc == 0 and t.count("launch") == 1 and f"dims=({N},{K},1)" in t
+    # shape.rs:1030-1036: [1,3,M,K] x [2,1,K,N] -> [2,3,M,N]: offsets are not linear in a flat batch index -> peeled into 2 launches
+    rc, t = plan.matmul(BF16, BF16, [1, 3, M, K], cs([1, 3, M, K]), [2, 1, K, N], cs([2, 1, K, N]), [2, 3, M, N], cs([2, 3, M, N]))
+    assert rc == 0 and t.count("launch") == 2
+
+
+def test_shape_errors_match_the_reference_rule(plan):
+    # shape.rs:1046-1063
+    rc, _ = plan.matmul(BF16, BF16, [1, 3, 2, 4], cs([1, 3, 2, 4]), [2, 1, 3, 2], cs([2, 1, 3, 2]), [2, 3, 2, 2], cs([2, 3, 2, 2]))
+    assert rc == 6 and b"inner dimensions differ" in plan.lib.b200_last_error()
+    rc, _ = plan.matmul(BF16, BF16, [1, 3, 2, 4], cs([1, 3, 2, 4]), [2, 2, 4, 2], cs([2, 2, 4, 2]), [2, 3, 2, 2], cs([2, 3, 2, 2]))
+    assert rc == 6 and b"cannot broadcast" in plan.lib.b200_last_error()
+    rc, _ = plan.matmul(BF16, F16, [8, 8], [8, 1], [8, 8], [8, 1], [8, 8], [8, 1])
+    assert rc == 7                                                         # bf16 in, f16 out: unsupported pair
+    rc, _ = plan.matmul(E4M3, BF16, [256, 256], [256, 1], [256, 256], [256, 1], [256, 256], [256, 1])
+    assert rc == 0
+    rc, _ = plan.matmul(_ffi.I8, F32, [256, 256], [256, 1], [256, 256], [256, 1], [256, 256], [256, 1])
+    assert rc == 7                                                         # int8 accumulates to i32 only
+
+
+def test_wave_model_prefers_big_tiles(plan):
+    # 4096^3: 256 tiles of 256x256 = 4 waves on 74 CTA pairs; the 256x128 tile would be 7 half-cost waves but it is
+    # L2-bandwidth bound (measured 0.66 efficiency) -> 2sm_n256 stays
+    n = 4096
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert "gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1)" in t
+    plan.option("gemm.variant", "2sm_n128")
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert "gemm_bf16_bf16_2sm_n128_kn" in t and "smem=197888" in t
+    # a GPU with fewer SMs gets a smaller persistent grid
+    small = Planner(sms=64)
+    rc, t = small.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert "grid=(64,1,1)" in t
+    small.close()
+
+
+def test_reduce_plans(plan):
+    SUM, ARGMAX, MEAN = _ffi.REDUCE_SUM, _ffi.REDUCE_ARGMAX, _ffi.REDUCE_MEAN
+    rc, t = plan.reduce(SUM, F32, [1 << 28], -1)
+    assert rc == 0 and t.strip() == "launch reduce_all_sum_f32 grid=(592,1,1) block=512 smem=0 cluster=1"
+    rc, t = plan.reduce(SUM, F32, [4], -1)
+    assert "grid=(1,1,1)" in t
+    rc, t = plan.reduce(SUM, F32, [512, 8192], 1)                          # the book's shape: a block per row
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(512,1,1) block=512 smem=0 cluster=1"
+    rc, t = plan.reduce(SUM, F32, [1000, 3], 1)                            # short rows: one thread per row
+    assert "reduce_rows_sum_f32 grid=(4,1,1) block=256" in t
+    rc, t = plan.reduce(SUM, F32, [4, 1 << 24], 1)                         # few long rows: two passes over pooled partials
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["reduce_rows_sum_f32", "reduce_rows_sum_f32"] and "alloc" in t
+    rc, t = plan.reduce(ARGMAX, BF16, [4, 1 << 24], 1)                     # arg ops never split
+    assert t.count("launch") == 1 and "reduce_rows_argmax_bf16" in t
+    rc, t = plan.reduce(MEAN, F16, [64, 256, 1024], 1)                     # middle axis -> columns kernel
+    assert "reduce_cols_sum_f16" in t
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 0)                         # outer axis, few outputs: split along the axis
+    assert t.count("launch reduce_cols_sum_f32") == 2
+    rc, t = plan.reduce(SUM, F32, [100, 72], 1, strides=[128, 1])          # pitched rows: gather first
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_rows_sum_f32"]
+    rc, _ = plan.reduce(SUM, F32, [4, 0], 1)
+    assert rc == 6                                                         # empty reduced extent
+    rc, t = plan.reduce(SUM, F32, [0, 4], 1)
+    assert rc == 0 and t == ""
+    rc, _ = plan.reduce(SUM, U32, [4], -1)
+    assert rc == 7
+
+
+def test_device_only_entry_points_refuse_a_planning_context(plan):
+    ev = C.c_void_p()
+    assert plan.lib.b200_event_create(plan.ctx, C.byref(ev)) == 7
+    assert plan.lib.b200_write(plan.ctx, None, A, None, 16) == 7
+    assert plan.lib.b200_sync(plan.ctx, None) == 0
