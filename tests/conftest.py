@@ -25,3 +25,5 @@ def client():
     c = ComputeClient.load(0)
     yield c
     c.sync()
+    for other in list(ComputeClient._clients.values()):   # leave every device idle and released before the process exits
+        other.close()
