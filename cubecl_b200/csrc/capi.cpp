@@ -1082,9 +1082,11 @@ static int launch_reduce_rows(b200_ctx* c, CUstream st, int op, int dt, uint64_t
   int rc = get_func(c, name, &f);
   if (rc) return rc;
   const uint64_t vec = 16 / dtype_size(dt);
-  // threads per row: ~4 vectors per thread, power of two, 1..512
+  // threads per row (power of two).  Many rows: at most a warp per row (no block barrier per row, many rows in flight);
+  // few rows: up to a 512-thread block per row so the row itself supplies the parallelism.  ~4 vectors per thread.
+  const uint64_t tpr_cap = (outer >= (uint64_t)c->props.num_sms * 16 && len * dtype_size(dt) <= (128u << 10)) ? 32 : 512;
   uint64_t tpr = 1;
-  while (tpr < 512 && tpr * vec * 4 < len) tpr <<= 1;
+  while (tpr < tpr_cap && tpr * vec * 4 < len) tpr <<= 1;
   int tpr_log2 = 0;
   while ((1ull << tpr_log2) < tpr) ++tpr_log2;
   const unsigned threads = tpr > 32 ? (unsigned)tpr : 256;

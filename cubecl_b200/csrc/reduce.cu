@@ -490,6 +490,36 @@ __device__ __forceinline__ void reduce_rows_body(const ReduceParams& p, int tpr_
   const bool vec_ok = (p.len % VEC) == 0 && (p.in % 16) == 0;
   const uint64_t nvec = vec_ok ? p.len / VEC : 0;
 
+  if (tpr <= 32 && vec_ok && nvec <= tpr) {
+    // short rows (at most one 128-bit vector per thread): 4 independent rows in flight per thread group, so the loads of
+    // consecutive rows overlap instead of serialising behind each row's shuffle tree
+    const uint64_t rstride = static_cast<uint64_t>(gridDim.x) * rows_per_block;
+    for (uint64_t row0 = static_cast<uint64_t>(blockIdx.x) * rows_per_block; row0 < p.outer; row0 += 4 * rstride) {
+      uint4 q[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t row = row0 + j * rstride + sub;
+        ok[j] = row < p.outer && t < nvec;
+        if (ok[j]) q[j] = ldg_stream_u4(base + (row * p.len + static_cast<uint64_t>(t) * VEC) * sizeof(typename E::T));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float r = ValOp<OP>::identity();
+        if (ok[j]) {
+          float f[VEC];
+          E::unpack(q[j], f);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) r = ValOp<OP>::apply(r, f[e]);
+        }
+        for (uint32_t o = tpr >> 1; o > 0; o >>= 1) r = ValOp<OP>::apply(r, __shfl_down_sync(0xffffffffu, r, o));
+        const uint64_t row = row0 + j * rstride + sub;
+        if (t == 0 && row < p.outer) reinterpret_cast<float*>(p.out)[row] = r * p.scale;
+      }
+    }
+    return;
+  }
+
   for (uint64_t row0 = static_cast<uint64_t>(blockIdx.x) * rows_per_block; row0 < p.outer;
        row0 += static_cast<uint64_t>(gridDim.x) * rows_per_block) {
     const uint64_t row = row0 + sub;
