@@ -7,7 +7,7 @@
 //      wmma_probe_f16            <- crates/cubecl-std/src/throughput/runners/compute_cmma.rs:47-91 lowered through
 //                                   crates/cubecl-cpp/src/shared/mma.rs:67-155 (nvcuda::wmma 16x16x16, f16 -> f16)
 //      memread_probe_vec4        <- crates/cubecl-std/src/throughput/runners/memory_read.rs:68-154 (float_4 loads)
-//  * 3xTF32 operand splitting (f32 matmul at near-f32 accuracy on the tf32 tensor pipe)
+//  * the 3xTF32 low-part split (f32 matmul at near-f32 accuracy on the tf32 tensor pipe)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -112,19 +112,17 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------ 3xTF32 split
-// hi = x with the low 13 mantissa bits cleared (what the tf32 datapath reads anyway), lo = x - hi (exact in f32).
-// mode 0 (operand whose K is innermost, [rows, K]):  out[b][r][3K] = [hi | hi | lo]   (lhs)
-// mode 1 (same layout, the other operand)         :  out[b][r][3K] = [hi | lo | hi]   (rhs stored [N,K])
-// mode 2 (rhs stored row-major [K, N])            :  out[b][3K][N] = [hi ; lo ; hi] stacked along K
-// mode 3 (lhs stored [K, M], transposed view)     :  out[b][3K][M] = [hi ; hi ; lo] stacked along K
-// A tf32 GEMM over K' = 3K then computes hi*hi + hi*lo + lo*hi with f32 accumulation.
+// lo = x - hi, hi = x with the low 13 mantissa bits cleared: the tf32 datapath ignores those bits of an f32 operand, so
+// the ORIGINAL tensor already acts as "hi" and only `lo` (exact in f32) is materialised, with the input's own strides
+// compacted to a [batch, rows, out_rs] copy (rows padded to 16 bytes).  The GEMM then accumulates hi*hi + hi*lo + lo*hi in one launch
+// (GemmParams::k_segments == 3).
 struct SplitParams {
   uint64_t in, out;
   uint64_t batch, rows, cols;   // logical [batch, rows, cols], cols innermost (stride 1)
   uint64_t in_bs, in_rs;        // input strides in elements
-  uint32_t mode, pad;
+  uint64_t out_rs;              // output row pitch in elements (>= cols, multiple of 4 so rows stay 16-byte aligned for TMA)
 };
-extern "C" __global__ void __launch_bounds__(256) split_tf32(const __grid_constant__ SplitParams p) {
+extern "C" __global__ void __launch_bounds__(256) split_tf32_lo(const __grid_constant__ SplitParams p) {
   const uint64_t per = p.rows * p.cols, total = p.batch * per;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
@@ -132,18 +130,7 @@ extern "C" __global__ void __launch_bounds__(256) split_tf32(const __grid_consta
     const uint64_t r = rem / p.cols, c = rem - r * p.cols;
     const float x = reinterpret_cast<const float*>(p.in)[b * p.in_bs + r * p.in_rs + c];
     const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    const float lo = x - hi;
-    float* o = reinterpret_cast<float*>(p.out) + b * 3 * per;
-    if (p.mode == 2) {
-      o[rem] = hi; o[per + rem] = lo; o[2 * per + rem] = hi;
-    } else if (p.mode == 3) {
-      o[rem] = hi; o[per + rem] = hi; o[2 * per + rem] = lo;
-    } else {
-      float* row = o + r * 3 * p.cols;
-      row[c] = hi;
-      row[p.cols + c] = (p.mode == 0) ? hi : lo;
-      row[2 * p.cols + c] = (p.mode == 0) ? lo : hi;
-    }
+    reinterpret_cast<float*>(p.out)[(b * p.rows + r) * p.out_rs + c] = x - hi;
   }
 }
 

@@ -207,6 +207,7 @@ struct GemmParams {
   uint32_t M, N, K, batch;
   uint32_t tiles_m, tiles_n, group_m;
   uint32_t a_bmul, b_bmul, vec_store;
+  uint32_t k_segments, pad;
 };
 struct ReduceParams {
   uint64_t in, out, ws;
@@ -225,8 +226,7 @@ struct SimtGemmParams {
   uint32_t M, N, K, batch, in_dtype, out_dtype;
 };
 struct SplitParams {
-  uint64_t in, out, batch, rows, cols, in_bs, in_rs;
-  uint32_t mode, pad;
+  uint64_t in, out, batch, rows, cols, in_bs, in_rs, out_rs;
 };
 struct XgpuParams {
   uint64_t mailbox[8];
@@ -761,6 +761,7 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
 struct GemmProblem {
   int in_dtype, out_dtype;
   uint64_t a, b, out;
+  uint64_t a_lo = 0, b_lo = 0;  // 3xTF32: compact low parts (same logical layout class as a / b), 0 otherwise
   uint64_t M, N, K, batch;
   uint64_t a_sm, a_sk, a_sb;
   uint64_t b_sk, b_sn, b_sb;
@@ -858,9 +859,22 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     rc = encode_tmap(c, &tb, dt, esz, g.b, g.N, g.K, b_bcast ? 1 : g.batch, b_sk, b_bcast ? b_sk * g.K : g.b_sb, chunk, block_k, mn_swz);
   }
   if (rc) return rc;
+  // 3xTF32: compact low parts, same operand-major class as the originals (K-major: [rows, K]; MN-major: [K, cols])
+  CUtensorMap ta_lo = ta, tb_lo = tb;
+  const bool split = (g.a_lo != 0 && g.b_lo != 0);
+  if (split) {
+    const uint64_t ab = a_bcast ? 1 : g.batch, bb = b_bcast ? 1 : g.batch;
+    rc = !a_mn ? encode_tmap(c, &ta_lo, dt, esz, g.a_lo, g.K, g.M, ab, pad16(g.K), pad16(g.K) * g.M, block_k, 128)
+               : encode_tmap(c, &ta_lo, dt, esz, g.a_lo, g.M, g.K, ab, pad16(g.M), pad16(g.M) * g.K, chunk, block_k, mn_swz);
+    if (rc) return rc;
+    rc = !b_mn ? encode_tmap(c, &tb_lo, dt, esz, g.b_lo, g.K, g.N, bb, pad16(g.K), pad16(g.K) * g.N, block_k, n_local)
+               : encode_tmap(c, &tb_lo, dt, esz, g.b_lo, g.N, g.K, bb, pad16(g.N), pad16(g.N) * g.K, chunk, block_k, mn_swz);
+    if (rc) return rc;
+  }
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.k_segments = split ? 3 : 1;
   p.out = g.out;
   p.out_row_stride = g.o_sm;
   p.out_batch_stride = g.o_sb;
@@ -875,16 +889,19 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   const uint64_t total_tiles = static_cast<uint64_t>(p.tiles_m) * p.tiles_n * p.batch;
   if (total_tiles >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "too many tiles");
   const unsigned clusters = (unsigned)std::min<uint64_t>(total_tiles, std::max(1, c->props.num_sms / v.cg));
-  void* args[] = {&ta, &tb, &p};
+  void* args[] = {&ta, &tb, &ta_lo, &tb_lo, &p};
   return launch(c, f, clusters * v.cg, 1, 1, 256, smem, v.cg, st, args);
 }
 
+static inline uint64_t pad4(uint64_t elems) { return (elems + 3) / 4 * 4; }
+
+// lo = x - trunc_tf32(x) of a logical [batch, rows, cols] view (cols innermost), written with row pitch pad4(cols)
 static int launch_split(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uint64_t batch, uint64_t rows, uint64_t cols,
-                        uint64_t in_bs, uint64_t in_rs, uint32_t mode) {
+                        uint64_t in_bs, uint64_t in_rs) {
   CUfunction f;
-  int rc = get_func(c, "split_tf32", &f);
+  int rc = get_func(c, "split_tf32_lo", &f);
   if (rc) return rc;
-  SplitParams p{in, out, batch, rows, cols, in_bs, in_rs, mode, 0};
+  SplitParams p{in, out, batch, rows, cols, in_bs, in_rs, pad4(cols)};
   const uint64_t total = batch * rows * cols;
   const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->props.num_sms * 16);
   void* args[] = {&p};
@@ -902,33 +919,27 @@ static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
     return launch_simt(c, st, g);
   }
   if (g.in_dtype == B200_F32 && opt(c, "gemm.f32", "3xtf32") == "3xtf32") {
-    // split both operands into tf32 hi/lo along K and run one tf32 GEMM with K' = 3K
+    // 3xTF32 in ONE GEMM launch: the tf32 datapath reads only the top 19 bits of an f32 operand, so the original tensors
+    // are the "hi" parts; only lo = x - hi is materialised (compact), and the kernel runs K three times:
+    // (A,B) + (A,B_lo) + (A_lo,B), f32 accumulation throughout.
     const uint64_t ab = (g.a_sb == 0) ? 1 : g.batch, bb = (g.b_sb == 0) ? 1 : g.batch;
-    CUdeviceptr a3 = 0, b3 = 0;
-    int rc = pool_alloc(c, ab * g.M * 3 * g.K * 4, &a3);
+    const uint64_t a_elems = !a_mn ? g.M * pad4(g.K) : g.K * pad4(g.M), b_elems = !b_mn ? g.N * pad4(g.K) : g.K * pad4(g.N);
+    CUdeviceptr a_lo = 0, b_lo = 0;
+    int rc = pool_alloc(c, ab * a_elems * 4, &a_lo);
     if (rc) return rc;
-    rc = pool_alloc(c, bb * g.N * 3 * g.K * 4, &b3);
-    if (rc) { pool_free(c, a3); return rc; }
-    // lhs -> [M, 3K] = [hi|hi|lo] (K-major) or, for a transposed lhs, [3K, M] = [hi;hi;lo] stacked along K
-    rc = !a_mn ? launch_split(c, st, g.a, a3, ab, g.M, g.K, g.a_sb, g.a_sm, 0)
-               : launch_split(c, st, g.a, a3, ab, g.K, g.M, g.a_sb, g.a_sk, 3);
-    if (!rc) {
-      if (!b_mn) rc = launch_split(c, st, g.b, b3, bb, g.N, g.K, g.b_sb, g.b_sn, 1);
-      else rc = launch_split(c, st, g.b, b3, bb, g.K, g.N, g.b_sb, g.b_sk, 2);
-    }
+    rc = pool_alloc(c, bb * b_elems * 4, &b_lo);
+    if (rc) { pool_free(c, a_lo); return rc; }
+    rc = !a_mn ? launch_split(c, st, g.a, a_lo, ab, g.M, g.K, g.a_sb, g.a_sm) : launch_split(c, st, g.a, a_lo, ab, g.K, g.M, g.a_sb, g.a_sk);
+    if (!rc) rc = !b_mn ? launch_split(c, st, g.b, b_lo, bb, g.N, g.K, g.b_sb, g.b_sn) : launch_split(c, st, g.b, b_lo, bb, g.K, g.N, g.b_sb, g.b_sk);
     if (!rc) {
       GemmProblem h = g;
-      h.a = a3; h.K = 3 * g.K;
-      if (!a_mn) { h.a_sm = 3 * g.K; h.a_sk = 1; } else { h.a_sm = 1; h.a_sk = g.M; }
-      h.a_sb = (g.a_sb == 0) ? 0 : g.M * 3 * g.K;
-      h.b = b3;
-      if (!b_mn) { h.b_sk = 1; h.b_sn = 3 * g.K; } else { h.b_sk = g.N; h.b_sn = 1; }
-      h.b_sb = (g.b_sb == 0) ? 0 : g.N * 3 * g.K;
+      h.a_lo = a_lo;
+      h.b_lo = b_lo;
       rc = launch_tcgen05(c, st, h, a_mn, b_mn);
     }
     // stream-ordered reuse: the pool hands these pages out again only to later work on this context
-    pool_free(c, a3);
-    pool_free(c, b3);
+    pool_free(c, a_lo);
+    pool_free(c, b_lo);
     return rc;
   }
   return launch_tcgen05(c, st, g, a_mn, b_mn);

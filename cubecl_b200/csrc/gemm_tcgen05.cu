@@ -26,6 +26,8 @@ struct GemmParams {
   uint32_t group_m;           // rasterisation: tiles are walked in column strips of `group_m` tile-rows (L2 reuse)
   uint32_t a_bmul, b_bmul;    // 0 = operand broadcast over batch (tensor map has batch extent 1), 1 = batched
   uint32_t vec_store;         // 1 when every output row start is 16-byte aligned
+  uint32_t k_segments;        // 1, or 3 for the 3xTF32 schedule: the K loop runs three times over (A,B), (A,B_lo), (A_lo,B)
+  uint32_t pad;
 };
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6 };
@@ -95,7 +97,8 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, const GemmParams& p)
 }
 
 template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES>
-__device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtensorMap* tma_b, const GemmParams& p) {
+__device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUtensorMap* tma_b_hi, const CUtensorMap* tma_a_lo,
+                                          const CUtensorMap* tma_b_lo, const GemmParams& p) {
   constexpr int ESZ = (KIND == KIND_TF32) ? 4 : (KIND >= KIND_E4M3) ? 1 : 2;
   // operand format field of the instruction descriptor (meaning depends on the MMA kind)
   constexpr uint32_t FMT = (KIND == KIND_E4M3 || KIND == KIND_U8) ? 0u : (KIND == KIND_E5M2 || KIND == KIND_S8) ? 1u : static_cast<uint32_t>(KIND);
@@ -134,8 +137,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
   const uint32_t n_clusters = (CG == 2) ? num_clusters_x() : gridDim.x;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(tma_a);
-    tma_prefetch_desc(tma_b);
+    tma_prefetch_desc(tma_a_hi);
+    tma_prefetch_desc(tma_b_hi);
+    if (p.k_segments > 1) { tma_prefetch_desc(tma_a_lo); tma_prefetch_desc(tma_b_lo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -160,7 +164,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const uint32_t total_tiles = p.batch * p.tiles_m * p.tiles_n;
-  const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  // 3xTF32: x = hi + lo with hi = the top 19 bits of x (exactly what the tf32 datapath reads from an f32 operand, so the
+  // ORIGINAL tensors serve as "hi") and lo = x - hi materialised once.  A*B ~= hi*hi + hi*lo + lo*hi is accumulated by
+  // running the K loop over three segments with the operand descriptors swapped per segment.
+  const uint32_t seg_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t num_kb = seg_kb * p.k_segments;
 
   if (warp == 0) {
     // ===================================================================== TMA producer (one lane per CTA)
@@ -176,7 +184,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          const int k0 = static_cast<int>(kb * BLOCK_K);
+          const uint32_t seg = kb / seg_kb;  // 0 unless k_segments == 3
+          const CUtensorMap* tma_a = (seg == 2) ? tma_a_lo : tma_a_hi;
+          const CUtensorMap* tma_b = (seg == 1) ? tma_b_lo : tma_b_hi;
+          const int k0 = static_cast<int>((kb - seg * seg_kb) * BLOCK_K);
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
             if constexpr (!A_MN) {
@@ -295,8 +306,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a, const CUtens
 #define GEMM_KERNEL(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES)                                                   \
   extern "C" __global__ void __launch_bounds__(kNumThreads, 1)                                                   \
       NAME(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,                 \
+           const __grid_constant__ CUtensorMap tma_a_lo, const __grid_constant__ CUtensorMap tma_b_lo,           \
            const __grid_constant__ GemmParams p) {                                                               \
-    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES>(&tma_a, &tma_b, p);                                           \
+    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES>(&tma_a, &tma_b, &tma_a_lo, &tma_b_lo, p);                     \
   }
 
 // name: gemm_<in>_<out>_<cg>sm_n<BLOCK_N>_<a><b>

@@ -79,10 +79,10 @@ def test_f32_defaults_to_3xtf32_with_two_split_passes(plan):
     rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert rc == 0
     launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
-    assert launches == ["split_tf32", "split_tf32", "gemm_tf32_f32_2sm_n256_kn"]
-    assert f"tmap esz=4 dims=({3 * n},{n},1)" in t                      # K' = 3K
+    assert launches == ["split_tf32_lo", "split_tf32_lo", "gemm_tf32_f32_2sm_n256_kn"]   # lo parts only, ONE gemm launch
+    assert t.count("tmap ") == 4                                         # A, B (originals = hi) + A_lo, B_lo
     assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
-    assert t.count("alloc ") == 2
+    assert t.count("alloc ") == 2 and f"alloc {n * n * 4}" in t          # 1x temporaries, not 3x
     plan.option("gemm.f32", "tf32")
     rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gemm_tf32_f32_2sm_n256_kn"]
