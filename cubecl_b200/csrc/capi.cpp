@@ -1114,7 +1114,11 @@ static int launch_reduce_cols(b200_ctx* c, CUstream st, int op, int dt, uint64_t
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;
-  const uint64_t total = outer * inner;
+  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
+  const uint64_t vec = 16 / dtype_size(dt);
+  // value ops read 128-bit vectors of `vec` consecutive columns per thread when the layout allows it (kernel re-checks)
+  const bool vector_path = !arg && inner % vec == 0 && in % 16 == 0 && out % 16 == 0;
+  const uint64_t total = vector_path ? outer * (inner / vec) : outer * inner;
   const unsigned threads = 256;
   const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total + threads - 1) / threads, (uint64_t)c->props.num_sms * 16));
   ReduceParams p{in, out, 0, outer, len, inner, scale, 0};

@@ -599,8 +599,53 @@ __device__ __forceinline__ void argreduce_rows_body(const ReduceParams& p, int t
 template <int OP, int DT>
 __device__ __forceinline__ void reduce_cols_body(const ReduceParams& p) {
   using E = Elem<DT>;
+  constexpr int VEC = E::VEC;
   const uint64_t total = p.outer * p.inner;
   const char* base = reinterpret_cast<const char*>(p.in);
+  if (p.inner % VEC == 0 && p.in % 16 == 0 && p.out % 16 == 0) {
+    // vector path: each thread owns VEC consecutive columns -> one 128-bit load per row, 4 rows in flight
+    const uint64_t inner_v = p.inner / VEC, total_v = p.outer * inner_v;
+    for (uint64_t idx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total_v;
+         idx += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+      const uint64_t o = idx / inner_v, iv = idx - o * inner_v;
+      const uint64_t off = o * p.len * p.inner + iv * VEC;  // elements
+      float a[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a[u][j] = ValOp<OP>::identity();
+      uint64_t l = 0;
+      for (; l + 3 < p.len; l += 4) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = ldg_stream_u4(base + (off + (l + u) * p.inner) * sizeof(typename E::T));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[VEC];
+          E::unpack(r[u], f);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) a[u][j] = ValOp<OP>::apply(a[u][j], f[j]);
+        }
+      }
+      for (; l < p.len; ++l) {
+        float f[VEC];
+        E::unpack(ldg_stream_u4(base + (off + l * p.inner) * sizeof(typename E::T)), f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a[0][j] = ValOp<OP>::apply(a[0][j], f[j]);
+      }
+      float* dst = reinterpret_cast<float*>(p.out) + o * p.inner + iv * VEC;
+#pragma unroll
+      for (int j = 0; j < VEC; j += 4) {
+        float4 v;
+        v.x = ValOp<OP>::apply(ValOp<OP>::apply(a[0][j], a[1][j]), ValOp<OP>::apply(a[2][j], a[3][j])) * p.scale;
+        v.y = ValOp<OP>::apply(ValOp<OP>::apply(a[0][j + 1], a[1][j + 1]), ValOp<OP>::apply(a[2][j + 1], a[3][j + 1])) * p.scale;
+        v.z = ValOp<OP>::apply(ValOp<OP>::apply(a[0][j + 2], a[1][j + 2]), ValOp<OP>::apply(a[2][j + 2], a[3][j + 2])) * p.scale;
+        v.w = ValOp<OP>::apply(ValOp<OP>::apply(a[0][j + 3], a[1][j + 3]), ValOp<OP>::apply(a[2][j + 3], a[3][j + 3])) * p.scale;
+        reinterpret_cast<float4*>(dst)[j / 4] = v;
+      }
+    }
+    return;
+  }
   for (uint64_t idx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t o = idx / p.inner, i = idx - o * p.inner;
@@ -647,7 +692,7 @@ __device__ __forceinline__ void argreduce_cols_body(const ReduceParams& p) {
     argreduce_all_body<OP, DT>(p);                                                                 \
   }
 #define REDUCE_ROWS(NAME, OP, DT)                                                                                   \
-  extern "C" __global__ void __launch_bounds__(1024) NAME(const __grid_constant__ ReduceParams p, int tpr_log2) {   \
+  extern "C" __global__ void __launch_bounds__(512) NAME(const __grid_constant__ ReduceParams p, int tpr_log2) {    \
     reduce_rows_body<OP, DT>(p, tpr_log2);                                                                          \
   }
 #define ARGREDUCE_ROWS(NAME, OP, DT)                                                                                \
@@ -655,7 +700,7 @@ __device__ __forceinline__ void argreduce_cols_body(const ReduceParams& p) {
     argreduce_rows_body<OP, DT>(p, tpr_log2);                                                                       \
   }
 #define REDUCE_COLS(NAME, OP, DT)                                                                  \
-  extern "C" __global__ void __launch_bounds__(1024) NAME(const __grid_constant__ ReduceParams p) { \
+  extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ ReduceParams p) {  \
     reduce_cols_body<OP, DT>(p);                                                                   \
   }
 #define ARGREDUCE_COLS(NAME, OP, DT)                                                               \
@@ -663,8 +708,8 @@ __device__ __forceinline__ void argreduce_cols_body(const ReduceParams& p) {
     argreduce_cols_body<OP, DT>(p);                                                                \
   }
 
-#define ALL_SHAPES(OPN, OP, DTN, DT)                       \
-  REDUCE_ALL(reduce_all_##OPN##_##DTN, OP, DT, 8, false)   \
+#define ALL_SHAPES(OPN, OP, DTN, DT)                                                \
+  REDUCE_ALL(reduce_all_##OPN##_##DTN, OP, DT, (DT == DT_F32 ? 8 : 4), false)       \
   REDUCE_ROWS(reduce_rows_##OPN##_##DTN, OP, DT)           \
   REDUCE_COLS(reduce_cols_##OPN##_##DTN, OP, DT)
 #define ALL_ARG_SHAPES(OPN, OP, DTN, DT)               \
