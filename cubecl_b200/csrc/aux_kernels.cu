@@ -56,6 +56,9 @@ struct SimtGemmParams {
   uint64_t o_sb, o_sm, o_sn;
   uint32_t M, N, K, batch;
   uint32_t in_dtype, out_dtype;  // b200_dtype: 0 f32, 1 f16, 2 bf16; inputs also 10 fp8 e4m3, 11 fp8 e5m2
+  uint64_t bias;                 // fused epilogue, same meaning as GemmParams
+  float alpha;
+  uint32_t epi_act, epi_on, pad;
 };
 
 __device__ __forceinline__ float load_as_f32(uint64_t base, uint64_t idx, uint32_t dt) {
@@ -106,8 +109,17 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
   }
   if (m < p.M && n < p.N) {
     const uint64_t io = bz * p.o_sb + static_cast<uint64_t>(m) * p.o_sm + static_cast<uint64_t>(n) * p.o_sn;
-    if (integer) reinterpret_cast<int*>(p.out)[io] = iacc;
-    else store_from_f32(p.out, io, p.out_dtype, acc);
+    if (integer) {
+      reinterpret_cast<int*>(p.out)[io] = iacc;
+    } else {
+      if (p.epi_on) {
+        acc *= p.alpha;
+        if (p.bias) acc += reinterpret_cast<const float*>(p.bias)[n];
+        if (p.epi_act == 1) acc = fmaxf(acc, 0.f);
+        else if (p.epi_act == 2) acc = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752f));
+      }
+      store_from_f32(p.out, io, p.out_dtype, acc);
+    }
   }
 }
 

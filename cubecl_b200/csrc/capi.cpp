@@ -207,7 +207,10 @@ struct GemmParams {
   uint32_t M, N, K, batch;
   uint32_t tiles_m, tiles_n, group_m;
   uint32_t a_bmul, b_bmul, vec_store;
-  uint32_t k_segments, pad;
+  uint32_t k_segments, epi_act;
+  uint64_t bias;
+  float alpha;
+  uint32_t epi_on;
 };
 struct ReduceParams {
   uint64_t in, out, ws;
@@ -224,6 +227,9 @@ struct SimtGemmParams {
   uint64_t a, b, out;
   uint64_t a_sb, a_sm, a_sk, b_sb, b_sk, b_sn, o_sb, o_sm, o_sn;
   uint32_t M, N, K, batch, in_dtype, out_dtype;
+  uint64_t bias;
+  float alpha;
+  uint32_t epi_act, epi_on, pad;
 };
 struct SplitParams {
   uint64_t in, out, batch, rows, cols, in_bs, in_rs, out_rs;
@@ -762,6 +768,9 @@ struct GemmProblem {
   int in_dtype, out_dtype;
   uint64_t a, b, out;
   uint64_t a_lo = 0, b_lo = 0;  // 3xTF32: compact low parts (same logical layout class as a / b), 0 otherwise
+  uint64_t bias = 0;            // fused epilogue: out = act(alpha * acc + bias[n])
+  float alpha = 1.0f;
+  uint32_t act = 0;
   uint64_t M, N, K, batch;
   uint64_t a_sm, a_sk, a_sb;
   uint64_t b_sk, b_sn, b_sb;
@@ -773,8 +782,10 @@ static int launch_simt(b200_ctx* c, CUstream st, const GemmProblem& g) {
   int rc = get_func(c, "gemm_simt_strided", &f);
   if (rc) return rc;
   if (g.batch > 65535) return fail(B200_ERR_UNSUPPORTED, "simt matmul: batch %llu > 65535", (unsigned long long)g.batch);
+  const uint32_t epi_on = (g.alpha != 1.0f || g.bias != 0 || g.act != 0) ? 1u : 0u;
   SimtGemmParams p{g.a, g.b, g.out, g.a_sb, g.a_sm, g.a_sk, g.b_sb, g.b_sk, g.b_sn, g.o_sb, g.o_sm, g.o_sn,
-                   (uint32_t)g.M, (uint32_t)g.N, (uint32_t)g.K, (uint32_t)g.batch, (uint32_t)g.in_dtype, (uint32_t)g.out_dtype};
+                   (uint32_t)g.M, (uint32_t)g.N, (uint32_t)g.K, (uint32_t)g.batch, (uint32_t)g.in_dtype, (uint32_t)g.out_dtype,
+                   g.bias, g.alpha, g.act, epi_on, 0};
   void* args[] = {&p};
   return launch(c, f, (unsigned)((g.N + 15) / 16), (unsigned)((g.M + 15) / 16), (unsigned)g.batch, 256, 0, 1, st, args);
 }
@@ -875,6 +886,8 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.k_segments = split ? 3 : 1;
+  p.alpha = g.alpha; p.bias = g.bias; p.epi_act = g.act;
+  p.epi_on = (g.alpha != 1.0f || g.bias != 0 || g.act != 0) ? 1u : 0u;
   p.out = g.out;
   p.out_row_stride = g.o_sm;
   p.out_batch_stride = g.o_sb;
@@ -985,10 +998,34 @@ static int matmul_rec(b200_ctx* c, CUstream st, GemmProblem g, int nb, const uin
   return B200_OK;
 }
 
+static int matmul_impl(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
+                       b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                       const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
+                       const uint64_t* strides_out, const b200_epilogue* ep);
+
 extern "C" int b200_matmul(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
                            b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
                            const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
                            const uint64_t* strides_out) {
+  return matmul_impl(c, s, in_dtype, out_dtype, lhs, rhs, out, rank, shape_lhs, strides_lhs, shape_rhs, strides_rhs, shape_out,
+                     strides_out, nullptr);
+}
+
+extern "C" int b200_matmul_fused(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
+                                 b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                                 const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
+                                 const uint64_t* strides_out, const b200_epilogue* ep) {
+  if (!ep) return fail(B200_ERR_INVALID_ARG, "matmul_fused: null epilogue");
+  if (ep->activation < 0 || ep->activation > 2) return fail(B200_ERR_INVALID_ARG, "matmul_fused: unknown activation %d", ep->activation);
+  if (in_dtype == B200_U8 || in_dtype == B200_I8) return fail(B200_ERR_UNSUPPORTED, "matmul_fused: integer accumulators have no float epilogue");
+  return matmul_impl(c, s, in_dtype, out_dtype, lhs, rhs, out, rank, shape_lhs, strides_lhs, shape_rhs, strides_rhs, shape_out,
+                     strides_out, ep);
+}
+
+static int matmul_impl(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
+                       b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                       const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
+                       const uint64_t* strides_out, const b200_epilogue* ep) {
   CTX_ENTER(c);
   if (rank < 2 || rank > 8) return fail(B200_ERR_INVALID_ARG, "matmul: rank %d unsupported (need 2..8)", rank);
   if (!shape_lhs || !strides_lhs || !shape_rhs || !strides_rhs || !shape_out || !strides_out)
@@ -1028,6 +1065,7 @@ extern "C" int b200_matmul(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200
   g.a_sm = strides_lhs[rank - 2]; g.a_sk = strides_lhs[rank - 1];
   g.b_sk = strides_rhs[rank - 2]; g.b_sn = strides_rhs[rank - 1];
   g.o_sm = strides_out[rank - 2]; g.o_sn = strides_out[rank - 1];
+  if (ep) { g.alpha = ep->alpha; g.bias = ep->bias; g.act = (uint32_t)ep->activation; }
   for (int i = 0; i < nb; ++i)
     if (shape_out[i] == 0) return B200_OK;
   return matmul_rec(c, st, g, nb, shape_out, shape_lhs, strides_lhs, shape_rhs, strides_rhs, strides_out);

@@ -1,5 +1,5 @@
 // Hand-written sm_100a GEMM: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators in TMEM) -> tcgen05.ld epilogue.
-// Persistent, warp-specialised (1 TMA producer warp, 1 MMA issuer thread, 4 epilogue warps), optional CTA pair
+// Persistent, warp-specialised (2 TMA producer threads, 1 MMA issuer thread, 4 epilogue warps), optional CTA pair
 // (cta_group::2, UMMA M = 256) and double-buffered TMEM accumulators so the epilogue of tile i overlaps the
 // mainloop of tile i+1.
 //
@@ -27,13 +27,16 @@ struct GemmParams {
   uint32_t a_bmul, b_bmul;    // 0 = operand broadcast over batch (tensor map has batch extent 1), 1 = batched
   uint32_t vec_store;         // 1 when every output row start is 16-byte aligned
   uint32_t k_segments;        // 1, or 3 for the 3xTF32 schedule: the K loop runs three times over (A,B), (A,B_lo), (A_lo,B)
-  uint32_t pad;
+  uint32_t epi_act;           // fused epilogue (float accumulators only): 0 = none, 1 = relu, 2 = gelu (erf form)
+  uint64_t bias;              // f32[N] added per output column, or 0
+  float alpha;                // out = act(alpha * acc + bias[n]); the epilogue is skipped when alpha == 1, bias == 0, act == 0
+  uint32_t epi_on;
 };
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6 };
 enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };  // OUT_F32 is a raw 32-bit store: it also carries the s32 accumulators of kind::i8
 
-constexpr int kNumThreads = 256;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
+constexpr int kNumThreads = 256;  // warps 0 and 3 TMA producers, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
 
 template <int OUT>
 __device__ __forceinline__ void store_chunk32(uint64_t row_ptr, uint32_t n0, uint32_t N, bool vec, const uint32_t (&v)[32]) {
@@ -170,58 +173,49 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   const uint32_t seg_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const uint32_t num_kb = seg_kb * p.k_segments;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer (one lane per CTA)
+  if (warp == 0 || warp == 3) {
+    // ===================================================================== TMA producers (one lane each in warps 0 and 3)
+    // A TMA issue costs its thread on the order of 100 cycles and an MN-major 32-bit operand needs 4 of them per stage,
+    // so a single issuing thread caps the k-block rate (measured: tf32 with a row-major rhs ran 16 % slower than with a
+    // K-major rhs).  The per-stage copies ("items": A chunks first, then B chunks) are therefore dealt alternately to two
+    // producer threads in different warps (SASS UTMALDG is a warp-uniform instruction: lanes of one warp would serialise).
+    // Both wait on the same empty barrier; a copy may land before warp 0's expect_tx of that phase (the tx-count goes
+    // transiently negative), which mbarrier semantics allow -- the phase cannot complete before that arrival.
     if (lane == 0) {
+      const uint32_t who = (warp == 0) ? 0u : 1u;
       const uint32_t leader_full0 = (CG == 2) ? mapa_shared(full_bar(0), 0) : full_bar(0);
+      constexpr int kAItems = A_MN ? NUM_CHUNKS_A : 1, kBItems = B_MN ? NUM_CHUNKS : 1;
       uint32_t s = 0, ph = 0;
       for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
         const TileCoord tc = tile_coord(t, p);
         const int m0 = static_cast<int>((tc.m_blk * CG + rank) * 128);
         const int n0 = static_cast<int>(tc.n_blk * BLOCK_N + rank * N_LOCAL);
         const int ba = static_cast<int>(tc.b * p.a_bmul), bb = static_cast<int>(tc.b * p.b_bmul);
+        uint32_t seg = 0, kk = 0;  // segment (0 unless k_segments == 3) and k-block within the segment
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          const uint32_t seg = kb / seg_kb;  // 0 unless k_segments == 3
+          const uint32_t fb = (CG == 2) ? leader_full0 + 8u * s : full_bar(s);
+          const int k0 = static_cast<int>(kk * BLOCK_K);
+          if (who == 0 && leader) mbar_arrive_expect_tx(full_bar(s), CG * STAGE_BYTES);
           const CUtensorMap* tma_a = (seg == 2) ? tma_a_lo : tma_a_hi;
           const CUtensorMap* tma_b = (seg == 1) ? tma_b_lo : tma_b_hi;
-          const int k0 = static_cast<int>((kb - seg * seg_kb) * BLOCK_K);
-          if constexpr (CG == 1) {
-            mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
-            if constexpr (!A_MN) {
-              tma_load_3d(sa, tma_a, full_bar(s), k0, m0, ba);
-            } else {
 #pragma unroll
-              for (int c = 0; c < NUM_CHUNKS_A; ++c)
-                tma_load_3d(sa + c * CHUNK_BYTES, tma_a, full_bar(s), m0 + c * CHUNK_N, k0, ba);
-            }
-            if constexpr (!B_MN) {
-              tma_load_3d(sb, tma_b, full_bar(s), k0, n0, bb);
+          for (int item = 0; item < kAItems + kBItems; ++item) {
+            if ((item & 1) != static_cast<int>(who)) continue;
+            if (item < kAItems) {
+              const uint32_t dst = A_MN ? sa + item * CHUNK_BYTES : sa;
+              const int c0 = A_MN ? m0 + item * CHUNK_N : k0, c1 = A_MN ? k0 : m0;
+              if constexpr (CG == 1) tma_load_3d(dst, tma_a, fb, c0, c1, ba); else tma_load_3d_2sm(dst, tma_a, fb, c0, c1, ba);
             } else {
-#pragma unroll
-              for (int c = 0; c < NUM_CHUNKS; ++c)
-                tma_load_3d(sb + c * CHUNK_BYTES, tma_b, full_bar(s), n0 + c * CHUNK_N, k0, bb);
-            }
-          } else {
-            const uint32_t fb = leader_full0 + 8u * s;
-            if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE_BYTES);
-            if constexpr (!A_MN) {
-              tma_load_3d_2sm(sa, tma_a, fb, k0, m0, ba);
-            } else {
-#pragma unroll
-              for (int c = 0; c < NUM_CHUNKS_A; ++c)
-                tma_load_3d_2sm(sa + c * CHUNK_BYTES, tma_a, fb, m0 + c * CHUNK_N, k0, ba);
-            }
-            if constexpr (!B_MN) {
-              tma_load_3d_2sm(sb, tma_b, fb, k0, n0, bb);
-            } else {
-#pragma unroll
-              for (int c = 0; c < NUM_CHUNKS; ++c)
-                tma_load_3d_2sm(sb + c * CHUNK_BYTES, tma_b, fb, n0 + c * CHUNK_N, k0, bb);
+              const int c = item - kAItems;
+              const uint32_t dst = B_MN ? sb + c * CHUNK_BYTES : sb;
+              const int c0 = B_MN ? n0 + c * CHUNK_N : k0, c1 = B_MN ? k0 : n0;
+              if constexpr (CG == 1) tma_load_3d(dst, tma_b, fb, c0, c1, bb); else tma_load_3d_2sm(dst, tma_b, fb, c0, c1, bb);
             }
           }
+          if (++kk == seg_kb) { kk = 0; ++seg; }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -283,7 +277,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         tmem_ld_32x32b_x32(taddr + c * 32, v);
         tmem_ld_wait();
         const uint32_t n0 = n_tile + c * 32;
-        if (m < p.M && n0 < p.N) store_chunk32<OUT>(row_ptr, n0, p.N, p.vec_store != 0, v);
+        if (m < p.M && n0 < p.N) {
+          if (KIND < KIND_U8 && p.epi_on) {
+            // fused epilogue on the f32 accumulators: out = act(alpha * acc + bias[n]); bias loads are warp-uniform
+            const float* bias = reinterpret_cast<const float*>(p.bias);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(v[j]) * p.alpha;
+              if (bias != nullptr && n0 + j < p.N) x += __ldg(bias + n0 + j);
+              if (p.epi_act == 1) x = fmaxf(x, 0.f);
+              else if (p.epi_act == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+              v[j] = __float_as_uint(x);
+            }
+          }
+          store_chunk32<OUT>(row_ptr, n0, p.N, p.vec_store != 0, v);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -40,9 +40,16 @@ def calculate_matmul_output(shape_lhs, shape_rhs) -> list[int]:
     return out + [shape_lhs[-2], shape_rhs[-1]]
 
 
-def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: TensorHandle, stream=None) -> None:
+ACTIVATIONS = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+
+
+def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: TensorHandle, stream=None,
+           alpha: float = 1.0, bias: TensorHandle | None = None, activation: str | None = None) -> None:
     """Enqueue the matmul on the client's stream.  Never raises for launch problems: errors are deferred to
-    client.sync()/read_one() like the reference's launch path."""
+    client.sync()/read_one() like the reference's launch path.
+    Optional fused epilogue: out = activation(alpha * (lhs @ rhs) + bias[n]) with `bias` an f32 [N] tensor."""
+    if alpha != 1.0 or bias is not None or activation not in (None, "none"):
+        return _launch_fused(client, lhs, rhs, out, stream, alpha, bias, activation)
     try:
         if lhs.dtype != rhs.dtype:
             raise B200Error(6, f"lhs dtype {lhs.dtype} != rhs dtype {rhs.dtype}")
@@ -54,6 +61,27 @@ def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: Ten
             C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(out.handle.ptr), rank,
             _ffi.u64_array(lhs.shape), _ffi.u64_array(lhs.strides), _ffi.u64_array(rhs.shape), _ffi.u64_array(rhs.strides),
             _ffi.u64_array(out.shape), _ffi.u64_array(out.strides)))
+    except B200Error as e:
+        client._defer(e)
+
+
+def _launch_fused(client, lhs, rhs, out, stream, alpha, bias, activation) -> None:
+    try:
+        if activation not in ACTIVATIONS:
+            raise B200Error(6, f"unknown activation {activation!r}")
+        if bias is not None and (bias.dtype != "f32" or not bias.is_contiguous() or bias.size() != out.shape[-1]):
+            raise B200Error(6, "bias must be a contiguous f32 tensor with N elements")
+        if lhs.dtype != rhs.dtype:
+            raise B200Error(6, f"lhs dtype {lhs.dtype} != rhs dtype {rhs.dtype}")
+        rank = len(lhs.shape)
+        if len(rhs.shape) != rank or len(out.shape) != rank:
+            raise B200Error(6, "matmul: lhs, rhs and out must have equal rank")
+        ep = _ffi.Epilogue(float(alpha), ACTIVATIONS[activation], bias.handle.ptr if bias is not None else 0)
+        _ffi.check(client._lib.b200_matmul_fused(
+            client._ctx, stream, DTYPES[lhs.dtype], DTYPES[out.dtype],
+            C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(out.handle.ptr), rank,
+            _ffi.u64_array(lhs.shape), _ffi.u64_array(lhs.strides), _ffi.u64_array(rhs.shape), _ffi.u64_array(rhs.strides),
+            _ffi.u64_array(out.shape), _ffi.u64_array(out.strides), C.byref(ep)))
     except B200Error as e:
         client._defer(e)
 

@@ -138,6 +138,20 @@ int b200_matmul(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dtype ou
                 const uint64_t* shape_rhs, const uint64_t* strides_rhs,
                 const uint64_t* shape_out, const uint64_t* strides_out);
 
+/* Fused epilogue: out = act(alpha * (lhs @ rhs) + bias[n]) applied to the f32 accumulators inside the GEMM
+ * epilogue (TMEM -> registers -> here -> store), no extra pass over the output.  bias: f32[N] device pointer or 0.
+ * activation: 0 none, 1 relu, 2 gelu (erf form).  Float inputs only. */
+typedef struct b200_epilogue {
+  float alpha;
+  int32_t activation;
+  b200_dptr bias;
+} b200_epilogue;
+int b200_matmul_fused(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype,
+                      b200_dptr lhs, b200_dptr rhs, b200_dptr out, int rank,
+                      const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                      const uint64_t* shape_rhs, const uint64_t* strides_rhs,
+                      const uint64_t* shape_out, const uint64_t* strides_out, const b200_epilogue* epilogue);
+
 /* ---- reduce::launch (cubek) -----------------------------------------------------------------------------------------
  * Reduces `axis` (0..rank-1) of a CONTIGUOUS row-major input, or every element when axis == -1.  Output is contiguous
  * with the reduced axis removed (one element for axis == -1): F32 values, or U32 indices along the axis for arg ops.

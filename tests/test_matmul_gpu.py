@@ -198,6 +198,36 @@ def run_matmul_int(client, a, b, dtype, lhs_t=False, rhs_t=False):
     return out.to_numpy(client)
 
 
+# ------------------------------------------------------------------------------------------------ fused epilogue
+@pytest.mark.parametrize("variant", ["auto", "1sm_n128", "simt"])
+@pytest.mark.parametrize("in_dtype,out_dtype", [("bf16", "bf16"), ("bf16", "f32"), ("f32", "f32"), ("f8e4m3", "f16")])
+@pytest.mark.parametrize("activation", [None, "relu", "gelu"])
+def test_fused_epilogue(client, variant, in_dtype, out_dtype, activation):
+    # out = act(alpha * (A @ B) + bias[n]) inside the GEMM epilogue; oracle: the same formula in f64
+    from math import erf
+    client.set_option("gemm.variant", variant)
+    M, N, K = 300, 264, 192
+    a_dev, a = make_operand((M, K), in_dtype, 101)
+    b_dev, b = make_operand((K, N), in_dtype, 102)
+    bias = synth.uniform_f32(103, N, -2.0, 2.0)
+    alpha = 0.125
+    lhs, rhs = TensorHandle.from_numpy(client, a_dev, in_dtype), TensorHandle.from_numpy(client, b_dev, in_dtype)
+    out = TensorHandle.empty_contiguous(client, [M, N], out_dtype)
+    matmul.launch(client, lhs, rhs, out, alpha=alpha, bias=TensorHandle.from_numpy(client, bias, "f32"), activation=activation)
+    got = synth.from_device_dtype(out.to_numpy(client), out_dtype).astype(np.float64)
+    f64, fabs = oracle.matmul_f64(a, b)
+    x = alpha * f64 + bias.astype(np.float64)[None, :]
+    if activation == "relu":
+        exp = np.maximum(x, 0.0)
+    elif activation == "gelu":
+        exp = 0.5 * x * (1.0 + np.vectorize(erf)(x / np.sqrt(2.0)))
+    else:
+        exp = x
+    scale = alpha * fabs + np.abs(bias)[None, :] + 1e-6
+    tol = {"f32": 1e-5 if in_dtype != "f32" else 1e-4, "bf16": 1e-2, "f16": 2e-3}[out_dtype]
+    assert np.max(np.abs(got - exp) / scale) <= tol
+
+
 def test_simt_is_bit_exact_with_reference_order(client):
     # the strided SIMT kernel accumulates exactly like cmma.rs:695-721 (f32, ascending k, separate mul/add)
     client.set_option("gemm.variant", "simt")
