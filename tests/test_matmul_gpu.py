@@ -228,6 +228,52 @@ def test_fused_epilogue(client, variant, in_dtype, out_dtype, activation):
     assert np.max(np.abs(got - exp) / scale) <= tol
 
 
+def test_fuzz_shapes_layouts_dtypes(client):
+    # 60 seeded random problems (ragged M/N/K, both operand majors, batch, every dtype); TMA-describable or not, each must
+    # match the f64 oracle -- integer dtypes exactly
+    rng = np.random.default_rng(2024)
+    seen_paths = set()
+    for case in range(60):
+        dtype = ["bf16", "f16", "f32", "f8e4m3", "f8e5m2", "i8", "u8"][case % 7]
+        align = {"bf16": 8, "f16": 8, "f32": 4, "f8e4m3": 16, "f8e5m2": 16, "i8": 16, "u8": 16}[dtype]
+        aligned = rng.random() < 0.75
+        def dim(hi):
+            d = int(rng.integers(1, hi))
+            return max(align, d // align * align) if aligned else d
+        M, N, K = dim(500), dim(600), dim(700)
+        lhs_t, rhs_t = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        batch = int(rng.integers(1, 4)) if case % 5 == 0 else 1
+        a_shape = ((batch,) if batch > 1 else ()) + ((K, M) if lhs_t else (M, K))
+        b_shape = ((batch,) if batch > 1 else ()) + ((N, K) if rhs_t else (K, N))
+        before = client.launch_count()
+        if dtype in ("i8", "u8"):
+            lo, hi, npdt = (-128, 128, np.int8) if dtype == "i8" else (0, 256, np.uint8)
+            a = rng.integers(lo, hi, size=a_shape).astype(npdt)
+            b = rng.integers(lo, hi, size=b_shape).astype(npdt)
+            lhs, rhs = TensorHandle.from_numpy(client, a, dtype), TensorHandle.from_numpy(client, b, dtype)
+            lhs = lhs.transposed() if lhs_t else lhs
+            rhs = rhs.transposed() if rhs_t else rhs
+            out = TensorHandle.empty_contiguous(client, matmul.calculate_matmul_output(lhs.shape, rhs.shape), "i32")
+            matmul.launch(client, lhs, rhs, out)
+            got = out.to_numpy(client).astype(np.int64)
+            al = np.swapaxes(a, -1, -2) if lhs_t else a
+            bl = np.swapaxes(b, -1, -2) if rhs_t else b
+            assert np.array_equal(got, np.matmul(al.astype(np.int64), bl.astype(np.int64))), (case, dtype, M, N, K, lhs_t, rhs_t)
+        else:
+            a_dev, a = make_operand(a_shape, dtype, 1000 + case)
+            b_dev, b = make_operand(b_shape, dtype, 2000 + case)
+            client.set_option("gemm.f32", "3xtf32" if case % 2 else "tf32")
+            got = run_matmul(client, a_dev, b_dev, dtype, "f32", rhs_transposed=rhs_t, lhs_transposed=lhs_t)
+            al = np.swapaxes(a, -1, -2) if lhs_t else a
+            bl = np.swapaxes(b, -1, -2) if rhs_t else b
+            exp = np.matmul(al.astype(np.float64), bl.astype(np.float64))
+            scale = np.matmul(np.abs(al).astype(np.float64), np.abs(bl).astype(np.float64)) + 1e-30
+            tol = 1e-3 if dtype == "f32" else 1e-5
+            assert np.max(np.abs(got - exp) / scale) <= tol, (case, dtype, M, N, K, lhs_t, rhs_t, batch)
+        seen_paths.add(client.launch_count() - before)
+    assert len(seen_paths) >= 2   # both the single-launch tcgen05/SIMT path and the split + GEMM path were exercised
+
+
 def test_simt_is_bit_exact_with_reference_order(client):
     # the strided SIMT kernel accumulates exactly like cmma.rs:695-721 (f32, ascending k, separate mul/add)
     client.set_option("gemm.variant", "simt")
