@@ -8,7 +8,13 @@ from cubecl_b200 import ComputeClient, TensorHandle, matmul, reduce  # noqa: E40
 what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 c = ComputeClient.load(0)
-if what == "reduce":
+if what == "reduce_rows":
+    t = TensorHandle.empty_contiguous(c, [8192, 8192], "f32")
+    c.fill_uniform(t.handle, "f32", 8192 * 8192, 5, 0.0, 1.0)
+    out = TensorHandle.empty_contiguous(c, [8192], "f32")
+    for i in range(iters):
+        reduce.launch(c, t, out, 1, "sum")
+elif what == "reduce":
     n = 1 << 28
     xs = [TensorHandle.empty_contiguous(c, [n], "f32") for _ in range(2)]
     for i, x in enumerate(xs):
@@ -17,8 +23,14 @@ if what == "reduce":
     for i in range(iters):
         reduce.launch(c, xs[i % 2], out, None, "sum")
 else:
+    odt = None
     if what == "gemm_batched":
         shape, dt = [8, 4096, 4096], "bf16"
+    elif what == "gemm_fp8":
+        shape, dt, odt = [8192, 8192], "f8e4m3", "bf16"
+    elif what == "gemm_f32_3x":
+        shape, dt = [4096, 4096], "f32"
+        c.set_option("gemm.f32", "3xtf32")
     elif what == "gemm_f32":
         shape, dt = [4096, 4096], "f32"
         c.set_option("gemm.f32", "tf32")
@@ -29,7 +41,7 @@ else:
         n *= s
     a = TensorHandle.empty_contiguous(c, shape, dt)
     b = TensorHandle.empty_contiguous(c, shape, dt)
-    o = TensorHandle.empty_contiguous(c, shape, dt)
+    o = TensorHandle.empty_contiguous(c, shape, odt or dt)
     c.fill_uniform(a.handle, dt, n, 3, -1.0, 1.0)
     c.fill_uniform(b.handle, dt, n, 4, -1.0, 1.0)
     for _ in range(iters):

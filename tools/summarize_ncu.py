@@ -35,7 +35,8 @@ def raw(rep: Path):
 
 traffic = {}
 lines = [f"# ncu --set full summaries, round {tag} (source reports: gpurun_out/{tag}_*.ncu-rep, not tracked)\n"]
-for name, key in (("gemm", "gemm_bf16_8192_dram_bytes"), ("reduce", "reduce_sum_2p28_dram_bytes")):
+extra = [(p.stem[len(tag) + 1:], None) for p in sorted(OUT.glob(f"{tag}_x_*.ncu-rep"))]
+for name, key in [("gemm", "gemm_bf16_8192_dram_bytes"), ("reduce", "reduce_sum_2p28_dram_bytes")] + extra:
     rep = OUT / f"{tag}_{name}.ncu-rep"
     if not rep.exists():
         continue
@@ -48,7 +49,8 @@ for name, key in (("gemm", "gemm_bf16_8192_dram_bytes"), ("reduce", "reduce_sum_
         rd, wr = d.get("dram__bytes_read.sum"), d.get("dram__bytes_write.sum")
         if rd and wr:
             tot = float(rd[1]) * UNIT.get(rd[0], 1.0) + float(wr[1]) * UNIT.get(wr[0], 1.0)
-            traffic[key] = tot
+            if key:
+                traffic[key] = tot
             lines.append(f"{'dram traffic (read+write) per launch':75s} {tot:16.0f} byte\n")
 (PROF / f"{tag}_ncu_full_summary.txt").write_text("".join(lines))
 if traffic:
