@@ -52,6 +52,18 @@ for name, key in [("gemm", "gemm_bf16_8192_dram_bytes"), ("reduce", "reduce_sum_
             if key:
                 traffic[key] = tot
             lines.append(f"{'dram traffic (read+write) per launch':75s} {tot:16.0f} byte\n")
+# extended captures exported remotely as CSV (the .ncu-rep embeds the whole cubin and is too large to bring back)
+for csvp in sorted(OUT.glob(f"{tag}_x_*.csv")):
+    rows = list(csv.reader(csvp.open()))
+    if len(rows) < 3:
+        continue
+    H, U = rows[0], rows[1]
+    for r in rows[2:]:
+        d = {h: (u, v) for h, u, v in zip(H, U, r)}
+        lines.append(f"\n## {csvp.stem[len(tag) + 3:]}: {d.get('Kernel Name', ('', '?'))[1]}\n")
+        for k in KEYS:
+            if k in d:
+                lines.append(f"{k:75s} {d[k][1]:>16s} {d[k][0]}\n")
 (PROF / f"{tag}_ncu_full_summary.txt").write_text("".join(lines))
 if traffic:
     (PROF / "traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
