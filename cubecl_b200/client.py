@@ -157,22 +157,9 @@ class ComputeClient:
         return a.reshape(shape) if shape is not None else a
 
     def empty_tensor(self, shape: Sequence[int], elem_size: int):
-        """(handle, strides) with the CUDA pitched layout: row pitch = row bytes rounded up to
-        clamp(next_pow2(row_bytes), 16, 512) (PitchedMemoryLayoutPolicy::apply, crates/cubecl-runtime/src/allocator.rs:21-72)."""
-        shape = [int(s) for s in shape]
-        if not shape:
-            return self.empty(elem_size), []
-        row_bytes = shape[-1] * elem_size
-        align = min(512, max(16, 1 << max(0, (row_bytes - 1).bit_length()))) if row_bytes else 16
-        pitch = (row_bytes + align - 1) // align * align if len(shape) > 1 else row_bytes
-        strides = [0] * len(shape)
-        strides[-1] = 1
-        if len(shape) > 1:
-            strides[-2] = pitch // elem_size
-            for i in range(len(shape) - 3, -1, -1):
-                strides[i] = strides[i + 1] * shape[i + 1]
-        total = (strides[0] * shape[0] if len(shape) > 1 else shape[0]) * elem_size
-        return self.empty(max(total, 1)), strides
+        """(handle, strides) with the CUDA runtime's pitched layout (client.empty_tensor -> PitchedMemoryLayoutPolicy)."""
+        strides, size = pitched_layout(shape, elem_size)
+        return self.empty(max(size, 1)), strides
 
     def memory_usage(self) -> MemoryUsage:
         a, b = C.c_uint64(), C.c_uint64()
@@ -328,6 +315,37 @@ class ComputeClient:
 
     def probe_memcopy(self, dst: Handle, src: Handle, nbytes: int) -> None:
         _ffi.check(self._lib.b200_probe_memcopy(self._ctx, None, C.c_uint64(dst.ptr), C.c_uint64(src.ptr), int(nbytes)))
+
+
+def optimal_align(last_dim: int, elem_size: int, buffer_align: int = 512) -> int:
+    """crates/cubecl-runtime/src/memory_management/memory_pool/handle.rs:255-263: unit rows stay contiguous, otherwise the
+    row byte size rounded up to a power of two, clamped to [16, buffer_align] (mem_alignment = 512 on CUDA, runtime.rs:81)."""
+    if last_dim == 1:
+        return elem_size
+    row = last_dim * elem_size
+    return min(max(1 << max(0, (row - 1).bit_length()), 16), buffer_align)
+
+
+def pitched_layout(shape: Sequence[int], elem_size: int, mem_alignment: int = 512) -> tuple[list[int], int]:
+    """(strides in elements, allocation bytes) of PitchedMemoryLayoutPolicy::apply with MemoryLayoutStrategy::Optimized
+    (crates/cubecl-runtime/src/allocator.rs:21-72): pitch = row bytes rounded up to optimal_align; strides[rank-2] =
+    pitch / elem_size; outer strides compact over that."""
+    shape = [int(s) for s in shape]
+    rank = len(shape)
+    width = shape[-1] if rank else 1
+    height = 1
+    for s in shape[:-1]:
+        height *= s
+    height = max(height, 1)
+    align = optimal_align(width, elem_size, mem_alignment)
+    width_bytes = width * elem_size
+    pitch = (width_bytes + align - 1) // align * align
+    strides = [1] * rank
+    if rank > 1:
+        strides[rank - 2] = pitch // elem_size
+    for i in range(rank - 3, -1, -1):
+        strides[i] = strides[i + 1] * shape[i + 1]
+    return strides, height * pitch
 
 
 def contiguous_strides(shape: Sequence[int]) -> list[int]:

@@ -60,7 +60,7 @@ extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
   X(cuMemAlloc) X(cuMemFree) X(cuMemAllocHost) X(cuMemFreeHost) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync)            \
   X(cuMemcpyDtoDAsync) X(cuMemsetD32Async) X(cuMemGetInfo)                                                           \
   X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent)                                   \
-  X(cuEventCreate) X(cuEventRecord) X(cuEventElapsedTime) X(cuEventDestroy) X(cuEventSynchronize)                    \
+  X(cuEventCreate) X(cuEventRecord) X(cuEventElapsedTime) X(cuEventDestroy) X(cuEventSynchronize) X(cuEventQuery)                    \
   X(cuTensorMapEncodeTiled) X(cuGetErrorString) X(cuGetErrorName)                                                    \
   X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuCtxEnablePeerAccess) X(cuDeviceCanAccessPeer)
 
@@ -248,6 +248,12 @@ static constexpr size_t kWsBytes = kWsTicketOffset + 256;
 struct PoolBlock {
   size_t size;
   bool in_use;
+  // Stream-ordered reuse (the reference's pools are per-stream and cross-stream hand-offs wait on events,
+  // cubecl-runtime/src/stream/event.rs:50-57): a freed page remembers the stream that last used it and an event recorded
+  // there; the same stream may take it back at once, any other requester only once the event has completed.
+  CUstream last_stream = nullptr;
+  CUevent done = nullptr;
+  bool pending = false;
 };
 
 struct CommState {
@@ -419,7 +425,10 @@ extern "C" int b200_destroy(b200_ctx* c) {
     for (auto& kv : c->p2p)
       for (CUdeviceptr q : kv.second.opened) g_drv.cuIpcCloseMemHandle_p(q);
     if (c->mailbox) g_drv.cuMemFree_p(c->mailbox);
-    for (auto& kv : c->blocks) g_drv.cuMemFree_p(kv.first);
+    for (auto& kv : c->blocks) {
+      if (kv.second.done) g_drv.cuEventDestroy_p(kv.second.done);
+      g_drv.cuMemFree_p(kv.first);
+    }
     for (auto& kv : c->reduce_ws) g_drv.cuMemFree_p(kv.second);
     for (auto& kv : c->pinned) g_drv.cuMemFreeHost_p(kv.first);
     if (c->comm_event) g_drv.cuEventDestroy_p(c->comm_event);
@@ -485,7 +494,7 @@ static size_t pool_round(size_t bytes) {
   return (bytes + align - 1) / align * align;
 }
 
-static int pool_alloc(b200_ctx* c, size_t bytes, CUdeviceptr* out) {
+static int pool_alloc(b200_ctx* c, size_t bytes, CUdeviceptr* out, CUstream for_stream = nullptr) {
   const size_t sz = pool_round(bytes);
   if (c->dry) {
     *out = c->fake_next;
@@ -496,38 +505,59 @@ static int pool_alloc(b200_ctx* c, size_t bytes, CUdeviceptr* out) {
     return B200_OK;
   }
   auto it = c->free_lists.find(sz);
-  if (it != c->free_lists.end() && !it->second.empty()) {
-    *out = it->second.back();
-    it->second.pop_back();
-    c->blocks[*out].in_use = true;
-    c->bytes_in_use += sz;
-    return B200_OK;
+  if (it != c->free_lists.end()) {
+    std::vector<CUdeviceptr>& fl = it->second;
+    for (size_t i = fl.size(); i-- > 0;) {
+      PoolBlock& b = c->blocks[fl[i]];
+      bool usable = !b.pending || (for_stream != nullptr && b.last_stream == for_stream);
+      if (!usable && b.done && g_drv.cuEventQuery_p(b.done) == CUDA_SUCCESS) { b.pending = false; usable = true; }
+      if (!usable) continue;  // still in flight on another stream: leave it for later
+      *out = fl[i];
+      fl.erase(fl.begin() + static_cast<long>(i));
+      b.in_use = true;
+      c->bytes_in_use += sz;
+      return B200_OK;
+    }
   }
   CUdeviceptr p = 0;
   CUresult r = g_drv.cuMemAlloc_p(&p, sz);
   if (r == CUDA_ERROR_OUT_OF_MEMORY) {
-    // release cached pages and retry once (memory_cleanup semantics)
+    // release cached pages and retry once (memory_cleanup semantics); cuMemFree synchronises, so pending pages are safe
     for (auto& fl : c->free_lists) {
-      for (CUdeviceptr q : fl.second) { g_drv.cuMemFree_p(q); c->bytes_reserved -= fl.first; c->blocks.erase(q); }
+      for (CUdeviceptr q : fl.second) {
+        PoolBlock& b = c->blocks[q];
+        if (b.done) g_drv.cuEventDestroy_p(b.done);
+        g_drv.cuMemFree_p(q);
+        c->bytes_reserved -= fl.first;
+        c->blocks.erase(q);
+      }
       fl.second.clear();
     }
     r = g_drv.cuMemAlloc_p(&p, sz);
   }
   if (r != CUDA_SUCCESS) return fail(map_cu(r), "cuMemAlloc(%zu bytes) failed: %s", sz, cu_err(r));
-  c->blocks[p] = PoolBlock{sz, true};
+  PoolBlock nb;
+  nb.size = sz;
+  nb.in_use = true;
+  c->blocks[p] = nb;
   c->bytes_reserved += sz;
   c->bytes_in_use += sz;
   *out = p;
   return B200_OK;
 }
 
-static int pool_free(b200_ctx* c, CUdeviceptr p) {
+// `used_on`: the stream whose queued work may still touch the page (nullptr = the context's compute stream).
+static int pool_free(b200_ctx* c, CUdeviceptr p, CUstream used_on = nullptr) {
   if (c->dry) return B200_OK;
   auto it = c->blocks.find(p);
   if (it == c->blocks.end() || !it->second.in_use) return fail(B200_ERR_INVALID_ARG, "b200_free: pointer not owned by this context");
-  it->second.in_use = false;
-  c->bytes_in_use -= it->second.size;
-  c->free_lists[it->second.size].push_back(p);
+  PoolBlock& b = it->second;
+  b.in_use = false;
+  b.last_stream = used_on ? used_on : c->stream;
+  if (!b.done && g_drv.cuEventCreate_p(&b.done, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) b.done = nullptr;
+  b.pending = (b.done != nullptr) && g_drv.cuEventRecord_p(b.done, b.last_stream) == CUDA_SUCCESS;
+  c->bytes_in_use -= b.size;
+  c->free_lists[b.size].push_back(p);
   return B200_OK;
 }
 
@@ -557,7 +587,13 @@ extern "C" int b200_memory_cleanup(b200_ctx* c) {
   CTX_ENTER_DEVICE(c);
   CU_CHECK(g_drv.cuCtxSynchronize_p());
   for (auto& fl : c->free_lists) {
-    for (CUdeviceptr q : fl.second) { g_drv.cuMemFree_p(q); c->bytes_reserved -= fl.first; c->blocks.erase(q); }
+    for (CUdeviceptr q : fl.second) {
+      PoolBlock& b = c->blocks[q];
+      if (b.done) g_drv.cuEventDestroy_p(b.done);
+      g_drv.cuMemFree_p(q);
+      c->bytes_reserved -= fl.first;
+      c->blocks.erase(q);
+    }
     fl.second.clear();
   }
   return B200_OK;
@@ -938,10 +974,10 @@ static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
     const uint64_t ab = (g.a_sb == 0) ? 1 : g.batch, bb = (g.b_sb == 0) ? 1 : g.batch;
     const uint64_t a_elems = !a_mn ? g.M * pad4(g.K) : g.K * pad4(g.M), b_elems = !b_mn ? g.N * pad4(g.K) : g.K * pad4(g.N);
     CUdeviceptr a_lo = 0, b_lo = 0;
-    int rc = pool_alloc(c, ab * a_elems * 4, &a_lo);
+    int rc = pool_alloc(c, ab * a_elems * 4, &a_lo, st);
     if (rc) return rc;
-    rc = pool_alloc(c, bb * b_elems * 4, &b_lo);
-    if (rc) { pool_free(c, a_lo); return rc; }
+    rc = pool_alloc(c, bb * b_elems * 4, &b_lo, st);
+    if (rc) { pool_free(c, a_lo, st); return rc; }
     rc = !a_mn ? launch_split(c, st, g.a, a_lo, ab, g.M, g.K, g.a_sb, g.a_sm) : launch_split(c, st, g.a, a_lo, ab, g.K, g.M, g.a_sb, g.a_sk);
     if (!rc) rc = !b_mn ? launch_split(c, st, g.b, b_lo, bb, g.N, g.K, g.b_sb, g.b_sn) : launch_split(c, st, g.b, b_lo, bb, g.K, g.N, g.b_sb, g.b_sk);
     if (!rc) {
@@ -951,8 +987,8 @@ static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
       rc = launch_tcgen05(c, st, h, a_mn, b_mn);
     }
     // stream-ordered reuse: the pool hands these pages out again only to later work on this context
-    pool_free(c, a_lo);
-    pool_free(c, b_lo);
+    pool_free(c, a_lo, st);
+    pool_free(c, b_lo, st);
     return rc;
   }
   return launch_tcgen05(c, st, g, a_mn, b_mn);
@@ -1198,11 +1234,11 @@ extern "C" int b200_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_d
       while (outer * S < 4 * sms && len % (S * 2) == 0 && len / (S * 2) >= 4096 && ((len / (S * 2)) * esz) % 16 == 0) S *= 2;
       if (S > 1) {
         CUdeviceptr tmp;
-        int rc = pool_alloc(c, outer * S * 4, &tmp);
+        int rc = pool_alloc(c, outer * S * 4, &tmp, st);
         if (rc) return rc;
         rc = launch_reduce_rows(c, st, op, in_dtype, in, tmp, outer * S, len / S, 1.0f);
         if (!rc) rc = launch_reduce_rows(c, st, op, B200_F32, tmp, out, outer, S, scale);
-        pool_free(c, tmp);
+        pool_free(c, tmp, st);
         return rc;
       }
     }
@@ -1215,11 +1251,11 @@ extern "C" int b200_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_d
     while (outer * S * inner < sms * 1024 && len % (S * 2) == 0 && len / (S * 2) >= 16) S *= 2;
     if (S > 1) {
       CUdeviceptr tmp;
-      int rc = pool_alloc(c, outer * S * inner * 4, &tmp);
+      int rc = pool_alloc(c, outer * S * inner * 4, &tmp, st);
       if (rc) return rc;
       rc = launch_reduce_cols(c, st, op, in_dtype, in, tmp, outer * S, len / S, inner, 1.0f);
       if (!rc) rc = launch_reduce_cols(c, st, op, B200_F32, tmp, out, outer, S, inner, scale);
-      pool_free(c, tmp);
+      pool_free(c, tmp, st);
       return rc;
     }
   }
@@ -1269,11 +1305,11 @@ extern "C" int b200_reduce_strided(b200_ctx* c, b200_stream s, b200_reduce_op op
   for (int i = 0; i < rank; ++i) n *= shape[i];
   if (n == 0) return b200_reduce(c, s, op, in_dtype, in, out, rank, shape, axis);
   CUdeviceptr tmp;
-  int rc = pool_alloc(c, n * dtype_size(in_dtype), &tmp);
+  int rc = pool_alloc(c, n * dtype_size(in_dtype), &tmp, resolve_stream(c, s));
   if (rc) return rc;
   rc = b200_into_contiguous(c, s, in_dtype, in, tmp, rank, shape, strides);
   if (!rc) rc = b200_reduce(c, s, op, in_dtype, tmp, out, rank, shape, axis);
-  pool_free(c, tmp);
+  pool_free(c, tmp, resolve_stream(c, s));
   return rc;
 }
 

@@ -4,7 +4,7 @@ import pytest
 
 from cubecl_b200 import reduce as b200_reduce
 from cubecl_b200 import synth
-from cubecl_b200.client import contiguous_strides
+from cubecl_b200.client import contiguous_strides, optimal_align, pitched_layout
 from cubecl_b200.distributed import shard_range
 
 
@@ -51,3 +51,18 @@ def test_device_dtype_round_trip():
     for dt in ("f32", "f16", "bf16"):
         back = synth.from_device_dtype(synth.to_device_dtype(x, dt), dt)
         assert np.allclose(back, x, rtol=1e-2)
+
+
+def test_pitched_layout_restates_the_reference_policy():
+    # PitchedMemoryLayoutPolicy::apply (allocator.rs:21-72) + optimal_align (memory_pool/handle.rs:255-263), mem_alignment 512
+    assert optimal_align(1, 4) == 4                      # unit rows stay contiguous
+    assert optimal_align(3, 4) == 16                     # 12 B -> 16 (minimum)
+    assert optimal_align(72, 2) == 256                   # 144 B -> next pow2
+    assert optimal_align(8192, 2) == 512                 # clamped to the buffer alignment
+    assert pitched_layout([100, 72], 2) == ([128, 1], 100 * 256)          # 144-byte rows pitch to 256 B = 128 bf16
+    assert pitched_layout([100, 72], 4) == ([128, 1], 100 * 512)          # 288-byte rows pitch to 512 B = 128 f32
+    assert pitched_layout([8192, 8192], 2) == ([8192, 1], 8192 * 16384)   # already 512-aligned: compact
+    assert pitched_layout([2, 3, 5], 4) == ([24, 8, 1], 6 * 32)           # 20-byte rows -> 32 B; outer strides compact over the pitch
+    assert pitched_layout([7, 1], 4) == ([1, 1], 7 * 4)                   # last dim 1: no padding
+    assert pitched_layout([9], 4) == ([1], 64)                            # rank 1: stride 1, size padded to the row alignment
+    assert pitched_layout([], 4) == ([], 4)

