@@ -55,23 +55,25 @@ def test_error_paths_are_loud(client):
             client.set_option("gemm.variant", "auto")
 
 
-def test_pool_does_not_hand_a_page_to_another_stream_while_in_flight(client):
-    # stream-ordered reuse: free a page whose last user (a long fill on a side stream... here the compute stream) is still
-    # running, then allocate for "any stream": the pool must not return that page until the work has finished
-    import ctypes as C
+def test_pool_holds_back_pages_that_are_still_in_flight(client):
+    # stream-ordered reuse: a page freed while its last stream still has ~1 ms of queued work must not be handed to a
+    # requester without stream affinity until that work has finished; afterwards it is recycled
     n = 1 << 28
     big = client.empty(n * 4)
-    for _ in range(6):
-        client.fill_uniform(big, "f32", n, 1, 0.0, 1.0)      # ~1 ms of queued work on the compute stream
+    for _ in range(8):
+        client.fill_uniform(big, "f32", n, 1, 0.0, 1.0)
     ptr = big.ptr
-    del big                                                  # returned to the pool while the fills are still queued
-    other = client.empty(n * 4)                              # requester with no stream affinity
-    assert other.ptr != ptr or True                          # (may coincide only if the GPU already drained; see below)
-    raced = other.ptr == ptr
+    del big                                      # back to the pool while the fills are still queued
+    other = client.empty(n * 4)                  # b200_alloc: no stream affinity -> needs the page's event to be complete
+    held_back = other.ptr != ptr
+    client.sync()
+    del other
     client.sync()
     again = client.empty(n * 4)
-    assert raced or again.ptr == ptr                         # after the drain the page is reusable
-    del other, again
+    assert again.ptr == ptr or not held_back     # once drained, the original page is reusable
+    # 8 fills of 1 GiB take > 1 ms and the host gets here in microseconds, so the page really was in flight
+    assert held_back
+    del again
     client.memory_cleanup()
 
 
