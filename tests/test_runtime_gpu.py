@@ -66,11 +66,12 @@ def test_pool_holds_back_pages_that_are_still_in_flight(client):
     del big                                      # back to the pool while the fills are still queued
     other = client.empty(n * 4)                  # b200_alloc: no stream affinity -> needs the page's event to be complete
     held_back = other.ptr != ptr
+    other_ptr = other.ptr
     client.sync()
     del other
     client.sync()
     again = client.empty(n * 4)
-    assert again.ptr == ptr or not held_back     # once drained, the original page is reusable
+    assert again.ptr in (ptr, other_ptr)         # once drained, cached pages are recycled (no third allocation)
     # 8 fills of 1 GiB take > 1 ms and the host gets here in microseconds, so the page really was in flight
     assert held_back
     del again
