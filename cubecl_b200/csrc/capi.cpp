@@ -333,9 +333,13 @@ static int get_func(b200_ctx* c, const std::string& name, CUfunction* out) {
   if (c->dry) { c->pending_kernel = name; *out = nullptr; return B200_OK; }
   auto it = c->funcs.find(name);
   if (it != c->funcs.end()) { *out = it->second; return B200_OK; }
-  for (CUmodule m : c->modules) {
+  // modules are loaded in the order gemm, reduce, aux; the name prefix says where a kernel lives (no failing lookups,
+  // which API-level tools such as compute-sanitizer would report)
+  const size_t home = (name.rfind("gemm_", 0) == 0 && name != "gemm_simt_strided") || name.rfind("umma_", 0) == 0 ? 0
+                      : name.rfind("reduce_", 0) == 0 ? 1 : 2;
+  if (home < c->modules.size()) {
     CUfunction f;
-    if (g_drv.cuModuleGetFunction_p(&f, m, name.c_str()) == CUDA_SUCCESS) {
+    if (g_drv.cuModuleGetFunction_p(&f, c->modules[home], name.c_str()) == CUDA_SUCCESS) {
       c->funcs[name] = f;
       *out = f;
       return B200_OK;
