@@ -150,3 +150,39 @@ def test_pitched_and_permuted_inputs(client):
     tt = TensorHandle.from_numpy(client, x, "f32").transposed()          # logical [cols, rows]
     got = reduce.launch_alloc(client, tt, 1, "max").to_numpy(client)
     assert np.array_equal(got, x.T.max(axis=1))
+
+
+def test_fuzz_shapes_axes_ops_dtypes(client):
+    # 80 seeded random reductions: rank 1-4, any axis or all, every op and input dtype, odd extents (vector tails, short
+    # and long rows, split paths) -- value ops vs the f64 oracle, index/extremum ops exactly
+    rng = np.random.default_rng(77)
+    ops = ["sum", "mean", "max", "min", "prod", "argmax", "argmin"]
+    for case in range(80):
+        rank = int(rng.integers(1, 5))
+        budget = int(rng.choice([300, 5000, 200000, 3000000]))
+        shape = []
+        for d in range(rank):
+            hi = max(2, int(round(budget ** (1.0 / (rank - d)))) * 2)
+            ext = int(rng.integers(1, hi))
+            shape.append(ext)
+            budget = max(1, budget // ext)
+        axis = None if rng.random() < 0.2 else int(rng.integers(0, rank))
+        op = ops[case % len(ops)]
+        dtype = ["f32", "f16", "bf16"][case % 3]
+        n = int(np.prod(shape))
+        lo, hi = (0.97, 1.03) if op == "prod" else (-1.0, 1.0)
+        x = synth.uniform_f32(500 + case, n, lo, hi).reshape(shape)
+        if op in ("argmax", "argmin", "max", "min") and n > 8:      # plant ties so the lowest-index rule is exercised
+            flat = x.reshape(-1)
+            flat[rng.integers(0, n, 4)] = 2.0 if op in ("argmax", "max") else -2.0
+        got, vals = _run(client, x, axis, op, dtype)
+        exp = oracle.reduce(vals, axis, op)
+        tag = (case, shape, axis, op, dtype)
+        if op in ("argmax", "argmin", "max", "min"):
+            assert np.array_equal(got, exp), tag
+        elif op == "prod":
+            assert np.allclose(got, oracle.reduce_f64(vals, axis, "prod"), rtol=2e-3), tag
+        else:
+            ref = oracle.reduce_f64(vals, axis, op)
+            scale = oracle.reduce_f64(np.abs(vals), axis, op)
+            assert np.all(np.abs(got - ref) <= 2e-5 * scale + 1e-30), tag
