@@ -211,6 +211,8 @@ struct GemmParams {
   uint64_t bias;
   float alpha;
   uint32_t epi_on;
+  uint32_t full_tiles, split_tiles, split_s, pad0;  // tail split, see gemm_tcgen05.cu
+  uint64_t split_ws, split_tickets;
 };
 struct ReduceParams {
   uint64_t in, out, ws;
@@ -242,7 +244,8 @@ struct XgpuParams {
 static constexpr size_t kMailboxBytes = 4096;
 static constexpr uint32_t kWsMaxBlocks = 4096;
 static constexpr uint32_t kWsTicketOffset = kWsMaxBlocks * 4 + kWsMaxBlocks * 8;
-static constexpr size_t kWsBytes = kWsTicketOffset + 256;
+static constexpr uint32_t kWsGemmTicketOffset = kWsTicketOffset + 256;  // u32 per (tail tile, CTA rank) of a split GEMM
+static constexpr size_t kWsBytes = kWsGemmTicketOffset + 1024;
 
 // ================================================================================================ context
 struct PoolBlock {
@@ -478,7 +481,7 @@ extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
 
 extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
-  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "reduce.variant", "reduce.threads",
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
@@ -850,6 +853,8 @@ static bool tma_ok(const GemmProblem& g, bool* a_mn, bool* b_mn) {
   return true;
 }
 
+static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out);
+
 static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
   const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
   const char* in_tag = g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
@@ -941,9 +946,62 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
 
   const uint64_t total_tiles = static_cast<uint64_t>(p.tiles_m) * p.tiles_n * p.batch;
   if (total_tiles >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "too many tiles");
-  const unsigned clusters = (unsigned)std::min<uint64_t>(total_tiles, std::max(1, c->props.num_sms / v.cg));
+  const unsigned max_clusters = (unsigned)std::max(1, c->props.num_sms / v.cg);
+  unsigned clusters = (unsigned)std::min<uint64_t>(total_tiles, max_clusters);
+
+  // Tail split: when the last wave would leave most CTA pairs idle, cut each of its tiles into S K-slices (deterministic:
+  // slabs are added in slice order by whichever slice finishes last).  time(S) in tile-times = full_waves + ceil(rem*S/C)/S.
+  const std::string split_opt = opt(c, "gemm.split_k", "auto");
+  const uint64_t num_kb = ((g.K + block_k - 1) / block_k) * p.k_segments;
+  const uint64_t rem = total_tiles % max_clusters, full_waves = total_tiles / max_clusters;
+  const bool float_acc = !(g.in_dtype == B200_U8 || g.in_dtype == B200_I8);
+  unsigned split_s = 1;
+  if (split_opt != "off" && float_acc && rem != 0) {
+    const unsigned s_max = 4, min_kb = 8;
+    if (split_opt == "auto") {
+      double best_t = static_cast<double>(full_waves) + 1.0;
+      const double base_t = best_t;
+      for (unsigned s2 = 2; s2 <= s_max; ++s2) {
+        if (num_kb / s2 < min_kb) break;
+        // Measured on B200 (tools/perf_sweep.py split, profiles/r01_split_k_sweep.log): publishing a slab, the ticket round
+        // trip and the ordered re-read by the last slice cost about (14 + 8 S) k-block times (one k-block = 128 B of K per
+        // row, ~0.4 us on a pair tile whatever the dtype), all exposed because nothing follows the tail.  So the split pays
+        // for K-heavy problems with few tiles (512^2 x 16384: 114 -> 50 us) and not for 4096^3 bf16 (break-even).
+        const double overhead = (14.0 + 8.0 * s2) / static_cast<double>(num_kb);
+        const double t = full_waves + static_cast<double>((rem * s2 + max_clusters - 1) / max_clusters) / s2 + overhead;
+        if (t < best_t - 1e-9) { best_t = t; split_s = s2; }
+      }
+      if (base_t - best_t < 0.08 * base_t) split_s = 1;  // inside the measurement noise: keep whole tiles
+    } else {
+      const int want = atoi(split_opt.c_str());
+      if (want < 1 || want > 8) return fail(B200_ERR_INVALID_ARG, "gemm.split_k must be auto, off or 1..8");
+      split_s = (unsigned)std::min<uint64_t>((uint64_t)want, std::max<uint64_t>(1, num_kb));
+    }
+  }
+  CUdeviceptr slabs = 0;
+  if (split_s > 1) {
+    CUdeviceptr ws = 0;
+    rc = reduce_workspace(c, st, &ws);
+    if (rc) return rc;
+    const uint64_t slab_bytes = 128ull * v.cg * v.block_n * 4;
+    rc = pool_alloc(c, rem * split_s * slab_bytes, &slabs, st);
+    if (rc) return rc;
+    p.full_tiles = (uint32_t)(total_tiles - rem);
+    p.split_tiles = (uint32_t)rem;
+    p.split_s = split_s;
+    p.split_ws = slabs;
+    p.split_tickets = ws + kWsGemmTicketOffset;
+    clusters = (unsigned)std::min<uint64_t>(p.full_tiles + rem * split_s, max_clusters);
+    if (c->dry) {
+      char line[160];
+      snprintf(line, sizeof(line), "gemm tail split: %u full tiles + %u tiles x %u k-slices\n", p.full_tiles, p.split_tiles, split_s);
+      c->plan += line;
+    }
+  }
   void* args[] = {&ta, &tb, &ta_lo, &tb_lo, &p};
-  return launch(c, f, clusters * v.cg, 1, 1, 256, smem, v.cg, st, args);
+  rc = launch(c, f, clusters * v.cg, 1, 1, 256, smem, v.cg, st, args);
+  if (slabs) pool_free(c, slabs, st);  // stream-ordered: reusable by later work once this launch has drained
+  return rc;
 }
 
 static inline uint64_t pad4(uint64_t elems) { return (elems + 3) / 4 * 4; }

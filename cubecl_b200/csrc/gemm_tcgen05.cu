@@ -31,6 +31,13 @@ struct GemmParams {
   uint64_t bias;              // f32[N] added per output column, or 0
   float alpha;                // out = act(alpha * acc + bias[n]); the epilogue is skipped when alpha == 1, bias == 0, act == 0
   uint32_t epi_on;
+  // Tail split (deterministic split-K for a mostly empty last wave): work units [0, full_tiles) are whole tiles; each of the
+  // remaining `split_tiles` tiles is cut into `split_s` K-slices that run on different CTA pairs.  A slice stores its f32
+  // accumulators to its own slab in `split_ws`; the last slice to finish (ticket) adds the slabs in slice order and writes
+  // the output, so the result does not depend on which slice arrived last.  split_s <= 1 disables the mechanism.
+  uint32_t full_tiles, split_tiles, split_s, pad0;
+  uint64_t split_ws;          // slabs: [split_tiles][split_s][CG] x (128 x BLOCK_N f32, thread-interleaved 16 B units)
+  uint64_t split_tickets;     // u32 [split_tiles][CG], zero on entry, left zero on exit
 };
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6 };
@@ -99,6 +106,26 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, const GemmParams& p)
   return c;
 }
 
+struct WorkUnit {
+  uint32_t tile, kb0, kb1, slice;
+  bool partial;
+};
+
+__device__ __forceinline__ WorkUnit unit_decode(uint32_t u, const GemmParams& p, uint32_t num_kb) {
+  WorkUnit w;
+  if (p.split_s <= 1 || u < p.full_tiles) {
+    w.tile = u; w.kb0 = 0; w.kb1 = num_kb; w.slice = 0; w.partial = false;
+  } else {
+    const uint32_t v = u - p.full_tiles;
+    w.tile = p.full_tiles + v / p.split_s;
+    w.slice = v % p.split_s;
+    w.kb0 = static_cast<uint32_t>((static_cast<uint64_t>(num_kb) * w.slice) / p.split_s);
+    w.kb1 = static_cast<uint32_t>((static_cast<uint64_t>(num_kb) * (w.slice + 1)) / p.split_s);
+    w.partial = true;
+  }
+  return w;
+}
+
 template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUtensorMap* tma_b_hi, const CUtensorMap* tma_a_lo,
                                           const CUtensorMap* tma_b_lo, const GemmParams& p) {
@@ -131,6 +158,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t split_flag = tmem_slot + 4;  // "this CTA reduces the slabs" broadcast among the epilogue warps
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -166,7 +194,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const uint32_t total_tiles = p.batch * p.tiles_m * p.tiles_n;
+  const uint32_t total_tiles = (p.split_s > 1) ? p.full_tiles + p.split_tiles * p.split_s  // work units, see GemmParams
+                                               : p.batch * p.tiles_m * p.tiles_n;
   // 3xTF32: x = hi + lo with hi = the top 19 bits of x (exactly what the tf32 datapath reads from an f32 operand, so the
   // ORIGINAL tensors serve as "hi") and lo = x - hi materialised once.  A*B ~= hi*hi + hi*lo + lo*hi is accumulated by
   // running the K loop over three segments with the operand descriptors swapped per segment.
@@ -187,12 +216,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       constexpr int kAItems = A_MN ? NUM_CHUNKS_A : 1, kBItems = B_MN ? NUM_CHUNKS : 1;
       uint32_t s = 0, ph = 0;
       for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
-        const TileCoord tc = tile_coord(t, p);
+        const WorkUnit wu = unit_decode(t, p, num_kb);
+        const TileCoord tc = tile_coord(wu.tile, p);
         const int m0 = static_cast<int>((tc.m_blk * CG + rank) * 128);
         const int n0 = static_cast<int>(tc.n_blk * BLOCK_N + rank * N_LOCAL);
         const int ba = static_cast<int>(tc.b * p.a_bmul), bb = static_cast<int>(tc.b * p.b_bmul);
-        uint32_t seg = 0, kk = 0;  // segment (0 unless k_segments == 3) and k-block within the segment
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        uint32_t seg = wu.kb0 / seg_kb, kk = wu.kb0 - seg * seg_kb;  // segment (0 unless k_segments == 3), k-block within it
+        for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
@@ -226,10 +256,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     if (leader && lane == 0) {
       uint32_t s = 0, ph = 0, as = 0, aph = 0;
       for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
+        const WorkUnit wu = unit_decode(t, p, num_kb);
         mbar_wait(tempty_bar(as), aph ^ 1);  // epilogue (both CTAs) drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + s * STAGE_BYTES;
@@ -247,7 +278,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
             const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
-            umma_ss<CG, KIND>(d_tmem, a_k, b_k, IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_ss<CG, KIND>(d_tmem, a_k, b_k, IDESC, (kb != wu.kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit<CG>(empty_bar(s));  // smem slot reusable once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -263,34 +294,56 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     const uint32_t tempty_leader = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t osz = (OUT == OUT_F32) ? 4 : 2;
     uint32_t as = 0, aph = 0;
+    // out = act(alpha * acc + bias[n]) on 32 accumulator columns held by this thread (float kinds only)
+    auto fused_epilogue = [&](uint32_t (&v)[32], uint32_t n0) {
+      if (KIND < KIND_U8 && p.epi_on) {
+        const float* bias = reinterpret_cast<const float*>(p.bias);  // warp-uniform loads
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) * p.alpha;
+          if (bias != nullptr && n0 + j < p.N) x += __ldg(bias + n0 + j);
+          if (p.epi_act == 1) x = fmaxf(x, 0.f);
+          else if (p.epi_act == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+          v[j] = __float_as_uint(x);
+        }
+      }
+    };
     for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
-      const TileCoord tc = tile_coord(t, p);
-      const uint32_t m = (tc.m_blk * CG + rank) * 128 + q * 32 + lane;
+      const WorkUnit wu = unit_decode(t, p, num_kb);
+      const TileCoord tc = tile_coord(wu.tile, p);
+      const uint32_t row_in_cta = q * 32 + lane;
+      const uint32_t m = (tc.m_blk * CG + rank) * 128 + row_in_cta;
       const uint32_t n_tile = tc.n_blk * BLOCK_N;
       const uint64_t row_ptr = p.out + (static_cast<uint64_t>(tc.b) * p.out_batch_stride + static_cast<uint64_t>(m) * p.out_row_stride) * osz;
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+      if (!wu.partial) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const uint32_t n0 = n_tile + c * 32;
-        if (m < p.M && n0 < p.N) {
-          if (KIND < KIND_U8 && p.epi_on) {
-            // fused epilogue on the f32 accumulators: out = act(alpha * acc + bias[n]); bias loads are warp-uniform
-            const float* bias = reinterpret_cast<const float*>(p.bias);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(v[j]) * p.alpha;
-              if (bias != nullptr && n0 + j < p.N) x += __ldg(bias + n0 + j);
-              if (p.epi_act == 1) x = fmaxf(x, 0.f);
-              else if (p.epi_act == 2) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-              v[j] = __float_as_uint(x);
-            }
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const uint32_t n0 = n_tile + c * 32;
+          if (m < p.M && n0 < p.N) {
+            fused_epilogue(v, n0);
+            store_chunk32<OUT>(row_ptr, n0, p.N, p.vec_store != 0, v);
           }
-          store_chunk32<OUT>(row_ptr, n0, p.N, p.vec_store != 0, v);
+        }
+      } else {
+        // K-slice of a tail tile: raw f32 accumulators -> this slice's slab.  Slab layout per CTA: [chunk c][j][thread] x 16 B,
+        // so one warp store covers 512 contiguous bytes (a row-per-thread layout costs 32 LSU wavefronts per store and is
+        // exposed here: nothing overlaps the tail).
+        const uint32_t tail = wu.tile - p.full_tiles;
+        const uint64_t cta_slab_bytes = static_cast<uint64_t>(128) * BLOCK_N * 4;
+        uint4* dst = reinterpret_cast<uint4*>(p.split_ws + ((static_cast<uint64_t>(tail) * p.split_s + wu.slice) * CG + rank) * cta_slab_bytes) + row_in_cta;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) __stcg(dst + (c * 8 + j) * 128, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
       }
       tcgen05_fence_before();
@@ -299,6 +352,64 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
       }
       if (++as == 2) { as = 0; aph ^= 1; }
+      if (wu.partial) {
+        // publish the slab, take a ticket for (tile, CTA rank); the last of the split_s slices reduces in slice order
+        const uint32_t tail = wu.tile - p.full_tiles;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          unsigned int* ticket = reinterpret_cast<unsigned int*>(p.split_tickets) + tail * CG + rank;
+          const unsigned int old = atomicAdd(ticket, 1u);
+          const uint32_t last = (old == p.split_s - 1) ? 1u : 0u;
+          if (last) *ticket = 0;  // every slice has arrived: leave the ticket ready for the next launch
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(split_flag), "r"(last) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t last;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(split_flag) : "memory");
+        if (last) {
+          __threadfence();
+          const uint64_t cta_slab_bytes = static_cast<uint64_t>(128) * BLOCK_N * 4;
+          const uint64_t slice_stride = cta_slab_bytes * CG / 16;  // in uint4
+          const float4* src0 = reinterpret_cast<const float4*>(p.split_ws + (static_cast<uint64_t>(tail) * p.split_s * CG + rank) * cta_slab_bytes) + row_in_cta;
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            // slices are ADDED in slice order (bit-reproducible); two slices' loads are in flight at a time
+            for (uint32_t sl = 0; sl < p.split_s; sl += 2) {
+              const bool two = sl + 1 < p.split_s;
+              const float4* s0 = src0 + sl * slice_stride + c * 8 * 128;
+              const float4* s1 = s0 + (two ? slice_stride : 0);
+              float4 x0[8], x1[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x0[j] = __ldcg(s0 + j * 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x1[j] = __ldcg(s1 + j * 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                acc[4 * j] += x0[j].x; acc[4 * j + 1] += x0[j].y; acc[4 * j + 2] += x0[j].z; acc[4 * j + 3] += x0[j].w;
+              }
+              if (two) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  acc[4 * j] += x1[j].x; acc[4 * j + 1] += x1[j].y; acc[4 * j + 2] += x1[j].z; acc[4 * j + 3] += x1[j].w;
+                }
+              }
+            }
+            uint32_t v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
+            const uint32_t n0 = n_tile + c * 32;
+            if (m < p.M && n0 < p.N) {
+              fused_epilogue(v, n0);
+              store_chunk32<OUT>(row_ptr, n0, p.N, p.vec_store != 0, v);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the flag word is reused by the next partial unit
+      }
     }
   }
 

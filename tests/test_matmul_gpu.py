@@ -17,6 +17,7 @@ def _reset_options(client):
     yield
     client.set_option("gemm.variant", "auto")
     client.set_option("gemm.f32", "3xtf32")
+    client.set_option("gemm.split_k", "auto")
 
 
 # ------------------------------------------------------------------------------------------------ reference goldens
@@ -226,6 +227,72 @@ def test_fused_epilogue(client, variant, in_dtype, out_dtype, activation):
     scale = alpha * fabs + np.abs(bias)[None, :] + 1e-6
     tol = {"f32": 1e-5 if in_dtype != "f32" else 1e-4, "bf16": 1e-2, "f16": 2e-3}[out_dtype]
     assert np.max(np.abs(got - exp) / scale) <= tol
+
+
+# ------------------------------------------------------------------------------------------------ tail split (split-K)
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("split", ["2", "3", "4"])
+@pytest.mark.parametrize("in_dtype,out_dtype,mode,tol", [("bf16", "f32", "-", 1e-5), ("bf16", "bf16", "-", 1e-2),
+                                                         ("f32", "f32", "3xtf32", 2e-6), ("f32", "f32", "tf32", 1e-3)])
+def test_tail_split_all_tiles(client, variant, split, in_dtype, out_dtype, mode, tol):
+    # fewer tiles than CTA pairs: every tile is cut into K-slices; ragged M/N, K not a multiple of the slice count
+    client.set_option("gemm.variant", variant)
+    client.set_option("gemm.split_k", split)
+    if mode != "-":
+        client.set_option("gemm.f32", mode)
+    M, N, K = 300, 520, 1096
+    a_dev, a = make_operand((M, K), in_dtype, 301)
+    b_dev, b = make_operand((K, N), in_dtype, 302)
+    got = run_matmul(client, a_dev, b_dev, in_dtype, out_dtype)
+    check_against_oracle(got, a, b, out_dtype, tight=tol)
+    again = run_matmul(client, a_dev, b_dev, in_dtype, out_dtype)
+    assert np.array_equal(got, again)          # slabs are added in slice order: bit-reproducible
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("split", ["off", "2", "4"])
+def test_tail_split_after_full_waves(client, variant, split):
+    # 80 (2-CTA) / 160 / 320 (1-CTA) tiles: full waves of whole tiles first, then the sliced remainder; batch of 2 on top
+    client.set_option("gemm.variant", variant)
+    client.set_option("gemm.split_k", split)
+    M, N, K = 2560, 2048, 512
+    a_dev, a = make_operand((M, K), "bf16", 311)
+    b_dev, b = make_operand((N, K), "bf16", 312)
+    got = run_matmul(client, a_dev, b_dev, "bf16", "f32", rhs_transposed=True)
+    check_against_oracle(got, a, np.ascontiguousarray(b.T), "f32", tight=1e-5)
+    client.set_option("gemm.split_k", "off")
+    ref = run_matmul(client, a_dev, b_dev, "bf16", "f32", rhs_transposed=True)
+    # f32 accumulation in a different association: tiny differences only, and none in the whole-tile region for "off"
+    assert np.max(np.abs(got - ref)) <= 1e-4 * np.max(np.abs(ref))
+    if split == "off":
+        assert np.array_equal(got, ref)
+
+
+def test_tail_split_batched_fused_epilogue_and_fp8(client):
+    from math import erf
+    client.set_option("gemm.split_k", "3")
+    Bn, M, N, K = 3, 260, 272, 1536
+    a_dev, a = make_operand((Bn, M, K), "f8e4m3", 321)
+    b_dev, b = make_operand((1, K, N), "f8e4m3", 322)
+    bias = synth.uniform_f32(323, N, -2.0, 2.0)
+    lhs, rhs = TensorHandle.from_numpy(client, a_dev, "f8e4m3"), TensorHandle.from_numpy(client, b_dev, "f8e4m3")
+    out = TensorHandle.empty_contiguous(client, [Bn, M, N], "f16")
+    matmul.launch(client, lhs, rhs, out, alpha=0.25, bias=TensorHandle.from_numpy(client, bias, "f32"), activation="gelu")
+    got = synth.from_device_dtype(out.to_numpy(client), "f16").astype(np.float64).reshape(Bn, M, N)
+    for i in range(Bn):
+        f64, fabs = oracle.matmul_f64(a[i], b[0])
+        x = 0.25 * f64 + bias.astype(np.float64)[None, :]
+        exp = 0.5 * x * (1.0 + np.vectorize(erf)(x / np.sqrt(2.0)))
+        scale = 0.25 * fabs + np.abs(bias)[None, :] + 1e-6
+        assert np.max(np.abs(got[i] - exp) / scale) <= 2e-3
+
+
+def test_tail_split_leaves_integer_paths_alone(client):
+    client.set_option("gemm.split_k", "4")
+    a = (np.arange(256 * 2048) % 251).astype(np.uint8).reshape(256, 2048)
+    b = (np.arange(2048 * 256) % 241).astype(np.uint8).reshape(2048, 256)
+    got = run_matmul_int(client, a, b, "u8")
+    assert np.array_equal(got, a.astype(np.int64) @ b.astype(np.int64))
 
 
 def test_fuzz_shapes_layouts_dtypes(client):

@@ -82,10 +82,41 @@ def test_f32_defaults_to_3xtf32_with_two_split_passes(plan):
     assert launches == ["split_tf32_lo", "split_tf32_lo", "gemm_tf32_f32_2sm_n256_kn"]   # lo parts only, ONE gemm launch
     assert t.count("tmap ") == 4                                         # A, B (originals = hi) + A_lo, B_lo
     assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
-    assert t.count("alloc ") == 2 and f"alloc {n * n * 4}" in t          # 1x temporaries, not 3x
+    assert t.count(f"alloc {n * n * 4}") == 2                            # 1x temporaries (lo parts), not 3x
+    assert "gemm tail split: 222 full tiles + 34 tiles x 2 k-slices" in t  # 256 tiles on 74 CTA pairs: 4th wave is 46 % full
     plan.option("gemm.f32", "tf32")
     rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gemm_tf32_f32_2sm_n256_kn"]
+
+
+def test_tail_split_policy(plan):
+    """Deterministic split-K of the last partial wave (launch_tcgen05): only when it pays, never for integer accumulators."""
+    def mm(n, k, dt=BF16, out=BF16):
+        return plan.matmul(dt, out, [n, k], [k, 1], [k, n], [n, 1], [n, n], [n, 1])
+    rc, t = mm(8192, 8192)                     # 1024 tiles = 13.8 waves: tail is 84 % full, nothing to gain
+    assert rc == 0 and "tail split" not in t
+    rc, t = mm(4096, 4096)                     # 3.46 waves, but 64 k-blocks per tile: the slab exchange would eat the gain
+    assert rc == 0 and "tail split" not in t
+    rc, t = mm(4096, 4096, dt=F32, out=F32)    # 3xTF32: 384 k-blocks per tile -> 3 waves + 68 half tiles on 74 pairs
+    assert rc == 0 and "222 full tiles + 34 tiles x 2 k-slices" in t
+    assert f"alloc {34 * 2 * 256 * 256 * 4}" in t and "grid=(148,1,1)" in t
+    rc, t = mm(1024, 8192)                     # 32 n128 tiles on 74 pairs: 2 slices fill 64 of them
+    assert rc == 0 and "0 full tiles + 32 tiles x 2 k-slices" in t and "2sm_n128" in t and "grid=(128,1,1)" in t
+    rc, t = mm(512, 16384)                     # 8 tiles, 256 k-blocks each: 4 slices
+    assert rc == 0 and "0 full tiles + 8 tiles x 4 k-slices" in t
+    rc, t = mm(1024, 256)                      # 4 k-blocks: too short to slice
+    assert rc == 0 and "tail split" not in t
+    rc, t = mm(4096, 4096, dt=8, out=4)        # u8 -> i32: exact integer accumulation stays in one CTA pair
+    assert rc == 0 and "tail split" not in t
+    plan.option("gemm.split_k", "off")
+    rc, t = mm(512, 16384)
+    assert rc == 0 and "tail split" not in t
+    plan.option("gemm.split_k", "3")
+    rc, t = mm(4096, 4096)
+    assert rc == 0 and "34 tiles x 3 k-slices" in t
+    plan.option("gemm.split_k", "9")
+    rc, t = mm(4096, 4096)
+    assert rc != 0
 
 
 def test_small_and_unaligned_problems(plan):

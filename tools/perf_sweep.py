@@ -83,6 +83,36 @@ if "gemm" in what:
         c.set_option("gemm.group_m", 8)
         del a, b, o
 
+if "split" in what:
+    # tail split (deterministic split-K of the last partial wave): off vs forced S vs the auto policy
+    print("gemm.split_k sweep (auto variant), CUDA events:")
+    for (idt, odt, m, n, k, batch, mode) in (("bf16", "bf16", 4096, 4096, 4096, 1, "-"), ("bf16", "bf16", 2048, 2048, 2048, 1, "-"),
+                                             ("bf16", "bf16", 1024, 1024, 8192, 1, "-"), ("bf16", "bf16", 6144, 6144, 6144, 1, "-"),
+                                             ("bf16", "bf16", 5120, 5120, 5120, 1, "-"), ("bf16", "bf16", 8192, 8192, 8192, 1, "-"),
+                                             ("bf16", "bf16", 512, 512, 16384, 1, "-"), ("bf16", "f32", 3072, 3072, 3072, 1, "-"),
+                                             ("f32", "f32", 4096, 4096, 4096, 1, "tf32"), ("f32", "f32", 4096, 4096, 4096, 1, "3xtf32"),
+                                             ("f8e4m3", "bf16", 4096, 4096, 4096, 1, "-"), ("bf16", "bf16", 4096, 4096, 4096, 3, "-")):
+        sa = [batch, m, k] if batch > 1 else [m, k]
+        sb = [batch, k, n] if batch > 1 else [k, n]
+        so = [batch, m, n] if batch > 1 else [m, n]
+        a = TensorHandle.empty_contiguous(c, sa, idt)
+        b = TensorHandle.empty_contiguous(c, sb, idt)
+        o = TensorHandle.empty_contiguous(c, so, odt)
+        c.fill_uniform(a.handle, idt, int(np.prod(sa)), 3, -1.0, 1.0)
+        c.fill_uniform(b.handle, idt, int(np.prod(sb)), 4, -1.0, 1.0)
+        if idt == "f32":
+            c.set_option("gemm.f32", mode)
+        flops = 2.0 * m * n * k * batch
+        row = []
+        for sk in ("off", "2", "3", "4", "auto"):
+            c.set_option("gemm.split_k", sk)
+            ms = min(time_ms(c, lambda: matmul.launch(c, a, b, o), iters=20, warm=3) for _ in range(3))
+            row.append(f"{sk}={ms * 1e3:7.1f}us/{flops / ms / 1e9:6.0f}TF")
+        print(f"  {idt:6s}->{odt:4s} {mode:6s} {batch}x{m}x{n}x{k}: " + "  ".join(row), flush=True)
+        c.set_option("gemm.split_k", "auto")
+        c.set_option("gemm.f32", "3xtf32")
+        del a, b, o
+
 if "axis" in what:
     # the reduction tutorial's shapes (cubecl-book: 1.085 ms / 3.124 ms / 1.483 ms / 0.924 ms on an unnamed wgpu device)
     print("axis reductions (sum), CUDA events, min of 5 x 20 launches:")
