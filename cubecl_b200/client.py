@@ -24,12 +24,14 @@ from . import _ffi
 from ._ffi import B200Error
 
 DTYPES = {"f32": _ffi.F32, "f16": _ffi.F16, "bf16": _ffi.BF16, "u32": _ffi.U32, "i32": _ffi.I32, "f64": _ffi.F64,
-          "i64": _ffi.I64, "u64": _ffi.U64, "u8": _ffi.U8, "i8": _ffi.I8, "f8e4m3": _ffi.F8E4M3, "f8e5m2": _ffi.F8E5M2}
+          "i64": _ffi.I64, "u64": _ffi.U64, "u8": _ffi.U8, "i8": _ffi.I8, "f8e4m3": _ffi.F8E4M3, "f8e5m2": _ffi.F8E5M2,
+          "f4e2m1x2": _ffi.F4E2M1X2, "ue8m0": _ffi.UE8M0}   # f4e2m1x2: one ELEMENT of this dtype is a byte holding two e2m1
 DTYPE_SIZE = {"f32": 4, "f16": 2, "bf16": 2, "u32": 4, "i32": 4, "f64": 8, "i64": 8, "u64": 8, "u8": 1, "i8": 1,
-              "f8e4m3": 1, "f8e5m2": 1}
+              "f8e4m3": 1, "f8e5m2": 1, "f4e2m1x2": 1, "ue8m0": 1}
 # numpy view used when bytes come back to the host (bf16 has no numpy type: raw uint16 bit patterns)
 NP_VIEW = {"f32": np.float32, "f16": np.float16, "bf16": np.uint16, "u32": np.uint32, "i32": np.int32, "f64": np.float64,
-           "i64": np.int64, "u64": np.uint64, "u8": np.uint8, "i8": np.int8, "f8e4m3": np.uint8, "f8e5m2": np.uint8}
+           "i64": np.int64, "u64": np.uint64, "u8": np.uint8, "i8": np.int8, "f8e4m3": np.uint8, "f8e5m2": np.uint8,
+           "f4e2m1x2": np.uint8, "ue8m0": np.uint8}
 
 
 class ServerError(RuntimeError):

@@ -123,6 +123,87 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Block-scaled (MX) support.
+//
+// pack_scales: ue8m0 scales in the reference's layout -- [batch, rows, n_scales] row-major, one scale per row per 32 K
+// elements (test_cmma_scaled: crates/cubecl-core/src/runtime_tests/cmma.rs:1518-1533) -- to the tensor core's packed form:
+// [batch * tiles][atoms][512 B], tile = 128 rows, atom = 4 consecutive scales, byte (r % 32) * 16 + (r / 32) * 4 + s.
+// Rows / scales beyond the tensor are written as 127 (= 1.0), so padded K blocks multiply TMA's zero fill by a finite value.
+struct PackScalesParams {
+  uint64_t in, out;
+  uint32_t batch, rows, n_scales, tiles, atoms, pad;
+};
+
+extern "C" __global__ void __launch_bounds__(256) pack_scales(const __grid_constant__ PackScalesParams p) {
+  const uint64_t words = static_cast<uint64_t>(p.batch) * p.tiles * p.atoms * 128;  // one 32-bit word = 4 scales of one row
+  const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
+  uint32_t* out = reinterpret_cast<uint32_t*>(p.out);
+  for (uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; w < words; w += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t in_chunk = static_cast<uint32_t>(w % 128);
+    const uint64_t chunk = w / 128;
+    const uint32_t atom = static_cast<uint32_t>(chunk % p.atoms);
+    const uint64_t bt = chunk / p.atoms;
+    const uint32_t tile = static_cast<uint32_t>(bt % p.tiles), b = static_cast<uint32_t>(bt / p.tiles);
+    const uint32_t r32 = in_chunk / 4, g = in_chunk % 4;
+    const uint32_t row = tile * 128 + g * 32 + r32;
+    uint32_t word = 0;
+#pragma unroll
+    for (uint32_t sidx = 0; sidx < 4; ++sidx) {
+      const uint32_t ks = atom * 4 + sidx;
+      const uint32_t v = (row < p.rows && ks < p.n_scales) ? in[(static_cast<uint64_t>(b) * p.rows + row) * p.n_scales + ks] : 127u;
+      word |= v << (8 * sidx);
+    }
+    out[w] = word;
+  }
+}
+
+__device__ __forceinline__ float ue8m0_to_f32(uint32_t bits) {
+  if (bits == 255u) return __uint_as_float(0x7FC00000u);      // NaN
+  if (bits == 0u) return __uint_as_float(0x00400000u);        // 2^-127 (an f32 subnormal)
+  return __uint_as_float(bits << 23);
+}
+__device__ __forceinline__ float mx_elem_to_f32(uint64_t base, uint64_t idx, uint32_t dt) {
+  if (dt == 12) {  // packed e2m1: element 2i in the low nibble of byte i (e2m1x2::from_f32_slice, cubecl-common/src/float/fp4.rs:204-216)
+    const uint32_t byte = reinterpret_cast<const uint8_t*>(base)[idx >> 1];
+    const uint32_t nib = (idx & 1) ? (byte >> 4) : (byte & 0xFu);
+    const float mag[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+    const float v = mag[nib & 7u];
+    return (nib & 8u) ? -v : v;
+  }
+  return load_as_f32(base, idx, dt);
+}
+
+// Reference-order block-scaled matmul (the expected-value loop of test_cmma_scaled, cmma.rs:1572-1590):
+//   out[m,n] = sum over l, increasing, in f32 with separately rounded operations, of ((a[m,l] * sa[m,l/32]) * b[n,l]) * sb[n,l/32]
+// One thread per output element; the path for shapes TMA cannot describe, and the on-device cross-check of the tcgen05 path.
+struct ScaledSimtParams {
+  uint64_t a, b, sa, sb, out;
+  uint32_t batch, M, N, K;       // K in elements
+  uint32_t a_dtype, b_dtype, out_dtype, scale_block;
+  uint32_t a_bmul, b_bmul, pad0, pad1;
+};
+
+extern "C" __global__ void __launch_bounds__(256) gemm_scaled_simt(const __grid_constant__ ScaledSimtParams p) {
+  const uint64_t total = static_cast<uint64_t>(p.batch) * p.M * p.N;
+  const uint32_t n_scales = (p.K + p.scale_block - 1) / p.scale_block;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t n = static_cast<uint32_t>(i % p.N);
+    const uint32_t m = static_cast<uint32_t>((i / p.N) % p.M);
+    const uint32_t b = static_cast<uint32_t>(i / (static_cast<uint64_t>(p.N) * p.M));
+    const uint64_t arow = (static_cast<uint64_t>(b) * p.a_bmul * p.M + m), brow = (static_cast<uint64_t>(b) * p.b_bmul * p.N + n);
+    const uint8_t* sa = reinterpret_cast<const uint8_t*>(p.sa) + arow * n_scales;
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(p.sb) + brow * n_scales;
+    float acc = 0.f;
+    for (uint32_t l = 0; l < p.K; ++l) {
+      const float av = mx_elem_to_f32(p.a, arow * p.K + l, p.a_dtype), bv = mx_elem_to_f32(p.b, brow * p.K + l, p.b_dtype);
+      const float as = ue8m0_to_f32(sa[l / p.scale_block]), bs = ue8m0_to_f32(sb[l / p.scale_block]);
+      acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__fmul_rn(av, as), bv), bs));
+    }
+    store_from_f32(p.out, i, p.out_dtype, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ 3xTF32 split
 // lo = x - hi, hi = x with the low 13 mantissa bits cleared: the tf32 datapath ignores those bits of an f32 operand, so
 // the ORIGINAL tensor already acts as "hi" and only `lo` (exact in f32) is materialised, with the input's own strides

@@ -213,6 +213,17 @@ struct GemmParams {
   uint32_t epi_on;
   uint32_t full_tiles, split_tiles, split_s, pad0;  // tail split, see gemm_tcgen05.cu
   uint64_t split_ws, split_tickets;
+  uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;  // block-scaled kinds
+};
+struct PackScalesParams {
+  uint64_t in, out;
+  uint32_t batch, rows, n_scales, tiles, atoms, pad;
+};
+struct ScaledSimtParams {
+  uint64_t a, b, sa, sb, out;
+  uint32_t batch, M, N, K;
+  uint32_t a_dtype, b_dtype, out_dtype, scale_block;
+  uint32_t a_bmul, b_bmul, pad0, pad1;
 };
 struct ReduceParams {
   uint64_t in, out, ws;
@@ -338,7 +349,7 @@ static int get_func(b200_ctx* c, const std::string& name, CUfunction* out) {
   if (it != c->funcs.end()) { *out = it->second; return B200_OK; }
   // modules are loaded in the order gemm, reduce, aux; the name prefix says where a kernel lives (no failing lookups,
   // which API-level tools such as compute-sanitizer would report)
-  const size_t home = (name.rfind("gemm_", 0) == 0 && name != "gemm_simt_strided") || name.rfind("umma_", 0) == 0 ? 0
+  const size_t home = (name.rfind("gemm_", 0) == 0 && name != "gemm_simt_strided" && name != "gemm_scaled_simt") || name.rfind("umma_", 0) == 0 ? 0
                       : name.rfind("reduce_", 0) == 0 ? 1 : 2;
   if (home < c->modules.size()) {
     CUfunction f;
@@ -770,20 +781,33 @@ static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
   return true;
 }
 
-static unsigned gemm_smem_bytes(const GemmVariant& v) { return v.stages * (16384 + (v.block_n / v.cg) * 128) + 1024 + 256; }
+// mx_kind: 0 = unscaled, 1 = mxf8 (one 512-byte scale chunk per 128 rows per k-block), 2 = mxf4 (two)
+static unsigned gemm_sf_stage_bytes(const GemmVariant& v, int mx_kind) {
+  if (!mx_kind) return 0;
+  const unsigned raw = 512u * mx_kind * (1 + v.block_n / 128);
+  return (raw + 1023u) / 1024u * 1024u;
+}
+static unsigned gemm_smem_bytes(const GemmVariant& v, int mx_kind = 0) {
+  return v.stages * (16384 + (v.block_n / v.cg) * 128 + gemm_sf_stage_bytes(v, mx_kind)) + 1024 + 256;
+}
 
 static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, size_t esz, uint64_t base, uint64_t d0,
                        uint64_t d1, uint64_t d2, uint64_t s1_elems, uint64_t s2_elems, uint32_t b0, uint32_t b1,
-                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint32_t b2 = 1) {
   char key[256];
-  snprintf(key, sizeof(key), "%d|%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u", (int)dt, (int)swz, (unsigned long long)base,
+  snprintf(key, sizeof(key), "%d|%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u|%u", (int)dt, (int)swz, (unsigned long long)base,
            (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_elems,
-           (unsigned long long)s2_elems, b0, b1);
+           (unsigned long long)s2_elems, b0, b1, b2);
   if (c->dry) {
     char line[256];
-    snprintf(line, sizeof(line), "tmap esz=%zu dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u) swizzle=%d\n", esz,
-             (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)(s1_elems * esz),
-             (unsigned long long)(s2_elems * esz), b0, b1, (int)swz);
+    if (b2 == 1)
+      snprintf(line, sizeof(line), "tmap esz=%zu dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u) swizzle=%d\n", esz,
+               (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)(s1_elems * esz),
+               (unsigned long long)(s2_elems * esz), b0, b1, (int)swz);
+    else
+      snprintf(line, sizeof(line), "tmap esz=%zu dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u) swizzle=%d\n", esz,
+               (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)(s1_elems * esz),
+               (unsigned long long)(s2_elems * esz), b0, b1, b2, (int)swz);
     c->plan += line;
     memset(out, 0, sizeof(*out));
     return B200_OK;
@@ -792,7 +816,7 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
   if (it != c->tmap_cache.end()) { *out = it->second; return B200_OK; }
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {s1_elems * esz, s2_elems * esz};
-  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, dt, 3, reinterpret_cast<void*>(base), dims, strides, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
@@ -818,6 +842,11 @@ struct GemmProblem {
   uint64_t a_sm, a_sk, a_sb;
   uint64_t b_sk, b_sn, b_sb;
   uint64_t o_sm, o_sn, o_sb;
+  // block-scaled (MX) problems: in_dtype is a 1-byte marker, K / a_sm / b_sn count BYTES of K-major packed operands
+  int mx_kind = 0;                 // 0 unscaled, 1 mxf8 (e4m3 / e5m2), 2 mxf4 (packed e2m1)
+  uint32_t fmt_a = 0, fmt_b = 0;   // instruction-descriptor operand formats
+  uint64_t sfa = 0, sfb = 0;       // packed scale tensors [batch * tiles][atoms][512 B]
+  uint64_t sf_atoms = 0;           // 4-scale atoms along K
 };
 
 static int launch_simt(b200_ctx* c, CUstream st, const GemmProblem& g) {
@@ -857,7 +886,8 @@ static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out);
 
 static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
   const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
-  const char* in_tag = g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
+  const char* in_tag = g.mx_kind == 1 ? "mxf8" : g.mx_kind == 2 ? "mxf4"
+                       : g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
                        : g.in_dtype == B200_F8E5M2 ? "e5m2" : g.in_dtype == B200_U8 ? "u8" : g.in_dtype == B200_I8 ? "s8" : "tf32";
   const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : g.out_dtype == B200_I32 ? "i32" : "f32";
   const uint32_t block_k = static_cast<uint32_t>(128 / esz);
@@ -869,13 +899,16 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   for (const GemmVariant& v : kVariants) {
     if (forced != "auto" && forced != v.tag) continue;
     if (forced == "auto" && v.eff <= 0.0) continue;
-    if (!variant_has_dtype(v, g.in_dtype)) continue;
+    if (g.mx_kind ? !strcmp(v.tag, "2sm_n256s7") : !variant_has_dtype(v, g.in_dtype)) continue;
     if (forced == "auto" && v.cg == 2 && g.M <= 128) continue;  // a CTA pair would idle its second half: one CTA per tile
     const uint64_t tm = (g.M + 128 * v.cg - 1) / (128 * v.cg), tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
     const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
     const uint64_t waves = (tiles + clusters - 1) / clusters;
-    const double cost = static_cast<double>(waves) * (128.0 * v.block_n) / (v.eff > 0 ? v.eff : 1.0);  // per-SM MMA time per wave
+    double eff = v.eff > 0 ? v.eff : 1.0;
+    // scaled 256-wide tiles hold ONE accumulator in TMEM (512 columns - scale columns): the epilogue is not overlapped
+    if (g.mx_kind && v.block_n == 256) eff = 0.8;
+    const double cost = static_cast<double>(waves) * (128.0 * v.block_n) / eff;  // per-SM MMA time per wave
     if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; }
   }
   if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant for this dtype", forced.c_str());
@@ -885,7 +918,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;
-  const unsigned smem = gemm_smem_bytes(v);
+  const unsigned smem = gemm_smem_bytes(v, g.mx_kind);
   if (!c->dry) CU_CHECK(g_drv.cuFuncSetAttribute_p(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
 
   const CUtensorMapDataType dt = g.in_dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -930,6 +963,19 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  if (g.mx_kind) {
+    // packed scale tensors viewed as (16 B, 32 rows x atoms, 128-row tiles); one box = the chunks of one k-block
+    const uint64_t tiles_a = (g.M + 127) / 128, tiles_b = (g.N + 127) / 128;
+    const uint64_t ab = a_bcast ? 1 : g.batch, bb = b_bcast ? 1 : g.batch;
+    rc = encode_tmap(c, &ta_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfa, 16, 32 * g.sf_atoms, tiles_a * ab, 16, 512 * g.sf_atoms,
+                     16, 32 * g.mx_kind, CU_TENSOR_MAP_SWIZZLE_NONE, 1);
+    if (rc) return rc;
+    rc = encode_tmap(c, &tb_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfb, 16, 32 * g.sf_atoms, tiles_b * bb, 16, 512 * g.sf_atoms,
+                     16, 32 * g.mx_kind, CU_TENSOR_MAP_SWIZZLE_NONE, v.block_n / 128);
+    if (rc) return rc;
+    p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
+    p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
+  }
   p.k_segments = split ? 3 : 1;
   p.alpha = g.alpha; p.bias = g.bias; p.epi_act = g.act;
   p.epi_on = (g.alpha != 1.0f || g.bias != 0 || g.act != 0) ? 1u : 0u;
@@ -1118,6 +1164,87 @@ extern "C" int b200_matmul_fused(b200_ctx* c, b200_stream s, b200_dtype in_dtype
   if (in_dtype == B200_U8 || in_dtype == B200_I8) return fail(B200_ERR_UNSUPPORTED, "matmul_fused: integer accumulators have no float epilogue");
   return matmul_impl(c, s, in_dtype, out_dtype, lhs, rhs, out, rank, shape_lhs, strides_lhs, shape_rhs, strides_rhs, shape_out,
                      strides_out, ep);
+}
+
+// ------------------------------------------------------------------------------------------------ block-scaled matmul
+static int launch_pack_scales(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uint64_t batch, uint64_t rows,
+                              uint64_t n_scales, uint64_t tiles, uint64_t atoms) {
+  CUfunction f;
+  int rc = get_func(c, "pack_scales", &f);
+  if (rc) return rc;
+  PackScalesParams p{in, out, (uint32_t)batch, (uint32_t)rows, (uint32_t)n_scales, (uint32_t)tiles, (uint32_t)atoms, 0};
+  const uint64_t words = batch * tiles * atoms * 128;
+  const unsigned grid = (unsigned)std::min<uint64_t>((words + 255) / 256, (uint64_t)c->props.num_sms * 8);
+  void* args[] = {&p};
+  return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
+}
+
+extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dtype, b200_dtype rhs_dtype, b200_dtype out_dtype,
+                                  b200_dptr lhs, b200_dptr rhs, b200_dptr lhs_scales, b200_dptr rhs_scales, b200_dptr out,
+                                  uint64_t batch, uint64_t M, uint64_t N, uint64_t K, int scale_block, int scales_packed) {
+  CTX_ENTER(c);
+  const bool fp4 = (lhs_dtype == B200_F4E2M1X2);
+  auto is_fp8 = [](int d) { return d == B200_F8E4M3 || d == B200_F8E5M2; };
+  if (!(fp4 ? rhs_dtype == B200_F4E2M1X2 : (is_fp8(lhs_dtype) && is_fp8(rhs_dtype))))
+    return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: operands must be fp8 (e4m3/e5m2, mixable) or both packed e2m1");
+  if (out_dtype != B200_F32 && out_dtype != B200_BF16 && out_dtype != B200_F16)
+    return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: output must be f32, bf16 or f16");
+  if (scale_block != 32) return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: scale block %d (ue8m0 scales cover 32 elements of K)", scale_block);
+  if (K == 0 || K % 32) return fail(B200_ERR_INVALID_ARG, "matmul_scaled: K = %llu must be a positive multiple of the scale block", (unsigned long long)K);
+  if (batch == 0 || M == 0 || N == 0) return B200_OK;
+  if (!lhs || !rhs || !lhs_scales || !rhs_scales || !out) return fail(B200_ERR_INVALID_ARG, "matmul_scaled: null device pointer");
+  if (M >= (1ull << 31) || N >= (1ull << 31) || K >= (1ull << 31) || batch >= (1ull << 20)) return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: extent too large");
+  CUstream st = resolve_stream(c, s);
+  const uint64_t n_scales = K / 32, atoms = (n_scales + 3) / 4;
+  const uint64_t k_bytes = fp4 ? K / 2 : K;
+  const size_t osz = dtype_size(out_dtype);
+  const std::string forced = opt(c, "gemm.variant", "auto");
+  const bool tma = (lhs % 16 == 0 && rhs % 16 == 0 && k_bytes % 16 == 0 && (!scales_packed || (lhs_scales % 16 == 0 && rhs_scales % 16 == 0)));
+  if (forced == "simt" || !tma) {
+    if (scales_packed) return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: packed scales need 16-byte aligned operands and K rows");
+    if (forced != "simt" && forced != "auto")
+      return fail(B200_ERR_UNSUPPORTED, "gemm.variant=%s forced but operands are not TMA-describable", forced.c_str());
+    CUfunction f;
+    int rc = get_func(c, "gemm_scaled_simt", &f);
+    if (rc) return rc;
+    ScaledSimtParams p{lhs, rhs, lhs_scales, rhs_scales, out, (uint32_t)batch, (uint32_t)M, (uint32_t)N, (uint32_t)K,
+                       (uint32_t)lhs_dtype, (uint32_t)rhs_dtype, (uint32_t)out_dtype, 32u, 1u, 1u, 0u, 0u};
+    const uint64_t total = batch * M * N;
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->props.num_sms * 16);
+    void* args[] = {&p};
+    return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
+  }
+  // scales -> the tensor core's packed chunks (skipped when the caller already holds them in that form)
+  const uint64_t tiles_a = (M + 127) / 128, tiles_b = (N + 127) / 128;
+  CUdeviceptr sfa = lhs_scales, sfb = rhs_scales;
+  int rc = B200_OK;
+  if (!scales_packed) {
+    sfa = sfb = 0;
+    rc = pool_alloc(c, batch * tiles_a * atoms * 512, &sfa, st);
+    if (rc) return rc;
+    rc = pool_alloc(c, batch * tiles_b * atoms * 512, &sfb, st);
+    if (rc) { pool_free(c, sfa, st); return rc; }
+    rc = launch_pack_scales(c, st, lhs_scales, sfa, batch, M, n_scales, tiles_a, atoms);
+    if (!rc) rc = launch_pack_scales(c, st, rhs_scales, sfb, batch, N, n_scales, tiles_b, atoms);
+  }
+  if (!rc) {
+    GemmProblem g{};
+    g.in_dtype = B200_F8E4M3;  // 1-byte marker: the operands are described to TMA as bytes
+    g.out_dtype = out_dtype;
+    g.a = lhs; g.b = rhs; g.out = out;
+    g.M = M; g.N = N; g.K = k_bytes; g.batch = batch;
+    g.a_sm = k_bytes; g.a_sk = 1; g.a_sb = batch > 1 ? M * k_bytes : 0;
+    g.b_sn = k_bytes; g.b_sk = 1; g.b_sb = batch > 1 ? N * k_bytes : 0;
+    g.o_sm = N; g.o_sn = 1; g.o_sb = batch > 1 ? M * N : 0;
+    g.mx_kind = fp4 ? 2 : 1;
+    g.fmt_a = fp4 ? 1u : (lhs_dtype == B200_F8E5M2 ? 1u : 0u);
+    g.fmt_b = fp4 ? 1u : (rhs_dtype == B200_F8E5M2 ? 1u : 0u);
+    g.sfa = sfa; g.sfb = sfb; g.sf_atoms = atoms;
+    (void)osz;
+    rc = launch_tcgen05(c, st, g, false, false);
+  }
+  if (!scales_packed) { pool_free(c, sfa, st); pool_free(c, sfb, st); }
+  return rc;
 }
 
 static int matmul_impl(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,

@@ -38,9 +38,14 @@ struct GemmParams {
   uint32_t full_tiles, split_tiles, split_s, pad0;
   uint64_t split_ws;          // slabs: [split_tiles][split_s][CG] x (128 x BLOCK_N f32, thread-interleaved 16 B units)
   uint64_t split_tickets;     // u32 [split_tiles][CG], zero on entry, left zero on exit
+  // Block-scaled kinds (KIND_MXF8 / KIND_MXF4): operand formats for the instruction descriptor and the number of 128-row
+  // scale-factor tiles per batch entry of each operand (the packed scale tensors are [batch * tiles][k atoms][512 B]).
+  uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;
 };
 
-enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6 };
+enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6,
+             KIND_MXF8 = 7,    // kind::mxf8f6f4.block_scale: e4m3 / e5m2 operands (chosen at run time), ue8m0 scale per 32 K
+             KIND_MXF4 = 8 };  // kind::mxf4.block_scale: packed e2m1 operands (K counted in BYTES by this kernel), ue8m0 per 32 K
 enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };  // OUT_F32 is a raw 32-bit store: it also carries the s32 accumulators of kind::i8
 
 constexpr int kNumThreads = 256;  // warps 0 and 3 TMA producers, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
@@ -126,29 +131,47 @@ __device__ __forceinline__ WorkUnit unit_decode(uint32_t u, const GemmParams& p,
   return w;
 }
 
-template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES>
+// Block-scaled kinds reuse the whole pipeline.  Per k-block (128 bytes of K per row) the stage additionally carries the
+// scale factors of the tile rows in the hardware's packed form -- one 512-byte chunk per 128 rows x 4 consecutive scales:
+// byte (r % 32) * 16 + (r / 32) * 4 + s -- loaded by TMA from the pre-packed scale tensors (tma_a_lo / tma_b_lo slots),
+// copied smem -> TMEM by the MMA thread (tcgen05.cp 32x128b.warpx4: row group g of the chunk lands in column g, byte s of
+// the word is scale s) right before the four MMAs that consume them; tcgen05.cp and tcgen05.mma execute in issue order, so
+// one TMEM scale buffer suffices.  kind::mxf8f6f4: one chunk per k-block, MMA k uses byte k.  kind::mxf4: K = 64 elements
+// per MMA and two scales per row per MMA -> two chunks per k-block, MMA k uses chunk k / 2, bytes 2 (k % 2) and +1.
+// ACC = accumulator stages in TMEM: 256-wide scaled tiles have room for one only (512 columns - scale columns).
+template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES, int ACC = 2>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUtensorMap* tma_b_hi, const CUtensorMap* tma_a_lo,
                                           const CUtensorMap* tma_b_lo, const GemmParams& p) {
+  constexpr bool SCALED = (KIND >= KIND_MXF8);
+  constexpr bool INT_ACC = (KIND == KIND_U8 || KIND == KIND_S8);
+  static_assert(!SCALED || (!A_MN && !B_MN && BLOCK_N % 128 == 0), "block-scaled kinds: K-major operands, 128-row scale tiles");
+  constexpr int SF_ATOMS = !SCALED ? 0 : (KIND == KIND_MXF4) ? 2 : 1;  // 512-byte scale chunks per 128 rows per k-block
+  constexpr int SF_TILES_B = BLOCK_N / 128;
+  constexpr uint32_t SFA_BYTES = 512u * SF_ATOMS, SFB_BYTES = 512u * SF_ATOMS * SF_TILES_B;
+  constexpr uint32_t SF_BYTES = (SFA_BYTES + SFB_BYTES + 1023u) / 1024u * 1024u;
+  constexpr uint32_t SF_COLS = 4u * SF_ATOMS * (1 + SF_TILES_B);
   constexpr int ESZ = (KIND == KIND_TF32) ? 4 : (KIND >= KIND_E4M3) ? 1 : 2;
   // operand format field of the instruction descriptor (meaning depends on the MMA kind)
   constexpr uint32_t FMT = (KIND == KIND_E4M3 || KIND == KIND_U8) ? 0u : (KIND == KIND_E5M2 || KIND == KIND_S8) ? 1u : static_cast<uint32_t>(KIND);
-  constexpr uint32_t C_FMT = (KIND >= KIND_U8) ? 2u : 1u;  // s32 accumulators for integer inputs, f32 otherwise
+  constexpr uint32_t C_FMT = INT_ACC ? 2u : 1u;  // s32 accumulators for integer inputs, f32 otherwise
   constexpr int BLOCK_K = 128 / ESZ;  // one 128-byte swizzle row of K per stage
   constexpr int UMMA_K = 32 / ESZ;
   constexpr int UMMA_M = 128 * CG;
   constexpr int N_LOCAL = BLOCK_N / CG;  // rows of the B tile this CTA stages
   constexpr uint32_t A_BYTES = 128 * 128;
   constexpr uint32_t B_BYTES = N_LOCAL * 128;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + SF_BYTES;
+  constexpr uint32_t STAGE_TX = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;  // bytes one CTA's copies deliver per stage
   constexpr int CHUNK_N = 128 / ESZ;                 // MN-major operand: M/N elements per 128-byte row
   constexpr uint32_t CHUNK_BYTES = BLOCK_K * 128;    // MN-major operand: one [BLOCK_K x 128 B] chunk
   constexpr int NUM_CHUNKS = N_LOCAL / CHUNK_N;      // B chunks per CTA
   constexpr int NUM_CHUNKS_A = 128 / CHUNK_N;        // A chunks per CTA (128 rows of M)
-  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
-                               : (2 * BLOCK_N <= 256) ? 256 : 512;
-  static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+  constexpr uint32_t ACC_COLS = ACC * BLOCK_N, TMEM_NEED = ACC_COLS + SF_COLS;
+  constexpr uint32_t TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 : (TMEM_NEED <= 128) ? 128 : (TMEM_NEED <= 256) ? 256 : 512;
+  static_assert(TMEM_NEED <= 512, "accumulator stages + scale factors must fit TMEM");
+  constexpr uint32_t SFA_COL = ACC_COLS, SFB_COL = ACC_COLS + 4u * SF_ATOMS;
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024-byte alignment for SWIZZLE_128B");
-  constexpr uint32_t IDESC = make_idesc(FMT, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N, C_FMT);
+  constexpr uint32_t IDESC = make_idesc(FMT, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N, C_FMT);  // unscaled kinds
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -170,7 +193,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tma_a_hi);
     tma_prefetch_desc(tma_b_hi);
-    if (p.k_segments > 1) { tma_prefetch_desc(tma_a_lo); tma_prefetch_desc(tma_b_lo); }
+    if (p.k_segments > 1 || SCALED) { tma_prefetch_desc(tma_a_lo); tma_prefetch_desc(tma_b_lo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -228,7 +251,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           const uint32_t sb = sa + A_BYTES;
           const uint32_t fb = (CG == 2) ? leader_full0 + 8u * s : full_bar(s);
           const int k0 = static_cast<int>(kk * BLOCK_K);
-          if (who == 0 && leader) mbar_arrive_expect_tx(full_bar(s), CG * STAGE_BYTES);
+          if (who == 0 && leader) mbar_arrive_expect_tx(full_bar(s), CG * STAGE_TX);
           const CUtensorMap* tma_a = (seg == 2) ? tma_a_lo : tma_a_hi;
           const CUtensorMap* tma_b = (seg == 1) ? tma_b_lo : tma_b_hi;
 #pragma unroll
@@ -243,6 +266,20 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
               const uint32_t dst = B_MN ? sb + c * CHUNK_BYTES : sb;
               const int c0 = B_MN ? n0 + c * CHUNK_N : k0, c1 = B_MN ? k0 : n0;
               if constexpr (CG == 1) tma_load_3d(dst, tma_b, fb, c0, c1, bb); else tma_load_3d_2sm(dst, tma_b, fb, c0, c1, bb);
+            }
+          }
+          if constexpr (SCALED) {
+            // scale chunks of this k-block: A rows of this CTA (one 128-row tile), B rows of the whole BLOCK_N (the MMA of
+            // each CTA of a pair needs the scales of all N columns); box = (16 B, 32 * SF_ATOMS rows, tiles)
+            const int sf_row = static_cast<int>(kk * SF_ATOMS * 32);
+            if (who == 0) {
+              const int tile = static_cast<int>(tc.b * p.a_bmul * p.sf_tiles_a + tc.m_blk * CG + rank);
+              if constexpr (CG == 1) tma_load_3d(sb + B_BYTES, tma_a_lo, fb, 0, sf_row, tile);
+              else tma_load_3d_2sm(sb + B_BYTES, tma_a_lo, fb, 0, sf_row, tile);
+            } else {
+              const int tile = static_cast<int>(tc.b * p.b_bmul * p.sf_tiles_b + tc.n_blk * SF_TILES_B);
+              if constexpr (CG == 1) tma_load_3d(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, sf_row, tile);
+              else tma_load_3d_2sm(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, sf_row, tile);
             }
           }
           if (++kk == seg_kb) { kk = 0; ++seg; }
@@ -274,17 +311,40 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           };
           const uint64_t a_desc = A_MN ? mn_desc(sa) : make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t b_desc = B_MN ? mn_desc(sb) : make_smem_desc_sw128(sb, 16, 1024);
+          if constexpr (SCALED) {
+            const uint32_t sfa_s = sb + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
+            // unswizzled 32 x 16 B chunk: 8-row groups 128 B apart (SBO); a single 16-byte column, so no LBO
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
-            const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
-            umma_ss<CG, KIND>(d_tmem, a_k, b_k, IDESC, (kb != wu.kb0 || k != 0) ? 1u : 0u);
+            for (int atom = 0; atom < SF_ATOMS; ++atom)
+              tmem_cp_32x128b_warpx4<CG>(tmem_base + SFA_COL + 4u * atom, make_smem_desc(sfa_s + 512u * atom, 0, 128, 0));
+#pragma unroll
+            for (int tile = 0; tile < SF_TILES_B; ++tile)
+#pragma unroll
+              for (int atom = 0; atom < SF_ATOMS; ++atom)
+                tmem_cp_32x128b_warpx4<CG>(tmem_base + SFB_COL + 4u * (atom * SF_TILES_B + tile),
+                                           make_smem_desc(sfb_s + 512u * (tile * SF_ATOMS + atom), 0, 128, 0));
+            const uint32_t idesc_base = make_idesc_scaled(p.sf_fmt_a, p.sf_fmt_b, UMMA_M, BLOCK_N);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t atom = (KIND == KIND_MXF4) ? k / 2 : 0;
+              const uint32_t sf_id = (KIND == KIND_MXF4) ? (k & 1) * 2 : k;
+              umma_ss_scaled<CG, (KIND == KIND_MXF4) ? 1 : 0>(d_tmem, a_desc + 2 * k, b_desc + 2 * k,
+                                                              idesc_base | (sf_id << 29) | (sf_id << 4), tmem_base + SFA_COL + 4u * atom,
+                                                              tmem_base + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
+              const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
+              umma_ss<CG, (SCALED ? KIND_E4M3 : KIND)>(d_tmem, a_k, b_k, IDESC, (kb != wu.kb0 || k != 0) ? 1u : 0u);
+            }
           }
           umma_commit<CG>(empty_bar(s));  // smem slot reusable once these MMAs retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit<CG>(tfull_bar(as));  // accumulator complete -> epilogue
-        if (++as == 2) { as = 0; aph ^= 1; }
+        if (++as == ACC) { as = 0; aph ^= 1; }
       }
     }
     __syncwarp();
@@ -296,7 +356,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     uint32_t as = 0, aph = 0;
     // out = act(alpha * acc + bias[n]) on 32 accumulator columns held by this thread (float kinds only)
     auto fused_epilogue = [&](uint32_t (&v)[32], uint32_t n0) {
-      if (KIND < KIND_U8 && p.epi_on) {
+      if (!INT_ACC && p.epi_on) {
         const float* bias = reinterpret_cast<const float*>(p.bias);  // warp-uniform loads
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -351,7 +411,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
       }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == ACC) { as = 0; aph ^= 1; }
       if (wu.partial) {
         // publish the slab, take a ticket for (tile, CTA rank); the last of the split_s slices reduces in slice order
         const uint32_t tail = wu.tile - p.full_tiles;
@@ -422,13 +482,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 // Dynamic shared memory a variant needs (host mirrors this in capi.cpp: gemm_smem_bytes()).
 //   STAGES * (16384 + (BLOCK_N/CG)*128) + 1024 (alignment slack) + 256 (barriers)
 
-#define GEMM_KERNEL(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES)                                                   \
+#define GEMM_KERNEL_ACC(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC)                                          \
   extern "C" __global__ void __launch_bounds__(kNumThreads, 1)                                                   \
       NAME(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,                 \
            const __grid_constant__ CUtensorMap tma_a_lo, const __grid_constant__ CUtensorMap tma_b_lo,           \
            const __grid_constant__ GemmParams p) {                                                               \
-    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES>(&tma_a, &tma_b, &tma_a_lo, &tma_b_lo, p);                     \
+    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC>(&tma_a, &tma_b, &tma_a_lo, &tma_b_lo, p);                \
   }
+#define GEMM_KERNEL(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES) GEMM_KERNEL_ACC(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, 2)
 
 // name: gemm_<in>_<out>_<cg>sm_n<BLOCK_N>_<a><b>
 //   a: k = lhs stored [M,K] row-major (K-major), m = lhs stored [K,M] (transposed view, M contiguous)
@@ -466,6 +527,19 @@ GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
 GEMM_DTYPES(1sm_n128, 1, 128, 6)
 GEMM_FP8(1sm_n128, 1, 128, 6)
+
+// Block-scaled (MX) kinds: K-major operands only (lhs [M,K], rhs [N,K]); stage = operands + scale chunks.
+//   gemm_mxf8_<out>_<tile>_kk: e4m3 / e5m2 (either per operand), gemm_mxf4_<out>_<tile>_kk: packed e2m1
+#define GEMM_MX(TILE, CG, BN, STAGES, ACC)                                                       \
+  GEMM_KERNEL_ACC(gemm_mxf8_f32_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_F32, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_mxf8_bf16_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_BF16, STAGES, ACC) \
+  GEMM_KERNEL_ACC(gemm_mxf8_f16_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_F16, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_mxf4_f32_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F32, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_mxf4_bf16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_BF16, STAGES, ACC) \
+  GEMM_KERNEL_ACC(gemm_mxf4_f16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F16, STAGES, ACC)
+GEMM_MX(2sm_n256, 2, 256, 6, 1)  // 512 TMEM columns: one 256-wide accumulator + 24 scale columns (no epilogue overlap)
+GEMM_MX(2sm_n128, 2, 128, 8, 2)
+GEMM_MX(1sm_n128, 1, 128, 6, 2)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/

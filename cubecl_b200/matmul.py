@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
+
 from . import _ffi
 from ._ffi import B200Error
 from .client import ComputeClient, DTYPES, TensorHandle
@@ -82,6 +84,41 @@ def _launch_fused(client, lhs, rhs, out, stream, alpha, bias, activation) -> Non
             C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(out.handle.ptr), rank,
             _ffi.u64_array(lhs.shape), _ffi.u64_array(lhs.strides), _ffi.u64_array(rhs.shape), _ffi.u64_array(rhs.strides),
             _ffi.u64_array(out.shape), _ffi.u64_array(out.strides), C.byref(ep)))
+    except B200Error as e:
+        client._defer(e)
+
+
+def launch_scaled(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, lhs_scales: TensorHandle, rhs_scales: TensorHandle,
+                  out: TensorHandle, stream=None, scale_block: int = 32, scales_packed: bool = False) -> None:
+    """Block-scaled (MX) matmul -- the GEMM-level form of MmaDefinition::new_scaled / execute_scaled (frontend/cmma.rs:438-460,
+    798-840) with the operand layout of test_cmma_scaled (runtime_tests/cmma.rs:1476-1593):
+      lhs [.., M, K] and rhs [.., N, K], both K-contiguous, dtype f8e4m3 / f8e5m2 (mixable) or both f4e2m1x2 (shape [.., rows, K/2]
+      bytes); scales ue8m0 [.., rows, K/32]; out [.., M, N] = sum_k (lhs * lhs_scale) * (rhs * rhs_scale), f32 accumulate.
+    Errors are deferred to client.sync() like every launch."""
+    try:
+        fp4 = lhs.dtype == "f4e2m1x2"
+        for t in (lhs, rhs, lhs_scales, rhs_scales, out):
+            if not t.is_contiguous():
+                raise B200Error(6, "matmul_scaled: tensors must be contiguous (K-major operands)")
+        if len(lhs.shape) < 2 or len(lhs.shape) != len(rhs.shape) or lhs.shape[:-2] != rhs.shape[:-2]:
+            raise B200Error(6, "matmul_scaled: lhs [..,M,K] and rhs [..,N,K] need equal batch dims")
+        if lhs.shape[-1] != rhs.shape[-1]:
+            raise B200Error(6, "matmul_scaled: K mismatch")
+        M, N = lhs.shape[-2], rhs.shape[-2]
+        K = lhs.shape[-1] * (2 if fp4 else 1)
+        batch = int(np.prod(lhs.shape[:-2])) if len(lhs.shape) > 2 else 1
+        if K % scale_block:
+            raise B200Error(6, "matmul_scaled: K must be a multiple of the scale block")
+        if list(out.shape) != list(lhs.shape[:-2]) + [M, N]:
+            raise B200Error(6, f"matmul_scaled: out shape {out.shape} != {list(lhs.shape[:-2]) + [M, N]}")
+        if not scales_packed:
+            for t, rows in ((lhs_scales, M), (rhs_scales, N)):
+                if list(t.shape) != list(lhs.shape[:-2]) + [rows, K // scale_block] or t.dtype != "ue8m0":
+                    raise B200Error(6, "matmul_scaled: scales must be ue8m0 [.., rows, K / scale_block]")
+        _ffi.check(client._lib.b200_matmul_scaled(
+            client._ctx, stream, DTYPES[lhs.dtype], DTYPES[rhs.dtype], DTYPES[out.dtype],
+            C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(lhs_scales.handle.ptr),
+            C.c_uint64(rhs_scales.handle.ptr), C.c_uint64(out.handle.ptr), batch, M, N, K, int(scale_block), int(bool(scales_packed))))
     except B200Error as e:
         client._defer(e)
 

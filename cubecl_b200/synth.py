@@ -88,6 +88,60 @@ def f32_to_fp8_bits(x: np.ndarray, kind: str) -> np.ndarray:
     return (code | sign).astype(np.uint8)
 
 
+# ---- MX formats (block-scaled matmul): e2m1 (fp4) packed two per byte, ue8m0 scales
+E2M1_VALUES = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0], dtype=np.float32)   # magnitude of code & 7; bit 3 = sign
+
+
+def e2m1_codes_to_f32(codes: np.ndarray) -> np.ndarray:
+    codes = np.asarray(codes, dtype=np.uint8)
+    v = E2M1_VALUES[codes & 7]
+    return np.where(codes & 8, -v, v).astype(np.float32)
+
+
+def f32_to_e2m1_codes(x: np.ndarray) -> np.ndarray:
+    """Round to nearest (ties to the even code), saturating at +-6."""
+    xf = np.ascontiguousarray(x, dtype=np.float32)
+    a = np.minimum(np.abs(xf.astype(np.float64)), 6.0)
+    hi = np.clip(np.searchsorted(E2M1_VALUES.astype(np.float64), a, side="left"), 0, 7)
+    lo = np.clip(hi - 1, 0, 7)
+    d_lo, d_hi = np.abs(a - E2M1_VALUES[lo]), np.abs(E2M1_VALUES[hi] - a)
+    code = np.where((d_hi < d_lo) | ((d_hi == d_lo) & (hi % 2 == 0)), hi, lo)
+    return (code | (np.signbit(xf).astype(np.int64) << 3)).astype(np.uint8)
+
+
+def pack_e2m1x2(codes: np.ndarray) -> np.ndarray:
+    """[.., K] 4-bit codes -> [.., K/2] bytes, element 2i in the low nibble (e2m1x2::from_f32_slice, cubecl-common/src/float/fp4.rs:204-216)."""
+    codes = np.asarray(codes, dtype=np.uint8)
+    assert codes.shape[-1] % 2 == 0
+    return (codes[..., 0::2] & 0xF) | ((codes[..., 1::2] & 0xF) << 4)
+
+
+def unpack_e2m1x2(packed: np.ndarray) -> np.ndarray:
+    packed = np.asarray(packed, dtype=np.uint8)
+    out = np.empty(packed.shape[:-1] + (packed.shape[-1] * 2,), dtype=np.uint8)
+    out[..., 0::2] = packed & 0xF
+    out[..., 1::2] = packed >> 4
+    return out
+
+
+def ue8m0_to_f32(bits: np.ndarray) -> np.ndarray:
+    """2^(bits - 127); 255 is NaN (ue8m0, cubecl-common float module)."""
+    b = np.asarray(bits, dtype=np.uint8).astype(np.int64)
+    return np.where(b == 255, np.nan, np.ldexp(1.0, b - 127)).astype(np.float32)
+
+
+def pack_scale_chunks(scales: np.ndarray) -> np.ndarray:
+    """[rows, n_scales] ue8m0 -> the tensor core's packed chunks [ceil(rows/128)][ceil(n_scales/4)][512]:
+    byte (r % 32) * 16 + (r / 32) * 4 + s; padding = 127 (1.0).  Host mirror of the pack_scales kernel."""
+    scales = np.asarray(scales, dtype=np.uint8)
+    rows, ns = scales.shape
+    tiles, atoms = (rows + 127) // 128, (ns + 3) // 4
+    padded = np.full((tiles * 128, atoms * 4), 127, dtype=np.uint8)
+    padded[:rows, :ns] = scales
+    v = padded.reshape(tiles, 4, 32, atoms, 4)          # [tile][g = r/32][r%32][atom][s]
+    return np.ascontiguousarray(v.transpose(0, 3, 2, 1, 4)).reshape(tiles, atoms, 512)   # [tile][atom][r%32][g][s]
+
+
 def to_device_dtype(x_f32: np.ndarray, dtype: str) -> np.ndarray:
     """f32 values -> array in the device representation of `dtype` (bf16 as uint16 bits)."""
     if dtype == "f32":

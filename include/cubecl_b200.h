@@ -52,7 +52,9 @@ typedef enum b200_status {
 typedef enum b200_dtype {
   B200_F32 = 0, B200_F16 = 1, B200_BF16 = 2, B200_U32 = 3, B200_I32 = 4, B200_F64 = 5, B200_I64 = 6, B200_U64 = 7,
   B200_U8 = 8, B200_I8 = 9,
-  B200_F8E4M3 = 10, B200_F8E5M2 = 11   /* fp8 matmul inputs (FloatKind::E4M3 / E5M2; manual-MMA dtypes of cuda/mma/manual.rs:108-186) */
+  B200_F8E4M3 = 10, B200_F8E5M2 = 11,  /* fp8 matmul inputs (FloatKind::E4M3 / E5M2; manual-MMA dtypes of cuda/mma/manual.rs:108-186) */
+  B200_F4E2M1X2 = 12,                  /* two e2m1 per byte, element 2i in the low nibble (e2m1x2, cubecl-common/src/float/fp4.rs:28,204-216) */
+  B200_UE8M0 = 13                      /* block scale 2^(bits-127) (FloatKind::UE8M0; scales_type of ScaledMmaConfig) */
 } b200_dtype;
 
 /* Reduction instructions of the `reduce::launch` surface (cubek); in-tree semantics: examples/sum_things/src/lib.rs:6-33,
@@ -151,6 +153,20 @@ int b200_matmul_fused(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dt
                       const uint64_t* shape_lhs, const uint64_t* strides_lhs,
                       const uint64_t* shape_rhs, const uint64_t* strides_rhs,
                       const uint64_t* shape_out, const uint64_t* strides_out, const b200_epilogue* epilogue);
+
+/* Block-scaled (MX) matmul: out[b,m,n] = sum_k (lhs[b,m,k] * lhs_scales[b,m,k/32]) * (rhs[b,n,k] * rhs_scales[b,n,k/32]),
+ * f32 accumulation.  Replaces MmaDefinition::new_scaled / execute_scaled (crates/cubecl-core/src/frontend/cmma.rs:438-460,
+ * 798-840), the ScaledMmaConfig feature rows (crates/cubecl-ir/src/features.rs:190-211; on CUDA the reference offers them
+ * for sm_120 only, cubecl-cpp/src/cuda/mma/manual.rs:201-255 -- sm_100 needs tcgen05 kind::mxf8f6f4 / kind::mxf4) and is
+ * pinned by test_cmma_scaled / test_cmma_scaled_fp4 (crates/cubecl-core/src/runtime_tests/cmma.rs:1476-1700).
+ * Layouts follow those tests: lhs [batch, m, k] and rhs [batch, n, k] K-contiguous ("col-major" rhs), dtypes B200_F8E4M3 /
+ * B200_F8E5M2 (mixable) or both B200_F4E2M1X2 (k / 2 bytes per row); scales are B200_UE8M0 bytes [batch, rows, k / 32]
+ * row-major (scales_packed = 0) or already in the tensor core's packed form [batch * ceil(rows/128)][ceil(k/128)][512 B],
+ * byte (r % 32) * 16 + (r / 32) * 4 + s (scales_packed = 1).  out [batch, m, n] contiguous, f32 / bf16 / f16.
+ * scale_block must be 32 and k a multiple of it.  Operands that TMA cannot describe take the reference-order SIMT path. */
+int b200_matmul_scaled(b200_ctx* ctx, b200_stream stream, b200_dtype lhs_dtype, b200_dtype rhs_dtype, b200_dtype out_dtype,
+                       b200_dptr lhs, b200_dptr rhs, b200_dptr lhs_scales, b200_dptr rhs_scales, b200_dptr out,
+                       uint64_t batch, uint64_t m, uint64_t n, uint64_t k, int scale_block, int scales_packed);
 
 /* ---- reduce::launch (cubek) -----------------------------------------------------------------------------------------
  * Reduces `axis` (0..rank-1) of a CONTIGUOUS row-major input, or every element when axis == -1.  Output is contiguous

@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.oracle_matmul_f64.argtypes = [_f32p, _f32p, _f64p, C.c_void_p] + [C.c_uint64] * 7
         L.oracle_matmul_points_f64.restype = None
         L.oracle_matmul_points_f64.argtypes = [_f32p, _f32p, _u64p, _u64p, C.c_uint64, _f64p, _f64p] + [C.c_uint64] * 5
+        L.oracle_matmul_scaled.restype = None
+        L.oracle_matmul_scaled.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, _f64p, _f64p] + [C.c_uint64] * 4
         L.oracle_num_threads.restype = C.c_int
         L.oracle_sum_blocked_f32.restype = C.c_float
         L.oracle_sum_blocked_f32.argtypes = [_f32p, C.c_size_t, C.c_int]
@@ -178,6 +180,20 @@ def matmul_f64(lhs, rhs):
     oabs = np.empty((M, N), dtype=np.float64)
     lib().oracle_matmul_f64(a.ravel(), b.ravel(), out.ravel(), oabs.ctypes.data_as(C.c_void_p), M, N, K, K, 1, N, 1)
     return out, oabs
+
+
+def matmul_scaled(lhs, rhs_nk, lhs_scales, rhs_scales, block=32):
+    """Block-scaled matmul in the reference's own order (test_cmma_scaled's expected loop, cmma.rs:1572-1590).
+    lhs [M,K], rhs_nk [N,K], scales widened to f32 [rows, K/block].  Returns (f32 reference order, f64 truth, sum|terms|)."""
+    a, b, sa, sb = _c32(lhs), _c32(rhs_nk), _c32(lhs_scales), _c32(rhs_scales)
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and K % block == 0 and sa.shape == (M, K // block) and sb.shape == (N, K // block)
+    o32 = np.empty((M, N), dtype=np.float32)
+    o64 = np.empty((M, N), dtype=np.float64)
+    oabs = np.empty((M, N), dtype=np.float64)
+    lib().oracle_matmul_scaled(a.ravel(), b.ravel(), sa.ravel(), sb.ravel(), o32.ravel(), o64.ravel(), oabs.ravel(), M, N, K, block)
+    return o32, o64, oabs
 
 
 def matmul_points_f64(lhs, rhs, ms, ns):

@@ -172,6 +172,39 @@ void oracle_matmul_points_f64(const float* lhs, const float* rhs, const uint64_t
   }
 }
 
+/* Block-scaled matmul, reference semantics: the expected-value loop of test_cmma_scaled / test_cmma_scaled_fp4
+ * (crates/cubecl-core/src/runtime_tests/cmma.rs:1572-1590, 1688-1706):
+ *   sum += lhs_val * lhs_scale * rhs_val * rhs_scale, l increasing, l_scales = l / (k / scales_factor), f32 throughout
+ * (Rust evaluates a * b * c * d left to right).  lhs [M,K], rhs [N,K] (the test's col-major rhs), scales already widened
+ * to f32: lhs_scales [M, K/block], rhs_scales [N, K/block].  out_f32 = reference order; out_f64 / out_abs = ground truth
+ * and its tolerance scale sum |terms| (either may be NULL). */
+void oracle_matmul_scaled(const float* lhs, const float* rhs, const float* lhs_scales, const float* rhs_scales, float* out_f32,
+                          double* out_f64, double* out_abs, uint64_t M, uint64_t N, uint64_t K, uint64_t block) {
+  const uint64_t ns = K / block;
+#pragma omp parallel for schedule(static)
+  for (int64_t mi = 0; mi < (int64_t)M; ++mi) {
+    const uint64_t m = (uint64_t)mi;
+    for (uint64_t n = 0; n < N; ++n) {
+      float sum = 0.0f;
+      double d = 0.0, dabs = 0.0;
+      for (uint64_t l = 0; l < K; ++l) {
+        const uint64_t ls = l / block;
+        const float lv = lhs[m * K + l], lsc = lhs_scales[m * ns + ls], rv = rhs[n * K + l], rsc = rhs_scales[n * ns + ls];
+        float t = lv * lsc;
+        t = t * rv;
+        t = t * rsc;
+        sum += t;
+        const double td = (double)lv * (double)lsc * (double)rv * (double)rsc;
+        d += td;
+        dabs += td < 0 ? -td : td;
+      }
+      if (out_f32) out_f32[m * N + n] = sum;
+      if (out_f64) out_f64[m * N + n] = d;
+      if (out_abs) out_abs[m * N + n] = dabs;
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------ CPU baseline legs
  * "cubecl-cpu execution model": one worker per core, each owning a contiguous slice (crates/cubecl-cpu/src/runtime.rs:
  * 95-121, compute/threadpool/mod.rs:86-107).  Used by bench.py's cpu_baseline / --impl reference; reference-order

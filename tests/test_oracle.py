@@ -182,3 +182,66 @@ def test_fp8_codecs_match_torch():
         t = torch.from_numpy(x).clamp(-torch.finfo(tdt).max, torch.finfo(tdt).max).to(tdt)
         assert np.array_equal(synth.f32_to_fp8_bits(x, kind), t.view(torch.uint8).numpy())
         assert np.array_equal(synth.fp8_bits_to_f32(t.view(torch.uint8).numpy(), kind), t.float().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ block-scaled matmul
+def _reference_scaled_expected(m, n, k, factor, lhs_val, rhs_val, lhs_scale_bits, rhs_scale_bits):
+    """Literal restatement (pure Python, f32 at every step) of the expected-value loop of test_cmma_scaled /
+    test_cmma_scaled_fp4: crates/cubecl-core/src/runtime_tests/cmma.rs:1572-1590, 1688-1706."""
+    f = np.float32
+    out = np.zeros((m, n), dtype=np.float32)
+    for i in range(m):
+        for j in range(n):
+            acc = f(0.0)
+            for l in range(k):
+                ls = l // (k // factor)
+                sl = f(synth.ue8m0_to_f32(np.uint8(lhs_scale_bits(i, ls))))
+                sr = f(synth.ue8m0_to_f32(np.uint8(rhs_scale_bits(ls, j))))
+                acc = f(acc + f(f(f(f(lhs_val(i, l)) * sl) * f(rhs_val(l, j))) * sr))
+            out[i, j] = acc
+    return out
+
+
+def test_scaled_oracle_matches_the_reference_expected_loop_fp8():
+    # generators of test_cmma_scaled (cmma.rs:1518-1533): lhs = 2i + j, rhs = 3i + j (col-major), scales 120 + ...
+    m, n, k, factor = 16, 8, 32, 1
+    exp = _reference_scaled_expected(m, n, k, factor, lambda i, l: i * 2 + l, lambda l, j: l * 3 + j,
+                                     lambda i, s: i * 2 + s + 120, lambda s, j: s * 3 + j + 120)
+    lhs = np.array([[i * 2 + l for l in range(k)] for i in range(m)], dtype=np.float32)
+    rhs_nk = np.array([[l * 3 + j for l in range(k)] for j in range(n)], dtype=np.float32)
+    sa = synth.ue8m0_to_f32(np.array([[i * 2 + s + 120 for s in range(factor)] for i in range(m)], dtype=np.uint8))
+    sb = synth.ue8m0_to_f32(np.array([[s * 3 + j + 120 for s in range(factor)] for j in range(n)], dtype=np.uint8))
+    o32, o64, oabs = oracle.matmul_scaled(lhs, rhs_nk, sa, sb, 32)
+    assert np.array_equal(o32, exp)
+    assert np.max(np.abs(o32 - o64) / oabs) < 1e-6
+
+
+def test_scaled_oracle_matches_the_reference_expected_loop_fp4():
+    # test_cmma_scaled_fp4 (cmma.rs:1621-1640): e2m1 codes ((i + j) % 15) + 1, two scales per row (k = 64, factor 2)
+    m, n, k, factor = 16, 8, 64, 2
+    val = lambda a, b: float(synth.e2m1_codes_to_f32(np.uint8(((a + b) % 15) + 1)))
+    exp = _reference_scaled_expected(m, n, k, factor, val, val, lambda i, s: i * 2 + s + 120, lambda s, j: s * 3 + j + 120)
+    lhs = np.array([[val(i, l) for l in range(k)] for i in range(m)], dtype=np.float32)
+    rhs_nk = np.array([[val(l, j) for l in range(k)] for j in range(n)], dtype=np.float32)
+    sa = synth.ue8m0_to_f32(np.array([[i * 2 + s + 120 for s in range(factor)] for i in range(m)], dtype=np.uint8))
+    sb = synth.ue8m0_to_f32(np.array([[s * 3 + j + 120 for s in range(factor)] for j in range(n)], dtype=np.uint8))
+    o32, _, _ = oracle.matmul_scaled(lhs, rhs_nk, sa, sb, 32)
+    assert np.array_equal(o32, exp)
+
+
+def test_mx_codecs():
+    codes = np.arange(16, dtype=np.uint8)
+    vals = synth.e2m1_codes_to_f32(codes)
+    assert list(vals[:8]) == [0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0] and np.array_equal(vals[8:], -vals[:8])
+    assert np.array_equal(synth.f32_to_e2m1_codes(vals)[1:8], codes[1:8]) and np.array_equal(synth.f32_to_e2m1_codes(vals)[9:], codes[9:])
+    assert list(synth.f32_to_e2m1_codes(np.array([0.25, 0.75, 1.25, 2.5, 5.0, 7.0, -100.0], dtype=np.float32))) == [0, 2, 2, 4, 6, 7, 15]
+    packed = synth.pack_e2m1x2(np.array([[1, 2, 3, 15]], dtype=np.uint8))
+    assert packed.tolist() == [[0x21, 0xF3]] and synth.unpack_e2m1x2(packed).tolist() == [[1, 2, 3, 15]]   # even element -> low nibble
+    assert synth.ue8m0_to_f32(np.array([127, 128, 120, 0], dtype=np.uint8)).tolist() == [1.0, 2.0, 2.0 ** -7, 2.0 ** -127]
+    assert np.isnan(synth.ue8m0_to_f32(np.array([255], dtype=np.uint8))[0])
+    sc = (np.arange(300 * 9) % 251).astype(np.uint8).reshape(300, 9)
+    pk = synth.pack_scale_chunks(sc)
+    assert pk.shape == (3, 3, 512)
+    for r, s_ in ((0, 0), (31, 3), (32, 4), (200, 6), (299, 8)):
+        assert pk[r // 128, s_ // 4, (r % 32) * 16 + ((r % 128) // 32) * 4 + (s_ % 4)] == sc[r, s_]
+    assert pk[2, 2, (299 % 32) * 16 + ((299 % 128) // 32) * 4 + 1] == 127 and pk[2, 0, 31 * 16 + 3 * 4] == 127   # padding = 1.0

@@ -34,6 +34,10 @@ class Planner:
                                   _ffi.u64_array(rs), _ffi.u64_array(rst), _ffi.u64_array(os_), _ffi.u64_array(ost))
         return rc, self.text()
 
+    def matmul_scaled(self, ldt, rdt, odt, batch, m, n, k, block=32, packed=0, a=A, b=B, o=O, sa=0x40000000, sb=0x50000000):
+        rc = self.lib.b200_matmul_scaled(self.ctx, None, ldt, rdt, odt, a, b, sa, sb, o, batch, m, n, k, block, packed)
+        return rc, self.text()
+
     def reduce(self, op, dt, shape, axis, strides=None):
         rc = self.lib.b200_reduce_strided(self.ctx, None, op, dt, A, O, len(shape), _ffi.u64_array(shape),
                                           _ffi.u64_array(strides) if strides else None, axis)
@@ -117,6 +121,41 @@ def test_tail_split_policy(plan):
     plan.option("gemm.split_k", "9")
     rc, t = mm(4096, 4096)
     assert rc != 0
+
+
+def test_block_scaled_plans(plan):
+    """b200_matmul_scaled: scale packing passes, scale-chunk tensor maps, tile choice, fallbacks, validation."""
+    E5M2, FP4 = _ffi.F8E5M2, _ffi.F4E2M1X2
+    rc, t = plan.matmul_scaled(E4M3, E5M2, BF16, 1, 8192, 8192, 8192)
+    assert rc == 0
+    launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
+    assert launches == ["pack_scales", "pack_scales", "gemm_mxf8_bf16_2sm_n256_kk"]
+    assert t.count(f"alloc {64 * 64 * 512}") == 2                           # 64 row tiles x 64 k-atoms x 512 B each
+    # operands as bytes, K-major, 128B swizzle; scale chunks: (16 B, 32 rows x atoms, tiles), one k-block per box, B: 2 tiles
+    assert "tmap esz=1 dims=(8192,8192,1) strides=(8192,67108864) box=(128,128) swizzle=3" in t
+    assert "tmap esz=1 dims=(16,2048,64) strides=(16,32768) box=(16,32) swizzle=0" in t
+    assert "tmap esz=1 dims=(16,2048,64) strides=(16,32768) box=(16,32,2) swizzle=0" in t
+    assert "smem=210176 cluster=2" in t                                     # 6 x (16K + 16K + 2K) + 1280
+    rc, t = plan.matmul_scaled(FP4, FP4, F32, 2, 4096, 4096, 8192)          # packed e2m1: 4096 bytes of K per row
+    assert rc == 0 and "gemm_mxf4_f32_" in t
+    assert "tmap esz=1 dims=(4096,4096,2) strides=(4096,16777216) box=(128,128) swizzle=3" in t
+    assert "box=(16,64) swizzle=0" in t and "box=(16,64,2) swizzle=0" in t   # two chunks per k-block (256 elements of K)
+    rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 16, 8, 32)               # the reference's m16 n8 k32 test shape
+    assert rc == 0 and "gemm_mxf8_f32_1sm_n128_kk" in t
+    rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 64, 64, 128, packed=1)   # caller-packed scales: no packing pass
+    assert rc == 0 and "pack_scales" not in t and "alloc" not in t
+    rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 64, 64, 128, a=A + 4)    # misaligned operand: reference-order SIMT path
+    assert rc == 0 and t.strip().startswith("launch gemm_scaled_simt")
+    plan.option("gemm.variant", "simt")
+    rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 64, 64, 128)
+    assert rc == 0 and "gemm_scaled_simt" in t
+    plan.option("gemm.variant", "auto")
+    assert plan.matmul_scaled(E4M3, E4M3, F32, 1, 64, 64, 100)[0] != 0      # K not a multiple of the scale block
+    assert plan.matmul_scaled(E4M3, E4M3, F32, 1, 64, 64, 128, block=16)[0] != 0
+    assert plan.matmul_scaled(E4M3, FP4, F32, 1, 64, 64, 128)[0] != 0       # fp4 cannot mix with fp8
+    assert plan.matmul_scaled(BF16, BF16, F32, 1, 64, 64, 128)[0] != 0
+    assert plan.matmul_scaled(E4M3, E4M3, I32, 1, 64, 64, 128)[0] != 0
+    assert plan.matmul_scaled(E4M3, E4M3, F32, 0, 64, 64, 128) == (0, "")   # empty batch: nothing to do
 
 
 def test_small_and_unaligned_problems(plan):

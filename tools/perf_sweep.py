@@ -83,6 +83,30 @@ if "gemm" in what:
         c.set_option("gemm.group_m", 8)
         del a, b, o
 
+if "scaled" in what:
+    # block-scaled (MX) GEMM: every tile variant, row-major scales (packing passes inside the timed call) and pre-packed
+    print("block-scaled matmul, CUDA events (flops = 2 M N K):")
+    for (dt, n, k) in (("f8e4m3", 8192, 8192), ("f4e2m1x2", 8192, 8192), ("f8e4m3", 4096, 4096), ("f4e2m1x2", 4096, 4096),
+                       ("f4e2m1x2", 8192, 16384)):
+        kb = k // 2 if dt == "f4e2m1x2" else k
+        a = TensorHandle.empty_contiguous(c, [n, kb], dt)
+        b = TensorHandle.empty_contiguous(c, [n, kb], dt)
+        o = TensorHandle.empty_contiguous(c, [n, n], "bf16")
+        c.fill_uniform(a.handle, "f8e4m3", n * kb, 3, -1.0, 1.0)   # finite e4m3 codes; as e2m1 pairs every byte is finite
+        c.fill_uniform(b.handle, "f8e4m3", n * kb, 4, -1.0, 1.0)
+        sa = TensorHandle.from_numpy(c, np.full((n, k // 32), 127, np.uint8), "ue8m0")
+        sb = TensorHandle.from_numpy(c, np.full((n, k // 32), 126, np.uint8), "ue8m0")
+        tiles, atoms = n // 128, k // 128
+        pa = TensorHandle.from_numpy(c, np.full((tiles, atoms, 512), 127, np.uint8), "ue8m0")
+        flops = 2.0 * n * n * k
+        for variant in ("2sm_n256", "2sm_n128", "1sm_n128"):
+            c.set_option("gemm.variant", variant)
+            ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, sa, sb, o), iters=10, warm=2) for _ in range(3))
+            msp = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scales_packed=True), iters=10, warm=2) for _ in range(3))
+            print(f"  {dt:9s} {n}x{n}x{k} {variant}: {ms * 1e3:8.1f} us {flops / ms / 1e9:7.0f} TF/s | pre-packed scales {msp * 1e3:8.1f} us {flops / msp / 1e9:7.0f} TF/s", flush=True)
+        c.set_option("gemm.variant", "auto")
+        del a, b, o
+
 if "split" in what:
     # tail split (deterministic split-K of the last partial wave): off vs forced S vs the auto policy
     print("gemm.split_k sweep (auto variant), CUDA events:")
