@@ -493,7 +493,19 @@ def main():
             ms_8, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
             line["matmul_fp8_8192"] = {"value": world * FLOPS_MM * extra_steps / (ms_8 * 1e-3) / 1e12, "unit": "TFLOP/s",
                                        "config": "fp8 e4m3 x e4m3 -> bf16, f32 accumulate, 8192^3 per GPU"}
-            del a8, b8
+            # widening row: block-scaled MX formats -- tcgen05 kind::mxf8f6f4 / kind::mxf4, ue8m0 scale per 32 K,
+            # row-major scales as the reference's scaled MMA takes them (the two packing passes run inside the timed call)
+            import numpy as _np
+            sc = TensorHandle.from_numpy(c, _np.full((N_MM, N_MM // 32), 127, _np.uint8), "ue8m0")
+            ms_m8, _ = timed(lambda: matmul.launch_scaled(c, a8, b8, sc, sc, o), extra_steps, 3)
+            a4 = TensorHandle(a8.handle, [N_MM, N_MM // 2], [N_MM // 2, 1], "f4e2m1x2")   # the same bytes read as packed e2m1
+            b4 = TensorHandle(b8.handle, [N_MM, N_MM // 2], [N_MM // 2, 1], "f4e2m1x2")
+            ms_m4, _ = timed(lambda: matmul.launch_scaled(c, a4, b4, sc, sc, o), extra_steps, 3)
+            line["matmul_block_scaled_8192"] = {
+                "unit": "TFLOP/s", "mxfp8_e4m3": world * FLOPS_MM * extra_steps / (ms_m8 * 1e-3) / 1e12,
+                "mxfp4_e2m1": world * FLOPS_MM * extra_steps / (ms_m4 * 1e-3) / 1e12,
+                "config": "8192^3 per GPU -> bf16, ue8m0 scale per 32 elements of K for both operands, scale packing included"}
+            del a8, b8, a4, b4, sc
             # what CubeCL's own kernels reach on this GPU (hand-written from its emit rules)
             if world == 1:
                 scratch = c.empty(1024)

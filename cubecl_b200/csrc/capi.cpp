@@ -214,6 +214,7 @@ struct GemmParams {
   uint32_t full_tiles, split_tiles, split_s, pad0;  // tail split, see gemm_tcgen05.cu
   uint64_t split_ws, split_tickets;
   uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;  // block-scaled kinds
+  uint32_t tma_store, pad1;
 };
 struct PackScalesParams {
   uint64_t in, out;
@@ -492,7 +493,7 @@ extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
 
 extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
-  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "reduce.variant", "reduce.threads",
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
@@ -772,12 +773,10 @@ struct GemmVariant {
   double eff;       // measured MMA-pipe efficiency relative to 2sm_n256 (8192^3, B200): the N=128 shapes need
                     // 128 B/cycle/SM of operand reads from shared memory and are smem-bandwidth bound
 };
-static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59},
-                                       {"2sm_n256s7", 2, 256, 7, 0.0 /* tuning only: never auto-selected */}};
+static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59}};
 static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
   const bool bits8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2 || in_dtype == B200_U8 || in_dtype == B200_I8);
   if (bits8) return !strcmp(v.tag, "2sm_n256") || !strcmp(v.tag, "1sm_n128");
-  if (!strcmp(v.tag, "2sm_n256s7")) return in_dtype == B200_BF16;
   return true;
 }
 
@@ -787,8 +786,10 @@ static unsigned gemm_sf_stage_bytes(const GemmVariant& v, int mx_kind) {
   const unsigned raw = 512u * mx_kind * (1 + v.block_n / 128);
   return (raw + 1023u) / 1024u * 1024u;
 }
+static int gemm_stages(const GemmVariant& v, int mx_kind) { return (mx_kind == 2 && v.block_n == 256) ? 5 : v.stages; }
+// alignment slack + operand ring (+ scale chunks) + barrier block + epilogue staging (4 warps x [32 rows x 128 B])
 static unsigned gemm_smem_bytes(const GemmVariant& v, int mx_kind = 0) {
-  return v.stages * (16384 + (v.block_n / v.cg) * 128 + gemm_sf_stage_bytes(v, mx_kind)) + 1024 + 256;
+  return 1024 + gemm_stages(v, mx_kind) * (16384 + (v.block_n / v.cg) * 128 + gemm_sf_stage_bytes(v, mx_kind)) + 1024 + 16384;
 }
 
 static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, size_t esz, uint64_t base, uint64_t d0,
@@ -899,7 +900,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   for (const GemmVariant& v : kVariants) {
     if (forced != "auto" && forced != v.tag) continue;
     if (forced == "auto" && v.eff <= 0.0) continue;
-    if (g.mx_kind ? !strcmp(v.tag, "2sm_n256s7") : !variant_has_dtype(v, g.in_dtype)) continue;
+    if (!g.mx_kind && !variant_has_dtype(v, g.in_dtype)) continue;
     if (forced == "auto" && v.cg == 2 && g.M <= 128) continue;  // a CTA pair would idle its second half: one CTA per tile
     const uint64_t tm = (g.M + 128 * v.cg - 1) / (128 * v.cg), tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
@@ -989,6 +990,18 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   p.a_bmul = a_bcast ? 0 : 1;
   p.b_bmul = b_bcast ? 0 : 1;
   p.vec_store = (g.out % 16 == 0 && (g.o_sm * osz) % 16 == 0 && (g.o_sb * osz) % 16 == 0) ? 1 : 0;
+  // whole tiles leave through swizzled staging tiles and TMA stores when `out` is describable: (N, M, batch), 128-byte boxes
+  CUtensorMap tout;
+  memset(&tout, 0, sizeof(tout));
+  const uint64_t lim40 = 1ull << 40;
+  if (p.vec_store && opt(c, "gemm.epilogue", "tma") == "tma" && g.o_sm * osz < lim40 && g.o_sb * osz < lim40 && (g.M == 1 || g.o_sm >= g.N)) {
+    const uint64_t o_sm = g.M > 1 ? g.o_sm : (g.N + 15) / 16 * 16;
+    const uint64_t o_sb = g.batch > 1 ? g.o_sb : o_sm * g.M;
+    rc = encode_tmap(c, &tout, osz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, osz, g.out, g.N, g.M, g.batch,
+                     o_sm, o_sb, static_cast<uint32_t>(128 / osz), 32);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
 
   const uint64_t total_tiles = static_cast<uint64_t>(p.tiles_m) * p.tiles_n * p.batch;
   if (total_tiles >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "too many tiles");
@@ -1044,7 +1057,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
       c->plan += line;
     }
   }
-  void* args[] = {&ta, &tb, &ta_lo, &tb_lo, &p};
+  void* args[] = {&ta, &tb, &ta_lo, &tb_lo, &tout, &p};
   rc = launch(c, f, clusters * v.cg, 1, 1, 256, smem, v.cg, st, args);
   if (slabs) pool_free(c, slabs, st);  // stream-ordered: reusable by later work once this launch has drained
   return rc;

@@ -41,6 +41,9 @@ struct GemmParams {
   // Block-scaled kinds (KIND_MXF8 / KIND_MXF4): operand formats for the instruction descriptor and the number of 128-row
   // scale-factor tiles per batch entry of each operand (the packed scale tensors are [batch * tiles][k atoms][512 B]).
   uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;
+  // 1: whole tiles leave through shared memory and TMA stores (tma_out describes `out` as (N, M, batch)); needs a 16-byte
+  // aligned base and row / batch pitches.  0: each thread stores its own row directly.
+  uint32_t tma_store, pad1;
 };
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6,
@@ -141,7 +144,7 @@ __device__ __forceinline__ WorkUnit unit_decode(uint32_t u, const GemmParams& p,
 // ACC = accumulator stages in TMEM: 256-wide scaled tiles have room for one only (512 columns - scale columns).
 template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES, int ACC = 2>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUtensorMap* tma_b_hi, const CUtensorMap* tma_a_lo,
-                                          const CUtensorMap* tma_b_lo, const GemmParams& p) {
+                                          const CUtensorMap* tma_b_lo, const CUtensorMap* tma_out, const GemmParams& p) {
   constexpr bool SCALED = (KIND >= KIND_MXF8);
   constexpr bool INT_ACC = (KIND == KIND_U8 || KIND == KIND_S8);
   static_assert(!SCALED || (!A_MN && !B_MN && BLOCK_N % 128 == 0), "block-scaled kinds: K-major operands, 128-row scale tiles");
@@ -182,6 +185,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t split_flag = tmem_slot + 4;  // "this CTA reduces the slabs" broadcast among the epilogue warps
+  // epilogue staging: one [32 rows x 128 B] tile per epilogue warp, 128B-swizzled like the tensor map that stores it
+  const uint32_t epi_base = bar_base + 1024u;
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -193,6 +198,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tma_a_hi);
     tma_prefetch_desc(tma_b_hi);
+    if (p.tma_store) tma_prefetch_desc(tma_out);
     if (p.k_segments > 1 || SCALED) { tma_prefetch_desc(tma_a_lo); tma_prefetch_desc(tma_b_lo); }
   }
   if (warp == 1 && lane == 0) {
@@ -312,16 +318,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           const uint64_t a_desc = A_MN ? mn_desc(sa) : make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t b_desc = B_MN ? mn_desc(sb) : make_smem_desc_sw128(sb, 16, 1024);
           if constexpr (SCALED) {
+            // Scale chunks smem -> TMEM, then the four MMAs that read them.  tcgen05.cp and tcgen05.mma execute in issue
+            // order in one pipe, so a single TMEM scale buffer is safe.  Measured (ncu, 8192^3): each copy occupies that pipe
+            // for ~100 cycles -- 3 per k-block for mxf8 (tensor pipe 62 % busy), 6 for mxf4 (48 %); issuing them a k-block
+            // ahead into a second TMEM buffer changed nothing, so it is occupancy, not latency.
             const uint32_t sfa_s = sb + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
+            const uint32_t sf_t = tmem_base;
             // unswizzled 32 x 16 B chunk: 8-row groups 128 B apart (SBO); a single 16-byte column, so no LBO
 #pragma unroll
             for (int atom = 0; atom < SF_ATOMS; ++atom)
-              tmem_cp_32x128b_warpx4<CG>(tmem_base + SFA_COL + 4u * atom, make_smem_desc(sfa_s + 512u * atom, 0, 128, 0));
+              tmem_cp_32x128b_warpx4<CG>(sf_t + SFA_COL + 4u * atom, make_smem_desc(sfa_s + 512u * atom, 0, 128, 0));
 #pragma unroll
             for (int tile = 0; tile < SF_TILES_B; ++tile)
 #pragma unroll
               for (int atom = 0; atom < SF_ATOMS; ++atom)
-                tmem_cp_32x128b_warpx4<CG>(tmem_base + SFB_COL + 4u * (atom * SF_TILES_B + tile),
+                tmem_cp_32x128b_warpx4<CG>(sf_t + SFB_COL + 4u * (atom * SF_TILES_B + tile),
                                            make_smem_desc(sfb_s + 512u * (tile * SF_ATOMS + atom), 0, 128, 0));
             const uint32_t idesc_base = make_idesc_scaled(p.sf_fmt_a, p.sf_fmt_b, UMMA_M, BLOCK_N);
 #pragma unroll
@@ -329,8 +340,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
               const uint32_t atom = (KIND == KIND_MXF4) ? k / 2 : 0;
               const uint32_t sf_id = (KIND == KIND_MXF4) ? (k & 1) * 2 : k;
               umma_ss_scaled<CG, (KIND == KIND_MXF4) ? 1 : 0>(d_tmem, a_desc + 2 * k, b_desc + 2 * k,
-                                                              idesc_base | (sf_id << 29) | (sf_id << 4), tmem_base + SFA_COL + 4u * atom,
-                                                              tmem_base + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
+                                                              idesc_base | (sf_id << 29) | (sf_id << 4), sf_t + SFA_COL + 4u * atom,
+                                                              sf_t + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
           } else {
 #pragma unroll
@@ -340,7 +351,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
               umma_ss<CG, (SCALED ? KIND_E4M3 : KIND)>(d_tmem, a_k, b_k, IDESC, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
           }
-          umma_commit<CG>(empty_bar(s));  // smem slot reusable once these MMAs retire
+          umma_commit<CG>(empty_bar(s));  // smem slot reusable once these MMAs (and scale copies) retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit<CG>(tfull_bar(as));  // accumulator complete -> epilogue
@@ -378,7 +389,58 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
-      if (!wu.partial) {
+      if (!wu.partial && p.tma_store) {
+        // TMEM -> registers -> (epilogue, convert) -> swizzled staging tile -> one TMA store per 128-byte-wide column group.
+        // A direct store has every lane write its own row: 32 LSU wavefronts per instruction, ~3 us per 128x256 bf16 tile,
+        // which matters wherever the epilogue is not hidden behind the next tile's MMAs (single-accumulator scaled tiles,
+        // the last wave).  The staged form costs 4 wavefronts per shared-memory store and the TMA unit clips ragged edges.
+        constexpr int CW = (OUT == OUT_F32) ? 32 : 64;   // columns per staging tile: 128 bytes per row
+        const int m_row0 = static_cast<int>((tc.m_blk * CG + rank) * 128 + q * 32);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / CW; ++c) {
+          const uint32_t n0 = n_tile + c * CW;
+          const uint32_t stage_smem = epi_base + q * 4096u;
+          if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < CW / 32; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + c * CW + h * 32, v);
+            tmem_ld_wait();
+            fused_epilogue(v, n0 + h * 32);
+            const uint32_t row = stage_smem + lane * 128u;
+            if constexpr (OUT == OUT_F32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((static_cast<uint32_t>(j) ^ (lane & 7u)) << 4)),
+                             "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+            } else {
+              uint32_t packed[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
+                if constexpr (OUT == OUT_BF16) {
+                  __nv_bfloat162 t2 = __floats2bfloat162_rn(lo, hi);
+                  packed[j] = *reinterpret_cast<uint32_t*>(&t2);
+                } else {
+                  __half2 t2 = __floats2half2_rn(lo, hi);
+                  packed[j] = *reinterpret_cast<uint32_t*>(&t2);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((static_cast<uint32_t>(h * 4 + j) ^ (lane & 7u)) << 4)),
+                             "r"(packed[4 * j]), "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]) : "memory");
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA unit
+          __syncwarp();
+          if (lane == 0 && m_row0 < static_cast<int>(p.M) && n0 < p.N) {
+            tma_store_3d(tma_out, stage_smem, static_cast<int>(n0), m_row0, static_cast<int>(tc.b));
+            tma_store_commit();
+          }
+        }
+      } else if (!wu.partial) {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
@@ -471,6 +533,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the flag word is reused by the next partial unit
       }
     }
+    if (lane == 0) tma_store_wait<0>();  // outstanding TMA stores read this CTA's shared memory: finish before teardown
+    __syncwarp();
   }
 
   tcgen05_fence_before();
@@ -480,14 +544,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 }
 
 // Dynamic shared memory a variant needs (host mirrors this in capi.cpp: gemm_smem_bytes()).
-//   STAGES * (16384 + (BLOCK_N/CG)*128) + 1024 (alignment slack) + 256 (barriers)
+//   1024 (alignment slack) + STAGES * (16384 + (BLOCK_N/CG)*128 + scale chunks) + 1024 (barriers) + 16384 (epilogue staging)
 
 #define GEMM_KERNEL_ACC(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC)                                          \
   extern "C" __global__ void __launch_bounds__(kNumThreads, 1)                                                   \
       NAME(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,                 \
            const __grid_constant__ CUtensorMap tma_a_lo, const __grid_constant__ CUtensorMap tma_b_lo,           \
-           const __grid_constant__ GemmParams p) {                                                               \
-    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC>(&tma_a, &tma_b, &tma_a_lo, &tma_b_lo, p);                \
+           const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ GemmParams p) {                  \
+    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC>(&tma_a, &tma_b, &tma_a_lo, &tma_b_lo, &tma_out, p);      \
   }
 #define GEMM_KERNEL(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES) GEMM_KERNEL_ACC(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, 2)
 
@@ -520,8 +584,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 // 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
 GEMM_DTYPES(2sm_n256, 2, 256, 6)
 GEMM_FP8(2sm_n256, 2, 256, 6)
-// tuning variant: 7 stages (224 KB of operand ring), bf16 only
-GEMM_LAYOUTS(gemm_bf16_bf16_2sm_n256s7, 2, 256, KIND_BF16, OUT_BF16, 7)
 // 2-SM, 256x128 tiles: 24 KB/stage/CTA -> 8 stages = 192 KB (smem-read bound: 128 B/cycle/SM of operands)
 GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
@@ -537,7 +599,13 @@ GEMM_FP8(1sm_n128, 1, 128, 6)
   GEMM_KERNEL_ACC(gemm_mxf4_f32_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F32, STAGES, ACC)   \
   GEMM_KERNEL_ACC(gemm_mxf4_bf16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_BF16, STAGES, ACC) \
   GEMM_KERNEL_ACC(gemm_mxf4_f16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F16, STAGES, ACC)
-GEMM_MX(2sm_n256, 2, 256, 6, 1)  // 512 TMEM columns: one 256-wide accumulator + 24 scale columns (no epilogue overlap)
+// 512 TMEM columns: one 256-wide accumulator + 12 / 24 scale columns (no epilogue overlap)
+GEMM_KERNEL_ACC(gemm_mxf8_f32_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_F32, 6, 1)
+GEMM_KERNEL_ACC(gemm_mxf8_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_BF16, 6, 1)
+GEMM_KERNEL_ACC(gemm_mxf8_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_F16, 6, 1)
+GEMM_KERNEL_ACC(gemm_mxf4_f32_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F32, 5, 1)   // 35 KB stages: 5 fit beside the staging
+GEMM_KERNEL_ACC(gemm_mxf4_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_BF16, 5, 1)
+GEMM_KERNEL_ACC(gemm_mxf4_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F16, 5, 1)
 GEMM_MX(2sm_n128, 2, 128, 8, 2)
 GEMM_MX(1sm_n128, 1, 128, 6, 2)
 

@@ -18,6 +18,7 @@ def _reset_options(client):
     client.set_option("gemm.variant", "auto")
     client.set_option("gemm.f32", "3xtf32")
     client.set_option("gemm.split_k", "auto")
+    client.set_option("gemm.epilogue", "tma")
 
 
 # ------------------------------------------------------------------------------------------------ reference goldens
@@ -227,6 +228,41 @@ def test_fused_epilogue(client, variant, in_dtype, out_dtype, activation):
     scale = alpha * fabs + np.abs(bias)[None, :] + 1e-6
     tol = {"f32": 1e-5 if in_dtype != "f32" else 1e-4, "bf16": 1e-2, "f16": 2e-3}[out_dtype]
     assert np.max(np.abs(got - exp) / scale) <= tol
+
+
+# ------------------------------------------------------------------------------------------------ epilogue store paths
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("in_dtype,out_dtype", [("bf16", "bf16"), ("bf16", "f32"), ("f16", "f16"), ("f8e4m3", "bf16"), ("f32", "f32")])
+@pytest.mark.parametrize("M,N,K", [(300, 520, 192), (128, 256, 64), (33, 72, 128), (1, 8, 64)])
+def test_tma_store_epilogue_equals_direct_stores(client, variant, in_dtype, out_dtype, M, N, K):
+    # staged TMA stores (ragged edges clipped by the tensor map) must write exactly what the per-thread stores write,
+    # and nothing outside the M x N window of a larger, pre-filled buffer
+    if in_dtype.startswith("f8") and variant == "2sm_n128":
+        pytest.skip("no fp8 kernels for this tile")
+    client.set_option("gemm.variant", variant)
+    a_dev, a = make_operand((M, K), in_dtype, 401)
+    b_dev, b = make_operand((N, K), in_dtype, 402)
+    outs = []
+    for mode in ("tma", "direct"):
+        client.set_option("gemm.epilogue", mode)
+        outs.append(run_matmul(client, a_dev, b_dev, in_dtype, out_dtype, rhs_transposed=True))
+    assert np.array_equal(outs[0], outs[1])
+    check_against_oracle(outs[0], a, np.ascontiguousarray(b.T), out_dtype)
+
+
+def test_tma_store_respects_pitched_output_window(client):
+    # out is a [M, N] window with a row pitch of N + 24 elements inside a buffer pre-filled with a sentinel
+    M, N, K, pitch = 200, 136, 96, 160
+    a_dev, a = make_operand((M, K), "bf16", 411)
+    b_dev, b = make_operand((K, N), "bf16", 412)
+    lhs, rhs = TensorHandle.from_numpy(client, a_dev, "bf16"), TensorHandle.from_numpy(client, b_dev, "bf16")
+    backing = TensorHandle.from_numpy(client, np.full((M, pitch), -7.0, np.float32), "f32")
+    out = TensorHandle(backing.handle, [M, N], [pitch, 1], "f32")
+    matmul.launch(client, lhs, rhs, out)
+    client.sync()
+    full = backing.to_numpy(client).reshape(M, pitch)
+    assert np.all(full[:, N:] == -7.0)
+    check_against_oracle(full[:, :N], a, b, "f32", tight=1e-5)
 
 
 # ------------------------------------------------------------------------------------------------ tail split (split-K)

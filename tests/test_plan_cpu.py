@@ -64,11 +64,17 @@ def test_headline_plan_is_one_persistent_2sm_launch(plan):
     rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert rc == 0
     lines = t.strip().splitlines()
-    assert lines[-1] == "launch gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1) block=256 smem=197888 cluster=2"
+    # smem: 1 KB alignment slack + 6 x 32 KB operand stages + 1 KB barriers + 16 KB epilogue staging
+    assert lines[-1] == "launch gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1) block=256 smem=215040 cluster=2"
     # A: K-major box [64 k x 128 m]; B (row-major [K,N]): MN-major box [64 n x 64 k]; both SWIZZLE_128B (enum 3)
     assert "tmap esz=2 dims=(8192,8192,1) strides=(16384,134217728) box=(64,128) swizzle=3" in lines[0]
     assert "box=(64,64) swizzle=3" in lines[1]
-    assert len(lines) == 3
+    # C leaves through TMA stores: (N, M, batch) in [64 col x 32 row] = 128-byte-wide swizzled boxes
+    assert "tmap esz=2 dims=(8192,8192,1) strides=(16384,134217728) box=(64,32) swizzle=3" in lines[2]
+    assert len(lines) == 4
+    plan.option("gemm.epilogue", "direct")
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0 and t.count("tmap ") == 2
 
 
 def test_operand_major_combinations_pick_the_right_kernel(plan):
@@ -84,7 +90,7 @@ def test_f32_defaults_to_3xtf32_with_two_split_passes(plan):
     assert rc == 0
     launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
     assert launches == ["split_tf32_lo", "split_tf32_lo", "gemm_tf32_f32_2sm_n256_kn"]   # lo parts only, ONE gemm launch
-    assert t.count("tmap ") == 4                                         # A, B (originals = hi) + A_lo, B_lo
+    assert t.count("tmap ") == 5                                         # A, B (originals = hi) + A_lo, B_lo + C
     assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
     assert t.count(f"alloc {n * n * 4}") == 2                            # 1x temporaries (lo parts), not 3x
     assert "gemm tail split: 222 full tiles + 34 tiles x 2 k-slices" in t  # 256 tiles on 74 CTA pairs: 4th wave is 46 % full
@@ -135,7 +141,7 @@ def test_block_scaled_plans(plan):
     assert "tmap esz=1 dims=(8192,8192,1) strides=(8192,67108864) box=(128,128) swizzle=3" in t
     assert "tmap esz=1 dims=(16,2048,64) strides=(16,32768) box=(16,32) swizzle=0" in t
     assert "tmap esz=1 dims=(16,2048,64) strides=(16,32768) box=(16,32,2) swizzle=0" in t
-    assert "smem=210176 cluster=2" in t                                     # 6 x (16K + 16K + 2K) + 1280
+    assert "smem=227328 cluster=2" in t                                     # 6 x (16K + 16K + 2K) + 1K + 1K + 16K staging
     rc, t = plan.matmul_scaled(FP4, FP4, F32, 2, 4096, 4096, 8192)          # packed e2m1: 4096 bytes of K per row
     assert rc == 0 and "gemm_mxf4_f32_" in t
     assert "tmap esz=1 dims=(4096,4096,2) strides=(4096,16777216) box=(128,128) swizzle=3" in t
@@ -202,7 +208,7 @@ def test_wave_model_prefers_big_tiles(plan):
     assert "gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1)" in t
     plan.option("gemm.variant", "2sm_n128")
     rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
-    assert "gemm_bf16_bf16_2sm_n128_kn" in t and "smem=197888" in t
+    assert "gemm_bf16_bf16_2sm_n128_kn" in t and "smem=215040" in t
     # a GPU with fewer SMs gets a smaller persistent grid
     small = Planner(sms=64)
     rc, t = small.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])

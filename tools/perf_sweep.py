@@ -66,7 +66,7 @@ if "gemm" in what:
         for mode in (("tf32", "3xtf32") if idt == "f32" else ("-",)):
             if idt == "f32":
                 c.set_option("gemm.f32", mode)
-            for variant in (("2sm_n256", "2sm_n256s7", "2sm_n128", "1sm_n128") if (idt == "bf16" and batch == 1) else
+            for variant in (("2sm_n256", "2sm_n128", "1sm_n128") if (idt == "bf16" and batch == 1) else
                             ("2sm_n256", "1sm_n128") if idt.startswith("f8") else ("2sm_n256", "2sm_n128", "1sm_n128")):
                 for rhs_t in (False, True):
                     for gm in ((8, 4, 16) if (variant == "2sm_n256" and not rhs_t and idt == "bf16" and batch == 1) else (8,)):

@@ -22,6 +22,19 @@ elif what == "reduce":
     out = TensorHandle.empty_contiguous(c, [1], "f32")
     for i in range(iters):
         reduce.launch(c, xs[i % 2], out, None, "sum")
+elif what in ("gemm_mxf8", "gemm_mxf4"):
+    import numpy as np
+    n, k = 8192, 8192
+    dt = "f8e4m3" if what == "gemm_mxf8" else "f4e2m1x2"
+    kb = k if what == "gemm_mxf8" else k // 2
+    a = TensorHandle.empty_contiguous(c, [n, kb], dt)
+    b = TensorHandle.empty_contiguous(c, [n, kb], dt)
+    o = TensorHandle.empty_contiguous(c, [n, n], "bf16")
+    c.fill_uniform(a.handle, "f8e4m3", n * kb, 3, -1.0, 1.0)
+    c.fill_uniform(b.handle, "f8e4m3", n * kb, 4, -1.0, 1.0)
+    pa = TensorHandle.from_numpy(c, np.full((n // 128, k // 128, 512), 127, np.uint8), "ue8m0")
+    for _ in range(iters):
+        matmul.launch_scaled(c, a, b, pa, pa, o, scales_packed=True)
 else:
     odt = None
     if what == "gemm_batched":
