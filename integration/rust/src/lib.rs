@@ -66,6 +66,14 @@ extern "C" {
         shape_rhs: *const u64, strides_rhs: *const u64,
         shape_out: *const u64, strides_out: *const u64,
     ) -> c_int;
+    /// Block-scaled (MX) matmul: lhs [batch, m, k], rhs [batch, n, k] K-contiguous (e4m3 / e5m2, or both packed e2m1),
+    /// ue8m0 scales [batch, rows, k / 32]; replaces `MmaDefinition::new_scaled` / `execute_scaled` tiles
+    /// (crates/cubecl-core/src/frontend/cmma.rs:438-460, 798-840) at GEMM level.
+    pub fn b200_matmul_scaled(
+        ctx: *mut b200_ctx, s: b200_stream, lhs_dtype: c_int, rhs_dtype: c_int, out_dtype: c_int,
+        lhs: b200_dptr, rhs: b200_dptr, lhs_scales: b200_dptr, rhs_scales: b200_dptr, out: b200_dptr,
+        batch: u64, m: u64, n: u64, k: u64, scale_block: c_int, scales_packed: c_int,
+    ) -> c_int;
     pub fn b200_reduce_strided(
         ctx: *mut b200_ctx, s: b200_stream, op: c_int, in_dtype: c_int, input: b200_dptr, out: b200_dptr,
         rank: c_int, shape: *const u64, strides: *const u64, axis: c_int,
