@@ -308,6 +308,13 @@ class ComputeClient:
         _ffi.check(self._lib.b200_probe_umma(self._ctx, None, int(n_iter), C.c_uint64(scratch.ptr), C.byref(ops)))
         return ops.value
 
+    def probe_umma_kind(self, dtype: str, block_scaled: bool, n_iter: int, scratch: Handle) -> float:
+        """tcgen05 peak probe for fp8 (plain / block-scaled) and block-scaled fp4 operands; returns the op count of the launch."""
+        ops = C.c_double()
+        _ffi.check(self._lib.b200_probe_umma_kind(self._ctx, None, DTYPES[dtype], int(bool(block_scaled)), int(n_iter),
+                                                  C.c_uint64(scratch.ptr), C.byref(ops)))
+        return ops.value
+
     def probe_memread(self, buf: Handle, nbytes: int, scratch: Handle) -> None:
         _ffi.check(self._lib.b200_probe_memread(self._ctx, None, C.c_uint64(buf.ptr), int(nbytes), C.c_uint64(scratch.ptr)))
 

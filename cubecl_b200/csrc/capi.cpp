@@ -1770,6 +1770,28 @@ extern "C" int b200_probe_umma(b200_ctx* c, b200_stream s, uint32_t n_iter, b200
   return rc;
 }
 
+extern "C" int b200_probe_umma_kind(b200_ctx* c, b200_stream s, b200_dtype dtype, int block_scaled, uint32_t n_iter, b200_dptr scratch,
+                                    double* ops) {
+  CTX_ENTER_DEVICE(c);
+  if (dtype == B200_BF16 && !block_scaled) return b200_probe_umma(c, s, n_iter, scratch, ops);
+  const char* name = (dtype == B200_F8E4M3 && !block_scaled) ? "umma_probe_e4m3_2sm"
+                     : (dtype == B200_F8E4M3 && block_scaled) ? "umma_probe_mxf8_2sm"
+                     : (dtype == B200_F4E2M1X2 && block_scaled) ? "umma_probe_mxf4_2sm" : nullptr;
+  if (!name) return fail(B200_ERR_UNSUPPORTED, "probe_umma_kind: bf16, f8e4m3 (plain or block-scaled) or block-scaled f4e2m1x2");
+  CUfunction f;
+  int rc = get_func(c, name, &f);
+  if (rc) return rc;
+  const unsigned smem = 32768 + 2048 + 1024 + 64;
+  CU_CHECK(g_drv.cuFuncSetAttribute_p(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+  const unsigned clusters = (unsigned)std::max(1, c->props.num_sms / 2);
+  uint64_t sp = scratch;
+  void* args[] = {&sp, &n_iter};
+  rc = launch(c, f, clusters * 2, 1, 1, 256, smem, 2, resolve_stream(c, s), args);
+  const double k_per_instr = dtype == B200_F4E2M1X2 ? 64.0 : 32.0;
+  if (!rc && ops) *ops = static_cast<double>(clusters) * n_iter * 4.0 * 2.0 * 256 * 256 * k_per_instr;
+  return rc;
+}
+
 extern "C" int b200_probe_memread(b200_ctx* c, b200_stream s, b200_dptr buf, uint64_t bytes, b200_dptr scratch) {
   CTX_ENTER(c);
   CUfunction f;

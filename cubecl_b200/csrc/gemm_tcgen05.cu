@@ -319,9 +319,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           const uint64_t b_desc = B_MN ? mn_desc(sb) : make_smem_desc_sw128(sb, 16, 1024);
           if constexpr (SCALED) {
             // Scale chunks smem -> TMEM, then the four MMAs that read them.  tcgen05.cp and tcgen05.mma execute in issue
-            // order in one pipe, so a single TMEM scale buffer is safe.  Measured (ncu, 8192^3): each copy occupies that pipe
-            // for ~100 cycles -- 3 per k-block for mxf8 (tensor pipe 62 % busy), 6 for mxf4 (48 %); issuing them a k-block
-            // ahead into a second TMEM buffer changed nothing, so it is occupancy, not latency.
+            // order in one pipe, so a single TMEM scale buffer is safe.  Measured (8192^3, copies switched off): each copy
+            // occupies that pipe for 25-50 cycles -- 9 % of the mxf8 run (3 per k-block), 25 % of the mxf4 run (6 per
+            // k-block); issuing them a k-block ahead into a second TMEM buffer changed nothing (occupancy, not latency).
             const uint32_t sfa_s = sb + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
             const uint32_t sf_t = tmem_base;
             // unswizzled 32 x 16 B chunk: 8-row groups 128 B apart (SBO); a single 16-byte column, so no LBO
@@ -389,7 +389,60 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
-      if (!wu.partial && p.tma_store) {
+      bool released = false;  // the accumulator stage was already handed back to the MMA warp
+      if (ACC == 1 && OUT != OUT_F32 && !wu.partial && p.tma_store) {
+        // Single accumulator (256-wide scaled tiles): the next tile's MMAs wait for this drain, so the whole row is pulled
+        // into registers first -- converted and packed, 128 registers for 256 columns -- the TMEM stage is released, and
+        // only then do the staging stores / TMA stores run, under the next tile's mainloop.
+        constexpr int NPK = (ACC == 1 && OUT != OUT_F32) ? BLOCK_N / 2 : 1;
+        uint32_t packed[NPK];
+        if constexpr (ACC == 1 && OUT != OUT_F32) {
+#pragma unroll
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, v);
+            tmem_ld_wait();
+            fused_epilogue(v, n_tile + c * 32);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
+              if constexpr (OUT == OUT_BF16) {
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(lo, hi);
+                packed[c * 16 + j] = *reinterpret_cast<uint32_t*>(&t2);
+              } else {
+                __half2 t2 = __floats2half2_rn(lo, hi);
+                packed[c * 16 + j] = *reinterpret_cast<uint32_t*>(&t2);
+              }
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
+          }
+          released = true;
+          const int m_row0 = static_cast<int>((tc.m_blk * CG + rank) * 128 + q * 32);
+          const uint32_t stage_smem = epi_base + q * 4096u;
+          const uint32_t row = stage_smem + lane * 128u;
+#pragma unroll
+          for (int c = 0; c < BLOCK_N / 64; ++c) {
+            const uint32_t n0 = n_tile + c * 64;
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((static_cast<uint32_t>(j) ^ (lane & 7u)) << 4)),
+                           "r"(packed[c * 32 + 4 * j]), "r"(packed[c * 32 + 4 * j + 1]), "r"(packed[c * 32 + 4 * j + 2]),
+                           "r"(packed[c * 32 + 4 * j + 3]) : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m_row0 < static_cast<int>(p.M) && n0 < p.N) {
+              tma_store_3d(tma_out, stage_smem, static_cast<int>(n0), m_row0, static_cast<int>(tc.b));
+              tma_store_commit();
+            }
+          }
+        }
+      } else if (!wu.partial && p.tma_store) {
         // TMEM -> registers -> (epilogue, convert) -> swizzled staging tile -> one TMA store per 128-byte-wide column group.
         // A direct store has every lane write its own row: 32 LSU wavefronts per instruction, ~3 us per 128x256 bf16 tile,
         // which matters wherever the epilogue is not hidden behind the next tile's MMAs (single-accumulator scaled tiles,
@@ -468,10 +521,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           for (int j = 0; j < 8; ++j) __stcg(dst + (c * 8 + j) * 128, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
+      if (!released) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
+        }
       }
       if (++as == ACC) { as = 0; aph ^= 1; }
       if (wu.partial) {
@@ -660,3 +715,67 @@ extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_bf16_2sm
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc<2>(tmem_base, 256);
 }
+
+// The same probe for the other tensor-core kinds on 8-bit / 4-bit operands: PK 1 = kind::f8f6f4 (e4m3), 2 = kind::mxf8f6f4
+// block-scaled (e4m3, ue8m0 scales = 1.0 copied to TMEM once), 3 = kind::mxf4 block-scaled (packed e2m1, two scales per
+// row per instruction).  Operands are all ones, so out[pair] = K_per_instruction * 4 * n_iter with K = 32, 32, 64.
+template <int PK>
+__device__ __forceinline__ void umma_probe_8bit_body(float* out, uint32_t n_iter) {
+  extern __shared__ uint8_t smem_probe8_raw[];
+  const uint32_t smem_base = (smem_u32(smem_probe8_raw) + 1023u) & ~1023u;
+  const uint32_t sa = smem_base, sb = smem_base + 16384, sf = smem_base + 32768;  // sf: 1.5 KB of scale chunks
+  const uint32_t done_bar = smem_base + 32768 + 2048, tmem_slot = done_bar + 8;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool leader = cluster_ctarank() == 0;
+  const uint32_t ones = (PK == 3) ? 0x22222222u : 0x38383838u;  // e2m1 1.0 = 0x2 per nibble, e4m3 1.0 = 0x38 per byte
+  for (uint32_t i = threadIdx.x; i < 32768 / 4; i += blockDim.x)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_base + 4 * i), "r"(ones) : "memory");
+  for (uint32_t i = threadIdx.x; i < 2048 / 4; i += blockDim.x)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sf + 4 * i), "r"(0x7F7F7F7Fu) : "memory");  // ue8m0 127 = 1.0
+  fence_proxy_async_smem();
+  if (warp == 1 && lane == 0) {
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(tmem_slot, 512);
+    tmem_relinquish<2>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (warp == 1 && leader && lane == 0) {
+    const uint64_t a_desc = make_smem_desc_sw128(sa, 16, 1024), b_desc = make_smem_desc_sw128(sb, 16, 1024);
+    if constexpr (PK >= 2) {
+      for (int j = 0; j < 3; ++j) tmem_cp_32x128b_warpx4<2>(tmem_base + 256 + 4 * j, make_smem_desc(sf + 512 * j, 0, 128, 0));
+    }
+    constexpr uint32_t idesc = (PK == 1) ? make_idesc(0, 0, 0, 256, 256) : make_idesc_scaled(PK == 3 ? 1 : 0, PK == 3 ? 1 : 0, 256, 256);
+    for (uint32_t i = 0; i < n_iter; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t acc = (i | k) != 0 ? 1u : 0u;
+        if constexpr (PK == 1) umma_ss<2, KIND_E4M3>(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+        else umma_ss_scaled<2, (PK == 3) ? 1 : 0>(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, tmem_base + 256, tmem_base + 260, acc);
+      }
+    }
+    umma_commit<2>(done_bar);
+  }
+  __syncwarp();
+  mbar_wait(done_bar, 0);
+  tcgen05_fence_after();
+  if (warp == 4) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base, v);
+    tmem_ld_wait();
+    if (lane == 0 && leader) out[cluster_id_x()] = __uint_as_float(v[0]);
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_e4m3_2sm(float* out, uint32_t n_iter) { umma_probe_8bit_body<1>(out, n_iter); }
+extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_mxf8_2sm(float* out, uint32_t n_iter) { umma_probe_8bit_body<2>(out, n_iter); }
+extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_mxf4_2sm(float* out, uint32_t n_iter) { umma_probe_8bit_body<3>(out, n_iter); }

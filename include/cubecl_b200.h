@@ -231,6 +231,11 @@ int b200_probe_wmma(b200_ctx* ctx, b200_stream s, b200_dtype dtype, uint32_t n_i
  * TMEM accumulator) on smem-resident operands; *ops = pairs * n_iter * 4 * 2*256*256*16.  scratch: >= 4 * num_sms/2 bytes;
  * scratch[pair] = 64 * n_iter afterwards. */
 int b200_probe_umma(b200_ctx* ctx, b200_stream s, uint32_t n_iter, b200_dptr scratch, double* ops);
+/* The same probe for the other operand kinds: dtype B200_BF16 (as above), B200_F8E4M3 (kind::f8f6f4, or kind::mxf8f6f4
+ * block-scaled when block_scaled != 0) or B200_F4E2M1X2 (kind::mxf4, block_scaled only).  UMMA 256x256xK with K = 16 / 32 /
+ * 64 elements; *ops = pairs * n_iter * 4 * 2*256*256*K; scratch[pair] = 4 * K * n_iter afterwards. */
+int b200_probe_umma_kind(b200_ctx* ctx, b200_stream s, b200_dtype dtype, int block_scaled, uint32_t n_iter, b200_dptr scratch,
+                         double* ops);
 /* memory_read_throughput with float_4 lines over `bytes` of `buf` (memory_read.rs:68-154): grid = SMs*32, block = 256. */
 int b200_probe_memread(b200_ctx* ctx, b200_stream s, b200_dptr buf, uint64_t bytes, b200_dptr scratch_16);
 /* memory_write_throughput (memory_write.rs: writes only) and memory_direct (memory_direct.rs: copy, both directions counted). */

@@ -117,6 +117,12 @@ def test_reference_probes_run(client):
     pairs = client.properties["num_streaming_multiprocessors"] // 2
     assert ops == pairs * 16 * 4 * 2 * 256 * 256 * 16
     assert np.all(np.frombuffer(client.read_one(scratch), dtype=np.float32)[:pairs] == 1024.0)
+    # fp8, block-scaled fp8 and block-scaled fp4 peaks: K = 32 / 32 / 64 per UMMA, scales = 1.0 -> acc = 4 * K * n_iter
+    for dtype, scaled, kk in (("f8e4m3", False, 32), ("f8e4m3", True, 32), ("f4e2m1x2", True, 64)):
+        ops = client.probe_umma_kind(dtype, scaled, 16, scratch)
+        client.sync()
+        assert ops == pairs * 16 * 4 * 2 * 256 * 256 * kk
+        assert np.all(np.frombuffer(client.read_one(scratch), dtype=np.float32)[:pairs] == 4.0 * kk * 16)
     buf = client.empty(1 << 24)
     client.fill_modulo(buf, "f32", 1 << 22, 2)
     client.probe_memread(buf, 1 << 24, scratch)

@@ -171,6 +171,14 @@ if "probes" in what:
     import numpy as _np
     vals = _np.frombuffer(c.read_one(scratch), dtype=_np.float32)[:4]
     print(f"tcgen05 peak probe (UMMA 256x256x16 bf16, 74 CTA pairs, smem-resident): {ops[0] / ms / 1e9:8.1f} TFLOP/s  acc[0]={vals[0]} (expect {64 * 8192})")
+    for dt, scaled, label in (("f8e4m3", False, "kind::f8f6f4 e4m3"), ("f8e4m3", True, "kind::mxf8f6f4.block_scale e4m3"),
+                              ("f4e2m1x2", True, "kind::mxf4.block_scale e2m1")):
+        def run_k():
+            ops[0] = c.probe_umma_kind(dt, scaled, 8192, scratch)
+
+        ms = time_ms(c, run_k, iters=5, warm=2)
+        vals = _np.frombuffer(c.read_one(scratch), dtype=_np.float32)[:4]
+        print(f"tcgen05 peak probe ({label}, UMMA 256x256, smem-resident): {ops[0] / ms / 1e9:8.1f} TFLOP/s  acc[0]={vals[0]}")
     buf = c.empty(512 << 20)
     c.fill_modulo(buf, "f32", (512 << 20) // 4, 8)
     ms = time_ms(c, lambda: c.probe_memread(buf, 512 << 20, scratch), iters=10, warm=2)
