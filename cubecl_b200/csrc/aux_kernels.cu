@@ -129,10 +129,10 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
 // pack_scales: ue8m0 scales in the reference's layout -- [batch, rows, n_scales] row-major, one scale per row per 32 K
 // elements (test_cmma_scaled: crates/cubecl-core/src/runtime_tests/cmma.rs:1518-1533) -- to the tensor core's packed form:
 // [batch * tiles][atoms][512 B], tile = 128 rows, atom = 4 consecutive scales, byte (r % 32) * 16 + (r / 32) * 4 + s.
-// Rows / scales beyond the tensor are written as 127 (= 1.0), so padded K blocks multiply TMA's zero fill by a finite value.
+// Rows / scales beyond the tensor are written as 1.0 (127 / 0x38), so padded K blocks multiply TMA's zero fill by a finite value.
 struct PackScalesParams {
   uint64_t in, out;
-  uint32_t batch, rows, n_scales, tiles, atoms, pad;
+  uint32_t batch, rows, n_scales, tiles, atoms, pad_value;  // pad_value: the scale byte that means 1.0 (127 ue8m0, 0x38 ue4m3)
 };
 
 extern "C" __global__ void __launch_bounds__(256) pack_scales(const __grid_constant__ PackScalesParams p) {
@@ -151,7 +151,7 @@ extern "C" __global__ void __launch_bounds__(256) pack_scales(const __grid_const
 #pragma unroll
     for (uint32_t sidx = 0; sidx < 4; ++sidx) {
       const uint32_t ks = atom * 4 + sidx;
-      const uint32_t v = (row < p.rows && ks < p.n_scales) ? in[(static_cast<uint64_t>(b) * p.rows + row) * p.n_scales + ks] : 127u;
+      const uint32_t v = (row < p.rows && ks < p.n_scales) ? in[(static_cast<uint64_t>(b) * p.rows + row) * p.n_scales + ks] : p.pad_value;
       word |= v << (8 * sidx);
     }
     out[w] = word;
@@ -181,7 +181,7 @@ struct ScaledSimtParams {
   uint64_t a, b, sa, sb, out;
   uint32_t batch, M, N, K;       // K in elements
   uint32_t a_dtype, b_dtype, out_dtype, scale_block;
-  uint32_t a_bmul, b_bmul, pad0, pad1;
+  uint32_t a_bmul, b_bmul, scale_ue4m3, pad1;   // scale_ue4m3: scales are |e4m3| (NVFP4: the sign bit is ignored) instead of ue8m0
 };
 
 extern "C" __global__ void __launch_bounds__(256) gemm_scaled_simt(const __grid_constant__ ScaledSimtParams p) {
@@ -197,7 +197,8 @@ extern "C" __global__ void __launch_bounds__(256) gemm_scaled_simt(const __grid_
     float acc = 0.f;
     for (uint32_t l = 0; l < p.K; ++l) {
       const float av = mx_elem_to_f32(p.a, arow * p.K + l, p.a_dtype), bv = mx_elem_to_f32(p.b, brow * p.K + l, p.b_dtype);
-      const float as = ue8m0_to_f32(sa[l / p.scale_block]), bs = ue8m0_to_f32(sb[l / p.scale_block]);
+      const float as = p.scale_ue4m3 ? fabsf(load_as_f32(reinterpret_cast<uint64_t>(sa), l / p.scale_block, 10)) : ue8m0_to_f32(sa[l / p.scale_block]);
+      const float bs = p.scale_ue4m3 ? fabsf(load_as_f32(reinterpret_cast<uint64_t>(sb), l / p.scale_block, 10)) : ue8m0_to_f32(sb[l / p.scale_block]);
       acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__fmul_rn(av, as), bv), bs));
     }
     store_from_f32(p.out, i, p.out_dtype, acc);

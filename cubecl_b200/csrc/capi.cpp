@@ -218,13 +218,13 @@ struct GemmParams {
 };
 struct PackScalesParams {
   uint64_t in, out;
-  uint32_t batch, rows, n_scales, tiles, atoms, pad;
+  uint32_t batch, rows, n_scales, tiles, atoms, pad_value;
 };
 struct ScaledSimtParams {
   uint64_t a, b, sa, sb, out;
   uint32_t batch, M, N, K;
   uint32_t a_dtype, b_dtype, out_dtype, scale_block;
-  uint32_t a_bmul, b_bmul, pad0, pad1;
+  uint32_t a_bmul, b_bmul, scale_ue4m3, pad1;
 };
 struct ReduceParams {
   uint64_t in, out, ws;
@@ -780,13 +780,17 @@ static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
   return true;
 }
 
-// mx_kind: 0 = unscaled, 1 = mxf8 (one 512-byte scale chunk per 128 rows per k-block), 2 = mxf4 (two)
+// mx_kind: 0 = unscaled, 1 = mxf8 (one 512-byte scale chunk per 128 rows per k-block), 2 = mxf4 (two), 3 = nvfp4 (four)
+static unsigned mx_atoms(int mx_kind) { return mx_kind == 3 ? 4u : (unsigned)mx_kind; }
 static unsigned gemm_sf_stage_bytes(const GemmVariant& v, int mx_kind) {
   if (!mx_kind) return 0;
-  const unsigned raw = 512u * mx_kind * (1 + v.block_n / 128);
+  const unsigned raw = 512u * mx_atoms(mx_kind) * (1 + v.block_n / 128);
   return (raw + 1023u) / 1024u * 1024u;
 }
-static int gemm_stages(const GemmVariant& v, int mx_kind) { return (mx_kind == 2 && v.block_n == 256) ? 5 : v.stages; }
+static int gemm_stages(const GemmVariant& v, int mx_kind) {
+  if (mx_kind == 3) return v.block_n == 256 ? 5 : v.cg == 2 ? 7 : 5;   // 38 / 28 / 36 KB stages
+  return (mx_kind == 2 && v.block_n == 256) ? 5 : v.stages;
+}
 // alignment slack + operand ring (+ scale chunks) + barrier block + epilogue staging (4 warps x [32 rows x 128 B])
 static unsigned gemm_smem_bytes(const GemmVariant& v, int mx_kind = 0) {
   return 1024 + gemm_stages(v, mx_kind) * (16384 + (v.block_n / v.cg) * 128 + gemm_sf_stage_bytes(v, mx_kind)) + 1024 + 16384;
@@ -844,7 +848,7 @@ struct GemmProblem {
   uint64_t b_sk, b_sn, b_sb;
   uint64_t o_sm, o_sn, o_sb;
   // block-scaled (MX) problems: in_dtype is a 1-byte marker, K / a_sm / b_sn count BYTES of K-major packed operands
-  int mx_kind = 0;                 // 0 unscaled, 1 mxf8 (e4m3 / e5m2), 2 mxf4 (packed e2m1)
+  int mx_kind = 0;                 // 0 unscaled, 1 mxf8 (e4m3 / e5m2), 2 mxf4 (packed e2m1, ue8m0 / 32), 3 nvfp4 (packed e2m1, ue4m3 / 16)
   uint32_t fmt_a = 0, fmt_b = 0;   // instruction-descriptor operand formats
   uint64_t sfa = 0, sfb = 0;       // packed scale tensors [batch * tiles][atoms][512 B]
   uint64_t sf_atoms = 0;           // 4-scale atoms along K
@@ -887,7 +891,7 @@ static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out);
 
 static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
   const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
-  const char* in_tag = g.mx_kind == 1 ? "mxf8" : g.mx_kind == 2 ? "mxf4"
+  const char* in_tag = g.mx_kind == 1 ? "mxf8" : g.mx_kind == 2 ? "mxf4" : g.mx_kind == 3 ? "nvf4"
                        : g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
                        : g.in_dtype == B200_F8E5M2 ? "e5m2" : g.in_dtype == B200_U8 ? "u8" : g.in_dtype == B200_I8 ? "s8" : "tf32";
   const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : g.out_dtype == B200_I32 ? "i32" : "f32";
@@ -969,10 +973,10 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     const uint64_t tiles_a = (g.M + 127) / 128, tiles_b = (g.N + 127) / 128;
     const uint64_t ab = a_bcast ? 1 : g.batch, bb = b_bcast ? 1 : g.batch;
     rc = encode_tmap(c, &ta_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfa, 16, 32 * g.sf_atoms, tiles_a * ab, 16, 512 * g.sf_atoms,
-                     16, 32 * g.mx_kind, CU_TENSOR_MAP_SWIZZLE_NONE, 1);
+                     16, 32 * mx_atoms(g.mx_kind), CU_TENSOR_MAP_SWIZZLE_NONE, 1);
     if (rc) return rc;
     rc = encode_tmap(c, &tb_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfb, 16, 32 * g.sf_atoms, tiles_b * bb, 16, 512 * g.sf_atoms,
-                     16, 32 * g.mx_kind, CU_TENSOR_MAP_SWIZZLE_NONE, v.block_n / 128);
+                     16, 32 * mx_atoms(g.mx_kind), CU_TENSOR_MAP_SWIZZLE_NONE, v.block_n / 128);
     if (rc) return rc;
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
@@ -1181,11 +1185,11 @@ extern "C" int b200_matmul_fused(b200_ctx* c, b200_stream s, b200_dtype in_dtype
 
 // ------------------------------------------------------------------------------------------------ block-scaled matmul
 static int launch_pack_scales(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uint64_t batch, uint64_t rows,
-                              uint64_t n_scales, uint64_t tiles, uint64_t atoms) {
+                              uint64_t n_scales, uint64_t tiles, uint64_t atoms, uint32_t pad_value) {
   CUfunction f;
   int rc = get_func(c, "pack_scales", &f);
   if (rc) return rc;
-  PackScalesParams p{in, out, (uint32_t)batch, (uint32_t)rows, (uint32_t)n_scales, (uint32_t)tiles, (uint32_t)atoms, 0};
+  PackScalesParams p{in, out, (uint32_t)batch, (uint32_t)rows, (uint32_t)n_scales, (uint32_t)tiles, (uint32_t)atoms, pad_value};
   const uint64_t words = batch * tiles * atoms * 128;
   const unsigned grid = (unsigned)std::min<uint64_t>((words + 255) / 256, (uint64_t)c->props.num_sms * 8);
   void* args[] = {&p};
@@ -1202,13 +1206,16 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
     return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: operands must be fp8 (e4m3/e5m2, mixable) or both packed e2m1");
   if (out_dtype != B200_F32 && out_dtype != B200_BF16 && out_dtype != B200_F16)
     return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: output must be f32, bf16 or f16");
-  if (scale_block != 32) return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: scale block %d (ue8m0 scales cover 32 elements of K)", scale_block);
-  if (K == 0 || K % 32) return fail(B200_ERR_INVALID_ARG, "matmul_scaled: K = %llu must be a positive multiple of the scale block", (unsigned long long)K);
+  // scale_block 32: ue8m0 scales (MXFP8 / MXFP4); scale_block 16: ue4m3 scales, packed e2m1 operands only (NVFP4)
+  const bool nvf4 = (scale_block == 16);
+  if (scale_block != 32 && !(nvf4 && fp4))
+    return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: scale block %d (32 = ue8m0 scales; 16 = ue4m3 scales, packed e2m1 operands only)", scale_block);
+  if (K == 0 || K % 32) return fail(B200_ERR_INVALID_ARG, "matmul_scaled: K = %llu must be a positive multiple of 32", (unsigned long long)K);
   if (batch == 0 || M == 0 || N == 0) return B200_OK;
   if (!lhs || !rhs || !lhs_scales || !rhs_scales || !out) return fail(B200_ERR_INVALID_ARG, "matmul_scaled: null device pointer");
   if (M >= (1ull << 31) || N >= (1ull << 31) || K >= (1ull << 31) || batch >= (1ull << 20)) return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: extent too large");
   CUstream st = resolve_stream(c, s);
-  const uint64_t n_scales = K / 32, atoms = (n_scales + 3) / 4;
+  const uint64_t n_scales = K / scale_block, atoms = (n_scales + 3) / 4;
   const uint64_t k_bytes = fp4 ? K / 2 : K;
   const size_t osz = dtype_size(out_dtype);
   const std::string forced = opt(c, "gemm.variant", "auto");
@@ -1221,7 +1228,7 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
     int rc = get_func(c, "gemm_scaled_simt", &f);
     if (rc) return rc;
     ScaledSimtParams p{lhs, rhs, lhs_scales, rhs_scales, out, (uint32_t)batch, (uint32_t)M, (uint32_t)N, (uint32_t)K,
-                       (uint32_t)lhs_dtype, (uint32_t)rhs_dtype, (uint32_t)out_dtype, 32u, 1u, 1u, 0u, 0u};
+                       (uint32_t)lhs_dtype, (uint32_t)rhs_dtype, (uint32_t)out_dtype, (uint32_t)scale_block, 1u, 1u, nvf4 ? 1u : 0u, 0u};
     const uint64_t total = batch * M * N;
     const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->props.num_sms * 16);
     void* args[] = {&p};
@@ -1237,8 +1244,9 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
     if (rc) return rc;
     rc = pool_alloc(c, batch * tiles_b * atoms * 512, &sfb, st);
     if (rc) { pool_free(c, sfa, st); return rc; }
-    rc = launch_pack_scales(c, st, lhs_scales, sfa, batch, M, n_scales, tiles_a, atoms);
-    if (!rc) rc = launch_pack_scales(c, st, rhs_scales, sfb, batch, N, n_scales, tiles_b, atoms);
+    const uint32_t one = nvf4 ? 0x38u : 127u;
+    rc = launch_pack_scales(c, st, lhs_scales, sfa, batch, M, n_scales, tiles_a, atoms, one);
+    if (!rc) rc = launch_pack_scales(c, st, rhs_scales, sfb, batch, N, n_scales, tiles_b, atoms, one);
   }
   if (!rc) {
     GemmProblem g{};
@@ -1249,7 +1257,7 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
     g.a_sm = k_bytes; g.a_sk = 1; g.a_sb = batch > 1 ? M * k_bytes : 0;
     g.b_sn = k_bytes; g.b_sk = 1; g.b_sb = batch > 1 ? N * k_bytes : 0;
     g.o_sm = N; g.o_sn = 1; g.o_sb = batch > 1 ? M * N : 0;
-    g.mx_kind = fp4 ? 2 : 1;
+    g.mx_kind = nvf4 ? 3 : fp4 ? 2 : 1;
     g.fmt_a = fp4 ? 1u : (lhs_dtype == B200_F8E5M2 ? 1u : 0u);
     g.fmt_b = fp4 ? 1u : (rhs_dtype == B200_F8E5M2 ? 1u : 0u);
     g.sfa = sfa; g.sfb = sfb; g.sf_atoms = atoms;

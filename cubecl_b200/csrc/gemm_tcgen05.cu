@@ -48,7 +48,8 @@ struct GemmParams {
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6,
              KIND_MXF8 = 7,    // kind::mxf8f6f4.block_scale: e4m3 / e5m2 operands (chosen at run time), ue8m0 scale per 32 K
-             KIND_MXF4 = 8 };  // kind::mxf4.block_scale: packed e2m1 operands (K counted in BYTES by this kernel), ue8m0 per 32 K
+             KIND_MXF4 = 8,    // kind::mxf4.block_scale: packed e2m1 operands (K counted in BYTES by this kernel), ue8m0 per 32 K
+             KIND_NVF4 = 9 };  // kind::mxf4nvf4.block_scale.scale_vec::4X: packed e2m1, ue4m3 scale per 16 K (NVFP4)
 enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };  // OUT_F32 is a raw 32-bit store: it also carries the s32 accumulators of kind::i8
 
 constexpr int kNumThreads = 256;  // warps 0 and 3 TMA producers, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
@@ -141,6 +142,7 @@ __device__ __forceinline__ WorkUnit unit_decode(uint32_t u, const GemmParams& p,
 // the word is scale s) right before the four MMAs that consume them; tcgen05.cp and tcgen05.mma execute in issue order, so
 // one TMEM scale buffer suffices.  kind::mxf8f6f4: one chunk per k-block, MMA k uses byte k.  kind::mxf4: K = 64 elements
 // per MMA and two scales per row per MMA -> two chunks per k-block, MMA k uses chunk k / 2, bytes 2 (k % 2) and +1.
+// kind::mxf4nvf4 (NVFP4): a scale per 16 elements -> four scales per row per MMA, four chunks per k-block, MMA k uses chunk k.
 // ACC = accumulator stages in TMEM: 256-wide scaled tiles have room for one only (512 columns - scale columns).
 template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES, int ACC = 2>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUtensorMap* tma_b_hi, const CUtensorMap* tma_a_lo,
@@ -148,7 +150,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   constexpr bool SCALED = (KIND >= KIND_MXF8);
   constexpr bool INT_ACC = (KIND == KIND_U8 || KIND == KIND_S8);
   static_assert(!SCALED || (!A_MN && !B_MN && BLOCK_N % 128 == 0), "block-scaled kinds: K-major operands, 128-row scale tiles");
-  constexpr int SF_ATOMS = !SCALED ? 0 : (KIND == KIND_MXF4) ? 2 : 1;  // 512-byte scale chunks per 128 rows per k-block
+  constexpr int SF_ATOMS = !SCALED ? 0 : (KIND == KIND_NVF4) ? 4 : (KIND == KIND_MXF4) ? 2 : 1;  // 512-byte scale chunks per 128 rows per k-block
   constexpr int SF_TILES_B = BLOCK_N / 128;
   constexpr uint32_t SFA_BYTES = 512u * SF_ATOMS, SFB_BYTES = 512u * SF_ATOMS * SF_TILES_B;
   constexpr uint32_t SF_BYTES = (SFA_BYTES + SFB_BYTES + 1023u) / 1024u * 1024u;
@@ -334,12 +336,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
               for (int atom = 0; atom < SF_ATOMS; ++atom)
                 tmem_cp_32x128b_warpx4<CG>(sf_t + SFB_COL + 4u * (atom * SF_TILES_B + tile),
                                            make_smem_desc(sfb_s + 512u * (tile * SF_ATOMS + atom), 0, 128, 0));
-            const uint32_t idesc_base = make_idesc_scaled(p.sf_fmt_a, p.sf_fmt_b, UMMA_M, BLOCK_N);
+            const uint32_t idesc_base = make_idesc_scaled(p.sf_fmt_a, p.sf_fmt_b, UMMA_M, BLOCK_N, KIND == KIND_NVF4 ? 0u : 1u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint32_t atom = (KIND == KIND_MXF4) ? k / 2 : 0;
-              const uint32_t sf_id = (KIND == KIND_MXF4) ? (k & 1) * 2 : k;
-              umma_ss_scaled<CG, (KIND == KIND_MXF4) ? 1 : 0>(d_tmem, a_desc + 2 * k, b_desc + 2 * k,
+              const uint32_t atom = (KIND == KIND_NVF4) ? k : (KIND == KIND_MXF4) ? k / 2 : 0;
+              const uint32_t sf_id = (KIND == KIND_NVF4) ? 0 : (KIND == KIND_MXF4) ? (k & 1) * 2 : k;
+              umma_ss_scaled<CG, (KIND == KIND_NVF4) ? 2 : (KIND == KIND_MXF4) ? 1 : 0>(d_tmem, a_desc + 2 * k, b_desc + 2 * k,
                                                               idesc_base | (sf_id << 29) | (sf_id << 4), sf_t + SFA_COL + 4u * atom,
                                                               sf_t + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
@@ -663,6 +665,14 @@ GEMM_KERNEL_ACC(gemm_mxf4_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT
 GEMM_KERNEL_ACC(gemm_mxf4_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F16, 5, 1)
 GEMM_MX(2sm_n128, 2, 128, 8, 2)
 GEMM_MX(1sm_n128, 1, 128, 6, 2)
+// NVFP4: four scale chunks per 128 rows per k-block (6 KB / 4 KB of scales per stage)
+#define GEMM_NVF4(TILE, CG, BN, STAGES, ACC)                                                          \
+  GEMM_KERNEL_ACC(gemm_nvf4_f32_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_F32, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_nvf4_bf16_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_BF16, STAGES, ACC) \
+  GEMM_KERNEL_ACC(gemm_nvf4_f16_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_F16, STAGES, ACC)
+GEMM_NVF4(2sm_n256, 2, 256, 5, 1)
+GEMM_NVF4(2sm_n128, 2, 128, 7, 2)
+GEMM_NVF4(1sm_n128, 1, 128, 5, 2)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/

@@ -218,7 +218,8 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
 // Block-scaled forms (MX formats): D[tmem] (+)= (A * SFA) * (B * SFB) with one scale per row per 32 K elements, the scale
 // factors read from TMEM.  MXKIND 0 = kind::mxf8f6f4 (K = 32 per instruction, one scale per row: byte `sf_id` of the
 // 32-bit TMEM word, selected in the instruction descriptor), 1 = kind::mxf4 with scale_vec::2X (packed e2m1, K = 64 per
-// instruction, two scales per row: bytes sf_id, sf_id + 1).
+// instruction, two scales per row: bytes sf_id, sf_id + 1), 2 = kind::mxf4nvf4 with scale_vec::4X (NVFP4: packed e2m1, K = 64,
+// four ue4m3 scales per row -- one per 16 elements -- the whole 32-bit word).
 #define B200_UMMA_SCALED_ASM(CGS, KINDS)                                                                          \
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                \
                "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(d_tmem), \
@@ -229,9 +230,12 @@ __device__ __forceinline__ void umma_ss_scaled(uint32_t d_tmem, uint64_t a_desc,
                                                uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
   if constexpr (MXKIND == 0) {
     if constexpr (CG == 1) B200_UMMA_SCALED_ASM("1", "mxf8f6f4.block_scale"); else B200_UMMA_SCALED_ASM("2", "mxf8f6f4.block_scale");
-  } else {
+  } else if constexpr (MXKIND == 1) {
     if constexpr (CG == 1) B200_UMMA_SCALED_ASM("1", "mxf4.block_scale.scale_vec::2X");
     else B200_UMMA_SCALED_ASM("2", "mxf4.block_scale.scale_vec::2X");
+  } else {
+    if constexpr (CG == 1) B200_UMMA_SCALED_ASM("1", "mxf4nvf4.block_scale.scale_vec::4X");
+    else B200_UMMA_SCALED_ASM("2", "mxf4nvf4.block_scale.scale_vec::4X");
   }
 }
 
@@ -245,11 +249,12 @@ __device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t 
     asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(smem_desc) : "memory");
 }
 
-// Instruction descriptor of the block-scaled kinds (f32 accumulate, K-major operands, ue8m0 scales); the scale-factor
-// byte ids (bits 29-30 for A, 4-5 for B) are OR-ed in per instruction.
-//   a_fmt/b_fmt: kind::mxf8f6f4 -> 0 = e4m3, 1 = e5m2; kind::mxf4 -> 1 = e2m1.
-__host__ __device__ constexpr uint32_t make_idesc_scaled(uint32_t a_fmt, uint32_t b_fmt, uint32_t umma_m, uint32_t umma_n) {
-  return (a_fmt << 7) | (b_fmt << 10) | ((umma_n >> 3) << 17) | (1u << 23) /* ue8m0 */ | ((umma_m >> 4) << 24);
+// Instruction descriptor of the block-scaled kinds (f32 accumulate, K-major operands); the scale-factor byte ids (bits
+// 29-30 for A, 4-5 for B) are OR-ed in per instruction.
+//   a_fmt/b_fmt: kind::mxf8f6f4 -> 0 = e4m3, 1 = e5m2; kind::mxf4 / mxf4nvf4 -> 1 = e2m1.  ue8m0: scale format bit (23).
+__host__ __device__ constexpr uint32_t make_idesc_scaled(uint32_t a_fmt, uint32_t b_fmt, uint32_t umma_m, uint32_t umma_n,
+                                                         uint32_t ue8m0 = 1) {
+  return (a_fmt << 7) | (b_fmt << 10) | ((umma_n >> 3) << 17) | (ue8m0 << 23) | ((umma_m >> 4) << 24);
 }
 
 // All previously issued tcgen05.mma of this thread arrive (once) on `bar` when they retire.

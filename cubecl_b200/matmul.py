@@ -94,6 +94,7 @@ def launch_scaled(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, l
     798-840) with the operand layout of test_cmma_scaled (runtime_tests/cmma.rs:1476-1593):
       lhs [.., M, K] and rhs [.., N, K], both K-contiguous, dtype f8e4m3 / f8e5m2 (mixable) or both f4e2m1x2 (shape [.., rows, K/2]
       bytes); scales ue8m0 [.., rows, K/32]; out [.., M, N] = sum_k (lhs * lhs_scale) * (rhs * rhs_scale), f32 accumulate.
+      scale_block=16 selects NVFP4: f4e2m1x2 operands with f8e4m3 scale bytes [.., rows, K/16] (sign ignored).
     Errors are deferred to client.sync() like every launch."""
     try:
         fp4 = lhs.dtype == "f4e2m1x2"
@@ -113,8 +114,9 @@ def launch_scaled(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, l
             raise B200Error(6, f"matmul_scaled: out shape {out.shape} != {list(lhs.shape[:-2]) + [M, N]}")
         if not scales_packed:
             for t, rows in ((lhs_scales, M), (rhs_scales, N)):
-                if list(t.shape) != list(lhs.shape[:-2]) + [rows, K // scale_block] or t.dtype != "ue8m0":
-                    raise B200Error(6, "matmul_scaled: scales must be ue8m0 [.., rows, K / scale_block]")
+                want = "f8e4m3" if scale_block == 16 else "ue8m0"      # NVFP4 scales are e4m3 bytes (sign ignored)
+                if list(t.shape) != list(lhs.shape[:-2]) + [rows, K // scale_block] or t.dtype != want:
+                    raise B200Error(6, f"matmul_scaled: scales must be {want} [.., rows, K / scale_block]")
         _ffi.check(client._lib.b200_matmul_scaled(
             client._ctx, stream, DTYPES[lhs.dtype], DTYPES[rhs.dtype], DTYPES[out.dtype],
             C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(lhs_scales.handle.ptr),

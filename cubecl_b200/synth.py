@@ -130,13 +130,13 @@ def ue8m0_to_f32(bits: np.ndarray) -> np.ndarray:
     return np.where(b == 255, np.nan, np.ldexp(1.0, b - 127)).astype(np.float32)
 
 
-def pack_scale_chunks(scales: np.ndarray) -> np.ndarray:
-    """[rows, n_scales] ue8m0 -> the tensor core's packed chunks [ceil(rows/128)][ceil(n_scales/4)][512]:
-    byte (r % 32) * 16 + (r / 32) * 4 + s; padding = 127 (1.0).  Host mirror of the pack_scales kernel."""
+def pack_scale_chunks(scales: np.ndarray, pad: int = 127) -> np.ndarray:
+    """[rows, n_scales] scale bytes -> the tensor core's packed chunks [ceil(rows/128)][ceil(n_scales/4)][512]:
+    byte (r % 32) * 16 + (r / 32) * 4 + s; padding = 1.0 (127 for ue8m0, 0x38 for ue4m3).  Host mirror of the pack_scales kernel."""
     scales = np.asarray(scales, dtype=np.uint8)
     rows, ns = scales.shape
     tiles, atoms = (rows + 127) // 128, (ns + 3) // 4
-    padded = np.full((tiles * 128, atoms * 4), 127, dtype=np.uint8)
+    padded = np.full((tiles * 128, atoms * 4), pad, dtype=np.uint8)
     padded[:rows, :ns] = scales
     v = padded.reshape(tiles, 4, 32, atoms, 4)          # [tile][g = r/32][r%32][atom][s]
     return np.ascontiguousarray(v.transpose(0, 3, 2, 1, 4)).reshape(tiles, atoms, 512)   # [tile][atom][r%32][g][s]

@@ -163,7 +163,9 @@ int b200_matmul_fused(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dt
  * B200_F8E5M2 (mixable) or both B200_F4E2M1X2 (k / 2 bytes per row); scales are B200_UE8M0 bytes [batch, rows, k / 32]
  * row-major (scales_packed = 0) or already in the tensor core's packed form [batch * ceil(rows/128)][ceil(k/128)][512 B],
  * byte (r % 32) * 16 + (r / 32) * 4 + s (scales_packed = 1).  out [batch, m, n] contiguous, f32 / bf16 / f16.
- * scale_block must be 32 and k a multiple of it.  Operands that TMA cannot describe take the reference-order SIMT path. */
+ * scale_block = 32: ue8m0 scales (MXFP8 / MXFP4).  scale_block = 16: NVFP4 -- packed e2m1 operands with e4m3 scale bytes
+ * [batch, rows, k / 16] whose sign is ignored (the third ScaledMmaConfig row of manual.rs:241-250; kind::mxf4nvf4).
+ * k must be a multiple of 32.  Operands that TMA cannot describe take the reference-order SIMT path. */
 int b200_matmul_scaled(b200_ctx* ctx, b200_stream stream, b200_dtype lhs_dtype, b200_dtype rhs_dtype, b200_dtype out_dtype,
                        b200_dptr lhs, b200_dptr rhs, b200_dptr lhs_scales, b200_dptr rhs_scales, b200_dptr out,
                        uint64_t batch, uint64_t m, uint64_t n, uint64_t k, int scale_block, int scales_packed);

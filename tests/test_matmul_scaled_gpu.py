@@ -28,17 +28,19 @@ def quantise(vals, dtype):
     return bits, synth.fp8_bits_to_f32(bits, dtype)
 
 
-def run_scaled(client, a_dev, b_dev, sa_bits, sb_bits, lhs_dtype, rhs_dtype, out_dtype, packed=False):
+def run_scaled(client, a_dev, b_dev, sa_bits, sb_bits, lhs_dtype, rhs_dtype, out_dtype, packed=False, scale_block=32):
     lhs, rhs = TensorHandle.from_numpy(client, a_dev, lhs_dtype), TensorHandle.from_numpy(client, b_dev, rhs_dtype)
+    one = 0x38 if scale_block == 16 else 127
     if packed:
-        sa = np.stack([synth.pack_scale_chunks(x) for x in sa_bits.reshape(-1, *sa_bits.shape[-2:])])
-        sb = np.stack([synth.pack_scale_chunks(x) for x in sb_bits.reshape(-1, *sb_bits.shape[-2:])])
+        sa = np.stack([synth.pack_scale_chunks(x, one) for x in sa_bits.reshape(-1, *sa_bits.shape[-2:])])
+        sb = np.stack([synth.pack_scale_chunks(x, one) for x in sb_bits.reshape(-1, *sb_bits.shape[-2:])])
     else:
         sa, sb = sa_bits, sb_bits
-    ls, rs = TensorHandle.from_numpy(client, sa, "ue8m0"), TensorHandle.from_numpy(client, sb, "ue8m0")
+    sdt = "f8e4m3" if scale_block == 16 else "ue8m0"
+    ls, rs = TensorHandle.from_numpy(client, sa, sdt), TensorHandle.from_numpy(client, sb, sdt)
     shape = list(a_dev.shape[:-2]) + [a_dev.shape[-2], b_dev.shape[-2]]
     out = TensorHandle.empty_contiguous(client, shape, out_dtype)
-    matmul.launch_scaled(client, lhs, rhs, ls, rs, out, scales_packed=packed)
+    matmul.launch_scaled(client, lhs, rhs, ls, rs, out, scales_packed=packed, scale_block=scale_block)
     client.sync()
     return synth.from_device_dtype(out.to_numpy(client), out_dtype).reshape(shape)
 
@@ -138,6 +140,51 @@ def test_prepacked_scales_and_batches(client, dtype):
     assert np.array_equal(plain, packed)
     for i in range(batch[0]):
         check(plain[i], a[i], b[i], sa[i], sb[i], 2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ NVFP4 (ue4m3 scale per 16)
+def nvfp4_problem(M, N, K, seed, batch=()):
+    """packed e2m1 operands + e4m3 scale bytes per 16 elements; some scale bytes carry a sign bit, which the hardware ignores
+    (third ScaledMmaConfig row, crates/cubecl-cpp/src/cuda/mma/manual.rs:240-250: "Sign of scales is ignored")"""
+    rng = np.random.default_rng(seed)
+    a_dev, a = quantise(rng.uniform(-6, 6, size=batch + (M, K)).astype(np.float32), "f4e2m1x2")
+    b_dev, b = quantise(rng.uniform(-6, 6, size=batch + (N, K)).astype(np.float32), "f4e2m1x2")
+    sa = synth.f32_to_fp8_bits(rng.uniform(0.05, 8.0, size=batch + (M, K // 16)).astype(np.float32), "f8e4m3")
+    sb = synth.f32_to_fp8_bits(rng.uniform(0.05, 8.0, size=batch + (N, K // 16)).astype(np.float32), "f8e4m3")
+    sa[..., 0::7] |= 0x80
+    sb[..., 0::5] |= 0x80
+    return a_dev, a, b_dev, b, sa, sb
+
+
+def check_nvfp4(got, a, b, sa, sb, tol):
+    fa, fb = np.abs(synth.fp8_bits_to_f32(sa, "f8e4m3")), np.abs(synth.fp8_bits_to_f32(sb, "f8e4m3"))
+    o32, f64, fabs = oracle.matmul_scaled(a, b, fa, fb, 16)
+    err = np.max(np.abs(got.astype(np.float64) - f64) / np.maximum(fabs, 1e-30))
+    assert err <= tol, f"max |gpu - f64| / sum|terms| = {err:.3e} > {tol:.1e}"
+    return o32
+
+
+@pytest.mark.parametrize("variant", ["simt"] + TC_VARIANTS)
+@pytest.mark.parametrize("out_dtype,tol", [("f32", 2e-6), ("bf16", 1e-2)])
+@pytest.mark.parametrize("M,N,K", [(16, 8, 64), (300, 520, 1024), (128, 256, 96), (257, 129, 2048)])
+def test_parity_nvfp4(client, variant, out_dtype, tol, M, N, K):
+    # (16, 8, 64) with four scales per row is the shape of the reference's e2m1x2 / E4M3-scale feature row (k 64, factor 4)
+    client.set_option("gemm.variant", variant)
+    a_dev, a, b_dev, b, sa, sb = nvfp4_problem(M, N, K, seed=M + N + K)
+    got = run_scaled(client, a_dev, b_dev, sa, sb, "f4e2m1x2", "f4e2m1x2", out_dtype, scale_block=16)
+    o32 = check_nvfp4(got, a, b, sa, sb, tol)
+    if variant == "simt" and out_dtype == "f32":
+        assert np.array_equal(got, o32)              # reference-order loop, bit for bit
+
+
+def test_nvfp4_prepacked_scales_and_batches(client):
+    batch, M, N, K = (2,), 200, 136, 384
+    a_dev, a, b_dev, b, sa, sb = nvfp4_problem(M, N, K, seed=13, batch=batch)
+    plain = run_scaled(client, a_dev, b_dev, sa, sb, "f4e2m1x2", "f4e2m1x2", "f32", scale_block=16)
+    packed = run_scaled(client, a_dev, b_dev, sa, sb, "f4e2m1x2", "f4e2m1x2", "f32", packed=True, scale_block=16)
+    assert np.array_equal(plain, packed)
+    for i in range(batch[0]):
+        check_nvfp4(plain[i], a[i], b[i], sa[i], sb[i], 2e-6)
 
 
 def test_split_k_tail_on_scaled_problem(client):

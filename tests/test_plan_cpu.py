@@ -146,6 +146,9 @@ def test_block_scaled_plans(plan):
     assert rc == 0 and "gemm_mxf4_f32_" in t
     assert "tmap esz=1 dims=(4096,4096,2) strides=(4096,16777216) box=(128,128) swizzle=3" in t
     assert "box=(16,64) swizzle=0" in t and "box=(16,64,2) swizzle=0" in t   # two chunks per k-block (256 elements of K)
+    rc, t = plan.matmul_scaled(FP4, FP4, BF16, 1, 8192, 8192, 8192, block=16)   # NVFP4: four chunks per k-block, 5 stages of 38 KB
+    assert rc == 0 and "gemm_nvf4_bf16_2sm_n256_kk" in t and "box=(16,128,2) swizzle=0" in t and "smem=212992 cluster=2" in t
+    assert t.count(f"alloc {64 * 128 * 512}") == 2                          # 64 row tiles x 128 k-atoms (K / 16 / 4) x 512 B
     rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 16, 8, 32)               # the reference's m16 n8 k32 test shape
     assert rc == 0 and "gemm_mxf8_f32_1sm_n128_kk" in t
     rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 64, 64, 128, packed=1)   # caller-packed scales: no packing pass

@@ -104,6 +104,10 @@ if "scaled" in what:
             ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, sa, sb, o), iters=10, warm=2) for _ in range(3))
             msp = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scales_packed=True), iters=10, warm=2) for _ in range(3))
             print(f"  {dt:9s} {n}x{n}x{k} {variant}: {ms * 1e3:8.1f} us {flops / ms / 1e9:7.0f} TF/s | pre-packed scales {msp * 1e3:8.1f} us {flops / msp / 1e9:7.0f} TF/s", flush=True)
+        if dt == "f4e2m1x2":
+            s16 = TensorHandle.from_numpy(c, np.full((n, k // 16), 0x38, np.uint8), "f8e4m3")
+            ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, s16, s16, o, scale_block=16), iters=10, warm=2) for _ in range(3))
+            print(f"  nvfp4     {n}x{n}x{k} auto    : {ms * 1e3:8.1f} us {flops / ms / 1e9:7.0f} TF/s (ue4m3 scale per 16, packing included)", flush=True)
         c.set_option("gemm.variant", "auto")
         del a, b, o
 
