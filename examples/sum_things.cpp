@@ -2,6 +2,7 @@
 // [-1, 10, 1, 5] demo plus the cmma.rs:552-576 golden matmul, every number computed on the GPU through the C ABI.
 // Build: g++ -std=c++17 -Iinclude examples/sum_things.cpp -Lcubecl_b200/lib -lcubecl_b200 -Wl,-rpath,$PWD/cubecl_b200/lib
 // Exit code 0 = all checks passed (used by tests/test_cpp_host_gpu.py on the GPU box).
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -44,6 +45,24 @@ int main() {
       for (int n = 0; n < 16; ++n)
         if (cf[r * 16 + n] != 504.f + 896.f * r) { std::printf("golden mismatch at %d,%d: %g\n", r, n, cf[r * 16 + n]); return 3; }
     std::printf("cmma golden ok (row r = 504 + 896 r)\n");
+
+    // block-scaled matmul: e4m3 ones [32, 64] x [16, 64], row scales 2^(i % 4), column scales 2^-(j % 3), one per 32 K
+    // -> out[i, j] = 64 * 2^(i % 4 - j % 3), exact (MmaDefinition::execute_scaled semantics, frontend/cmma.rs:798-840)
+    std::vector<uint8_t> ones(32 * 64, 0x38), sa(32 * 2), sb(16 * 2);
+    for (int i = 0; i < 32; ++i) sa[2 * i] = sa[2 * i + 1] = static_cast<uint8_t>(127 + i % 4);
+    for (int j = 0; j < 16; ++j) sb[2 * j] = sb[2 * j + 1] = static_cast<uint8_t>(127 - j % 3);
+    TensorHandle ml = TensorHandle::new_contiguous({32, 64}, client.create_from_slice(ones.data(), 32 * 64), DType::F8E4M3);
+    TensorHandle mr = TensorHandle::new_contiguous({16, 64}, client.create_from_slice(ones.data(), 16 * 64), DType::F8E4M3);
+    TensorHandle ms_a = TensorHandle::new_contiguous({32, 2}, client.create_from_slice(sa.data(), sa.size()), DType::UE8M0);
+    TensorHandle ms_b = TensorHandle::new_contiguous({16, 2}, client.create_from_slice(sb.data(), sb.size()), DType::UE8M0);
+    TensorHandle mo = TensorHandle::empty(client, {32, 16}, DType::F32);
+    matmul::launch_scaled(client, ml, mr, ms_a, ms_b, mo);
+    auto mb = client.read_one(mo.handle);
+    const float* mf = reinterpret_cast<const float*>(mb.data());
+    for (int i = 0; i < 32; ++i)
+      for (int j = 0; j < 16; ++j)
+        if (mf[i * 16 + j] != std::ldexp(64.f, i % 4 - j % 3)) { std::printf("scaled mismatch at %d,%d: %g\n", i, j, mf[i * 16 + j]); return 5; }
+    std::printf("block-scaled matmul ok (out[i,j] = 64 * 2^(i%%4 - j%%3))\n");
 
     // deferred errors: inner dims differ -> nothing thrown at launch, ServerError at sync
     TensorHandle bad = TensorHandle::empty(client, {24, 16}, DType::F16);

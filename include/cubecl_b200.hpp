@@ -32,8 +32,17 @@ struct MatmulShapeError : std::invalid_argument {
   using std::invalid_argument::invalid_argument;
 };
 
-enum class DType : int { F32 = B200_F32, F16 = B200_F16, BF16 = B200_BF16, U32 = B200_U32 };
-inline size_t dtype_size(DType d) { return (d == DType::F16 || d == DType::BF16) ? 2 : 4; }
+enum class DType : int { F32 = B200_F32, F16 = B200_F16, BF16 = B200_BF16, U32 = B200_U32, U8 = B200_U8, I8 = B200_I8,
+                         F8E4M3 = B200_F8E4M3, F8E5M2 = B200_F8E5M2,
+                         F4E2M1X2 = B200_F4E2M1X2,  // one element = one byte holding two e2m1 values
+                         UE8M0 = B200_UE8M0 };
+inline size_t dtype_size(DType d) {
+  switch (d) {
+    case DType::F16: case DType::BF16: return 2;
+    case DType::F32: case DType::U32: return 4;
+    default: return 1;
+  }
+}
 
 using Shape = std::vector<uint64_t>;
 using Strides = std::vector<uint64_t>;
@@ -180,6 +189,25 @@ inline void launch(ComputeClient& client, const TensorHandle& lhs, const TensorH
   const int rc = b200_matmul(client.raw(), nullptr, static_cast<b200_dtype>(lhs.dtype), static_cast<b200_dtype>(out.dtype),
                              lhs.handle.ptr(), rhs.handle.ptr(), out.handle.ptr(), rank, lhs.shape.data(), lhs.strides.data(),
                              rhs.shape.data(), rhs.strides.data(), out.shape.data(), out.strides.data());
+  if (rc != B200_OK) client.defer(b200_last_error());
+}
+/// Block-scaled (MX) matmul, the GEMM-level form of MmaDefinition::new_scaled / execute_scaled
+/// (crates/cubecl-core/src/frontend/cmma.rs:438-460, 798-840): lhs [.., M, K] and rhs [.., N, K] K-contiguous (fp8, or both
+/// F4E2M1X2 with K/2 bytes per row), scales [.., rows, K/scale_block] (UE8M0 for block 32; e4m3 bytes for NVFP4, block 16).
+inline void launch_scaled(ComputeClient& client, const TensorHandle& lhs, const TensorHandle& rhs, const TensorHandle& lhs_scales,
+                          const TensorHandle& rhs_scales, const TensorHandle& out, int scale_block = 32, bool scales_packed = false) {
+  const size_t r = lhs.shape.size();
+  if (r < 2 || rhs.shape.size() != r || out.shape.size() != r || lhs.shape[r - 1] != rhs.shape[r - 1]) {
+    client.defer("InvalidArgument: matmul_scaled needs lhs [..,M,K] and rhs [..,N,K] of equal rank and K");
+    return;
+  }
+  uint64_t batch = 1;
+  for (size_t i = 0; i + 2 < r; ++i) batch *= lhs.shape[i];
+  const uint64_t k = lhs.shape[r - 1] * (lhs.dtype == DType::F4E2M1X2 ? 2 : 1);
+  const int rc = b200_matmul_scaled(client.raw(), nullptr, static_cast<b200_dtype>(lhs.dtype), static_cast<b200_dtype>(rhs.dtype),
+                                    static_cast<b200_dtype>(out.dtype), lhs.handle.ptr(), rhs.handle.ptr(), lhs_scales.handle.ptr(),
+                                    rhs_scales.handle.ptr(), out.handle.ptr(), batch, lhs.shape[r - 2], rhs.shape[r - 2], k, scale_block,
+                                    scales_packed ? 1 : 0);
   if (rc != B200_OK) client.defer(b200_last_error());
 }
 }  // namespace matmul

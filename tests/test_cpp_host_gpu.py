@@ -19,3 +19,4 @@ def test_cpp_host_layer_end_to_end():
     r = subprocess.run([str(EXE)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "[15, 15, 15, 15]" in r.stdout and "cmma golden ok" in r.stdout and "deferred error surfaced" in r.stdout
+    assert "block-scaled matmul ok" in r.stdout

@@ -38,9 +38,15 @@ lines = [f"# ncu --set full summaries, round {tag} (source reports: gpurun_out/{
 extra = [(p.stem[len(tag) + 1:], None) for p in sorted(OUT.glob(f"{tag}_x_*.ncu-rep"))]
 for name, key in [("gemm", "gemm_bf16_8192_dram_bytes"), ("reduce", "reduce_sum_2p28_dram_bytes")] + extra:
     rep = OUT / f"{tag}_{name}.ncu-rep"
-    if not rep.exists():
+    csv_export = OUT / f"{tag}_{name}.csv"     # `ncu -i rep --page raw --csv` run on the GPU box (the .ncu-rep embeds the whole cubin)
+    if rep.exists():
+        records = raw(rep)
+    elif csv_export.exists():
+        rows = list(csv.reader(csv_export.open()))
+        records = [{h: (u, v) for h, u, v in zip(rows[0], rows[1], r)} for r in rows[2:]] if len(rows) >= 3 else []
+    else:
         continue
-    for d in raw(rep):
+    for d in records[-1:]:
         kname = d.get("Kernel Name", ("", "?"))[1]
         lines.append(f"\n## {name}: {kname}\n")
         for k in KEYS:
