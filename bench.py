@@ -20,6 +20,7 @@ host cores, on a bounded sample of the same workload; rank 0 only.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -57,6 +58,30 @@ def ncu_traffic():
 
 
 # ---------------------------------------------------------------------------------------------------- clocks
+@contextlib.contextmanager
+def near_gpu(index: int):
+    """While pinned host buffers are allocated, run on the CPUs NVML reports as local to GPU `index`: the pages are placed on
+    that NUMA node (first touch at pin time), so the per-step H2D / D2H copies do not cross the socket interconnect.
+    One process per GPU, each next to its own device.  Restores the affinity afterwards; a no-op if NVML cannot tell."""
+    old = None
+    try:
+        nv, h = ClockSampler._handle(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {i * 64 + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed and os.environ.get("B200_BENCH_NUMA", "1") != "0":
+            old = allowed
+            os.sched_setaffinity(0, cpus & allowed)
+    except Exception:  # noqa: BLE001
+        old = None
+    try:
+        yield
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
+
+
 class ClockSampler:
     """Samples SM clock / power / throttle reasons through NVML from a thread DURING the timed region (the recipe's
     nvidia-smi line needs ~100 ms per sample; a 20-step timed region lasts ~15 ms)."""
@@ -310,8 +335,9 @@ def main():
 
     # ------------------------------------------------------------------ e2e: host buffers through the public API
     nbytes = N_MM * N_MM * 2
-    hab, hc = c.host_alloc(2 * nbytes), c.host_alloc(nbytes)     # A|B contiguous in pinned memory: one H2D per step
-    hab.view(np.uint16)[:] = 0x3F80  # 1.0 in bf16 (contents do not change the work)
+    with near_gpu(e.local_rank):
+        hab, hc = c.host_alloc(2 * nbytes), c.host_alloc(nbytes)     # A|B contiguous in pinned memory: one H2D per step
+        hab.view(np.uint16)[:] = 0x3F80  # 1.0 in bf16 (contents do not change the work)
 
     # Pipelined through the public multi-stream API: H2D of step i+1 | matmul of step i | D2H of step i-1 run on three
     # streams over two device slots, ordered by events; every step still copies both operands in and the result out.
@@ -439,8 +465,9 @@ def main():
         red["value"] = gbs
     # reduce e2e at N=1 (1 GiB pinned H2D + 4 B D2H)
     if world == 1 and not args.quick:
-        hx = c.host_alloc(BYTES_RED)
-        hr = c.host_alloc(4)
+        with near_gpu(e.local_rank):
+            hx = c.host_alloc(BYTES_RED)
+            hr = c.host_alloc(4)
         hx.view(np.float32)[:] = 1.0
 
         def red_e2e():

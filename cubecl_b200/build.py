@@ -23,7 +23,9 @@ BUILD = PKG / "build"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libcubecl_b200.so"
 
-CUBINS = {"gemm": "gemm_tcgen05.cu", "reduce": "reduce.cu", "aux": "aux_kernels.cu"}
+# tag -> (source, extra nvcc flags); the GEMM source is split in two cubins so the halves compile in parallel
+CUBINS = {"gemm": ("gemm_tcgen05.cu", ["-DGEMM_PART=0"]), "gemm_mx": ("gemm_tcgen05.cu", ["-DGEMM_PART=1"]),
+          "reduce": ("reduce.cu", []), "aux": ("aux_kernels.cu", [])}
 NVCC_FLAGS = ["-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"]
 
 
@@ -67,12 +69,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB
     nvcc = _nvcc()
-    for tag, src in CUBINS.items():
-        out = BUILD / f"{tag}.cubin"
-        log = _run([nvcc, *NVCC_FLAGS, "-Xptxas", "-v", str(CSRC / src), "-o", str(out)])
+
+    def compile_one(item):
+        tag, (src, extra) = item
+        log = _run([nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", str(CSRC / src), "-o", str(BUILD / f"{tag}.cubin")])
         (BUILD / f"{tag}.ptxas.log").write_text(log)
-        if verbose:
-            print(log)
+        return log
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(CUBINS)) as pool:
+        for log in pool.map(compile_one, CUBINS.items()):
+            if verbose:
+                print(log)
     # embed the cubins with .incbin (64-byte aligned, begin/end symbols)
     asm = [".section .rodata\n"]
     for tag in CUBINS:

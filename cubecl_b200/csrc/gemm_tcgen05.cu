@@ -638,6 +638,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   GEMM_LAYOUTS(gemm_u8_i32_##TILE, CG, BN, KIND_U8, OUT_F32, STAGES)             \
   GEMM_LAYOUTS(gemm_s8_i32_##TILE, CG, BN, KIND_S8, OUT_F32, STAGES)
 
+// The kernels are built as two cubins from this one source (cubecl_b200/build.py compiles them in parallel):
+//   GEMM_PART 0 ("gemm")    f16 / bf16 / tf32 / fp8 / int8 kernels and the bf16 peak probe
+//   GEMM_PART 1 ("gemm_mx") block-scaled kernels (mxf8 / mxf4 / nvf4) and the 8-bit / 4-bit peak probes
+#ifndef GEMM_PART
+#define GEMM_PART 0
+#endif
+
+#if GEMM_PART == 0
 // 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
 GEMM_DTYPES(2sm_n256, 2, 256, 6)
 GEMM_FP8(2sm_n256, 2, 256, 6)
@@ -646,33 +654,6 @@ GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
 GEMM_DTYPES(1sm_n128, 1, 128, 6)
 GEMM_FP8(1sm_n128, 1, 128, 6)
-
-// Block-scaled (MX) kinds: K-major operands only (lhs [M,K], rhs [N,K]); stage = operands + scale chunks.
-//   gemm_mxf8_<out>_<tile>_kk: e4m3 / e5m2 (either per operand), gemm_mxf4_<out>_<tile>_kk: packed e2m1
-#define GEMM_MX(TILE, CG, BN, STAGES, ACC)                                                       \
-  GEMM_KERNEL_ACC(gemm_mxf8_f32_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_F32, STAGES, ACC)   \
-  GEMM_KERNEL_ACC(gemm_mxf8_bf16_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_BF16, STAGES, ACC) \
-  GEMM_KERNEL_ACC(gemm_mxf8_f16_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_F16, STAGES, ACC)   \
-  GEMM_KERNEL_ACC(gemm_mxf4_f32_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F32, STAGES, ACC)   \
-  GEMM_KERNEL_ACC(gemm_mxf4_bf16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_BF16, STAGES, ACC) \
-  GEMM_KERNEL_ACC(gemm_mxf4_f16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F16, STAGES, ACC)
-// 512 TMEM columns: one 256-wide accumulator + 12 / 24 scale columns (no epilogue overlap)
-GEMM_KERNEL_ACC(gemm_mxf8_f32_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_F32, 6, 1)
-GEMM_KERNEL_ACC(gemm_mxf8_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_BF16, 6, 1)
-GEMM_KERNEL_ACC(gemm_mxf8_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_F16, 6, 1)
-GEMM_KERNEL_ACC(gemm_mxf4_f32_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F32, 5, 1)   // 35 KB stages: 5 fit beside the staging
-GEMM_KERNEL_ACC(gemm_mxf4_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_BF16, 5, 1)
-GEMM_KERNEL_ACC(gemm_mxf4_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F16, 5, 1)
-GEMM_MX(2sm_n128, 2, 128, 8, 2)
-GEMM_MX(1sm_n128, 1, 128, 6, 2)
-// NVFP4: four scale chunks per 128 rows per k-block (6 KB / 4 KB of scales per stage)
-#define GEMM_NVF4(TILE, CG, BN, STAGES, ACC)                                                          \
-  GEMM_KERNEL_ACC(gemm_nvf4_f32_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_F32, STAGES, ACC)   \
-  GEMM_KERNEL_ACC(gemm_nvf4_bf16_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_BF16, STAGES, ACC) \
-  GEMM_KERNEL_ACC(gemm_nvf4_f16_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_F16, STAGES, ACC)
-GEMM_NVF4(2sm_n256, 2, 256, 5, 1)
-GEMM_NVF4(2sm_n128, 2, 128, 7, 2)
-GEMM_NVF4(1sm_n128, 1, 128, 5, 2)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/
@@ -725,6 +706,35 @@ extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_bf16_2sm
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc<2>(tmem_base, 256);
 }
+#endif  // GEMM_PART == 0
+
+#if GEMM_PART == 1
+// Block-scaled (MX) kinds: K-major operands only (lhs [M,K], rhs [N,K]); stage = operands + scale chunks.
+//   gemm_mxf8_<out>_<tile>_kk: e4m3 / e5m2 (either per operand), gemm_mxf4_<out>_<tile>_kk: packed e2m1
+#define GEMM_MX(TILE, CG, BN, STAGES, ACC)                                                       \
+  GEMM_KERNEL_ACC(gemm_mxf8_f32_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_F32, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_mxf8_bf16_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_BF16, STAGES, ACC) \
+  GEMM_KERNEL_ACC(gemm_mxf8_f16_##TILE##_kk, CG, BN, false, false, KIND_MXF8, OUT_F16, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_mxf4_f32_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F32, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_mxf4_bf16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_BF16, STAGES, ACC) \
+  GEMM_KERNEL_ACC(gemm_mxf4_f16_##TILE##_kk, CG, BN, false, false, KIND_MXF4, OUT_F16, STAGES, ACC)
+// 512 TMEM columns: one 256-wide accumulator + 12 / 24 scale columns (no epilogue overlap)
+GEMM_KERNEL_ACC(gemm_mxf8_f32_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_F32, 6, 1)
+GEMM_KERNEL_ACC(gemm_mxf8_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_BF16, 6, 1)
+GEMM_KERNEL_ACC(gemm_mxf8_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF8, OUT_F16, 6, 1)
+GEMM_KERNEL_ACC(gemm_mxf4_f32_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F32, 5, 1)   // 35 KB stages: 5 fit beside the staging
+GEMM_KERNEL_ACC(gemm_mxf4_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_BF16, 5, 1)
+GEMM_KERNEL_ACC(gemm_mxf4_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F16, 5, 1)
+GEMM_MX(2sm_n128, 2, 128, 8, 2)
+GEMM_MX(1sm_n128, 1, 128, 6, 2)
+// NVFP4: four scale chunks per 128 rows per k-block (6 KB / 4 KB of scales per stage)
+#define GEMM_NVF4(TILE, CG, BN, STAGES, ACC)                                                          \
+  GEMM_KERNEL_ACC(gemm_nvf4_f32_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_F32, STAGES, ACC)   \
+  GEMM_KERNEL_ACC(gemm_nvf4_bf16_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_BF16, STAGES, ACC) \
+  GEMM_KERNEL_ACC(gemm_nvf4_f16_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_F16, STAGES, ACC)
+GEMM_NVF4(2sm_n256, 2, 256, 5, 1)
+GEMM_NVF4(2sm_n128, 2, 128, 7, 2)
+GEMM_NVF4(1sm_n128, 1, 128, 5, 2)
 
 // The same probe for the other tensor-core kinds on 8-bit / 4-bit operands: PK 1 = kind::f8f6f4 (e4m3), 2 = kind::mxf8f6f4
 // block-scaled (e4m3, ue8m0 scales = 1.0 copied to TMEM once), 3 = kind::mxf4 block-scaled (packed e2m1, two scales per
@@ -789,3 +799,4 @@ __device__ __forceinline__ void umma_probe_8bit_body(float* out, uint32_t n_iter
 extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_e4m3_2sm(float* out, uint32_t n_iter) { umma_probe_8bit_body<1>(out, n_iter); }
 extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_mxf8_2sm(float* out, uint32_t n_iter) { umma_probe_8bit_body<2>(out, n_iter); }
 extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_mxf4_2sm(float* out, uint32_t n_iter) { umma_probe_8bit_body<3>(out, n_iter); }
+#endif  // GEMM_PART == 1

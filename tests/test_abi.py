@@ -32,8 +32,14 @@ def test_cubins_are_embedded_and_sm100a():
     if r.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in r.stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR"):     # MMA, TMA load, TMA store, TMEM load, commit
         assert mnemonic in r.stdout, f"{mnemonic} missing: not a tcgen05/TMA kernel"
+    # block-scaled kernels: scaled MMA forms and the smem -> TMEM scale copies
+    mx = ROOT / "cubecl_b200" / "build" / "gemm_mx.cubin"
+    for fun, mma in (("gemm_mxf8_bf16_2sm_n256_kk", "UTCQMMA"), ("gemm_mxf4_bf16_2sm_n256_kk", "UTCOMMA"), ("gemm_nvf4_bf16_2sm_n256_kk", "UTCOMMA")):
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, str(mx)], capture_output=True, text=True).stdout
+        assert mma in sass and "UTCCP" in sass, f"{fun}: block-scaled tcgen05 SASS missing"
+    assert ".4X" in sass                                                      # NVFP4: four scales per row per instruction
     red = subprocess.run(["cuobjdump", "-sass", "-fun", "reduce_all_sum_f32", str(ROOT / "cubecl_b200" / "build" / "reduce.cubin")],
                          capture_output=True, text=True).stdout
     assert "LDG.E.128" in red or "LDG.E.NA.128" in red or ".128" in red
@@ -43,7 +49,7 @@ def test_cubins_are_embedded_and_sm100a():
 def test_embedded_images_are_elf_cubins_for_sm100():
     # "driver-API load of a prebuilt sm_100a .cubin": the images inside the .so are the nvcc -cubin outputs, byte for byte
     lib = _ffi.load()
-    for name in ("gemm", "reduce", "aux"):
+    for name in ("gemm", "gemm_mx", "reduce", "aux"):
         img, size = ctypes.c_void_p(), ctypes.c_size_t()
         assert lib.b200_get_cubin(name.encode(), ctypes.byref(img), ctypes.byref(size)) == 0
         blob = ctypes.string_at(img.value, size.value)
