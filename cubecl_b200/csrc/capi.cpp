@@ -15,6 +15,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -501,7 +502,7 @@ extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
 
 extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
-  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "reduce.variant", "reduce.threads",
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "reduce.row_balance", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
@@ -1390,6 +1391,23 @@ static int launch_reduce_rows(b200_ctx* c, CUstream st, int op, int dt, uint64_t
   const uint64_t tpr_cap = (outer >= (uint64_t)c->props.num_sms * 16 && len * dtype_size(dt) <= (128u << 10)) ? 32 : 512;
   uint64_t tpr = 1;
   while (tpr < tpr_cap && tpr * vec * 4 < len) tpr <<= 1;
+  // Wave quantisation: with a warp per row, R = SMs x 48 rows are resident (6 blocks of 256 threads, register-limited) and
+  // the kernel lasts ceil(outer / R) row-times -- 8192 rows of 32 KB are 1.15 waves, i.e. a second, nearly empty round
+  // (ncu: SMs idle 22 % of the launch).  Spreading a row over more threads shortens the row-time faster than it adds
+  // rounds, so take the smallest thread count whose last round is at least 90 % full (each thread keeps >= 2 vectors).
+  if (tpr == 32 && tpr_cap == 32 && opt(c, "reduce.row_balance", "off") == "on") {
+    auto fill = [&](uint64_t t) {
+      const double resident = static_cast<double>(c->props.num_sms) * (1536.0 / static_cast<double>(t));
+      const double w = static_cast<double>(outer) / resident;
+      return w <= 1.0 ? 1.0 : w / std::ceil(w);   // everything resident at once: nothing to balance
+    };
+    uint64_t best = tpr;
+    for (uint64_t t = tpr; t <= 512 && t * vec * 2 <= len; t <<= 1) {
+      if (fill(t) >= 0.9) { best = t; break; }
+      if (fill(t) > fill(best) + 0.05) best = t;
+    }
+    tpr = best;
+  }
   int tpr_log2 = 0;
   while ((1ull << tpr_log2) < tpr) ++tpr_log2;
   const unsigned threads = tpr > 32 ? (unsigned)tpr : 256;

@@ -229,6 +229,12 @@ def test_reduce_plans(plan):
     assert t.strip() == "launch reduce_rows_sum_f32 grid=(512,1,1) block=512 smem=0 cluster=1"
     rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)                         # many rows: a warp per row, 8 rows per block
     assert t.strip() == "launch reduce_rows_sum_f32 grid=(1024,1,1) block=256 smem=0 cluster=1"
+    plan.option("reduce.row_balance", "on")                                # 1.15 waves of warps -> 4.6 waves of 128-thread rows
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(2368,1,1) block=128 smem=0 cluster=1"
+    rc, t = plan.reduce(SUM, F32, [4096, 4096], 1)                         # everything resident at once: nothing to balance
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(512,1,1) block=256 smem=0 cluster=1"
+    plan.option("reduce.row_balance", "off")
     rc, t = plan.reduce(SUM, F32, [1000, 3], 1)                            # short rows: one thread per row
     assert "reduce_rows_sum_f32 grid=(4,1,1) block=256" in t
     rc, t = plan.reduce(SUM, F32, [4, 1 << 24], 1)                         # few long rows: two passes over pooled partials

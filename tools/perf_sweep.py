@@ -143,16 +143,22 @@ if "split" in what:
 
 if "axis" in what:
     # the reduction tutorial's shapes (cubecl-book: 1.085 ms / 3.124 ms / 1.483 ms / 0.924 ms on an unnamed wgpu device)
-    print("axis reductions (sum), CUDA events, min of 5 x 20 launches:")
+    print("axis reductions (sum), CUDA events, min of 5 x 20 launches (reduce.row_balance off | on):")
     for shape, axis in (([512, 8192], 1), ([128, 32768], 1), ([64, 256, 1024], 2), ([64, 64, 4096], 2), ([8192, 8192], 1),
+                        ([10000, 8192], 1), ([20000, 2048], 1), ([9000, 16384], 1),
                         ([8192, 8192], 0), ([16, 1 << 24], 1), ([1 << 14, 1 << 14], 0), ([1 << 26, 4], 1), ([4, 1 << 26], 0)):
         n = int(np.prod(shape))
         t = TensorHandle.empty_contiguous(c, shape, "f32")
         c.fill_uniform(t.handle, "f32", n, 11, 0.0, 1.0)
         oshape = reduce.output_shape(shape, axis)
         out = TensorHandle.empty_contiguous(c, oshape, "f32")
-        best = min(time_ms(c, lambda: reduce.launch(c, t, out, axis, "sum"), iters=20, warm=3) for _ in range(5))
-        print(f"  {str(shape):22s} axis={axis}: {best * 1e3:9.1f} us  {n * 4 / best / 1e6:8.1f} GB/s", flush=True)
+        res = []
+        for mode in ("off", "on"):
+            c.set_option("reduce.row_balance", mode)
+            best = min(time_ms(c, lambda: reduce.launch(c, t, out, axis, "sum"), iters=20, warm=3) for _ in range(5))
+            res.append(f"{best * 1e3:9.1f} us {n * 4 / best / 1e6:8.1f} GB/s")
+        c.set_option("reduce.row_balance", "off")
+        print(f"  {str(shape):22s} axis={axis}: " + "  |  ".join(res), flush=True)
         del t, out
 
 if "probes" in what:
