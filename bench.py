@@ -34,6 +34,9 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# stdout carries exactly one JSON line: NCCL's own log (the "NCCL version ..." banner that NCCL_DEBUG=VERSION/INFO prints,
+# from torch's communicator and from this library's) goes to stderr unless the caller already chose a file
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 N_MM = 8192                      # BASELINE config 3
 FLOPS_MM = 2.0 * N_MM ** 3
