@@ -39,7 +39,7 @@ extra = [(p.stem[len(tag) + 1:], None) for p in sorted(OUT.glob(f"{tag}_x_*.ncu-
 for name, key in [("gemm", "gemm_bf16_8192_dram_bytes"), ("reduce", "reduce_sum_2p28_dram_bytes")] + extra:
     rep = OUT / f"{tag}_{name}.ncu-rep"
     csv_export = OUT / f"{tag}_{name}.csv"     # `ncu -i rep --page raw --csv` run on the GPU box (the .ncu-rep embeds the whole cubin)
-    if rep.exists():
+    if rep.exists() and not (csv_export.exists() and csv_export.stat().st_mtime > rep.stat().st_mtime):
         records = raw(rep)
     elif csv_export.exists():
         rows = list(csv.reader(csv_export.open()))
