@@ -1245,6 +1245,8 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
   }
   // scales -> the tensor core's packed chunks (skipped when the caller already holds them in that form)
   const uint64_t tiles_a = (M + 127) / 128, tiles_b = (N + 127) / 128;
+  if (batch * tiles_a >= (1ull << 31) || batch * tiles_b >= (1ull << 31) || atoms * 32 >= (1ull << 31))
+    return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: scale tensor too large for 32-bit TMA coordinates");
   CUdeviceptr sfa = lhs_scales, sfb = rhs_scales;
   int rc = B200_OK;
   if (!scales_packed) {
