@@ -1226,7 +1226,6 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
   CUstream st = resolve_stream(c, s);
   const uint64_t n_scales = K / scale_block, atoms = (n_scales + 3) / 4;
   const uint64_t k_bytes = fp4 ? K / 2 : K;
-  const size_t osz = dtype_size(out_dtype);
   const std::string forced = opt(c, "gemm.variant", "auto");
   const bool tma = (lhs % 16 == 0 && rhs % 16 == 0 && k_bytes % 16 == 0 && (!scales_packed || (lhs_scales % 16 == 0 && rhs_scales % 16 == 0)));
   if (forced == "simt" || !tma) {
@@ -1272,7 +1271,6 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
     g.fmt_a = fp4 ? 1u : (lhs_dtype == B200_F8E5M2 ? 1u : 0u);
     g.fmt_b = fp4 ? 1u : (rhs_dtype == B200_F8E5M2 ? 1u : 0u);
     g.sfa = sfa; g.sfb = sfb; g.sf_atoms = atoms;
-    (void)osz;
     rc = launch_tcgen05(c, st, g, false, false);
   }
   if (!scales_packed) { pool_free(c, sfa, st); pool_free(c, sfb, st); }
