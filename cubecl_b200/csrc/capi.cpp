@@ -502,7 +502,7 @@ extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
 
 extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
-  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "reduce.row_balance", "reduce.variant", "reduce.threads",
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "reduce.row_balance", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
@@ -780,11 +780,19 @@ struct GemmVariant {
   const char* tag;  // suffix in the kernel name
   int cg, block_n, stages;
   double eff;       // measured MMA-pipe efficiency relative to 2sm_n256 (8192^3, B200): the N=128 shapes need
-                    // 128 B/cycle/SM of operand reads from shared memory and are smem-bandwidth bound
+                    // 128 B/cycle/SM of operand reads from shared memory and are smem-bandwidth bound.
+                    // 0 = never chosen automatically (gemm.variant=<tag> only)
+  int mt;           // 128-row sub-tiles of M per CTA: the pair tile is (128 * cg * mt) x block_n
 };
-static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0}, {"2sm_n128", 2, 128, 8, 0.66}, {"1sm_n128", 1, 128, 6, 0.59}};
+static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0, 1}, {"2sm_n128", 2, 128, 8, 0.66, 1}, {"1sm_n128", 1, 128, 6, 0.59, 1},
+                                        // 512 x 256 pair tile, one accumulator stage, 384 threads (gemm_tcgen05.cu, MT = 2): opt-in
+                                        {"2sm_m512", 2, 256, 4, 0.0, 2},
+                                        // diagnostic: 256 x 256 tile with ONE accumulator stage (bf16 -> bf16, K-major lhs only)
+                                        {"2sm_n256a1", 2, 256, 6, 0.0, 1}};
 static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
   const bool bits8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2 || in_dtype == B200_U8 || in_dtype == B200_I8);
+  if (!strcmp(v.tag, "2sm_m512")) return in_dtype == B200_BF16 || in_dtype == B200_F16;
+  if (!strcmp(v.tag, "2sm_n256a1")) return in_dtype == B200_BF16;
   if (bits8) return !strcmp(v.tag, "2sm_n256") || !strcmp(v.tag, "1sm_n128");
   return true;
 }
@@ -800,18 +808,23 @@ static int gemm_stages(const GemmVariant& v, int mx_kind) {
   if (mx_kind == 3) return v.block_n == 256 ? 5 : v.cg == 2 ? 7 : 5;   // 38 / 28 / 36 KB stages
   return (mx_kind == 2 && v.block_n == 256) ? 5 : v.stages;
 }
-// alignment slack + operand ring (+ scale chunks) + barrier block + epilogue staging (4 warps x [32 rows x 128 B])
+// alignment slack + operand ring (+ scale chunks) + barrier block + epilogue staging (4 * mt warps x [32 rows x 128 B])
 static unsigned gemm_smem_bytes(const GemmVariant& v, int mx_kind = 0) {
-  return 1024 + gemm_stages(v, mx_kind) * (16384 + (v.block_n / v.cg) * 128 + gemm_sf_stage_bytes(v, mx_kind)) + 1024 + 16384;
+  return 1024 + gemm_stages(v, mx_kind) * (16384 * v.mt + (v.block_n / v.cg) * 128 + gemm_sf_stage_bytes(v, mx_kind)) + 1024 + 16384 * v.mt;
 }
 
 static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, size_t esz, uint64_t base, uint64_t d0,
                        uint64_t d1, uint64_t d2, uint64_t s1_elems, uint64_t s2_elems, uint32_t b0, uint32_t b1,
                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint32_t b2 = 1) {
+  // L2 promotion: how much of a line's neighbourhood a TMA load pulls into L2 (tuning knob; 256 B measured best so far)
+  const int promo_bytes = atoi(opt(c, "gemm.l2_promotion", "256").c_str());
+  const CUtensorMapL2promotion promo = promo_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : promo_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                       : promo_bytes >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
   char key[256];
-  snprintf(key, sizeof(key), "%d|%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u|%u", (int)dt, (int)swz, (unsigned long long)base,
+  snprintf(key, sizeof(key), "%d|%d|%llx|%llu|%llu|%llu|%llu|%llu|%u|%u|%u|%d", (int)dt, (int)swz, (unsigned long long)base,
            (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1_elems,
-           (unsigned long long)s2_elems, b0, b1, b2);
+           (unsigned long long)s2_elems, b0, b1, b2, (int)promo);
   if (c->dry) {
     char line[256];
     if (b2 == 1)
@@ -833,8 +846,7 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, dt, 3, reinterpret_cast<void*>(base), dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(B200_ERR_INVALID_ARG, "cuTensorMapEncodeTiled failed: %s (dims %llu,%llu,%llu strides %llu,%llu box %u,%u)",
                 cu_err(r), (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
@@ -915,7 +927,8 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (forced == "auto" && v.eff <= 0.0) continue;
     if (!g.mx_kind && !variant_has_dtype(v, g.in_dtype)) continue;
     if (forced == "auto" && v.cg == 2 && g.M <= 128) continue;  // a CTA pair would idle its second half: one CTA per tile
-    const uint64_t tm = (g.M + 128 * v.cg - 1) / (128 * v.cg), tn = (g.N + v.block_n - 1) / v.block_n;
+    const uint64_t tile_m = 128ull * v.cg * v.mt;
+    const uint64_t tm = (g.M + tile_m - 1) / tile_m, tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
     const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
     const uint64_t waves = (tiles + clusters - 1) / clusters;
@@ -997,7 +1010,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   p.out_row_stride = g.o_sm;
   p.out_batch_stride = g.o_sb;
   p.M = (uint32_t)g.M; p.N = (uint32_t)g.N; p.K = (uint32_t)g.K; p.batch = (uint32_t)g.batch;
-  p.tiles_m = (uint32_t)((g.M + 128 * v.cg - 1) / (128 * v.cg));
+  p.tiles_m = (uint32_t)((g.M + 128 * v.cg * v.mt - 1) / (128 * v.cg * v.mt));
   p.tiles_n = (uint32_t)((g.N + v.block_n - 1) / v.block_n);
   p.group_m = (uint32_t)std::max(1, atoi(opt(c, "gemm.group_m", "8").c_str()));
   p.a_bmul = a_bcast ? 0 : 1;
@@ -1028,7 +1041,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   const uint64_t rem = total_tiles % max_clusters, full_waves = total_tiles / max_clusters;
   const bool float_acc = !(g.in_dtype == B200_U8 || g.in_dtype == B200_I8);
   unsigned split_s = 1;
-  if (split_opt != "off" && float_acc && rem != 0) {
+  if (split_opt != "off" && float_acc && rem != 0 && v.mt == 1) {  // the slab protocol is per 128-row CTA tile
     const unsigned s_max = 4, min_kb = 8;
     if (split_opt == "auto") {
       double best_t = static_cast<double>(full_waves) + 1.0;
@@ -1071,7 +1084,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     }
   }
   void* args[] = {&ta, &tb, &ta_lo, &tb_lo, &tout, &p};
-  rc = launch(c, f, clusters * v.cg, 1, 1, 256, smem, v.cg, st, args);
+  rc = launch(c, f, clusters * v.cg, 1, 1, 256 + 128 * (v.mt - 1), smem, v.cg, st, args);
   if (slabs) pool_free(c, slabs, st);  // stream-ordered: reusable by later work once this launch has drained
   return rc;
 }

@@ -144,12 +144,21 @@ __device__ __forceinline__ WorkUnit unit_decode(uint32_t u, const GemmParams& p,
 // per MMA and two scales per row per MMA -> two chunks per k-block, MMA k uses chunk k / 2, bytes 2 (k % 2) and +1.
 // kind::mxf4nvf4 (NVFP4): a scale per 16 elements -> four scales per row per MMA, four chunks per k-block, MMA k uses chunk k.
 // ACC = accumulator stages in TMEM: 256-wide scaled tiles have room for one only (512 columns - scale columns).
-template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES, int ACC = 2>
+// MT = 128-row sub-tiles of M per CTA.  MT = 2 (CG = 2, BLOCK_N = 256, ACC = 1) is the 512 x 256 pair tile: each CTA stages
+// 256 rows of A and half of B per k-block (48 KB, 4 stages) and holds two 128 x 256 accumulators -- all 512 TMEM columns.
+// Per FLOP it pulls 25 % less operand data from L2 than the 256 x 256 tile ((512 + 256) / (512 * 256) vs (256 + 256) /
+// (256 * 256) rows per output) -- the shape cuBLAS's nvjet_tst_256x256_64x4_2x1_2cta kernel runs (profiles/r01_cublas_*).
+// With no second accumulator stage the epilogue cannot hide behind the next tile, so each sub-tile ("unit") has its own
+// full / empty barriers and its own epilogue warpgroup (warps 4-7: unit 0, warps 8-11: unit 1; 384 threads): a unit is
+// pulled into packed registers and handed back at once, and its staging / TMA stores run under the next tile's MMAs.
+template <int CG, int BLOCK_N, bool A_MN, bool B_MN, int KIND, int OUT, int STAGES, int ACC = 2, int MT = 1>
 __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUtensorMap* tma_b_hi, const CUtensorMap* tma_a_lo,
                                           const CUtensorMap* tma_b_lo, const CUtensorMap* tma_out, const GemmParams& p) {
   constexpr bool SCALED = (KIND >= KIND_MXF8);
   constexpr bool INT_ACC = (KIND == KIND_U8 || KIND == KIND_S8);
   static_assert(!SCALED || (!A_MN && !B_MN && BLOCK_N % 128 == 0), "block-scaled kinds: K-major operands, 128-row scale tiles");
+  static_assert(MT == 1 || (MT == 2 && CG == 2 && ACC == 1 && !SCALED), "two M sub-tiles per CTA: CTA pair, one accumulator stage");
+  static_assert(ACC * MT <= 2, "two accumulator units (barrier pairs) at most");
   constexpr int SF_ATOMS = !SCALED ? 0 : (KIND == KIND_NVF4) ? 4 : (KIND == KIND_MXF4) ? 2 : 1;  // 512-byte scale chunks per 128 rows per k-block
   constexpr int SF_TILES_B = BLOCK_N / 128;
   constexpr uint32_t SFA_BYTES = 512u * SF_ATOMS, SFB_BYTES = 512u * SF_ATOMS * SF_TILES_B;
@@ -163,15 +172,16 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   constexpr int UMMA_K = 32 / ESZ;
   constexpr int UMMA_M = 128 * CG;
   constexpr int N_LOCAL = BLOCK_N / CG;  // rows of the B tile this CTA stages
-  constexpr uint32_t A_BYTES = 128 * 128;
+  constexpr uint32_t A_SUB_BYTES = 128 * 128;       // one 128-row sub-tile of A: 128 rows x 128 B
+  constexpr uint32_t A_BYTES = MT * A_SUB_BYTES;
   constexpr uint32_t B_BYTES = N_LOCAL * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + SF_BYTES;
   constexpr uint32_t STAGE_TX = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;  // bytes one CTA's copies deliver per stage
   constexpr int CHUNK_N = 128 / ESZ;                 // MN-major operand: M/N elements per 128-byte row
   constexpr uint32_t CHUNK_BYTES = BLOCK_K * 128;    // MN-major operand: one [BLOCK_K x 128 B] chunk
   constexpr int NUM_CHUNKS = N_LOCAL / CHUNK_N;      // B chunks per CTA
-  constexpr int NUM_CHUNKS_A = 128 / CHUNK_N;        // A chunks per CTA (128 rows of M)
-  constexpr uint32_t ACC_COLS = ACC * BLOCK_N, TMEM_NEED = ACC_COLS + SF_COLS;
+  constexpr int NUM_CHUNKS_A = MT * 128 / CHUNK_N;   // A chunks per CTA (128 * MT rows of M)
+  constexpr uint32_t ACC_COLS = ACC * MT * BLOCK_N, TMEM_NEED = ACC_COLS + SF_COLS;
   constexpr uint32_t TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 : (TMEM_NEED <= 128) ? 128 : (TMEM_NEED <= 256) ? 256 : 512;
   static_assert(TMEM_NEED <= 512, "accumulator stages + scale factors must fit TMEM");
   constexpr uint32_t SFA_COL = ACC_COLS, SFB_COL = ACC_COLS + 4u * SF_ATOMS;
@@ -187,7 +197,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t split_flag = tmem_slot + 4;  // "this CTA reduces the slabs" broadcast among the epilogue warps
-  // epilogue staging: one [32 rows x 128 B] tile per epilogue warp, 128B-swizzled like the tensor map that stores it
+  // epilogue staging: one [32 rows x 128 B] tile per epilogue warp (4 * MT of them), 128B-swizzled like the tensor map that stores it
   const uint32_t epi_base = bar_base + 1024u;
 
   const uint32_t warp = threadIdx.x >> 5;
@@ -244,12 +254,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     if (lane == 0) {
       const uint32_t who = (warp == 0) ? 0u : 1u;
       const uint32_t leader_full0 = (CG == 2) ? mapa_shared(full_bar(0), 0) : full_bar(0);
-      constexpr int kAItems = A_MN ? NUM_CHUNKS_A : 1, kBItems = B_MN ? NUM_CHUNKS : 1;
+      constexpr int kAItems = A_MN ? NUM_CHUNKS_A : MT, kBItems = B_MN ? NUM_CHUNKS : 1;
       uint32_t s = 0, ph = 0;
       for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
         const WorkUnit wu = unit_decode(t, p, num_kb);
         const TileCoord tc = tile_coord(wu.tile, p);
-        const int m0 = static_cast<int>((tc.m_blk * CG + rank) * 128);
+        const int m0 = static_cast<int>((tc.m_blk * CG + rank) * (128 * MT));
         const int n0 = static_cast<int>(tc.n_blk * BLOCK_N + rank * N_LOCAL);
         const int ba = static_cast<int>(tc.b * p.a_bmul), bb = static_cast<int>(tc.b * p.b_bmul);
         uint32_t seg = wu.kb0 / seg_kb, kk = wu.kb0 - seg * seg_kb;  // segment (0 unless k_segments == 3), k-block within it
@@ -266,8 +276,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           for (int item = 0; item < kAItems + kBItems; ++item) {
             if ((item & 1) != static_cast<int>(who)) continue;
             if (item < kAItems) {
-              const uint32_t dst = A_MN ? sa + item * CHUNK_BYTES : sa;
-              const int c0 = A_MN ? m0 + item * CHUNK_N : k0, c1 = A_MN ? k0 : m0;
+              const uint32_t dst = A_MN ? sa + item * CHUNK_BYTES : sa + item * A_SUB_BYTES;  // K-major: one 128-row box per sub-tile
+              const int c0 = A_MN ? m0 + item * CHUNK_N : k0, c1 = A_MN ? k0 : m0 + item * 128;
               if constexpr (CG == 1) tma_load_3d(dst, tma_a, fb, c0, c1, ba); else tma_load_3d_2sm(dst, tma_a, fb, c0, c1, ba);
             } else {
               const int c = item - kAItems;
@@ -302,9 +312,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       uint32_t s = 0, ph = 0, as = 0, aph = 0;
       for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
         const WorkUnit wu = unit_decode(t, p, num_kb);
-        mbar_wait(tempty_bar(as), aph ^ 1);  // epilogue (both CTAs) drained this accumulator stage
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        if constexpr (MT == 1) {
+          mbar_wait(tempty_bar(as), aph ^ 1);  // epilogue (both CTAs) drained this accumulator stage
+          tcgen05_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + as * (MT * BLOCK_N);
         for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
@@ -345,25 +357,46 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                                                               idesc_base | (sf_id << 29) | (sf_id << 4), sf_t + SFA_COL + 4u * atom,
                                                               sf_t + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
-          } else {
+          } else if constexpr (MT == 1) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t a_k = a_desc + static_cast<uint64_t>(A_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
               const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
               umma_ss<CG, (SCALED ? KIND_E4M3 : KIND)>(d_tmem, a_k, b_k, IDESC, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
+          } else {
+            // two accumulator units per tile (rows [0,128) and [128,256) of this CTA), the same B stage for both.  A unit is
+            // waited for right before its first MMA of the tile and committed right after its last one, so the epilogue of
+            // unit 0 starts while unit 1's last MMAs still run and the next tile's unit 0 starts while unit 1 drains.
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              if (kb == wu.kb0) {
+                mbar_wait(tempty_bar(mt), aph ^ 1);
+                tcgen05_fence_after();
+              }
+              const uint64_t a_mt = a_desc + static_cast<uint64_t>((mt * A_SUB_BYTES) >> 4);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t a_k = a_mt + static_cast<uint64_t>(A_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
+                const uint64_t b_k = b_desc + static_cast<uint64_t>(B_MN ? ((k * UMMA_K * 128) >> 4) : ((k * 32) >> 4));
+                umma_ss<CG, KIND>(d_tmem + mt * BLOCK_N, a_k, b_k, IDESC, (kb != wu.kb0 || k != 0) ? 1u : 0u);
+              }
+              if (kb + 1 == wu.kb1) umma_commit<CG>(tfull_bar(mt));  // this unit's accumulator is complete -> its epilogue warpgroup
+            }
           }
           umma_commit<CG>(empty_bar(s));  // smem slot reusable once these MMAs (and scale copies) retire
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit<CG>(tfull_bar(as));  // accumulator complete -> epilogue
+        if constexpr (MT == 1) umma_commit<CG>(tfull_bar(as));  // accumulator complete -> epilogue
         if (++as == ACC) { as = 0; aph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================================================================== epilogue (4 warps, TMEM -> regs -> global)
+    // ===================================================================== epilogue (4 warps per accumulator unit, TMEM -> regs -> global)
     const uint32_t q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t ewarp = (MT == 1) ? q : warp - 4;      // staging tile of this warp (0 .. 4 * MT - 1)
+    const uint32_t mt = (MT == 1) ? 0u : (ewarp >> 2);    // M sub-tile = accumulator unit this warpgroup drains
     const uint32_t tempty_leader = (CG == 2) ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t osz = (OUT == OUT_F32) ? 4 : 2;
     uint32_t as = 0, aph = 0;
@@ -383,16 +416,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     };
     for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
       const WorkUnit wu = unit_decode(t, p, num_kb);
+      const bool partial = (MT == 1) && wu.partial;  // the tail split is a 256-thread, one-unit protocol: never planned for MT = 2
       const TileCoord tc = tile_coord(wu.tile, p);
       const uint32_t row_in_cta = q * 32 + lane;
-      const uint32_t m = (tc.m_blk * CG + rank) * 128 + row_in_cta;
+      const uint32_t unit = as * MT + mt;  // barrier pair + TMEM column block of this accumulator
+      const uint32_t m = (tc.m_blk * CG + rank) * (128 * MT) + mt * 128 + row_in_cta;
       const uint32_t n_tile = tc.n_blk * BLOCK_N;
       const uint64_t row_ptr = p.out + (static_cast<uint64_t>(tc.b) * p.out_batch_stride + static_cast<uint64_t>(m) * p.out_row_stride) * osz;
-      mbar_wait(tfull_bar(as), aph);
+      mbar_wait(tfull_bar(unit), aph);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((q * 32u) << 16) + unit * BLOCK_N;
       bool released = false;  // the accumulator stage was already handed back to the MMA warp
-      if (ACC == 1 && OUT != OUT_F32 && !wu.partial && p.tma_store) {
+      if (ACC == 1 && OUT != OUT_F32 && !partial && p.tma_store) {
         // Single accumulator (256-wide scaled tiles): the next tile's MMAs wait for this drain, so the whole row is pulled
         // into registers first -- converted and packed, 128 registers for 256 columns -- the TMEM stage is released, and
         // only then do the staging stores / TMA stores run, under the next tile's mainloop.
@@ -420,11 +455,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
+            if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * unit); else mbar_arrive(tempty_bar(unit));
           }
           released = true;
-          const int m_row0 = static_cast<int>((tc.m_blk * CG + rank) * 128 + q * 32);
-          const uint32_t stage_smem = epi_base + q * 4096u;
+          const int m_row0 = static_cast<int>((tc.m_blk * CG + rank) * (128 * MT) + mt * 128 + q * 32);
+          const uint32_t stage_smem = epi_base + ewarp * 4096u;
           const uint32_t row = stage_smem + lane * 128u;
 #pragma unroll
           for (int c = 0; c < BLOCK_N / 64; ++c) {
@@ -444,17 +479,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             }
           }
         }
-      } else if (!wu.partial && p.tma_store) {
+      } else if (!partial && p.tma_store) {
         // TMEM -> registers -> (epilogue, convert) -> swizzled staging tile -> one TMA store per 128-byte-wide column group.
         // A direct store has every lane write its own row: 32 LSU wavefronts per instruction, ~3 us per 128x256 bf16 tile,
         // which matters wherever the epilogue is not hidden behind the next tile's MMAs (single-accumulator scaled tiles,
         // the last wave).  The staged form costs 4 wavefronts per shared-memory store and the TMA unit clips ragged edges.
         constexpr int CW = (OUT == OUT_F32) ? 32 : 64;   // columns per staging tile: 128 bytes per row
-        const int m_row0 = static_cast<int>((tc.m_blk * CG + rank) * 128 + q * 32);
+        const int m_row0 = static_cast<int>((tc.m_blk * CG + rank) * (128 * MT) + mt * 128 + q * 32);
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / CW; ++c) {
           const uint32_t n0 = n_tile + c * CW;
-          const uint32_t stage_smem = epi_base + q * 4096u;
+          const uint32_t stage_smem = epi_base + ewarp * 4096u;
           if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
           __syncwarp();
 #pragma unroll
@@ -495,7 +530,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             tma_store_commit();
           }
         }
-      } else if (!wu.partial) {
+      } else if (!partial) {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
@@ -527,11 +562,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * as); else mbar_arrive(tempty_bar(as));
+          if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader + 8u * unit); else mbar_arrive(tempty_bar(unit));
         }
       }
       if (++as == ACC) { as = 0; aph ^= 1; }
-      if (wu.partial) {
+      if (partial) {
         // publish the slab, take a ticket for (tile, CTA rank); the last of the split_s slices reduces in slice order
         const uint32_t tail = wu.tile - p.full_tiles;
         __threadfence();
@@ -601,15 +636,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 }
 
 // Dynamic shared memory a variant needs (host mirrors this in capi.cpp: gemm_smem_bytes()).
-//   1024 (alignment slack) + STAGES * (16384 + (BLOCK_N/CG)*128 + scale chunks) + 1024 (barriers) + 16384 (epilogue staging)
+//   1024 (alignment slack) + STAGES * (MT * 16384 + (BLOCK_N/CG)*128 + scale chunks) + 1024 (barriers) + MT * 16384 (epilogue staging)
 
-#define GEMM_KERNEL_ACC(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC)                                          \
-  extern "C" __global__ void __launch_bounds__(kNumThreads, 1)                                                   \
+// threads: 256 = warps 0-7; MT = 2 adds the second epilogue warpgroup (warps 8-11): 384
+#define GEMM_KERNEL_MT(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC, MT)                                       \
+  extern "C" __global__ void __launch_bounds__(kNumThreads + 128 * (MT - 1), 1)                                  \
       NAME(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,                 \
            const __grid_constant__ CUtensorMap tma_a_lo, const __grid_constant__ CUtensorMap tma_b_lo,           \
            const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ GemmParams p) {                  \
-    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC>(&tma_a, &tma_b, &tma_a_lo, &tma_b_lo, &tma_out, p);      \
+    gemm_body<CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC, MT>(&tma_a, &tma_b, &tma_a_lo, &tma_b_lo, &tma_out, p);  \
   }
+#define GEMM_KERNEL_ACC(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC) GEMM_KERNEL_MT(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC, 1)
 #define GEMM_KERNEL(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES) GEMM_KERNEL_ACC(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, 2)
 
 // name: gemm_<in>_<out>_<cg>sm_n<BLOCK_N>_<a><b>
@@ -654,6 +691,20 @@ GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
 GEMM_DTYPES(1sm_n128, 1, 128, 6)
 GEMM_FP8(1sm_n128, 1, 128, 6)
+// 2-SM, 512x256 pair tiles (MT = 2, see gemm_body): 48 KB/stage/CTA -> 4 stages = 192 KB, one accumulator stage, 384 threads.
+// Opt-in (gemm.variant=2sm_m512) until measured against the 256x256 tile.
+#define GEMM_M512(PFX, KIND, OUT)                                        \
+  GEMM_KERNEL_MT(PFX##_2sm_m512_kn, 2, 256, false, true, KIND, OUT, 4, 1, 2)  \
+  GEMM_KERNEL_MT(PFX##_2sm_m512_kk, 2, 256, false, false, KIND, OUT, 4, 1, 2) \
+  GEMM_KERNEL_MT(PFX##_2sm_m512_mn, 2, 256, true, true, KIND, OUT, 4, 1, 2)   \
+  GEMM_KERNEL_MT(PFX##_2sm_m512_mk, 2, 256, true, false, KIND, OUT, 4, 1, 2)
+GEMM_M512(gemm_bf16_bf16, KIND_BF16, OUT_BF16)
+GEMM_M512(gemm_bf16_f32, KIND_BF16, OUT_F32)
+GEMM_M512(gemm_f16_f16, KIND_F16, OUT_F16)
+GEMM_M512(gemm_f16_f32, KIND_F16, OUT_F32)
+// diagnostic: the 256x256 tile with ONE accumulator stage (what an un-hidden epilogue costs per tile); gemm.variant=2sm_n256a1
+GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kn, 2, 256, false, true, KIND_BF16, OUT_BF16, 6, 1)
+GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kk, 2, 256, false, false, KIND_BF16, OUT_BF16, 6, 1)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/

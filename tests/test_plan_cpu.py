@@ -260,3 +260,33 @@ def test_device_only_entry_points_refuse_a_planning_context(plan):
     assert plan.lib.b200_event_create(plan.ctx, C.byref(ev)) == 7
     assert plan.lib.b200_write(plan.ctx, None, A, None, 16) == 7
     assert plan.lib.b200_sync(plan.ctx, None) == 0
+
+
+def test_pair_tile_512_plan_is_opt_in_with_384_threads_and_no_tail_split(plan):
+    n = 8192
+    # auto never picks the opt-in variants
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0 and "2sm_n256_kn" in t and "m512" not in t and "a1" not in t
+    plan.option("gemm.variant", "2sm_m512")
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0
+    lines = t.strip().splitlines()
+    # smem: 1 KB slack + 4 x (32 KB of A + 16 KB of B) + 1 KB barriers + 2 x 16 KB staging (8 epilogue warps) = 226 KB
+    assert lines[-1] == "launch gemm_bf16_bf16_2sm_m512_kn grid=(148,1,1) block=384 smem=231424 cluster=2"
+    assert 231424 <= 232448                                              # sm_100 opt-in maximum per block (227 KB)
+    assert "box=(64,128) swizzle=3" in lines[0]                           # A still moves as 128-row boxes (two per stage)
+    # 4096^3 on 512 x 256 tiles: 8 x 16 = 128 tiles on 74 pairs; a partial last wave is NOT cut into K-slices for this tile
+    plan.option("gemm.split_k", "4")
+    m = 4096
+    rc, t = plan.matmul(BF16, BF16, [m, m], [m, 1], [m, m], [m, 1], [m, m], [m, 1])
+    assert rc == 0 and "tail split" not in t and "grid=(148,1,1) block=384" in t
+    # small M: 2 tiles of 512 rows x 1 -> 2 pairs
+    rc, t = plan.matmul(BF16, F32, [600, 256], [256, 1], [256, 256], [256, 1], [600, 256], [256, 1])
+    assert rc == 0 and "gemm_bf16_f32_2sm_m512_kn grid=(4,1,1) block=384" in t
+    # dtypes without an instantiation are refused, not silently re-routed
+    rc, t = plan.matmul(E4M3, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc != 0
+    plan.option("gemm.variant", "2sm_n256a1")
+    plan.option("gemm.split_k", "auto")
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0 and "launch gemm_bf16_bf16_2sm_n256a1_kn grid=(148,1,1) block=256 smem=215040 cluster=2" in t
