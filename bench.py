@@ -320,7 +320,7 @@ def main():
         "gpu_launches": launches * world,
         "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": per_gpu_tflops / pk["bf16_tflops"], "traffic": traffic.get("gemm_bf16_8192_dram_bytes"),
-                     "peak_source": pk["source"] + " (cuBLAS bf16 burst)", "kernel": "gemm_bf16_bf16_2sm_n256_kn",
+                     "peak_source": pk["source"] + " (cuBLAS bf16 burst)", "kernel": "gemm_bf16_bf16_2sm_m512_kn",
                      "algorithmic_flops_per_launch": FLOPS_MM},
         "clocks": clocks,
     }
@@ -334,7 +334,7 @@ def main():
         line["sustained"] = {"value": world * FLOPS_MM * n_sus / (ms_sus * 1e-3) / 1e12, "unit": "TFLOP/s", "launches": n_sus,
                              "seconds": ms_sus * 1e-3, "frac_of_sustained_peak": FLOPS_MM * n_sus / (ms_sus * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                              "peak_sustained": pk["bf16_tflops_sustained"], "clocks": cl2,
-                             "note": "back-to-back launches for ~1 s: the 1 kW power cap pulls SM clocks to ~1.4 GHz (ncu: 1.41 GHz, tensor pipe 92 % active)"}
+                             "note": "back-to-back launches for ~1 s: the 1 kW power cap pulls SM clocks to ~1.5 GHz (ncu: 1.53 GHz, tensor pipe 94 % active)"}
 
     # ------------------------------------------------------------------ e2e: host buffers through the public API
     nbytes = N_MM * N_MM * 2
@@ -523,6 +523,18 @@ def main():
             ms_8, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
             line["matmul_fp8_8192"] = {"value": world * FLOPS_MM * extra_steps / (ms_8 * 1e-3) / 1e12, "unit": "TFLOP/s",
                                        "config": "fp8 e4m3 x e4m3 -> bf16, f32 accumulate, 8192^3 per GPU"}
+            # same box, same operands: the 512x256 pair tile vs the 256x256 double-accumulator tile (bf16: auto picks the
+            # former; fp8: forced, to decide its default)
+            c.set_option("gemm.variant", "2sm_n256")
+            ms_bn, _ = timed(mm_step, extra_steps, 3)
+            c.set_option("gemm.variant", "auto")
+            line["tile_variants_8192"] = {"unit": "TFLOP/s", "bf16_2sm_n256": world * FLOPS_MM * extra_steps / (ms_bn * 1e-3) / 1e12,
+                                          "note": "gemm.variant forced; the headline (auto) runs bf16 on 2sm_m512, matmul_fp8_8192 runs 2sm_n256"}
+            if os.environ.get("B200_BENCH_EXPERIMENTAL") == "1":     # forced-only kernels that are not a default anywhere yet
+                c.set_option("gemm.variant", "2sm_m512")
+                ms_8m, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
+                c.set_option("gemm.variant", "auto")
+                line["tile_variants_8192"]["fp8_2sm_m512"] = world * FLOPS_MM * extra_steps / (ms_8m * 1e-3) / 1e12
             # widening row: block-scaled MX formats -- tcgen05 kind::mxf8f6f4 / kind::mxf4, ue8m0 scale per 32 K,
             # row-major scales as the reference's scaled MMA takes them (the two packing passes run inside the timed call)
             import numpy as _np
@@ -578,7 +590,10 @@ def main():
             line["reduce"]["cpu_baseline"] = cpu_reduce_sample()
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(ex)}
-    c.sync()
+    try:
+        c.sync()
+    except Exception as ex:  # noqa: BLE001  (a fault in a secondary row must not cost the measured headline)
+        line["final_sync_error"] = repr(ex)
     if rank0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -785,13 +785,16 @@ struct GemmVariant {
   int mt;           // 128-row sub-tiles of M per CTA: the pair tile is (128 * cg * mt) x block_n
 };
 static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0, 1}, {"2sm_n128", 2, 128, 8, 0.66, 1}, {"1sm_n128", 1, 128, 6, 0.59, 1},
-                                        // 512 x 256 pair tile, one accumulator stage, 384 threads (gemm_tcgen05.cu, MT = 2): opt-in
-                                        {"2sm_m512", 2, 256, 4, 0.0, 2},
+                                        // 512 x 256 pair tile, one accumulator stage, 384 threads (gemm_tcgen05.cu, MT = 2).  Measured
+                                        // bf16 8192^3, same box, power state equalised (profiles/r01_pair_tile_ab.log): x1.059 of
+                                        // 2sm_n256 in a 50-launch burst and x1.058 held for 1 s (25 % less L2->SM operand traffic
+                                        // -> 1.53 instead of 1.45 GHz under the power cap), 0.98 of cuBLAS
+                                        {"2sm_m512", 2, 256, 4, 1.06, 2},
                                         // diagnostic: 256 x 256 tile with ONE accumulator stage (bf16 -> bf16, K-major lhs only)
                                         {"2sm_n256a1", 2, 256, 6, 0.0, 1}};
 static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
   const bool bits8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2 || in_dtype == B200_U8 || in_dtype == B200_I8);
-  if (!strcmp(v.tag, "2sm_m512")) return in_dtype == B200_BF16 || in_dtype == B200_F16;
+  if (!strcmp(v.tag, "2sm_m512")) return in_dtype == B200_BF16 || in_dtype == B200_F16 || in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2;
   if (!strcmp(v.tag, "2sm_n256a1")) return in_dtype == B200_BF16;
   if (bits8) return !strcmp(v.tag, "2sm_n256") || !strcmp(v.tag, "1sm_n128");
   return true;
@@ -927,6 +930,10 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (forced == "auto" && v.eff <= 0.0) continue;
     if (!g.mx_kind && !variant_has_dtype(v, g.in_dtype)) continue;
     if (forced == "auto" && v.cg == 2 && g.M <= 128) continue;  // a CTA pair would idle its second half: one CTA per tile
+    if (g.mx_kind && v.mt != 1) continue;                       // block-scaled kinds have no two-unit instantiation
+    // the two-unit tile hides its epilogue only on the packed-register path (16-bit outputs); f32 outputs stay on 2sm_n256
+    if (forced == "auto" && v.mt == 2 && !(g.out_dtype == B200_BF16 || g.out_dtype == B200_F16)) continue;
+    if (forced == "auto" && v.mt == 2 && !(g.in_dtype == B200_BF16 || g.in_dtype == B200_F16)) continue;  // fp8: forced only until measured
     const uint64_t tile_m = 128ull * v.cg * v.mt;
     const uint64_t tm = (g.M + tile_m - 1) / tile_m, tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
@@ -935,7 +942,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     // block-scaled kinds: measured 8192^3 ratios to the 256-wide tile are 0.63 (2sm_n128) and 0.61 (1sm_n128) for mxfp8,
     // 0.63 / 0.66 for mxfp4 -- the same ordering as the unscaled table, so it is reused
     const double eff = v.eff > 0 ? v.eff : 1.0;
-    const double cost = static_cast<double>(waves) * (128.0 * v.block_n) / eff;  // per-SM MMA time per wave
+    const double cost = static_cast<double>(waves) * (128.0 * v.mt * v.block_n) / eff;  // per-SM MMA time per wave
     if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; }
   }
   if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant for this dtype", forced.c_str());

@@ -702,6 +702,11 @@ GEMM_M512(gemm_bf16_bf16, KIND_BF16, OUT_BF16)
 GEMM_M512(gemm_bf16_f32, KIND_BF16, OUT_F32)
 GEMM_M512(gemm_f16_f16, KIND_F16, OUT_F16)
 GEMM_M512(gemm_f16_f32, KIND_F16, OUT_F32)
+// fp8 on the same tile (forced only until measured: gemm.variant=2sm_m512)
+GEMM_M512(gemm_e4m3_bf16, KIND_E4M3, OUT_BF16)
+GEMM_M512(gemm_e4m3_f16, KIND_E4M3, OUT_F16)
+GEMM_M512(gemm_e5m2_bf16, KIND_E5M2, OUT_BF16)
+GEMM_M512(gemm_e5m2_f16, KIND_E5M2, OUT_F16)
 // diagnostic: the 256x256 tile with ONE accumulator stage (what an un-hidden epilogue costs per tile); gemm.variant=2sm_n256a1
 GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kn, 2, 256, false, true, KIND_BF16, OUT_BF16, 6, 1)
 GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kk, 2, 256, false, false, KIND_BF16, OUT_BF16, 6, 1)

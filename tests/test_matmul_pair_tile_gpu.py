@@ -1,4 +1,5 @@
-"""GPU parity of the opt-in GEMM tile variants (gemm.variant = 2sm_m512 / 2sm_n256a1) against the oracle.
+"""GPU parity of the 512 x 256 pair tile (2sm_m512; auto-chosen for 16-bit results by the wave model) and of the
+single-accumulator diagnostic tile (2sm_n256a1), both forced through gemm.variant, against the oracle.
 
 2sm_m512 is the 512 x 256 pair tile (two 128-row accumulator units per CTA, one epilogue warpgroup per unit, 4 x 48 KB
 stages); 2sm_n256a1 is the 256 x 256 tile with a single accumulator stage (diagnostic).  Same oracle, same tolerances and
@@ -36,6 +37,23 @@ def test_pair_tile_512_parity_ragged(client, lhs_t, rhs_t, in_dtype, out_dtype):
     assert client.launch_count() - before == 1
     check_against_oracle(got, np.ascontiguousarray(a.T) if lhs_t else a, b.T if rhs_t else b, out_dtype,
                          tight=1e-5 if out_dtype == "f32" else None)
+
+
+@pytest.mark.parametrize("lhs_t", [False, True], ids=["lhs_mk", "lhs_km"])
+@pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
+@pytest.mark.parametrize("dtype,out_dtype", [("f8e4m3", "bf16"), ("f8e5m2", "f16")])
+def test_pair_tile_512_parity_fp8(client, lhs_t, rhs_t, dtype, out_dtype):
+    client.set_option("gemm.variant", "2sm_m512")
+    M, N, K = 704, 528, 720   # 16-byte multiples for 1-byte rows; 5.6 k-blocks of 128 fp8 elements
+    a_dev, a = make_operand((K, M) if lhs_t else (M, K), dtype, 351)
+    b_dev, b = make_operand((N, K) if rhs_t else (K, N), dtype, 352)
+    before = client.launch_count()
+    got = run_matmul(client, a_dev, b_dev, dtype, out_dtype, rhs_transposed=rhs_t, lhs_transposed=lhs_t)
+    assert client.launch_count() - before == 1
+    check_against_oracle(got, np.ascontiguousarray(a.T) if lhs_t else a, b.T if rhs_t else b, out_dtype)
+    client.set_option("gemm.variant", "2sm_n256")   # and bit-identical to the 256 x 256 tile
+    ref = run_matmul(client, a_dev, b_dev, dtype, out_dtype, rhs_transposed=rhs_t, lhs_transposed=lhs_t)
+    assert np.array_equal(got, ref)
 
 
 @pytest.mark.parametrize("variant", ["2sm_m512", "2sm_n256a1"])
@@ -79,7 +97,7 @@ def test_pair_tile_512_batched_fused_epilogue_and_pitched_output(client):
         assert np.max(np.abs(full[i, :, :N] - exp) / scale) <= 1e-5
 
 
-def test_pair_tile_512_is_never_chosen_automatically_and_rejects_other_dtypes(client):
+def test_pair_tile_512_rejects_dtypes_it_is_not_built_for(client):
     from cubecl_b200 import ServerError
     a_dev, _ = make_operand((256, 64), "f32", 341)
     b_dev, _ = make_operand((64, 256), "f32", 342)

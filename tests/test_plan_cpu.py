@@ -64,8 +64,12 @@ def test_headline_plan_is_one_persistent_2sm_launch(plan):
     rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert rc == 0
     lines = t.strip().splitlines()
-    # smem: 1 KB alignment slack + 6 x 32 KB operand stages + 1 KB barriers + 16 KB epilogue staging
-    assert lines[-1] == "launch gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1) block=256 smem=215040 cluster=2"
+    # 16-bit in and out: the 512 x 256 pair tile (7 waves of 74 pairs instead of 14, measured x1.06 per FLOP)
+    # smem: 1 KB alignment slack + 4 x 48 KB operand stages + 1 KB barriers + 32 KB epilogue staging
+    assert lines[-1] == "launch gemm_bf16_bf16_2sm_m512_kn grid=(148,1,1) block=384 smem=231424 cluster=2"
+    # an f32 result keeps the double-accumulator 256 x 256 tile: 1 KB + 6 x 32 KB + 1 KB + 16 KB
+    rc, t32 = plan.matmul(BF16, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0 and t32.strip().splitlines()[-1] == "launch gemm_bf16_f32_2sm_n256_kn grid=(148,1,1) block=256 smem=215040 cluster=2"
     # A: K-major box [64 k x 128 m]; B (row-major [K,N]): MN-major box [64 n x 64 k]; both SWIZZLE_128B (enum 3)
     assert "tmap esz=2 dims=(8192,8192,1) strides=(16384,134217728) box=(64,128) swizzle=3" in lines[0]
     assert "box=(64,64) swizzle=3" in lines[1]
@@ -122,10 +126,10 @@ def test_tail_split_policy(plan):
     rc, t = mm(512, 16384)
     assert rc == 0 and "tail split" not in t
     plan.option("gemm.split_k", "3")
-    rc, t = mm(4096, 4096)
+    rc, t = mm(4096, 4096, out=F32)            # (bf16 -> bf16 runs the 512 x 256 tile, which is never sliced)
     assert rc == 0 and "34 tiles x 3 k-slices" in t
     plan.option("gemm.split_k", "9")
-    rc, t = mm(4096, 4096)
+    rc, t = mm(4096, 4096, out=F32)
     assert rc != 0
 
 
@@ -205,10 +209,16 @@ def test_shape_errors_match_the_reference_rule(plan):
 
 def test_wave_model_prefers_big_tiles(plan):
     # 4096^3: 256 tiles of 256x256 = 4 waves on 74 CTA pairs; the 256x128 tile would be 7 half-cost waves but it is
-    # L2-bandwidth bound (measured 0.66 efficiency) -> 2sm_n256 stays
+    # L2-bandwidth bound (measured 0.66 efficiency) -> 2sm_n256 stays for an f32 result ...
     n = 4096
+    rc, t = plan.matmul(BF16, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert "gemm_bf16_f32_2sm_n256_kn grid=(148,1,1)" in t
+    # ... and 128 tiles of 512x256 = 2 waves of twice the work at x1.06 efficiency win for a 16-bit result
     rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
-    assert "gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1)" in t
+    assert "gemm_bf16_bf16_2sm_m512_kn grid=(148,1,1)" in t
+    # 2048^2 outputs: 64 tiles of 256x256 (one wave) beat 32 tiles of 512x256 (one wave of twice the work)
+    rc, t = plan.matmul(BF16, BF16, [2048, n], [n, 1], [n, 2048], [2048, 1], [2048, 2048], [2048, 1])
+    assert "gemm_bf16_bf16_2sm_n256_kn grid=(128,1,1)" in t
     plan.option("gemm.variant", "2sm_n128")
     rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert "gemm_bf16_bf16_2sm_n128_kn" in t and "smem=215040" in t
@@ -262,11 +272,8 @@ def test_device_only_entry_points_refuse_a_planning_context(plan):
     assert plan.lib.b200_sync(plan.ctx, None) == 0
 
 
-def test_pair_tile_512_plan_is_opt_in_with_384_threads_and_no_tail_split(plan):
+def test_pair_tile_512_plan_has_384_threads_and_no_tail_split(plan):
     n = 8192
-    # auto never picks the opt-in variants
-    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
-    assert rc == 0 and "2sm_n256_kn" in t and "m512" not in t and "a1" not in t
     plan.option("gemm.variant", "2sm_m512")
     rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert rc == 0
@@ -283,8 +290,16 @@ def test_pair_tile_512_plan_is_opt_in_with_384_threads_and_no_tail_split(plan):
     # small M: 2 tiles of 512 rows x 1 -> 2 pairs
     rc, t = plan.matmul(BF16, F32, [600, 256], [256, 1], [256, 256], [256, 1], [600, 256], [256, 1])
     assert rc == 0 and "gemm_bf16_f32_2sm_m512_kn grid=(4,1,1) block=384" in t
-    # dtypes without an instantiation are refused, not silently re-routed
+    # fp8 has the tile too, but only when forced (auto keeps fp8 on 2sm_n256 until the tile is measured there)
     rc, t = plan.matmul(E4M3, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0 and "launch gemm_e4m3_bf16_2sm_m512_kn grid=(148,1,1) block=384 smem=231424 cluster=2" in t
+    plan.option("gemm.variant", "auto")
+    rc, t = plan.matmul(E4M3, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0 and "gemm_e4m3_bf16_2sm_n256_kn" in t
+    plan.option("gemm.variant", "2sm_m512")
+    # dtypes without an instantiation are refused, not silently re-routed
+    plan.option("gemm.f32", "tf32")
+    rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert rc != 0
     plan.option("gemm.variant", "2sm_n256a1")
     plan.option("gemm.split_k", "auto")

@@ -85,7 +85,7 @@ print(f"bf16 {N}^3, identical operand bits, CUDA events; order: cuBLAS, ours, cu
 rows = []
 for rep in range(2):
     rows.append(("cublas", protocol(cublas_events, f"cuBLAS (torch.matmul) #{rep}")))
-    rows.append(("ours", protocol(ours_events, f"gemm_bf16_bf16_2sm_n256_kn #{rep}")))
+    rows.append(("ours", protocol(ours_events, f"ours (gemm.variant=auto) #{rep}")))
 for i, name in enumerate(("best-of-10 single", "mean of 50", "sustained")):
     cb = min(r[1][i] for r in rows if r[0] == "cublas")
     us = min(r[1][i] for r in rows if r[0] == "ours")
