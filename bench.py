@@ -527,14 +527,11 @@ def main():
             # former; fp8: forced, to decide its default)
             c.set_option("gemm.variant", "2sm_n256")
             ms_bn, _ = timed(mm_step, extra_steps, 3)
+            ms_8n, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
             c.set_option("gemm.variant", "auto")
             line["tile_variants_8192"] = {"unit": "TFLOP/s", "bf16_2sm_n256": world * FLOPS_MM * extra_steps / (ms_bn * 1e-3) / 1e12,
-                                          "note": "gemm.variant forced; the headline (auto) runs bf16 on 2sm_m512, matmul_fp8_8192 runs 2sm_n256"}
-            if os.environ.get("B200_BENCH_EXPERIMENTAL") == "1":     # forced-only kernels that are not a default anywhere yet
-                c.set_option("gemm.variant", "2sm_m512")
-                ms_8m, _ = timed(lambda: matmul.launch(c, a8, b8, o), extra_steps, 3)
-                c.set_option("gemm.variant", "auto")
-                line["tile_variants_8192"]["fp8_2sm_m512"] = world * FLOPS_MM * extra_steps / (ms_8m * 1e-3) / 1e12
+                                          "fp8_2sm_n256": world * FLOPS_MM * extra_steps / (ms_8n * 1e-3) / 1e12,
+                                          "note": "gemm.variant forced to the 256x256 double-accumulator tile; the headline and matmul_fp8_8192 (auto) run the 512x256 pair tile 2sm_m512"}
             # widening row: block-scaled MX formats -- tcgen05 kind::mxf8f6f4 / kind::mxf4, ue8m0 scale per 32 K,
             # row-major scales as the reference's scaled MMA takes them (the two packing passes run inside the timed call)
             import numpy as _np

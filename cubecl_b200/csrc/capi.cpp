@@ -788,7 +788,8 @@ static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0, 1}, {"2sm_n
                                         // 512 x 256 pair tile, one accumulator stage, 384 threads (gemm_tcgen05.cu, MT = 2).  Measured
                                         // bf16 8192^3, same box, power state equalised (profiles/r01_pair_tile_ab.log): x1.059 of
                                         // 2sm_n256 in a 50-launch burst and x1.058 held for 1 s (25 % less L2->SM operand traffic
-                                        // -> 1.53 instead of 1.45 GHz under the power cap), 0.98 of cuBLAS
+                                        // -> 1.53 instead of 1.45 GHz under the power cap), 0.98 of cuBLAS; fp8 e4m3 8192^3: x1.04
+                                        // (3223 vs 3098 TFLOP/s, profiles/r01_bench_n1.json tile_variants_8192)
                                         {"2sm_m512", 2, 256, 4, 1.06, 2},
                                         // diagnostic: 256 x 256 tile with ONE accumulator stage (bf16 -> bf16, K-major lhs only)
                                         {"2sm_n256a1", 2, 256, 6, 0.0, 1}};
@@ -933,7 +934,6 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (g.mx_kind && v.mt != 1) continue;                       // block-scaled kinds have no two-unit instantiation
     // the two-unit tile hides its epilogue only on the packed-register path (16-bit outputs); f32 outputs stay on 2sm_n256
     if (forced == "auto" && v.mt == 2 && !(g.out_dtype == B200_BF16 || g.out_dtype == B200_F16)) continue;
-    if (forced == "auto" && v.mt == 2 && !(g.in_dtype == B200_BF16 || g.in_dtype == B200_F16)) continue;  // fp8: forced only until measured
     const uint64_t tile_m = 128ull * v.cg * v.mt;
     const uint64_t tm = (g.M + tile_m - 1) / tile_m, tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;

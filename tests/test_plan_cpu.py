@@ -290,12 +290,14 @@ def test_pair_tile_512_plan_has_384_threads_and_no_tail_split(plan):
     # small M: 2 tiles of 512 rows x 1 -> 2 pairs
     rc, t = plan.matmul(BF16, F32, [600, 256], [256, 1], [256, 256], [256, 1], [600, 256], [256, 1])
     assert rc == 0 and "gemm_bf16_f32_2sm_m512_kn grid=(4,1,1) block=384" in t
-    # fp8 has the tile too, but only when forced (auto keeps fp8 on 2sm_n256 until the tile is measured there)
+    # fp8 runs the same tile (measured x1.04 at 8192^3), forced or chosen by the wave model; f32 results stay on 2sm_n256
     rc, t = plan.matmul(E4M3, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert rc == 0 and "launch gemm_e4m3_bf16_2sm_m512_kn grid=(148,1,1) block=384 smem=231424 cluster=2" in t
     plan.option("gemm.variant", "auto")
     rc, t = plan.matmul(E4M3, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
-    assert rc == 0 and "gemm_e4m3_bf16_2sm_n256_kn" in t
+    assert rc == 0 and "gemm_e4m3_bf16_2sm_m512_kn" in t
+    rc, t = plan.matmul(E4M3, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0 and "gemm_e4m3_f32_2sm_n256_kn" in t
     plan.option("gemm.variant", "2sm_m512")
     # dtypes without an instantiation are refused, not silently re-routed
     plan.option("gemm.f32", "tf32")
