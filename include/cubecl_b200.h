@@ -95,7 +95,8 @@ int b200_get_props(b200_ctx* ctx, b200_props* out);
 int b200_plan_begin(int num_sms, b200_ctx** out);
 int b200_plan_text(b200_ctx* ctx, char* buf, size_t capacity, size_t* needed);
 /* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
- * (auto|2sm_n256|2sm_n128|1sm_n128|simt), "gemm.f32" (3xtf32|tf32), "gemm.group_m", "gemm.split_k" (auto|off|1..8: deterministic K-split of the last partial wave), "gemm.epilogue" (tma|direct), "reduce.row_balance" (off|on: spread rows over more threads when the last wave of a warp-per-row launch would be nearly empty), "reduce.variant"
+ * (auto|2sm_m512|2sm_n256|2sm_n128|1sm_n128|simt; 2sm_n256a1 = single-accumulator diagnostic), "gemm.f32" (3xtf32|tf32), "gemm.group_m",
+ * "gemm.l2_promotion" (256|128|64|0: TMA L2 promotion bytes of the operand tensor maps), "gemm.split_k" (auto|off|1..8: deterministic K-split of the last partial wave), "gemm.epilogue" (tma|direct), "reduce.row_balance" (off|on: spread rows over more threads when the last wave of a warp-per-row launch would be nearly empty), "reduce.variant"
  * (auto|u2|u4|u8|u16|b4|b8|w2|w4), "reduce.threads", "reduce.blocks_per_sm". */
 int b200_set_option(b200_ctx* ctx, const char* key, const char* value);
 /* Number of device kernels this context has launched so far (bench.py reports it as gpu_launches). */
