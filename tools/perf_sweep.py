@@ -66,10 +66,10 @@ if "gemm" in what:
         for mode in (("tf32", "3xtf32") if idt == "f32" else ("-",)):
             if idt == "f32":
                 c.set_option("gemm.f32", mode)
-            for variant in (("2sm_n256", "2sm_n128", "1sm_n128") if (idt == "bf16" and batch == 1) else
-                            ("2sm_n256", "1sm_n128") if idt.startswith("f8") else ("2sm_n256", "2sm_n128", "1sm_n128")):
+            for variant in (("2sm_m512", "2sm_n256", "2sm_n128", "1sm_n128") if idt == "bf16" else
+                            ("2sm_m512", "2sm_n256", "1sm_n128") if idt.startswith("f8") else ("2sm_n256", "2sm_n128", "1sm_n128")):
                 for rhs_t in (False, True):
-                    for gm in ((8, 4, 16) if (variant == "2sm_n256" and not rhs_t and idt == "bf16" and batch == 1) else (8,)):
+                    for gm in ((8, 4, 16) if (variant in ("2sm_n256", "2sm_m512") and not rhs_t and idt == "bf16" and batch == 1) else (8,)):
                         c.set_option("gemm.variant", variant)
                         c.set_option("gemm.group_m", gm)
                         bb = b.transposed() if rhs_t else b
