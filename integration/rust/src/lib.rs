@@ -9,6 +9,7 @@
 //! passes them here together with the `CUstream` of the current `StreamId` (crates/cubecl-cuda/src/compute/server.rs:
 //! 1024-1144); errors are queued on the stream like any launch error (server.rs:269-284).  See INTEGRATION.md.
 
+pub mod launch;
 pub mod sys;
 
 use core::ffi::{c_int, c_void, CStr};

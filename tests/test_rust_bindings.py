@@ -19,6 +19,7 @@ spec.loader.exec_module(gen)
 HEADER = (ROOT / "include" / "cubecl_b200.h").read_text()
 SYS_RS = (ROOT / "integration" / "rust" / "src" / "sys.rs").read_text()
 LIB_RS = (ROOT / "integration" / "rust" / "src" / "lib.rs").read_text()
+LAUNCH_RS = (ROOT / "integration" / "rust" / "src" / "launch.rs").read_text()
 
 
 def test_sys_rs_is_what_the_header_generates():
@@ -80,3 +81,18 @@ def test_safe_layer_enums_carry_the_header_values():
         r = {norm(k): v for k, v in rust_enum(rust).items()}
         h = {norm(k[len(prefix):] if k.startswith(prefix) else k[len("B200_"):]): v for k, v in header[c].items()}
         assert r == h, (rust, r, h)
+
+
+def test_launch_surface_only_uses_what_the_safe_layer_exports():
+    # launch.rs (matmul::launch / reduce::launch over TensorHandle) is built on Context methods and crate-level items
+    assert "pub mod launch;" in LIB_RS
+    for m in re.finditer(r"ctx\.(\w+)\s*\(", LAUNCH_RS):
+        decl = re.search(r"pub (?:unsafe )?fn " + m.group(1) + r"\s*\(([^{]*?)\)\s*->", LIB_RS, flags=re.S)
+        assert decl, f"launch.rs calls Context::{m.group(1)}, which lib.rs does not define"
+        want = len([a for a in decl.group(1).split(",") if a.strip() and "self" not in a])
+        assert _call_args(LAUNCH_RS, m.end() - 1) == want, m.group(1)
+    imported = re.search(r"use crate::\{(.*?)\};", LAUNCH_RS).group(1).split(",")
+    for item in (i.strip() for i in imported):
+        assert re.search(r"pub (?:struct|enum|fn|type) " + item + r"\b", LIB_RS) or re.search(r"pub use sys::\{[^}]*\b" + item + r"\b", LIB_RS), item
+    # the shape rule is the one the Python mirror implements (shape.rs:489-517)
+    assert "if l == r || r == 1" in LAUNCH_RS and "else if l == 1" in LAUNCH_RS
