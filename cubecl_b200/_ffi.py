@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200_get_props": (C.c_int, [_vp, C.POINTER(Props)]),
     "b200_set_option": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
     "b200_launch_count": (C.c_int, [_vp, _u64p]),
+    "b200_last_kernel": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "b200_alloc": (C.c_int, [_vp, C.c_size_t, _u64p]),
     "b200_free": (C.c_int, [_vp, C.c_uint64]),
     "b200_memory_usage": (C.c_int, [_vp, _u64p, _u64p]),
@@ -90,6 +91,7 @@ SIGNATURES = {
                                      C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]),
     "b200_reduce": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _u64p, C.c_int]),
     "b200_reduce_strided": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _u64p, _u64p, C.c_int]),
+    "b200_reduce_debug": (C.c_int, [_vp, _vp, _u64p]),
     "b200_into_contiguous": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _u64p, _u64p]),
     "b200_comm_get_unique_id": (C.c_int, [_vp, _vp]),
     "b200_comm_init": (C.c_int, [_vp, _intp, C.c_int, _vp]),

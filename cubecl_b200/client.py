@@ -117,6 +117,18 @@ class ComputeClient:
     def set_option(self, key: str, value) -> None:
         _ffi.check(self._lib.b200_set_option(self._ctx, key.encode(), str(value).encode()))
 
+    def last_kernel(self) -> str:
+        """Entry-point name of the most recently launched kernel (what a harness reports as the kernel it timed)."""
+        buf = C.create_string_buffer(256)
+        _ffi.check(self._lib.b200_last_kernel(self._ctx, buf, 256))
+        return buf.value.decode()
+
+    def reduce_debug(self, stream=None) -> list[int]:
+        """[exchange ns, grid-stage ns, 0, 0] of the last fused reduce + exchange launched with reduce.debug=1."""
+        words = (C.c_uint64 * 4)()
+        _ffi.check(self._lib.b200_reduce_debug(self._ctx, stream, words))
+        return [int(w) for w in words]
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         _ffi.check(self._lib.b200_launch_count(self._ctx, C.byref(n)))

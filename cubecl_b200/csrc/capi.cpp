@@ -230,10 +230,18 @@ struct ScaledSimtParams {
   uint32_t a_bmul, b_bmul, scale_ue4m3, pad1;
 };
 struct ReduceParams {
-  uint64_t in, out, ws;
+  uint64_t in, out, out2, ws;
   uint64_t outer, len, inner;
+  uint64_t s_outer, s_len;       // element strides of the outer and the reduced axis
+  uint64_t row_len, row_pitch;   // inner offset i -> (i / row_len) * row_pitch + i % row_len (row_len == inner: no pitch)
+  uint64_t seg_len;              // the reduced axis is cut into nseg segments (first pass of a two-pass reduction)
+  uint32_t nseg, ctu;
   float scale;
-  uint32_t pad;
+  uint32_t flags;                // 1: record stage timings in the workspace debug words, 2: column kernels use vector units
+};
+struct ArgCombineParams {
+  uint64_t keys, idx, out;
+  uint64_t outer, nseg, inner;
 };
 struct FillParams {
   uint64_t out, n, seed;
@@ -256,9 +264,13 @@ struct XgpuParams {
   uint32_t rank, nranks, epoch, pad;
   uint64_t index_offset;
 };
-static constexpr size_t kMailboxBytes = 4096;
+// One 256-byte slot block (value + index words, two epoch parities, eight source ranks) per DEVICE SET, addressed by the
+// set's device bitmask: overlapping sets ({0,1} and {0,1,2,3}) never share slots, and every rank derives the same offset.
+static constexpr size_t kMailboxSetBytes = 256;
+static constexpr size_t kMailboxBytes = 256 * kMailboxSetBytes;
 static constexpr uint32_t kWsMaxBlocks = 4096;
 static constexpr uint32_t kWsTicketOffset = kWsMaxBlocks * 4 + kWsMaxBlocks * 8;
+static constexpr uint32_t kWsDebugOffset = kWsTicketOffset + 64;         // four u64 words written by the reduce grid stage on request
 static constexpr uint32_t kWsGemmTicketOffset = kWsTicketOffset + 256;  // u32 per (tail tile, CTA rank) of a split GEMM
 static constexpr size_t kWsBytes = kWsGemmTicketOffset + 1024;
 
@@ -315,6 +327,7 @@ struct b200_ctx {
   bool dry = false;
   std::string plan;
   std::string pending_kernel;
+  std::string last_kernel;         // name of the most recently launched kernel (b200_last_kernel)
   uint64_t fake_next = 0x7000000000ull;
 };
 
@@ -348,6 +361,7 @@ static int load_module(b200_ctx* c, const unsigned char* begin, const unsigned c
 }
 
 static int get_func(b200_ctx* c, const std::string& name, CUfunction* out) {
+  c->last_kernel = name;
   if (c->dry) { c->pending_kernel = name; *out = nullptr; return B200_OK; }
   auto it = c->funcs.find(name);
   if (it != c->funcs.end()) { *out = it->second; return B200_OK; }
@@ -502,11 +516,18 @@ extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
 
 extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
-  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "reduce.row_balance", "reduce.variant", "reduce.threads",
-                                "reduce.blocks_per_sm"};
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "reduce.variant", "reduce.threads",
+                                "reduce.blocks_per_sm", "reduce.rows_vpt", "reduce.rows_blocks_per_sm", "reduce.cols_blocks_per_sm",
+                                "reduce.debug"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
   return fail(B200_ERR_INVALID_ARG, "unknown option '%s'", key);
+}
+
+extern "C" int b200_last_kernel(b200_ctx* c, char* buf, size_t capacity) {
+  if (!c || !buf || capacity == 0) return fail(B200_ERR_INVALID_ARG, "last_kernel: bad arguments");
+  snprintf(buf, capacity, "%s", c->last_kernel.c_str());
+  return B200_OK;
 }
 
 extern "C" int b200_launch_count(b200_ctx* c, uint64_t* count) {
@@ -1375,147 +1396,335 @@ static const char* op_tag(int op) {
 static const char* dt_tag(int dt) { return dt == B200_F32 ? "f32" : dt == B200_F16 ? "f16" : dt == B200_BF16 ? "bf16" : nullptr; }
 static bool fill_dtype_ok(int dt) { return dt_tag(dt) || dt == B200_F8E4M3 || dt == B200_F8E5M2; }
 
-static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, uint64_t in, uint64_t out, uint64_t n, float scale) {
-  std::string name = std::string("reduce_all_") + op_tag(op) + "_" + dt_tag(dt);
+extern "C" int b200_into_contiguous(b200_ctx* c, b200_stream s, b200_dtype dtype, b200_dptr in, b200_dptr out, int rank,
+                                    const uint64_t* shape, const uint64_t* strides);
+
+// A reducible VIEW of the input: logical [outer, len, inner] with explicit element strides and an optional row pitch.
+struct RView {
+  uint64_t in = 0;
+  uint64_t outer = 1, len = 1, inner = 1;
+  uint64_t s_outer = 0, s_len = 1;
+  uint64_t row_len = 1, row_pitch = 1;
+};
+
+static unsigned opt_uint(b200_ctx* c, const char* key, unsigned dflt, unsigned lo, unsigned hi) {
+  const std::string v = opt(c, key, "");
+  if (v.empty()) return dflt;
+  const long x = atol(v.c_str());
+  return (unsigned)std::min<long>(hi, std::max<long>(lo, x));
+}
+static uint64_t pow2_ceil(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+static uint64_t pow2_floor(uint64_t x) { uint64_t p = 1; while (p * 2 <= x) p <<= 1; return p; }
+static uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Reduce every element of the view `v` (v.len elements in logical rows of v.row_len, v.row_pitch apart) to out[0].
+static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t out, float scale) {
   const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
-  unsigned threads = 512, bps = 2;
-  if (!arg && op_tag(op) == std::string("sum") && dt == B200_F32) {
-    const std::string v = opt(c, "reduce.variant", "auto");
-    if (v != "auto" && v != "u8") name += "_" + v;
+  const bool pitched = v.row_len != v.len;
+  const uint64_t n = v.len;
+  const size_t esz = dtype_size(dt);
+  std::string name = std::string(pitched ? "reduce_allp_" : "reduce_all_") + op_tag(op) + "_" + dt_tag(dt);
+  unsigned threads = opt_uint(c, "reduce.threads", 512, 32, 512) / 32 * 32;
+  unsigned bps = opt_uint(c, "reduce.blocks_per_sm", 4, 1, 64);
+  unsigned smem = 0;
+  bool bulk = false;
+  if (!pitched && !arg) {
+    // variants: the plain 128-bit streaming kernel, its tuning forms (f32 sum only) and the bulk-copy staged kernel
+    const std::string var = opt(c, "reduce.variant", "auto");
+    if (var == "tma") {
+      bulk = n * esz >= 64 * 16384;           // needs whole 16 KB tiles to be worth a ring; small inputs use plain loads
+    } else if (var != "auto" && var != "u8") {
+      if (std::string(op_tag(op)) == "sum" && dt == B200_F32) name += "_" + var;
+    }
   }
-  threads = (unsigned)std::min(512, std::max(32, atoi(opt(c, "reduce.threads", "512").c_str())));
-  threads = threads / 32 * 32;
-  bps = (unsigned)std::max(1, atoi(opt(c, "reduce.blocks_per_sm", "4").c_str()));
+  const uint64_t vec = 16 / esz;
+  unsigned grid;
+  if (bulk) {
+    name += "_tma";
+    threads = 256 + 32;                       // eight consumer warps + one producer warp
+    smem = 8 * 16384 + 128;
+    const uint64_t tiles = n * esz / 16384;
+    grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)c->props.num_sms * opt_uint(c, "reduce.blocks_per_sm", 1, 1, 1)));
+  } else {
+    const uint64_t want = (n / vec + threads - 1) / threads;  // blocks that still get >= 1 vector per thread
+    grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)c->props.num_sms * bps, kWsMaxBlocks)));
+  }
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;
+  if (smem && !c->dry) CU_CHECK(g_drv.cuFuncSetAttribute_p(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
   CUdeviceptr ws;
   rc = reduce_workspace(c, st, &ws);
   if (rc) return rc;
-  const uint64_t vec = 16 / dtype_size(dt);
-  uint64_t want = (n / vec + threads - 1) / threads;  // blocks that still get >= 1 vector per thread
-  unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)c->props.num_sms * bps, kWsMaxBlocks)));
-  ReduceParams p{in, out, ws, 1, n, 1, scale, 0};
+  ReduceParams p{};
+  p.in = v.in; p.out = out; p.ws = ws;
+  p.outer = 1; p.len = n; p.inner = 1;
+  p.row_len = v.row_len; p.row_pitch = v.row_pitch;
+  p.seg_len = n; p.nseg = 1; p.scale = scale;
   void* args[] = {&p};
-  return launch(c, f, grid, 1, 1, threads, 0, 1, st, args);
+  return launch(c, f, grid, 1, 1, threads, smem, 1, st, args);
 }
 
-static int launch_reduce_rows(b200_ctx* c, CUstream st, int op, int dt, uint64_t in, uint64_t out, uint64_t outer, uint64_t len, float scale) {
+// One launch of the rows kernel: items = outer x nseg, item (o, s) covers elements [s * seg_len, ..) of row o.
+static int launch_rows_kernel(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t seg_len, uint64_t out, uint64_t out2, float scale) {
   const std::string name = std::string("reduce_rows_") + op_tag(op) + "_" + dt_tag(dt);
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;
-  const uint64_t vec = 16 / dtype_size(dt);
-  // threads per row (power of two).  Many rows: at most a warp per row (no block barrier per row, many rows in flight);
-  // few rows: up to a 512-thread block per row so the row itself supplies the parallelism.  ~4 vectors per thread.
-  const uint64_t tpr_cap = (outer >= (uint64_t)c->props.num_sms * 16 && len * dtype_size(dt) <= (128u << 10)) ? 32 : 512;
-  uint64_t tpr = 1;
-  while (tpr < tpr_cap && tpr * vec * 4 < len) tpr <<= 1;
-  // Wave quantisation: with a warp per row, R = SMs x 48 rows are resident (6 blocks of 256 threads, register-limited) and
-  // the kernel lasts ceil(outer / R) row-times -- 8192 rows of 32 KB are 1.15 waves, i.e. a second, nearly empty round
-  // (ncu: SMs idle 22 % of the launch).  Spreading a row over more threads shortens the row-time faster than it adds
-  // rounds, so take the smallest thread count whose last round is at least 90 % full (each thread keeps >= 2 vectors).
-  if (tpr == 32 && tpr_cap == 32 && opt(c, "reduce.row_balance", "off") == "on") {
-    auto fill = [&](uint64_t t) {
-      const double resident = static_cast<double>(c->props.num_sms) * (1536.0 / static_cast<double>(t));
-      const double w = static_cast<double>(outer) / resident;
-      return w <= 1.0 ? 1.0 : w / std::ceil(w);   // everything resident at once: nothing to balance
-    };
-    uint64_t best = tpr;
-    for (uint64_t t = tpr; t <= 512 && t * vec * 2 <= len; t <<= 1) {
-      if (fill(t) >= 0.9) { best = t; break; }
-      if (fill(t) > fill(best) + 0.05) best = t;
-    }
-    tpr = best;
-  }
+  const size_t esz = dtype_size(dt);
+  const uint64_t vec = 16 / esz;
+  const uint64_t nseg = ceil_div(v.len, seg_len), items = v.outer * nseg;
+  // Threads per item (power of two): about `vpt` 128-bit vectors per thread, so a 32 KB row is one 256-thread block and the
+  // grid has many more blocks than resident slots (the hardware scheduler balances the tail block by block -- a warp per
+  // 32 KB row left the last, nearly empty wave running at a third of the bandwidth: ncu, round 1).
+  const unsigned vpt = opt_uint(c, "reduce.rows_vpt", 8, 1, 64);
+  const uint64_t nv = ceil_div(std::min(seg_len, v.len), vec);
+  uint64_t tpr = std::min<uint64_t>(512, pow2_ceil(ceil_div(nv, vpt)));
   int tpr_log2 = 0;
   while ((1ull << tpr_log2) < tpr) ++tpr_log2;
-  const unsigned threads = tpr > 32 ? (unsigned)tpr : 256;
-  const uint64_t rows_per_block = threads >> tpr_log2;
-  const uint64_t blocks = (outer + rows_per_block - 1) / rows_per_block;
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)c->props.num_sms * 16));
-  ReduceParams p{in, out, 0, outer, len, 1, scale, 0};
+  const unsigned threads = tpr > 256 ? (unsigned)tpr : 256;
+  const uint64_t items_per_block = threads >> tpr_log2;
+  uint64_t blocks = ceil_div(items, items_per_block);
+  const bool uniform = (v.in % 16) == 0 && ((v.s_outer * esz) % 16) == 0 && (v.len % vec) == 0;
+  if (tpr <= 32 && uniform && nseg == 1 && v.len / vec <= tpr) blocks = ceil_div(blocks, 4);  // short rows: four rows in flight per thread group
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(blocks, 0x7FFFFFFFull));
+  ReduceParams p{};
+  p.in = v.in; p.out = out; p.out2 = out2;
+  p.outer = v.outer; p.len = v.len; p.inner = 1;
+  p.s_outer = v.s_outer; p.s_len = 1;
+  p.row_len = 1; p.row_pitch = 1;
+  p.seg_len = seg_len; p.nseg = (uint32_t)nseg; p.scale = scale;
   void* args[] = {&p, &tpr_log2};
   return launch(c, f, grid, 1, 1, threads, 0, 1, st, args);
 }
 
-static int launch_reduce_cols(b200_ctx* c, CUstream st, int op, int dt, uint64_t in, uint64_t out, uint64_t outer, uint64_t len, uint64_t inner, float scale) {
+// One launch of the column kernel over the view (items = outer x nseg x column tiles).
+static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t seg_len, uint64_t out, uint64_t out2, float scale) {
   const std::string name = std::string("reduce_cols_") + op_tag(op) + "_" + dt_tag(dt);
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;
-  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
-  const uint64_t vec = 16 / dtype_size(dt);
-  // value ops read 128-bit vectors of `vec` consecutive columns per thread when the layout allows it (kernel re-checks)
-  const bool vector_path = !arg && inner % vec == 0 && in % 16 == 0 && out % 16 == 0;
-  const uint64_t total = vector_path ? outer * (inner / vec) : outer * inner;
-  const unsigned threads = 256;
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((total + threads - 1) / threads, (uint64_t)c->props.num_sms * 16));
-  ReduceParams p{in, out, 0, outer, len, inner, scale, 0};
+  const size_t esz = dtype_size(dt);
+  const uint64_t vec = 16 / esz;
+  const bool vector = v.inner % vec == 0 && v.row_len % vec == 0 && v.in % 16 == 0 && (v.s_len * esz) % 16 == 0 &&
+                      (v.s_outer * esz) % 16 == 0 && (v.row_pitch * esz) % 16 == 0;
+  const uint64_t units = vector ? v.inner / vec : v.inner;
+  const uint64_t nseg = ceil_div(v.len, seg_len);
+  const uint64_t seg = std::min(seg_len, v.len);
+  // tile shape: RL row lanes x ctu column units per 256-thread block.  A warp's worth of units (512 contiguous bytes per row
+  // in vector mode) keeps the loads coalesced; the rest of the block goes to row lanes as long as every lane still has ~4 rows
+  const uint64_t ctu_min = std::min<uint64_t>(units, 32);
+  const uint64_t rl_max = 256 / ctu_min;
+  const uint64_t rl = std::min<uint64_t>(rl_max, std::max<uint64_t>(1, pow2_floor(std::max<uint64_t>(1, seg / 4))));
+  const uint64_t ctu = std::min<uint64_t>(units, 256 / rl);
+  const uint64_t tiles = ceil_div(units, ctu);
+  const uint64_t items = v.outer * nseg * tiles;
+  const unsigned bps = 8;
+  // short axis: a block's item is small, so blocks walk several items (persistent grid); long axis: one item per block
+  const uint64_t cap = seg * ctu * (vector ? 16 : esz) >= (64u << 10) ? 0x7FFFFFFFull : (uint64_t)c->props.num_sms * bps;
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(items, cap));
+  ReduceParams p{};
+  p.in = v.in; p.out = out; p.out2 = out2;
+  p.outer = v.outer; p.len = v.len; p.inner = v.inner;
+  p.s_outer = v.s_outer; p.s_len = v.s_len;
+  p.row_len = v.row_len; p.row_pitch = v.row_pitch;
+  p.seg_len = seg_len; p.nseg = (uint32_t)nseg; p.ctu = (uint32_t)ctu; p.scale = scale;
+  p.flags = vector ? 2u : 0u;
   void* args[] = {&p};
-  return launch(c, f, grid, 1, 1, threads, 0, 1, st, args);
+  return launch(c, f, grid, 1, 1, 256, 0, 1, st, args);
+}
+
+static int launch_argcombine(b200_ctx* c, CUstream st, uint64_t keys, uint64_t idx, uint64_t out, uint64_t outer, uint64_t nseg, uint64_t inner) {
+  CUfunction f;
+  int rc = get_func(c, "reduce_argcombine", &f);
+  if (rc) return rc;
+  ArgCombineParams p{keys, idx, out, outer, nseg, inner};
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ceil_div(outer * inner, 256), (uint64_t)c->props.num_sms * 8));
+  void* args[] = {&p};
+  return launch(c, f, grid, 1, 1, 256, 0, 1, st, args);
+}
+
+// Reduce the `len` axis of the view.  Few outputs with a long axis are reduced in two passes (segments of the axis first,
+// then the per-segment partials), both deterministic; everything else is one launch.
+static int reduce_axis_view(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t out, float scale) {
+  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
+  const uint64_t sms = c->props.num_sms;
+  const size_t esz = dtype_size(dt);
+  const uint64_t vec = 16 / esz;
+  // Segment the axis when whole rows / columns cannot fill the machine: aim at ~16 blocks per SM (several waves of small
+  // blocks, so the block scheduler evens out the tail) while every segment keeps a useful amount of work.
+  uint64_t seg_len = v.len;
+  if (v.inner == 1) {
+    const unsigned bps = opt_uint(c, "reduce.rows_blocks_per_sm", 4, 1, 64);
+    if (v.outer < sms * bps && v.len >= 16384) {
+      const uint64_t nseg = std::min<uint64_t>(ceil_div(sms * 16, v.outer), v.len / 4096);
+      if (nseg > 1) seg_len = ceil_div(ceil_div(v.len, nseg), 512) * 512;   // 512 elements: segments stay vector-aligned
+    }
+  } else {
+    const uint64_t units = (v.inner % vec == 0) ? v.inner / vec : v.inner;
+    const uint64_t tiles = ceil_div(units, std::min<uint64_t>(units, 32));
+    const unsigned bps = opt_uint(c, "reduce.cols_blocks_per_sm", 4, 1, 64);
+    if (v.outer * tiles < sms * bps && v.len >= 256) {
+      const uint64_t nseg = std::min<uint64_t>(ceil_div(sms * 16, v.outer * tiles), v.len / 64);
+      if (nseg > 1) seg_len = ceil_div(v.len, nseg);
+    }
+  }
+  const uint64_t nseg = ceil_div(v.len, seg_len);
+  if (arg && nseg > 1 && !c->dry && v.len >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "arg-reduce: axis extent does not fit u32 indices");
+  if (nseg == 1) {
+    return v.inner == 1 ? launch_rows_kernel(c, st, op, dt, v, v.len, out, 0, scale) : launch_cols_kernel(c, st, op, dt, v, v.len, out, 0, scale);
+  }
+  // two passes: partials [outer, nseg, inner] (f32 values, or u32 keys + u32 indices), then the partials
+  const uint64_t count = v.outer * nseg * v.inner;
+  CUdeviceptr tmp = 0, tmp2 = 0;
+  int rc = pool_alloc(c, count * 4, &tmp, st);
+  if (rc) return rc;
+  if (arg) {
+    rc = pool_alloc(c, count * 4, &tmp2, st);
+    if (rc) { pool_free(c, tmp, st); return rc; }
+  }
+  rc = v.inner == 1 ? launch_rows_kernel(c, st, op, dt, v, seg_len, tmp, tmp2, 1.0f) : launch_cols_kernel(c, st, op, dt, v, seg_len, tmp, tmp2, 1.0f);
+  if (!rc) {
+    if (arg) {
+      rc = launch_argcombine(c, st, tmp, tmp2, out, v.outer, nseg, v.inner);
+    } else {
+      RView t;
+      t.in = tmp; t.outer = v.outer; t.len = nseg; t.inner = v.inner;
+      t.s_outer = nseg * v.inner; t.s_len = v.inner; t.row_len = v.inner; t.row_pitch = v.inner;
+      rc = v.inner == 1 ? launch_rows_kernel(c, st, op, B200_F32, t, nseg, out, 0, scale) : launch_cols_kernel(c, st, op, B200_F32, t, nseg, out, 0, scale);
+    }
+  }
+  pool_free(c, tmp, st);
+  if (tmp2) pool_free(c, tmp2, st);
+  return rc;
+}
+
+// Can the strided tensor be reduced IN PLACE?  Yes when, in memory order, it is a dense tensor whose innermost rows may be
+// pitched (what PitchedMemoryLayoutPolicy produces, crates/cubecl-runtime/src/allocator.rs:21-72) -- in any axis
+// permutation that keeps the kept axes in their logical order (a transposed view reduces the other physical axis).
+// Anything else (broadcast strides, gaps elsewhere, permuted outputs) goes through into_contiguous.
+static bool plan_view(int rank, const uint64_t* shape, const uint64_t* strides, int axis, bool arg, uint64_t in, RView* v) {
+  struct Dim { uint64_t ext, st; int pos; bool ax; };
+  std::vector<Dim> d;
+  bool unit_axis = false;
+  uint64_t expect = 1;
+  std::vector<uint64_t> cst(rank);
+  for (int i = rank - 1; i >= 0; --i) { cst[i] = expect; expect *= shape[i]; }
+  for (int i = 0; i < rank; ++i) {
+    if (shape[i] == 1) { if (i == axis) unit_axis = true; continue; }
+    d.push_back(Dim{shape[i], strides ? strides[i] : cst[i], i, i == axis});
+  }
+  std::stable_sort(d.begin(), d.end(), [](const Dim& a, const Dim& b) { return a.st > b.st; });
+  const int k = (int)d.size();
+  bool pitched = false;
+  if (k > 0) {
+    if (d[k - 1].st != 1) return false;
+    for (int j = k - 2; j >= 0; --j) {
+      const uint64_t e = d[j + 1].st * d[j + 1].ext;
+      if (d[j].st == e) continue;
+      if (j == k - 2 && d[j].st > e) { pitched = true; continue; }
+      return false;
+    }
+  }
+  // kept axes must appear in memory order exactly as in logical order (otherwise the output would need a permuted store)
+  int last = -1;
+  for (int j = 0; j < k; ++j) {
+    if (d[j].ax && !(axis < 0)) continue;
+    if (axis < 0 && !arg) continue;     // a value reduction over everything is order-independent
+    if (d[j].pos < last) return false;
+    last = d[j].pos;
+  }
+  v->in = in;
+  uint64_t total = 1;
+  for (int j = 0; j < k; ++j) total *= d[j].ext;
+  const uint64_t row = k > 0 ? d[k - 1].ext : 1, pitch = pitched ? d[k - 2].st : row;
+  if (axis < 0) {
+    v->outer = 1; v->len = total; v->inner = 1;
+    v->row_len = pitched ? row : total; v->row_pitch = pitched ? pitch : total;
+    return true;
+  }
+  if (unit_axis) {  // reducing an axis of extent 1: a (converting) copy of everything else
+    v->outer = 1; v->len = 1; v->s_len = 0; v->inner = total;
+    v->row_len = pitched ? row : total; v->row_pitch = pitched ? pitch : total;
+    return true;
+  }
+  int pa = -1;
+  for (int j = 0; j < k; ++j) if (d[j].ax) pa = j;
+  if (pa < 0) return false;
+  v->outer = 1; v->inner = 1;
+  for (int j = 0; j < pa; ++j) v->outer *= d[j].ext;
+  for (int j = pa + 1; j < k; ++j) v->inner *= d[j].ext;
+  v->len = d[pa].ext;
+  v->s_len = d[pa].st;
+  v->s_outer = pa > 0 ? d[pa - 1].st : 0;
+  if (pitched && pa <= k - 3) { v->row_len = row; v->row_pitch = pitch; }
+  else { v->row_len = v->inner; v->row_pitch = v->inner; }
+  return true;
+}
+
+static int reduce_impl(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
+                       int rank, const uint64_t* shape, const uint64_t* strides, int axis) {
+  if (!op_tag(op)) return fail(B200_ERR_INVALID_ARG, "reduce: unknown op %d", (int)op);
+  if (!dt_tag(in_dtype)) return fail(B200_ERR_UNSUPPORTED, "reduce: input dtype %d unsupported (f32, f16, bf16)", (int)in_dtype);
+  if (rank < 1 || rank > 8 || !shape) return fail(B200_ERR_INVALID_ARG, "reduce: bad rank/shape");
+  if (axis < -1 || axis >= rank) return fail(B200_ERR_INVALID_ARG, "reduce: axis %d out of range for rank %d", axis, rank);
+  uint64_t n = 1, len = 1;
+  for (int i = 0; i < rank; ++i) n *= shape[i];
+  len = axis < 0 ? n : shape[axis];
+  uint64_t outputs = 1;
+  for (int i = 0; i < rank; ++i) if (axis >= 0 && i != axis) outputs *= shape[i];
+  if (outputs == 0) return B200_OK;  // empty output
+  if (len == 0) return fail(B200_ERR_INVALID_ARG, "reduce: reduced extent is 0 (identity-filled outputs are not defined by the reference)");
+  if (!in || !out) return fail(B200_ERR_INVALID_ARG, "reduce: null device pointer");
+  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
+  if (arg && len >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "arg-reduce: axis extent %llu does not fit u32 indices", (unsigned long long)len);
+  if (in % dtype_size(in_dtype)) return fail(B200_ERR_INVALID_ARG, "reduce: input pointer is not aligned to its element size");
+  const float scale = (op == B200_REDUCE_MEAN) ? static_cast<float>(1.0 / static_cast<double>(len)) : 1.0f;
+  CUstream st = resolve_stream(c, s);
+  RView v;
+  if (plan_view(rank, shape, strides, axis, arg, in, &v)) {
+    if (axis < 0) return launch_reduce_all(c, st, op, in_dtype, v, out, scale);
+    return reduce_axis_view(c, st, op, in_dtype, v, out, scale);
+  }
+  // not reducible in place: gather into a compact temporary first (into_contiguous), then reduce that
+  CUdeviceptr tmp;
+  int rc = pool_alloc(c, n * dtype_size(in_dtype), &tmp, st);
+  if (rc) return rc;
+  rc = b200_into_contiguous(c, s, in_dtype, in, tmp, rank, shape, strides);
+  if (!rc) {
+    RView w;
+    const bool ok = plan_view(rank, shape, nullptr, axis, arg, tmp, &w);
+    rc = !ok ? fail(B200_ERR_UNKNOWN, "reduce: contiguous plan failed")
+             : axis < 0 ? launch_reduce_all(c, st, op, in_dtype, w, out, scale) : reduce_axis_view(c, st, op, in_dtype, w, out, scale);
+  }
+  pool_free(c, tmp, st);
+  return rc;
 }
 
 extern "C" int b200_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
                            int rank, const uint64_t* shape, int axis) {
   CTX_ENTER(c);
-  if (!op_tag(op)) return fail(B200_ERR_INVALID_ARG, "reduce: unknown op %d", (int)op);
-  if (!dt_tag(in_dtype)) return fail(B200_ERR_UNSUPPORTED, "reduce: input dtype %d unsupported (f32, f16, bf16)", (int)in_dtype);
-  if (rank < 1 || rank > 8 || !shape) return fail(B200_ERR_INVALID_ARG, "reduce: bad rank/shape");
-  if (axis < -1 || axis >= rank) return fail(B200_ERR_INVALID_ARG, "reduce: axis %d out of range for rank %d", axis, rank);
-  uint64_t outer = 1, len = 1, inner = 1;
-  if (axis == -1) {
-    for (int i = 0; i < rank; ++i) len *= shape[i];
-  } else {
-    for (int i = 0; i < axis; ++i) outer *= shape[i];
-    len = shape[axis];
-    for (int i = axis + 1; i < rank; ++i) inner *= shape[i];
-  }
-  if (outer * inner == 0) return B200_OK;  // empty output
-  if (len == 0) return fail(B200_ERR_INVALID_ARG, "reduce: reduced extent is 0 (identity-filled outputs are not defined by the reference)");
-  if (!in || !out) return fail(B200_ERR_INVALID_ARG, "reduce: null device pointer");
-  const bool arg = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
-  if (arg && len >= (1ull << 32)) return fail(B200_ERR_UNSUPPORTED, "arg-reduce: axis extent %llu does not fit u32 indices", (unsigned long long)len);
-  const float scale = (op == B200_REDUCE_MEAN) ? static_cast<float>(1.0 / static_cast<double>(len)) : 1.0f;
+  return reduce_impl(c, s, op, in_dtype, in, out, rank, shape, nullptr, axis);
+}
+
+extern "C" int b200_reduce_strided(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
+                                   int rank, const uint64_t* shape, const uint64_t* strides, int axis) {
+  CTX_ENTER(c);
+  return reduce_impl(c, s, op, in_dtype, in, out, rank, shape, strides, axis);
+}
+
+// Stage timings (ns) of the most recent fused reduce + exchange launched with option reduce.debug=1 on stream `s`:
+// words[0] = exchange (publish -> all peers seen), words[1] = partials + f64 tree of the last block.  Synchronises the stream.
+extern "C" int b200_reduce_debug(b200_ctx* c, b200_stream s, uint64_t* words4) {
+  CTX_ENTER_DEVICE(c);
+  if (!words4) return fail(B200_ERR_INVALID_ARG, "reduce_debug: null output");
   CUstream st = resolve_stream(c, s);
-  const uint64_t sms = c->props.num_sms;
-  const size_t esz = dtype_size(in_dtype);
-
-  if (outer == 1 && inner == 1) return launch_reduce_all(c, st, op, in_dtype, in, out, len, scale);
-
-  if (inner == 1) {
-    // few long rows: split every row into S segments, reduce [outer*S, len/S] to f32 partials, then reduce [outer, S]
-    if (!arg && outer < 2 * sms && len >= (1u << 16)) {
-      uint64_t S = 1;
-      while (outer * S < 4 * sms && len % (S * 2) == 0 && len / (S * 2) >= 4096 && ((len / (S * 2)) * esz) % 16 == 0) S *= 2;
-      if (S > 1) {
-        CUdeviceptr tmp;
-        int rc = pool_alloc(c, outer * S * 4, &tmp, st);
-        if (rc) return rc;
-        rc = launch_reduce_rows(c, st, op, in_dtype, in, tmp, outer * S, len / S, 1.0f);
-        if (!rc) rc = launch_reduce_rows(c, st, op, B200_F32, tmp, out, outer, S, scale);
-        pool_free(c, tmp, st);
-        return rc;
-      }
-    }
-    return launch_reduce_rows(c, st, op, in_dtype, in, out, outer, len, scale);
-  }
-
-  // inner > 1: few outputs but a long axis -> split the axis the same way
-  if (!arg && outer * inner < sms * 256 && len >= 64) {
-    uint64_t S = 1;
-    while (outer * S * inner < sms * 1024 && len % (S * 2) == 0 && len / (S * 2) >= 16) S *= 2;
-    if (S > 1) {
-      CUdeviceptr tmp;
-      int rc = pool_alloc(c, outer * S * inner * 4, &tmp, st);
-      if (rc) return rc;
-      rc = launch_reduce_cols(c, st, op, in_dtype, in, tmp, outer * S, len / S, inner, 1.0f);
-      if (!rc) rc = launch_reduce_cols(c, st, op, B200_F32, tmp, out, outer, S, inner, scale);
-      pool_free(c, tmp, st);
-      return rc;
-    }
-  }
-  return launch_reduce_cols(c, st, op, in_dtype, in, out, outer, len, inner, scale);
+  CUdeviceptr ws;
+  int rc = reduce_workspace(c, st, &ws);
+  if (rc) return rc;
+  CU_CHECK(g_drv.cuMemcpyDtoHAsync_p(words4, ws + kWsDebugOffset, 32, st));
+  CU_CHECK(g_drv.cuStreamSynchronize_p(st));
+  return B200_OK;
 }
 
 struct GatherParams {
@@ -1542,31 +1751,6 @@ extern "C" int b200_into_contiguous(b200_ctx* c, b200_stream s, b200_dtype dtype
   const unsigned grid = (unsigned)std::min<uint64_t>((p.n + 255) / 256, (uint64_t)c->props.num_sms * 32);
   void* args[] = {&p};
   return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, resolve_stream(c, s), args);
-}
-
-extern "C" int b200_reduce_strided(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in, b200_dptr out,
-                                   int rank, const uint64_t* shape, const uint64_t* strides, int axis) {
-  CTX_ENTER(c);
-  if (rank < 1 || rank > 8 || !shape) return fail(B200_ERR_INVALID_ARG, "reduce: bad rank/shape");
-  bool contiguous = true;
-  if (strides) {
-    uint64_t expect = 1;
-    for (int i = rank - 1; i >= 0; --i) {
-      if (shape[i] != 1 && strides[i] != expect) contiguous = false;
-      expect *= shape[i];
-    }
-  }
-  if (contiguous) return b200_reduce(c, s, op, in_dtype, in, out, rank, shape, axis);
-  uint64_t n = 1;
-  for (int i = 0; i < rank; ++i) n *= shape[i];
-  if (n == 0) return b200_reduce(c, s, op, in_dtype, in, out, rank, shape, axis);
-  CUdeviceptr tmp;
-  int rc = pool_alloc(c, n * dtype_size(in_dtype), &tmp, resolve_stream(c, s));
-  if (rc) return rc;
-  rc = b200_into_contiguous(c, s, in_dtype, in, tmp, rank, shape, strides);
-  if (!rc) rc = b200_reduce(c, s, op, in_dtype, tmp, out, rank, shape, axis);
-  pool_free(c, tmp, resolve_stream(c, s));
-  return rc;
 }
 
 // ================================================================================================ collectives
@@ -1682,13 +1866,16 @@ extern "C" int b200_p2p_connect(b200_ctx* c, const int* device_ids, int n, const
   if (c->p2p.count(key)) return B200_OK;
   P2PState st;
   st.n = n;
+  unsigned mask = 0;
+  for (int id : key) mask |= 1u << (static_cast<unsigned>(id) & 7u);
+  const uint64_t set_off = static_cast<uint64_t>(mask & 0xFFu) * kMailboxSetBytes;
   for (int r = 0; r < n; ++r) {
     int src = -1;
     for (int j = 0; j < n; ++j)
       if (device_ids[j] == key[r]) src = j;
     if (key[r] == c->device) {
       st.rank = r;
-      st.mailbox[r] = c->mailbox;
+      st.mailbox[r] = c->mailbox + set_off;
       continue;
     }
     if (pids[src] == static_cast<int64_t>(getpid())) {
@@ -1704,7 +1891,7 @@ extern "C" int b200_p2p_connect(b200_ctx* c, const int* device_ids, int n, const
       g_drv.cuDevicePrimaryCtxRelease_p(pd);
       if (r2 != CUDA_SUCCESS && r2 != CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED)
         return fail(map_cu(r2), "cuCtxEnablePeerAccess(%d) failed: %s", key[r], cu_err(r2));
-      st.mailbox[r] = local_ptrs[src];
+      st.mailbox[r] = local_ptrs[src] + set_off;
     } else {
       CUipcMemHandle h;
       memcpy(&h, static_cast<const char*>(ipc_handles) + static_cast<size_t>(src) * B200_IPC_HANDLE_BYTES, sizeof(h));
@@ -1712,7 +1899,7 @@ extern "C" int b200_p2p_connect(b200_ctx* c, const int* device_ids, int n, const
       CUresult r2 = g_drv.cuIpcOpenMemHandle_p(&mapped, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
       if (r2 != CUDA_SUCCESS) return fail(map_cu(r2), "cuIpcOpenMemHandle(device %d) failed: %s", key[r], cu_err(r2));
       st.opened.push_back(mapped);
-      st.mailbox[r] = mapped;
+      st.mailbox[r] = mapped + set_off;
     }
   }
   if (st.rank < 0) return fail(B200_ERR_INVALID_ARG, "p2p_connect: device %d is not in the device set", c->device);
@@ -1742,16 +1929,22 @@ static int reduce_all_reduce_impl(b200_ctx* c, b200_stream s, b200_reduce_op op,
   unsigned bps = (unsigned)std::max(1, atoi(opt(c, "reduce.blocks_per_sm", "4").c_str()));
   const uint64_t want = (n / 4 + threads - 1) / threads;
   unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)c->props.num_sms * bps, kWsMaxBlocks)));
-  ReduceParams p{in, out, ws, 1, n, 1, 1.0f, 0};
+  ReduceParams p{};
+  p.in = in; p.out = out; p.ws = ws;
+  p.outer = 1; p.len = n; p.inner = 1;
+  p.row_len = n; p.row_pitch = n; p.seg_len = n; p.nseg = 1; p.scale = 1.0f;
+  p.flags = opt(c, "reduce.debug", "0") == "1" ? 1u : 0u;
   XgpuParams xg;
   memset(&xg, 0, sizeof(xg));
   for (int r = 0; r < st.n; ++r) xg.mailbox[r] = st.mailbox[r];
   xg.rank = (uint32_t)st.rank;
   xg.nranks = (uint32_t)st.n;
   xg.index_offset = index_offset;
-  xg.epoch = ++st.epoch;  // every rank calls in the same order (collective semantics), so epochs agree
+  xg.epoch = st.epoch + 1;  // every rank calls in the same order (collective semantics), so epochs agree
   void* args[] = {&p, &xg};
-  return launch(c, f, grid, 1, 1, threads, 0, 1, cs, args);
+  rc = launch(c, f, grid, 1, 1, threads, 0, 1, cs, args);
+  if (!rc) st.epoch += 1;   // only a launch that really went out consumes the epoch (a failed call must not desynchronise the ranks)
+  return rc;
 }
 
 extern "C" int b200_reduce_all_reduce(b200_ctx* c, b200_stream s, b200_reduce_op op, b200_dtype in_dtype, b200_dptr in,

@@ -92,12 +92,35 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 #define B200_MBAR_TIMEOUT_NS 4000000000ull  // a pipeline wait longer than 4 s is a deadlock: trap loudly, never hang the GPU
 #endif
 
+// try_wait with a suspend-time hint: the thread may be parked by the hardware for up to `ns` before the instruction
+// returns false, instead of re-issuing the poll (fewer executed instructions per waiting warp, less issue-slot and power
+// pressure next to the MMA / TMA warps).
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return done;
+}
+
+#ifndef B200_MBAR_SUSPEND_NS
+#define B200_MBAR_SUSPEND_NS 20000u
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > B200_MBAR_TIMEOUT_NS) {
-      asm volatile("trap;");
+  // slow path: parked polls; the deadline is only looked at every 64 polls (the clock read is not free either)
+  uint64_t t0 = 0;
+  uint32_t polls = 0;
+  while (!mbar_try_wait_hint(bar, parity, B200_MBAR_SUSPEND_NS)) {
+    if ((++polls & 63u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > B200_MBAR_TIMEOUT_NS) asm volatile("trap;");
     }
   }
 }
@@ -157,6 +180,21 @@ __device__ __forceinline__ void tma_store_wait_read() {
 template <int N>
 __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 1-D bulk copy global -> shared (UBLKCP in SASS): `bytes` and both addresses multiples of 16; completes on `bar`.
+// `policy` is an L2 cache policy (createpolicy): streaming reads use evict_first so they do not displace resident data.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- tcgen05

@@ -96,11 +96,18 @@ int b200_plan_begin(int num_sms, b200_ctx** out);
 int b200_plan_text(b200_ctx* ctx, char* buf, size_t capacity, size_t* needed);
 /* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
  * (auto|2sm_m512|2sm_n256|2sm_n128|1sm_n128|simt; 2sm_n256a1 = single-accumulator diagnostic), "gemm.f32" (3xtf32|tf32), "gemm.group_m",
- * "gemm.l2_promotion" (256|128|64|0: TMA L2 promotion bytes of the operand tensor maps), "gemm.split_k" (auto|off|1..8: deterministic K-split of the last partial wave), "gemm.epilogue" (tma|direct), "reduce.row_balance" (off|on: spread rows over more threads when the last wave of a warp-per-row launch would be nearly empty), "reduce.variant"
- * (auto|u2|u4|u8|u16|b4|b8|w2|w4), "reduce.threads", "reduce.blocks_per_sm". */
+ * "gemm.l2_promotion" (256|128|64|0: TMA L2 promotion bytes of the operand tensor maps), "gemm.split_k" (auto|off|1..8: deterministic K-split of the last partial wave), "gemm.epilogue" (tma|direct), "reduce.variant"
+ * (auto|u2|u4|u8|u16|b4|b8|w2|w4: load-unroll / blocked / 256-bit forms of the all-elements kernel; tma: 16 KB bulk copies
+ * into a shared-memory ring), "reduce.threads", "reduce.blocks_per_sm" (all-elements kernel), "reduce.rows_vpt" (128-bit
+ * vectors per thread that size the threads-per-row of the row kernel), "reduce.rows_blocks_per_sm" /
+ * "reduce.cols_blocks_per_sm" (below this many blocks per SM a long reduced axis is cut into segments: two passes),
+ * "reduce.debug" (1: the fused reduce + exchange records its stage timings, see b200_reduce_debug). */
 int b200_set_option(b200_ctx* ctx, const char* key, const char* value);
 /* Number of device kernels this context has launched so far (bench.py reports it as gpu_launches). */
 int b200_launch_count(b200_ctx* ctx, uint64_t* count);
+/* Name of the kernel (cubin entry point) the context launched most recently, NUL-terminated, truncated to `capacity`:
+ * what a measurement harness reports as the kernel it timed (bench.py: roofline.kernel). */
+int b200_last_kernel(b200_ctx* ctx, char* buf, size_t capacity);
 
 /* ---- memory: ComputeClient::{empty,create_from_slice,read_one} (cubecl-runtime/src/client.rs:654,452,256) ----------- */
 /* Pooled device allocation, 512-byte aligned (mem_alignment, cubecl-cuda/src/runtime.rs:81). */
@@ -174,15 +181,24 @@ int b200_matmul_scaled(b200_ctx* ctx, b200_stream stream, b200_dtype lhs_dtype, 
 /* ---- reduce::launch (cubek) -----------------------------------------------------------------------------------------
  * Reduces `axis` (0..rank-1) of a CONTIGUOUS row-major input, or every element when axis == -1.  Output is contiguous
  * with the reduced axis removed (one element for axis == -1): F32 values, or U32 indices along the axis for arg ops.
- * Input dtype F32 / F16 / BF16, f32 accumulation.  Single launch, no host sync; uses a per-stream workspace owned by ctx. */
+ * Input dtype F32 / F16 / BF16, f32 accumulation; `in` needs element alignment only (a sub-slice view is fine: the kernels
+ * peel scalar head / tail elements around the 128-bit body).  One launch, no host sync -- two launches when few outputs
+ * meet a long axis (segments first, then the partials; deterministic); uses a per-stream workspace owned by ctx. */
 int b200_reduce(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype,
                 b200_dptr in, b200_dptr out, int rank, const uint64_t* shape, int axis);
 
-/* Same, for an input described by strides in elements (pitched rows from TensorHandle::empty, permuted views): a
- * non-contiguous input is first gathered into a pooled compact temporary (into_contiguous, crates/cubecl-std/src/tensor/
- * contiguous.rs), then reduced.  strides == NULL means contiguous. */
+/* Same, for an input described by strides in elements.  Pitched rows (TensorHandle::empty -> PitchedMemoryLayoutPolicy,
+ * crates/cubecl-runtime/src/allocator.rs:21-72) and axis permutations that keep the kept axes in order (a transposed view)
+ * are reduced IN PLACE -- the kernels take the outer / axis strides and the row pitch, so the traffic is 1x the logical
+ * bytes and the padding is never read.  Only views no such description fits (broadcast strides, gaps between outer
+ * dimensions, permuted outputs) are first gathered into a pooled compact temporary (into_contiguous,
+ * crates/cubecl-std/src/tensor/contiguous.rs).  strides == NULL means contiguous. */
 int b200_reduce_strided(b200_ctx* ctx, b200_stream s, b200_reduce_op op, b200_dtype in_dtype,
                         b200_dptr in, b200_dptr out, int rank, const uint64_t* shape, const uint64_t* strides, int axis);
+/* Stage timings of the most recent fused reduce + exchange launched on `s` with option "reduce.debug" = 1, in ns:
+ * words4[0] = exchange (publish to the peers' mailboxes -> every peer's value seen), words4[1] = partials + f64 tree of the
+ * last block; words4[2..3] reserved.  Synchronises the stream. */
+int b200_reduce_debug(b200_ctx* ctx, b200_stream s, uint64_t* words4);
 /* out (compact row-major) = gather of the strided rank<=8 tensor `in`. */
 int b200_into_contiguous(b200_ctx* ctx, b200_stream s, b200_dtype dtype, b200_dptr in, b200_dptr out, int rank,
                          const uint64_t* shape, const uint64_t* strides);

@@ -475,7 +475,7 @@ def _host_rows(seed, rows, ncols, dtype):
     return synth.from_device_dtype(synth.to_device_dtype(out, dtype), dtype)
 
 
-@pytest.mark.parametrize("variant", ["auto", "2sm_n128"])
+@pytest.mark.parametrize("variant", ["auto", "2sm_n256", "2sm_n128"])
 def test_bf16_8192_sampled_points_and_linearity(client, variant):
     # BASELINE config 3 at full size: 256 sampled outputs vs f64 dot products of host-regenerated operands
     client.set_option("gemm.variant", variant)
@@ -495,9 +495,74 @@ def test_bf16_8192_sampled_points_and_linearity(client, variant):
     sub = got[np.ix_(ms, ns)].astype(np.float64)
     assert np.max(np.abs(sub - f64) / fabs) <= 1e-2
     assert np.max(np.abs(sub - f64)) <= 0.02 * np.max(np.abs(f64)) + 0.5  # bf16 output rounding only
-    # checksum of checksums: sum over all outputs == (column sums of A) . (row sums of B), in f64 on sampled structure
-    col = got.astype(np.float64).sum()
-    assert np.isfinite(col)
+
+
+def _host_operand(seed, rows, cols, dtype, chunk_rows=1024):
+    """A whole device-filled [rows, cols] operand regenerated on the host (counter hash), as the f32 values the device holds."""
+    out = np.empty((rows, cols), dtype=np.float32)
+    for r0 in range(0, rows, chunk_rows):
+        r1 = min(rows, r0 + chunk_rows)
+        v = synth.uniform_f32(seed, (r1 - r0) * cols, -1.0, 1.0, start=r0 * cols)
+        out[r0:r1] = synth.from_device_dtype(synth.to_device_dtype(v, dtype), dtype).reshape(r1 - r0, cols)
+    return out
+
+
+def _block_checksums_ok(got, a, b, out_dtype, bm=32, bn=64):
+    """Checksum identity over EVERY [bm x bn] block of the product (the epilogue's staging-tile granularity, so every
+    512 x 256 / 256 x 256 tile, every CTA half and every epilogue warp's rows are covered):
+        sum_{m in rows, n in cols} C[m, n] == sum_k (sum_{m in rows} A[m, k]) * (sum_{n in cols} B[k, n])      (f64)
+    The only differences are the output rounding (one ulp of the output type per element, random sign) and the f32
+    accumulation; the bound is 12 standard deviations of that noise, against block sums of magnitude ~1e3-1e4.  Any wrong
+    row segment, swapped tile, missing K-slice or stale accumulator moves a block sum by far more."""
+    M, K = a.shape
+    N = b.shape[1]
+    asum = a.astype(np.float64).reshape(M // bm, bm, K).sum(axis=1)             # [M/bm, K]
+    bsum = b.astype(np.float64).reshape(K, N // bn, bn).sum(axis=2)             # [K, N/bn]
+    expect = asum @ bsum                                                        # [M/bm, N/bn]
+    have = got.astype(np.float64).reshape(M // bm, bm, N // bn, bn).sum(axis=(1, 3))
+    # per-element rounding noise: |c| * 2^-9 (bf16) / 2^-12 (f16) / 2^-25 (f32, plus accumulation ~1e-6 |a||b| K)
+    rel = {"bf16": 2.0 ** -9, "f16": 2.0 ** -12, "f32": 2.0 ** -20}[out_dtype]
+    rms_c = np.sqrt(np.mean(got.astype(np.float64) ** 2))
+    sigma = rel * rms_c * np.sqrt(bm * bn) / np.sqrt(3.0)
+    worst = float(np.max(np.abs(have - expect)))
+    return worst <= 12.0 * sigma + 1e-6 * np.max(np.abs(expect)), worst, 12.0 * sigma
+
+
+def test_bf16_8192_every_block_checksum(client):
+    # BASELINE config 3 at full size on the DEFAULT path (auto -> the 512 x 256 pair tile): all 67 M outputs take part,
+    # through 32,768 block checksums against f64 sums of the host-regenerated operands
+    n = 8192
+    a = _device_operand(client, [n, n], "bf16", 3)
+    b = _device_operand(client, [n, n], "bf16", 4)
+    out = TensorHandle.empty_contiguous(client, [n, n], "bf16")
+    matmul.launch(client, a, b, out)
+    got = synth.bf16_bits_to_f32(out.to_numpy(client))
+    assert "m512" in client.last_kernel()
+    ah, bh = _host_operand(3, n, n, "bf16"), _host_operand(4, n, n, "bf16")
+    ok, worst, bound = _block_checksums_ok(got, ah, bh, "bf16")
+    assert ok, f"block checksum off by {worst:.3f} (bound {bound:.3f})"
+    # the check has teeth: one corrupted 32-element row segment is caught
+    bad = got.copy()
+    bad[4100, 4096:4128] += 4.0
+    assert not _block_checksums_ok(bad, ah, bh, "bf16")[0]
+    # checksum of checksums: the grand total equals colsum(A) . rowsum(B)
+    total = float(ah.astype(np.float64).sum(axis=0) @ bh.astype(np.float64).sum(axis=1))
+    assert abs(float(got.astype(np.float64).sum()) - total) <= 12.0 * (2.0 ** -9) * np.sqrt(np.mean(got.astype(np.float64) ** 2)) * n / np.sqrt(3.0)
+
+
+def test_batched_8x4096_every_block_checksum(client):
+    # BASELINE config 5, the per-GPU slice (8 x 4096^3 bf16): every output of every batch through block checksums
+    n, B = 4096, 8
+    a = _device_operand(client, [B, n, n], "bf16", 6)
+    b = _device_operand(client, [B, n, n], "bf16", 7)
+    out = TensorHandle.empty_contiguous(client, [B, n, n], "bf16")
+    matmul.launch(client, a, b, out)
+    got = synth.bf16_bits_to_f32(out.to_numpy(client)).reshape(B, n, n)
+    for bi in range(B):
+        ah = synth.from_device_dtype(synth.to_device_dtype(synth.uniform_f32(6, n * n, -1.0, 1.0, start=bi * n * n), "bf16"), "bf16").reshape(n, n)
+        bh = synth.from_device_dtype(synth.to_device_dtype(synth.uniform_f32(7, n * n, -1.0, 1.0, start=bi * n * n), "bf16"), "bf16").reshape(n, n)
+        ok, worst, bound = _block_checksums_ok(got[bi], ah, bh, "bf16")
+        assert ok, f"batch {bi}: block checksum off by {worst:.3f} (bound {bound:.3f})"
 
 
 def test_f32_4096_sampled_points(client):

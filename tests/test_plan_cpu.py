@@ -235,28 +235,56 @@ def test_reduce_plans(plan):
     assert rc == 0 and t.strip() == "launch reduce_all_sum_f32 grid=(592,1,1) block=512 smem=0 cluster=1"
     rc, t = plan.reduce(SUM, F32, [4], -1)
     assert "grid=(1,1,1)" in t
-    rc, t = plan.reduce(SUM, F32, [512, 8192], 1)                          # the book's shape: a block per row
-    assert t.strip() == "launch reduce_rows_sum_f32 grid=(512,1,1) block=512 smem=0 cluster=1"
-    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)                         # many rows: a warp per row, 8 rows per block
-    assert t.strip() == "launch reduce_rows_sum_f32 grid=(1024,1,1) block=256 smem=0 cluster=1"
-    plan.option("reduce.row_balance", "on")                                # 1.15 waves of warps -> 4.6 waves of 128-thread rows
-    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)
-    assert t.strip() == "launch reduce_rows_sum_f32 grid=(2368,1,1) block=128 smem=0 cluster=1"
-    rc, t = plan.reduce(SUM, F32, [4096, 4096], 1)                         # everything resident at once: nothing to balance
+    rc, t = plan.reduce(SUM, F32, [512, 8192], 1)                          # the book's shape: a 256-thread block per 32 KB row
     assert t.strip() == "launch reduce_rows_sum_f32 grid=(512,1,1) block=256 smem=0 cluster=1"
-    plan.option("reduce.row_balance", "off")
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)                         # many rows: still a block per row -> 9 waves of small blocks
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(8192,1,1) block=256 smem=0 cluster=1"
+    rc, t = plan.reduce(SUM, F32, [20000, 2048], 1)                        # 8 KB rows: two warps per row, four rows per block
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(5000,1,1) block=256 smem=0 cluster=1"
+    plan.option("reduce.rows_vpt", 16)                                     # tuning knob: vectors per thread
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(4096,1,1) block=256 smem=0 cluster=1"
+    plan.option("reduce.rows_vpt", 8)
     rc, t = plan.reduce(SUM, F32, [1000, 3], 1)                            # short rows: one thread per row
     assert "reduce_rows_sum_f32 grid=(4,1,1) block=256" in t
+    rc, t = plan.reduce(SUM, F32, [1 << 26, 4], 1)                         # one vector per row: four rows in flight per thread
+    assert "reduce_rows_sum_f32 grid=(65536,1,1) block=256" in t
     rc, t = plan.reduce(SUM, F32, [4, 1 << 24], 1)                         # few long rows: two passes over pooled partials
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["reduce_rows_sum_f32", "reduce_rows_sum_f32"] and "alloc" in t
-    rc, t = plan.reduce(ARGMAX, BF16, [4, 1 << 24], 1)                     # arg ops never split
-    assert t.count("launch") == 1 and "reduce_rows_argmax_bf16" in t
+    assert "grid=(2344,1,1) block=512" in t                                # 586 segments of 28672 elements per row
+    rc, t = plan.reduce(ARGMAX, BF16, [4, 1 << 24], 1)                     # arg ops split too: (key, index) partials + combine
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["reduce_rows_argmax_bf16", "reduce_argcombine"]
+    assert t.count("alloc") == 2
     rc, t = plan.reduce(MEAN, F16, [64, 256, 1024], 1)                     # middle axis -> columns kernel
     assert "reduce_cols_sum_f16" in t
     rc, t = plan.reduce(SUM, F32, [8192, 8192], 0)                         # outer axis, few outputs: split along the axis
-    assert t.count("launch reduce_cols_sum_f32") == 2
-    rc, t = plan.reduce(SUM, F32, [100, 72], 1, strides=[128, 1])          # pitched rows: gather first
-    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_rows_sum_f32"]
+    assert t.count("launch reduce_cols_sum_f32") == 2 and "grid=(2368,1,1)" in t
+    rc, t = plan.reduce(SUM, F32, [4, 1 << 26], 0)                         # short axis, many columns: persistent grid, one launch
+    assert t.strip() == "launch reduce_cols_sum_f32 grid=(1184,1,1) block=256 smem=0 cluster=1"
+    # views reduced in place (1x the logical bytes): pitched rows on every axis, transposed views, a permuted rank-3 view
+    for axis, kernel in ((1, "reduce_rows_sum_f32"), (0, "reduce_cols_sum_f32"), (-1, "reduce_allp_sum_f32")):
+        rc, t = plan.reduce(SUM, F32, [100, 72], axis, strides=[128, 1])
+        assert rc == 0 and [ln.split()[1] for ln in t.splitlines()] == [kernel], (axis, t)
+    rc, t = plan.reduce(ARGMAX, F32, [100, 72], -1, strides=[128, 1])
+    assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_allp_argmax_f32"]
+    rc, t = plan.reduce(SUM, F32, [72, 100], 1, strides=[1, 72])           # x.T over its last axis = x over axis 0
+    assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_cols_sum_f32"]
+    rc, t = plan.reduce(SUM, F32, [72, 100], 0, strides=[1, 72])
+    assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_rows_sum_f32"]
+    rc, t = plan.reduce(SUM, F32, [3, 5, 7], 1, strides=[35, 1, 5])        # reduced axis innermost in memory, kept axes in order
+    assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_rows_sum_f32"]
+    # what no (outer stride, axis stride, row pitch) description fits is gathered first: a flat argmax of a transposed view
+    # (the index is logical), gaps between outer dimensions
+    rc, t = plan.reduce(ARGMAX, F32, [72, 100], -1, strides=[1, 72])
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_all_argmax_f32"]
+    rc, t = plan.reduce(SUM, F32, [3, 5, 7], 0, strides=[70, 14, 2])
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_cols_sum_f32"]
+    plan.option("reduce.variant", "tma")                                   # bulk-copy staged form: one CTA per SM, 8 x 16 KB ring
+    rc, t = plan.reduce(SUM, F32, [1 << 28], -1)
+    assert t.strip() == "launch reduce_all_sum_f32_tma grid=(148,1,1) block=288 smem=131200 cluster=1"
+    rc, t = plan.reduce(SUM, F32, [1000], -1)                              # too small for a ring: plain loads
+    assert "reduce_all_sum_f32 " in t
+    plan.option("reduce.variant", "auto")
     rc, _ = plan.reduce(SUM, F32, [4, 0], 1)
     assert rc == 6                                                         # empty reduced extent
     rc, t = plan.reduce(SUM, F32, [0, 4], 1)
