@@ -230,7 +230,7 @@ struct ScaledSimtParams {
   uint32_t a_bmul, b_bmul, scale_ue4m3, pad1;
 };
 struct ReduceParams {
-  uint64_t in, out, out2, ws;
+  uint64_t in, out, out2, final_out, ws;
   uint64_t outer, len, inner;
   uint64_t s_outer, s_len;       // element strides of the outer and the reduced axis
   uint64_t row_len, row_pitch;   // inner offset i -> (i / row_len) * row_pitch + i % row_len (row_len == inner: no pitch)
@@ -272,7 +272,9 @@ static constexpr uint32_t kWsMaxBlocks = 4096;
 static constexpr uint32_t kWsTicketOffset = kWsMaxBlocks * 4 + kWsMaxBlocks * 8;
 static constexpr uint32_t kWsDebugOffset = kWsTicketOffset + 64;         // four u64 words written by the reduce grid stage on request
 static constexpr uint32_t kWsGemmTicketOffset = kWsTicketOffset + 256;  // u32 per (tail tile, CTA rank) of a split GEMM
-static constexpr size_t kWsBytes = kWsGemmTicketOffset + 1024;
+static constexpr uint32_t kWsColTicketOffset = kWsGemmTicketOffset + 1024;  // u32[1024]: one per (outer, column tile) of a fused split column reduction
+static constexpr uint32_t kWsColTickets = 1024;
+static constexpr size_t kWsBytes = kWsColTicketOffset + kWsColTickets * 4;
 
 // ================================================================================================ context
 struct PoolBlock {
@@ -328,6 +330,10 @@ struct b200_ctx {
   std::string plan;
   std::string pending_kernel;
   std::string last_kernel;         // name of the most recently launched kernel (b200_last_kernel)
+  // Programmatic dependent launch of back-to-back all-element reductions on the context's own stream (every kernel there
+  // is launched by this library, so the predecessor is known): output pointer of the reduce_all launch that is the LAST
+  // kernel queued on c->stream, 0 if the last kernel was anything else.
+  uint64_t pdl_prev_out = 0;
   uint64_t fake_next = 0x7000000000ull;
 };
 
@@ -518,7 +524,7 @@ extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) 
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
   static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm", "reduce.rows_vpt", "reduce.rows_blocks_per_sm", "reduce.cols_blocks_per_sm",
-                                "reduce.debug"};
+                                "reduce.debug", "reduce.pdl"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
   return fail(B200_ERR_INVALID_ARG, "unknown option '%s'", key);
@@ -759,23 +765,31 @@ extern "C" int b200_event_destroy(b200_ctx* c, b200_event e) {
 
 // ================================================================================================ launch helper
 static int launch(b200_ctx* c, CUfunction f, unsigned grid_x, unsigned grid_y, unsigned grid_z, unsigned block,
-                  unsigned smem, unsigned cluster_x, CUstream st, void** args) {
+                  unsigned smem, unsigned cluster_x, CUstream st, void** args, bool pdl = false) {
   CUlaunchConfig cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDimX = grid_x; cfg.gridDimY = grid_y; cfg.gridDimZ = grid_z;
   cfg.blockDimX = block; cfg.blockDimY = 1; cfg.blockDimZ = 1;
   cfg.sharedMemBytes = smem;
   cfg.hStream = st;
-  CUlaunchAttribute at[1];
+  CUlaunchAttribute at[2];
+  unsigned nat = 0;
   if (cluster_x > 1) {
-    at[0].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
-    at[0].value.clusterDim.x = cluster_x; at[0].value.clusterDim.y = 1; at[0].value.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[nat].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+    at[nat].value.clusterDim.x = cluster_x; at[nat].value.clusterDim.y = 1; at[nat].value.clusterDim.z = 1;
+    ++nat;
   }
+  if (pdl) {  // this kernel may begin once every block of the preceding kernel has triggered (griddepcontrol) or exited
+    at[nat].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    at[nat].value.programmaticStreamSerializationAllowed = 1;
+    ++nat;
+  }
+  if (nat) { cfg.attrs = at; cfg.numAttrs = nat; }
+  if (st == c->stream) c->pdl_prev_out = 0;   // whoever launches a reduce_all sets it again after this call
   if (c->dry) {
     char line[256];
-    snprintf(line, sizeof(line), "launch %s grid=(%u,%u,%u) block=%u smem=%u cluster=%u\n", c->pending_kernel.c_str(), grid_x,
-             grid_y, grid_z, block, smem, cluster_x);
+    snprintf(line, sizeof(line), "launch %s grid=(%u,%u,%u) block=%u smem=%u cluster=%u%s\n", c->pending_kernel.c_str(), grid_x,
+             grid_y, grid_z, block, smem, cluster_x, pdl ? " pdl" : "");
     c->plan += line;
     c->launches++;
     return B200_OK;
@@ -1430,10 +1444,12 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RVi
   bool bulk = false;
   if (!pitched && !arg) {
     // variants: the plain 128-bit streaming kernel, its tuning forms (f32 sum only) and the bulk-copy staged kernel
+    // auto = the bulk-copy staged kernel once the input is big enough to fill a ring on every SM (measured, 1 GiB f32 sum:
+    // 7.08 TB/s against 6.92 for the best plain-load form, profiles/r02_reduce_sweep.log); plain loads below that
     const std::string var = opt(c, "reduce.variant", "auto");
-    if (var == "tma") {
-      bulk = n * esz >= 64 * 16384;           // needs whole 16 KB tiles to be worth a ring; small inputs use plain loads
-    } else if (var != "auto" && var != "u8") {
+    if (var == "tma" || var == "auto") {
+      bulk = n * esz >= (var == "tma" ? 64ull * 16384 : (uint64_t)c->props.num_sms * 8 * 16384);
+    } else if (var != "u8") {
       if (std::string(op_tag(op)) == "sum" && dt == B200_F32) name += "_" + var;
     }
   }
@@ -1462,7 +1478,15 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RVi
   p.row_len = v.row_len; p.row_pitch = v.row_pitch;
   p.seg_len = n; p.nseg = 1; p.scale = scale;
   void* args[] = {&p};
-  return launch(c, f, grid, 1, 1, threads, smem, 1, st, args);
+  // Overlap with the preceding all-element reduction on the context's stream: safe because that kernel writes only its
+  // 4-byte result and the workspace, this one reads neither before its own griddepcontrol.wait -- unless its input is the
+  // predecessor's output.
+  const uint64_t in_end = v.in + (pitched ? (n / v.row_len) * v.row_pitch : n) * esz;
+  const bool pdl = st == c->stream && c->pdl_prev_out != 0 && opt(c, "reduce.pdl", "on") == "on" &&
+                   !(c->pdl_prev_out + 4 > v.in && c->pdl_prev_out < in_end);
+  rc = launch(c, f, grid, 1, 1, threads, smem, 1, st, args, pdl);
+  if (!rc && st == c->stream) c->pdl_prev_out = out;
+  return rc;
 }
 
 // One launch of the rows kernel: items = outer x nseg, item (o, s) covers elements [s * seg_len, ..) of row o.
@@ -1477,7 +1501,10 @@ static int launch_rows_kernel(b200_ctx* c, CUstream st, int op, int dt, const RV
   // Threads per item (power of two): about `vpt` 128-bit vectors per thread, so a 32 KB row is one 256-thread block and the
   // grid has many more blocks than resident slots (the hardware scheduler balances the tail block by block -- a warp per
   // 32 KB row left the last, nearly empty wave running at a third of the bandwidth: ncu, round 1).
-  const unsigned vpt = opt_uint(c, "reduce.rows_vpt", 8, 1, 64);
+  // measured (profiles/r02_reduce_sweep.log): 16 vectors per thread for inputs that stream from HBM for a while ([9000,16384]
+  // 6.38 vs 6.09 TB/s, argmax [8192,8192] 5.65 vs 4.90), 8 for small launch-bound inputs ([512,8192] 7.1 vs 8.6 us)
+  const bool big = v.outer * v.len * esz >= (128ull << 20);
+  const unsigned vpt = opt_uint(c, "reduce.rows_vpt", big ? 16 : 8, 1, 64);
   const uint64_t nv = ceil_div(std::min(seg_len, v.len), vec);
   uint64_t tpr = std::min<uint64_t>(512, pow2_ceil(ceil_div(nv, vpt)));
   int tpr_log2 = 0;
@@ -1499,7 +1526,10 @@ static int launch_rows_kernel(b200_ctx* c, CUstream st, int op, int dt, const RV
 }
 
 // One launch of the column kernel over the view (items = outer x nseg x column tiles).
-static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t seg_len, uint64_t out, uint64_t out2, float scale) {
+// `final_out` != 0 with a segmented axis: finish in the same launch when the (outer, column tile) tickets fit the workspace
+// (*fused = true), else the caller runs the second pass.
+static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t seg_len, uint64_t out, uint64_t out2, float scale,
+                              uint64_t final_out = 0, bool* fused = nullptr) {
   const std::string name = std::string("reduce_cols_") + op_tag(op) + "_" + dt_tag(dt);
   CUfunction f;
   int rc = get_func(c, name, &f);
@@ -1530,6 +1560,14 @@ static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RV
   p.row_len = v.row_len; p.row_pitch = v.row_pitch;
   p.seg_len = seg_len; p.nseg = (uint32_t)nseg; p.ctu = (uint32_t)ctu; p.scale = scale;
   p.flags = vector ? 2u : 0u;
+  if (fused) *fused = false;
+  if (final_out && nseg > 1 && v.outer * tiles <= kWsColTickets) {
+    CUdeviceptr ws;
+    rc = reduce_workspace(c, st, &ws);
+    if (rc) return rc;
+    p.ws = ws; p.final_out = final_out; p.flags |= 4u;
+    if (fused) *fused = true;
+  }
   void* args[] = {&p};
   return launch(c, f, grid, 1, 1, 256, 0, 1, st, args);
 }
@@ -1539,7 +1577,8 @@ static int launch_argcombine(b200_ctx* c, CUstream st, uint64_t keys, uint64_t i
   int rc = get_func(c, "reduce_argcombine", &f);
   if (rc) return rc;
   ArgCombineParams p{keys, idx, out, outer, nseg, inner};
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ceil_div(outer * inner, 256), (uint64_t)c->props.num_sms * 8));
+  const uint64_t threads = nseg >= 8 ? outer * inner * 32 : outer * inner;   // a warp per output when there are many segments
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(ceil_div(threads, 256), (uint64_t)c->props.num_sms * 8));
   void* args[] = {&p};
   return launch(c, f, grid, 1, 1, 256, 0, 1, st, args);
 }
@@ -1556,7 +1595,7 @@ static int reduce_axis_view(b200_ctx* c, CUstream st, int op, int dt, const RVie
   uint64_t seg_len = v.len;
   if (v.inner == 1) {
     const unsigned bps = opt_uint(c, "reduce.rows_blocks_per_sm", 4, 1, 64);
-    if (v.outer < sms * bps && v.len >= 16384) {
+    if (v.outer < sms * bps && v.len >= 16384 && v.outer * v.len * esz >= (32ull << 20)) {   // below ~32 MB one launch wins (launch-bound)
       const uint64_t nseg = std::min<uint64_t>(ceil_div(sms * 16, v.outer), v.len / 4096);
       if (nseg > 1) seg_len = ceil_div(ceil_div(v.len, nseg), 512) * 512;   // 512 elements: segments stay vector-aligned
     }
@@ -1583,8 +1622,10 @@ static int reduce_axis_view(b200_ctx* c, CUstream st, int op, int dt, const RVie
     rc = pool_alloc(c, count * 4, &tmp2, st);
     if (rc) { pool_free(c, tmp, st); return rc; }
   }
-  rc = v.inner == 1 ? launch_rows_kernel(c, st, op, dt, v, seg_len, tmp, tmp2, 1.0f) : launch_cols_kernel(c, st, op, dt, v, seg_len, tmp, tmp2, 1.0f);
-  if (!rc) {
+  bool fused = false;
+  rc = v.inner == 1 ? launch_rows_kernel(c, st, op, dt, v, seg_len, tmp, tmp2, 1.0f)
+                    : launch_cols_kernel(c, st, op, dt, v, seg_len, tmp, tmp2, scale, out, &fused);
+  if (!rc && !fused) {
     if (arg) {
       rc = launch_argcombine(c, st, tmp, tmp2, out, v.outer, nseg, v.inner);
     } else {
@@ -1942,7 +1983,10 @@ static int reduce_all_reduce_impl(b200_ctx* c, b200_stream s, b200_reduce_op op,
   xg.index_offset = index_offset;
   xg.epoch = st.epoch + 1;  // every rank calls in the same order (collective semantics), so epochs agree
   void* args[] = {&p, &xg};
-  rc = launch(c, f, grid, 1, 1, threads, 0, 1, cs, args);
+  const bool pdl = cs == c->stream && c->pdl_prev_out != 0 && opt(c, "reduce.pdl", "on") == "on" &&
+                   !(c->pdl_prev_out + 4 > in && c->pdl_prev_out < in + n * 4);
+  rc = launch(c, f, grid, 1, 1, threads, 0, 1, cs, args, pdl);
+  if (!rc && cs == c->stream) c->pdl_prev_out = out;
   if (!rc) st.epoch += 1;   // only a launch that really went out consumes the epoch (a failed call must not desynchronise the ranks)
   return rc;
 }

@@ -29,6 +29,8 @@ struct ReduceParams {
   uint64_t in;        // input view, element (o, l, i) at in + (o * s_outer + l * s_len + inner_off(i)) elements
   uint64_t out;       // output [outer (* segments), inner]: f32 values, u32 indices (arg ops), or u32 keys (arg ops, split pass)
   uint64_t out2;      // arg ops, split pass: u32 indices along the reduced axis; 0 otherwise
+  uint64_t final_out; // column kernels, split pass with a fused finish (flags bit 2): the real output [outer, inner]; the block
+                      // that completes a column tile's last segment (ticket) combines the partials in `out` / `out2` itself
   uint64_t ws;        // workspace: partial values f32[grid] | partial packed pairs u64[grid] | u32 ticket | debug words
   uint64_t outer, len, inner;
   uint64_t s_outer, s_len;
@@ -38,7 +40,8 @@ struct ReduceParams {
   uint32_t nseg;      // a two-pass reduction); nseg == 1: whole axis
   uint32_t ctu;       // column kernels: column units (one 128-bit vector, or one element) per block tile
   float scale;        // applied to the final value (mean = 1/len, sum = 1)
-  uint32_t flags;     // bit 0: record stage timings in the workspace debug words
+  uint32_t flags;     // bit 0: record stage timings in the workspace debug words; bit 1: column kernels use vector units;
+                      // bit 2: fused finish of a split column reduction (see final_out)
 };
 
 // Cross-GPU exchange fused into the grid stage (one kernel = local reduce + all-reduce of the scalar over NVLink peer
@@ -62,6 +65,8 @@ constexpr uint32_t kWsMaxBlocks = 4096;
 constexpr uint32_t kWsIdxOffset = kWsMaxBlocks * 4;
 constexpr uint32_t kWsTicketOffset = kWsIdxOffset + kWsMaxBlocks * 8;
 constexpr uint32_t kWsDebugOffset = kWsTicketOffset + 64;
+constexpr uint32_t kWsColTicketOffset = kWsTicketOffset + 256 + 1024;   // after the GEMM's tickets: u32[1024], one per (outer, column tile)
+constexpr uint32_t kWsColTickets = 1024;
 
 // ------------------------------------------------------------------------------------------------ value ops
 template <int OP>
@@ -242,6 +247,13 @@ __device__ __forceinline__ uint64_t ld_sys_u64(uint64_t addr) {
   return v;
 }
 
+// Programmatic dependent launch (PDL): a reduction over all elements touches only its input until its grid stage, so the
+// NEXT such launch on the stream may start streaming while this one's last block is still finishing.  `pdl_trigger` (after
+// the streaming loop) lets a dependent launch begin; `pdl_wait` (before the first access to the shared workspace) holds this
+// launch until its predecessor has completed and flushed.  Both are no-ops unless the host asked for the overlap.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ================================================================================================ grid stage
 // Per-block partial -> workspace; the last block to finish (ticket) reduces the partials in block order (deterministic for a
 // fixed grid) and writes out[0] * scale -- or, in the XGPU form, exchanges the rank's scalar with its peers first.
@@ -250,6 +262,7 @@ __device__ __forceinline__ void grid_stage_value(const ReduceParams& p, float bl
   __shared__ bool s_last;
   float* partials = reinterpret_cast<float*>(p.ws);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(p.ws + kWsTicketOffset);
+  pdl_wait();
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = block_val;
     __threadfence();
@@ -330,6 +343,7 @@ __device__ __forceinline__ void grid_stage_arg(const ReduceParams& p, uint64_t b
   __shared__ bool s_last;
   uint64_t* partials = reinterpret_cast<uint64_t*>(p.ws + kWsIdxOffset);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(p.ws + kWsTicketOffset);
+  pdl_wait();
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = block_pair;
     __threadfence();
@@ -510,6 +524,7 @@ __device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const Xgp
     else local = ValOp<OP>::apply(local, f);
   }
 
+  pdl_trigger();
   if constexpr (ARG) {
     const uint64_t block_pair = block_max64(cand.packed(), s_red64);
     grid_stage_arg<XGPU>(p, block_pair, s_red64, xg);
@@ -615,6 +630,7 @@ __device__ __forceinline__ void reduce_all_bulk_body(const ReduceParams& p) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) local = ValOp<OP>::apply(local, acc[u][j]);
   }
+  pdl_trigger();
   const float block_val = block_reduce<OP>(local, s_red);
   grid_stage_value<OP, false>(p, block_val, s_red, nullptr);
 }
@@ -946,8 +962,10 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
       res[j] = ValOp<OP>::apply(ValOp<OP>::apply(a[0][j], a[1][j]), ValOp<OP>::apply(a[2][j], a[3][j]));
       resp[j] = cand[j].packed();
     }
-    if (RL > 1) {
-      // combine the row lanes of each unit: slot (rl, cu) at [threadIdx.x * UV + j]; lanes that found nothing hold the identity
+    // combine the row lanes of each unit through shared memory: slot (rl, cu) at [threadIdx.x * UV + j]; lanes that found
+    // nothing hold the identity.  The result is valid in the lanes with rl == 0.  (block-uniform control flow)
+    auto combine_lanes = [&]() {
+      if (RL <= 1) return;
 #pragma unroll
       for (int j = 0; j < UV; ++j) {
         if constexpr (ARG) s_raw[threadIdx.x * UV + j] = resp[j];
@@ -971,19 +989,60 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
           else res[j] = s_val[threadIdx.x * UV + j];
         }
       }
-      __syncthreads();  // the slots are reused by the next item
-    }
+      __syncthreads();  // the slots are reused (next combine / next item)
+    };
+    combine_lanes();
+    const bool fused = (p.flags & 4u) != 0;
     if (valid && rl == 0) {
       const uint64_t ob = q * p.inner + i0;
 #pragma unroll
       for (int j = 0; j < UV; ++j) {
         if constexpr (!ARG) {
-          reinterpret_cast<float*>(p.out)[ob + j] = res[j] * p.scale;
+          reinterpret_cast<float*>(p.out)[ob + j] = fused ? res[j] : res[j] * p.scale;
         } else if (p.out2 == 0) {
           reinterpret_cast<uint32_t*>(p.out)[ob + j] = arg_index(resp[j]);
         } else {
           reinterpret_cast<uint32_t*>(p.out)[ob + j] = static_cast<uint32_t>(resp[j] >> 32);
           reinterpret_cast<uint32_t*>(p.out2)[ob + j] = arg_index(resp[j]);  // already global along the axis (l0 + l was fed)
+        }
+      }
+    }
+    if (fused) {
+      // Fused finish of a split reduction: every block publishes its segment's partials, takes a ticket for its (outer,
+      // column tile); whoever completes the set re-reads all nseg partial rows of the tile -- each row lane a fixed subset of
+      // the segments, then the same lane tree -- so the result does not depend on which block came last.  No second launch.
+      __shared__ uint32_t s_last;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(p.ws + kWsColTicketOffset) + (o * tiles + tile);
+        const unsigned int old = atomicAdd(ticket, 1u);
+        s_last = (old == p.nseg - 1) ? 1u : 0u;
+        if (s_last) *ticket = 0;  // left ready for the next launch on this stream
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+#pragma unroll
+        for (int j = 0; j < UV; ++j) { res[j] = ValOp<OP>::identity(); resp[j] = 0; }
+        if (valid) {
+          for (uint64_t sg = rl; sg < p.nseg; sg += RL) {
+            const uint64_t at = (o * p.nseg + sg) * p.inner + i0;
+#pragma unroll
+            for (int j = 0; j < UV; ++j) {
+              if constexpr (ARG) resp[j] = umax64(resp[j], arg_pack(__ldcg(reinterpret_cast<const uint32_t*>(p.out) + at + j),
+                                                                    __ldcg(reinterpret_cast<const uint32_t*>(p.out2) + at + j)));
+              else res[j] = ValOp<OP>::apply(res[j], __ldcg(reinterpret_cast<const float*>(p.out) + at + j));
+            }
+          }
+        }
+        combine_lanes();
+        if (valid && rl == 0) {
+#pragma unroll
+          for (int j = 0; j < UV; ++j) {
+            if constexpr (ARG) reinterpret_cast<uint32_t*>(p.final_out)[o * p.inner + i0 + j] = arg_index(resp[j]);
+            else reinterpret_cast<float*>(p.final_out)[o * p.inner + i0 + j] = res[j] * p.scale;
+          }
         }
       }
     }
@@ -1011,13 +1070,33 @@ struct ArgCombineParams {
 };
 extern "C" __global__ void __launch_bounds__(256) reduce_argcombine(const __grid_constant__ ArgCombineParams p) {
   const uint64_t total = p.outer * p.inner;
+  const uint32_t* keys = reinterpret_cast<const uint32_t*>(p.keys);
+  const uint32_t* idx = reinterpret_cast<const uint32_t*>(p.idx);
+  if (p.nseg >= 8) {
+    // many segments, (usually) few outputs: a warp per output, lanes over the segments (a serial walk of thousands of
+    // dependent-latency loads by one thread took longer than the first pass)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t e = warp; e < total; e += nwarps) {
+      const uint64_t o = e / p.inner, i = e - o * p.inner;
+      uint64_t best = 0;
+      for (uint64_t s = lane; s < p.nseg; s += 32) {
+        const uint64_t at = (o * p.nseg + s) * p.inner + i;
+        best = umax64(best, arg_pack(keys[at], idx[at]));
+      }
+      best = warp_max64(best);
+      if (lane == 0) reinterpret_cast<uint32_t*>(p.out)[e] = arg_index(best);
+    }
+    return;
+  }
   for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
        e += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t o = e / p.inner, i = e - o * p.inner;
     uint64_t best = 0;
     for (uint64_t s = 0; s < p.nseg; ++s) {
       const uint64_t at = (o * p.nseg + s) * p.inner + i;
-      best = umax64(best, arg_pack(reinterpret_cast<const uint32_t*>(p.keys)[at], reinterpret_cast<const uint32_t*>(p.idx)[at]));
+      best = umax64(best, arg_pack(keys[at], idx[at]));
     }
     reinterpret_cast<uint32_t*>(p.out)[e] = arg_index(best);
   }

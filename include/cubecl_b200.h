@@ -101,7 +101,9 @@ int b200_plan_text(b200_ctx* ctx, char* buf, size_t capacity, size_t* needed);
  * into a shared-memory ring), "reduce.threads", "reduce.blocks_per_sm" (all-elements kernel), "reduce.rows_vpt" (128-bit
  * vectors per thread that size the threads-per-row of the row kernel), "reduce.rows_blocks_per_sm" /
  * "reduce.cols_blocks_per_sm" (below this many blocks per SM a long reduced axis is cut into segments: two passes),
- * "reduce.debug" (1: the fused reduce + exchange records its stage timings, see b200_reduce_debug). */
+ * "reduce.debug" (1: the fused reduce + exchange records its stage timings, see b200_reduce_debug), "reduce.pdl" (on|off:
+ * back-to-back all-element reductions on the context's own stream overlap through programmatic dependent launch -- the next
+ * launch streams its input while the previous one's last block finishes; results are unchanged). */
 int b200_set_option(b200_ctx* ctx, const char* key, const char* value);
 /* Number of device kernels this context has launched so far (bench.py reports it as gpu_launches). */
 int b200_launch_count(b200_ctx* ctx, uint64_t* count);

@@ -231,20 +231,30 @@ def test_wave_model_prefers_big_tiles(plan):
 
 def test_reduce_plans(plan):
     SUM, ARGMAX, MEAN = _ffi.REDUCE_SUM, _ffi.REDUCE_ARGMAX, _ffi.REDUCE_MEAN
+    rc, t = plan.reduce(SUM, F32, [1 << 28], -1)                          # big value reductions: bulk-copy staged, one CTA per SM
+    assert rc == 0 and t.strip() == "launch reduce_all_sum_f32_tma grid=(148,1,1) block=288 smem=131200 cluster=1"
+    plan.option("reduce.variant", "u8")                                    # the plain 128-bit streaming form
     rc, t = plan.reduce(SUM, F32, [1 << 28], -1)
     assert rc == 0 and t.strip() == "launch reduce_all_sum_f32 grid=(592,1,1) block=512 smem=0 cluster=1"
+    plan.option("reduce.variant", "auto")
+    rc, t = plan.reduce(ARGMAX, F32, [1 << 28], -1)
+    assert t.strip() == "launch reduce_all_argmax_f32 grid=(592,1,1) block=512 smem=0 cluster=1"
+    rc, t = plan.reduce(SUM, F32, [1 << 20], -1)                          # 4 MB: plain loads
+    assert "launch reduce_all_sum_f32 grid=(512,1,1) block=512" in t
     rc, t = plan.reduce(SUM, F32, [4], -1)
     assert "grid=(1,1,1)" in t
     rc, t = plan.reduce(SUM, F32, [512, 8192], 1)                          # the book's shape: a 256-thread block per 32 KB row
     assert t.strip() == "launch reduce_rows_sum_f32 grid=(512,1,1) block=256 smem=0 cluster=1"
-    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)                         # many rows: still a block per row -> 9 waves of small blocks
-    assert t.strip() == "launch reduce_rows_sum_f32 grid=(8192,1,1) block=256 smem=0 cluster=1"
-    rc, t = plan.reduce(SUM, F32, [20000, 2048], 1)                        # 8 KB rows: two warps per row, four rows per block
-    assert t.strip() == "launch reduce_rows_sum_f32 grid=(5000,1,1) block=256 smem=0 cluster=1"
-    plan.option("reduce.rows_vpt", 16)                                     # tuning knob: vectors per thread
-    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)                         # 256 MB: 16 vectors per thread, two rows per block
     assert t.strip() == "launch reduce_rows_sum_f32 grid=(4096,1,1) block=256 smem=0 cluster=1"
-    plan.option("reduce.rows_vpt", 8)
+    rc, t = plan.reduce(SUM, F32, [2048, 8192], 1)                         # 64 MB: 8 vectors per thread, a block per row
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(2048,1,1) block=256 smem=0 cluster=1"
+    rc, t = plan.reduce(SUM, F32, [20000, 2048], 1)                        # 8 KB rows: a warp per row, eight rows per block
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(2500,1,1) block=256 smem=0 cluster=1"
+    plan.option("reduce.rows_vpt", 8)                                      # tuning knob: vectors per thread
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 1)
+    assert t.strip() == "launch reduce_rows_sum_f32 grid=(8192,1,1) block=256 smem=0 cluster=1"
+    plan.option("reduce.rows_vpt", "")
     rc, t = plan.reduce(SUM, F32, [1000, 3], 1)                            # short rows: one thread per row
     assert "reduce_rows_sum_f32 grid=(4,1,1) block=256" in t
     rc, t = plan.reduce(SUM, F32, [1 << 26, 4], 1)                         # one vector per row: four rows in flight per thread
@@ -257,8 +267,10 @@ def test_reduce_plans(plan):
     assert t.count("alloc") == 2
     rc, t = plan.reduce(MEAN, F16, [64, 256, 1024], 1)                     # middle axis -> columns kernel
     assert "reduce_cols_sum_f16" in t
-    rc, t = plan.reduce(SUM, F32, [8192, 8192], 0)                         # outer axis, few outputs: split along the axis
-    assert t.count("launch reduce_cols_sum_f32") == 2 and "grid=(2368,1,1)" in t
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 0)                         # outer axis, few outputs: segments of the axis, finished
+    assert t.count("launch reduce_cols_sum_f32") == 1 and "grid=(2368,1,1)" in t   # in the same launch (ticket per column tile)
+    rc, t = plan.reduce(ARGMAX, F32, [1 << 20, 8], 0)                      # arg ops too: (key, index) partials, fused finish
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["reduce_cols_argmax_f32"] and t.count("alloc") == 2
     rc, t = plan.reduce(SUM, F32, [4, 1 << 26], 0)                         # short axis, many columns: persistent grid, one launch
     assert t.strip() == "launch reduce_cols_sum_f32 grid=(1184,1,1) block=256 smem=0 cluster=1"
     # views reduced in place (1x the logical bytes): pitched rows on every axis, transposed views, a permuted rank-3 view
@@ -279,9 +291,9 @@ def test_reduce_plans(plan):
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_all_argmax_f32"]
     rc, t = plan.reduce(SUM, F32, [3, 5, 7], 0, strides=[70, 14, 2])
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_cols_sum_f32"]
-    plan.option("reduce.variant", "tma")                                   # bulk-copy staged form: one CTA per SM, 8 x 16 KB ring
-    rc, t = plan.reduce(SUM, F32, [1 << 28], -1)
-    assert t.strip() == "launch reduce_all_sum_f32_tma grid=(148,1,1) block=288 smem=131200 cluster=1"
+    plan.option("reduce.variant", "tma")                                   # forced: used from 1 MB up
+    rc, t = plan.reduce(SUM, BF16, [1 << 20], -1)
+    assert t.strip() == "launch reduce_all_sum_bf16_tma grid=(128,1,1) block=288 smem=131200 cluster=1"
     rc, t = plan.reduce(SUM, F32, [1000], -1)                              # too small for a ring: plain loads
     assert "reduce_all_sum_f32 " in t
     plan.option("reduce.variant", "auto")

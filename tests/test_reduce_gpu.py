@@ -30,7 +30,8 @@ def test_sum_all_integer_pattern_exact(client, variant, n):
     try:
         x = (np.arange(n) % 8).astype(np.float32)
         got, _ = _run(client, x, None, "sum")
-        assert float(got[0]) == float(x.astype(np.float64).sum())
+        # exact integer partials everywhere; the only rounding is the final f64 -> f32 conversion of the total
+        assert float(got[0]) == float(np.float32(x.astype(np.float64).sum()))
     finally:
         client.set_option("reduce.variant", "auto")
 
@@ -246,6 +247,41 @@ def test_plane_sum_golden_through_the_cuda_path(client, golden, dtype, vec):
         assert got.tolist() == [496.0]
         got_all, _ = _run(client, inp, None, "sum", dtype)               # the same 32 values through the all-elements kernel
         assert got_all.tolist() == [496.0]
+
+
+def test_back_to_back_reductions_overlap_safely(client):
+    # consecutive all-element reductions on the client's stream overlap (programmatic dependent launch: the next launch
+    # streams its input while the previous one's last block finishes).  Results must be what serial execution gives:
+    # alternating inputs and outputs, the shared workspace reused every launch, and a chain whose input IS the previous
+    # output (that pair must not overlap)
+    n = (1 << 24) + 1024
+    xs, exp = [], []
+    for i in range(3):
+        x = ((np.arange(n) + i) % (5 + i)).astype(np.float32)
+        xs.append(TensorHandle.from_numpy(client, x, "f32"))
+        exp.append(float(np.float32(x.astype(np.float64).sum())))
+    outs = [TensorHandle.empty_contiguous(client, [1], "f32") for _ in range(60)]
+    aouts = [TensorHandle.empty_contiguous(client, [1], "u32") for _ in range(6)]
+    for variant in ("auto", "u8"):
+        client.set_option("reduce.variant", variant)
+        for k, o in enumerate(outs):
+            reduce.launch(client, xs[k % 3], o, None, "sum")
+        for k, o in enumerate(aouts):
+            reduce.launch(client, xs[k % 3], o, None, "argmax")
+        client.sync()
+        for k, o in enumerate(outs):
+            assert float(o.to_numpy(client)[0]) == exp[k % 3], (variant, k)
+        for k, o in enumerate(aouts):
+            assert int(o.to_numpy(client)[0]) == 4, (variant, k)   # first index holding the largest value of every pattern
+    client.set_option("reduce.variant", "auto")
+    chain = TensorHandle.empty_contiguous(client, [1], "f32")
+    reduce.launch(client, xs[0], outs[0], None, "sum")
+    reduce.launch(client, outs[0], chain, None, "sum")      # reads the predecessor's 4-byte result
+    assert float(chain.to_numpy(client)[0]) == exp[0]
+    client.set_option("reduce.pdl", "off")
+    reduce.launch(client, xs[1], outs[1], None, "sum")
+    assert float(outs[1].to_numpy(client)[0]) == exp[1]
+    client.set_option("reduce.pdl", "on")
 
 
 def test_arg_reductions_special_values(client):

@@ -31,26 +31,59 @@ if "reduce" in what:
     for i, t in enumerate(bufs):
         c.fill_uniform(t.handle, "f32", n, 5 + i, 0.0, 1.0)
     out = TensorHandle.empty_contiguous(c, [1], "f32")
+    aout = TensorHandle.empty_contiguous(c, [1], "u32")
+    scratch = c.empty(1024)
     k = [0]
 
     def run():
         k[0] += 1
         reduce.launch(c, bufs[k[0] % 3], out, None, "sum")
 
-    print("reduce-sum f32 2^28 (1 GiB), rotating 3 buffers (no L2 reuse):")
-    for variant in ("u2", "u4", "u8", "b4", "b8", "w2"):
-        for threads in (256, 512):
-            for bps in (2, 4, 8, 16):
-                if threads * bps > 4096:
-                    continue
-                c.set_option("reduce.variant", variant)
-                c.set_option("reduce.threads", threads)
-                c.set_option("reduce.blocks_per_sm", bps)
-                ms = time_ms(c, run)
-                print(f"  {variant:4s} threads={threads:4d} blocks/SM={bps}: {ms * 1e3:8.1f} us  {n * 4 / ms / 1e6:8.1f} GB/s", flush=True)
+    def run_arg():
+        k[0] += 1
+        reduce.launch(c, bufs[k[0] % 3], aout, None, "argmax")
+
+    def run_probe():
+        k[0] += 1
+        c.probe_memread(bufs[k[0] % 3].handle, n * 4, scratch)
+
+    print("reduce-sum f32 2^28 (1 GiB), rotating 3 buffers (no L2 reuse); min of 3 x 20 launches:")
+    rows = []
+    for variant, threads, bps in (("u8", 512, 4), ("u8", 512, 2), ("u8", 256, 8), ("u8", 256, 4), ("u4", 512, 4), ("u16", 512, 2), ("u16", 256, 4),
+                                  ("b8", 512, 4), ("b4", 512, 4), ("w2", 512, 4), ("w4", 512, 2), ("tma", 0, 1)):
+        c.set_option("reduce.variant", variant)
+        if threads:
+            c.set_option("reduce.threads", threads)
+            c.set_option("reduce.blocks_per_sm", bps)
+        ms = min(time_ms(c, run) for _ in range(3))
+        rows.append((ms, variant, threads, bps))
+        print(f"  {variant:4s} threads={threads:4d} blocks/SM={bps}: {ms * 1e3:8.1f} us  {n * 4 / ms / 1e6:8.1f} GB/s   ({c.last_kernel()})", flush=True)
     c.set_option("reduce.variant", "auto")
     c.set_option("reduce.threads", 512)
     c.set_option("reduce.blocks_per_sm", 4)
+    ms_p = min(time_ms(c, run_probe) for _ in range(3))
+    print(f"  reference-equivalent vec4 read probe, same buffers: {ms_p * 1e3:8.1f} us  {n * 4 / ms_p / 1e6:8.1f} GB/s")
+    ms_d = min(time_ms(c, run) for _ in range(3))
+    print(f"  default (auto, {c.last_kernel()}, back-to-back launches overlap through PDL): {ms_d * 1e3:8.1f} us  {n * 4 / ms_d / 1e6:8.1f} GB/s  = {ms_p / ms_d:.3f} x the probe")
+    c.set_option("reduce.pdl", "off")
+    ms_n = min(time_ms(c, run) for _ in range(3))
+    print(f"  default with reduce.pdl=off: {ms_n * 1e3:8.1f} us  {n * 4 / ms_n / 1e6:8.1f} GB/s  = {ms_p / ms_n:.3f} x the probe")
+    c.set_option("reduce.variant", "u8")
+    ms_u = min(time_ms(c, run) for _ in range(3))
+    c.set_option("reduce.pdl", "on")
+    ms_up = min(time_ms(c, run) for _ in range(3))
+    print(f"  plain 128-bit loads (u8): pdl off {ms_u * 1e3:8.1f} us {n * 4 / ms_u / 1e6:8.1f} GB/s | pdl on {ms_up * 1e3:8.1f} us {n * 4 / ms_up / 1e6:8.1f} GB/s")
+    c.set_option("reduce.variant", "auto")
+    ms_a = min(time_ms(c, run_arg) for _ in range(3))
+    print(f"  argmax f32 2^28 ({c.last_kernel()}): {ms_a * 1e3:8.1f} us  {n * 4 / ms_a / 1e6:8.1f} GB/s")
+    for dt in ("bf16", "f16"):
+        tb = [TensorHandle(bufs[i].handle, [n * 2], [1], dt) for i in range(3)]   # the same gigabyte read as 2^29 16-bit elements
+
+        def run16():
+            k[0] += 1
+            reduce.launch(c, tb[k[0] % 3], out, None, "max")
+        ms_h = min(time_ms(c, run16) for _ in range(3))
+        print(f"  max {dt} 2^29 ({c.last_kernel()}): {ms_h * 1e3:8.1f} us  {n * 4 / ms_h / 1e6:8.1f} GB/s")
     del bufs
 
 if "gemm" in what:
@@ -131,35 +164,58 @@ if "split" in what:
         if idt == "f32":
             c.set_option("gemm.f32", mode)
         flops = 2.0 * m * n * k * batch
-        row = []
-        for sk in ("off", "2", "3", "4", "auto"):
-            c.set_option("gemm.split_k", sk)
-            ms = min(time_ms(c, lambda: matmul.launch(c, a, b, o), iters=20, warm=3) for _ in range(3))
-            row.append(f"{sk}={ms * 1e3:7.1f}us/{flops / ms / 1e9:6.0f}TF")
+        import time as _time
+        opts = ("off", "2", "3", "4", "auto")
+        best = {sk: float("inf") for sk in opts}
+        for rnd in range(4):                      # interleaved rounds with a pause: no option is measured in a hotter state
+            for sk in (opts if rnd % 2 == 0 else opts[::-1]):
+                c.set_option("gemm.split_k", sk)
+                _time.sleep(0.05)
+                best[sk] = min(best[sk], time_ms(c, lambda: matmul.launch(c, a, b, o), iters=10, warm=2))
+        row = [f"{sk}={best[sk] * 1e3:7.1f}us/{flops / best[sk] / 1e9:6.0f}TF" for sk in opts]
+        fastest = min(best[sk] for sk in opts if sk != "auto")
+        row.append(f"auto/best={fastest / best['auto']:.3f}")
         print(f"  {idt:6s}->{odt:4s} {mode:6s} {batch}x{m}x{n}x{k}: " + "  ".join(row), flush=True)
         c.set_option("gemm.split_k", "auto")
         c.set_option("gemm.f32", "3xtf32")
         del a, b, o
 
 if "axis" in what:
-    # the reduction tutorial's shapes (cubecl-book: 1.085 ms / 3.124 ms / 1.483 ms / 0.924 ms on an unnamed wgpu device)
-    print("axis reductions (sum), CUDA events, min of 5 x 20 launches (reduce.row_balance off | on):")
-    for shape, axis in (([512, 8192], 1), ([128, 32768], 1), ([64, 256, 1024], 2), ([64, 64, 4096], 2), ([8192, 8192], 1),
-                        ([10000, 8192], 1), ([20000, 2048], 1), ([9000, 16384], 1),
-                        ([8192, 8192], 0), ([16, 1 << 24], 1), ([1 << 14, 1 << 14], 0), ([1 << 26, 4], 1), ([4, 1 << 26], 0)):
-        n = int(np.prod(shape))
-        t = TensorHandle.empty_contiguous(c, shape, "f32")
-        c.fill_uniform(t.handle, "f32", n, 11, 0.0, 1.0)
-        oshape = reduce.output_shape(shape, axis)
-        out = TensorHandle.empty_contiguous(c, oshape, "f32")
-        res = []
-        for mode in ("off", "on"):
-            c.set_option("reduce.row_balance", mode)
-            best = min(time_ms(c, lambda: reduce.launch(c, t, out, axis, "sum"), iters=20, warm=3) for _ in range(5))
-            res.append(f"{best * 1e3:9.1f} us {n * 4 / best / 1e6:8.1f} GB/s")
-        c.set_option("reduce.row_balance", "off")
-        print(f"  {str(shape):22s} axis={axis}: " + "  |  ".join(res), flush=True)
-        del t, out
+    # the reduction tutorial's shapes (cubecl-book: 1.085 ms / 3.124 ms / 1.483 ms / 0.924 ms on an unnamed wgpu device) and
+    # the shapes that stress the row / column kernels.  GB/s counts the ALGORITHMIC bytes: input read + output written.
+    # Inputs <= 64 MiB are rotated over enough copies to exceed the 126 MB L2.
+    print("axis reductions, CUDA events, min of 5 x 20 launches; GB/s = (input + output bytes) / time:")
+    shapes = (([512, 8192], 1), ([128, 32768], 1), ([64, 256, 1024], 2), ([64, 64, 4096], 2), ([8192, 8192], 1),
+              ([10000, 8192], 1), ([20000, 2048], 1), ([9000, 16384], 1), ([8192, 8192], 0), ([16, 1 << 24], 1),
+              ([1 << 14, 1 << 14], 0), ([1 << 26, 4], 1), ([4, 1 << 26], 0), ([1 << 22, 64], 0), ([64, 1 << 22], 1), ([256, 1024, 1024], 1))
+    sel = [a for a in what if a.startswith("vpt=")]
+    vpts = [int(a.split("=")[1]) for a in sel] or [8]
+    for op in ("sum", "argmax"):
+        for shape, axis in shapes:
+            n = int(np.prod(shape))
+            copies = max(1, min(8, (192 << 20) // (n * 4) + 1))
+            ts = [TensorHandle.empty_contiguous(c, shape, "f32") for _ in range(copies)]
+            for i, t in enumerate(ts):
+                c.fill_uniform(t.handle, "f32", n, 11 + i, 0.0, 1.0)
+            oshape = reduce.output_shape(shape, axis)
+            out = TensorHandle.empty_contiguous(c, oshape, reduce.output_dtype(op))
+            nbytes = n * 4 + int(np.prod(oshape)) * 4
+            k = [0]
+
+            def run():
+                k[0] += 1
+                reduce.launch(c, ts[k[0] % copies], out, axis, op)
+            res = []
+            for vpt in vpts:
+                c.set_option("reduce.rows_vpt", vpt)
+                l0 = c.launch_count()
+                run()
+                launches = c.launch_count() - l0
+                best = min(time_ms(c, run, iters=20, warm=3) for _ in range(5))
+                res.append(f"vpt={vpt}: {best * 1e3:8.1f} us {nbytes / best / 1e6:8.1f} GB/s")
+            c.set_option("reduce.rows_vpt", 8)
+            print(f"  {op:6s} {str(shape):22s} axis={axis} launches={launches} x{copies} buffers: " + "  |  ".join(res), flush=True)
+            del ts, out
 
 if "probes" in what:
     scratch = c.empty(1024)
