@@ -214,7 +214,7 @@ struct GemmParams {
   uint64_t bias;
   float alpha;
   uint32_t epi_on;
-  uint32_t full_tiles, split_tiles, split_s, pad0;  // tail split, see gemm_tcgen05.cu
+  uint32_t full_tiles, sk_tiles, sk_ranges, sk_umax;  // stream-K head, see gemm_tcgen05.cu
   uint64_t split_ws, split_tickets;
   uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;  // block-scaled kinds
   uint32_t tma_store, pad1;
@@ -272,7 +272,8 @@ static constexpr uint32_t kWsMaxBlocks = 4096;
 static constexpr uint32_t kWsTicketOffset = kWsMaxBlocks * 4 + kWsMaxBlocks * 8;
 static constexpr uint32_t kWsDebugOffset = kWsTicketOffset + 64;         // four u64 words written by the reduce grid stage on request
 static constexpr uint32_t kWsGemmTicketOffset = kWsTicketOffset + 256;  // u32 per (tail tile, CTA rank) of a split GEMM
-static constexpr uint32_t kWsColTicketOffset = kWsGemmTicketOffset + 1024;  // u32[1024]: one per (outer, column tile) of a fused split column reduction
+static constexpr uint32_t kWsGemmTickets = 1024;                             // u32 entries
+static constexpr uint32_t kWsColTicketOffset = kWsGemmTicketOffset + kWsGemmTickets * 4;  // u32[1024]: one per (outer, column tile) of a fused split column reduction
 static constexpr uint32_t kWsColTickets = 1024;
 static constexpr size_t kWsBytes = kWsColTicketOffset + kWsColTickets * 4;
 
@@ -524,7 +525,7 @@ extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) 
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
   static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm", "reduce.rows_vpt", "reduce.rows_blocks_per_sm", "reduce.cols_blocks_per_sm",
-                                "reduce.debug", "reduce.pdl"};
+                                "reduce.debug", "reduce.pdl", "reduce.tma_stages", "reduce.tma_ctas_per_sm"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
   return fail(B200_ERR_INVALID_ARG, "unknown option '%s'", key);
@@ -949,6 +950,52 @@ static bool tma_ok(const GemmProblem& g, bool* a_mn, bool* b_mn) {
 
 static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out);
 
+// Stream-K head plan for `tiles` tiles on `clusters` CTA pairs (gemm_tcgen05.cu, GemmParams): the rem = tiles % clusters
+// tiles that would form a partial last wave are instead cut along K into `ranges` equal ranges processed FIRST, so all
+// pairs stay busy and the slab exchange runs under the whole tiles that follow.
+//   time (in tile-times) without: full_waves + 1.   with: full_waves + rem / clusters + overhead / num_kb, where the overhead
+//   (in k-block times) is small when whole tiles follow (slab store + ticket, hidden: ~4) and (14 + 8 parts) when the head
+//   is the whole problem (measured round 1: publishing, the ticket round trip and the ordered re-read are exposed).
+// gemm.split_k: auto (only when the model gains >= 4 %), off, on (whenever rem != 0), or N = 1..8 (N ranges per tile).
+struct SkPlan {
+  double time = 0;           // modelled time in tile-times
+  uint64_t sk_tiles = 0, ranges = 0, umax = 0;
+  bool bad_option = false;
+};
+static SkPlan sk_plan(uint64_t tiles, uint64_t clusters, uint64_t num_kb, const std::string& option, bool eligible) {
+  SkPlan pl;
+  const uint64_t full_waves = tiles / clusters, rem = tiles % clusters;
+  pl.time = static_cast<double>(full_waves + (rem ? 1 : 0));
+  if (option == "off" || !eligible || rem == 0 || num_kb < 2) return pl;
+  uint64_t ranges = clusters;
+  bool force = false;
+  if (option == "on") force = true;
+  else if (option != "auto") {
+    const int want = atoi(option.c_str());
+    if (want < 1 || want > 8) { pl.bad_option = true; return pl; }
+    if (want == 1) return pl;
+    ranges = rem * static_cast<uint64_t>(want);
+    force = true;
+  }
+  const uint64_t total_kb = rem * num_kb;
+  ranges = std::min(ranges, total_kb);                                    // every range owns at least one k-block
+  if (ranges <= rem && !force) return pl;                                 // no tile would be cut
+  const uint64_t share = (total_kb + ranges - 1) / ranges;
+  const double parts = std::max(1.0, static_cast<double>(ranges) / static_cast<double>(rem));
+  const double head = static_cast<double>((ranges + clusters - 1) / clusters) * static_cast<double>(share) / static_cast<double>(num_kb);
+  const double overhead = (full_waves >= 1 ? 4.0 : 14.0 + 8.0 * parts) / static_cast<double>(num_kb);
+  const double t_sk = static_cast<double>(full_waves) + head + overhead;
+  if (!force) {
+    if (share < 8) return pl;                                             // slices too thin to amortise an exchange
+    if (t_sk > 0.96 * pl.time) return pl;
+  }
+  pl.time = t_sk;
+  pl.sk_tiles = rem;
+  pl.ranges = ranges;
+  pl.umax = (share + num_kb - 1) / num_kb + 1;                            // tiles one range can touch
+  return pl;
+}
+
 static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
   const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
   const char* in_tag = g.mx_kind == 1 ? "mxf8" : g.mx_kind == 2 ? "mxf4" : g.mx_kind == 3 ? "nvf4"
@@ -957,10 +1004,16 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : g.out_dtype == B200_I32 ? "i32" : "f32";
   const uint32_t block_k = static_cast<uint32_t>(128 / esz);
 
-  // pick the tile variant by padded work per wave (ties -> larger tile, less L2 traffic)
+  // pick the tile variant by modelled time (ties -> larger tile, less L2 traffic): waves of tiles, with the last partial wave
+  // replaced by a stream-K head where that pays (sk_plan)
   const std::string forced = opt(c, "gemm.variant", "auto");
+  const std::string split_opt = opt(c, "gemm.split_k", "auto");
+  const bool float_acc = !(g.in_dtype == B200_U8 || g.in_dtype == B200_I8);
+  const uint64_t k_segments = (g.a_lo != 0 && g.b_lo != 0) ? 3 : 1;
+  const uint64_t num_kb = ((g.K + block_k - 1) / block_k) * k_segments;
   const GemmVariant* best = nullptr;
   double best_cost = 0;
+  SkPlan best_sk;
   for (const GemmVariant& v : kVariants) {
     if (forced != "auto" && forced != v.tag) continue;
     if (forced == "auto" && v.eff <= 0.0) continue;
@@ -973,14 +1026,16 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     const uint64_t tm = (g.M + tile_m - 1) / tile_m, tn = (g.N + v.block_n - 1) / v.block_n;
     const uint64_t tiles = tm * tn * g.batch;
     const uint64_t clusters = std::max(1, c->props.num_sms / v.cg);
-    const uint64_t waves = (tiles + clusters - 1) / clusters;
+    // the slab exchange is a per-128-row-CTA-tile protocol with f32 accumulators: not for the pair tile, not for integers
+    const SkPlan sk = sk_plan(tiles, clusters, num_kb, split_opt, float_acc && v.mt == 1);
     // block-scaled kinds: measured 8192^3 ratios to the 256-wide tile are 0.63 (2sm_n128) and 0.61 (1sm_n128) for mxfp8,
     // 0.63 / 0.66 for mxfp4 -- the same ordering as the unscaled table, so it is reused
     const double eff = v.eff > 0 ? v.eff : 1.0;
-    const double cost = static_cast<double>(waves) * (128.0 * v.mt * v.block_n) / eff;  // per-SM MMA time per wave
-    if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; }
+    const double cost = sk.time * (128.0 * v.mt * v.block_n) / eff;  // per-SM MMA time
+    if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; best_sk = sk; }
   }
   if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant for this dtype", forced.c_str());
+  if (best_sk.bad_option) return fail(B200_ERR_INVALID_ARG, "gemm.split_k must be auto, off, on or 1..8");
   const GemmVariant& v = *best;
 
   const std::string name = std::string("gemm_") + in_tag + "_" + out_tag + "_" + v.tag + (a_mn ? "_m" : "_k") + (b_mn ? "n" : "k");
@@ -1045,7 +1100,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }
-  p.k_segments = split ? 3 : 1;
+  p.k_segments = (uint32_t)k_segments;
   p.alpha = g.alpha; p.bias = g.bias; p.epi_act = g.act;
   p.epi_on = (g.alpha != 1.0f || g.bias != 0 || g.act != 0) ? 1u : 0u;
   p.out = g.out;
@@ -1076,52 +1131,29 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   const unsigned max_clusters = (unsigned)std::max(1, c->props.num_sms / v.cg);
   unsigned clusters = (unsigned)std::min<uint64_t>(total_tiles, max_clusters);
 
-  // Tail split: when the last wave would leave most CTA pairs idle, cut each of its tiles into S K-slices (deterministic:
-  // slabs are added in slice order by whichever slice finishes last).  time(S) in tile-times = full_waves + ceil(rem*S/C)/S.
-  const std::string split_opt = opt(c, "gemm.split_k", "auto");
-  const uint64_t num_kb = ((g.K + block_k - 1) / block_k) * p.k_segments;
-  const uint64_t rem = total_tiles % max_clusters, full_waves = total_tiles / max_clusters;
-  const bool float_acc = !(g.in_dtype == B200_U8 || g.in_dtype == B200_I8);
-  unsigned split_s = 1;
-  if (split_opt != "off" && float_acc && rem != 0 && v.mt == 1) {  // the slab protocol is per 128-row CTA tile
-    const unsigned s_max = 4, min_kb = 8;
-    if (split_opt == "auto") {
-      double best_t = static_cast<double>(full_waves) + 1.0;
-      const double base_t = best_t;
-      for (unsigned s2 = 2; s2 <= s_max; ++s2) {
-        if (num_kb / s2 < min_kb) break;
-        // Measured on B200 (tools/perf_sweep.py split, profiles/r01_split_k_sweep.log): publishing a slab, the ticket round
-        // trip and the ordered re-read by the last slice cost about (14 + 8 S) k-block times (one k-block = 128 B of K per
-        // row, ~0.4 us on a pair tile whatever the dtype), all exposed because nothing follows the tail.  So the split pays
-        // for K-heavy problems with few tiles (512^2 x 16384: 114 -> 50 us) and not for 4096^3 bf16 (break-even).
-        const double overhead = (14.0 + 8.0 * s2) / static_cast<double>(num_kb);
-        const double t = full_waves + static_cast<double>((rem * s2 + max_clusters - 1) / max_clusters) / s2 + overhead;
-        if (t < best_t - 1e-9) { best_t = t; split_s = s2; }
-      }
-      if (base_t - best_t < 0.08 * base_t) split_s = 1;  // inside the measurement noise: keep whole tiles
-    } else {
-      const int want = atoi(split_opt.c_str());
-      if (want < 1 || want > 8) return fail(B200_ERR_INVALID_ARG, "gemm.split_k must be auto, off or 1..8");
-      split_s = (unsigned)std::min<uint64_t>((uint64_t)want, std::max<uint64_t>(1, num_kb));
-    }
-  }
+  // Stream-K head (plan chosen with the variant above)
   CUdeviceptr slabs = 0;
-  if (split_s > 1) {
+  p.full_tiles = (uint32_t)total_tiles;
+  if (best_sk.sk_tiles) {
+    if (best_sk.sk_tiles * v.cg > kWsGemmTickets) return fail(B200_ERR_UNSUPPORTED, "stream-K head: %llu tiles exceed the ticket area", (unsigned long long)best_sk.sk_tiles);
     CUdeviceptr ws = 0;
     rc = reduce_workspace(c, st, &ws);
     if (rc) return rc;
     const uint64_t slab_bytes = 128ull * v.cg * v.block_n * 4;
-    rc = pool_alloc(c, rem * split_s * slab_bytes, &slabs, st);
+    rc = pool_alloc(c, best_sk.ranges * best_sk.umax * slab_bytes, &slabs, st);
     if (rc) return rc;
-    p.full_tiles = (uint32_t)(total_tiles - rem);
-    p.split_tiles = (uint32_t)rem;
-    p.split_s = split_s;
+    p.full_tiles = (uint32_t)(total_tiles - best_sk.sk_tiles);
+    p.sk_tiles = (uint32_t)best_sk.sk_tiles;
+    p.sk_ranges = (uint32_t)best_sk.ranges;
+    p.sk_umax = (uint32_t)best_sk.umax;
     p.split_ws = slabs;
     p.split_tickets = ws + kWsGemmTicketOffset;
-    clusters = (unsigned)std::min<uint64_t>(p.full_tiles + rem * split_s, max_clusters);
+    // the head's ranges are dealt to pairs 0 .. ranges-1 (mod the grid); whole tiles to every pair
+    clusters = (unsigned)std::min<uint64_t>(std::max<uint64_t>(p.full_tiles, best_sk.ranges), max_clusters);
     if (c->dry) {
-      char line[160];
-      snprintf(line, sizeof(line), "gemm tail split: %u full tiles + %u tiles x %u k-slices\n", p.full_tiles, p.split_tiles, split_s);
+      char line[200];
+      snprintf(line, sizeof(line), "gemm stream-k head: %u whole tiles + %u tiles in %u k-ranges (<= %u slabs per range)\n", p.full_tiles, p.sk_tiles,
+               p.sk_ranges, p.sk_umax);
       c->plan += line;
     }
   }
@@ -1440,7 +1472,7 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RVi
   std::string name = std::string(pitched ? "reduce_allp_" : "reduce_all_") + op_tag(op) + "_" + dt_tag(dt);
   unsigned threads = opt_uint(c, "reduce.threads", 512, 32, 512) / 32 * 32;
   unsigned bps = opt_uint(c, "reduce.blocks_per_sm", 4, 1, 64);
-  unsigned smem = 0;
+  unsigned smem = 0, stages = 0;
   bool bulk = false;
   if (!pitched && !arg) {
     // variants: the plain 128-bit streaming kernel, its tuning forms (f32 sum only) and the bulk-copy staged kernel
@@ -1458,9 +1490,11 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RVi
   if (bulk) {
     name += "_tma";
     threads = 256 + 32;                       // eight consumer warps + one producer warp
-    smem = 8 * 16384 + 128;
+    stages = opt_uint(c, "reduce.tma_stages", 8, 2, 8);
+    smem = stages * 16384 + 128;
     const uint64_t tiles = n * esz / 16384;
-    grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)c->props.num_sms * opt_uint(c, "reduce.blocks_per_sm", 1, 1, 1)));
+    const unsigned per_sm = stages <= 6 ? opt_uint(c, "reduce.tma_ctas_per_sm", 1, 1, 2) : 1;
+    grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)c->props.num_sms * per_sm));
   } else {
     const uint64_t want = (n / vec + threads - 1) / threads;  // blocks that still get >= 1 vector per thread
     grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)c->props.num_sms * bps, kWsMaxBlocks)));
@@ -1477,6 +1511,7 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RVi
   p.outer = 1; p.len = n; p.inner = 1;
   p.row_len = v.row_len; p.row_pitch = v.row_pitch;
   p.seg_len = n; p.nseg = 1; p.scale = scale;
+  p.ctu = stages;                             // bulk-copy kernels: ring depth
   void* args[] = {&p};
   // Overlap with the preceding all-element reduction on the context's stream: safe because that kernel writes only its
   // 4-byte result and the workspace, this one reads neither before its own griddepcontrol.wait -- unless its input is the

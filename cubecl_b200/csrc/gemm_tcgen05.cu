@@ -31,13 +31,16 @@ struct GemmParams {
   uint64_t bias;              // f32[N] added per output column, or 0
   float alpha;                // out = act(alpha * acc + bias[n]); the epilogue is skipped when alpha == 1, bias == 0, act == 0
   uint32_t epi_on;
-  // Tail split (deterministic split-K for a mostly empty last wave): work units [0, full_tiles) are whole tiles; each of the
-  // remaining `split_tiles` tiles is cut into `split_s` K-slices that run on different CTA pairs.  A slice stores its f32
-  // accumulators to its own slab in `split_ws`; the last slice to finish (ticket) adds the slabs in slice order and writes
-  // the output, so the result does not depend on which slice arrived last.  split_s <= 1 disables the mechanism.
-  uint32_t full_tiles, split_tiles, split_s, pad0;
-  uint64_t split_ws;          // slabs: [split_tiles][split_s][CG] x (128 x BLOCK_N f32, thread-interleaved 16 B units)
-  uint64_t split_tickets;     // u32 [split_tiles][CG], zero on entry, left zero on exit
+  // Stream-K head (deterministic, replaces a mostly empty LAST wave): tiles [0, full_tiles) are whole "data-parallel" tiles;
+  // the k-blocks of the remaining `sk_tiles` tiles form one linear space of sk_tiles * num_kb k-blocks that is cut into
+  // `sk_ranges` equal ranges; CTA pair c works through ranges c, c + C, ... FIRST (a range may cover the end of one tile and
+  // the start of the next: one work unit per tile it touches), then through its whole tiles c, c + C, ....  A unit that
+  // covers only part of a tile's K stores its f32 accumulators to its own slab and takes a ticket for the tile; whoever
+  // completes the tile adds the slabs in k order (so the result does not depend on who came last) and writes the output --
+  // under the MMAs of the following whole tiles, which is why the partial tiles go first.  sk_tiles == 0 disables it.
+  uint32_t full_tiles, sk_tiles, sk_ranges, sk_umax;  // sk_umax: slabs reserved per range (max tiles a range can touch)
+  uint64_t split_ws;          // slabs: [sk_ranges][sk_umax][CG] x (128 x BLOCK_N f32, thread-interleaved 16 B units)
+  uint64_t split_tickets;     // u32 [sk_tiles][CG], zero on entry, left zero on exit
   // Block-scaled kinds (KIND_MXF8 / KIND_MXF4): operand formats for the instruction descriptor and the number of 128-row
   // scale-factor tiles per batch entry of each operand (the packed scale tensors are [batch * tiles][k atoms][512 B]).
   uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;
@@ -116,23 +119,67 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, const GemmParams& p)
 }
 
 struct WorkUnit {
-  uint32_t tile, kb0, kb1, slice;
+  uint32_t tile, kb0, kb1;
+  uint32_t slab;   // partial units: slab index (range * sk_umax + unit within the range)
   bool partial;
 };
 
-__device__ __forceinline__ WorkUnit unit_decode(uint32_t u, const GemmParams& p, uint32_t num_kb) {
-  WorkUnit w;
-  if (p.split_s <= 1 || u < p.full_tiles) {
-    w.tile = u; w.kb0 = 0; w.kb1 = num_kb; w.slice = 0; w.partial = false;
-  } else {
-    const uint32_t v = u - p.full_tiles;
-    w.tile = p.full_tiles + v / p.split_s;
-    w.slice = v % p.split_s;
-    w.kb0 = static_cast<uint32_t>((static_cast<uint64_t>(num_kb) * w.slice) / p.split_s);
-    w.kb1 = static_cast<uint32_t>((static_cast<uint64_t>(num_kb) * (w.slice + 1)) / p.split_s);
-    w.partial = true;
+// The sequence of work units of one CTA pair: stream-K ranges first, whole tiles after (see GemmParams).  Every role of the
+// CTA (TMA producers, MMA issuer, epilogue warps) walks the same sequence with its own copy of this iterator.
+struct UnitIter {
+  uint32_t c, C, num_kb;
+  uint32_t r;          // current stream-K range (c, c + C, ...), >= sk_ranges once the head is done
+  uint32_t u;          // unit index inside the current range
+  uint64_t pos, hi;    // unconsumed part [pos, hi) of the current range, in linear k-blocks
+  uint32_t next_tile;  // next whole tile
+  bool open;           // [pos, hi) of range r has been set up
+};
+
+__device__ __forceinline__ UnitIter unit_iter(uint32_t cluster, uint32_t n_clusters, uint32_t num_kb) {
+  UnitIter it;
+  it.c = cluster; it.C = n_clusters; it.num_kb = num_kb;
+  it.r = cluster; it.u = 0; it.pos = 0; it.hi = 0; it.next_tile = cluster; it.open = false;
+  return it;
+}
+
+__device__ __forceinline__ uint64_t sk_range_lo(uint32_t r, const GemmParams& p, uint32_t num_kb) {
+  return (static_cast<uint64_t>(r) * p.sk_tiles * num_kb) / p.sk_ranges;
+}
+// range that owns linear k-block x: the largest r with sk_range_lo(r) <= x (ranges are non-empty: sk_ranges <= sk_tiles * num_kb)
+__device__ __forceinline__ uint32_t sk_owner(uint64_t x, const GemmParams& p, uint32_t num_kb) {
+  return static_cast<uint32_t>(((x + 1) * p.sk_ranges - 1) / (static_cast<uint64_t>(p.sk_tiles) * num_kb));
+}
+
+__device__ __forceinline__ bool next_unit(UnitIter& it, const GemmParams& p, WorkUnit& w) {
+  while (p.sk_tiles != 0 && it.r < p.sk_ranges) {
+    if (!it.open) {
+      it.pos = sk_range_lo(it.r, p, it.num_kb);
+      it.hi = sk_range_lo(it.r + 1, p, it.num_kb);
+      it.u = 0;
+      it.open = true;
+    }
+    if (it.pos < it.hi) {
+      const uint32_t tau = static_cast<uint32_t>(it.pos / it.num_kb);
+      const uint64_t t0 = static_cast<uint64_t>(tau) * it.num_kb;
+      const uint64_t end = (it.hi < t0 + it.num_kb) ? it.hi : t0 + it.num_kb;
+      w.tile = p.full_tiles + tau;
+      w.kb0 = static_cast<uint32_t>(it.pos - t0);
+      w.kb1 = static_cast<uint32_t>(end - t0);
+      w.partial = !(w.kb0 == 0 && w.kb1 == it.num_kb);
+      w.slab = it.r * p.sk_umax + it.u;
+      it.pos = end;
+      ++it.u;
+      return true;
+    }
+    it.r += it.C;
+    it.open = false;
   }
-  return w;
+  if (it.next_tile < p.full_tiles) {
+    w.tile = it.next_tile; w.kb0 = 0; w.kb1 = it.num_kb; w.slab = 0; w.partial = false;
+    it.next_tile += it.C;
+    return true;
+  }
+  return false;
 }
 
 // Block-scaled kinds reuse the whole pipeline.  Per k-block (128 bytes of K per row) the stage additionally carries the
@@ -235,8 +282,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const uint32_t total_tiles = (p.split_s > 1) ? p.full_tiles + p.split_tiles * p.split_s  // work units, see GemmParams
-                                               : p.batch * p.tiles_m * p.tiles_n;
   // 3xTF32: x = hi + lo with hi = the top 19 bits of x (exactly what the tf32 datapath reads from an f32 operand, so the
   // ORIGINAL tensors serve as "hi") and lo = x - hi materialised once.  A*B ~= hi*hi + hi*lo + lo*hi is accumulated by
   // running the K loop over three segments with the operand descriptors swapped per segment.
@@ -256,8 +301,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       const uint32_t leader_full0 = (CG == 2) ? mapa_shared(full_bar(0), 0) : full_bar(0);
       constexpr int kAItems = A_MN ? NUM_CHUNKS_A : MT, kBItems = B_MN ? NUM_CHUNKS : 1;
       uint32_t s = 0, ph = 0;
-      for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
-        const WorkUnit wu = unit_decode(t, p, num_kb);
+      UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
+      WorkUnit wu;
+      while (next_unit(it, p, wu)) {
         const TileCoord tc = tile_coord(wu.tile, p);
         const int m0 = static_cast<int>((tc.m_blk * CG + rank) * (128 * MT));
         const int n0 = static_cast<int>(tc.n_blk * BLOCK_N + rank * N_LOCAL);
@@ -310,8 +356,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     // ===================================================================== MMA issuer (one thread, leader CTA)
     if (leader && lane == 0) {
       uint32_t s = 0, ph = 0, as = 0, aph = 0;
-      for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
-        const WorkUnit wu = unit_decode(t, p, num_kb);
+      UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
+      WorkUnit wu;
+      while (next_unit(it, p, wu)) {
         if constexpr (MT == 1) {
           mbar_wait(tempty_bar(as), aph ^ 1);  // epilogue (both CTAs) drained this accumulator stage
           tcgen05_fence_after();
@@ -414,9 +461,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         }
       }
     };
-    for (uint32_t t = cluster_id; t < total_tiles; t += n_clusters) {
-      const WorkUnit wu = unit_decode(t, p, num_kb);
-      const bool partial = (MT == 1) && wu.partial;  // the tail split is a 256-thread, one-unit protocol: never planned for MT = 2
+    UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
+    WorkUnit wu;
+    while (next_unit(it, p, wu)) {
+      const bool partial = (MT == 1) && wu.partial;  // the slab exchange is a 256-thread, one-unit protocol: never planned for MT = 2
       const TileCoord tc = tile_coord(wu.tile, p);
       const uint32_t row_in_cta = q * 32 + lane;
       const uint32_t unit = as * MT + mt;  // barrier pair + TMEM column block of this accumulator
@@ -543,12 +591,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           }
         }
       } else {
-        // K-slice of a tail tile: raw f32 accumulators -> this slice's slab.  Slab layout per CTA: [chunk c][j][thread] x 16 B,
-        // so one warp store covers 512 contiguous bytes (a row-per-thread layout costs 32 LSU wavefronts per store and is
-        // exposed here: nothing overlaps the tail).
-        const uint32_t tail = wu.tile - p.full_tiles;
+        // part of a stream-K tile's K range: raw f32 accumulators -> this unit's slab.  Slab layout per CTA: [chunk c][j][thread]
+        // x 16 B, so one warp store covers 512 contiguous bytes (a row-per-thread layout costs 32 LSU wavefronts per store).
         const uint64_t cta_slab_bytes = static_cast<uint64_t>(128) * BLOCK_N * 4;
-        uint4* dst = reinterpret_cast<uint4*>(p.split_ws + ((static_cast<uint64_t>(tail) * p.split_s + wu.slice) * CG + rank) * cta_slab_bytes) + row_in_cta;
+        uint4* dst = reinterpret_cast<uint4*>(p.split_ws + (static_cast<uint64_t>(wu.slab) * CG + rank) * cta_slab_bytes) + row_in_cta;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
@@ -567,15 +613,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       }
       if (++as == ACC) { as = 0; aph ^= 1; }
       if (partial) {
-        // publish the slab, take a ticket for (tile, CTA rank); the last of the split_s slices reduces in slice order
-        const uint32_t tail = wu.tile - p.full_tiles;
+        // publish the slab, take a ticket for (tile, CTA rank); whoever completes the tile's set of parts reduces them in k order
+        const uint32_t tau = wu.tile - p.full_tiles;
+        const uint32_t first = sk_owner(static_cast<uint64_t>(tau) * num_kb, p, num_kb);               // range holding the tile's k-block 0
+        const uint32_t parts = sk_owner(static_cast<uint64_t>(tau + 1) * num_kb - 1, p, num_kb) - first + 1;
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 128) {
-          unsigned int* ticket = reinterpret_cast<unsigned int*>(p.split_tickets) + tail * CG + rank;
+          unsigned int* ticket = reinterpret_cast<unsigned int*>(p.split_tickets) + tau * CG + rank;
           const unsigned int old = atomicAdd(ticket, 1u);
-          const uint32_t last = (old == p.split_s - 1) ? 1u : 0u;
-          if (last) *ticket = 0;  // every slice has arrived: leave the ticket ready for the next launch
+          const uint32_t last = (old == parts - 1) ? 1u : 0u;
+          if (last) *ticket = 0;  // every part has arrived: leave the ticket ready for the next launch
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(split_flag), "r"(last) : "memory");
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -584,18 +632,22 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         if (last) {
           __threadfence();
           const uint64_t cta_slab_bytes = static_cast<uint64_t>(128) * BLOCK_N * 4;
-          const uint64_t slice_stride = cta_slab_bytes * CG / 16;  // in uint4
-          const float4* src0 = reinterpret_cast<const float4*>(p.split_ws + (static_cast<uint64_t>(tail) * p.split_s * CG + rank) * cta_slab_bytes) + row_in_cta;
+          // slab of part j of this tile: range first + j; the tile is that range's (tau - first tile of the range)-th unit
+          auto part_slab = [&](uint32_t j) {
+            const uint32_t r = first + j;
+            const uint32_t u = tau - static_cast<uint32_t>(sk_range_lo(r, p, num_kb) / num_kb);
+            return reinterpret_cast<const float4*>(p.split_ws + ((static_cast<uint64_t>(r) * p.sk_umax + u) * CG + rank) * cta_slab_bytes) + row_in_cta;
+          };
 #pragma unroll 1
           for (int c = 0; c < BLOCK_N / 32; ++c) {
             float acc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-            // slices are ADDED in slice order (bit-reproducible); two slices' loads are in flight at a time
-            for (uint32_t sl = 0; sl < p.split_s; sl += 2) {
-              const bool two = sl + 1 < p.split_s;
-              const float4* s0 = src0 + sl * slice_stride + c * 8 * 128;
-              const float4* s1 = s0 + (two ? slice_stride : 0);
+            // parts are ADDED in k order (bit-reproducible whoever arrived last); two parts' loads are in flight at a time
+            for (uint32_t sl = 0; sl < parts; sl += 2) {
+              const bool two = sl + 1 < parts;
+              const float4* s0 = part_slab(sl) + c * 8 * 128;
+              const float4* s1 = two ? part_slab(sl + 1) + c * 8 * 128 : s0;
               float4 x0[8], x1[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) x0[j] = __ldcg(s0 + j * 128);

@@ -65,7 +65,7 @@ constexpr uint32_t kWsMaxBlocks = 4096;
 constexpr uint32_t kWsIdxOffset = kWsMaxBlocks * 4;
 constexpr uint32_t kWsTicketOffset = kWsIdxOffset + kWsMaxBlocks * 8;
 constexpr uint32_t kWsDebugOffset = kWsTicketOffset + 64;
-constexpr uint32_t kWsColTicketOffset = kWsTicketOffset + 256 + 1024;   // after the GEMM's tickets: u32[1024], one per (outer, column tile)
+constexpr uint32_t kWsColTicketOffset = kWsTicketOffset + 256 + 4096;   // after the GEMM's 1024 tickets: u32[1024], one per (outer, column tile)
 constexpr uint32_t kWsColTickets = 1024;
 
 // ------------------------------------------------------------------------------------------------ value ops
@@ -545,7 +545,8 @@ __device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const Xgp
 // window of gridDim x 16 KB x (stages in flight); no register is spent on loads in flight and no address arithmetic per
 // 16 bytes.  Head (unaligned base) and tail (< one tile) elements go through plain loads.
 constexpr uint32_t kBulkStageBytes = 16384;
-constexpr int kBulkStages = 8;
+constexpr int kBulkStages = 8;       // at most; the launch picks the ring depth (ReduceParams::ctu): 8 = one CTA per SM,
+                                     // <= 6 lets two CTAs share an SM (the next launch's CTA can start under PDL)
 constexpr int kBulkConsumers = 256;  // threads; + one producer warp
 
 template <int OP, int DT>
@@ -559,6 +560,7 @@ __device__ __forceinline__ void reduce_all_bulk_body(const ReduceParams& p) {
   __shared__ uint64_t s_bars[2 * kBulkStages];
   const uint32_t ring = (b200::smem_u32(bulk_smem_raw) + 127u) & ~127u;
   const uint32_t full0 = b200::smem_u32(s_bars), empty0 = full0 + 8u * kBulkStages;
+  const uint32_t stages = (p.ctu >= 2 && p.ctu <= static_cast<uint32_t>(kBulkStages)) ? p.ctu : static_cast<uint32_t>(kBulkStages);
 
   const uint64_t n = p.len;
   const uint32_t mis = static_cast<uint32_t>(p.in) & 15u;
@@ -572,7 +574,7 @@ __device__ __forceinline__ void reduce_all_bulk_body(const ReduceParams& p) {
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBulkStages; ++s) {
+    for (uint32_t s = 0; s < stages; ++s) {
       b200::mbar_init(full0 + 8u * s, 1);
       b200::mbar_init(empty0 + 8u * s, kBulkConsumers / 32);
     }
@@ -590,7 +592,7 @@ __device__ __forceinline__ void reduce_all_bulk_body(const ReduceParams& p) {
         b200::mbar_wait(empty0 + 8u * s, ph ^ 1u);
         b200::mbar_arrive_expect_tx(full0 + 8u * s, kBulkStageBytes);
         b200::bulk_load_1d(ring + s * kBulkStageBytes, base + t * kBulkStageBytes, kBulkStageBytes, full0 + 8u * s, pol);
-        if (++s == kBulkStages) { s = 0; ph ^= 1u; }
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
     __syncwarp();
@@ -618,7 +620,7 @@ __device__ __forceinline__ void reduce_all_bulk_body(const ReduceParams& p) {
       }
       __syncwarp();
       if (lane == 0) b200::mbar_arrive(empty0 + 8u * s);  // every lane has consumed its slices: the stage may be refilled
-      if (++s == kBulkStages) { s = 0; ph ^= 1u; }
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
     // head + tail through plain loads, spread over the consumers of the whole grid
     const uint64_t ctid = static_cast<uint64_t>(blockIdx.x) * kBulkConsumers + threadIdx.x;
@@ -802,9 +804,9 @@ __device__ __forceinline__ void reduce_rows_body(const ReduceParams& p, int tpr_
       if (head > L) head = L;
       const uint64_t nvec = (L - head) / VEC;
       const char* vb = rb + head * sizeof(T);
-      if (t < head) {
-        const float f = E::get(rb, t);
-        if constexpr (ARG) cand.feed<OP>(f, t);
+      for (uint64_t i = t; i < head; i += tpr) {   // up to VEC - 1 head elements, possibly more than the item has threads
+        const float f = E::get(rb, i);
+        if constexpr (ARG) cand.feed<OP>(f, static_cast<uint32_t>(i));
         else a1 = ValOp<OP>::apply(a1, f);
       }
       uint64_t v = t;
@@ -1109,7 +1111,7 @@ extern "C" __global__ void __launch_bounds__(256) reduce_argcombine(const __grid
     reduce_all_body<OP, DT, UNROLL, WIDE>(p);                                                                             \
   }
 #define REDUCE_ALL_BULK(NAME, OP, DT)                                                                               \
-  extern "C" __global__ void __launch_bounds__(kBulkConsumers + 32, 1) NAME(const __grid_constant__ ReduceParams p) { \
+  extern "C" __global__ void __launch_bounds__(kBulkConsumers + 32, 2) NAME(const __grid_constant__ ReduceParams p) { \
     reduce_all_bulk_body<OP, DT>(p);                                                                                \
   }
 #define REDUCE_ALL_PITCHED(NAME, OP, DT)                                                           \

@@ -97,37 +97,46 @@ def test_f32_defaults_to_3xtf32_with_two_split_passes(plan):
     assert t.count("tmap ") == 5                                         # A, B (originals = hi) + A_lo, B_lo + C
     assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
     assert t.count(f"alloc {n * n * 4}") == 2                            # 1x temporaries (lo parts), not 3x
-    assert "gemm tail split: 222 full tiles + 34 tiles x 2 k-slices" in t  # 256 tiles on 74 CTA pairs: 4th wave is 46 % full
+    # 256 tiles on 74 CTA pairs = 3.46 waves: the 34 tiles of the partial wave become a stream-K head cut into 74 equal k-ranges
+    assert "gemm stream-k head: 222 whole tiles + 34 tiles in 74 k-ranges" in t
     plan.option("gemm.f32", "tf32")
     rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gemm_tf32_f32_2sm_n256_kn"]
 
 
-def test_tail_split_policy(plan):
-    """Deterministic split-K of the last partial wave (launch_tcgen05): only when it pays, never for integer accumulators."""
+def test_stream_k_head_policy(plan):
+    """Deterministic stream-K head instead of a partial last wave (launch_tcgen05 / sk_plan): only when the model gains,
+    never for integer accumulators or the pair tile; it also feeds the tile choice."""
     def mm(n, k, dt=BF16, out=BF16):
         return plan.matmul(dt, out, [n, k], [k, 1], [k, n], [n, 1], [n, n], [n, 1])
-    rc, t = mm(8192, 8192)                     # 1024 tiles = 13.8 waves: tail is 84 % full, nothing to gain
-    assert rc == 0 and "tail split" not in t
-    rc, t = mm(4096, 4096)                     # 3.46 waves, but 64 k-blocks per tile: the slab exchange would eat the gain
-    assert rc == 0 and "tail split" not in t
-    rc, t = mm(4096, 4096, dt=F32, out=F32)    # 3xTF32: 384 k-blocks per tile -> 3 waves + 68 half tiles on 74 pairs
-    assert rc == 0 and "222 full tiles + 34 tiles x 2 k-slices" in t
-    assert f"alloc {34 * 2 * 256 * 256 * 4}" in t and "grid=(148,1,1)" in t
-    rc, t = mm(1024, 8192)                     # 32 n128 tiles on 74 pairs: 2 slices fill 64 of them
-    assert rc == 0 and "0 full tiles + 32 tiles x 2 k-slices" in t and "2sm_n128" in t and "grid=(128,1,1)" in t
-    rc, t = mm(512, 16384)                     # 8 tiles, 256 k-blocks each: 4 slices
-    assert rc == 0 and "0 full tiles + 8 tiles x 4 k-slices" in t
-    rc, t = mm(1024, 256)                      # 4 k-blocks: too short to slice
-    assert rc == 0 and "tail split" not in t
+    rc, t = mm(8192, 8192)                     # 512 pair tiles = 6.92 waves: nothing to gain
+    assert rc == 0 and "stream-k" not in t and "2sm_m512" in t
+    rc, t = mm(4096, 4096)                     # 2 waves of pair tiles (1.73 needed) lose to 3.46 waves of 256x256 tiles with a head
+    assert rc == 0 and "222 whole tiles + 34 tiles in 74 k-ranges (<= 2 slabs per range)" in t and "2sm_n256" in t
+    assert f"alloc {74 * 2 * 256 * 256 * 4}" in t and "grid=(148,1,1)" in t
+    rc, t = mm(4096, 4096, dt=F32, out=F32)    # 3xTF32 (BASELINE config 2): same cut, 384 k-blocks per tile
+    assert rc == 0 and "222 whole tiles + 34 tiles in 74 k-ranges" in t
+    rc, t = mm(6144, 6144)                     # 3.89 waves of pair tiles: already 97 % full
+    assert rc == 0 and "stream-k" not in t and "2sm_m512" in t
+    rc, t = mm(1024, 8192)                     # fewer tiles than pairs: the head is the whole problem
+    assert rc == 0 and "0 whole tiles + 32 tiles in 74 k-ranges" in t and "2sm_n128" in t and "grid=(148,1,1)" in t
+    rc, t = mm(512, 16384)                     # 8 tiles, 256 k-blocks each, ~9 parts per tile
+    assert rc == 0 and "0 whole tiles + 8 tiles in 74 k-ranges" in t
+    rc, t = mm(1024, 256)                      # 4 k-blocks: too short to cut
+    assert rc == 0 and "stream-k" not in t
+    rc, t = mm(2048, 2048)                     # 64 of 74 pairs busy for one wave: an exposed exchange would cost more
+    assert rc == 0 and "stream-k" not in t
     rc, t = mm(4096, 4096, dt=8, out=4)        # u8 -> i32: exact integer accumulation stays in one CTA pair
-    assert rc == 0 and "tail split" not in t
+    assert rc == 0 and "stream-k" not in t
     plan.option("gemm.split_k", "off")
     rc, t = mm(512, 16384)
-    assert rc == 0 and "tail split" not in t
-    plan.option("gemm.split_k", "3")
-    rc, t = mm(4096, 4096, out=F32)            # (bf16 -> bf16 runs the 512 x 256 tile, which is never sliced)
-    assert rc == 0 and "34 tiles x 3 k-slices" in t
+    assert rc == 0 and "stream-k" not in t
+    plan.option("gemm.split_k", "3")           # N = ranges per tile of the head (test knob)
+    rc, t = mm(4096, 4096, out=F32)
+    assert rc == 0 and "34 tiles in 102 k-ranges" in t
+    plan.option("gemm.split_k", "on")
+    rc, t = mm(3072, 3072, out=F32)            # 1.95 waves: not worth it under auto, forced here
+    assert rc == 0 and "74 whole tiles + 70 tiles in 74 k-ranges" in t
     plan.option("gemm.split_k", "9")
     rc, t = mm(4096, 4096, out=F32)
     assert rc != 0
@@ -208,14 +217,18 @@ def test_shape_errors_match_the_reference_rule(plan):
 
 
 def test_wave_model_prefers_big_tiles(plan):
-    # 4096^3: 256 tiles of 256x256 = 4 waves on 74 CTA pairs; the 256x128 tile would be 7 half-cost waves but it is
-    # L2-bandwidth bound (measured 0.66 efficiency) -> 2sm_n256 stays for an f32 result ...
+    # 4096^3: 256 tiles of 256x256 = 3.46 waves on 74 CTA pairs (with the stream-K head); the 256x128 tile would be 6.92
+    # half-cost waves but it is smem-bandwidth bound (measured 0.66 efficiency) -> 2sm_n256 for an f32 result ...
     n = 4096
     rc, t = plan.matmul(BF16, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert "gemm_bf16_f32_2sm_n256_kn grid=(148,1,1)" in t
-    # ... and 128 tiles of 512x256 = 2 waves of twice the work at x1.06 efficiency win for a 16-bit result
+    # ... and for a 16-bit result too: 128 tiles of 512x256 would be 2 whole waves of twice the work (3.77 at x1.06) > 3.49
+    rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert "gemm_bf16_bf16_2sm_n256_kn grid=(148,1,1)" in t
+    plan.option("gemm.split_k", "off")                                     # without the head: 2 waves of pair tiles (3.77) < 4 whole waves
     rc, t = plan.matmul(BF16, BF16, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert "gemm_bf16_bf16_2sm_m512_kn grid=(148,1,1)" in t
+    plan.option("gemm.split_k", "auto")
     # 2048^2 outputs: 64 tiles of 256x256 (one wave) beat 32 tiles of 512x256 (one wave of twice the work)
     rc, t = plan.matmul(BF16, BF16, [2048, n], [n, 1], [n, 2048], [2048, 1], [2048, 2048], [2048, 1])
     assert "gemm_bf16_bf16_2sm_n256_kn grid=(128,1,1)" in t
@@ -322,11 +335,11 @@ def test_pair_tile_512_plan_has_384_threads_and_no_tail_split(plan):
     assert lines[-1] == "launch gemm_bf16_bf16_2sm_m512_kn grid=(148,1,1) block=384 smem=231424 cluster=2"
     assert 231424 <= 232448                                              # sm_100 opt-in maximum per block (227 KB)
     assert "box=(64,128) swizzle=3" in lines[0]                           # A still moves as 128-row boxes (two per stage)
-    # 4096^3 on 512 x 256 tiles: 8 x 16 = 128 tiles on 74 pairs; a partial last wave is NOT cut into K-slices for this tile
+    # 4096^3 on 512 x 256 tiles: 8 x 16 = 128 tiles on 74 pairs; a partial last wave is NOT cut into K-ranges for this tile
     plan.option("gemm.split_k", "4")
     m = 4096
     rc, t = plan.matmul(BF16, BF16, [m, m], [m, 1], [m, m], [m, 1], [m, m], [m, 1])
-    assert rc == 0 and "tail split" not in t and "grid=(148,1,1) block=384" in t
+    assert rc == 0 and "stream-k" not in t and "grid=(148,1,1) block=384" in t
     # small M: 2 tiles of 512 rows x 1 -> 2 pairs
     rc, t = plan.matmul(BF16, F32, [600, 256], [256, 1], [256, 256], [256, 1], [600, 256], [256, 1])
     assert rc == 0 and "gemm_bf16_f32_2sm_m512_kn grid=(4,1,1) block=384" in t

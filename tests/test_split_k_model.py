@@ -1,47 +1,128 @@
-"""CPU model of the GEMM's tail split (deterministic split-K): a Python transcription of `unit_decode` and of the slab /
-ticket exchange in cubecl_b200/csrc/gemm_tcgen05.cu, checked for the invariants the kernel relies on -- every (tile, k-block)
-is computed exactly once, every slice is non-empty, and the reduced tile does not depend on which slice arrives last."""
+"""CPU model of the GEMM's stream-K head (deterministic split-K of what would be a partial last wave): a Python transcription
+of `next_unit`, `sk_range_lo`, `sk_owner` and of the slab / ticket exchange in cubecl_b200/csrc/gemm_tcgen05.cu, checked for
+the invariants the kernel relies on -- every (tile, k-block) is computed exactly once, every unit is non-empty, the number of
+partial units of a tile equals the `parts` the ticket waits for, the slab a finishing CTA reads for part j is the slab the unit
+that computed part j wrote, and the reduced tile does not depend on which part arrives last."""
 import itertools
 import random
 
 import numpy as np
 
 
-def unit_decode(u, full_tiles, split_s, num_kb):
-    """-> (tile, kb0, kb1, slice, partial); same integer arithmetic as the device function."""
-    if split_s <= 1 or u < full_tiles:
-        return u, 0, num_kb, 0, False
-    v = u - full_tiles
-    tile, sl = full_tiles + v // split_s, v % split_s
-    return tile, (num_kb * sl) // split_s, (num_kb * (sl + 1)) // split_s, sl, True
+def sk_range_lo(r, sk_tiles, num_kb, ranges):
+    return (r * sk_tiles * num_kb) // ranges
 
 
-def test_units_cover_every_tile_and_k_block_once():
+def sk_owner(x, sk_tiles, num_kb, ranges):
+    return ((x + 1) * ranges - 1) // (sk_tiles * num_kb)
+
+
+def units_of_cluster(c, C, full_tiles, sk_tiles, ranges, umax, num_kb):
+    """The work-unit sequence of CTA pair c: (tile, kb0, kb1, slab, partial) -- same integer arithmetic as the device iterator."""
+    out = []
+    r = c
+    while sk_tiles and r < ranges:
+        pos, hi, u = sk_range_lo(r, sk_tiles, num_kb, ranges), sk_range_lo(r + 1, sk_tiles, num_kb, ranges), 0
+        while pos < hi:
+            tau = pos // num_kb
+            t0 = tau * num_kb
+            end = min(hi, t0 + num_kb)
+            kb0, kb1 = pos - t0, end - t0
+            out.append((full_tiles + tau, kb0, kb1, r * umax + u, not (kb0 == 0 and kb1 == num_kb)))
+            pos, u = end, u + 1
+        r += C
+    t = c
+    while t < full_tiles:
+        out.append((t, 0, num_kb, 0, False))
+        t += C
+    return out
+
+
+def host_plan(tiles, clusters, num_kb, option="auto", eligible=True):
+    """capi.cpp sk_plan -> (time, sk_tiles, ranges, umax)."""
+    full_waves, rem = divmod(tiles, clusters)
+    time = float(full_waves + (1 if rem else 0))
+    none = (time, 0, 0, 0)
+    if option == "off" or not eligible or rem == 0 or num_kb < 2:
+        return none
+    ranges, force = clusters, False
+    if option == "on":
+        force = True
+    elif option != "auto":
+        want = int(option)
+        if want == 1:
+            return none
+        ranges, force = rem * want, True
+    total_kb = rem * num_kb
+    ranges = min(ranges, total_kb)
+    if ranges <= rem and not force:
+        return none
+    share = -(-total_kb // ranges)
+    parts = max(1.0, ranges / rem)
+    head = -(-ranges // clusters) * share / num_kb
+    overhead = (4.0 if full_waves >= 1 else 14.0 + 8.0 * parts) / num_kb
+    t_sk = full_waves + head + overhead
+    if not force:
+        if share < 8 or t_sk > 0.96 * time:
+            return none
+    return (t_sk, rem, ranges, -(-share // num_kb) + 1)
+
+
+def test_units_cover_every_tile_and_k_block_once_and_parts_match_the_tickets():
     rng = random.Random(7)
-    for _ in range(300):
+    for _ in range(400):
         clusters = rng.choice([37, 74, 148])
         total_tiles = rng.randint(1, 600)
-        rem = total_tiles % clusters
-        num_kb = rng.randint(1, 400)
-        split_s = rng.randint(1, min(8, num_kb))
-        full_tiles, split_tiles = (total_tiles - rem, rem) if split_s > 1 and rem else (total_tiles, 0)
-        units = full_tiles + split_tiles * split_s if split_tiles else total_tiles
-        seen = {}
-        for u in range(units):
-            tile, kb0, kb1, sl, partial = unit_decode(u, full_tiles, split_s if split_tiles else 1, num_kb)
-            assert 0 <= kb0 < kb1 <= num_kb                      # never an empty slice (S <= num_kb is enforced on the host)
-            assert partial == (tile >= full_tiles and split_tiles > 0)
-            for kb in range(kb0, kb1):
-                assert (tile, kb) not in seen
-                seen[(tile, kb)] = u
-        assert len(seen) == total_tiles * num_kb                 # nothing skipped, nothing doubled
-        # work units are dealt round-robin to CTA pairs: whole tiles first, so the sliced units form the last round(s)
-        first_partial = next((u for u in range(units) if unit_decode(u, full_tiles, split_s if split_tiles else 1, num_kb)[4]), units)
-        assert first_partial == full_tiles
+        num_kb = rng.randint(2, 400)
+        option = rng.choice(["on", "2", "3", "4", "5", "8", "auto"])
+        _, sk_tiles, ranges, umax = host_plan(total_tiles, clusters, num_kb, option)
+        full_tiles = total_tiles - sk_tiles
+        C = min(max(full_tiles, ranges), clusters) if sk_tiles else min(total_tiles, clusters)
+        seen, partial_units, slabs = {}, {}, set()
+        for c in range(C):
+            for (tile, kb0, kb1, slab, partial) in units_of_cluster(c, C, full_tiles, sk_tiles, ranges, umax, num_kb):
+                assert 0 <= kb0 < kb1 <= num_kb                          # never an empty unit
+                for kb in range(kb0, kb1):
+                    assert (tile, kb) not in seen
+                    seen[(tile, kb)] = c
+                if partial:
+                    assert tile >= full_tiles
+                    assert slab not in slabs and slab < ranges * umax    # one slab per partial unit, inside the allocation
+                    slabs.add(slab)
+                    partial_units.setdefault(tile - full_tiles, []).append((kb0, slab))
+        assert len(seen) == total_tiles * num_kb                         # nothing skipped, nothing doubled
+        for tau, units in partial_units.items():
+            first = sk_owner(tau * num_kb, sk_tiles, num_kb, ranges)
+            parts = sk_owner((tau + 1) * num_kb - 1, sk_tiles, num_kb, ranges) - first + 1
+            assert parts == len(units) >= 2                              # the ticket waits for exactly the units that exist
+            units.sort()                                                 # k order
+            for j, (_, slab) in enumerate(units):                        # part_slab(j) in the kernel
+                r = first + j
+                u = tau - sk_range_lo(r, sk_tiles, num_kb, ranges) // num_kb
+                assert r * umax + u == slab
+        if sk_tiles:
+            assert sk_tiles * (2 if clusters <= 74 else 1) <= 1024       # tickets: one per (tile, CTA rank) in a 1024-entry area
+
+
+def test_head_runs_before_whole_tiles_on_every_pair():
+    # the partial tiles go FIRST so that their slab exchange is hidden under the whole tiles that follow
+    for tiles, clusters, num_kb in ((256, 74, 128), (128 + 17, 37, 64), (600, 148, 33)):
+        _, sk_tiles, ranges, umax = host_plan(tiles, clusters, num_kb, "on")
+        assert sk_tiles == tiles % clusters
+        full = tiles - sk_tiles
+        for c in range(clusters):
+            seq = units_of_cluster(c, clusters, full, sk_tiles, ranges, umax, num_kb)
+            kinds = [t >= full for (t, *_rest) in seq]
+            assert kinds == sorted(kinds, reverse=True)                  # all head units, then all whole tiles
+        # an even cut: no pair gets more than ceil(total / ranges) k-blocks of head work
+        share = -(-sk_tiles * num_kb // ranges)
+        for c in range(clusters):
+            head = sum(kb1 - kb0 for (t, kb0, kb1, _s, _p) in units_of_cluster(c, clusters, full, sk_tiles, ranges, umax, num_kb) if t >= full)
+            assert head <= share
 
 
 def test_slab_exchange_is_order_independent_and_resets_its_ticket():
-    # S slices publish f32 partials and take a ticket; whoever draws S - 1 adds the slabs in SLICE order and zeroes the ticket
+    # P parts publish f32 partials and take a ticket; whoever draws P - 1 adds the slabs in K order and zeroes the ticket
     rng = np.random.default_rng(3)
     order_matters = False
     for S in (2, 3, 4):
@@ -49,7 +130,7 @@ def test_slab_exchange_is_order_independent_and_resets_its_ticket():
         results = set()
         for order in itertools.permutations(range(S)):
             ticket, slabs, out = 0, {}, None
-            for sl in order:                                     # arrival order of the slices
+            for sl in order:                                     # arrival order of the parts
                 slabs[sl] = partials[sl]                         # publish (threadfence) ...
                 old, ticket = ticket, ticket + 1                 # ... then atomicAdd
                 if old == S - 1:                                 # last arriver: ordered reduction, ticket left ready for the next launch
@@ -72,23 +153,16 @@ def test_slab_exchange_is_order_independent_and_resets_its_ticket():
     assert order_matters
 
 
-def test_host_policy_formula_matches_measured_cases():
-    # time(S) = full_waves + ceil(rem * S / C) / S + (14 + 8 S) / k_blocks, split for a >= 8 % gain (capi.cpp launch_tcgen05)
-    def choose(total_tiles, clusters, num_kb):
-        rem, full = total_tiles % clusters, total_tiles // clusters
-        if rem == 0:
-            return 1
-        base = best = full + 1.0
-        pick = 1
-        for s in range(2, 5):
-            if num_kb // s < 8:
-                break
-            t = full + -(-rem * s // clusters) / s + (14.0 + 8.0 * s) / num_kb
-            if t < best - 1e-9:
-                best, pick = t, s
-        return pick if base - best >= 0.08 * base else 1
-    assert choose(1024, 74, 128) == 1      # bf16 8192^3: tail 84 % full
-    assert choose(256, 74, 64) == 1        # bf16 4096^3: the slab exchange eats the gain
-    assert choose(256, 74, 384) == 2       # 3xTF32 4096^3: 384 k-blocks per tile
-    assert choose(8, 74, 256) == 4         # 512^2 x 16384 on 256x128 tiles
-    assert choose(32, 74, 128) == 2        # 1024^2 x 8192
+def test_host_policy_on_the_baseline_shapes():
+    # (tiles, CTA pairs, k-blocks per tile) -> is the last partial wave turned into a stream-K head?
+    def head(tiles, clusters, num_kb):
+        return host_plan(tiles, clusters, num_kb)[1]
+    assert head(1024, 74, 128) == 0      # bf16 8192^3 on 256x256 tiles: 13.84 waves, nothing to gain
+    assert head(256, 74, 128) == 34      # tf32 4096^3: 3.46 waves instead of 4 (BASELINE config 2)
+    assert head(256, 74, 384) == 34      # 3xTF32 4096^3
+    assert head(256, 74, 64) == 34       # bf16 4096^3 on 256x256 tiles
+    assert head(8, 74, 256) == 8         # 512^2 x 16384: the head is the whole problem (exposed exchange still pays: 9 parts)
+    assert head(4, 74, 8) == 0           # tiny K: slices would be thinner than 8 k-blocks
+    assert head(74, 74, 128) == 0        # exactly one wave
+    t_with, *_ = host_plan(256, 74, 128)
+    assert abs(t_with - (3 + 34 / 74 + 4.0 / 128)) < 0.02

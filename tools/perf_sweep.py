@@ -58,6 +58,17 @@ if "reduce" in what:
         ms = min(time_ms(c, run) for _ in range(3))
         rows.append((ms, variant, threads, bps))
         print(f"  {variant:4s} threads={threads:4d} blocks/SM={bps}: {ms * 1e3:8.1f} us  {n * 4 / ms / 1e6:8.1f} GB/s   ({c.last_kernel()})", flush=True)
+    c.set_option("reduce.variant", "tma")
+    for stages, per_sm in ((8, 1), (6, 1), (6, 2), (4, 2), (4, 1)):
+        c.set_option("reduce.tma_stages", stages)
+        c.set_option("reduce.tma_ctas_per_sm", per_sm)
+        for pdl in ("on", "off"):
+            c.set_option("reduce.pdl", pdl)
+            ms = min(time_ms(c, run) for _ in range(3))
+            print(f"  tma  stages={stages} CTAs/SM={per_sm} pdl={pdl:3s}: {ms * 1e3:8.1f} us  {n * 4 / ms / 1e6:8.1f} GB/s", flush=True)
+    c.set_option("reduce.pdl", "on")
+    c.set_option("reduce.tma_stages", 8)
+    c.set_option("reduce.tma_ctas_per_sm", 1)
     c.set_option("reduce.variant", "auto")
     c.set_option("reduce.threads", 512)
     c.set_option("reduce.blocks_per_sm", 4)
