@@ -58,7 +58,8 @@ struct SimtGemmParams {
   uint32_t in_dtype, out_dtype;  // b200_dtype: 0 f32, 1 f16, 2 bf16; inputs also 10 fp8 e4m3, 11 fp8 e5m2
   uint64_t bias;                 // fused epilogue, same meaning as GemmParams
   float alpha;
-  uint32_t epi_act, epi_on, pad;
+  uint32_t epi_act, epi_on;
+  uint32_t b_dtype_p1;           // rhs dtype + 1 when it differs from in_dtype (mixed fp8 / int8 pairs), 0 = same as lhs
 };
 
 __device__ __forceinline__ float load_as_f32(uint64_t base, uint64_t idx, uint32_t dt) {
@@ -82,8 +83,11 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
   __shared__ float sa[16][17];
   __shared__ float sb[16][17];
   const uint32_t tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const uint32_t m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx, bz = blockIdx.z;
+  const uint32_t n = blockIdx.x * 16 + tx, bz = blockIdx.z;
   const bool integer = (p.in_dtype == 8 || p.in_dtype == 9);  // u8 / i8 -> exact s32 accumulation
+  // 16-row tiles of M are walked with a stride of gridDim.y (the y extent of a grid stops at 65535)
+  for (uint64_t mt = blockIdx.y; mt * 16 < p.M; mt += gridDim.y) {
+  const uint32_t m = static_cast<uint32_t>(mt * 16) + ty;
   float acc = 0.f;
   int iacc = 0;
   for (uint32_t k0 = 0; k0 < p.K; k0 += 16) {
@@ -91,12 +95,13 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
     const bool va = (m < p.M && ka < p.K), vb = (kb < p.K && n < p.N);
     const uint64_t ia = bz * p.a_sb + static_cast<uint64_t>(m) * p.a_sm + static_cast<uint64_t>(ka) * p.a_sk;
     const uint64_t ib = bz * p.b_sb + static_cast<uint64_t>(kb) * p.b_sk + static_cast<uint64_t>(n) * p.b_sn;
+    const uint32_t b_dt = p.b_dtype_p1 ? p.b_dtype_p1 - 1 : p.in_dtype;
     if (integer) {  // 8-bit integers are exact in f32, so the staging tiles stay float
       sa[ty][tx] = va ? static_cast<float>(load_as_i32(p.a, ia, p.in_dtype)) : 0.f;
-      sb[ty][tx] = vb ? static_cast<float>(load_as_i32(p.b, ib, p.in_dtype)) : 0.f;
+      sb[ty][tx] = vb ? static_cast<float>(load_as_i32(p.b, ib, b_dt)) : 0.f;
     } else {
       sa[ty][tx] = va ? load_as_f32(p.a, ia, p.in_dtype) : 0.f;
-      sb[ty][tx] = vb ? load_as_f32(p.b, ib, p.in_dtype) : 0.f;
+      sb[ty][tx] = vb ? load_as_f32(p.b, ib, b_dt) : 0.f;
     }
     __syncthreads();
     const uint32_t kmax = min(16u, p.K - k0);
@@ -121,6 +126,7 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
       store_from_f32(p.out, io, p.out_dtype, acc);
     }
   }
+  }  // m tiles
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -319,5 +325,45 @@ extern "C" __global__ void __launch_bounds__(256) gather_strided(const __grid_co
     else if (p.esz == 2) reinterpret_cast<uint16_t*>(p.out)[i] = reinterpret_cast<const uint16_t*>(p.in)[off];
     else if (p.esz == 8) reinterpret_cast<uint64_t*>(p.out)[i] = reinterpret_cast<const uint64_t*>(p.in)[off];
     else reinterpret_cast<uint8_t*>(p.out)[i] = reinterpret_cast<const uint8_t*>(p.in)[off];
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ operand staging
+// Copy a strided [batch, rows, cols] operand into a pitched buffer TMA can describe (pitch a multiple of 16 bytes): one
+// 16-byte output vector per thread, gathered element by element from the (possibly misaligned) input rows.  Only in front
+// of the tensor-core GEMM for operands whose own pitch / base is not 16-byte aligned (bf16 with K = 4097, odd sub-views).
+struct RepitchParams {
+  uint64_t in, out;
+  uint64_t batch, rows, cols;
+  uint64_t in_sb, in_sr, in_sc;
+  uint64_t out_pitch;
+  uint32_t esz, pad;
+};
+extern "C" __global__ void __launch_bounds__(256) repitch_rows(const __grid_constant__ RepitchParams p) {
+  const uint32_t per = 16 / p.esz;                       // elements per output vector
+  const uint64_t vpr = p.out_pitch / per;                // vectors per output row
+  const uint64_t total = p.batch * p.rows * vpr;
+  for (uint64_t v = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+       v += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t row = v / vpr, cv = v - row * vpr;
+    const uint64_t b = row / p.rows, r = row - b * p.rows;
+    const uint64_t c0 = cv * per;
+    const uint64_t src = b * p.in_sb + r * p.in_sr;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};                    // padding columns are written as zeros (TMA never reads them anyway)
+    if (p.esz == 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + j < p.cols) w[j] = reinterpret_cast<const uint32_t*>(p.in)[src + (c0 + j) * p.in_sc];
+    } else if (p.esz == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < p.cols) w[j >> 1] |= static_cast<uint32_t>(reinterpret_cast<const uint16_t*>(p.in)[src + (c0 + j) * p.in_sc]) << (16 * (j & 1));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 + j < p.cols) w[j >> 2] |= static_cast<uint32_t>(reinterpret_cast<const uint8_t*>(p.in)[src + (c0 + j) * p.in_sc]) << (8 * (j & 3));
+    }
+    reinterpret_cast<uint4*>(p.out)[row * vpr + cv] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }

@@ -216,8 +216,8 @@ struct GemmParams {
   uint32_t epi_on;
   uint32_t full_tiles, sk_tiles, sk_ranges, sk_umax;  // stream-K head, see gemm_tcgen05.cu
   uint64_t split_ws, split_tickets;
-  uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;  // block-scaled kinds
-  uint32_t tma_store, pad1;
+  uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;  // block-scaled kinds; operand formats of a mixed 8-bit pair
+  uint32_t tma_store, fmt_mixed;
 };
 struct PackScalesParams {
   uint64_t in, out;
@@ -254,7 +254,7 @@ struct SimtGemmParams {
   uint32_t M, N, K, batch, in_dtype, out_dtype;
   uint64_t bias;
   float alpha;
-  uint32_t epi_act, epi_on, pad;
+  uint32_t epi_act, epi_on, b_dtype_p1;
 };
 struct SplitParams {
   uint64_t in, out, batch, rows, cols, in_bs, in_rs, out_rs;
@@ -523,7 +523,7 @@ extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
 
 extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
-  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "reduce.variant", "reduce.threads",
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "gemm.stage", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm", "reduce.rows_vpt", "reduce.rows_blocks_per_sm", "reduce.cols_blocks_per_sm",
                                 "reduce.debug", "reduce.pdl", "reduce.tma_stages", "reduce.tma_ctas_per_sm"};
   for (const char* k : known)
@@ -899,6 +899,7 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
 // One batched problem with LINEAR batch strides (0 = broadcast).  Strides in elements.
 struct GemmProblem {
   int in_dtype, out_dtype;
+  int rhs_dtype = -1;           // >= 0: a mixed 8-bit pair (fp8 e4m3 x e5m2, u8 x i8); in_dtype is then the lhs format
   uint64_t a, b, out;
   uint64_t a_lo = 0, b_lo = 0;  // 3xTF32: compact low parts (same logical layout class as a / b), 0 otherwise
   uint64_t bias = 0;            // fused epilogue: out = act(alpha * acc + bias[n])
@@ -920,32 +921,37 @@ static int launch_simt(b200_ctx* c, CUstream st, const GemmProblem& g) {
   int rc = get_func(c, "gemm_simt_strided", &f);
   if (rc) return rc;
   if (g.batch > 65535) return fail(B200_ERR_UNSUPPORTED, "simt matmul: batch %llu > 65535", (unsigned long long)g.batch);
+  if (g.M >= (1ull << 32) || g.N >= (1ull << 32) || g.K >= (1ull << 32))
+    return fail(B200_ERR_UNSUPPORTED, "simt matmul: extents must fit 32 bits (M=%llu N=%llu K=%llu)", (unsigned long long)g.M,
+                (unsigned long long)g.N, (unsigned long long)g.K);
   const uint32_t epi_on = (g.alpha != 1.0f || g.bias != 0 || g.act != 0) ? 1u : 0u;
   SimtGemmParams p{g.a, g.b, g.out, g.a_sb, g.a_sm, g.a_sk, g.b_sb, g.b_sk, g.b_sn, g.o_sb, g.o_sm, g.o_sn,
                    (uint32_t)g.M, (uint32_t)g.N, (uint32_t)g.K, (uint32_t)g.batch, (uint32_t)g.in_dtype, (uint32_t)g.out_dtype,
-                   g.bias, g.alpha, g.act, epi_on, 0};
+                   g.bias, g.alpha, g.act, epi_on, g.rhs_dtype >= 0 ? (uint32_t)g.rhs_dtype + 1u : 0u};
   void* args[] = {&p};
-  return launch(c, f, (unsigned)((g.N + 15) / 16), (unsigned)((g.M + 15) / 16), (unsigned)g.batch, 256, 0, 1, st, args);
+  // gridDim.y is limited to 65535: taller problems (M > 1,048,560) walk their 16-row tiles with a stride of gridDim.y
+  const uint64_t tiles_m = (g.M + 15) / 16;
+  return launch(c, f, (unsigned)((g.N + 15) / 16), (unsigned)std::min<uint64_t>(tiles_m, 65535), (unsigned)g.batch, 256, 0, 1, st, args);
 }
 
+// Can TMA describe one operand in place?  `mn` x K elements, strides in elements.  K-major (rows of K) or MN-major (rows of
+// the M / N extent): unit inner stride, 16-byte aligned base, row pitch and batch stride, pitch >= row, strides < 2^40 bytes.
+static bool operand_tma_ok(uint64_t ptr, size_t esz, uint64_t mn, uint64_t K, uint64_t s_mn, uint64_t s_k, uint64_t s_b, bool* mn_major) {
+  auto al16 = [&](uint64_t elems) { return (elems * esz) % 16 == 0; };
+  const uint64_t lim = 1ull << 40;
+  if (ptr % 16 || !al16(s_b)) return false;
+  if (s_mn * esz >= lim || s_k * esz >= lim || s_b * esz >= lim) return false;
+  if ((s_k == 1 || K == 1) && (mn == 1 || (al16(s_mn) && s_mn >= K))) { *mn_major = false; return true; }
+  if ((s_mn == 1 || mn == 1) && (K == 1 || (al16(s_k) && s_k >= mn))) { *mn_major = true; return true; }
+  return false;
+}
+static bool extents_tma_ok(const GemmProblem& g) {
+  return g.M < (1ull << 31) && g.N < (1ull << 31) && g.K < (1ull << 31) && g.batch < (1ull << 31) && (g.o_sn == 1 || g.N == 1);
+}
 static bool tma_ok(const GemmProblem& g, bool* a_mn, bool* b_mn) {
   const size_t esz = dtype_size(g.in_dtype);
-  auto al16 = [&](uint64_t elems) { return (elems * esz) % 16 == 0; };
-  if (g.M >= (1ull << 31) || g.N >= (1ull << 31) || g.K >= (1ull << 31) || g.batch >= (1ull << 31)) return false;
-  if (g.a % 16 || !al16(g.a_sb) || g.b % 16 || !al16(g.b_sb)) return false;
-  // lhs: K-major ([M,K] rows) or MN-major ([K,M] rows, i.e. a transposed view)
-  if ((g.a_sk == 1 || g.K == 1) && (g.M == 1 || (al16(g.a_sm) && g.a_sm >= g.K))) { *a_mn = false; }
-  else if ((g.a_sm == 1 || g.M == 1) && (g.K == 1 || (al16(g.a_sk) && g.a_sk >= g.M))) { *a_mn = true; }
-  else return false;
-  // rhs: K-major ([N,K] rows, transposed view) or MN-major ([K,N] rows)
-  if ((g.b_sk == 1 || g.K == 1) && (g.N == 1 || (al16(g.b_sn) && g.b_sn >= g.K))) { *b_mn = false; }
-  else if ((g.b_sn == 1 || g.N == 1) && (g.K == 1 || (al16(g.b_sk) && g.b_sk >= g.N))) { *b_mn = true; }
-  else return false;
-  if (!(g.o_sn == 1 || g.N == 1)) return false;
-  // TMA stride limit 2^40 bytes; a dimension of extent 1 gets a substituted 16-byte-multiple stride in encode
-  const uint64_t lim = 1ull << 40;
-  if (g.a_sm * esz >= lim || g.a_sk * esz >= lim || g.a_sb * esz >= lim || g.b_sk * esz >= lim || g.b_sn * esz >= lim || g.b_sb * esz >= lim) return false;
-  return true;
+  return extents_tma_ok(g) && operand_tma_ok(g.a, esz, g.M, g.K, g.a_sm, g.a_sk, g.a_sb, a_mn) &&
+         operand_tma_ok(g.b, esz, g.N, g.K, g.b_sn, g.b_sk, g.b_sb, b_mn);
 }
 
 static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out);
@@ -953,9 +959,14 @@ static int reduce_workspace(b200_ctx* c, CUstream st, CUdeviceptr* out);
 // Stream-K head plan for `tiles` tiles on `clusters` CTA pairs (gemm_tcgen05.cu, GemmParams): the rem = tiles % clusters
 // tiles that would form a partial last wave are instead cut along K into `ranges` equal ranges processed FIRST, so all
 // pairs stay busy and the slab exchange runs under the whole tiles that follow.
-//   time (in tile-times) without: full_waves + 1.   with: full_waves + rem / clusters + overhead / num_kb, where the overhead
-//   (in k-block times) is small when whole tiles follow (slab store + ticket, hidden: ~4) and (14 + 8 parts) when the head
-//   is the whole problem (measured round 1: publishing, the ticket round trip and the ordered re-read are exposed).
+//   time (in tile-times) without: full_waves + 1.
+//   with: full_waves + 1.4 * head + overhead / num_kb, head = ceil(ranges / clusters) * share / num_kb.
+// Measured (profiles/r02_split_sweep.log): while the head runs, S pairs stream the operands of ONE tile, so the phase needs
+// S times the operand bandwidth of a normal wave with less panel sharing in L2 -- it runs ~1.4x longer than its MMA time
+// (bf16 4096^3: 92.0 us with S = 2 against 94.6 us for two waves of pair tiles; tf32 4096^3: 179 against 186 us).  Equal
+// parts (ranges = rem * S) beat the even cut over all pairs whenever they fit (fp8 4096^3: 54.6 against 72.3 us), so S =
+// floor(clusters / rem) when that is >= 2.  The exchange itself is hidden when whole tiles follow (~4 k-block times) and
+// exposed, (14 + 8 parts) k-block times, when the head is the whole problem (round 1 measurement).
 // gemm.split_k: auto (only when the model gains >= 4 %), off, on (whenever rem != 0), or N = 1..8 (N ranges per tile).
 struct SkPlan {
   double time = 0;           // modelled time in tile-times
@@ -967,24 +978,41 @@ static SkPlan sk_plan(uint64_t tiles, uint64_t clusters, uint64_t num_kb, const 
   const uint64_t full_waves = tiles / clusters, rem = tiles % clusters;
   pl.time = static_cast<double>(full_waves + (rem ? 1 : 0));
   if (option == "off" || !eligible || rem == 0 || num_kb < 2) return pl;
-  uint64_t ranges = clusters;
-  bool force = false;
-  if (option == "on") force = true;
-  else if (option != "auto") {
+  const uint64_t total_kb = rem * num_kb;
+  auto model = [&](uint64_t ranges, bool even_parts) {
+    const uint64_t share = (total_kb + ranges - 1) / ranges;
+    const double parts = std::max(1.0, static_cast<double>(ranges) / static_cast<double>(rem));
+    const double head = static_cast<double>((ranges + clusters - 1) / clusters) * static_cast<double>(share) / static_cast<double>(num_kb);
+    const double overhead = (full_waves >= 1 ? 4.0 : 14.0 + 8.0 * parts) / static_cast<double>(num_kb);
+    return static_cast<double>(full_waves) + (even_parts ? 1.4 : 1.6) * head + overhead;
+  };
+  uint64_t ranges = 0;
+  bool force = false, even = true;
+  if (option == "auto" || option == "on") {
+    force = (option == "on");
+    const uint64_t s_fit = std::min<uint64_t>(clusters / rem, 8);
+    if (s_fit >= 2) {
+      // equal parts; when whole tiles follow, as many as fit; when the head is everything, the S the model likes best
+      uint64_t best_s = s_fit;
+      if (full_waves == 0)
+        for (uint64_t s2 = 2; s2 <= s_fit; ++s2)
+          if (num_kb / s2 >= 8 && model(rem * s2, true) < model(rem * best_s, true) - 1e-12) best_s = s2;
+      ranges = rem * best_s;
+    } else {
+      ranges = clusters;       // more than half a wave of tiles: an even cut over all pairs, tiles in 1-2 uneven parts
+      even = false;
+    }
+  } else {
     const int want = atoi(option.c_str());
     if (want < 1 || want > 8) { pl.bad_option = true; return pl; }
     if (want == 1) return pl;
     ranges = rem * static_cast<uint64_t>(want);
     force = true;
   }
-  const uint64_t total_kb = rem * num_kb;
   ranges = std::min(ranges, total_kb);                                    // every range owns at least one k-block
   if (ranges <= rem && !force) return pl;                                 // no tile would be cut
   const uint64_t share = (total_kb + ranges - 1) / ranges;
-  const double parts = std::max(1.0, static_cast<double>(ranges) / static_cast<double>(rem));
-  const double head = static_cast<double>((ranges + clusters - 1) / clusters) * static_cast<double>(share) / static_cast<double>(num_kb);
-  const double overhead = (full_waves >= 1 ? 4.0 : 14.0 + 8.0 * parts) / static_cast<double>(num_kb);
-  const double t_sk = static_cast<double>(full_waves) + head + overhead;
+  const double t_sk = model(ranges, even);
   if (!force) {
     if (share < 8) return pl;                                             // slices too thin to amortise an exchange
     if (t_sk > 0.96 * pl.time) return pl;
@@ -1100,6 +1128,10 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }
+  if (!g.mx_kind && g.rhs_dtype >= 0 && g.rhs_dtype != g.in_dtype) {
+    auto fmt8 = [](int dt) { return (dt == B200_F8E5M2 || dt == B200_I8) ? 1u : 0u; };   // kind::f8f6f4: e4m3 0 / e5m2 1; kind::i8: u8 0 / s8 1
+    p.sf_fmt_a = fmt8(g.in_dtype); p.sf_fmt_b = fmt8(g.rhs_dtype); p.fmt_mixed = 1;
+  }
   p.k_segments = (uint32_t)k_segments;
   p.alpha = g.alpha; p.bias = g.bias; p.epi_act = g.act;
   p.epi_on = (g.alpha != 1.0f || g.bias != 0 || g.act != 0) ? 1u : 0u;
@@ -1178,6 +1210,43 @@ static int launch_split(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uin
   return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
 }
 
+struct RepitchParams {
+  uint64_t in, out;
+  uint64_t batch, rows, cols;        // logical [batch, rows, cols] of the copy, cols innermost in the OUTPUT
+  uint64_t in_sb, in_sr, in_sc;      // input strides in elements
+  uint64_t out_pitch;                // output row pitch in elements (16-byte multiple)
+  uint32_t esz, pad;
+};
+
+// One pass that copies an operand TMA cannot describe (row pitch or base not 16-byte aligned, no unit stride) into a pooled
+// buffer it can: [batch, rows, pitch] with the operand's own contiguous dimension innermost when it has one.
+static int stage_operand(b200_ctx* c, CUstream st, size_t esz, uint64_t ptr, uint64_t batch, uint64_t mn, uint64_t K, uint64_t s_mn, uint64_t s_k,
+                         uint64_t s_b, CUdeviceptr* out, uint64_t* o_smn, uint64_t* o_sk, uint64_t* o_sb) {
+  const bool keep_mn_major = (s_mn == 1 && s_k != 1);          // rows of the M / N extent: keep them (coalesced both ways)
+  const uint64_t rows = keep_mn_major ? K : mn, cols = keep_mn_major ? mn : K;
+  const uint64_t q = 16 / esz, pitch = (cols + q - 1) / q * q;
+  const uint64_t nb = (s_b == 0) ? 1 : batch;                  // a broadcast operand is staged once
+  CUdeviceptr buf;
+  int rc = pool_alloc(c, nb * rows * pitch * esz, &buf, st);
+  if (rc) return rc;
+  CUfunction f;
+  rc = get_func(c, "repitch_rows", &f);
+  if (rc) { pool_free(c, buf, st); return rc; }
+  RepitchParams p{ptr, buf, nb, rows, cols, s_b, keep_mn_major ? s_k : s_mn, keep_mn_major ? s_mn : s_k, pitch, (uint32_t)esz, 0};
+  const uint64_t vecs = nb * rows * (pitch / q);               // one 16-byte output vector per thread
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((vecs + 255) / 256, 0x7FFFFFFFull));
+  void* args[] = {&p};
+  rc = launch(c, f, grid, 1, 1, 256, 0, 1, st, args);
+  if (rc) { pool_free(c, buf, st); return rc; }
+  *out = buf;
+  *o_smn = keep_mn_major ? 1 : pitch;
+  *o_sk = keep_mn_major ? pitch : 1;
+  *o_sb = (s_b == 0) ? 0 : rows * pitch;
+  return B200_OK;
+}
+
+static int run_gemm_staged(b200_ctx* c, CUstream st, const GemmProblem& g);
+
 static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
   if (g.M == 0 || g.N == 0 || g.batch == 0) return B200_OK;
   const std::string forced = opt(c, "gemm.variant", "auto");
@@ -1186,6 +1255,11 @@ static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
   if (forced == "simt" || !tma) {
     if (forced != "simt" && forced != "auto")
       return fail(B200_ERR_UNSUPPORTED, "gemm.variant=%s forced but operands are not TMA-describable", forced.c_str());
+    // Operands whose pitch / base TMA cannot describe (bf16 with K = 4097, an odd sub-view): one staging pass into an
+    // aligned pooled copy, then the tensor-core kernel -- the strided SIMT kernel is kept for tiny problems and for
+    // outputs without a unit inner stride.  gemm.stage=off keeps the SIMT path (reference-order arithmetic) for everything.
+    const bool big = g.M * g.N * g.K * g.batch >= (1ull << 21);
+    if (forced == "auto" && g.K > 0 && big && extents_tma_ok(g) && opt(c, "gemm.stage", "on") == "on") return run_gemm_staged(c, st, g);
     return launch_simt(c, st, g);
   }
   if (g.in_dtype == B200_F32 && opt(c, "gemm.f32", "3xtf32") == "3xtf32") {
@@ -1213,6 +1287,29 @@ static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
     return rc;
   }
   return launch_tcgen05(c, st, g, a_mn, b_mn);
+}
+
+static int run_gemm_staged(b200_ctx* c, CUstream st, const GemmProblem& g) {
+  const size_t esz = dtype_size(g.in_dtype);
+  GemmProblem h = g;
+  CUdeviceptr sa = 0, sb = 0;
+  bool mn;
+  int rc = B200_OK;
+  if (!operand_tma_ok(g.a, esz, g.M, g.K, g.a_sm, g.a_sk, g.a_sb, &mn)) {
+    rc = stage_operand(c, st, esz, g.a, g.batch, g.M, g.K, g.a_sm, g.a_sk, g.a_sb, &sa, &h.a_sm, &h.a_sk, &h.a_sb);
+    if (!rc) h.a = sa;
+  }
+  if (!rc && !operand_tma_ok(g.b, esz, g.N, g.K, g.b_sn, g.b_sk, g.b_sb, &mn)) {
+    rc = stage_operand(c, st, esz, g.b, g.batch, g.N, g.K, g.b_sn, g.b_sk, g.b_sb, &sb, &h.b_sn, &h.b_sk, &h.b_sb);
+    if (!rc) h.b = sb;
+  }
+  if (!rc) {
+    bool a_mn = false, b_mn = false;
+    rc = tma_ok(h, &a_mn, &b_mn) ? run_gemm(c, st, h) : launch_simt(c, st, g);
+  }
+  if (sa) pool_free(c, sa, st);
+  if (sb) pool_free(c, sb, st);
+  return rc;
 }
 
 // Collapse batch dims [0, nb) of one operand into a linear stride; false if the offsets are not linear in the flat index.
@@ -1258,7 +1355,7 @@ static int matmul_rec(b200_ctx* c, CUstream st, GemmProblem g, int nb, const uin
 static int matmul_impl(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
                        b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
                        const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
-                       const uint64_t* strides_out, const b200_epilogue* ep);
+                       const uint64_t* strides_out, const b200_epilogue* ep, int rhs_dtype = -1);
 
 extern "C" int b200_matmul(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
                            b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
@@ -1364,10 +1461,25 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
   return rc;
 }
 
+// Mixed 8-bit operand formats (the cartesian products the reference instantiates for its manual MMA,
+// crates/cubecl-cpp/src/cuda/mma/manual.rs:151-166 i8 x u8 / u8 x i8 and :170-186 fp8 pairs): same kernels, the two format
+// fields of the tcgen05 instruction descriptor differ.
+extern "C" int b200_matmul_mixed(b200_ctx* c, b200_stream s, b200_dtype lhs_dtype, b200_dtype rhs_dtype, b200_dtype out_dtype, b200_dptr lhs,
+                                 b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                                 const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
+                                 const uint64_t* strides_out) {
+  auto fp8 = [](int d) { return d == B200_F8E4M3 || d == B200_F8E5M2; };
+  auto int8 = [](int d) { return d == B200_U8 || d == B200_I8; };
+  if (lhs_dtype != rhs_dtype && !((fp8(lhs_dtype) && fp8(rhs_dtype)) || (int8(lhs_dtype) && int8(rhs_dtype))))
+    return fail(B200_ERR_UNSUPPORTED, "matmul_mixed: operand formats %d x %d cannot be mixed (fp8 e4m3/e5m2 pairs, u8/i8 pairs)", (int)lhs_dtype, (int)rhs_dtype);
+  return matmul_impl(c, s, lhs_dtype, out_dtype, lhs, rhs, out, rank, shape_lhs, strides_lhs, shape_rhs, strides_rhs, shape_out,
+                     strides_out, nullptr, lhs_dtype == rhs_dtype ? -1 : (int)rhs_dtype);
+}
+
 static int matmul_impl(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype, b200_dptr lhs,
                        b200_dptr rhs, b200_dptr out, int rank, const uint64_t* shape_lhs, const uint64_t* strides_lhs,
                        const uint64_t* shape_rhs, const uint64_t* strides_rhs, const uint64_t* shape_out,
-                       const uint64_t* strides_out, const b200_epilogue* ep) {
+                       const uint64_t* strides_out, const b200_epilogue* ep, int rhs_dtype) {
   CTX_ENTER(c);
   if (rank < 2 || rank > 8) return fail(B200_ERR_INVALID_ARG, "matmul: rank %d unsupported (need 2..8)", rank);
   if (!shape_lhs || !strides_lhs || !shape_rhs || !strides_rhs || !shape_out || !strides_out)
@@ -1401,7 +1513,7 @@ static int matmul_impl(b200_ctx* c, b200_stream s, b200_dtype in_dtype, b200_dty
   }
   CUstream st = resolve_stream(c, s);
   GemmProblem g{};
-  g.in_dtype = in_dtype; g.out_dtype = out_dtype;
+  g.in_dtype = in_dtype; g.out_dtype = out_dtype; g.rhs_dtype = rhs_dtype;
   g.a = lhs; g.b = rhs; g.out = out;
   g.M = M; g.N = N; g.K = K; g.batch = 1;
   g.a_sm = strides_lhs[rank - 2]; g.a_sk = strides_lhs[rank - 1];
@@ -1490,7 +1602,7 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RVi
   if (bulk) {
     name += "_tma";
     threads = 256 + 32;                       // eight consumer warps + one producer warp
-    stages = opt_uint(c, "reduce.tma_stages", 8, 2, 8);
+    stages = opt_uint(c, "reduce.tma_stages", 6, 2, 8);   // measured: 6 x 16 KB 145.4 us, 8 x 16 KB 147.3 us, 4 x 16 KB 150.0 us (1 GiB f32)
     smem = stages * 16384 + 128;
     const uint64_t tiles = n * esz / 16384;
     const unsigned per_sm = stages <= 6 ? opt_uint(c, "reduce.tma_ctas_per_sm", 1, 1, 2) : 1;

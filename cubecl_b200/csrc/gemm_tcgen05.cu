@@ -43,10 +43,12 @@ struct GemmParams {
   uint64_t split_tickets;     // u32 [sk_tiles][CG], zero on entry, left zero on exit
   // Block-scaled kinds (KIND_MXF8 / KIND_MXF4): operand formats for the instruction descriptor and the number of 128-row
   // scale-factor tiles per batch entry of each operand (the packed scale tensors are [batch * tiles][k atoms][512 B]).
+  // 8-bit unscaled kinds: sf_fmt_a / sf_fmt_b also carry the operand formats of a MIXED pair (e4m3 x e5m2, u8 x s8 ...,
+  // the reference's manual-MMA cartesian products, crates/cubecl-cpp/src/cuda/mma/manual.rs:151-186) when fmt_mixed != 0.
   uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;
   // 1: whole tiles leave through shared memory and TMA stores (tma_out describes `out` as (N, M, batch)); needs a 16-byte
   // aligned base and row / batch pitches.  0: each thread stores its own row directly.
-  uint32_t tma_store, pad1;
+  uint32_t tma_store, fmt_mixed;
 };
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6,
@@ -233,7 +235,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   static_assert(TMEM_NEED <= 512, "accumulator stages + scale factors must fit TMEM");
   constexpr uint32_t SFA_COL = ACC_COLS, SFB_COL = ACC_COLS + 4u * SF_ATOMS;
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024-byte alignment for SWIZZLE_128B");
-  constexpr uint32_t IDESC = make_idesc(FMT, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N, C_FMT);  // unscaled kinds
+  constexpr uint32_t IDESC_SAME = make_idesc(FMT, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N, C_FMT);  // unscaled kinds
+  // the operand formats are separate fields of the instruction descriptor: a mixed 8-bit pair only changes this word
+  const uint32_t IDESC = (ESZ == 1 && !SCALED && p.fmt_mixed)
+                             ? make_idesc_ab(p.sf_fmt_a, p.sf_fmt_b, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N, C_FMT) : IDESC_SAME;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;

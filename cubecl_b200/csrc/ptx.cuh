@@ -356,4 +356,9 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t a_mn, u
          | ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
 }
 
+__host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t fmt_a, uint32_t fmt_b, uint32_t a_mn, uint32_t b_mn, uint32_t umma_m,
+                                                     uint32_t umma_n, uint32_t c_fmt) {
+  return (c_fmt << 4) | (fmt_a << 7) | (fmt_b << 10) | (a_mn << 15) | (b_mn << 16) | ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
+}
+
 }  // namespace b200

@@ -53,11 +53,17 @@ def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: Ten
     if alpha != 1.0 or bias is not None or activation not in (None, "none"):
         return _launch_fused(client, lhs, rhs, out, stream, alpha, bias, activation)
     try:
-        if lhs.dtype != rhs.dtype:
-            raise B200Error(6, f"lhs dtype {lhs.dtype} != rhs dtype {rhs.dtype}")
         rank = len(lhs.shape)
         if len(rhs.shape) != rank or len(out.shape) != rank:
             raise B200Error(6, "matmul: lhs, rhs and out must have equal rank")
+        if lhs.dtype != rhs.dtype:
+            # mixed 8-bit formats (the reference's manual-MMA pairs: i8 x u8, e4m3 x e5m2 ...); anything else is refused by the library
+            _ffi.check(client._lib.b200_matmul_mixed(
+                client._ctx, stream, DTYPES[lhs.dtype], DTYPES[rhs.dtype], DTYPES[out.dtype],
+                C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(out.handle.ptr), rank,
+                _ffi.u64_array(lhs.shape), _ffi.u64_array(lhs.strides), _ffi.u64_array(rhs.shape), _ffi.u64_array(rhs.strides),
+                _ffi.u64_array(out.shape), _ffi.u64_array(out.strides)))
+            return
         _ffi.check(client._lib.b200_matmul(
             client._ctx, stream, DTYPES[lhs.dtype], DTYPES[out.dtype],
             C.c_uint64(lhs.handle.ptr), C.c_uint64(rhs.handle.ptr), C.c_uint64(out.handle.ptr), rank,

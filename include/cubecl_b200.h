@@ -96,7 +96,10 @@ int b200_plan_begin(int num_sms, b200_ctx** out);
 int b200_plan_text(b200_ctx* ctx, char* buf, size_t capacity, size_t* needed);
 /* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
  * (auto|2sm_m512|2sm_n256|2sm_n128|1sm_n128|simt; 2sm_n256a1 = single-accumulator diagnostic), "gemm.f32" (3xtf32|tf32), "gemm.group_m",
- * "gemm.l2_promotion" (256|128|64|0: TMA L2 promotion bytes of the operand tensor maps), "gemm.split_k" (auto|off|1..8: deterministic K-split of the last partial wave), "gemm.epilogue" (tma|direct), "reduce.variant"
+ * "gemm.l2_promotion" (256|128|64|0: TMA L2 promotion bytes of the operand tensor maps), "gemm.split_k" (auto|off|on|1..8:
+ * deterministic stream-K head -- the tiles of a partial last wave are cut along K into equal ranges that run FIRST, slabs
+ * added in k order; N = ranges per tile), "gemm.epilogue" (tma|direct), "gemm.stage" (on|off: operands TMA cannot describe --
+ * unaligned row pitch / base -- are first copied into an aligned pooled buffer and run on the tensor cores; off = strided SIMT kernel), "reduce.variant"
  * (auto|u2|u4|u8|u16|b4|b8|w2|w4: load-unroll / blocked / 256-bit forms of the all-elements kernel; tma: 16 KB bulk copies
  * into a shared-memory ring), "reduce.threads", "reduce.blocks_per_sm" (all-elements kernel), "reduce.rows_vpt" (128-bit
  * vectors per thread that size the threads-per-row of the row kernel), "reduce.rows_blocks_per_sm" /
@@ -149,6 +152,15 @@ int b200_matmul(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dtype ou
                 const uint64_t* shape_lhs, const uint64_t* strides_lhs,
                 const uint64_t* shape_rhs, const uint64_t* strides_rhs,
                 const uint64_t* shape_out, const uint64_t* strides_out);
+/* The same product with DIFFERENT 8-bit formats for the two operands -- the pairs the reference instantiates for its manual
+ * MMA: i8 x u8 / u8 x i8 -> i32 (crates/cubecl-cpp/src/cuda/mma/manual.rs:151-166) and fp8 e4m3 x e5m2 / e5m2 x e4m3
+ * (:170-186).  Same tcgen05 kernels (kind::i8 / kind::f8f6f4 take one format field per operand in the instruction
+ * descriptor); equal formats behave exactly like b200_matmul.  Other combinations: B200_ERR_UNSUPPORTED. */
+int b200_matmul_mixed(b200_ctx* ctx, b200_stream s, b200_dtype lhs_dtype, b200_dtype rhs_dtype, b200_dtype out_dtype,
+                      b200_dptr lhs, b200_dptr rhs, b200_dptr out, int rank,
+                      const uint64_t* shape_lhs, const uint64_t* strides_lhs,
+                      const uint64_t* shape_rhs, const uint64_t* strides_rhs,
+                      const uint64_t* shape_out, const uint64_t* strides_out);
 
 /* Fused epilogue: out = act(alpha * (lhs @ rhs) + bias[n]) applied to the f32 accumulators inside the GEMM
  * epilogue (TMEM -> registers -> here -> store), no extra pass over the output.  bias: f32[N] device pointer or 0.

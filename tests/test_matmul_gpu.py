@@ -19,6 +19,7 @@ def _reset_options(client):
     client.set_option("gemm.f32", "3xtf32")
     client.set_option("gemm.split_k", "auto")
     client.set_option("gemm.epilogue", "tma")
+    client.set_option("gemm.stage", "on")
 
 
 # ------------------------------------------------------------------------------------------------ reference goldens
@@ -198,6 +199,106 @@ def run_matmul_int(client, a, b, dtype, lhs_t=False, rhs_t=False):
     out = TensorHandle.empty_contiguous(client, matmul.calculate_matmul_output(lhs.shape, rhs.shape), "i32")
     matmul.launch(client, lhs, rhs, out)
     return out.to_numpy(client)
+
+
+# ------------------------------------------------------------------------------------------------ mixed 8-bit operand formats
+@pytest.mark.parametrize("variant", ["auto", "2sm_n256", "1sm_n128", "simt"])
+@pytest.mark.parametrize("lhs_dtype,rhs_dtype", [("i8", "u8"), ("u8", "i8")])
+def test_mixed_sign_int8_exact(client, variant, lhs_dtype, rhs_dtype):
+    # crates/cubecl-cpp/src/cuda/mma/manual.rs:151-166: the reference instantiates i8 x u8 and u8 x i8 -> i32 for its manual
+    # MMA; here the golden generator of cmma.rs:1099-1196 (lhs[i,j] = 2i+j, rhs[i,j] = 3i+j) shifted so the signed operand is
+    # negative, plus a seeded full-range problem; exact integers either way
+    client.set_option("gemm.variant", variant)
+    m, n, k = 16, 8, 32
+    lhs = np.array([[2 * i + j for j in range(k)] for i in range(m)], dtype=np.int64)
+    rhs = np.array([[3 * i + j for j in range(n)] for i in range(k)], dtype=np.int64)
+    if lhs_dtype == "i8":
+        lhs = lhs - 60
+    else:
+        rhs = rhs - 60
+    npdt = {"i8": np.int8, "u8": np.uint8}
+    l8 = TensorHandle.from_numpy(client, lhs.astype(npdt[lhs_dtype]), lhs_dtype)
+    r8 = TensorHandle.from_numpy(client, rhs.astype(npdt[rhs_dtype]), rhs_dtype)
+    out = TensorHandle.empty_contiguous(client, [m, n], "i32")
+    matmul.launch(client, l8, r8, out)
+    assert np.array_equal(out.to_numpy(client).astype(np.int64), lhs @ rhs)
+    rng = np.random.default_rng(93)
+    M, N, K = 272, 320, 640
+    rng_of = {"i8": (-128, 128), "u8": (0, 256)}
+    a = rng.integers(*rng_of[lhs_dtype], size=(M, K)).astype(npdt[lhs_dtype])
+    b = rng.integers(*rng_of[rhs_dtype], size=(N, K)).astype(npdt[rhs_dtype])      # rhs given transposed (K-major)
+    out = TensorHandle.empty_contiguous(client, [M, N], "i32")
+    matmul.launch(client, TensorHandle.from_numpy(client, a, lhs_dtype), TensorHandle.from_numpy(client, b, rhs_dtype).transposed(), out)
+    assert np.array_equal(out.to_numpy(client).astype(np.int64), a.astype(np.int64) @ b.T.astype(np.int64))
+
+
+@pytest.mark.parametrize("variant", ["auto", "2sm_n256", "2sm_m512", "1sm_n128", "simt"])
+@pytest.mark.parametrize("lhs_dtype,rhs_dtype", [("f8e4m3", "f8e5m2"), ("f8e5m2", "f8e4m3")])
+def test_mixed_fp8_formats(client, variant, lhs_dtype, rhs_dtype):
+    # manual.rs:170-186: kind::f8f6f4 takes one format per operand.  The reference's fp8 golden generator with one operand in
+    # each format (exact against the fp8-rounded operands, within its 3 % of the integer expectation), then a seeded problem
+    client.set_option("gemm.variant", variant)
+    m, n, k = 16, 8, 32
+    lhs = np.array([[2 * i + j for j in range(k)] for i in range(m)], dtype=np.float32)
+    rhs = np.array([[3 * i + j for j in range(n)] for i in range(k)], dtype=np.float32)
+    l8, r8 = synth.to_device_dtype(lhs, lhs_dtype), synth.to_device_dtype(rhs, rhs_dtype)
+    out_dt = "bf16" if variant == "2sm_m512" else "f32"
+    out = TensorHandle.empty_contiguous(client, [m, n], out_dt)
+    matmul.launch(client, TensorHandle.from_numpy(client, l8, lhs_dtype), TensorHandle.from_numpy(client, r8, rhs_dtype), out)
+    got = synth.from_device_dtype(out.to_numpy(client), out_dt).astype(np.float64)
+    exp_rounded = synth.from_device_dtype(l8, lhs_dtype).astype(np.float64) @ synth.from_device_dtype(r8, rhs_dtype).astype(np.float64)
+    if out_dt == "f32":
+        assert np.array_equal(got, exp_rounded)
+    exp_int = lhs.astype(np.float64) @ rhs.astype(np.float64)
+    assert np.all(np.abs(got - exp_int) <= (0.03 if out_dt == "f32" else 0.04) * exp_int + 1e-9)
+    M, N, K = 384, 512, 640
+    a_dev, a = make_operand((M, K), lhs_dtype, 181)
+    b_dev, b = make_operand((K, N), rhs_dtype, 182)
+    out = TensorHandle.empty_contiguous(client, [M, N], out_dt)
+    matmul.launch(client, TensorHandle.from_numpy(client, a_dev, lhs_dtype), TensorHandle.from_numpy(client, b_dev, rhs_dtype), out)
+    check_against_oracle(synth.from_device_dtype(out.to_numpy(client), out_dt).reshape(M, N), a, b, out_dt, tight=1e-5 if out_dt == "f32" else None)
+
+
+def test_mixed_formats_outside_the_8bit_families_are_refused(client):
+    a = TensorHandle.empty_contiguous(client, [16, 16], "bf16")
+    b = TensorHandle.empty_contiguous(client, [16, 16], "f16")
+    out = TensorHandle.empty_contiguous(client, [16, 16], "f32")
+    matmul.launch(client, a, b, out)
+    with pytest.raises(ServerError):
+        client.sync()
+
+
+# ------------------------------------------------------------------------------------------------ operands TMA cannot describe
+@pytest.mark.parametrize("dtype,out_dtype,tol", [("bf16", "bf16", None), ("bf16", "f32", 1e-5), ("f16", "f32", 1e-5), ("f32", "f32", 2e-6), ("f8e4m3", "f32", 1e-5)])
+def test_unaligned_row_pitch_is_staged_onto_the_tensor_cores(client, dtype, out_dtype, tol):
+    # K = 1001: lhs rows are not 16-byte aligned, so TMA cannot describe lhs [M, K] in place.  One staging pass copies it into
+    # an aligned pooled buffer and the tcgen05 kernel runs (no cliff down to the strided SIMT kernel); rhs [K, N] needs nothing.
+    M, N, K = 320, 256, 1001
+    a_dev, a = make_operand((M, K), dtype, 191)
+    b_dev, b = make_operand((K, N), dtype, 192)
+    before = client.launch_count()
+    got = run_matmul(client, a_dev, b_dev, dtype, out_dtype)
+    launches = client.launch_count() - before
+    assert "gemm_simt" not in client.last_kernel() and launches == (2 if dtype != "f32" else 4)   # repitch (+ 2 lo splits) + GEMM
+    check_against_oracle(got, a, b, out_dtype, tight=tol)
+    # rhs given transposed [N, K] with the same odd K (both operands staged), a batch with a broadcast rhs, and an odd N for
+    # a row-major rhs (MN-major copy: rows of N stay rows)
+    bt_dev, bt = make_operand((N, K), dtype, 193)
+    got = run_matmul(client, a_dev, bt_dev, dtype, out_dtype, rhs_transposed=True)
+    check_against_oracle(got, a, np.ascontiguousarray(bt.T), out_dtype, tight=tol)
+    if dtype in ("bf16", "f32"):
+        a3_dev, a3 = make_operand((3, M, K), dtype, 194)
+        b1_dev, b1 = make_operand((1, K, N - 3), dtype, 195)
+        got = run_matmul(client, a3_dev, b1_dev, dtype, out_dtype)
+        for i in range(3):
+            check_against_oracle(got[i], a3[i], b1[0], out_dtype, tight=tol)
+    client.set_option("gemm.stage", "off")                      # the reference-order SIMT kernel is still there
+    try:
+        got = run_matmul(client, a_dev, b_dev, dtype, out_dtype)
+        assert "gemm_simt" in client.last_kernel()
+        check_against_oracle(got, a, b, out_dtype, tight=tol)
+    finally:
+        client.set_option("gemm.stage", "on")
 
 
 # ------------------------------------------------------------------------------------------------ fused epilogue
@@ -587,16 +688,27 @@ def test_f32_4096_sampled_points(client):
 
 
 def test_batched_4096_matches_single(client):
-    # BASELINE config 5 shape family (per-GPU slice: 8 x 4096^3): every batch equals the same product run alone
+    # BASELINE config 5 shape family (per-GPU slice: 8 x 4096^3): every batch equals the same product run alone -- bit for bit
+    # when both run the same plan (the K association of a stream-K head depends on the tile count, so it is switched off for
+    # that comparison), and to one output rounding under the default plans
     n, B = 4096, 3
     a = _device_operand(client, [B, n, n], "bf16", 6)
     b = _device_operand(client, [B, n, n], "bf16", 7)
-    out = TensorHandle.empty_contiguous(client, [B, n, n], "bf16")
-    matmul.launch(client, a, b, out)
-    got = out.to_numpy(client)
-    for bi in (0, B - 1):
-        a1 = TensorHandle(a.handle.offset(bi * n * n * 2, n * n * 2), [n, n], [n, 1], "bf16")
-        b1 = TensorHandle(b.handle.offset(bi * n * n * 2, n * n * 2), [n, n], [n, 1], "bf16")
-        o1 = TensorHandle.empty_contiguous(client, [n, n], "bf16")
-        matmul.launch(client, a1, b1, o1)
-        assert np.array_equal(o1.to_numpy(client), got[bi])
+    for split, exact in (("off", True), ("auto", False)):
+        client.set_option("gemm.split_k", split)
+        client.set_option("gemm.variant", "2sm_n256" if exact else "auto")
+        out = TensorHandle.empty_contiguous(client, [B, n, n], "bf16")
+        matmul.launch(client, a, b, out)
+        got = out.to_numpy(client)
+        for bi in (0, B - 1):
+            a1 = TensorHandle(a.handle.offset(bi * n * n * 2, n * n * 2), [n, n], [n, 1], "bf16")
+            b1 = TensorHandle(b.handle.offset(bi * n * n * 2, n * n * 2), [n, n], [n, 1], "bf16")
+            o1 = TensorHandle.empty_contiguous(client, [n, n], "bf16")
+            matmul.launch(client, a1, b1, o1)
+            one = o1.to_numpy(client)
+            if exact:
+                assert np.array_equal(one, got[bi])
+            else:
+                x, y = synth.bf16_bits_to_f32(one).astype(np.float64), synth.bf16_bits_to_f32(got[bi]).astype(np.float64)
+                assert np.max(np.abs(x - y) / (np.abs(y) + 1.0)) <= 2.0 ** -7      # at most one bf16 rounding step apart
+                assert np.mean(one != got[bi]) < 0.02                               # and almost everywhere identical

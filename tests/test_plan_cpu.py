@@ -97,8 +97,8 @@ def test_f32_defaults_to_3xtf32_with_two_split_passes(plan):
     assert t.count("tmap ") == 5                                         # A, B (originals = hi) + A_lo, B_lo + C
     assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
     assert t.count(f"alloc {n * n * 4}") == 2                            # 1x temporaries (lo parts), not 3x
-    # 256 tiles on 74 CTA pairs = 3.46 waves: the 34 tiles of the partial wave become a stream-K head cut into 74 equal k-ranges
-    assert "gemm stream-k head: 222 whole tiles + 34 tiles in 74 k-ranges" in t
+    # 256 tiles on 74 CTA pairs = 3.46 waves: the 34 tiles of the partial wave become a stream-K head, two equal halves each
+    assert "gemm stream-k head: 222 whole tiles + 34 tiles in 68 k-ranges" in t
     plan.option("gemm.f32", "tf32")
     rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gemm_tf32_f32_2sm_n256_kn"]
@@ -112,16 +112,16 @@ def test_stream_k_head_policy(plan):
     rc, t = mm(8192, 8192)                     # 512 pair tiles = 6.92 waves: nothing to gain
     assert rc == 0 and "stream-k" not in t and "2sm_m512" in t
     rc, t = mm(4096, 4096)                     # 2 waves of pair tiles (1.73 needed) lose to 3.46 waves of 256x256 tiles with a head
-    assert rc == 0 and "222 whole tiles + 34 tiles in 74 k-ranges (<= 2 slabs per range)" in t and "2sm_n256" in t
-    assert f"alloc {74 * 2 * 256 * 256 * 4}" in t and "grid=(148,1,1)" in t
+    assert rc == 0 and "222 whole tiles + 34 tiles in 68 k-ranges (<= 2 slabs per range)" in t and "2sm_n256" in t
+    assert f"alloc {68 * 2 * 256 * 256 * 4}" in t and "grid=(148,1,1)" in t
     rc, t = mm(4096, 4096, dt=F32, out=F32)    # 3xTF32 (BASELINE config 2): same cut, 384 k-blocks per tile
-    assert rc == 0 and "222 whole tiles + 34 tiles in 74 k-ranges" in t
+    assert rc == 0 and "222 whole tiles + 34 tiles in 68 k-ranges" in t
     rc, t = mm(6144, 6144)                     # 3.89 waves of pair tiles: already 97 % full
     assert rc == 0 and "stream-k" not in t and "2sm_m512" in t
     rc, t = mm(1024, 8192)                     # fewer tiles than pairs: the head is the whole problem
-    assert rc == 0 and "0 whole tiles + 32 tiles in 74 k-ranges" in t and "2sm_n128" in t and "grid=(148,1,1)" in t
-    rc, t = mm(512, 16384)                     # 8 tiles, 256 k-blocks each, ~9 parts per tile
-    assert rc == 0 and "0 whole tiles + 8 tiles in 74 k-ranges" in t
+    assert rc == 0 and "0 whole tiles + 32 tiles in 64 k-ranges" in t and "2sm_n128" in t and "grid=(128,1,1)" in t
+    rc, t = mm(512, 16384)                     # 8 tiles, 256 k-blocks each: equal parts, the count the model likes best (7)
+    assert rc == 0 and "0 whole tiles + 8 tiles in 56 k-ranges" in t
     rc, t = mm(1024, 256)                      # 4 k-blocks: too short to cut
     assert rc == 0 and "stream-k" not in t
     rc, t = mm(2048, 2048)                     # 64 of 74 pairs busy for one wave: an exposed exchange would cost more
@@ -245,7 +245,7 @@ def test_wave_model_prefers_big_tiles(plan):
 def test_reduce_plans(plan):
     SUM, ARGMAX, MEAN = _ffi.REDUCE_SUM, _ffi.REDUCE_ARGMAX, _ffi.REDUCE_MEAN
     rc, t = plan.reduce(SUM, F32, [1 << 28], -1)                          # big value reductions: bulk-copy staged, one CTA per SM
-    assert rc == 0 and t.strip() == "launch reduce_all_sum_f32_tma grid=(148,1,1) block=288 smem=131200 cluster=1"
+    assert rc == 0 and t.strip() == "launch reduce_all_sum_f32_tma grid=(148,1,1) block=288 smem=98432 cluster=1"
     plan.option("reduce.variant", "u8")                                    # the plain 128-bit streaming form
     rc, t = plan.reduce(SUM, F32, [1 << 28], -1)
     assert rc == 0 and t.strip() == "launch reduce_all_sum_f32 grid=(592,1,1) block=512 smem=0 cluster=1"
@@ -306,7 +306,7 @@ def test_reduce_plans(plan):
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_cols_sum_f32"]
     plan.option("reduce.variant", "tma")                                   # forced: used from 1 MB up
     rc, t = plan.reduce(SUM, BF16, [1 << 20], -1)
-    assert t.strip() == "launch reduce_all_sum_bf16_tma grid=(128,1,1) block=288 smem=131200 cluster=1"
+    assert t.strip() == "launch reduce_all_sum_bf16_tma grid=(128,1,1) block=288 smem=98432 cluster=1"
     rc, t = plan.reduce(SUM, F32, [1000], -1)                              # too small for a ring: plain loads
     assert "reduce_all_sum_f32 " in t
     plan.option("reduce.variant", "auto")

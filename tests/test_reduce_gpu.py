@@ -205,7 +205,7 @@ def test_offset_views_need_element_alignment_only(client, dtype, offset):
     # a sub-slice view (Handle::offset) starts on an element boundary, not a 16-byte one: the all / rows / columns kernels and
     # their wide / bulk variants peel a scalar head instead of issuing a misaligned vector load (which would be a sticky fault)
     esz = 4 if dtype == "f32" else 2
-    n = (1 << 19) + 37
+    n = (1 << 19) + 301                                                  # >= 257 * 2041, the row / column case below
     vals = synth.uniform_f32(31, n + offset, -1.0, 1.0)
     dev = synth.to_device_dtype(vals, dtype)
     x = synth.from_device_dtype(dev, dtype)[offset:]

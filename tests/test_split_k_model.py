@@ -45,23 +45,38 @@ def host_plan(tiles, clusters, num_kb, option="auto", eligible=True):
     none = (time, 0, 0, 0)
     if option == "off" or not eligible or rem == 0 or num_kb < 2:
         return none
-    ranges, force = clusters, False
-    if option == "on":
-        force = True
-    elif option != "auto":
+    total_kb = rem * num_kb
+
+    def model(ranges, even):
+        share = -(-total_kb // ranges)
+        parts = max(1.0, ranges / rem)
+        head = -(-ranges // clusters) * share / num_kb
+        overhead = (4.0 if full_waves >= 1 else 14.0 + 8.0 * parts) / num_kb
+        return full_waves + (1.4 if even else 1.6) * head + overhead
+
+    force, even = False, True
+    if option in ("auto", "on"):
+        force = option == "on"
+        s_fit = min(clusters // rem, 8)
+        if s_fit >= 2:
+            best = s_fit
+            if full_waves == 0:
+                for s2 in range(2, s_fit + 1):
+                    if num_kb // s2 >= 8 and model(rem * s2, True) < model(rem * best, True) - 1e-12:
+                        best = s2
+            ranges = rem * best
+        else:
+            ranges, even = clusters, False
+    else:
         want = int(option)
         if want == 1:
             return none
         ranges, force = rem * want, True
-    total_kb = rem * num_kb
     ranges = min(ranges, total_kb)
     if ranges <= rem and not force:
         return none
     share = -(-total_kb // ranges)
-    parts = max(1.0, ranges / rem)
-    head = -(-ranges // clusters) * share / num_kb
-    overhead = (4.0 if full_waves >= 1 else 14.0 + 8.0 * parts) / num_kb
-    t_sk = full_waves + head + overhead
+    t_sk = model(ranges, even)
     if not force:
         if share < 8 or t_sk > 0.96 * time:
             return none
@@ -154,15 +169,19 @@ def test_slab_exchange_is_order_independent_and_resets_its_ticket():
 
 
 def test_host_policy_on_the_baseline_shapes():
-    # (tiles, CTA pairs, k-blocks per tile) -> is the last partial wave turned into a stream-K head?
+    # (tiles, CTA pairs, k-blocks per tile) -> (tiles in the head, ranges)
     def head(tiles, clusters, num_kb):
-        return host_plan(tiles, clusters, num_kb)[1]
-    assert head(1024, 74, 128) == 0      # bf16 8192^3 on 256x256 tiles: 13.84 waves, nothing to gain
-    assert head(256, 74, 128) == 34      # tf32 4096^3: 3.46 waves instead of 4 (BASELINE config 2)
-    assert head(256, 74, 384) == 34      # 3xTF32 4096^3
-    assert head(256, 74, 64) == 34       # bf16 4096^3 on 256x256 tiles
-    assert head(8, 74, 256) == 8         # 512^2 x 16384: the head is the whole problem (exposed exchange still pays: 9 parts)
-    assert head(4, 74, 8) == 0           # tiny K: slices would be thinner than 8 k-blocks
-    assert head(74, 74, 128) == 0        # exactly one wave
+        return host_plan(tiles, clusters, num_kb)[1:3]
+    assert head(1024, 74, 128) == (0, 0)     # bf16 8192^3 on 256x256 tiles: 13.84 waves, nothing to gain
+    assert head(256, 74, 128) == (34, 68)    # tf32 4096^3 (BASELINE config 2): 34 tiles in two equal halves each
+    assert head(256, 74, 384) == (34, 68)    # 3xTF32 4096^3
+    assert head(256, 74, 64) == (34, 68)     # bf16 4096^3 on 256x256 tiles
+    # bf16 5120^3: 400 tiles of 256x256 = 5.41 waves -> modelled 5.75 with a head; the pair tile (3 whole waves of twice the work
+    # at x1.06 = 5.66) still wins the variant choice, as measured (171.8 against 176.5 us)
+    assert abs(host_plan(400, 74, 80)[0] - 5.75) < 1e-9 and 3 * 2 / 1.06 < 5.75
+    assert head(8, 74, 256)[0] == 8          # 512^2 x 16384: the head is the whole problem, equal parts chosen by the model
+    assert 2 <= head(8, 74, 256)[1] // 8 <= 8
+    assert head(4, 74, 8) == (0, 0)          # tiny K: slices would be thinner than 8 k-blocks
+    assert head(74, 74, 128) == (0, 0)       # exactly one wave
     t_with, *_ = host_plan(256, 74, 128)
-    assert abs(t_with - (3 + 34 / 74 + 4.0 / 128)) < 0.02
+    assert abs(t_with - (3 + 1.4 * 0.5 + 4.0 / 128)) < 1e-9
