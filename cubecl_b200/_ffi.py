@@ -67,6 +67,7 @@ SIGNATURES = {
     "b200_last_kernel": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "b200_alloc": (C.c_int, [_vp, C.c_size_t, _u64p]),
     "b200_free": (C.c_int, [_vp, C.c_uint64]),
+    "b200_free_async": (C.c_int, [_vp, C.c_uint64, _vp]),
     "b200_memory_usage": (C.c_int, [_vp, _u64p, _u64p]),
     "b200_memory_cleanup": (C.c_int, [_vp]),
     "b200_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),

@@ -70,10 +70,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = _nvcc()
 
+    # every cubin is rebuilt only when ITS inputs changed (source, the shared PTX header, the flags): editing reduce.cu does not
+    # cost the five minutes of ptxas the GEMM instantiations take
+    def inputs_digest(src, extra):
+        h = hashlib.sha256(" ".join(NVCC_FLAGS + list(extra)).encode())
+        for f in (CSRC / src, CSRC / "ptx.cuh"):
+            h.update(f.read_bytes())
+        return h.hexdigest()
+
     def compile_one(item):
         tag, (src, extra) = item
-        log = _run([nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", str(CSRC / src), "-o", str(BUILD / f"{tag}.cubin")])
+        out, mark = BUILD / f"{tag}.cubin", BUILD / f"{tag}.stamp"
+        want = inputs_digest(src, extra)
+        if not force and out.exists() and mark.exists() and mark.read_text() == want:
+            return f"{tag}: up to date"
+        log = _run([nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", str(CSRC / src), "-o", str(out)])
         (BUILD / f"{tag}.ptxas.log").write_text(log)
+        mark.write_text(want)
         return log
 
     from concurrent.futures import ThreadPoolExecutor

@@ -47,6 +47,7 @@ class Handle:
 
     def __init__(self, client: "ComputeClient", ptr: int, size: int, owner: bool = True):
         self.client, self.ptr, self.size, self._owner = client, ptr, size, owner
+        self.last_stream = None   # a non-default stream that was handed this buffer (copies / launches): freed in that stream's order
 
     def offset(self, start_bytes: int, size: int | None = None) -> "Handle":
         """Sub-slice view (Handle::offset_start); does not own the allocation."""
@@ -54,10 +55,21 @@ class Handle:
         h._keep = self  # keep the parent alive
         return h
 
+    def used_on(self, stream) -> None:
+        """Remember that work on `stream` touches this buffer (and its parent allocation)."""
+        if stream is not None:
+            self.last_stream = stream
+            parent = getattr(self, "_keep", None)
+            if parent is not None:
+                parent.used_on(stream)
+
     def __del__(self):
         if getattr(self, "_owner", False) and self.ptr and self.client is not None and self.client._ctx:
             try:
-                self.client._lib.b200_free(self.client._ctx, C.c_uint64(self.ptr))
+                if self.last_stream is not None:
+                    self.client._lib.b200_free_async(self.client._ctx, C.c_uint64(self.ptr), self.last_stream)
+                else:
+                    self.client._lib.b200_free(self.client._ctx, C.c_uint64(self.ptr))
             except Exception:
                 pass
 
@@ -199,10 +211,12 @@ class ComputeClient:
 
     def write_async(self, handle: Handle, host: np.ndarray, nbytes: int | None = None, stream=None) -> None:
         n = host.nbytes if nbytes is None else nbytes
+        handle.used_on(stream)
         _ffi.check(self._lib.b200_write(self._ctx, stream, C.c_uint64(handle.ptr), host.ctypes.data_as(C.c_void_p), n))
 
     def read_async(self, host: np.ndarray, handle: Handle, nbytes: int | None = None, stream=None) -> None:
         n = host.nbytes if nbytes is None else nbytes
+        handle.used_on(stream)
         _ffi.check(self._lib.b200_read(self._ctx, stream, host.ctypes.data_as(C.c_void_p), C.c_uint64(handle.ptr), n))
 
     # -- extra streams (StreamId -> CUstream, cubecl-cuda/src/compute/stream.rs:24-44); None = the client's compute stream

@@ -457,6 +457,10 @@ extern "C" int b200_init(int device, b200_ctx** out) {
   if ((r = g_drv.cuStreamCreate_p(&c->stream, CU_STREAM_NON_BLOCKING)) != CUDA_SUCCESS ||
       (r = g_drv.cuStreamCreate_p(&c->comm_stream, CU_STREAM_NON_BLOCKING)) != CUDA_SUCCESS ||
       (r = g_drv.cuEventCreate_p(&c->comm_event, CU_EVENT_DISABLE_TIMING)) != CUDA_SUCCESS) {
+    // release what exists: streams created so far, the four loaded modules, the retained primary context
+    if (c->comm_stream) g_drv.cuStreamDestroy_p(c->comm_stream);
+    if (c->stream) g_drv.cuStreamDestroy_p(c->stream);
+    for (CUmodule m : c->modules) g_drv.cuModuleUnload_p(m);
     g_drv.cuDevicePrimaryCtxRelease_p(c->dev);
     return bail(fail(map_cu(r), "stream/event creation failed: %s", cu_err(r)));
   }
@@ -525,7 +529,7 @@ extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) 
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
   static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "gemm.stage", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm", "reduce.rows_vpt", "reduce.rows_blocks_per_sm", "reduce.cols_blocks_per_sm",
-                                "reduce.debug", "reduce.pdl", "reduce.tma_stages", "reduce.tma_ctas_per_sm"};
+                                "reduce.debug", "reduce.pdl", "reduce.tma_stages", "reduce.tma_ctas_per_sm", "reduce.cols_split_target"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
   return fail(B200_ERR_INVALID_ARG, "unknown option '%s'", key);
@@ -632,6 +636,13 @@ extern "C" int b200_free(b200_ctx* c, b200_dptr ptr) {
   return pool_free(c, static_cast<CUdeviceptr>(ptr));
 }
 
+// The stream-ordered form: `last_use` is the stream whose queued work may still touch the buffer (NULL = the context's
+// stream).  The page is handed out again only once an event recorded there has completed (or to that same stream).
+extern "C" int b200_free_async(b200_ctx* c, b200_dptr ptr, b200_stream last_use) {
+  CTX_ENTER(c);
+  return pool_free(c, static_cast<CUdeviceptr>(ptr), resolve_stream(c, last_use));
+}
+
 extern "C" int b200_memory_usage(b200_ctx* c, uint64_t* in_use, uint64_t* reserved) {
   if (!c) return fail(B200_ERR_INVALID_ARG, "null context");
   if (in_use) *in_use = c->bytes_in_use;
@@ -715,6 +726,9 @@ extern "C" int b200_stream_create(b200_ctx* c, b200_stream* out) {
 extern "C" int b200_stream_destroy(b200_ctx* c, b200_stream s) {
   CTX_ENTER_DEVICE(c);
   if (!s) return B200_OK;
+  CU_CHECK(g_drv.cuStreamSynchronize_p(static_cast<CUstream>(s)));   // pages freed on this stream are idle from here on
+  for (auto& kv : c->blocks)
+    if (kv.second.last_stream == static_cast<CUstream>(s)) { kv.second.last_stream = nullptr; kv.second.pending = false; }
   auto it = c->reduce_ws.find(static_cast<CUstream>(s));
   if (it != c->reduce_ws.end()) { g_drv.cuMemFree_p(it->second); c->reduce_ws.erase(it); }
   CU_CHECK(g_drv.cuStreamDestroy_p(static_cast<CUstream>(s)));
@@ -1751,7 +1765,8 @@ static int reduce_axis_view(b200_ctx* c, CUstream st, int op, int dt, const RVie
     const uint64_t tiles = ceil_div(units, std::min<uint64_t>(units, 32));
     const unsigned bps = opt_uint(c, "reduce.cols_blocks_per_sm", 4, 1, 64);
     if (v.outer * tiles < sms * bps && v.len >= 256) {
-      const uint64_t nseg = std::min<uint64_t>(ceil_div(sms * 16, v.outer * tiles), v.len / 64);
+      const uint64_t target = sms * opt_uint(c, "reduce.cols_split_target", 16, 1, 256);   // blocks aimed at when an axis is segmented
+      const uint64_t nseg = std::min<uint64_t>(ceil_div(target, v.outer * tiles), v.len / 64);
       if (nseg > 1) seg_len = ceil_div(v.len, nseg);
     }
   }

@@ -918,32 +918,35 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
     const char* cb = base + (o * p.s_outer + l0 * p.s_len + ioff) * sizeof(T);
     const uint64_t lstep = p.s_len * sizeof(T);
 
-    float a[4][UV];
+    // eight loads in flight per thread (at ~62 registers four blocks share an SM: 128 KB of loads in flight per SM), folded
+    // into two accumulator sets
+    constexpr int NL = 8;
+    float a[2][UV];
     ArgAcc cand[UV];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
       for (int j = 0; j < UV; ++j) a[u][j] = ValOp<OP>::identity();
     if (valid) {
       uint64_t l = rl;
-      for (; l + 3ull * RL < L; l += 4ull * RL) {
-        float f[4][UV];
+      for (; l + static_cast<uint64_t>(NL - 1) * RL < L; l += static_cast<uint64_t>(NL) * RL) {
+        float f[NL][UV];
         if constexpr (VECTOR) {
-          uint4 r[4];
+          uint4 r[NL];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) r[u] = ldg_stream_u4(cb + (l + static_cast<uint64_t>(u) * RL) * lstep);
+          for (int u = 0; u < NL; ++u) r[u] = ldg_stream_u4(cb + (l + static_cast<uint64_t>(u) * RL) * lstep);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) E::unpack(r[u], f[u]);
+          for (int u = 0; u < NL; ++u) E::unpack(r[u], f[u]);
         } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) f[u][0] = E::get(cb + (l + static_cast<uint64_t>(u) * RL) * lstep, 0);
+          for (int u = 0; u < NL; ++u) f[u][0] = E::get(cb + (l + static_cast<uint64_t>(u) * RL) * lstep, 0);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < NL; ++u)
 #pragma unroll
           for (int j = 0; j < UV; ++j) {
             if constexpr (ARG) cand[j].feed<OP>(f[u][j], static_cast<uint32_t>(l0 + l + static_cast<uint64_t>(u) * RL));
-            else a[u][j] = ValOp<OP>::apply(a[u][j], f[u][j]);
+            else a[u & 1][j] = ValOp<OP>::apply(a[u & 1][j], f[u][j]);
           }
       }
       for (; l < L; l += RL) {
@@ -961,7 +964,7 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
     uint64_t resp[UV];
 #pragma unroll
     for (int j = 0; j < UV; ++j) {
-      res[j] = ValOp<OP>::apply(ValOp<OP>::apply(a[0][j], a[1][j]), ValOp<OP>::apply(a[2][j], a[3][j]));
+      res[j] = ValOp<OP>::apply(a[0][j], a[1][j]);
       resp[j] = cand[j].packed();
     }
     // combine the row lanes of each unit through shared memory: slot (rl, cu) at [threadIdx.x * UV + j]; lanes that found
@@ -1014,9 +1017,9 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
       // column tile); whoever completes the set re-reads all nseg partial rows of the tile -- each row lane a fixed subset of
       // the segments, then the same lane tree -- so the result does not depend on which block came last.  No second launch.
       __shared__ uint32_t s_last;
-      __threadfence();
-      __syncthreads();
+      __syncthreads();            // the row-lane-0 threads have stored the partials ...
       if (threadIdx.x == 0) {
+        __threadfence();          // ... and this (cumulative) fence publishes them before the ticket
         unsigned int* ticket = reinterpret_cast<unsigned int*>(p.ws + kWsColTicketOffset) + (o * tiles + tile);
         const unsigned int old = atomicAdd(ticket, 1u);
         s_last = (old == p.nseg - 1) ? 1u : 0u;

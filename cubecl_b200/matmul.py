@@ -53,6 +53,8 @@ def launch(client: ComputeClient, lhs: TensorHandle, rhs: TensorHandle, out: Ten
     if alpha != 1.0 or bias is not None or activation not in (None, "none"):
         return _launch_fused(client, lhs, rhs, out, stream, alpha, bias, activation)
     try:
+        for th in (lhs, rhs, out):
+            th.handle.used_on(stream)
         rank = len(lhs.shape)
         if len(rhs.shape) != rank or len(out.shape) != rank:
             raise B200Error(6, "matmul: lhs, rhs and out must have equal rank")

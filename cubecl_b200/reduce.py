@@ -1,7 +1,8 @@
 """`reduce::launch` surface (cubek's reduce is out of tree; in-tree semantics: examples/sum_things/src/lib.rs:6-33,
 cubecl-book/src/getting-started/src/bin/v1-cpu.rs:7-15).
 
-Reduces one axis (or every element with axis=None) of a tensor (any strides; non-contiguous inputs are compacted first); f32 accumulation; output f32 (values) or
+Reduces one axis (or every element with axis=None) of a tensor (any strides: pitched rows and transposed views are read in
+place, only views no stride description fits are compacted first); f32 accumulation; output f32 (values) or
 u32 (indices for argmax/argmin: ties -> lowest index, first NaN wins).  Kernels: csrc/reduce.cu.
 """
 from __future__ import annotations
@@ -39,9 +40,11 @@ def launch(client: ComputeClient, input: TensorHandle, output: TensorHandle, axi
             raise B200Error(6, f"reduce: output dtype must be {output_dtype(op)} for op {op}")
         rank = len(input.shape)
         ax = -1 if axis is None else axis % rank
+        input.handle.used_on(stream)
+        output.handle.used_on(stream)
         if not output.is_contiguous():
             raise B200Error(7, "reduce: output must be contiguous")
-        # pitched / permuted inputs are gathered into a compact temporary inside the library (into_contiguous)
+        # pitched / permuted inputs are reduced in place by the library (strides + row pitch go to the kernels)
         _ffi.check(client._lib.b200_reduce_strided(client._ctx, stream, OPS[op], DTYPES[input.dtype], C.c_uint64(input.handle.ptr),
                                                    C.c_uint64(output.handle.ptr), rank, _ffi.u64_array(input.shape),
                                                    _ffi.u64_array(input.strides), ax))

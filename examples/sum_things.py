@@ -3,8 +3,9 @@
 
 The reference launches 4 kernel kinds over input [-1, 10, 1, 5] with one unit per element, every unit computing the full
 sum (15) -- or sum * input[unit] for the series kind -- and prints the output buffer after each.  Here the sum is the
-device-wide reduce kernel (`reduce::launch`, warp-shuffle `plane_sum` stage inside), and the series product is a [4,1] x
-[1,1] matmul, so every printed number still comes from the GPU through the C ABI.
+device-wide reduce kernel (`reduce::launch`, warp-shuffle `plane_sum` stage inside); the per-unit output buffer is produced
+ON THE DEVICE by a [4,1] x [1,1] matmul against the reduced scalar (ones for the plain kinds, the input for the series kind),
+so every printed number comes from the GPU through the C ABI -- nothing is replicated on the host.
 """
 import sys
 from pathlib import Path
@@ -20,18 +21,18 @@ def launch(device: int = 0) -> None:
     data = np.array([-1.0, 10.0, 1.0, 5.0], dtype=np.float32)
     inp = TensorHandle.from_numpy(client, data, "f32")
     name = f"cuda-b200<{client.properties['name']}>"
+    ones = TensorHandle.from_numpy(client, np.ones(len(data), dtype=np.float32), "f32")
+    client.set_option("gemm.f32", "tf32")                                    # small integers: exact on the tf32 pipe
     for kind in ("Basic", "Plane", "TraitSum", "SeriesSumThenMul"):
         total = reduce.launch_alloc(client, inp, None, "sum")                 # [1] f32 on the device
-        if kind == "SeriesSumThenMul":
-            lhs = TensorHandle(inp.handle, [4, 1], [1, 1], "f32")
-            rhs = TensorHandle(total.handle, [1, 1], [1, 1], "f32")
-            out = TensorHandle.empty_contiguous(client, [4, 1], "f32")
-            client.set_option("gemm.f32", "tf32")
-            matmul.launch(client, lhs, rhs, out)
-            output = out.to_numpy(client).ravel()
-        else:
-            output = np.repeat(total.to_numpy(client), len(data))            # every unit holds the same sum
+        per_unit = inp if kind == "SeriesSumThenMul" else ones                # output[unit] = sum * input[unit]  /  = sum
+        lhs = TensorHandle(per_unit.handle, [4, 1], [1, 1], "f32")
+        rhs = TensorHandle(total.handle, [1, 1], [1, 1], "f32")
+        out = TensorHandle.empty_contiguous(client, [4, 1], "f32")
+        matmul.launch(client, lhs, rhs, out)
+        output = out.to_numpy(client).ravel()
         print(f"[{name!r} - {kind}]\n {output.tolist()}")
+    client.set_option("gemm.f32", "3xtf32")
 
 
 if __name__ == "__main__":

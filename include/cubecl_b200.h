@@ -117,7 +117,12 @@ int b200_last_kernel(b200_ctx* ctx, char* buf, size_t capacity);
 /* ---- memory: ComputeClient::{empty,create_from_slice,read_one} (cubecl-runtime/src/client.rs:654,452,256) ----------- */
 /* Pooled device allocation, 512-byte aligned (mem_alignment, cubecl-cuda/src/runtime.rs:81). */
 int b200_alloc(b200_ctx* ctx, size_t bytes, b200_dptr* out);
+/* b200_free returns the page to the pool as of the CONTEXT's stream: a buffer that work queued on another stream (the
+ * `s` argument of the compute / copy entry points) may still touch must be freed with b200_free_async naming that stream --
+ * the pool then re-issues the page only after an event recorded there has completed (the reference binds pool memory to
+ * its stream and waits on cross-stream events, crates/cubecl-runtime/src/stream/event.rs:50-57). */
 int b200_free(b200_ctx* ctx, b200_dptr ptr);
+int b200_free_async(b200_ctx* ctx, b200_dptr ptr, b200_stream last_use);
 int b200_memory_usage(b200_ctx* ctx, uint64_t* bytes_in_use, uint64_t* bytes_reserved);  /* MemoryUsage, memory_management/base.rs:7-28 */
 int b200_memory_cleanup(b200_ctx* ctx);                                                  /* client.memory_cleanup */
 /* Pinned host staging (compute/stream.rs:138-178 pinned pool). */

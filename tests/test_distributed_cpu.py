@@ -43,6 +43,20 @@ def _worker(rank, world, port, tmp):
     assert np.array_equal(out, oracle.matmul_f32(a, b))
 
     assert max_over_ranks(float(rank + 1), dist) == float(world)
+
+    # the closed forms bench.py's multi-GPU parity object checks against (exact-integer data, runtime_tests/all_reduce.rs model)
+    import bench
+    n_red = 1 << 16
+    assert bench.mod8_prefix_sum(n_red) == int((np.arange(n_red) % 8).sum()) and bench.mod8_prefix_sum(13) == int((np.arange(13) % 8).sum())
+    lo, hi = shard_range(n_red, world, rank)
+    local = bench.mod8_prefix_sum(hi) - bench.mod8_prefix_sum(lo)
+    assert local == int((np.arange(lo, hi) % 8).sum())
+    tot = torch.tensor([float(local)], dtype=torch.float64)
+    dist.all_reduce(tot)
+    assert int(tot.item()) == bench.mod8_prefix_sum(n_red)
+    # one rank failing its check fails the whole record
+    assert bench.all_ranks_ok(True, dist, None) is True
+    assert bench.all_ranks_ok(rank != 1, dist, None) is False
     dist.barrier()
     dist.destroy_process_group()
     Path(tmp, f"ok{rank}").write_text("ok")

@@ -218,7 +218,8 @@ def test_mixed_sign_int8_exact(client, variant, lhs_dtype, rhs_dtype):
         rhs = rhs - 60
     npdt = {"i8": np.int8, "u8": np.uint8}
     l8 = TensorHandle.from_numpy(client, lhs.astype(npdt[lhs_dtype]), lhs_dtype)
-    r8 = TensorHandle.from_numpy(client, rhs.astype(npdt[rhs_dtype]), rhs_dtype)
+    # rhs handed over K-major (a transposed view of [n, k]): 32-byte rows, describable by TMA for the forced tile variants
+    r8 = TensorHandle.from_numpy(client, np.ascontiguousarray(rhs.T).astype(npdt[rhs_dtype]), rhs_dtype).transposed()
     out = TensorHandle.empty_contiguous(client, [m, n], "i32")
     matmul.launch(client, l8, r8, out)
     assert np.array_equal(out.to_numpy(client).astype(np.int64), lhs @ rhs)
@@ -244,7 +245,8 @@ def test_mixed_fp8_formats(client, variant, lhs_dtype, rhs_dtype):
     l8, r8 = synth.to_device_dtype(lhs, lhs_dtype), synth.to_device_dtype(rhs, rhs_dtype)
     out_dt = "bf16" if variant == "2sm_m512" else "f32"
     out = TensorHandle.empty_contiguous(client, [m, n], out_dt)
-    matmul.launch(client, TensorHandle.from_numpy(client, l8, lhs_dtype), TensorHandle.from_numpy(client, r8, rhs_dtype), out)
+    # rhs handed over K-major (a transposed view of [n, k]): 32-byte rows, describable by TMA for the forced tile variants
+    matmul.launch(client, TensorHandle.from_numpy(client, l8, lhs_dtype), TensorHandle.from_numpy(client, np.ascontiguousarray(r8.T), rhs_dtype).transposed(), out)
     got = synth.from_device_dtype(out.to_numpy(client), out_dt).astype(np.float64)
     exp_rounded = synth.from_device_dtype(l8, lhs_dtype).astype(np.float64) @ synth.from_device_dtype(r8, rhs_dtype).astype(np.float64)
     if out_dt == "f32":

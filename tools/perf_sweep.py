@@ -228,6 +228,49 @@ if "axis" in what:
             print(f"  {op:6s} {str(shape):22s} axis={axis} launches={launches} x{copies} buffers: " + "  |  ".join(res), flush=True)
             del ts, out
 
+if "cols" in what:
+    # column (outer-axis) reductions: how many blocks a segmented axis should aim at (reduce.cols_split_target x SMs)
+    print("column reductions, GB/s = (input + output bytes) / time, min of 5 x 20 launches:")
+    for shape, axis in (([8192, 8192], 0), ([1 << 14, 1 << 14], 0), ([1 << 22, 64], 0), ([4096, 4096], 0), ([64, 4096, 1024], 1)):
+        n = int(np.prod(shape))
+        copies = max(1, min(8, (192 << 20) // (n * 4) + 1))
+        ts = [TensorHandle.empty_contiguous(c, shape, "f32") for _ in range(copies)]
+        for i, t in enumerate(ts):
+            c.fill_uniform(t.handle, "f32", n, 11 + i, 0.0, 1.0)
+        for op in ("sum", "argmax"):
+            oshape = reduce.output_shape(shape, axis)
+            out = TensorHandle.empty_contiguous(c, oshape, reduce.output_dtype(op))
+            nbytes = n * 4 + int(np.prod(oshape)) * 4
+            k = [0]
+
+            def run():
+                k[0] += 1
+                reduce.launch(c, ts[k[0] % copies], out, axis, op)
+            res = []
+            for target in (4, 8, 16, 32, 64):
+                c.set_option("reduce.cols_split_target", target)
+                best = min(time_ms(c, run, iters=20, warm=3) for _ in range(5))
+                res.append(f"{target}: {best * 1e3:7.1f} us {nbytes / best / 1e6:7.1f}")
+            c.set_option("reduce.cols_split_target", 16)
+            print(f"  {op:6s} {str(shape):20s} axis={axis}: " + " | ".join(res), flush=True)
+        del ts
+
+if "unaligned" in what:
+    # operands TMA cannot describe are staged (one copy pass) and run on the tensor cores: K = 4097 against K = 4096
+    print("bf16 4096 x 4096 x K, lhs [M,K] row-major (row pitch 2K bytes), rhs [K,N] row-major:")
+    for k_ in (4096, 4097, 4104):
+        a = TensorHandle.empty_contiguous(c, [4096, k_], "bf16")
+        b = TensorHandle.empty_contiguous(c, [k_, 4096], "bf16")
+        o = TensorHandle.empty_contiguous(c, [4096, 4096], "bf16")
+        c.fill_uniform(a.handle, "bf16", 4096 * k_, 3, -1.0, 1.0)
+        c.fill_uniform(b.handle, "bf16", 4096 * k_, 4, -1.0, 1.0)
+        l0 = c.launch_count()
+        matmul.launch(c, a, b, o)
+        launches = c.launch_count() - l0
+        ms = min(time_ms(c, lambda: matmul.launch(c, a, b, o), iters=20, warm=3) for _ in range(3))
+        print(f"  K={k_}: {ms * 1e3:8.1f} us  {2.0 * 4096 * 4096 * k_ / ms / 1e9:7.0f} TFLOP/s  launches={launches}  last kernel {c.last_kernel()}", flush=True)
+        del a, b, o
+
 if "probes" in what:
     scratch = c.empty(1024)
     for dt in ("f16", "bf16"):

@@ -14,6 +14,20 @@ if what == "reduce_rows":
     out = TensorHandle.empty_contiguous(c, [8192], "f32")
     for i in range(iters):
         reduce.launch(c, t, out, 1, "sum")
+elif what == "reduce_cols":
+    t = TensorHandle.empty_contiguous(c, [8192, 8192], "f32")
+    c.fill_uniform(t.handle, "f32", 8192 * 8192, 5, 0.0, 1.0)
+    out = TensorHandle.empty_contiguous(c, [8192], "f32")
+    for i in range(iters):
+        reduce.launch(c, t, out, 0, "sum")
+elif what == "argmax":
+    n = 1 << 28
+    xs = [TensorHandle.empty_contiguous(c, [n], "f32") for _ in range(2)]
+    for i, x in enumerate(xs):
+        c.fill_uniform(x.handle, "f32", n, 5 + i, 0.0, 1.0)
+    out = TensorHandle.empty_contiguous(c, [1], "u32")
+    for i in range(iters):
+        reduce.launch(c, xs[i % 2], out, None, "argmax")
 elif what == "reduce":
     n = 1 << 28
     xs = [TensorHandle.empty_contiguous(c, [n], "f32") for _ in range(2)]
