@@ -529,7 +529,7 @@ extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) 
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
   static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "gemm.stage", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm", "reduce.rows_vpt", "reduce.rows_blocks_per_sm", "reduce.cols_blocks_per_sm",
-                                "reduce.debug", "reduce.pdl", "reduce.tma_stages", "reduce.tma_ctas_per_sm", "reduce.cols_split_target"};
+                                "reduce.debug", "reduce.pdl", "reduce.tma_stages", "reduce.tma_ctas_per_sm", "reduce.cols_split_target", "reduce.cols_loads", "reduce.cols_fused"};
   for (const char* k : known)
     if (!strcmp(k, key)) { c->options[key] = value; return B200_OK; }
   return fail(B200_ERR_INVALID_ARG, "unknown option '%s'", key);
@@ -1651,7 +1651,8 @@ static int launch_reduce_all(b200_ctx* c, CUstream st, int op, int dt, const RVi
 }
 
 // One launch of the rows kernel: items = outer x nseg, item (o, s) covers elements [s * seg_len, ..) of row o.
-static int launch_rows_kernel(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t seg_len, uint64_t out, uint64_t out2, float scale) {
+static int launch_rows_kernel(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t seg_len, uint64_t out, uint64_t out2, float scale,
+                              bool pdl = false) {
   const std::string name = std::string("reduce_rows_") + op_tag(op) + "_" + dt_tag(dt);
   CUfunction f;
   int rc = get_func(c, name, &f);
@@ -1683,15 +1684,16 @@ static int launch_rows_kernel(b200_ctx* c, CUstream st, int op, int dt, const RV
   p.row_len = 1; p.row_pitch = 1;
   p.seg_len = seg_len; p.nseg = (uint32_t)nseg; p.scale = scale;
   void* args[] = {&p, &tpr_log2};
-  return launch(c, f, grid, 1, 1, threads, 0, 1, st, args);
+  return launch(c, f, grid, 1, 1, threads, 0, 1, st, args, pdl);
 }
 
 // One launch of the column kernel over the view (items = outer x nseg x column tiles).
 // `final_out` != 0 with a segmented axis: finish in the same launch when the (outer, column tile) tickets fit the workspace
 // (*fused = true), else the caller runs the second pass.
 static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RView& v, uint64_t seg_len, uint64_t out, uint64_t out2, float scale,
-                              uint64_t final_out = 0, bool* fused = nullptr) {
-  const std::string name = std::string("reduce_cols_") + op_tag(op) + "_" + dt_tag(dt);
+                              uint64_t final_out = 0, bool* fused = nullptr, bool pdl = false) {
+  const bool arg_op = (op == B200_REDUCE_ARGMAX || op == B200_REDUCE_ARGMIN);
+  const std::string name = std::string("reduce_cols_") + op_tag(op) + "_" + dt_tag(dt) + (opt(c, "reduce.cols_loads", arg_op ? "4" : "8") == "8" ? "_n8" : "");
   CUfunction f;
   int rc = get_func(c, name, &f);
   if (rc) return rc;
@@ -1722,7 +1724,7 @@ static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RV
   p.seg_len = seg_len; p.nseg = (uint32_t)nseg; p.ctu = (uint32_t)ctu; p.scale = scale;
   p.flags = vector ? 2u : 0u;
   if (fused) *fused = false;
-  if (final_out && nseg > 1 && v.outer * tiles <= kWsColTickets) {
+  if (final_out && nseg > 1 && v.outer * tiles <= kWsColTickets && opt(c, "reduce.cols_fused", "off") == "on") {
     CUdeviceptr ws;
     rc = reduce_workspace(c, st, &ws);
     if (rc) return rc;
@@ -1730,7 +1732,7 @@ static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RV
     if (fused) *fused = true;
   }
   void* args[] = {&p};
-  return launch(c, f, grid, 1, 1, 256, 0, 1, st, args);
+  return launch(c, f, grid, 1, 1, 256, 0, 1, st, args, pdl);
 }
 
 static int launch_argcombine(b200_ctx* c, CUstream st, uint64_t keys, uint64_t idx, uint64_t out, uint64_t outer, uint64_t nseg, uint64_t inner) {
@@ -1765,8 +1767,13 @@ static int reduce_axis_view(b200_ctx* c, CUstream st, int op, int dt, const RVie
     const uint64_t tiles = ceil_div(units, std::min<uint64_t>(units, 32));
     const unsigned bps = opt_uint(c, "reduce.cols_blocks_per_sm", 4, 1, 64);
     if (v.outer * tiles < sms * bps && v.len >= 256) {
-      const uint64_t target = sms * opt_uint(c, "reduce.cols_split_target", 16, 1, 256);   // blocks aimed at when an axis is segmented
-      const uint64_t nseg = std::min<uint64_t>(ceil_div(target, v.outer * tiles), v.len / 64);
+      // ~8 blocks per SM (two resident waves of big blocks) measured best on average for value ops (eight loads in flight per
+      // thread) and arg ops (four) alike -- profiles/r02_cols_sweep.log.  Target 0: exactly one resident wave (4 blocks per SM).
+      const unsigned tgt = opt_uint(c, "reduce.cols_split_target", 8, 0, 256);
+      uint64_t nseg;
+      if (tgt == 0) nseg = std::max<uint64_t>(1, (sms * 4) / (v.outer * tiles));
+      else nseg = ceil_div(sms * tgt, v.outer * tiles);
+      nseg = std::min<uint64_t>(nseg, v.len / 64);
       if (nseg > 1) seg_len = ceil_div(v.len, nseg);
     }
   }
@@ -1794,7 +1801,11 @@ static int reduce_axis_view(b200_ctx* c, CUstream st, int op, int dt, const RVie
       RView t;
       t.in = tmp; t.outer = v.outer; t.len = nseg; t.inner = v.inner;
       t.s_outer = nseg * v.inner; t.s_len = v.inner; t.row_len = v.inner; t.row_pitch = v.inner;
-      rc = v.inner == 1 ? launch_rows_kernel(c, st, op, B200_F32, t, nseg, out, 0, scale) : launch_cols_kernel(c, st, op, B200_F32, t, nseg, out, 0, scale);
+      // the second pass only depends on the first: launched with programmatic serialization, its blocks are resident (and
+      // past their prologue) when the first pass drains; they wait in griddepcontrol.wait
+      const bool pdl = opt(c, "reduce.pdl", "on") == "on";
+      rc = v.inner == 1 ? launch_rows_kernel(c, st, op, B200_F32, t, nseg, out, 0, scale, pdl)
+                        : launch_cols_kernel(c, st, op, B200_F32, t, nseg, out, 0, scale, 0, nullptr, pdl);
     }
   }
   pool_free(c, tmp, st);

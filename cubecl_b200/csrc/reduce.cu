@@ -739,6 +739,7 @@ __device__ __forceinline__ void reduce_rows_body(const ReduceParams& p, int tpr_
   constexpr int VEC = E::VEC;
   __shared__ float s_red[kMaxWarps];
   __shared__ uint64_t s_red64[kMaxWarps];
+  pdl_wait();   // second pass of a split reduction: wait for the first pass's partials (no-op otherwise)
   const uint32_t tpr = 1u << tpr_log2;
   const uint32_t rows_per_block = blockDim.x >> tpr_log2;
   const uint32_t sub = threadIdx.x >> tpr_log2;  // which item of this block pass
@@ -886,7 +887,7 @@ __device__ __forceinline__ void reduce_rows_body(const ReduceParams& p, int tpr_
 // Few columns with a long axis: small ctu -> many row lanes.  Many columns with a short axis: ctu = blockDim, one row lane.
 constexpr int kColsThreads = 256;
 
-template <int OP, int DT, bool VECTOR>
+template <int OP, int DT, bool VECTOR, int NL /* loads in flight per thread */>
 __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_t* s_raw) {
   using E = Elem<DT>;
   using T = typename E::T;
@@ -918,13 +919,11 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
     const char* cb = base + (o * p.s_outer + l0 * p.s_len + ioff) * sizeof(T);
     const uint64_t lstep = p.s_len * sizeof(T);
 
-    // eight loads in flight per thread (at ~62 registers four blocks share an SM: 128 KB of loads in flight per SM), folded
-    // into two accumulator sets
-    constexpr int NL = 8;
-    float a[2][UV];
+    // NL loads in flight per thread, folded into four accumulator sets
+    float a[4][UV];
     ArgAcc cand[UV];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int j = 0; j < UV; ++j) a[u][j] = ValOp<OP>::identity();
     if (valid) {
@@ -946,7 +945,7 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
 #pragma unroll
           for (int j = 0; j < UV; ++j) {
             if constexpr (ARG) cand[j].feed<OP>(f[u][j], static_cast<uint32_t>(l0 + l + static_cast<uint64_t>(u) * RL));
-            else a[u & 1][j] = ValOp<OP>::apply(a[u & 1][j], f[u][j]);
+            else a[u & 3][j] = ValOp<OP>::apply(a[u & 3][j], f[u][j]);
           }
       }
       for (; l < L; l += RL) {
@@ -964,7 +963,7 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
     uint64_t resp[UV];
 #pragma unroll
     for (int j = 0; j < UV; ++j) {
-      res[j] = ValOp<OP>::apply(a[0][j], a[1][j]);
+      res[j] = ValOp<OP>::apply(ValOp<OP>::apply(a[0][j], a[1][j]), ValOp<OP>::apply(a[2][j], a[3][j]));
       resp[j] = cand[j].packed();
     }
     // combine the row lanes of each unit through shared memory: slot (rl, cu) at [threadIdx.x * UV + j]; lanes that found
@@ -1054,17 +1053,18 @@ __device__ __forceinline__ void reduce_cols_tiles(const ReduceParams& p, uint64_
   }
 }
 
-template <int OP, int DT>
+template <int OP, int DT, int NL>
 __device__ __forceinline__ void reduce_cols_body(const ReduceParams& p) {
   using E = Elem<DT>;
   using T = typename E::T;
   __shared__ uint64_t s_raw[kColsThreads * E::VEC];
+  pdl_wait();   // second pass of a split reduction launched with programmatic serialization: the partials must be complete
   const uint64_t esz = sizeof(T);
   const bool vec_ok = (p.flags & 2u) != 0 &&  // the host sized ctu for vector units
                       (p.inner % E::VEC) == 0 && (p.row_len % E::VEC) == 0 && (p.in % 16) == 0 && ((p.s_len * esz) % 16) == 0 &&
                       ((p.s_outer * esz) % 16) == 0 && ((p.row_pitch * esz) % 16) == 0;
-  if (vec_ok) reduce_cols_tiles<OP, DT, true>(p, s_raw);
-  else reduce_cols_tiles<OP, DT, false>(p, s_raw);
+  if (vec_ok) reduce_cols_tiles<OP, DT, true, NL>(p, s_raw);
+  else reduce_cols_tiles<OP, DT, false, NL>(p, s_raw);
 }
 
 // ================================================================================================ second pass of a split arg-reduction
@@ -1125,9 +1125,12 @@ extern "C" __global__ void __launch_bounds__(256) reduce_argcombine(const __grid
   extern "C" __global__ void __launch_bounds__(512) NAME(const __grid_constant__ ReduceParams p, int tpr_log2) {    \
     reduce_rows_body<OP, DT>(p, tpr_log2);                                                                          \
   }
-#define REDUCE_COLS(NAME, OP, DT)                                                                           \
-  extern "C" __global__ void __launch_bounds__(kColsThreads) NAME(const __grid_constant__ ReduceParams p) {  \
-    reduce_cols_body<OP, DT>(p);                                                                            \
+#define REDUCE_COLS(NAME, OP, DT)                                                                                 \
+  extern "C" __global__ void __launch_bounds__(kColsThreads) NAME(const __grid_constant__ ReduceParams p) {        \
+    reduce_cols_body<OP, DT, 4>(p);                                                                               \
+  }                                                                                                               \
+  extern "C" __global__ void __launch_bounds__(kColsThreads) NAME##_n8(const __grid_constant__ ReduceParams p) {   \
+    reduce_cols_body<OP, DT, 8>(p);                                                                               \
   }
 
 #define ALL_SHAPES(OPN, OP, DTN, DT)                                                \

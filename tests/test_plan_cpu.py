@@ -280,20 +280,25 @@ def test_reduce_plans(plan):
     assert t.count("alloc") == 2
     rc, t = plan.reduce(MEAN, F16, [64, 256, 1024], 1)                     # middle axis -> columns kernel
     assert "reduce_cols_sum_f16" in t
-    rc, t = plan.reduce(SUM, F32, [8192, 8192], 0)                         # outer axis, few outputs: segments of the axis, finished
-    assert t.count("launch reduce_cols_sum_f32") == 1 and "grid=(2368,1,1)" in t   # in the same launch (ticket per column tile)
-    rc, t = plan.reduce(ARGMAX, F32, [1 << 20, 8], 0)                      # arg ops too: (key, index) partials, fused finish
-    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["reduce_cols_argmax_f32"] and t.count("alloc") == 2
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 0)                         # outer axis, few outputs: 19 segments of the axis (8 blocks
+    lines = [ln for ln in t.splitlines() if ln.startswith("launch")]      # per SM), then the partials -- a dependent launch (PDL)
+    assert len(lines) == 2 and "reduce_cols_sum_f32_n8 grid=(1216,1,1)" in lines[0] and lines[1].endswith(" pdl")
+    plan.option("reduce.cols_fused", "on")                                 # alternative: the last block of a column tile finishes it
+    rc, t = plan.reduce(SUM, F32, [8192, 8192], 0)
+    assert t.count("launch") == 1
+    plan.option("reduce.cols_fused", "off")
+    rc, t = plan.reduce(ARGMAX, F32, [1 << 20, 8], 0)                      # arg ops too: (key, index) partials + combine, four loads in flight
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["reduce_cols_argmax_f32", "reduce_argcombine"] and t.count("alloc") == 2
     rc, t = plan.reduce(SUM, F32, [4, 1 << 26], 0)                         # short axis, many columns: persistent grid, one launch
-    assert t.strip() == "launch reduce_cols_sum_f32 grid=(1184,1,1) block=256 smem=0 cluster=1"
+    assert t.strip() == "launch reduce_cols_sum_f32_n8 grid=(1184,1,1) block=256 smem=0 cluster=1"
     # views reduced in place (1x the logical bytes): pitched rows on every axis, transposed views, a permuted rank-3 view
-    for axis, kernel in ((1, "reduce_rows_sum_f32"), (0, "reduce_cols_sum_f32"), (-1, "reduce_allp_sum_f32")):
+    for axis, kernel in ((1, "reduce_rows_sum_f32"), (0, "reduce_cols_sum_f32_n8"), (-1, "reduce_allp_sum_f32")):
         rc, t = plan.reduce(SUM, F32, [100, 72], axis, strides=[128, 1])
         assert rc == 0 and [ln.split()[1] for ln in t.splitlines()] == [kernel], (axis, t)
     rc, t = plan.reduce(ARGMAX, F32, [100, 72], -1, strides=[128, 1])
     assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_allp_argmax_f32"]
     rc, t = plan.reduce(SUM, F32, [72, 100], 1, strides=[1, 72])           # x.T over its last axis = x over axis 0
-    assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_cols_sum_f32"]
+    assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_cols_sum_f32_n8"]
     rc, t = plan.reduce(SUM, F32, [72, 100], 0, strides=[1, 72])
     assert [ln.split()[1] for ln in t.splitlines()] == ["reduce_rows_sum_f32"]
     rc, t = plan.reduce(SUM, F32, [3, 5, 7], 1, strides=[35, 1, 5])        # reduced axis innermost in memory, kept axes in order
@@ -303,7 +308,7 @@ def test_reduce_plans(plan):
     rc, t = plan.reduce(ARGMAX, F32, [72, 100], -1, strides=[1, 72])
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_all_argmax_f32"]
     rc, t = plan.reduce(SUM, F32, [3, 5, 7], 0, strides=[70, 14, 2])
-    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_cols_sum_f32"]
+    assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gather_strided", "reduce_cols_sum_f32_n8"]
     plan.option("reduce.variant", "tma")                                   # forced: used from 1 MB up
     rc, t = plan.reduce(SUM, BF16, [1 << 20], -1)
     assert t.strip() == "launch reduce_all_sum_bf16_tma grid=(128,1,1) block=288 smem=98432 cluster=1"

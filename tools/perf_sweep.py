@@ -247,12 +247,12 @@ if "cols" in what:
                 k[0] += 1
                 reduce.launch(c, ts[k[0] % copies], out, axis, op)
             res = []
-            for target in (4, 8, 16, 32, 64):
+            for target in (0, 4, 8, 12, 16):
                 c.set_option("reduce.cols_split_target", target)
-                best = min(time_ms(c, run, iters=20, warm=3) for _ in range(5))
-                res.append(f"{target}: {best * 1e3:7.1f} us {nbytes / best / 1e6:7.1f}")
-            c.set_option("reduce.cols_split_target", 16)
-            print(f"  {op:6s} {str(shape):20s} axis={axis}: " + " | ".join(res), flush=True)
+                best = min(time_ms(c, run, iters=20, warm=3) for _ in range(4))
+                res.append(f"t{target}:{best * 1e3:6.1f}us/{nbytes / best / 1e6:5.0f}")
+            c.set_option("reduce.cols_split_target", "")
+            print(f"  {op:6s} {str(shape):20s} axis={axis}: " + " ".join(res), flush=True)
         del ts
 
 if "unaligned" in what:
