@@ -330,6 +330,8 @@ def all_ranks_ok(ok: bool, dist, tdev) -> bool:
 
 # ---------------------------------------------------------------------------------------------------- our arm
 def main():
+    import faulthandler
+    faulthandler.enable()                # a native fault in any rank leaves a Python stack on stderr instead of a bare signal
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

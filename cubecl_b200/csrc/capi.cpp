@@ -318,6 +318,7 @@ struct b200_ctx {
   uint64_t bytes_in_use = 0, bytes_reserved = 0;
   std::unordered_map<void*, size_t> pinned;
   std::unordered_map<CUstream, CUdeviceptr> reduce_ws;
+  std::vector<CUstream> dead_streams;   // streams destroyed through b200_stream_destroy (drained there): never record on them again
   std::map<std::string, CUtensorMap> tmap_cache;
   std::map<std::vector<int>, CommState> comms;
   std::map<std::vector<int>, P2PState> p2p;
@@ -613,6 +614,8 @@ static int pool_free(b200_ctx* c, CUdeviceptr p, CUstream used_on = nullptr) {
   if (it == c->blocks.end() || !it->second.in_use) return fail(B200_ERR_INVALID_ARG, "b200_free: pointer not owned by this context");
   PoolBlock& b = it->second;
   b.in_use = false;
+  // a stream this context already destroyed was synchronised at that point: the page is idle as far as it is concerned
+  if (used_on && std::find(c->dead_streams.begin(), c->dead_streams.end(), used_on) != c->dead_streams.end()) used_on = nullptr;
   b.last_stream = used_on ? used_on : c->stream;
   if (!b.done && g_drv.cuEventCreate_p(&b.done, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) b.done = nullptr;
   b.pending = (b.done != nullptr) && g_drv.cuEventRecord_p(b.done, b.last_stream) == CUDA_SUCCESS;
@@ -719,6 +722,7 @@ extern "C" int b200_stream_create(b200_ctx* c, b200_stream* out) {
   if (!out) return fail(B200_ERR_INVALID_ARG, "null out");
   CUstream s;
   CU_CHECK(g_drv.cuStreamCreate_p(&s, CU_STREAM_NON_BLOCKING));
+  c->dead_streams.erase(std::remove(c->dead_streams.begin(), c->dead_streams.end(), s), c->dead_streams.end());  // the handle value may be recycled
   *out = s;
   return B200_OK;
 }
@@ -732,6 +736,7 @@ extern "C" int b200_stream_destroy(b200_ctx* c, b200_stream s) {
   auto it = c->reduce_ws.find(static_cast<CUstream>(s));
   if (it != c->reduce_ws.end()) { g_drv.cuMemFree_p(it->second); c->reduce_ws.erase(it); }
   CU_CHECK(g_drv.cuStreamDestroy_p(static_cast<CUstream>(s)));
+  c->dead_streams.push_back(static_cast<CUstream>(s));
   return B200_OK;
 }
 

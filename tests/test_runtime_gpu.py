@@ -78,6 +78,36 @@ def test_pool_holds_back_pages_that_are_still_in_flight(client):
     client.memory_cleanup()
 
 
+def test_buffer_freed_after_its_stream_was_destroyed(client):
+    # a handle remembers the non-default stream it was used on and is freed in that stream's order (b200_free_async); if the
+    # stream is gone by then (destroyed = drained), the free must fall back to the context's stream, not touch the dead handle
+    s = client.create_stream()
+    h = client.empty(1 << 20)
+    host = client.host_alloc(1 << 20)
+    client.write_async(h, host, stream=s)
+    assert h.last_stream is s
+    client.destroy_stream(s)
+    ptr = h.ptr
+    del h                                           # used to record an event on the destroyed stream (a host-side fault)
+    client.sync()
+    again = client.empty(1 << 20)
+    assert again.ptr == ptr                         # and the page is immediately reusable: the destroy drained the stream
+    client.host_free(host)
+    s2 = client.create_stream()                     # a live stream: the page is held back until that stream's event completes
+    big = client.empty(1 << 28)
+    for _ in range(4):
+        client._lib.b200_fill_uniform(client._ctx, s2, 0, __import__("ctypes").c_uint64(big.ptr), 1 << 26, 1, 0.0, 1.0)
+    big.used_on(s2)
+    p2 = big.ptr
+    del big
+    other = client.empty(1 << 28)
+    assert other.ptr != p2                          # still in flight on s2
+    client.sync_stream(s2)
+    client.destroy_stream(s2)
+    del other
+    client.memory_cleanup()
+
+
 def test_pooled_handles_are_recycled_per_size_class(client):
     before = client.memory_usage()
     hs = [client.empty(3 << 20) for _ in range(4)]
