@@ -224,7 +224,7 @@ def run_reference(args):
                        "note": "reference = CPU restatement of cubecl's semantics (oracle port); the Rust reference cannot be built here"},
             "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------- parity on the record
@@ -329,6 +329,18 @@ def all_ranks_ok(ok: bool, dist, tdev) -> bool:
 
 
 # ---------------------------------------------------------------------------------------------------- our arm
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# stdout carries exactly one JSON line.  Libraries loaded later (NCCL's version banner under NCCL_DEBUG=VERSION, seen on the
+# 2-GPU box) print to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the line goes
+# to a private duplicate of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     import faulthandler
     faulthandler.enable()                # a native fault in any rank leaves a Python stack on stderr instead of a bare signal
@@ -785,7 +797,7 @@ def main():
     except Exception as ex:  # noqa: BLE001  (a fault in a secondary row must not cost the measured headline)
         line["final_sync_error"] = repr(ex)
     if rank0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
