@@ -513,29 +513,41 @@ def main():
     if world > 1:
         # Why e2e scales worse than the kernel: the step is PCIe-bound (256 MiB in + 128 MiB out per GPU per step), and the
         # GPUs of a box share host memory / root complexes.  One rank copying alone vs every rank at once says how much.
-        def h2d_ms(reps=3):
-            c.sync_stream(s_h2d)
-            e0, e1 = c.event(), c.event()
-            c.record(e0, s_h2d)
+        def copy_ms(h2d=True, d2h=False, reps=3):
+            """device time of `reps` x (256 MiB H2D on one stream and / or 128 MiB D2H on the other, concurrently)"""
+            c.sync_stream(s_h2d); c.sync_stream(s_d2h)
+            evs = [c.event() for _ in range(4)]
+            c.record(evs[0], s_h2d); c.record(evs[2], s_d2h)
             for _ in range(reps):
-                c.write_async(slots[0][0], hab, stream=s_h2d)
-            c.record(e1, s_h2d)
-            t = c.elapsed_ms(e0, e1) / reps
-            c.event_destroy(e0); c.event_destroy(e1)
+                if h2d:
+                    c.write_async(slots[0][0], hab, stream=s_h2d)
+                if d2h:
+                    c.read_async(hc, slots[0][3].handle, stream=s_d2h)
+            c.record(evs[1], s_h2d); c.record(evs[3], s_d2h)
+            t = max(c.elapsed_ms(evs[0], evs[1]), c.elapsed_ms(evs[2], evs[3])) / reps
+            for e_ in evs:
+                c.event_destroy(e_)
             return t
 
-        solo = 0.0
+        solo = duplex_solo = 0.0
         for r in range(world):
             barrier()
             if e.rank == r:
-                solo = h2d_ms()
+                solo = copy_ms(True, False)
+                duplex_solo = copy_ms(True, True)
         barrier()
-        conc = h2d_ms()
+        conc = copy_ms(True, False)
         barrier()
-        solo_worst, conc_worst = D.max_over_ranks(solo, dist, tdev), D.max_over_ranks(conc, dist, tdev)
-        line["e2e"]["pcie"] = {"h2d_gbs_one_rank_at_a_time": 2 * nbytes / (solo_worst * 1e-3) / 1e9,
-                               "h2d_gbs_all_ranks_at_once": 2 * nbytes / (conc_worst * 1e-3) / 1e9,
-                               "note": "slowest rank, pinned NUMA-local host buffers; the per-GPU e2e step cannot beat (H2D + D2H bytes) / this rate"}
+        duplex = copy_ms(True, True)
+        barrier()
+        mx = lambda v: D.max_over_ranks(v, dist, tdev)  # noqa: E731
+        solo, conc, duplex_solo, duplex = mx(solo), mx(conc), mx(duplex_solo), mx(duplex)
+        line["e2e"]["pcie"] = {"h2d_gbs_one_rank_at_a_time": 2 * nbytes / (solo * 1e-3) / 1e9,
+                               "h2d_gbs_all_ranks_at_once": 2 * nbytes / (conc * 1e-3) / 1e9,
+                               "h2d_plus_d2h_ms_one_rank_at_a_time": duplex_solo, "h2d_plus_d2h_ms_all_ranks_at_once": duplex,
+                               "note": "slowest rank, pinned NUMA-local host buffers.  A pipelined e2e step cannot be shorter than the "
+                                       "concurrent 256 MiB H2D + 128 MiB D2H of one step (h2d_plus_d2h_ms_*): when every GPU of the box copies "
+                                       "in both directions at once the host side (memory / root complexes) is the limiter, not the kernels"}
     c.destroy_stream(s_h2d); c.destroy_stream(s_d2h)
     del slots
     for h in (hab, hc):
