@@ -141,6 +141,14 @@ impl Context {
         check(unsafe { sys::b200_set_option(self.0, k.as_ptr(), v.as_ptr()) })
     }
 
+    /// Entry-point name of the kernel this context launched most recently (what a harness reports as the kernel it timed).
+    pub fn last_kernel(&self) -> Result<String, Error> {
+        let mut buf = [0u8; 256];
+        check(unsafe { sys::b200_last_kernel(self.0, buf.as_mut_ptr() as *mut core::ffi::c_char, buf.len()) })?;
+        let end = buf.iter().position(|&b| b == 0).unwrap_or(buf.len());
+        Ok(String::from_utf8_lossy(&buf[..end]).into_owned())
+    }
+
     pub fn launch_count(&self) -> Result<u64, Error> {
         let mut n = 0u64;
         check(unsafe { sys::b200_launch_count(self.0, &mut n) })?;
@@ -158,6 +166,15 @@ impl Context {
     /// `ptr` must come from [`Context::alloc`] on this context and must not be used by work enqueued after this call.
     pub unsafe fn free(&mut self, ptr: b200_dptr) -> Result<(), Error> {
         check(sys::b200_free(self.0, ptr))
+    }
+
+    /// Frees in the order of `last_use`, the stream whose queued work may still touch the buffer (null = the context's
+    /// stream): the pool re-issues the page only once an event recorded there has completed.
+    ///
+    /// # Safety
+    /// Same contract as [`Context::free`].
+    pub unsafe fn free_async(&mut self, ptr: b200_dptr, last_use: b200_stream) -> Result<(), Error> {
+        check(sys::b200_free_async(self.0, ptr, last_use))
     }
 
     /// Stream-ordered host -> device copy; asynchronous when `src` is pinned (sync before reusing it).
@@ -242,6 +259,25 @@ impl Context {
         check(sys::b200_matmul(
             self.0, stream, in_dtype as c_int, out_dtype as c_int, lhs.ptr, rhs.ptr, out.ptr, rank as c_int,
             lhs.shape.as_ptr(), lhs.strides.as_ptr(), rhs.shape.as_ptr(), rhs.strides.as_ptr(),
+            out.shape.as_ptr(), out.strides.as_ptr(),
+        ))
+    }
+
+    /// The same product with different 8-bit formats per operand (i8 x u8, e4m3 x e5m2 ...: the reference's manual-MMA
+    /// pairs, crates/cubecl-cpp/src/cuda/mma/manual.rs:151-186).
+    ///
+    /// # Safety
+    /// Same contract as [`Context::matmul`].
+    pub unsafe fn matmul_mixed(
+        &mut self, stream: b200_stream, lhs_dtype: DType, rhs_dtype: DType, out_dtype: DType,
+        lhs: &TensorView, rhs: &TensorView, out: &TensorView,
+    ) -> Result<(), Error> {
+        let rank = lhs.shape.len();
+        assert!(rhs.shape.len() == rank && out.shape.len() == rank);
+        assert!(lhs.strides.len() == rank && rhs.strides.len() == rank && out.strides.len() == rank);
+        check(sys::b200_matmul_mixed(
+            self.0, stream, lhs_dtype as c_int, rhs_dtype as c_int, out_dtype as c_int, lhs.ptr, rhs.ptr, out.ptr,
+            rank as c_int, lhs.shape.as_ptr(), lhs.strides.as_ptr(), rhs.shape.as_ptr(), rhs.strides.as_ptr(),
             out.shape.as_ptr(), out.strides.as_ptr(),
         ))
     }

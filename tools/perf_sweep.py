@@ -228,6 +228,46 @@ if "axis" in what:
             print(f"  {op:6s} {str(shape):22s} axis={axis} launches={launches} x{copies} buffers: " + "  |  ".join(res), flush=True)
             del ts, out
 
+if "variants" in what:
+    # validation of the static tile-variant choice: every tcgen05 variant forced against `auto`, interleaved rounds, over a
+    # spread of shapes (the efficiency table the host uses was measured at 8192^3 only)
+    import time as _time
+    print("tile variants vs auto (bf16 -> bf16 unless noted), min over 4 interleaved rounds of 10 launches; TFLOP/s:")
+    cases = ((8192, 8192, 8192, 1, "bf16", "bf16"), (4096, 4096, 4096, 1, "bf16", "bf16"), (6144, 6144, 6144, 1, "bf16", "bf16"),
+             (5120, 5120, 5120, 1, "bf16", "bf16"), (3072, 3072, 3072, 1, "bf16", "bf16"), (2048, 2048, 2048, 1, "bf16", "bf16"),
+             (1024, 1024, 8192, 1, "bf16", "bf16"), (512, 512, 16384, 1, "bf16", "bf16"), (8192, 1024, 4096, 1, "bf16", "bf16"),
+             (1024, 8192, 4096, 1, "bf16", "bf16"), (16384, 4096, 1024, 1, "bf16", "bf16"), (4096, 4096, 4096, 8, "bf16", "bf16"),
+             (2048, 2048, 2048, 16, "bf16", "bf16"), (4096, 4096, 4096, 1, "bf16", "f32"), (8192, 8192, 8192, 1, "f8e4m3", "bf16"),
+             (4096, 4096, 4096, 1, "f8e4m3", "bf16"), (4096, 4096, 4096, 1, "f16", "f16"))
+    worst = 1.0
+    for (m, n, k, batch, idt, odt) in cases:
+        sa = [batch, m, k] if batch > 1 else [m, k]
+        sb = [batch, k, n] if batch > 1 else [k, n]
+        so = [batch, m, n] if batch > 1 else [m, n]
+        a = TensorHandle.empty_contiguous(c, sa, idt)
+        b = TensorHandle.empty_contiguous(c, sb, idt)
+        o = TensorHandle.empty_contiguous(c, so, odt)
+        c.fill_uniform(a.handle, idt, int(np.prod(sa)), 3, -1.0, 1.0)
+        c.fill_uniform(b.handle, idt, int(np.prod(sb)), 4, -1.0, 1.0)
+        flops = 2.0 * m * n * k * batch
+        opts = ["auto", "2sm_n256", "1sm_n128"] + (["2sm_m512"] if odt != "f32" else []) + (["2sm_n128"] if not idt.startswith("f8") else [])
+        best = {v: float("inf") for v in opts}
+        picked = ""
+        for rnd in range(4):
+            for v in (opts if rnd % 2 == 0 else opts[::-1]):
+                c.set_option("gemm.variant", v)
+                _time.sleep(0.03)
+                best[v] = min(best[v], time_ms(c, lambda: matmul.launch(c, a, b, o), iters=10, warm=2))
+                if v == "auto":
+                    picked = c.last_kernel()
+        c.set_option("gemm.variant", "auto")
+        fastest = min(best[v] for v in opts if v != "auto")
+        worst = min(worst, fastest / best["auto"])
+        print(f"  {idt}->{odt} {batch}x{m}x{n}x{k}: " + "  ".join(f"{v}={flops / best[v] / 1e9:6.0f}" for v in opts) +
+              f"  | auto/best={fastest / best['auto']:.3f} ({picked})", flush=True)
+        del a, b, o
+    print(f"  worst auto/best over the sweep: {worst:.3f}")
+
 if "cols" in what:
     # column (outer-axis) reductions: how many blocks a segmented axis should aim at (reduce.cols_split_target x SMs)
     print("column reductions, GB/s = (input + output bytes) / time, min of 5 x 20 launches:")
