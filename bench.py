@@ -581,7 +581,10 @@ def main():
                                "traffic": traffic.get("reduce_sum_2p28_dram_bytes"),
                                "traffic_source": "static: committed ncu --set full capture (profiles/traffic.json)",
                                "peak_source": pk["source"] + " (copy, read+write)",
-                               "kernel": red_kernel, "algorithmic_bytes_per_launch": BYTES_RED}
+                               "kernel": red_kernel, "algorithmic_bytes_per_launch": BYTES_RED,
+                               "note": "3 rotating 1 GiB inputs (nothing served from L2); consecutive launches on the stream overlap through "
+                                       "programmatic dependent launch (the next launch streams while this one's last block finishes) -- "
+                                       "reduce.pdl=off costs ~3 us per launch"}
     # argmax over the same 2^28 elements (north star: bit-exact argmax indices): its own roofline, same bytes
     a_out = TensorHandle.empty_contiguous(c, [1], "u32")
 
