@@ -139,6 +139,10 @@ extern "C" __global__ void __launch_bounds__(256) gemm_simt_strided(const __grid
 struct PackScalesParams {
   uint64_t in, out;
   uint32_t batch, rows, n_scales, tiles, atoms, pad_value;  // pad_value: the scale byte that means 1.0 (127 ue8m0, 0x38 ue4m3)
+  // `tiles` counts 128-row CHUNKS per batch entry.  A GEMM tile of `tile_rows` rows owns `chunks_per_tile` consecutive chunks
+  // (128 / 1: the plain layout; 224 / 2 for the 256 x 224 variant: chunk 2t holds rows [224 t, 224 t + 128), chunk 2t + 1 rows
+  // [224 t + 128, 224 t + 224) and padding), so a tile's 32-row groups always start a chunk.
+  uint32_t tile_rows, chunks_per_tile;
 };
 
 extern "C" __global__ void __launch_bounds__(256) pack_scales(const __grid_constant__ PackScalesParams p) {
@@ -152,12 +156,14 @@ extern "C" __global__ void __launch_bounds__(256) pack_scales(const __grid_const
     const uint64_t bt = chunk / p.atoms;
     const uint32_t tile = static_cast<uint32_t>(bt % p.tiles), b = static_cast<uint32_t>(bt / p.tiles);
     const uint32_t r32 = in_chunk / 4, g = in_chunk % 4;
-    const uint32_t row = tile * 128 + g * 32 + r32;
+    const uint32_t local = (tile % p.chunks_per_tile) * 128 + g * 32 + r32;      // row inside the GEMM tile
+    const uint32_t row = (tile / p.chunks_per_tile) * p.tile_rows + local;
+    const bool in_tile = local < p.tile_rows;
     uint32_t word = 0;
 #pragma unroll
     for (uint32_t sidx = 0; sidx < 4; ++sidx) {
       const uint32_t ks = atom * 4 + sidx;
-      const uint32_t v = (row < p.rows && ks < p.n_scales) ? in[(static_cast<uint64_t>(b) * p.rows + row) * p.n_scales + ks] : p.pad_value;
+      const uint32_t v = (in_tile && row < p.rows && ks < p.n_scales) ? in[(static_cast<uint64_t>(b) * p.rows + row) * p.n_scales + ks] : p.pad_value;
       word |= v << (8 * sidx);
     }
     out[w] = word;

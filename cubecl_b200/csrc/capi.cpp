@@ -222,6 +222,7 @@ struct GemmParams {
 struct PackScalesParams {
   uint64_t in, out;
   uint32_t batch, rows, n_scales, tiles, atoms, pad_value;
+  uint32_t tile_rows, chunks_per_tile;
 };
 struct ScaledSimtParams {
   uint64_t a, b, sa, sb, out;
@@ -846,9 +847,14 @@ static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0, 1}, {"2sm_n
                                         // -> 1.53 instead of 1.45 GHz under the power cap), 0.98 of cuBLAS; fp8 e4m3 8192^3: x1.04
                                         // (3223 vs 3098 TFLOP/s, profiles/r01_bench_n1.json tile_variants_8192)
                                         {"2sm_m512", 2, 256, 4, 1.06, 2},
+                                        // block-scaled kinds only: 256 x 224 tile -- two accumulator stages and the scale columns fit
+                                        // the 512 TMEM columns, so the epilogue hides behind the next tile (the 256-wide scaled tiles
+                                        // hold ONE stage).  Needs the B scales packed per 224-row tile, i.e. row-major scales.
+                                        {"2sm_n224", 2, 224, 6, 1.05, 1},
                                         // diagnostic: 256 x 256 tile with ONE accumulator stage (bf16 -> bf16, K-major lhs only)
                                         {"2sm_n256a1", 2, 256, 6, 0.0, 1}};
 static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
+  if (!strcmp(v.tag, "2sm_n224")) return false;   // block-scaled kinds only
   const bool bits8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2 || in_dtype == B200_U8 || in_dtype == B200_I8);
   if (!strcmp(v.tag, "2sm_m512")) return in_dtype == B200_BF16 || in_dtype == B200_F16 || in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2;
   if (!strcmp(v.tag, "2sm_n256a1")) return in_dtype == B200_BF16;
@@ -860,10 +866,11 @@ static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
 static unsigned mx_atoms(int mx_kind) { return mx_kind == 3 ? 4u : (unsigned)mx_kind; }
 static unsigned gemm_sf_stage_bytes(const GemmVariant& v, int mx_kind) {
   if (!mx_kind) return 0;
-  const unsigned raw = 512u * mx_atoms(mx_kind) * (1 + v.block_n / 128);
+  const unsigned raw = 512u * mx_atoms(mx_kind) * (1 + (v.block_n + 127) / 128);
   return (raw + 1023u) / 1024u * 1024u;
 }
 static int gemm_stages(const GemmVariant& v, int mx_kind) {
+  if (v.block_n == 224) return mx_kind == 3 ? 5 : 6;                   // 36 KB / 32-33 KB stages
   if (mx_kind == 3) return v.block_n == 256 ? 5 : v.cg == 2 ? 7 : 5;   // 38 / 28 / 36 KB stages
   return (mx_kind == 2 && v.block_n == 256) ? 5 : v.stages;
 }
@@ -933,6 +940,8 @@ struct GemmProblem {
   uint32_t fmt_a = 0, fmt_b = 0;   // instruction-descriptor operand formats
   uint64_t sfa = 0, sfb = 0;       // packed scale tensors [batch * tiles][atoms][512 B]
   uint64_t sf_atoms = 0;           // 4-scale atoms along K
+  int sfb_tile_rows = 128;         // how the rhs scales are packed: per 128-row chunk, or per 224-row GEMM tile (2sm_n224 only)
+  bool sfb_any_layout = false;     // planning pass: the caller packs the scales AFTER the variant is known
 };
 
 static int launch_simt(b200_ctx* c, CUstream st, const GemmProblem& g) {
@@ -1043,16 +1052,11 @@ static SkPlan sk_plan(uint64_t tiles, uint64_t clusters, uint64_t num_kb, const 
   return pl;
 }
 
-static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
-  const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
-  const char* in_tag = g.mx_kind == 1 ? "mxf8" : g.mx_kind == 2 ? "mxf4" : g.mx_kind == 3 ? "nvf4"
-                       : g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
-                       : g.in_dtype == B200_F8E5M2 ? "e5m2" : g.in_dtype == B200_U8 ? "u8" : g.in_dtype == B200_I8 ? "s8" : "tf32";
-  const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : g.out_dtype == B200_I32 ? "i32" : "f32";
+// Tile variant by modelled time (ties -> larger tile, less L2 traffic): waves of tiles, with the last partial wave replaced by a
+// stream-K head where that pays (sk_plan).  nullptr: gemm.variant names no variant this dtype / kind has.
+static const GemmVariant* pick_variant(b200_ctx* c, const GemmProblem& g, SkPlan* sk_out) {
+  const size_t esz = dtype_size(g.in_dtype);
   const uint32_t block_k = static_cast<uint32_t>(128 / esz);
-
-  // pick the tile variant by modelled time (ties -> larger tile, less L2 traffic): waves of tiles, with the last partial wave
-  // replaced by a stream-K head where that pays (sk_plan)
   const std::string forced = opt(c, "gemm.variant", "auto");
   const std::string split_opt = opt(c, "gemm.split_k", "auto");
   const bool float_acc = !(g.in_dtype == B200_U8 || g.in_dtype == B200_I8);
@@ -1060,13 +1064,14 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   const uint64_t num_kb = ((g.K + block_k - 1) / block_k) * k_segments;
   const GemmVariant* best = nullptr;
   double best_cost = 0;
-  SkPlan best_sk;
   for (const GemmVariant& v : kVariants) {
     if (forced != "auto" && forced != v.tag) continue;
     if (forced == "auto" && v.eff <= 0.0) continue;
     if (!g.mx_kind && !variant_has_dtype(v, g.in_dtype)) continue;
     if (forced == "auto" && v.cg == 2 && g.M <= 128) continue;  // a CTA pair would idle its second half: one CTA per tile
     if (g.mx_kind && v.mt != 1) continue;                       // block-scaled kinds have no two-unit instantiation
+    if (v.block_n == 224 && !(g.mx_kind && (g.sfb_any_layout || g.sfb_tile_rows == 224))) continue;
+    if (v.block_n != 224 && g.mx_kind && !g.sfb_any_layout && g.sfb_tile_rows == 224) continue;   // scales already packed for 224-row tiles
     // the two-unit tile hides its epilogue only on the packed-register path (16-bit outputs); f32 outputs stay on 2sm_n256
     if (forced == "auto" && v.mt == 2 && !(g.out_dtype == B200_BF16 || g.out_dtype == B200_F16)) continue;
     const uint64_t tile_m = 128ull * v.cg * v.mt;
@@ -1079,8 +1084,22 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     // 0.63 / 0.66 for mxfp4 -- the same ordering as the unscaled table, so it is reused
     const double eff = v.eff > 0 ? v.eff : 1.0;
     const double cost = sk.time * (128.0 * v.mt * v.block_n) / eff;  // per-SM MMA time
-    if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; best_sk = sk; }
+    if (!best || cost < best_cost * 0.999) { best = &v; best_cost = cost; *sk_out = sk; }
   }
+  return best;
+}
+
+static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a_mn, bool b_mn) {
+  const size_t esz = dtype_size(g.in_dtype), osz = dtype_size(g.out_dtype);
+  const char* in_tag = g.mx_kind == 1 ? "mxf8" : g.mx_kind == 2 ? "mxf4" : g.mx_kind == 3 ? "nvf4"
+                       : g.in_dtype == B200_BF16 ? "bf16" : g.in_dtype == B200_F16 ? "f16" : g.in_dtype == B200_F8E4M3 ? "e4m3"
+                       : g.in_dtype == B200_F8E5M2 ? "e5m2" : g.in_dtype == B200_U8 ? "u8" : g.in_dtype == B200_I8 ? "s8" : "tf32";
+  const char* out_tag = g.out_dtype == B200_BF16 ? "bf16" : g.out_dtype == B200_F16 ? "f16" : g.out_dtype == B200_I32 ? "i32" : "f32";
+  const uint32_t block_k = static_cast<uint32_t>(128 / esz);
+  const std::string forced = opt(c, "gemm.variant", "auto");
+  const uint64_t k_segments = (g.a_lo != 0 && g.b_lo != 0) ? 3 : 1;
+  SkPlan best_sk;
+  const GemmVariant* best = pick_variant(c, g, &best_sk);
   if (!best) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant for this dtype", forced.c_str());
   if (best_sk.bad_option) return fail(B200_ERR_INVALID_ARG, "gemm.split_k must be auto, off, on or 1..8");
   const GemmVariant& v = *best;
@@ -1136,13 +1155,15 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   memset(&p, 0, sizeof(p));
   if (g.mx_kind) {
     // packed scale tensors viewed as (16 B, 32 rows x atoms, 128-row tiles); one box = the chunks of one k-block
-    const uint64_t tiles_a = (g.M + 127) / 128, tiles_b = (g.N + 127) / 128;
+    // 128-row chunks per batch entry; the rhs scales packed per 224-row tile take two chunks per tile (see pack_scales)
+    const uint64_t tiles_a = (g.M + 127) / 128;
+    const uint64_t tiles_b = g.sfb_tile_rows == 224 ? 2 * ((g.N + 223) / 224) : (g.N + 127) / 128;
     const uint64_t ab = a_bcast ? 1 : g.batch, bb = b_bcast ? 1 : g.batch;
     rc = encode_tmap(c, &ta_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfa, 16, 32 * g.sf_atoms, tiles_a * ab, 16, 512 * g.sf_atoms,
                      16, 32 * mx_atoms(g.mx_kind), CU_TENSOR_MAP_SWIZZLE_NONE, 1);
     if (rc) return rc;
     rc = encode_tmap(c, &tb_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfb, 16, 32 * g.sf_atoms, tiles_b * bb, 16, 512 * g.sf_atoms,
-                     16, 32 * mx_atoms(g.mx_kind), CU_TENSOR_MAP_SWIZZLE_NONE, v.block_n / 128);
+                     16, 32 * mx_atoms(g.mx_kind), CU_TENSOR_MAP_SWIZZLE_NONE, (v.block_n + 127) / 128);
     if (rc) return rc;
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
@@ -1397,11 +1418,12 @@ extern "C" int b200_matmul_fused(b200_ctx* c, b200_stream s, b200_dtype in_dtype
 
 // ------------------------------------------------------------------------------------------------ block-scaled matmul
 static int launch_pack_scales(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uint64_t batch, uint64_t rows,
-                              uint64_t n_scales, uint64_t tiles, uint64_t atoms, uint32_t pad_value) {
+                              uint64_t n_scales, uint64_t tiles, uint64_t atoms, uint32_t pad_value, uint32_t tile_rows = 128) {
   CUfunction f;
   int rc = get_func(c, "pack_scales", &f);
   if (rc) return rc;
-  PackScalesParams p{in, out, (uint32_t)batch, (uint32_t)rows, (uint32_t)n_scales, (uint32_t)tiles, (uint32_t)atoms, pad_value};
+  PackScalesParams p{in, out, (uint32_t)batch, (uint32_t)rows, (uint32_t)n_scales, (uint32_t)tiles, (uint32_t)atoms, pad_value,
+                     tile_rows, tile_rows == 224 ? 2u : 1u};
   const uint64_t words = batch * tiles * atoms * 128;
   const unsigned grid = (unsigned)std::min<uint64_t>((words + 255) / 256, (uint64_t)c->props.num_sms * 8);
   void* args[] = {&p};
@@ -1445,8 +1467,30 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
     void* args[] = {&p};
     return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
   }
+  // the problem as the GEMM sees it (operands described to TMA as bytes); the tile variant is chosen BEFORE the scales are
+  // packed, because the 256 x 224 variant wants the rhs scales packed per 224-row tile
+  GemmProblem g{};
+  g.in_dtype = B200_F8E4M3;  // 1-byte marker
+  g.out_dtype = out_dtype;
+  g.a = lhs; g.b = rhs; g.out = out;
+  g.M = M; g.N = N; g.K = k_bytes; g.batch = batch;
+  g.a_sm = k_bytes; g.a_sk = 1; g.a_sb = batch > 1 ? M * k_bytes : 0;
+  g.b_sn = k_bytes; g.b_sk = 1; g.b_sb = batch > 1 ? N * k_bytes : 0;
+  g.o_sm = N; g.o_sn = 1; g.o_sb = batch > 1 ? M * N : 0;
+  g.mx_kind = nvf4 ? 3 : fp4 ? 2 : 1;
+  g.fmt_a = fp4 ? 1u : (lhs_dtype == B200_F8E5M2 ? 1u : 0u);
+  g.fmt_b = fp4 ? 1u : (rhs_dtype == B200_F8E5M2 ? 1u : 0u);
+  g.sf_atoms = atoms;
+  g.sfb_any_layout = !scales_packed;           // pre-packed scales are in the plain 128-row layout
+  SkPlan sk_unused;
+  const GemmVariant* v = pick_variant(c, g, &sk_unused);
+  if (!v) return fail(B200_ERR_INVALID_ARG, "gemm.variant '%s' is not a tcgen05 variant for block-scaled operands%s", forced.c_str(),
+                      scales_packed ? " with pre-packed scales" : "");
+  g.sfb_any_layout = false;
+  g.sfb_tile_rows = (v->block_n == 224) ? 224 : 128;
   // scales -> the tensor core's packed chunks (skipped when the caller already holds them in that form)
-  const uint64_t tiles_a = (M + 127) / 128, tiles_b = (N + 127) / 128;
+  const uint64_t tiles_a = (M + 127) / 128;
+  const uint64_t tiles_b = g.sfb_tile_rows == 224 ? 2 * ((N + 223) / 224) : (N + 127) / 128;
   if (batch * tiles_a >= (1ull << 31) || batch * tiles_b >= (1ull << 31) || atoms * 32 >= (1ull << 31))
     return fail(B200_ERR_UNSUPPORTED, "matmul_scaled: scale tensor too large for 32-bit TMA coordinates");
   CUdeviceptr sfa = lhs_scales, sfb = rhs_scales;
@@ -1459,21 +1503,10 @@ extern "C" int b200_matmul_scaled(b200_ctx* c, b200_stream s, b200_dtype lhs_dty
     if (rc) { pool_free(c, sfa, st); return rc; }
     const uint32_t one = nvf4 ? 0x38u : 127u;
     rc = launch_pack_scales(c, st, lhs_scales, sfa, batch, M, n_scales, tiles_a, atoms, one);
-    if (!rc) rc = launch_pack_scales(c, st, rhs_scales, sfb, batch, N, n_scales, tiles_b, atoms, one);
+    if (!rc) rc = launch_pack_scales(c, st, rhs_scales, sfb, batch, N, n_scales, tiles_b, atoms, one, (uint32_t)g.sfb_tile_rows);
   }
   if (!rc) {
-    GemmProblem g{};
-    g.in_dtype = B200_F8E4M3;  // 1-byte marker: the operands are described to TMA as bytes
-    g.out_dtype = out_dtype;
-    g.a = lhs; g.b = rhs; g.out = out;
-    g.M = M; g.N = N; g.K = k_bytes; g.batch = batch;
-    g.a_sm = k_bytes; g.a_sk = 1; g.a_sb = batch > 1 ? M * k_bytes : 0;
-    g.b_sn = k_bytes; g.b_sk = 1; g.b_sb = batch > 1 ? N * k_bytes : 0;
-    g.o_sm = N; g.o_sn = 1; g.o_sb = batch > 1 ? M * N : 0;
-    g.mx_kind = nvf4 ? 3 : fp4 ? 2 : 1;
-    g.fmt_a = fp4 ? 1u : (lhs_dtype == B200_F8E5M2 ? 1u : 0u);
-    g.fmt_b = fp4 ? 1u : (rhs_dtype == B200_F8E5M2 ? 1u : 0u);
-    g.sfa = sfa; g.sfb = sfb; g.sf_atoms = atoms;
+    g.sfa = sfa; g.sfb = sfb;
     rc = launch_tcgen05(c, st, g, false, false);
   }
   if (!scales_packed) { pool_free(c, sfa, st); pool_free(c, sfb, st); }

@@ -205,11 +205,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                                           const CUtensorMap* tma_b_lo, const CUtensorMap* tma_out, const GemmParams& p) {
   constexpr bool SCALED = (KIND >= KIND_MXF8);
   constexpr bool INT_ACC = (KIND == KIND_U8 || KIND == KIND_S8);
-  static_assert(!SCALED || (!A_MN && !B_MN && BLOCK_N % 128 == 0), "block-scaled kinds: K-major operands, 128-row scale tiles");
+  static_assert(!SCALED || (!A_MN && !B_MN && BLOCK_N % 32 == 0), "block-scaled kinds: K-major operands, 32-row scale groups");
   static_assert(MT == 1 || (MT == 2 && CG == 2 && ACC == 1 && !SCALED), "two M sub-tiles per CTA: CTA pair, one accumulator stage");
   static_assert(ACC * MT <= 2, "two accumulator units (barrier pairs) at most");
   constexpr int SF_ATOMS = !SCALED ? 0 : (KIND == KIND_NVF4) ? 4 : (KIND == KIND_MXF4) ? 2 : 1;  // 512-byte scale chunks per 128 rows per k-block
-  constexpr int SF_TILES_B = BLOCK_N / 128;
+  // 128-row scale chunks covering the B tile.  BLOCK_N = 224 (seven 32-row groups) takes two chunks whose second holds three
+  // valid groups: the host packs the B scales per 224-row tile for that variant (pack_scales, tile_rows = 224), so a tile's
+  // groups are never spread over unaligned chunks.  224 columns are what lets TWO accumulator stages (448 columns) and the
+  // scale columns (12 / 24 / 48) share the 512 TMEM columns -- the 256-wide scaled tiles have one stage and an exposed drain.
+  constexpr int SF_TILES_B = (BLOCK_N + 127) / 128;
   constexpr uint32_t SFA_BYTES = 512u * SF_ATOMS, SFB_BYTES = 512u * SF_ATOMS * SF_TILES_B;
   constexpr uint32_t SF_BYTES = (SFA_BYTES + SFB_BYTES + 1023u) / 1024u * 1024u;
   constexpr uint32_t SF_COLS = 4u * SF_ATOMS * (1 + SF_TILES_B);
@@ -583,6 +587,19 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             tma_store_commit();
           }
         }
+        if constexpr (BLOCK_N % CW != 0) {
+          // 224-wide tiles with 16-bit outputs: the last 32 columns are half a staging tile; a 64-wide TMA box would spill into
+          // the neighbouring tile, so they leave through direct stores
+          constexpr int c0 = BLOCK_N / CW * CW;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c0, v);
+          tmem_ld_wait();
+          const uint32_t n0 = n_tile + c0;
+          if (m < p.M && n0 < p.N) {
+            fused_epilogue(v, n0);
+            store_chunk32<OUT>(row_ptr, n0, p.N, p.vec_store != 0, v);
+          }
+        }
       } else if (!partial) {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -840,6 +857,8 @@ GEMM_KERNEL_ACC(gemm_mxf4_bf16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT
 GEMM_KERNEL_ACC(gemm_mxf4_f16_2sm_n256_kk, 2, 256, false, false, KIND_MXF4, OUT_F16, 5, 1)
 GEMM_MX(2sm_n128, 2, 128, 8, 2)
 GEMM_MX(1sm_n128, 1, 128, 6, 2)
+// 256 x 224 tiles: two accumulator stages + scale columns fit TMEM (448 + 12 / 24), 32 / 33 KB stages x 6
+GEMM_MX(2sm_n224, 2, 224, 6, 2)
 // NVFP4: four scale chunks per 128 rows per k-block (6 KB / 4 KB of scales per stage)
 #define GEMM_NVF4(TILE, CG, BN, STAGES, ACC)                                                          \
   GEMM_KERNEL_ACC(gemm_nvf4_f32_##TILE##_kk, CG, BN, false, false, KIND_NVF4, OUT_F32, STAGES, ACC)   \
@@ -848,6 +867,7 @@ GEMM_MX(1sm_n128, 1, 128, 6, 2)
 GEMM_NVF4(2sm_n256, 2, 256, 5, 1)
 GEMM_NVF4(2sm_n128, 2, 128, 7, 2)
 GEMM_NVF4(1sm_n128, 1, 128, 5, 2)
+GEMM_NVF4(2sm_n224, 2, 224, 5, 2)   // 448 + 48 scale columns, 36 KB stages x 5
 
 // The same probe for the other tensor-core kinds on 8-bit / 4-bit operands: PK 1 = kind::f8f6f4 (e4m3), 2 = kind::mxf8f6f4
 // block-scaled (e4m3, ue8m0 scales = 1.0 copied to TMEM once), 3 = kind::mxf4 block-scaled (packed e2m1, two scales per

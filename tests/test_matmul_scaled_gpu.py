@@ -9,7 +9,7 @@ from cubecl_b200 import ServerError, TensorHandle, matmul, synth
 
 pytestmark = pytest.mark.gpu
 
-TC_VARIANTS = ["2sm_n256", "2sm_n128", "1sm_n128"]
+TC_VARIANTS = ["2sm_n256", "2sm_n224", "2sm_n128", "1sm_n128"]
 
 
 @pytest.fixture(autouse=True)

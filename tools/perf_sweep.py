@@ -143,11 +143,15 @@ if "scaled" in what:
         tiles, atoms = n // 128, k // 128
         pa = TensorHandle.from_numpy(c, np.full((tiles, atoms, 512), 127, np.uint8), "ue8m0")
         flops = 2.0 * n * n * k
-        for variant in ("2sm_n256", "2sm_n128", "1sm_n128"):
+        for variant in ("auto", "2sm_n256", "2sm_n224", "2sm_n128", "1sm_n128"):
             c.set_option("gemm.variant", variant)
             ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, sa, sb, o), iters=10, warm=2) for _ in range(3))
+            picked = c.last_kernel()
+            if variant in ("2sm_n224",):     # pre-packed scales are in the plain 128-row layout: not for the 224-wide tile
+                print(f"  {dt:9s} {n}x{n}x{k} {variant}: {ms * 1e3:8.1f} us {flops / ms / 1e9:7.0f} TF/s (row-major scales, packing included)  [{picked}]", flush=True)
+                continue
             msp = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scales_packed=True), iters=10, warm=2) for _ in range(3))
-            print(f"  {dt:9s} {n}x{n}x{k} {variant}: {ms * 1e3:8.1f} us {flops / ms / 1e9:7.0f} TF/s | pre-packed scales {msp * 1e3:8.1f} us {flops / msp / 1e9:7.0f} TF/s", flush=True)
+            print(f"  {dt:9s} {n}x{n}x{k} {variant}: {ms * 1e3:8.1f} us {flops / ms / 1e9:7.0f} TF/s | pre-packed scales {msp * 1e3:8.1f} us {flops / msp / 1e9:7.0f} TF/s  [{picked}]", flush=True)
         if dt == "f4e2m1x2":
             s16 = TensorHandle.from_numpy(c, np.full((n, k // 16), 0x38, np.uint8), "f8e4m3")
             ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, s16, s16, o, scale_block=16), iters=10, warm=2) for _ in range(3))
