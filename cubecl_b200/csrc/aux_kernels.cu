@@ -146,27 +146,38 @@ struct PackScalesParams {
 };
 
 extern "C" __global__ void __launch_bounds__(256) pack_scales(const __grid_constant__ PackScalesParams p) {
-  const uint64_t words = static_cast<uint64_t>(p.batch) * p.tiles * p.atoms * 128;  // one 32-bit word = 4 scales of one row
+  // one 32-bit word = the 4 scales (one k atom) of one row.  Threads walk (chunk, row, atom) with the atom fastest, so the
+  // row-major input is read coalesced (whole words when the rows allow it); the scattered side is the 4-byte stores
+  // (round 1 walked the OUTPUT order and gathered single bytes from rows 32 apart: 20 us per 2 MB operand at 8192 x 8192)
+  const uint64_t words = static_cast<uint64_t>(p.batch) * p.tiles * p.atoms * 128;
   const uint8_t* in = reinterpret_cast<const uint8_t*>(p.in);
   uint32_t* out = reinterpret_cast<uint32_t*>(p.out);
+  const bool word_rows = (p.n_scales % 4 == 0) && (p.in % 4 == 0);
+  const uint32_t pad_word = p.pad_value * 0x01010101u;
   for (uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; w < words; w += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    const uint32_t in_chunk = static_cast<uint32_t>(w % 128);
-    const uint64_t chunk = w / 128;
-    const uint32_t atom = static_cast<uint32_t>(chunk % p.atoms);
-    const uint64_t bt = chunk / p.atoms;
-    const uint32_t tile = static_cast<uint32_t>(bt % p.tiles), b = static_cast<uint32_t>(bt / p.tiles);
-    const uint32_t r32 = in_chunk / 4, g = in_chunk % 4;
-    const uint32_t local = (tile % p.chunks_per_tile) * 128 + g * 32 + r32;      // row inside the GEMM tile
+    const uint32_t atom = static_cast<uint32_t>(w % p.atoms);
+    const uint64_t t1 = w / p.atoms;
+    const uint32_t lr = static_cast<uint32_t>(t1 % 128);                        // row inside the 128-row chunk
+    const uint64_t t2 = t1 / 128;
+    const uint32_t tile = static_cast<uint32_t>(t2 % p.tiles), b = static_cast<uint32_t>(t2 / p.tiles);
+    const uint32_t local = (tile % p.chunks_per_tile) * 128 + lr;               // row inside the GEMM tile
     const uint32_t row = (tile / p.chunks_per_tile) * p.tile_rows + local;
-    const bool in_tile = local < p.tile_rows;
-    uint32_t word = 0;
+    uint32_t word = pad_word;
+    if (local < p.tile_rows && row < p.rows) {
+      const uint64_t base = (static_cast<uint64_t>(b) * p.rows + row) * p.n_scales + atom * 4ull;
+      if (word_rows && atom * 4u + 3u < p.n_scales) {
+        word = *reinterpret_cast<const uint32_t*>(in + base);
+      } else {
+        word = 0;
 #pragma unroll
-    for (uint32_t sidx = 0; sidx < 4; ++sidx) {
-      const uint32_t ks = atom * 4 + sidx;
-      const uint32_t v = (in_tile && row < p.rows && ks < p.n_scales) ? in[(static_cast<uint64_t>(b) * p.rows + row) * p.n_scales + ks] : p.pad_value;
-      word |= v << (8 * sidx);
+        for (uint32_t sidx = 0; sidx < 4; ++sidx) {
+          const uint32_t ks = atom * 4 + sidx;
+          const uint32_t v = (ks < p.n_scales) ? in[base + sidx] : p.pad_value;
+          word |= v << (8 * sidx);
+        }
+      }
     }
-    out[w] = word;
+    out[((static_cast<uint64_t>(b) * p.tiles + tile) * p.atoms + atom) * 128 + (lr % 32) * 4 + lr / 32] = word;
   }
 }
 

@@ -850,7 +850,10 @@ static const GemmVariant kVariants[] = {{"2sm_n256", 2, 256, 6, 1.0, 1}, {"2sm_n
                                         // block-scaled kinds only: 256 x 224 tile -- two accumulator stages and the scale columns fit
                                         // the 512 TMEM columns, so the epilogue hides behind the next tile (the 256-wide scaled tiles
                                         // hold ONE stage).  Needs the B scales packed per 224-row tile, i.e. row-major scales.
-                                        {"2sm_n224", 2, 224, 6, 1.05, 1},
+                                        // MEASURED SLOWER (profiles/r02_block_scaled_sweep.log, 8192^3 -> bf16): mxfp8 2046 vs 2448 TFLOP/s,
+                                        // mxfp4 3798 vs 3866 -- UMMA N = 224 issues at the N = 256 rate, which costs more than the hidden
+                                        // epilogue returns.  eff 0: never chosen automatically (gemm.variant=2sm_n224 only).
+                                        {"2sm_n224", 2, 224, 6, 0.0, 1},
                                         // diagnostic: 256 x 256 tile with ONE accumulator stage (bf16 -> bf16, K-major lhs only)
                                         {"2sm_n256a1", 2, 256, 6, 0.0, 1}};
 static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {

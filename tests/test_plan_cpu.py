@@ -162,6 +162,12 @@ def test_block_scaled_plans(plan):
     rc, t = plan.matmul_scaled(FP4, FP4, BF16, 1, 8192, 8192, 8192, block=16)   # NVFP4: four chunks per k-block, 5 stages of 38 KB
     assert rc == 0 and "gemm_nvf4_bf16_2sm_n256_kk" in t and "box=(16,128,2) swizzle=0" in t and "smem=212992 cluster=2" in t
     assert t.count(f"alloc {64 * 128 * 512}") == 2                          # 64 row tiles x 128 k-atoms (K / 16 / 4) x 512 B
+    plan.option("gemm.variant", "2sm_n224")                                 # opt-in 256 x 224 tile: two accumulator stages fit TMEM;
+    rc, t = plan.matmul_scaled(E4M3, E5M2, BF16, 1, 8192, 8192, 8192)       # rhs scales packed per 224-row tile (37 tiles x 2 chunks)
+    assert rc == 0 and "gemm_mxf8_bf16_2sm_n224_kk grid=(148,1,1)" in t and f"alloc {74 * 64 * 512}" in t
+    assert "tmap esz=1 dims=(16,2048,74) strides=(16,32768) box=(16,32,2) swizzle=0" in t and "box=(128,112) swizzle=3" in t
+    assert plan.matmul_scaled(E4M3, E4M3, F32, 1, 256, 256, 128, packed=1)[0] != 0   # pre-packed scales are in the plain layout
+    plan.option("gemm.variant", "auto")
     rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 16, 8, 32)               # the reference's m16 n8 k32 test shape
     assert rc == 0 and "gemm_mxf8_f32_1sm_n128_kk" in t
     rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 64, 64, 128, packed=1)   # caller-packed scales: no packing pass
