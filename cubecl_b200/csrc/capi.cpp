@@ -1772,6 +1772,7 @@ static int launch_cols_kernel(b200_ctx* c, CUstream st, int op, int dt, const RV
     p.ws = ws; p.final_out = final_out; p.flags |= 4u;
     if (fused) *fused = true;
   }
+  if (nseg > 1 && !(p.flags & 4u)) p.scale = 1.0f;   // first pass of a two-launch reduction: the scale (mean) belongs to the second
   void* args[] = {&p};
   return launch(c, f, grid, 1, 1, 256, 0, 1, st, args, pdl);
 }
