@@ -610,7 +610,7 @@ def _host_operand(seed, rows, cols, dtype, chunk_rows=1024):
     return out
 
 
-def _block_checksums_ok(got, a, b, out_dtype, bm=32, bn=64):
+def _block_checksums_ok(got, a, b, out_dtype, bm=32, bn=64, rel=None):
     """Checksum identity over EVERY [bm x bn] block of the product (the epilogue's staging-tile granularity, so every
     512 x 256 / 256 x 256 tile, every CTA half and every epilogue warp's rows are covered):
         sum_{m in rows, n in cols} C[m, n] == sum_k (sum_{m in rows} A[m, k]) * (sum_{n in cols} B[k, n])      (f64)
@@ -624,7 +624,7 @@ def _block_checksums_ok(got, a, b, out_dtype, bm=32, bn=64):
     expect = asum @ bsum                                                        # [M/bm, N/bn]
     have = got.astype(np.float64).reshape(M // bm, bm, N // bn, bn).sum(axis=(1, 3))
     # per-element rounding noise: |c| * 2^-9 (bf16) / 2^-12 (f16) / 2^-25 (f32, plus accumulation ~1e-6 |a||b| K)
-    rel = {"bf16": 2.0 ** -9, "f16": 2.0 ** -12, "f32": 2.0 ** -20}[out_dtype]
+    rel = rel if rel is not None else {"bf16": 2.0 ** -9, "f16": 2.0 ** -12, "f32": 2.0 ** -20}[out_dtype]
     rms_c = np.sqrt(np.mean(got.astype(np.float64) ** 2))
     sigma = rel * rms_c * np.sqrt(bm * bn) / np.sqrt(3.0)
     worst = float(np.max(np.abs(have - expect)))
@@ -651,6 +651,27 @@ def test_bf16_8192_every_block_checksum(client):
     # checksum of checksums: the grand total equals colsum(A) . rowsum(B)
     total = float(ah.astype(np.float64).sum(axis=0) @ bh.astype(np.float64).sum(axis=1))
     assert abs(float(got.astype(np.float64).sum()) - total) <= 12.0 * (2.0 ** -9) * np.sqrt(np.mean(got.astype(np.float64) ** 2)) * n / np.sqrt(3.0)
+
+
+@pytest.mark.parametrize("mode,rel", [("tf32", 2.0 ** -11), ("3xtf32", 2.0 ** -16)])
+def test_f32_4096_every_block_checksum(client, mode, rel):
+    # BASELINE config 2 at full size on the default plan (256 x 256 tiles with a stream-K head: 34 tiles are summed from two
+    # K-halves): every output through the block checksums.  Noise model: tf32 rounds each operand to 11 bits (relative 2^-11 of the
+    # element magnitude, accumulated as a random walk over K -- bounded above by 2^-11 of rms(C) sqrt(block)); 3xTF32 restores
+    # ~f32 (2^-16 of rms(C) per element leaves 12 sigma of room for the f32 accumulation over 3 K products, ~1e-4 absolute)
+    client.set_option("gemm.f32", mode)
+    n = 4096
+    a = _device_operand(client, [n, n], "f32", 1)
+    b = _device_operand(client, [n, n], "f32", 2)
+    out = TensorHandle.empty_contiguous(client, [n, n], "f32")
+    matmul.launch(client, a, b, out)
+    got = out.to_numpy(client)
+    ah, bh = _host_operand(1, n, n, "f32"), _host_operand(2, n, n, "f32")
+    ok, worst, bound = _block_checksums_ok(got, ah, bh, "f32", rel=rel)
+    assert ok, f"{mode}: block checksum off by {worst:.4f} (bound {bound:.4f})"
+    bad = got.copy()
+    bad[1000, 2048:2080] += 0.5 if mode == "tf32" else 0.01
+    assert not _block_checksums_ok(bad, ah, bh, "f32", rel=rel)[0]
 
 
 def test_batched_8x4096_every_block_checksum(client):
