@@ -653,12 +653,14 @@ def test_bf16_8192_every_block_checksum(client):
     assert abs(float(got.astype(np.float64).sum()) - total) <= 12.0 * (2.0 ** -9) * np.sqrt(np.mean(got.astype(np.float64) ** 2)) * n / np.sqrt(3.0)
 
 
-@pytest.mark.parametrize("mode,rel", [("tf32", 2.0 ** -11), ("3xtf32", 2.0 ** -16)])
+@pytest.mark.parametrize("mode,rel", [("tf32", 2.0 ** -11), ("3xtf32", 2.0 ** -14)])
 def test_f32_4096_every_block_checksum(client, mode, rel):
     # BASELINE config 2 at full size on the default plan (256 x 256 tiles with a stream-K head: 34 tiles are summed from two
     # K-halves): every output through the block checksums.  Noise model: tf32 rounds each operand to 11 bits (relative 2^-11 of the
     # element magnitude, accumulated as a random walk over K -- bounded above by 2^-11 of rms(C) sqrt(block)); 3xTF32 restores
-    # ~f32 (2^-16 of rms(C) per element leaves 12 sigma of room for the f32 accumulation over 3 K products, ~1e-4 absolute)
+    # the operands to ~f32, but the tensor core adds each 8-deep partial product into the f32 accumulator with truncation, a bias
+    # of half an ulp TOWARD ZERO per instruction: 3 * 4096 / 8 = 1536 instructions * 1e-6 (ulp of 16..32) = ~1.5e-3 per element,
+    # signed like the element (measured: worst block sum 0.16, i.e. ~1e-3 per element) -- hence 2^-14 of rms(C)
     client.set_option("gemm.f32", mode)
     n = 4096
     a = _device_operand(client, [n, n], "f32", 1)
@@ -670,7 +672,7 @@ def test_f32_4096_every_block_checksum(client, mode, rel):
     ok, worst, bound = _block_checksums_ok(got, ah, bh, "f32", rel=rel)
     assert ok, f"{mode}: block checksum off by {worst:.4f} (bound {bound:.4f})"
     bad = got.copy()
-    bad[1000, 2048:2080] += 0.5 if mode == "tf32" else 0.01
+    bad[1000, 2048:2080] += 0.5 if mode == "tf32" else 0.05
     assert not _block_checksums_ok(bad, ah, bh, "f32", rel=rel)[0]
 
 
