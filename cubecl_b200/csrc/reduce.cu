@@ -407,6 +407,10 @@ __device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const Xgp
   constexpr uint32_t ALIGN = WIDE ? 32u : 16u;
   __shared__ float s_red[kMaxWarps];
   __shared__ uint64_t s_red64[kMaxWarps];
+  // Let a dependent launch begin right away: it only streams its own input until its griddepcontrol.wait, so its blocks take
+  // over SM slots as this grid's blocks retire and the two kernels' ramp / tail overlap completely (every block of this grid
+  // is resident or done by the time the dependent may launch, so the dependent can never starve it).
+  pdl_trigger();
 
   const uint64_t n = p.len;
   const uint32_t mis = static_cast<uint32_t>(p.in) & (ALIGN - 1u);
@@ -524,7 +528,6 @@ __device__ __forceinline__ void reduce_all_body(const ReduceParams& p, const Xgp
     else local = ValOp<OP>::apply(local, f);
   }
 
-  pdl_trigger();
   if constexpr (ARG) {
     const uint64_t block_pair = block_max64(cand.packed(), s_red64);
     grid_stage_arg<XGPU>(p, block_pair, s_red64, xg);
@@ -581,6 +584,7 @@ __device__ __forceinline__ void reduce_all_bulk_body(const ReduceParams& p) {
     b200::fence_mbar_init();
   }
   __syncthreads();
+  pdl_trigger();   // see reduce_all_body: a dependent launch may start streaming beside this one
 
   float local = ValOp<OP>::identity();
   if (warp == kBulkConsumers / 32) {
@@ -632,7 +636,6 @@ __device__ __forceinline__ void reduce_all_bulk_body(const ReduceParams& p) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) local = ValOp<OP>::apply(local, acc[u][j]);
   }
-  pdl_trigger();
   const float block_val = block_reduce<OP>(local, s_red);
   grid_stage_value<OP, false>(p, block_val, s_red, nullptr);
 }
