@@ -325,6 +325,7 @@ struct b200_ctx {
   std::map<std::vector<int>, P2PState> p2p;
   CUdeviceptr mailbox = 0;
   std::unordered_map<std::string, std::string> options;
+  std::unordered_map<std::string, std::string> env_cache;   // B200_<KEY> environment defaults, read once
   uint64_t launches = 0;
   // Dry-run planning context (no driver, no device): every launch / descriptor / pool request is RECORDED instead of
   // executed, so the host logic (validation, batch collapse, variant choice, split plans) is testable on a CPU box.
@@ -353,9 +354,15 @@ static inline CUstream resolve_stream(b200_ctx* c, b200_stream s) { return s ? s
 static std::string opt(b200_ctx* c, const char* key, const char* dflt) {
   auto it = c->options.find(key);
   if (it != c->options.end()) return it->second;
-  std::string env = std::string("B200_") + key;
-  for (auto& ch : env) ch = (ch == '.') ? '_' : static_cast<char>(toupper(ch));
-  if (const char* e = getenv(env.c_str())) return e;
+  // environment fallback B200_<KEY>, looked up once per key (getenv on every launch is measurable next to a 20 us kernel)
+  auto ev = c->env_cache.find(key);
+  if (ev == c->env_cache.end()) {
+    std::string env = std::string("B200_") + key;
+    for (auto& ch : env) ch = (ch == '.') ? '_' : static_cast<char>(toupper(ch));
+    const char* e = getenv(env.c_str());
+    ev = c->env_cache.emplace(key, e ? std::string(e) : std::string("\x01unset")).first;
+  }
+  if (ev->second != "\x01unset") return ev->second;
   return dflt;
 }
 

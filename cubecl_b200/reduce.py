@@ -13,6 +13,19 @@ from . import _ffi
 from ._ffi import B200Error
 from .client import ComputeClient, DTYPES, TensorHandle
 
+_IDS_CACHE: dict = {}
+
+
+def _ids_array(device_ids):
+    """(ctypes int array, n) of the sorted device set; cached -- the fused launches sit in 20 us loops."""
+    key = tuple(device_ids)
+    hit = _IDS_CACHE.get(key)
+    if hit is None:
+        ids = sorted(int(d) for d in key)
+        hit = _IDS_CACHE[key] = (_ffi.int_array(ids), len(ids))
+    return hit
+
+
 OPS = {"sum": _ffi.REDUCE_SUM, "prod": _ffi.REDUCE_PROD, "max": _ffi.REDUCE_MAX, "min": _ffi.REDUCE_MIN,
        "argmax": _ffi.REDUCE_ARGMAX, "argmin": _ffi.REDUCE_ARGMIN, "mean": _ffi.REDUCE_MEAN}
 
@@ -67,9 +80,9 @@ def launch_all_reduce(client: ComputeClient, input: TensorHandle, output: Tensor
             raise B200Error(7, "launch_all_reduce: f32 in, f32 out")
         if not input.is_contiguous():
             raise B200Error(7, "launch_all_reduce: input must be contiguous")
-        ids = sorted(int(d) for d in device_ids)
+        ids, n_ids = _ids_array(device_ids)
         _ffi.check(client._lib.b200_reduce_all_reduce(client._ctx, None, _ffi.REDUCE_SUM, DTYPES["f32"], C.c_uint64(input.handle.ptr),
-                                                      C.c_uint64(output.handle.ptr), input.size(), _ffi.int_array(ids), len(ids)))
+                                                      C.c_uint64(output.handle.ptr), input.size(), ids, n_ids))
     except B200Error as e:
         client._defer(e)
 
@@ -83,9 +96,8 @@ def launch_arg_all_reduce(client: ComputeClient, input: TensorHandle, output: Te
             raise B200Error(6, "launch_arg_all_reduce: op must be argmax or argmin")
         if input.dtype != "f32" or output.dtype != "u32" or not input.is_contiguous():
             raise B200Error(7, "launch_arg_all_reduce: contiguous f32 in, u32 out")
-        ids = sorted(int(d) for d in device_ids)
+        ids, n_ids = _ids_array(device_ids)
         _ffi.check(client._lib.b200_argreduce_all_reduce(client._ctx, None, OPS[op], DTYPES["f32"], C.c_uint64(input.handle.ptr),
-                                                         C.c_uint64(output.handle.ptr), input.size(), int(index_offset),
-                                                         _ffi.int_array(ids), len(ids)))
+                                                         C.c_uint64(output.handle.ptr), input.size(), int(index_offset), ids, n_ids))
     except B200Error as e:
         client._defer(e)

@@ -232,6 +232,28 @@ if "axis" in what:
             print(f"  {op:6s} {str(shape):22s} axis={axis} launches={launches} x{copies} buffers: " + "  |  ".join(res), flush=True)
             del ts, out
 
+if "launch" in what:
+    # host-side cost of one launch through the Python mirror + C ABI: a reduction too small to matter on the device, issued
+    # back to back; wall clock per launch (the GPU is idle most of the time)
+    import time as _time
+    x = TensorHandle.empty_contiguous(c, [1024], "f32")
+    c.fill_uniform(x.handle, "f32", 1024, 1, 0.0, 1.0)
+    out = TensorHandle.empty_contiguous(c, [1], "f32")
+    a = TensorHandle.empty_contiguous(c, [128, 64], "bf16")
+    b = TensorHandle.empty_contiguous(c, [64, 128], "bf16")
+    o = TensorHandle.empty_contiguous(c, [128, 128], "bf16")
+    for name, fn in (("reduce.launch (1024 f32)", lambda: reduce.launch(c, x, out, None, "sum")), ("matmul.launch (128x128x64 bf16)", lambda: matmul.launch(c, a, b, o))):
+        for _ in range(100):
+            fn()
+        c.sync()
+        t0 = _time.perf_counter()
+        for _ in range(2000):
+            fn()
+        t1 = _time.perf_counter()
+        c.sync()
+        t2 = _time.perf_counter()
+        print(f"  host cost per {name}: {(t1 - t0) / 2000 * 1e6:6.2f} us issue, {(t2 - t0) / 2000 * 1e6:6.2f} us issue + drain")
+
 if "variants" in what:
     # validation of the static tile-variant choice: every tcgen05 variant forced against `auto`, interleaved rounds, over a
     # spread of shapes (the efficiency table the host uses was measured at 8192^3 only)
