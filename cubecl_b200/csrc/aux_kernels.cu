@@ -239,15 +239,41 @@ struct SplitParams {
   uint64_t in_bs, in_rs;        // input strides in elements
   uint64_t out_rs;              // output row pitch in elements (>= cols, multiple of 4 so rows stay 16-byte aligned for TMA)
 };
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 extern "C" __global__ void __launch_bounds__(256) split_tf32_lo(const __grid_constant__ SplitParams p) {
+  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const bool vec = (p.cols % 4 == 0) && (p.in_rs % 4 == 0) && (p.in_bs % 4 == 0) && (p.in % 16 == 0) && (p.out % 16 == 0);
+  if (vec && p.in_rs == p.cols && p.out_rs == p.cols && (p.batch == 1 || p.in_bs == p.rows * p.cols)) {
+    // compact input and output (the common case): one flat stream of 128-bit vectors, no index arithmetic -- this pass runs in
+    // front of every 3xTF32 GEMM and at 4096^2 the scalar, divide-per-element form cost 68 us per operand against ~20 us of traffic
+    const uint64_t nv = p.batch * p.rows * p.cols / 4;
+    const float4* in = reinterpret_cast<const float4*>(p.in);
+    float4* out = reinterpret_cast<float4*>(p.out);
+    for (uint64_t i = tid; i < nv; i += nthreads) {
+      const float4 x = in[i];
+      out[i] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+    }
+    return;
+  }
+  if (vec) {
+    // strided rows, vector columns: one division per 128-bit vector
+    const uint64_t vpr = p.cols / 4, per = p.rows * vpr, nv = p.batch * per;
+    for (uint64_t i = tid; i < nv; i += nthreads) {
+      const uint64_t b = i / per, rem = i - b * per;
+      const uint64_t r = rem / vpr, c = (rem - r * vpr) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + b * p.in_bs + r * p.in_rs + c);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (b * p.rows + r) * p.out_rs + c) =
+          make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+    }
+    return;
+  }
   const uint64_t per = p.rows * p.cols, total = p.batch * per;
-  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+  for (uint64_t i = tid; i < total; i += nthreads) {
     const uint64_t b = i / per, rem = i - b * per;
     const uint64_t r = rem / p.cols, c = rem - r * p.cols;
-    const float x = reinterpret_cast<const float*>(p.in)[b * p.in_bs + r * p.in_rs + c];
-    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    reinterpret_cast<float*>(p.out)[(b * p.rows + r) * p.out_rs + c] = x - hi;
+    reinterpret_cast<float*>(p.out)[(b * p.rows + r) * p.out_rs + c] = tf32_lo(reinterpret_cast<const float*>(p.in)[b * p.in_bs + r * p.in_rs + c]);
   }
 }
 

@@ -1255,7 +1255,7 @@ static int launch_split(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uin
   if (rc) return rc;
   SplitParams p{in, out, batch, rows, cols, in_bs, in_rs, pad4(cols)};
   const uint64_t total = batch * rows * cols;
-  const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->props.num_sms * 16);
+  const unsigned grid = (unsigned)std::min<uint64_t>((total / 4 + 255) / 256 + 1, (uint64_t)c->props.num_sms * 16);
   void* args[] = {&p};
   return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
 }

@@ -232,6 +232,21 @@ if "axis" in what:
             print(f"  {op:6s} {str(shape):22s} axis={axis} launches={launches} x{copies} buffers: " + "  |  ".join(res), flush=True)
             del ts, out
 
+if "f32" in what:
+    print("f32 matmul on the tf32 pipe (f32-equivalent 2 M N K), whole launch sequence (3xTF32 = 2 lo-split passes + 1 GEMM):")
+    for n in (4096, 8192):
+        a = TensorHandle.empty_contiguous(c, [n, n], "f32")
+        b = TensorHandle.empty_contiguous(c, [n, n], "f32")
+        o = TensorHandle.empty_contiguous(c, [n, n], "f32")
+        c.fill_uniform(a.handle, "f32", n * n, 1, -1.0, 1.0)
+        c.fill_uniform(b.handle, "f32", n * n, 2, -1.0, 1.0)
+        for mode in ("tf32", "3xtf32"):
+            c.set_option("gemm.f32", mode)
+            ms = min(time_ms(c, lambda: matmul.launch(c, a, b, o), iters=10, warm=3) for _ in range(3))
+            print(f"  {n}^3 {mode:6s}: {ms * 1e3:8.1f} us  {2.0 * n ** 3 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+        c.set_option("gemm.f32", "3xtf32")
+        del a, b, o
+
 if "launch" in what:
     # host-side cost of one launch through the Python mirror + C ABI: a reduction too small to matter on the device, issued
     # back to back; wall clock per launch (the GPU is idle most of the time)
