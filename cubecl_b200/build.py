@@ -24,7 +24,8 @@ LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libcubecl_b200.so"
 
 # tag -> (source, extra nvcc flags); the GEMM source is split in two cubins so the halves compile in parallel
-CUBINS = {"gemm": ("gemm_tcgen05.cu", ["-DGEMM_PART=0"]), "gemm_mx": ("gemm_tcgen05.cu", ["-DGEMM_PART=1"]),
+CUBINS = {"gemm": ("gemm_tcgen05.cu", ["-DGEMM_PART=0"]), "gemm_b": ("gemm_tcgen05.cu", ["-DGEMM_PART=2"]),
+          "gemm_c": ("gemm_tcgen05.cu", ["-DGEMM_PART=3"]), "gemm_mx": ("gemm_tcgen05.cu", ["-DGEMM_PART=1"]),
           "reduce": ("reduce.cu", []), "aux": ("aux_kernels.cu", [])}
 NVCC_FLAGS = ["-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"]
 

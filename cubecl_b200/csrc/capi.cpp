@@ -30,6 +30,10 @@
 extern "C" {
 extern const unsigned char b200_cubin_gemm[];
 extern const unsigned char b200_cubin_gemm_end[];
+extern const unsigned char b200_cubin_gemm_b[];
+extern const unsigned char b200_cubin_gemm_b_end[];
+extern const unsigned char b200_cubin_gemm_c[];
+extern const unsigned char b200_cubin_gemm_c_end[];
 extern const unsigned char b200_cubin_gemm_mx[];
 extern const unsigned char b200_cubin_gemm_mx_end[];
 extern const unsigned char b200_cubin_reduce[];
@@ -381,13 +385,17 @@ static int get_func(b200_ctx* c, const std::string& name, CUfunction* out) {
   if (c->dry) { c->pending_kernel = name; *out = nullptr; return B200_OK; }
   auto it = c->funcs.find(name);
   if (it != c->funcs.end()) { *out = it->second; return B200_OK; }
-  // modules are loaded in the order gemm, reduce, aux, gemm_mx; the name prefix says where a kernel lives (no failing
-  // lookups, which API-level tools such as compute-sanitizer would report)
+  // modules are loaded in the order gemm, reduce, aux, gemm_mx, gemm_b, gemm_c; the kernel name says where a kernel lives (no
+  // failing lookups, which API-level tools such as compute-sanitizer would report)
   auto starts = [&](const char* pfx) { return name.rfind(pfx, 0) == 0; };
+  auto has = [&](const char* part) { return name.find(part) != std::string::npos; };
   const bool mx = starts("gemm_mxf8_") || starts("gemm_mxf4_") || starts("gemm_nvf4_") || starts("umma_probe_e4m3") ||
                   starts("umma_probe_mxf8") || starts("umma_probe_mxf4");
+  const bool tc_gemm = starts("gemm_") && name != "gemm_simt_strided" && name != "gemm_scaled_simt";
   const size_t home = mx ? 3
-                      : (starts("gemm_") && name != "gemm_simt_strided" && name != "gemm_scaled_simt") || starts("umma_") ? 0
+                      : tc_gemm && has("_2sm_m512_") ? 5
+                      : tc_gemm && (has("_2sm_n128_") || has("_1sm_n128_")) ? 4
+                      : tc_gemm || starts("umma_") ? 0
                       : starts("reduce_") ? 1 : 2;
   if (home < c->modules.size()) {
     CUfunction f;
@@ -407,7 +415,9 @@ extern "C" int b200_get_cubin(const char* name, const void** image, size_t* size
   else if (!strcmp(name, "reduce")) { b = b200_cubin_reduce; e = b200_cubin_reduce_end; }
   else if (!strcmp(name, "aux")) { b = b200_cubin_aux; e = b200_cubin_aux_end; }
   else if (!strcmp(name, "gemm_mx")) { b = b200_cubin_gemm_mx; e = b200_cubin_gemm_mx_end; }
-  else return fail(B200_ERR_INVALID_ARG, "get_cubin: unknown image '%s' (gemm|gemm_mx|reduce|aux)", name);
+  else if (!strcmp(name, "gemm_b")) { b = b200_cubin_gemm_b; e = b200_cubin_gemm_b_end; }
+  else if (!strcmp(name, "gemm_c")) { b = b200_cubin_gemm_c; e = b200_cubin_gemm_c_end; }
+  else return fail(B200_ERR_INVALID_ARG, "get_cubin: unknown image '%s' (gemm|gemm_b|gemm_c|gemm_mx|reduce|aux)", name);
   *image = b;
   *size = static_cast<size_t>(e - b);
   return B200_OK;
@@ -458,7 +468,9 @@ extern "C" int b200_init(int device, b200_ctx** out) {
   if ((rc = load_module(c, b200_cubin_gemm, b200_cubin_gemm_end, "gemm")) ||
       (rc = load_module(c, b200_cubin_reduce, b200_cubin_reduce_end, "reduce")) ||
       (rc = load_module(c, b200_cubin_aux, b200_cubin_aux_end, "aux")) ||
-      (rc = load_module(c, b200_cubin_gemm_mx, b200_cubin_gemm_mx_end, "gemm_mx"))) {
+      (rc = load_module(c, b200_cubin_gemm_mx, b200_cubin_gemm_mx_end, "gemm_mx")) ||
+      (rc = load_module(c, b200_cubin_gemm_b, b200_cubin_gemm_b_end, "gemm_b")) ||
+      (rc = load_module(c, b200_cubin_gemm_c, b200_cubin_gemm_c_end, "gemm_c"))) {
     for (CUmodule m : c->modules) g_drv.cuModuleUnload_p(m);
     g_drv.cuDevicePrimaryCtxRelease_p(c->dev);
     return bail(rc);

@@ -750,8 +750,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   GEMM_LAYOUTS(gemm_s8_i32_##TILE, CG, BN, KIND_S8, OUT_F32, STAGES)
 
 // The kernels are built as two cubins from this one source (cubecl_b200/build.py compiles them in parallel):
-//   GEMM_PART 0 ("gemm")    f16 / bf16 / tf32 / fp8 / int8 kernels and the bf16 peak probe
+//   GEMM_PART 0 ("gemm")    256 x 256 tiles (f16 / bf16 / tf32 / fp8 / int8), the single-accumulator diagnostic, the bf16 peak probe
+//   GEMM_PART 2 ("gemm_b")  256 x 128 and 128 x 128 tiles
+//   GEMM_PART 3 ("gemm_c")  512 x 256 pair tiles
 //   GEMM_PART 1 ("gemm_mx") block-scaled kernels (mxf8 / mxf4 / nvf4) and the 8-bit / 4-bit peak probes
+// (four images compiled in parallel: ptxas takes minutes for one image holding every instantiation)
 #ifndef GEMM_PART
 #define GEMM_PART 0
 #endif
@@ -760,11 +763,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 // 2-SM, 256x256 tiles: 32 KB/stage/CTA -> 6 stages = 192 KB
 GEMM_DTYPES(2sm_n256, 2, 256, 6)
 GEMM_FP8(2sm_n256, 2, 256, 6)
+#endif
+#if GEMM_PART == 2
 // 2-SM, 256x128 tiles: 24 KB/stage/CTA -> 8 stages = 192 KB (smem-read bound: 128 B/cycle/SM of operands)
 GEMM_DTYPES(2sm_n128, 2, 128, 8)
 // 1-SM, 128x128 tiles (small problems; also the bring-up path): 32 KB/stage -> 6 stages
 GEMM_DTYPES(1sm_n128, 1, 128, 6)
 GEMM_FP8(1sm_n128, 1, 128, 6)
+#endif
+#if GEMM_PART == 3
 // 2-SM, 512x256 pair tiles (MT = 2, see gemm_body): 48 KB/stage/CTA -> 4 stages = 192 KB, one accumulator stage, 384 threads.
 // Opt-in (gemm.variant=2sm_m512) until measured against the 256x256 tile.
 #define GEMM_M512(PFX, KIND, OUT)                                        \
@@ -781,6 +788,8 @@ GEMM_M512(gemm_e4m3_bf16, KIND_E4M3, OUT_BF16)
 GEMM_M512(gemm_e4m3_f16, KIND_E4M3, OUT_F16)
 GEMM_M512(gemm_e5m2_bf16, KIND_E5M2, OUT_BF16)
 GEMM_M512(gemm_e5m2_f16, KIND_E5M2, OUT_F16)
+#endif
+#if GEMM_PART == 0
 // diagnostic: the 256x256 tile with ONE accumulator stage (what an un-hidden epilogue costs per tile); gemm.variant=2sm_n256a1
 GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kn, 2, 256, false, true, KIND_BF16, OUT_BF16, 6, 1)
 GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kk, 2, 256, false, false, KIND_BF16, OUT_BF16, 6, 1)

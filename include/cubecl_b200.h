@@ -82,7 +82,7 @@ typedef struct b200_props {
 /* ---- lifecycle: R::client(device) -> DeviceService::init (cubecl-cuda/src/runtime.rs:52-350) ------------------------ */
 int b200_abi_version(void);
 int b200_device_count(int* count);
-/* The embedded prebuilt sm_100a images ("gemm" | "gemm_mx" | "reduce" | "aux"), for a host that prefers to cuModuleLoadData them into
+/* The embedded prebuilt sm_100a images ("gemm" | "gemm_b" | "gemm_c" | "gemm_mx" | "reduce" | "aux"), for a host that prefers to cuModuleLoadData them into
  * its own module cache (CudaContext::modules, crates/cubecl-cuda/src/compute/context.rs:38-62,293). No GPU needed. */
 int b200_get_cubin(const char* name, const void** image, size_t* size);
 int b200_init(int device, b200_ctx** out);   /* cuInit, primary ctx retain, load the embedded sm_100a cubins (context.rs:293) */

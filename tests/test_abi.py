@@ -40,16 +40,23 @@ def test_cubins_are_embedded_and_sm100a():
         sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, str(mx)], capture_output=True, text=True).stdout
         assert mma in sass and "UTCCP" in sass, f"{fun}: block-scaled tcgen05 SASS missing"
     assert ".4X" in sass                                                      # NVFP4: four scales per row per instruction
+    # the headline pair tile lives in its own image
+    pair = subprocess.run(["cuobjdump", "-sass", "-fun", "gemm_bf16_bf16_2sm_m512_kn", str(ROOT / "cubecl_b200" / "build" / "gemm_c.cubin")],
+                          capture_output=True, text=True).stdout
+    assert "UTCHMMA.2CTA" in pair and "UTMALDG" in pair and "HMMA." not in pair.replace("UTCHMMA.", "")
     red = subprocess.run(["cuobjdump", "-sass", "-fun", "reduce_all_sum_f32", str(ROOT / "cubecl_b200" / "build" / "reduce.cubin")],
                          capture_output=True, text=True).stdout
     assert "LDG.E.128" in red or "LDG.E.NA.128" in red or ".128" in red
     assert "SHFL.DOWN" in red
+    bulk = subprocess.run(["cuobjdump", "-sass", "-fun", "reduce_all_sum_f32_tma", str(ROOT / "cubecl_b200" / "build" / "reduce.cubin")],
+                          capture_output=True, text=True).stdout
+    assert "UBLKCP" in bulk and "SYNCS" in bulk                               # cp.async.bulk into the smem ring, mbarriers
 
 
 def test_embedded_images_are_elf_cubins_for_sm100():
     # "driver-API load of a prebuilt sm_100a .cubin": the images inside the .so are the nvcc -cubin outputs, byte for byte
     lib = _ffi.load()
-    for name in ("gemm", "gemm_mx", "reduce", "aux"):
+    for name in ("gemm", "gemm_b", "gemm_c", "gemm_mx", "reduce", "aux"):
         img, size = ctypes.c_void_p(), ctypes.c_size_t()
         assert lib.b200_get_cubin(name.encode(), ctypes.byref(img), ctypes.byref(size)) == 0
         blob = ctypes.string_at(img.value, size.value)

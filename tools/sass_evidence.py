@@ -12,7 +12,8 @@ ROOT = Path(__file__).resolve().parent.parent
 BUILD = ROOT / "cubecl_b200" / "build"
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 KERNELS = {
-    "gemm": ["gemm_bf16_bf16_2sm_m512_kn", "gemm_bf16_bf16_2sm_n256_kn", "gemm_tf32_f32_2sm_n256_kn", "gemm_e4m3_bf16_2sm_m512_kn", "gemm_u8_i32_2sm_n256_kn"],
+    "gemm_c": ["gemm_bf16_bf16_2sm_m512_kn", "gemm_e4m3_bf16_2sm_m512_kn"],
+    "gemm": ["gemm_bf16_bf16_2sm_n256_kn", "gemm_tf32_f32_2sm_n256_kn", "gemm_u8_i32_2sm_n256_kn"],
     "gemm_mx": ["gemm_mxf8_bf16_2sm_n256_kk", "gemm_mxf4_bf16_2sm_n256_kk", "gemm_nvf4_bf16_2sm_n256_kk"],
     "reduce": ["reduce_all_sum_f32_tma", "reduce_all_sum_f32", "reduce_all_argmax_f32", "reduce_rows_sum_f32", "reduce_cols_sum_f32", "reduce_all_sum_f32_xgpu"],
     "aux": ["wmma_probe_bf16", "memread_probe_vec4"],
