@@ -355,7 +355,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    from cubecl_b200 import ComputeClient, TensorHandle, matmul, reduce
+    from cubecl_b200 import ComputeClient, TensorHandle, matmul, reduce, synth
     from cubecl_b200 import distributed as D
 
     e = D.env()
@@ -709,19 +709,30 @@ def main():
             line["batched_bf16_4096"] = {"value": world * 8 * 2.0 * n4 ** 3 * extra_steps / (ms_b * 1e-3) / 1e12, "unit": "TFLOP/s",
                                          "config": f"B={8 * world} x 4096^3 bf16, 8 batches per GPU, batch-axis shard, no collective"}
             del ab, bb, ob
-            # config 2: f32 4096^3 on the tf32 tensor pipe (both f32 modes)
+            # config 2: f32 4096^3 on the tensor pipes: hybrid (default; tf32 product + two bf16 cross terms, ~2^-20), 3xTF32, plain tf32
             af = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
             bf = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
             of = TensorHandle.empty_contiguous(c, [n4, n4], "f32")
             c.fill_uniform(af.handle, "f32", n4 * n4, 1, -1.0, 1.0)
             c.fill_uniform(bf.handle, "f32", n4 * n4, 2, -1.0, 1.0)
             f32res = {}
-            for mode in ("3xtf32", "tf32"):
+            f32err = {}
+            rng_f = np.random.default_rng(7)
+            ms_i, ns_i = rng_f.integers(0, n4, 16), rng_f.integers(0, n4, 16)
+            a_rows = np.stack([synth.uniform_f32(1, n4, -1.0, 1.0, start=int(m) * n4) for m in ms_i]).astype(np.float64)
+            b_cols = np.stack([synth.uniform_at(2, np.arange(n4, dtype=np.uint64) * n4 + int(cc), -1.0, 1.0) for cc in ns_i]).astype(np.float64)
+            f64_s, abs_s = a_rows @ b_cols.T, np.abs(a_rows) @ np.abs(b_cols).T
+            for mode in ("hybrid", "3xtf32", "tf32"):
                 c.set_option("gemm.f32", mode)
                 ms_f, _ = timed(lambda: matmul.launch(c, af, bf, of), extra_steps, 3)
                 f32res[mode] = world * 2.0 * n4 ** 3 * extra_steps / (ms_f * 1e-3) / 1e12
-            c.set_option("gemm.f32", "3xtf32")
-            line["matmul_f32_4096"] = {"unit": "TFLOP/s (f32-equivalent 2*N^3)", "3xtf32_default": f32res["3xtf32"], "tf32": f32res["tf32"]}
+                got_s = of.to_numpy(c)[np.ix_(ms_i, ns_i)].astype(np.float64)
+                f32err[mode] = float(np.max(np.abs(got_s - f64_s) / abs_s))
+            c.set_option("gemm.f32", "hybrid")
+            line["matmul_f32_4096"] = {"unit": "TFLOP/s (f32-equivalent 2*N^3)", "hybrid_default": f32res["hybrid"], "3xtf32": f32res["3xtf32"],
+                                       "tf32": f32res["tf32"], "max_err_over_sum_abs_256_samples": f32err}
+            parity["matmul_f32_4096"] = {"ok": bool(f32err["hybrid"] <= 1e-5 and f32err["3xtf32"] <= 1e-5 and f32err["tf32"] <= 1e-3),
+                                         "worst_scaled_err": f32err}
             del af, bf, of
             # widening row: fp8 e4m3 8192^3 -> bf16 on the same kernel (kind::f8f6f4)
             a8 = TensorHandle.empty_contiguous(c, [N_MM, N_MM], "f8e4m3")

@@ -239,7 +239,11 @@ struct SplitParams {
   uint64_t in_bs, in_rs;        // input strides in elements
   uint64_t out_rs;              // output row pitch in elements (>= cols, multiple of 4 so rows stay 16-byte aligned for TMA)
 };
-__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// (a non-finite x has no low part: inf - inf would turn an infinite product into NaN)
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return (fabsf(x) < __int_as_float(0x7F800000)) ? lo : 0.f;
+}
 
 extern "C" __global__ void __launch_bounds__(256) split_tf32_lo(const __grid_constant__ SplitParams p) {
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -274,6 +278,68 @@ extern "C" __global__ void __launch_bounds__(256) split_tf32_lo(const __grid_con
     const uint64_t b = i / per, rem = i - b * per;
     const uint64_t r = rem / p.cols, c = rem - r * p.cols;
     reinterpret_cast<float*>(p.out)[(b * p.rows + r) * p.out_rs + c] = tf32_lo(reinterpret_cast<const float*>(p.in)[b * p.in_bs + r * p.in_rs + c]);
+  }
+}
+
+// Hybrid f32 schedule (GemmParams::hyb): the cross terms A*B_lo + A_lo*B run on bf16 copies.  One pass writes both planes of
+// the operand's pair buffer: plane 0 = bf16(x) (round to nearest even), plane 1 = bf16(x - trunc_tf32(x)); planes are
+// batch * rows * out_rs elements apart, rows pitched to out_rs (a multiple of 8 elements = 16 bytes, for TMA).
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// plane 0 only multiplies low parts: a non-finite x contributes through the tf32 segment alone (inf * lo with lo == 0 would be
+// NaN), and a finite x that rounds up to the bf16 infinity is kept at the largest finite bf16
+__device__ __forceinline__ uint32_t bf16_main_bits(float x) {
+  if (!(fabsf(x) < __int_as_float(0x7F800000))) return 0u;
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  uint32_t b = *reinterpret_cast<const uint16_t*>(&h);
+  if ((b & 0x7FFFu) == 0x7F80u) b -= 1u;
+  return b;
+}
+__device__ __forceinline__ uint32_t bf16x2_main(float lo, float hi) { return bf16_main_bits(lo) | (bf16_main_bits(hi) << 16); }
+extern "C" __global__ void __launch_bounds__(256) split_f32_bf16_pair(const __grid_constant__ SplitParams p) {
+  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t plane = p.batch * p.rows * p.out_rs;
+  uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
+  const float* in = reinterpret_cast<const float*>(p.in);
+  const bool al = (p.in % 16 == 0) && (p.out % 16 == 0) && (p.in_rs % 4 == 0) && (p.in_bs % 4 == 0);
+  if (al && p.cols % 8 == 0 && p.in_rs == p.cols && p.out_rs == p.cols && (p.batch == 1 || p.in_bs == p.rows * p.cols)) {
+    // compact input and output: a flat stream, 32 bytes in and 2 x 16 bytes out per thread and trip
+    const uint64_t nv = plane / 8;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    uint4* o0 = reinterpret_cast<uint4*>(out);
+    uint4* o1 = reinterpret_cast<uint4*>(out + plane);
+    for (uint64_t i = tid; i < nv; i += nthreads) {
+      const float4 x = in4[2 * i], y = in4[2 * i + 1];
+      o0[i] = make_uint4(bf16x2_main(x.x, x.y), bf16x2_main(x.z, x.w), bf16x2_main(y.x, y.y), bf16x2_main(y.z, y.w));
+      o1[i] = make_uint4(bf16x2_bits(tf32_lo(x.x), tf32_lo(x.y)), bf16x2_bits(tf32_lo(x.z), tf32_lo(x.w)),
+                         bf16x2_bits(tf32_lo(y.x), tf32_lo(y.y)), bf16x2_bits(tf32_lo(y.z), tf32_lo(y.w)));
+    }
+    return;
+  }
+  if (al && p.cols % 4 == 0) {
+    // strided rows, vector columns: one division per 4-element vector (8-byte stores; out_rs is a multiple of 8 elements)
+    const uint64_t vpr = p.cols / 4, per = p.rows * vpr, nv = p.batch * per;
+    for (uint64_t i = tid; i < nv; i += nthreads) {
+      const uint64_t b = i / per, rem = i - b * per;
+      const uint64_t r = rem / vpr, c4 = (rem - r * vpr) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(in + b * p.in_bs + r * p.in_rs + c4);
+      uint16_t* o = out + (b * p.rows + r) * p.out_rs + c4;
+      *reinterpret_cast<uint2*>(o) = make_uint2(bf16x2_main(x.x, x.y), bf16x2_main(x.z, x.w));
+      *reinterpret_cast<uint2*>(o + plane) = make_uint2(bf16x2_bits(tf32_lo(x.x), tf32_lo(x.y)), bf16x2_bits(tf32_lo(x.z), tf32_lo(x.w)));
+    }
+    return;
+  }
+  const uint64_t per = p.rows * p.cols, total = p.batch * per;
+  for (uint64_t i = tid; i < total; i += nthreads) {
+    const uint64_t b = i / per, rem = i - b * per;
+    const uint64_t r = rem / p.cols, cc = rem - r * p.cols;
+    const float x = in[b * p.in_bs + r * p.in_rs + cc];
+    uint16_t* o = out + (b * p.rows + r) * p.out_rs + cc;
+    o[0] = static_cast<uint16_t>(bf16_main_bits(x));
+    o[plane] = static_cast<uint16_t>(bf16x2_bits(tf32_lo(x), 0.f) & 0xFFFFu);
   }
 }
 

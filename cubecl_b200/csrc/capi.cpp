@@ -222,6 +222,7 @@ struct GemmParams {
   uint64_t split_ws, split_tickets;
   uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;  // block-scaled kinds; operand formats of a mixed 8-bit pair
   uint32_t tma_store, fmt_mixed;
+  uint32_t hyb, hyb_nba, hyb_nbb, pad_;  // hybrid f32 schedule: tf32 main product + two bf16 cross terms (gemm_tcgen05.cu)
 };
 struct PackScalesParams {
   uint64_t in, out;
@@ -950,6 +951,7 @@ struct GemmProblem {
   int rhs_dtype = -1;           // >= 0: a mixed 8-bit pair (fp8 e4m3 x e5m2, u8 x i8); in_dtype is then the lhs format
   uint64_t a, b, out;
   uint64_t a_lo = 0, b_lo = 0;  // 3xTF32: compact low parts (same logical layout class as a / b), 0 otherwise
+  bool hybrid = false;          // a_lo / b_lo are bf16 PAIR buffers [2][entries][rows][pitch]: bf16(x) planes, then bf16(x - trunc_tf32(x))
   uint64_t bias = 0;            // fused epilogue: out = act(alpha * acc + bias[n])
   float alpha = 1.0f;
   uint32_t act = 0;
@@ -1074,6 +1076,14 @@ static SkPlan sk_plan(uint64_t tiles, uint64_t clusters, uint64_t num_kb, const 
   return pl;
 }
 
+// k-blocks (pipeline stages) one tile's K loop runs: 3xTF32 walks K three times; the hybrid f32 schedule once in tf32 stages
+// (32 elements) and twice in bf16 stages (64 elements)
+static uint64_t gemm_num_kb(const GemmProblem& g, uint32_t block_k) {
+  const uint64_t seg = (g.K + block_k - 1) / block_k;
+  if (!(g.a_lo != 0 && g.b_lo != 0)) return seg;
+  return g.hybrid ? seg + 2 * ((g.K + 63) / 64) : 3 * seg;
+}
+
 // Tile variant by modelled time (ties -> larger tile, less L2 traffic): waves of tiles, with the last partial wave replaced by a
 // stream-K head where that pays (sk_plan).  nullptr: gemm.variant names no variant this dtype / kind has.
 static const GemmVariant* pick_variant(b200_ctx* c, const GemmProblem& g, SkPlan* sk_out) {
@@ -1082,8 +1092,7 @@ static const GemmVariant* pick_variant(b200_ctx* c, const GemmProblem& g, SkPlan
   const std::string forced = opt(c, "gemm.variant", "auto");
   const std::string split_opt = opt(c, "gemm.split_k", "auto");
   const bool float_acc = !(g.in_dtype == B200_U8 || g.in_dtype == B200_I8);
-  const uint64_t k_segments = (g.a_lo != 0 && g.b_lo != 0) ? 3 : 1;
-  const uint64_t num_kb = ((g.K + block_k - 1) / block_k) * k_segments;
+  const uint64_t num_kb = gemm_num_kb(g, block_k);
   const GemmVariant* best = nullptr;
   double best_cost = 0;
   for (const GemmVariant& v : kVariants) {
@@ -1163,7 +1172,18 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
   // 3xTF32: compact low parts, same operand-major class as the originals (K-major: [rows, K]; MN-major: [K, cols])
   CUtensorMap ta_lo = ta, tb_lo = tb;
   const bool split = (g.a_lo != 0 && g.b_lo != 0);
-  if (split) {
+  if (split && g.hybrid) {
+    // bf16 pair buffers: planes [0, entries) = bf16(x), [entries, 2 entries) = bf16(lo); 64 elements of K per stage
+    const uint64_t ab = a_bcast ? 1 : g.batch, bb = b_bcast ? 1 : g.batch;
+    auto pad8 = [](uint64_t e) { return (e + 7) / 8 * 8; };
+    const CUtensorMapDataType d16 = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    rc = !a_mn ? encode_tmap(c, &ta_lo, d16, 2, g.a_lo, g.K, g.M, 2 * ab, pad8(g.K), pad8(g.K) * g.M, 64, 128)
+               : encode_tmap(c, &ta_lo, d16, 2, g.a_lo, g.M, g.K, 2 * ab, pad8(g.M), pad8(g.M) * g.K, 64, 64);
+    if (rc) return rc;
+    rc = !b_mn ? encode_tmap(c, &tb_lo, d16, 2, g.b_lo, g.K, g.N, 2 * bb, pad8(g.K), pad8(g.K) * g.N, 64, n_local)
+               : encode_tmap(c, &tb_lo, d16, 2, g.b_lo, g.N, g.K, 2 * bb, pad8(g.N), pad8(g.N) * g.K, 64, 64);
+    if (rc) return rc;
+  } else if (split) {
     const uint64_t ab = a_bcast ? 1 : g.batch, bb = b_bcast ? 1 : g.batch;
     rc = !a_mn ? encode_tmap(c, &ta_lo, dt, esz, g.a_lo, g.K, g.M, ab, pad16(g.K), pad16(g.K) * g.M, block_k, 128)
                : encode_tmap(c, &ta_lo, dt, esz, g.a_lo, g.M, g.K, ab, pad16(g.M), pad16(g.M) * g.K, chunk, block_k, mn_swz);
@@ -1195,6 +1215,11 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     p.sf_fmt_a = fmt8(g.in_dtype); p.sf_fmt_b = fmt8(g.rhs_dtype); p.fmt_mixed = 1;
   }
   p.k_segments = (uint32_t)k_segments;
+  if (split && g.hybrid) {
+    p.hyb = 1;
+    p.hyb_nba = a_bcast ? 1u : (uint32_t)g.batch;
+    p.hyb_nbb = b_bcast ? 1u : (uint32_t)g.batch;
+  }
   p.alpha = g.alpha; p.bias = g.bias; p.epi_act = g.act;
   p.epi_on = (g.alpha != 1.0f || g.bias != 0 || g.act != 0) ? 1u : 0u;
   p.out = g.out;
@@ -1272,6 +1297,20 @@ static int launch_split(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uin
   return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
 }
 
+// bf16 pair of a logical [batch, rows, cols] f32 view: plane 0 = bf16(x), plane 1 = bf16(x - trunc_tf32(x)), rows pitched to 8 elements
+static inline uint64_t pad8e(uint64_t elems) { return (elems + 7) / 8 * 8; }
+static int launch_split_pair(b200_ctx* c, CUstream st, uint64_t in, uint64_t out, uint64_t batch, uint64_t rows, uint64_t cols,
+                             uint64_t in_bs, uint64_t in_rs) {
+  CUfunction f;
+  int rc = get_func(c, "split_f32_bf16_pair", &f);
+  if (rc) return rc;
+  SplitParams p{in, out, batch, rows, cols, in_bs, in_rs, pad8e(cols)};
+  const uint64_t total = batch * rows * cols;
+  const unsigned grid = (unsigned)std::min<uint64_t>((total / 8 + 255) / 256 + 1, (uint64_t)c->props.num_sms * 16);
+  void* args[] = {&p};
+  return launch(c, f, std::max(1u, grid), 1, 1, 256, 0, 1, st, args);
+}
+
 struct RepitchParams {
   uint64_t in, out;
   uint64_t batch, rows, cols;        // logical [batch, rows, cols] of the copy, cols innermost in the OUTPUT
@@ -1324,7 +1363,35 @@ static int run_gemm(b200_ctx* c, CUstream st, const GemmProblem& g) {
     if (forced == "auto" && g.K > 0 && big && extents_tma_ok(g) && opt(c, "gemm.stage", "on") == "on") return run_gemm_staged(c, st, g);
     return launch_simt(c, st, g);
   }
-  if (g.in_dtype == B200_F32 && opt(c, "gemm.f32", "3xtf32") == "3xtf32") {
+  const std::string f32_mode = g.in_dtype == B200_F32 ? opt(c, "gemm.f32", "hybrid") : std::string();
+  if (g.in_dtype == B200_F32 && f32_mode != "hybrid" && f32_mode != "3xtf32" && f32_mode != "tf32")
+    return fail(B200_ERR_INVALID_ARG, "gemm.f32 must be hybrid, 3xtf32 or tf32");
+  if (f32_mode == "hybrid") {
+    // f32-grade product in TWO tensor passes' worth of time, one launch: x = hi + lo with hi = the top 19 bits (what the tf32
+    // datapath reads from the original tensor).  hi*hi runs as kind::tf32 on the originals; the cross terms A*B_lo + A_lo*B run
+    // as kind::f16 on bf16 copies (bf16(A), bf16(B_lo), bf16(A_lo), bf16(B)) at twice the tf32 rate, into the same f32
+    // accumulators.  The cross terms are ~2^-11 of the product, so their bf16 rounding (2^-9) lands at ~2^-20 of it.
+    const uint64_t ab = (g.a_sb == 0) ? 1 : g.batch, bb = (g.b_sb == 0) ? 1 : g.batch;
+    const uint64_t a_elems = !a_mn ? g.M * pad8e(g.K) : g.K * pad8e(g.M), b_elems = !b_mn ? g.N * pad8e(g.K) : g.K * pad8e(g.N);
+    CUdeviceptr a_p = 0, b_p = 0;
+    int rc = pool_alloc(c, 2 * ab * a_elems * 2, &a_p, st);
+    if (rc) return rc;
+    rc = pool_alloc(c, 2 * bb * b_elems * 2, &b_p, st);
+    if (rc) { pool_free(c, a_p, st); return rc; }
+    rc = !a_mn ? launch_split_pair(c, st, g.a, a_p, ab, g.M, g.K, g.a_sb, g.a_sm) : launch_split_pair(c, st, g.a, a_p, ab, g.K, g.M, g.a_sb, g.a_sk);
+    if (!rc) rc = !b_mn ? launch_split_pair(c, st, g.b, b_p, bb, g.N, g.K, g.b_sb, g.b_sn) : launch_split_pair(c, st, g.b, b_p, bb, g.K, g.N, g.b_sb, g.b_sk);
+    if (!rc) {
+      GemmProblem h = g;
+      h.a_lo = a_p;
+      h.b_lo = b_p;
+      h.hybrid = true;
+      rc = launch_tcgen05(c, st, h, a_mn, b_mn);
+    }
+    pool_free(c, a_p, st);
+    pool_free(c, b_p, st);
+    return rc;
+  }
+  if (f32_mode == "3xtf32") {
     // 3xTF32 in ONE GEMM launch: the tf32 datapath reads only the top 19 bits of an f32 operand, so the original tensors
     // are the "hi" parts; only lo = x - hi is materialised (compact), and the kernel runs K three times:
     // (A,B) + (A,B_lo) + (A_lo,B), f32 accumulation throughout.

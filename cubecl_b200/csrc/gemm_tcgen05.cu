@@ -49,6 +49,12 @@ struct GemmParams {
   // 1: whole tiles leave through shared memory and TMA stores (tma_out describes `out` as (N, M, batch)); needs a 16-byte
   // aligned base and row / batch pitches.  0: each thread stores its own row directly.
   uint32_t tma_store, fmt_mixed;
+  // Hybrid f32 schedule (kind::tf32 kernels, k_segments == 3): segment 0 is the tf32 product of the ORIGINAL operands (their top
+  // 19 bits); segments 1 and 2 are the cross terms A*B_lo and A_lo*B on bf16 copies at twice the tensor rate -- kind::f16
+  // instructions into the same f32 accumulators, 64 elements of K per stage instead of 32.  tma_a_lo / tma_b_lo then describe
+  // bf16 PAIR buffers [2 * entries][rows][pitch]: entries [0, hyb_nba) hold bf16(x), entries [hyb_nba, 2 hyb_nba) hold
+  // bf16(x - trunc_tf32(x)).  Two tensor passes' worth of time instead of 3xTF32's three.
+  uint32_t hyb, hyb_nba, hyb_nbb, pad_;
 };
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6,
@@ -295,7 +301,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   // ORIGINAL tensors serve as "hi") and lo = x - hi materialised once.  A*B ~= hi*hi + hi*lo + lo*hi is accumulated by
   // running the K loop over three segments with the operand descriptors swapped per segment.
   const uint32_t seg_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const uint32_t num_kb = seg_kb * p.k_segments;
+  // hybrid schedule: the two bf16 segments cover K in 64-element stages (half as many k-blocks as the tf32 segment)
+  const bool hyb = (KIND == KIND_TF32) && p.hyb != 0 && p.k_segments == 3;
+  const uint32_t seg_kb1 = hyb ? (p.K + 63u) / 64u : seg_kb;
+  const uint32_t num_kb = (p.k_segments == 3) ? seg_kb + 2u * seg_kb1 : seg_kb * p.k_segments;
+  // (segment, k-block within it) of linear k-block kb
+  auto seg_of = [&](uint32_t kb, uint32_t& seg, uint32_t& kk) {
+    seg = 0; kk = kb;
+    if (kk >= seg_kb) { kk -= seg_kb; seg = 1u + kk / seg_kb1; kk -= (seg - 1u) * seg_kb1; }
+  };
 
   if (warp == 0 || warp == 3) {
     // ===================================================================== TMA producers (one lane each in warps 0 and 3)
@@ -317,28 +331,53 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         const int m0 = static_cast<int>((tc.m_blk * CG + rank) * (128 * MT));
         const int n0 = static_cast<int>(tc.n_blk * BLOCK_N + rank * N_LOCAL);
         const int ba = static_cast<int>(tc.b * p.a_bmul), bb = static_cast<int>(tc.b * p.b_bmul);
-        uint32_t seg = wu.kb0 / seg_kb, kk = wu.kb0 - seg * seg_kb;  // segment (0 unless k_segments == 3), k-block within it
+        uint32_t seg, kk;  // segment (0 unless k_segments == 3), k-block within it
+        seg_of(wu.kb0, seg, kk);
         for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           const uint32_t fb = (CG == 2) ? leader_full0 + 8u * s : full_bar(s);
-          const int k0 = static_cast<int>(kk * BLOCK_K);
           if (who == 0 && leader) mbar_arrive_expect_tx(full_bar(s), CG * STAGE_TX);
-          const CUtensorMap* tma_a = (seg == 2) ? tma_a_lo : tma_a_hi;
-          const CUtensorMap* tma_b = (seg == 1) ? tma_b_lo : tma_b_hi;
+          bool h16 = false;
+          if constexpr (KIND == KIND_TF32) h16 = hyb && seg != 0;
+          if (h16) {
+            // bf16 stage of the hybrid schedule: the same bytes per stage, 64 elements of K; MN-major operands arrive as
+            // [64 k-rows x 128 B] chunks (half as many as the tf32 stage's [32 x 128 B] chunks)
+            constexpr int kA16 = A_MN ? MT * 128 / 64 : MT, kB16 = B_MN ? N_LOCAL / 64 : 1;
+            const int k0 = static_cast<int>(kk * 64u);
+            const int ea = ba + static_cast<int>(seg == 2 ? p.hyb_nba : 0u), eb = bb + static_cast<int>(seg == 1 ? p.hyb_nbb : 0u);
 #pragma unroll
-          for (int item = 0; item < kAItems + kBItems; ++item) {
-            if ((item & 1) != static_cast<int>(who)) continue;
-            if (item < kAItems) {
-              const uint32_t dst = A_MN ? sa + item * CHUNK_BYTES : sa + item * A_SUB_BYTES;  // K-major: one 128-row box per sub-tile
-              const int c0 = A_MN ? m0 + item * CHUNK_N : k0, c1 = A_MN ? k0 : m0 + item * 128;
-              if constexpr (CG == 1) tma_load_3d(dst, tma_a, fb, c0, c1, ba); else tma_load_3d_2sm(dst, tma_a, fb, c0, c1, ba);
-            } else {
-              const int c = item - kAItems;
-              const uint32_t dst = B_MN ? sb + c * CHUNK_BYTES : sb;
-              const int c0 = B_MN ? n0 + c * CHUNK_N : k0, c1 = B_MN ? k0 : n0;
-              if constexpr (CG == 1) tma_load_3d(dst, tma_b, fb, c0, c1, bb); else tma_load_3d_2sm(dst, tma_b, fb, c0, c1, bb);
+            for (int item = 0; item < kA16 + kB16; ++item) {
+              if ((item & 1) != static_cast<int>(who)) continue;
+              if (item < kA16) {
+                const uint32_t dst = A_MN ? sa + item * 8192u : sa + item * A_SUB_BYTES;
+                const int c0 = A_MN ? m0 + item * 64 : k0, c1 = A_MN ? k0 : m0 + item * 128;
+                if constexpr (CG == 1) tma_load_3d(dst, tma_a_lo, fb, c0, c1, ea); else tma_load_3d_2sm(dst, tma_a_lo, fb, c0, c1, ea);
+              } else {
+                const int c = item - kA16;
+                const uint32_t dst = B_MN ? sb + c * 8192u : sb;
+                const int c0 = B_MN ? n0 + c * 64 : k0, c1 = B_MN ? k0 : n0;
+                if constexpr (CG == 1) tma_load_3d(dst, tma_b_lo, fb, c0, c1, eb); else tma_load_3d_2sm(dst, tma_b_lo, fb, c0, c1, eb);
+              }
+            }
+          } else {
+            const int k0 = static_cast<int>(kk * BLOCK_K);
+            const CUtensorMap* tma_a = (seg == 2) ? tma_a_lo : tma_a_hi;
+            const CUtensorMap* tma_b = (seg == 1) ? tma_b_lo : tma_b_hi;
+#pragma unroll
+            for (int item = 0; item < kAItems + kBItems; ++item) {
+              if ((item & 1) != static_cast<int>(who)) continue;
+              if (item < kAItems) {
+                const uint32_t dst = A_MN ? sa + item * CHUNK_BYTES : sa + item * A_SUB_BYTES;  // K-major: one 128-row box per sub-tile
+                const int c0 = A_MN ? m0 + item * CHUNK_N : k0, c1 = A_MN ? k0 : m0 + item * 128;
+                if constexpr (CG == 1) tma_load_3d(dst, tma_a, fb, c0, c1, ba); else tma_load_3d_2sm(dst, tma_a, fb, c0, c1, ba);
+              } else {
+                const int c = item - kAItems;
+                const uint32_t dst = B_MN ? sb + c * CHUNK_BYTES : sb;
+                const int c0 = B_MN ? n0 + c * CHUNK_N : k0, c1 = B_MN ? k0 : n0;
+                if constexpr (CG == 1) tma_load_3d(dst, tma_b, fb, c0, c1, bb); else tma_load_3d_2sm(dst, tma_b, fb, c0, c1, bb);
+              }
             }
           }
           if constexpr (SCALED) {
@@ -355,7 +394,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
               else tma_load_3d_2sm(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, sf_row, tile);
             }
           }
-          if (++kk == seg_kb) { kk = 0; ++seg; }
+          if (++kk == (seg == 0 ? seg_kb : seg_kb1)) { kk = 0; ++seg; }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -373,11 +412,34 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           tcgen05_fence_after();
         }
         const uint32_t d_tmem = tmem_base + as * (MT * BLOCK_N);
+        uint32_t seg = 0, kk = 0;
+        if constexpr (KIND == KIND_TF32) seg_of(wu.kb0, seg, kk);
         for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
+          if constexpr (KIND == KIND_TF32 && MT == 1) {
+            if (hyb) {
+              const bool h16 = seg != 0;
+              if (++kk == (seg == 0 ? seg_kb : seg_kb1)) { kk = 0; ++seg; }
+              if (h16) {
+                // bf16 stage of the hybrid schedule: kind::f16 into the same accumulators.  MN-major bf16 operands use the
+                // plain 128-byte swizzle ([64 k-rows x 128 B] chunks 8192 B apart, 8 k-rows per atom); 16 elements of K per
+                // instruction = 32 bytes (K-major) or 16 k-rows = 2048 B (MN-major)
+                constexpr uint32_t IDESC16 = make_idesc(KIND_BF16, A_MN ? 1 : 0, B_MN ? 1 : 0, UMMA_M, BLOCK_N, 1u);
+                const uint64_t a16 = A_MN ? make_smem_desc_sw128(sa, 8192, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+                const uint64_t b16 = B_MN ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_ss<CG, KIND_BF16>(d_tmem, a16 + static_cast<uint64_t>(A_MN ? k * 128 : k * 2), b16 + static_cast<uint64_t>(B_MN ? k * 128 : k * 2),
+                                         IDESC16, (kb != wu.kb0 || k != 0) ? 1u : 0u);  // a stream-K part may START in a bf16 segment
+                umma_commit<CG>(empty_bar(s));
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+                continue;
+              }
+            }
+          }
           // K-major operand: rows of 128 B along K, 8-row swizzle atoms 1024 B apart (SBO).
           // MN-major operand: 128-byte rows run along M/N, 8 k-rows per atom (SBO 1024), next 128-byte M/N chunk
           // CHUNK_BYTES further (LBO).  32-bit MN-major operands only exist in the 32-byte-atom swizzle: 4 k-rows per

@@ -16,7 +16,7 @@ VARIANTS = ["2sm_n256", "2sm_n128", "1sm_n128"]
 def _reset_options(client):
     yield
     client.set_option("gemm.variant", "auto")
-    client.set_option("gemm.f32", "3xtf32")
+    client.set_option("gemm.f32", "hybrid")
     client.set_option("gemm.split_k", "auto")
     client.set_option("gemm.epilogue", "tma")
     client.set_option("gemm.stage", "on")
@@ -33,7 +33,7 @@ def test_golden_cmma_simple_1(client, golden, variant):
     assert got.ravel().tolist() == golden["cmma_simple_1"]["expected"]
 
 
-@pytest.mark.parametrize("mode", ["tf32", "3xtf32"])
+@pytest.mark.parametrize("mode", ["tf32", "3xtf32", "hybrid"])
 def test_golden_cmma_tf32(client, golden, mode):
     # cmma.rs:834-891: f32 inputs on the tf32 pipe, rhs row-major [8,16]; small integers are exact in tf32
     client.set_option("gemm.f32", mode)
@@ -95,7 +95,8 @@ def test_parity_16bit(client, variant, rhs_t, in_dtype, out_dtype):
 
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
-@pytest.mark.parametrize("mode,tol", [("tf32", 1e-3), ("3xtf32", 2e-6)])
+# hybrid (the default): tf32 product + bf16 cross terms -- the cross terms (~2^-11 of a product) carry bf16 rounding (2^-9)
+@pytest.mark.parametrize("mode,tol", [("tf32", 1e-3), ("3xtf32", 2e-6), ("hybrid", 3e-6)])
 def test_parity_f32(client, variant, rhs_t, mode, tol):
     client.set_option("gemm.variant", variant)
     client.set_option("gemm.f32", mode)
@@ -108,7 +109,8 @@ def test_parity_f32(client, variant, rhs_t, mode, tol):
 
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("rhs_t", [False, True], ids=["rhs_kn", "rhs_nk"])
-@pytest.mark.parametrize("in_dtype,mode,tol", [("bf16", "-", 1e-5), ("f16", "-", 1e-5), ("f32", "tf32", 1e-3), ("f32", "3xtf32", 2e-6)])
+@pytest.mark.parametrize("in_dtype,mode,tol", [("bf16", "-", 1e-5), ("f16", "-", 1e-5), ("f32", "tf32", 1e-3), ("f32", "3xtf32", 2e-6),
+                                                 ("f32", "hybrid", 3e-6)])
 def test_parity_transposed_lhs(client, variant, rhs_t, in_dtype, mode, tol):
     # lhs given as a transposed view of a [K, M] buffer (MildlyPermuted{transposed}, matrix_batch_layout.rs:8-19):
     # MN-major A operand through TMA, no into_contiguous copy
@@ -120,7 +122,7 @@ def test_parity_transposed_lhs(client, variant, rhs_t, in_dtype, mode, tol):
     b_dev, b = make_operand((N, K) if rhs_t else (K, N), in_dtype, 72)
     before = client.launch_count()
     got = run_matmul(client, a_dev, b_dev, in_dtype, "f32", rhs_transposed=rhs_t, lhs_transposed=True)
-    assert client.launch_count() - before == (3 if mode == "3xtf32" else 1)   # tcgen05 path (+2 split kernels), not SIMT
+    assert client.launch_count() - before == (3 if mode in ("3xtf32", "hybrid") else 1)   # tcgen05 path (+2 split kernels), not SIMT
     check_against_oracle(got, np.ascontiguousarray(a_km.T), b.T if rhs_t else b, "f32", tight=tol)
 
 
@@ -372,7 +374,8 @@ def test_tma_store_respects_pitched_output_window(client):
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("split", ["2", "3", "4"])
 @pytest.mark.parametrize("in_dtype,out_dtype,mode,tol", [("bf16", "f32", "-", 1e-5), ("bf16", "bf16", "-", 1e-2),
-                                                         ("f32", "f32", "3xtf32", 2e-6), ("f32", "f32", "tf32", 1e-3)])
+                                                         ("f32", "f32", "3xtf32", 2e-6), ("f32", "f32", "tf32", 1e-3),
+                                                         ("f32", "f32", "hybrid", 3e-6)])
 def test_tail_split_all_tiles(client, variant, split, in_dtype, out_dtype, mode, tol):
     # fewer tiles than CTA pairs: every tile is cut into K-slices; ragged M/N, K not a multiple of the slice count
     client.set_option("gemm.variant", variant)
@@ -468,7 +471,7 @@ def test_fuzz_shapes_layouts_dtypes(client):
         else:
             a_dev, a = make_operand(a_shape, dtype, 1000 + case)
             b_dev, b = make_operand(b_shape, dtype, 2000 + case)
-            client.set_option("gemm.f32", "3xtf32" if case % 2 else "tf32")
+            client.set_option("gemm.f32", ("3xtf32", "tf32", "hybrid")[case % 3])
             got = run_matmul(client, a_dev, b_dev, dtype, "f32", rhs_transposed=rhs_t, lhs_transposed=lhs_t)
             al = np.swapaxes(a, -1, -2) if lhs_t else a
             bl = np.swapaxes(b, -1, -2) if rhs_t else b
@@ -532,6 +535,47 @@ def test_batched_and_broadcast(client):
     b_dev, b = make_operand((1, K, N), "bf16", 55)
     got = run_matmul(client, a_dev, b_dev, "bf16", "f32")
     assert np.allclose(got, np.matmul(a.astype(np.float64), b.astype(np.float64)), rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode,tol", [("hybrid", 3e-6), ("3xtf32", 2e-6)])
+def test_f32_split_modes_batched_broadcast_ragged(client, mode, tol):
+    # the split-operand f32 schedules on batched / broadcast operands (pair-buffer planes are indexed per batch entry), every
+    # operand-major combination, K that is neither a multiple of 32 nor of 64, unaligned row pitches (pad to 16 bytes)
+    client.set_option("gemm.f32", mode)
+    M, N, K = 136, 200, 333
+    a_dev, a = make_operand((3, M, K), "f32", 81)
+    b_dev, b = make_operand((3, K, N), "f32", 82)
+    check_against_oracle(run_matmul(client, a_dev, b_dev, "f32", "f32"), a, b, "f32", tight=tol)
+    b1_dev, b1 = make_operand((1, K, N), "f32", 83)          # rhs broadcast over the batch: ONE pair buffer entry
+    check_against_oracle(run_matmul(client, a_dev, b1_dev, "f32", "f32"), a, b1, "f32", tight=tol)
+    a1_dev, a1 = make_operand((1, M, K), "f32", 84)
+    check_against_oracle(run_matmul(client, a1_dev, b_dev, "f32", "f32"), a1, b, "f32", tight=tol)
+    M, N, K = 264, 328, 520                                   # 16-byte aligned pitches for the transposed views
+    for lhs_t in (False, True):
+        for rhs_t in (False, True):
+            a_dev, a = make_operand((2, K, M) if lhs_t else (2, M, K), "f32", 85)
+            b_dev, b = make_operand((2, N, K) if rhs_t else (2, K, N), "f32", 86)
+            got = run_matmul(client, a_dev, b_dev, "f32", "f32", rhs_transposed=rhs_t, lhs_transposed=lhs_t)
+            check_against_oracle(got, np.swapaxes(a, -1, -2) if lhs_t else a, np.swapaxes(b, -1, -2) if rhs_t else b, "f32", tight=tol)
+
+
+@pytest.mark.parametrize("mode", ["hybrid", "tf32"])
+def test_f32_nonfinite_operands_propagate_like_f32(client, mode):
+    # hybrid: an infinite operand has no low part and is dropped from the cross terms (inf - inf, inf * 0 would poison them):
+    # inf * finite stays inf, NaN stays NaN.  (3xtf32 multiplies the ORIGINAL lhs by rhs_lo, so inf * 0 = NaN there: documented.)
+    client.set_option("gemm.f32", mode)
+    M, N, K = 128, 128, 64
+    a = np.ones((M, K), dtype=np.float32)
+    b = np.ones((K, N), dtype=np.float32)
+    a[3, 5] = np.inf
+    a[7, 9] = -np.inf
+    b[11, 13] = np.nan
+    got = run_matmul(client, a, b, "f32", "f32")
+    exp = a.astype(np.float64) @ b.astype(np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    fin = np.isfinite(exp)
+    assert np.array_equal(got[~fin & ~np.isnan(exp)], exp[~fin & ~np.isnan(exp)].astype(np.float32))
+    assert np.array_equal(got[fin], exp[fin].astype(np.float32))
 
 
 def test_pitched_output_and_inputs(client):
@@ -653,7 +697,7 @@ def test_bf16_8192_every_block_checksum(client):
     assert abs(float(got.astype(np.float64).sum()) - total) <= 12.0 * (2.0 ** -9) * np.sqrt(np.mean(got.astype(np.float64) ** 2)) * n / np.sqrt(3.0)
 
 
-@pytest.mark.parametrize("mode,rel", [("tf32", 2.0 ** -11), ("3xtf32", 2.0 ** -14)])
+@pytest.mark.parametrize("mode,rel", [("tf32", 2.0 ** -11), ("3xtf32", 2.0 ** -14), ("hybrid", 2.0 ** -14)])
 def test_f32_4096_every_block_checksum(client, mode, rel):
     # BASELINE config 2 at full size on the default plan (256 x 256 tiles with a stream-K head: 34 tiles are summed from two
     # K-halves): every output through the block checksums.  Noise model: tf32 rounds each operand to 11 bits (relative 2^-11 of the
@@ -704,7 +748,7 @@ def test_f32_4096_sampled_points(client):
     fabs = np.abs(a_rows).astype(np.float64) @ np.abs(b_cols).astype(np.float64).T
     # 3xtf32 at K = 4096: f32 accumulation of 3K products dominates (measured 4e-6); the reference-order f32 loop itself
     # is only good to ~K * 2^-24 = 2.4e-4 in the worst case
-    for mode, tol in (("tf32", 1e-3), ("3xtf32", 1e-5)):
+    for mode, tol in (("tf32", 1e-3), ("3xtf32", 1e-5), ("hybrid", 1e-5)):
         client.set_option("gemm.f32", mode)
         out = TensorHandle.empty_contiguous(client, [n, n], "f32")
         matmul.launch(client, a, b, out)

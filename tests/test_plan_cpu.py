@@ -88,20 +88,35 @@ def test_operand_major_combinations_pick_the_right_kernel(plan):
         assert rc == 0 and f"launch gemm_f16_f32_" in t and t.strip().endswith("cluster=2") and suffix + " grid" in t
 
 
-def test_f32_defaults_to_3xtf32_with_two_split_passes(plan):
+def test_f32_defaults_to_the_hybrid_schedule_with_two_split_passes(plan):
     n = 4096
+    rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc == 0
+    launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
+    # default: tf32 product of the originals + two bf16 cross terms, ONE gemm launch behind two pair-split passes
+    assert launches == ["split_f32_bf16_pair", "split_f32_bf16_pair", "gemm_tf32_f32_2sm_n256_kn"]
+    assert t.count("tmap ") == 5                                         # A, B (originals = hi) + bf16 pair buffers + C
+    assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
+    # pair buffers: (K, M, 2 planes) K-major box [64 k x 128 m]; (N, K, 2 planes) MN-major box [64 n x 64 k]; plain 128-byte swizzle
+    assert f"tmap esz=2 dims=({n},{n},2) strides=({2 * n},{2 * n * n}) box=(64,128) swizzle=3" in t
+    assert f"tmap esz=2 dims=({n},{n},2) strides=({2 * n},{2 * n * n}) box=(64,64) swizzle=3" in t
+    assert t.count(f"alloc {n * n * 4}") == 2                            # two bf16 planes per operand = 1x the operand bytes
+    # 256 tiles on 74 CTA pairs = 3.46 waves: the 34 tiles of the partial wave become a stream-K head, two equal halves each
+    assert "gemm stream-k head: 222 whole tiles + 34 tiles in 68 k-ranges" in t
+    plan.option("gemm.f32", "3xtf32")
     rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert rc == 0
     launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
     assert launches == ["split_tf32_lo", "split_tf32_lo", "gemm_tf32_f32_2sm_n256_kn"]   # lo parts only, ONE gemm launch
     assert t.count("tmap ") == 5                                         # A, B (originals = hi) + A_lo, B_lo + C
-    assert "box=(32,32) swizzle=4" in t                                  # f32 MN-major operand: 32-byte-atom swizzle
     assert t.count(f"alloc {n * n * 4}") == 2                            # 1x temporaries (lo parts), not 3x
-    # 256 tiles on 74 CTA pairs = 3.46 waves: the 34 tiles of the partial wave become a stream-K head, two equal halves each
     assert "gemm stream-k head: 222 whole tiles + 34 tiles in 68 k-ranges" in t
     plan.option("gemm.f32", "tf32")
     rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
     assert [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")] == ["gemm_tf32_f32_2sm_n256_kn"]
+    plan.option("gemm.f32", "bogus")
+    rc, t = plan.matmul(F32, F32, [n, n], [n, 1], [n, n], [n, 1], [n, n], [n, 1])
+    assert rc != 0
 
 
 def test_stream_k_head_policy(plan):
@@ -114,7 +129,7 @@ def test_stream_k_head_policy(plan):
     rc, t = mm(4096, 4096)                     # 2 waves of pair tiles (1.73 needed) lose to 3.46 waves of 256x256 tiles with a head
     assert rc == 0 and "222 whole tiles + 34 tiles in 68 k-ranges (<= 2 slabs per range)" in t and "2sm_n256" in t
     assert f"alloc {68 * 2 * 256 * 256 * 4}" in t and "grid=(148,1,1)" in t
-    rc, t = mm(4096, 4096, dt=F32, out=F32)    # 3xTF32 (BASELINE config 2): same cut, 384 k-blocks per tile
+    rc, t = mm(4096, 4096, dt=F32, out=F32)    # hybrid f32 (BASELINE config 2): same cut, 256 k-blocks per tile
     assert rc == 0 and "222 whole tiles + 34 tiles in 68 k-ranges" in t
     rc, t = mm(6144, 6144)                     # 3.89 waves of pair tiles: already 97 % full
     assert rc == 0 and "stream-k" not in t and "2sm_m512" in t
