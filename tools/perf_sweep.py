@@ -107,7 +107,7 @@ if "gemm" in what:
         c.fill_uniform(a.handle, idt, int(np.prod(shape)), 3, -1.0, 1.0)
         c.fill_uniform(b.handle, idt, int(np.prod(shape)), 4, -1.0, 1.0)
         flops = 2.0 * n * n * n * batch
-        for mode in (("tf32", "3xtf32") if idt == "f32" else ("-",)):
+        for mode in (("tf32", "3xtf32", "hybrid") if idt == "f32" else ("-",)):
             if idt == "f32":
                 c.set_option("gemm.f32", mode)
             for variant in (("2sm_m512", "2sm_n256", "2sm_n128", "1sm_n128") if idt == "bf16" else
@@ -192,7 +192,7 @@ if "split" in what:
         row.append(f"auto/best={fastest / best['auto']:.3f}")
         print(f"  {idt:6s}->{odt:4s} {mode:6s} {batch}x{m}x{n}x{k}: " + "  ".join(row), flush=True)
         c.set_option("gemm.split_k", "auto")
-        c.set_option("gemm.f32", "3xtf32")
+        c.set_option("gemm.f32", "hybrid")
         del a, b, o
 
 if "axis" in what:
@@ -233,18 +233,18 @@ if "axis" in what:
             del ts, out
 
 if "f32" in what:
-    print("f32 matmul on the tf32 pipe (f32-equivalent 2 M N K), whole launch sequence (3xTF32 = 2 lo-split passes + 1 GEMM):")
-    for n in (4096, 8192):
+    print("f32 matmul on the tensor pipes (f32-equivalent 2 M N K), whole launch sequence (hybrid / 3xTF32 = 2 split passes + 1 GEMM):")
+    for n in (2048, 4096, 8192):
         a = TensorHandle.empty_contiguous(c, [n, n], "f32")
         b = TensorHandle.empty_contiguous(c, [n, n], "f32")
         o = TensorHandle.empty_contiguous(c, [n, n], "f32")
         c.fill_uniform(a.handle, "f32", n * n, 1, -1.0, 1.0)
         c.fill_uniform(b.handle, "f32", n * n, 2, -1.0, 1.0)
-        for mode in ("tf32", "3xtf32"):
+        for mode in ("tf32", "3xtf32", "hybrid"):
             c.set_option("gemm.f32", mode)
             ms = min(time_ms(c, lambda: matmul.launch(c, a, b, o), iters=10, warm=3) for _ in range(3))
             print(f"  {n}^3 {mode:6s}: {ms * 1e3:8.1f} us  {2.0 * n ** 3 / ms / 1e9:7.1f} TFLOP/s", flush=True)
-        c.set_option("gemm.f32", "3xtf32")
+        c.set_option("gemm.f32", "hybrid")
         del a, b, o
 
 if "launch" in what:

@@ -61,6 +61,9 @@ else:
     elif what == "gemm_f32":
         shape, dt = [4096, 4096], "f32"
         c.set_option("gemm.f32", "tf32")
+    elif what == "gemm_f32_hybrid":
+        shape, dt = [4096, 4096], "f32"
+        c.set_option("gemm.f32", "hybrid")
     else:
         shape, dt = [8192, 8192], "bf16"
     n = 1
