@@ -887,15 +887,17 @@ static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
 
 // mx_kind: 0 = unscaled, 1 = mxf8 (one 512-byte scale chunk per 128 rows per k-block), 2 = mxf4 (two), 3 = nvfp4 (four)
 static unsigned mx_atoms(int mx_kind) { return mx_kind == 3 ? 4u : (unsigned)mx_kind; }
+// scale images of one stage: every 512-byte atom is staged as four replicas (2 KB), written by the TMA load through a zero-stride
+// dimension of the scale tensor map (gemm_tcgen05.cu)
 static unsigned gemm_sf_stage_bytes(const GemmVariant& v, int mx_kind) {
   if (!mx_kind) return 0;
-  const unsigned raw = 512u * mx_atoms(mx_kind) * (1 + (v.block_n + 127) / 128);
-  return (raw + 1023u) / 1024u * 1024u;
+  return 2048u * mx_atoms(mx_kind) * (1 + (v.block_n + 127) / 128);
 }
+// block-scaled kinds: as many stages as fit 227 KB, eight at most (mirror of mx_stages() in gemm_tcgen05.cu)
 static int gemm_stages(const GemmVariant& v, int mx_kind) {
-  if (v.block_n == 224) return mx_kind == 3 ? 5 : 6;                   // 36 KB / 32-33 KB stages
-  if (mx_kind == 3) return v.block_n == 256 ? 5 : v.cg == 2 ? 7 : 5;   // 38 / 28 / 36 KB stages
-  return (mx_kind == 2 && v.block_n == 256) ? 5 : v.stages;
+  if (!mx_kind) return v.stages;
+  const int stage = 16384 + (v.block_n / v.cg) * 128 + (int)gemm_sf_stage_bytes(v, mx_kind);
+  return std::min(8, (232448 - 1024 - 1024 - 16384) / stage);
 }
 // alignment slack + operand ring (+ scale chunks) + barrier block + epilogue staging (4 * mt warps x [32 rows x 128 B])
 static unsigned gemm_smem_bytes(const GemmVariant& v, int mx_kind = 0) {
@@ -940,6 +942,35 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
     return fail(B200_ERR_INVALID_ARG, "cuTensorMapEncodeTiled failed: %s (dims %llu,%llu,%llu strides %llu,%llu box %u,%u)",
                 cu_err(r), (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
                 (unsigned long long)strides[0], (unsigned long long)strides[1], b0, b1);
+  if (c->tmap_cache.size() > 512) c->tmap_cache.clear();
+  c->tmap_cache[key] = *out;
+  return B200_OK;
+}
+
+// Scale-factor tensor map: the packed tensor [tiles][k atoms][512 B] viewed as (16 B, 32 rows, 4 REPLICAS with stride 0, k atoms,
+// tiles); a box of (16, 32, 4, atoms, tiles) lands in shared memory as [tile][atom][replica][row] -- every atom as the 2 KB,
+// four-times replicated image the 128x256b TMEM copies read (gemm_tcgen05.cu).
+static int encode_sf_tmap(b200_ctx* c, CUtensorMap* out, uint64_t base, uint64_t k_atoms, uint64_t tiles, uint32_t box_atoms, uint32_t box_tiles) {
+  char key[256];
+  snprintf(key, sizeof(key), "sf|%llx|%llu|%llu|%u|%u", (unsigned long long)base, (unsigned long long)k_atoms, (unsigned long long)tiles, box_atoms, box_tiles);
+  if (c->dry) {
+    char line[256];
+    snprintf(line, sizeof(line), "tmap scales dims=(16,32,4,%llu,%llu) strides=(16,0,512,%llu) box=(16,32,4,%u,%u)\n", (unsigned long long)k_atoms,
+             (unsigned long long)tiles, (unsigned long long)(512 * k_atoms), box_atoms, box_tiles);
+    c->plan += line;
+    memset(out, 0, sizeof(*out));
+    return B200_OK;
+  }
+  auto it = c->tmap_cache.find(key);
+  if (it != c->tmap_cache.end()) { *out = it->second; return B200_OK; }
+  cuuint64_t dims[5] = {16, 32, 4, k_atoms, tiles};
+  cuuint64_t strides[4] = {16, 0, 512, 512 * k_atoms};
+  cuuint32_t box[5] = {16, 32, 4, box_atoms, box_tiles};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, reinterpret_cast<void*>(base), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200_ERR_INVALID_ARG, "cuTensorMapEncodeTiled (scales) failed: %s", cu_err(r));
   if (c->tmap_cache.size() > 512) c->tmap_cache.clear();
   c->tmap_cache[key] = *out;
   return B200_OK;
@@ -1101,6 +1132,7 @@ static const GemmVariant* pick_variant(b200_ctx* c, const GemmProblem& g, SkPlan
     if (!g.mx_kind && !variant_has_dtype(v, g.in_dtype)) continue;
     if (forced == "auto" && v.cg == 2 && g.M <= 128) continue;  // a CTA pair would idle its second half: one CTA per tile
     if (g.mx_kind && v.mt != 1) continue;                       // block-scaled kinds have no two-unit instantiation
+    if (g.mx_kind == 3 && v.block_n == 224) continue;           // NVFP4: 448 accumulator columns leave room for one scale buffer only
     if (v.block_n == 224 && !(g.mx_kind && (g.sfb_any_layout || g.sfb_tile_rows == 224))) continue;
     if (v.block_n != 224 && g.mx_kind && !g.sfb_any_layout && g.sfb_tile_rows == 224) continue;   // scales already packed for 224-row tiles
     // the two-unit tile hides its epilogue only on the packed-register path (16-bit outputs); f32 outputs stay on 2sm_n256
@@ -1201,12 +1233,11 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     const uint64_t tiles_a = (g.M + 127) / 128;
     const uint64_t tiles_b = g.sfb_tile_rows == 224 ? 2 * ((g.N + 223) / 224) : (g.N + 127) / 128;
     const uint64_t ab = a_bcast ? 1 : g.batch, bb = b_bcast ? 1 : g.batch;
-    rc = encode_tmap(c, &ta_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfa, 16, 32 * g.sf_atoms, tiles_a * ab, 16, 512 * g.sf_atoms,
-                     16, 32 * mx_atoms(g.mx_kind), CU_TENSOR_MAP_SWIZZLE_NONE, 1);
+    rc = encode_sf_tmap(c, &ta_lo, g.sfa, g.sf_atoms, tiles_a * ab, mx_atoms(g.mx_kind), 1);
     if (rc) return rc;
-    rc = encode_tmap(c, &tb_lo, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, g.sfb, 16, 32 * g.sf_atoms, tiles_b * bb, 16, 512 * g.sf_atoms,
-                     16, 32 * mx_atoms(g.mx_kind), CU_TENSOR_MAP_SWIZZLE_NONE, (v.block_n + 127) / 128);
+    rc = encode_sf_tmap(c, &tb_lo, g.sfb, g.sf_atoms, tiles_b * bb, mx_atoms(g.mx_kind), (v.block_n + 127) / 128);
     if (rc) return rc;
+    p.pad_ = opt(c, "gemm.sf_desc_swap", "off") == "on" ? 1u : 0u;   // bring-up switch: LBO / SBO roles of the 128x256b copy source
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }
