@@ -947,15 +947,16 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
   return B200_OK;
 }
 
-// Scale-factor tensor map: the packed tensor [tiles][k atoms][512 B] viewed as (16 B, 32 rows, 4 REPLICAS with stride 0, k atoms,
-// tiles); a box of (16, 32, 4, atoms, tiles) lands in shared memory as [tile][atom][replica][row] -- every atom as the 2 KB,
-// four-times replicated image the 128x256b TMEM copies read (gemm_tcgen05.cu).
+// Scale-factor tensor map: the packed tensor [tiles][k atoms][512 B] viewed as (half an atom = 64 words, 2 halves, 4 REPLICAS
+// with stride 0, k atoms, tiles); a box of (64, 2, 4, atoms, tiles) lands in shared memory as [tile][atom][replica][512 B] --
+// every atom as the 2 KB, four-times replicated image the 128x256b TMEM copies read (gemm_tcgen05.cu).  256-byte box rows: the
+// first version used (16 B, 32 rows, ...) boxes, whose 16-byte rows cost the TMA unit more than the k-block's MMAs.
 static int encode_sf_tmap(b200_ctx* c, CUtensorMap* out, uint64_t base, uint64_t k_atoms, uint64_t tiles, uint32_t box_atoms, uint32_t box_tiles) {
   char key[256];
   snprintf(key, sizeof(key), "sf|%llx|%llu|%llu|%u|%u", (unsigned long long)base, (unsigned long long)k_atoms, (unsigned long long)tiles, box_atoms, box_tiles);
   if (c->dry) {
     char line[256];
-    snprintf(line, sizeof(line), "tmap scales dims=(16,32,4,%llu,%llu) strides=(16,0,512,%llu) box=(16,32,4,%u,%u)\n", (unsigned long long)k_atoms,
+    snprintf(line, sizeof(line), "tmap scales esz=4 dims=(64,2,4,%llu,%llu) strides=(256,0,512,%llu) box=(64,2,4,%u,%u)\n", (unsigned long long)k_atoms,
              (unsigned long long)tiles, (unsigned long long)(512 * k_atoms), box_atoms, box_tiles);
     c->plan += line;
     memset(out, 0, sizeof(*out));
@@ -963,11 +964,11 @@ static int encode_sf_tmap(b200_ctx* c, CUtensorMap* out, uint64_t base, uint64_t
   }
   auto it = c->tmap_cache.find(key);
   if (it != c->tmap_cache.end()) { *out = it->second; return B200_OK; }
-  cuuint64_t dims[5] = {16, 32, 4, k_atoms, tiles};
-  cuuint64_t strides[4] = {16, 0, 512, 512 * k_atoms};
-  cuuint32_t box[5] = {16, 32, 4, box_atoms, box_tiles};
+  cuuint64_t dims[5] = {64, 2, 4, k_atoms, tiles};
+  cuuint64_t strides[4] = {256, 0, 512, 512 * k_atoms};
+  cuuint32_t box[5] = {64, 2, 4, box_atoms, box_tiles};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, reinterpret_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, reinterpret_cast<void*>(base), dims, strides, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200_ERR_INVALID_ARG, "cuTensorMapEncodeTiled (scales) failed: %s", cu_err(r));
@@ -1237,7 +1238,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (rc) return rc;
     rc = encode_sf_tmap(c, &tb_lo, g.sfb, g.sf_atoms, tiles_b * bb, mx_atoms(g.mx_kind), (v.block_n + 127) / 128);
     if (rc) return rc;
-    p.pad_ = opt(c, "gemm.sf_desc_swap", "off") == "on" ? 1u : 0u;   // bring-up switch: LBO / SBO roles of the 128x256b copy source
+    p.pad_ = opt(c, "gemm.sf_copy", "thread") == "mma" ? 1u : 0u;   // A/B switch: copies issued by the MMA thread (round-2 scheme)
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }

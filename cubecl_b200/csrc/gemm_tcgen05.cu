@@ -205,7 +205,7 @@ __device__ __forceinline__ bool next_unit(UnitIter& it, const GemmParams& p, Wor
 // MMAs -> sf_empty), and (b) atoms go two per copy with the 128x256b shape (each lane takes its own 32-byte row: 16 B of one
 // atom image + 16 B of another).  That shape does not broadcast over the lane quarters, so the shared-memory image of an atom
 // is the 512-byte chunk four times over (2 KB) -- written by the TMA load itself through a ZERO-STRIDE dimension of the
-// scale tensor map (dims: 16 B, 32 rows, 4 replicas with stride 0, k atoms, row tiles): no extra global bytes, no extra pass.
+// scale tensor map (dims: 256 B, 2 halves of the atom, 4 replicas with stride 0, k atoms, row tiles): no extra global bytes, no extra pass.
 // ACC = accumulator stages in TMEM: 256-wide scaled tiles have room for one only (512 columns - scale columns).
 // MT = 128-row sub-tiles of M per CTA.  MT = 2 (CG = 2, BLOCK_N = 256, ACC = 1) is the 512 x 256 pair tile: each CTA stages
 // 256 rows of A and half of B per k-block (48 KB, 4 stages) and holds two 128 x 256 accumulators -- all 512 TMEM columns.
@@ -401,7 +401,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           }
           if constexpr (SCALED) {
             // scale atoms of this k-block as replicated images: A rows of this CTA (one 128-row tile), B rows of the whole BLOCK_N
-            // (the MMA of each CTA of a pair needs the scales of all N columns); box = (16 B, 32 rows, 4 replicas, atoms, tiles)
+            // (the MMA of each CTA of a pair needs the scales of all N columns); box = (256 B, 2 halves, 4 replicas, atoms, tiles)
             const int atom0 = static_cast<int>(kk * SF_ATOMS);
             if (who == 0) {
               const int tile = static_cast<int>(tc.b * p.a_bmul * p.sf_tiles_a + tc.m_blk * CG + rank);
@@ -470,10 +470,25 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           const uint64_t a_desc = A_MN ? mn_desc(sa) : make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t b_desc = B_MN ? mn_desc(sb) : make_smem_desc_sw128(sb, 16, 1024);
           if constexpr (SCALED) {
-            // the scale-copy thread (warp 2) has put this k-block's atoms into TMEM scale buffer sfb_i
-            mbar_wait(sf_full_bar(sfb_i), sfb_ph);
-            tcgen05_fence_after();
             const uint32_t sf_t = tmem_base + sfb_i * SF_COLS;
+            if (p.pad_ & 1u) {
+              // gemm.sf_copy=mma (A/B switch): the MMA thread copies the atoms itself, one broadcast copy per atom from the first
+              // replica of its image, in front of the MMAs that read them (the round-2 scheme)
+              const uint32_t sfa_s = sb + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
+#pragma unroll
+              for (int atom = 0; atom < SF_ATOMS; ++atom)
+                tmem_cp_32x128b_warpx4<CG>(sf_t + SFA_COL + 4u * atom, make_smem_desc(sfa_s + SF_IMG * atom, 0, 128, 0));
+#pragma unroll
+              for (int tile = 0; tile < SF_TILES_B; ++tile)
+#pragma unroll
+                for (int atom = 0; atom < SF_ATOMS; ++atom)
+                  tmem_cp_32x128b_warpx4<CG>(sf_t + SFB_COL + 4u * (atom * SF_TILES_B + tile),
+                                             make_smem_desc(sfb_s + SF_IMG * (tile * SF_ATOMS + atom), 0, 128, 0));
+            } else {
+              // the scale-copy thread (warp 2) has put this k-block's atoms into TMEM scale buffer sfb_i
+              mbar_wait(sf_full_bar(sfb_i), sfb_ph);
+              tcgen05_fence_after();
+            }
             const uint32_t idesc_base = make_idesc_scaled(p.sf_fmt_a, p.sf_fmt_b, UMMA_M, BLOCK_N, KIND == KIND_NVF4 ? 0u : 1u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -483,7 +498,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                                                               idesc_base | (sf_id << 29) | (sf_id << 4), sf_t + SFA_COL + 4u * atom,
                                                               sf_t + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
-            umma_commit<CG>(sf_empty_bar(sfb_i));  // buffer reusable once these MMAs retire
+            if (!(p.pad_ & 1u)) umma_commit<CG>(sf_empty_bar(sfb_i));  // buffer reusable once these MMAs retire
             if (++sfb_i == SF_NB) { sfb_i = 0; sfb_ph ^= 1; }
           } else if constexpr (MT == 1) {
 #pragma unroll
@@ -523,11 +538,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   } else if (warp == 2) {
     // ===================================================================== scale-copy thread (block-scaled kinds, leader CTA)
     if constexpr (SCALED) {
-      if (leader && lane == 0) {
+      if (leader && lane == 0 && !(p.pad_ & 1u)) {
         // 128-row source of a 128x256b copy: row R = 32 q + r of an atom image at R * 16 B (8-row groups 128 B apart: SBO), the
-        // second 16 bytes of each lane's row from another image `lbo` bytes further (LBO); gemm.sf_desc_swap flips the two fields
-        const bool swap = (p.pad_ & 1u) != 0;
-        auto wide_desc = [&](uint32_t addr, uint32_t lbo) { return swap ? make_smem_desc(addr, 128, lbo, 0) : make_smem_desc(addr, lbo, 128, 0); };
+        // second 16 bytes of each lane's row from another image `lbo` bytes further (LBO)
+        auto wide_desc = [&](uint32_t addr, uint32_t lbo) { return make_smem_desc(addr, lbo, 128, 0); };
         uint32_t s = 0, ph = 0, bi = 0, bph = 0;
         UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
         WorkUnit wu;

@@ -150,7 +150,7 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
       : "memory");
 }
 
-// 5-D tiled loads (scale-factor images: 16 B, 32 rows, 4 zero-stride replicas, k atoms, row tiles)
+// 5-D tiled loads (scale-factor images: 256 B, 2 halves of the 512-byte atom, 4 zero-stride replicas, k atoms, row tiles)
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"

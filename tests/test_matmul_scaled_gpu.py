@@ -164,7 +164,8 @@ def check_nvfp4(got, a, b, sa, sb, tol):
     return o32
 
 
-@pytest.mark.parametrize("variant", ["simt"] + TC_VARIANTS)
+# (no 256 x 224 NVFP4 tile: its two accumulator stages leave TMEM room for ONE 48-column scale buffer, the copy thread needs two)
+@pytest.mark.parametrize("variant", ["simt"] + [v for v in TC_VARIANTS if v != "2sm_n224"])
 @pytest.mark.parametrize("out_dtype,tol", [("f32", 2e-6), ("bf16", 1e-2)])
 @pytest.mark.parametrize("M,N,K", [(16, 8, 64), (300, 520, 1024), (128, 256, 96), (257, 129, 2048)])
 def test_parity_nvfp4(client, variant, out_dtype, tol, M, N, K):

@@ -159,6 +159,29 @@ if "scaled" in what:
         c.set_option("gemm.variant", "auto")
         del a, b, o
 
+if "scaledab" in what:
+    # block-scaled GEMM, 256 x 256 tile, pre-packed scales: scale atoms copied by the dedicated thread (default) vs by the MMA thread
+    print("block-scaled matmul 8192^3 -> bf16, pre-packed scales, CUDA events; gemm.sf_copy = thread | mma:")
+    n = k = 8192
+    for (dt, blk) in (("f8e4m3", 32), ("f4e2m1x2", 32), ("f4e2m1x2", 16)):
+        kb = k // 2 if dt == "f4e2m1x2" else k
+        a = TensorHandle.empty_contiguous(c, [n, kb], dt)
+        b = TensorHandle.empty_contiguous(c, [n, kb], dt)
+        o = TensorHandle.empty_contiguous(c, [n, n], "bf16")
+        c.fill_uniform(a.handle, "f8e4m3", n * kb, 3, -1.0, 1.0)
+        c.fill_uniform(b.handle, "f8e4m3", n * kb, 4, -1.0, 1.0)
+        tiles, atoms = n // 128, k // (4 * blk)
+        pa = TensorHandle.from_numpy(c, np.full((tiles, atoms, 512), 127 if blk == 32 else 0x38, np.uint8), "ue8m0" if blk == 32 else "f8e4m3")
+        flops = 2.0 * n * n * k
+        res = []
+        for mode in ("thread", "mma", "thread"):
+            c.set_option("gemm.sf_copy", mode)
+            ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scale_block=blk, scales_packed=True), iters=10, warm=2) for _ in range(3))
+            res.append(f"{mode}: {ms * 1e3:7.1f} us {flops / ms / 1e9:6.0f} TF/s")
+        print(f"  {dt:9s} scale/{blk}: " + " | ".join(res) + f"  [{c.last_kernel()}]", flush=True)
+        del a, b, o
+    c.set_option("gemm.sf_copy", "thread")
+
 if "split" in what:
     # tail split (deterministic split-K of the last partial wave): off vs forced S vs the auto policy
     print("gemm.split_k sweep (auto variant), CUDA events:")
