@@ -549,7 +549,7 @@ extern "C" int b200_get_props(b200_ctx* c, b200_props* out) {
 
 extern "C" int b200_set_option(b200_ctx* c, const char* key, const char* value) {
   if (!c || !key || !value) return fail(B200_ERR_INVALID_ARG, "null argument");
-  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "gemm.stage", "reduce.variant", "reduce.threads",
+  static const char* known[] = {"gemm.variant", "gemm.f32", "gemm.group_m", "gemm.split_k", "gemm.epilogue", "gemm.l2_promotion", "gemm.stage", "gemm.sf_copy", "reduce.variant", "reduce.threads",
                                 "reduce.blocks_per_sm", "reduce.rows_vpt", "reduce.rows_blocks_per_sm", "reduce.cols_blocks_per_sm",
                                 "reduce.debug", "reduce.pdl", "reduce.tma_stages", "reduce.tma_ctas_per_sm", "reduce.cols_split_target", "reduce.cols_loads", "reduce.cols_fused"};
   for (const char* k : known)
@@ -1238,7 +1238,10 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (rc) return rc;
     rc = encode_sf_tmap(c, &tb_lo, g.sfb, g.sf_atoms, tiles_b * bb, mx_atoms(g.mx_kind), (v.block_n + 127) / 128);
     if (rc) return rc;
-    p.pad_ = opt(c, "gemm.sf_copy", "thread") == "mma" ? 1u : 0u;   // A/B switch: copies issued by the MMA thread (round-2 scheme)
+    {  // A/B switches: scale copies issued by the MMA thread (round-2 scheme), or by the copy thread one atom at a time
+      const std::string sfc = opt(c, "gemm.sf_copy", "thread");
+      p.pad_ = sfc == "mma" ? 1u : sfc == "thread_x4" ? 2u : 0u;
+    }
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }

@@ -552,6 +552,16 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             tcgen05_fence_after();
             const uint32_t sfa_s = smem_base + s * STAGE_BYTES + A_BYTES + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
             const uint32_t sfa_t = tmem_base + bi * SF_COLS + SFA_COL, sfb_t = tmem_base + bi * SF_COLS + SFB_COL;
+            if (p.pad_ & 2u) {
+              // gemm.sf_copy=thread_x4 (A/B switch): one broadcast copy per atom from this thread
+#pragma unroll
+              for (int a = 0; a < SF_ATOMS; ++a) tmem_cp_32x128b_warpx4<CG>(sfa_t + 4u * a, make_smem_desc(sfa_s + SF_IMG * a, 0, 128, 0));
+#pragma unroll
+              for (int t = 0; t < SF_TILES_B; ++t)
+#pragma unroll
+                for (int a = 0; a < SF_ATOMS; ++a)
+                  tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * (a * SF_TILES_B + t), make_smem_desc(sfb_s + SF_IMG * (t * SF_ATOMS + a), 0, 128, 0));
+            } else {
             // A atoms (TMEM columns 4 a): consecutive atoms in pairs, a last odd one as a broadcast copy of its first replica
 #pragma unroll
             for (int a = 0; a < SF_ATOMS; a += 2) {
@@ -568,6 +578,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                 if (a + 1 < SF_ATOMS) tmem_cp_128x256b<CG>(sfb_t + 4u * a, wide_desc(sfb_s + SF_IMG * a, SF_IMG));
                 else tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * a, make_smem_desc(sfb_s + SF_IMG * a, 0, 128, 0));
               }
+            }
             }
             umma_commit<CG>(sf_full_bar(bi));      // arrives when the copies have completed
             if (++s == STAGES) { s = 0; ph ^= 1; }
