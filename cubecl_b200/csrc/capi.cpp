@@ -887,11 +887,10 @@ static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
 
 // mx_kind: 0 = unscaled, 1 = mxf8 (one 512-byte scale chunk per 128 rows per k-block), 2 = mxf4 (two), 3 = nvfp4 (four)
 static unsigned mx_atoms(int mx_kind) { return mx_kind == 3 ? 4u : (unsigned)mx_kind; }
-// scale images of one stage: every 512-byte atom is staged as four replicas (2 KB), written by the TMA load through a zero-stride
-// dimension of the scale tensor map (gemm_tcgen05.cu)
+// scale atoms of one stage (512 bytes each: A rows of the CTA, B rows of the whole tile), padded to the 1 KB stage alignment
 static unsigned gemm_sf_stage_bytes(const GemmVariant& v, int mx_kind) {
   if (!mx_kind) return 0;
-  return 2048u * mx_atoms(mx_kind) * (1 + (v.block_n + 127) / 128);
+  return (512u * mx_atoms(mx_kind) * (1 + (v.block_n + 127) / 128) + 1023u) / 1024u * 1024u;
 }
 // block-scaled kinds: as many stages as fit 227 KB, eight at most (mirror of mx_stages() in gemm_tcgen05.cu)
 static int gemm_stages(const GemmVariant& v, int mx_kind) {
@@ -947,16 +946,15 @@ static int encode_tmap(b200_ctx* c, CUtensorMap* out, CUtensorMapDataType dt, si
   return B200_OK;
 }
 
-// Scale-factor tensor map: the packed tensor [tiles][k atoms][512 B] viewed as (half an atom = 64 words, 2 halves, 4 REPLICAS
-// with stride 0, k atoms, tiles); a box of (64, 2, 4, atoms, tiles) lands in shared memory as [tile][atom][replica][512 B] --
-// every atom as the 2 KB, four-times replicated image the 128x256b TMEM copies read (gemm_tcgen05.cu).  256-byte box rows: the
-// first version used (16 B, 32 rows, ...) boxes, whose 16-byte rows cost the TMA unit more than the k-block's MMAs.
+// Scale-factor tensor map: the packed tensor [tiles][k atoms][512 B] viewed as (one 512-byte atom = 128 words, k atoms, tiles);
+// a box of (128, atoms, tiles) lands in shared memory as [tile][atom][512 B].  Whole atoms are the box rows: round 2 used
+// (16 B, 32 rows x atoms, tiles) boxes, whose 16-byte rows cost the TMA unit far more per byte.
 static int encode_sf_tmap(b200_ctx* c, CUtensorMap* out, uint64_t base, uint64_t k_atoms, uint64_t tiles, uint32_t box_atoms, uint32_t box_tiles) {
   char key[256];
   snprintf(key, sizeof(key), "sf|%llx|%llu|%llu|%u|%u", (unsigned long long)base, (unsigned long long)k_atoms, (unsigned long long)tiles, box_atoms, box_tiles);
   if (c->dry) {
     char line[256];
-    snprintf(line, sizeof(line), "tmap scales esz=4 dims=(64,2,4,%llu,%llu) strides=(256,0,512,%llu) box=(64,2,4,%u,%u)\n", (unsigned long long)k_atoms,
+    snprintf(line, sizeof(line), "tmap scales esz=4 dims=(128,%llu,%llu) strides=(512,%llu) box=(128,%u,%u)\n", (unsigned long long)k_atoms,
              (unsigned long long)tiles, (unsigned long long)(512 * k_atoms), box_atoms, box_tiles);
     c->plan += line;
     memset(out, 0, sizeof(*out));
@@ -964,11 +962,11 @@ static int encode_sf_tmap(b200_ctx* c, CUtensorMap* out, uint64_t base, uint64_t
   }
   auto it = c->tmap_cache.find(key);
   if (it != c->tmap_cache.end()) { *out = it->second; return B200_OK; }
-  cuuint64_t dims[5] = {64, 2, 4, k_atoms, tiles};
-  cuuint64_t strides[4] = {256, 0, 512, 512 * k_atoms};
-  cuuint32_t box[5] = {64, 2, 4, box_atoms, box_tiles};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, reinterpret_cast<void*>(base), dims, strides, box, estr,
+  cuuint64_t dims[3] = {128, k_atoms, tiles};
+  cuuint64_t strides[2] = {512, 512 * k_atoms};
+  cuuint32_t box[3] = {128, box_atoms, box_tiles};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_drv.cuTensorMapEncodeTiled_p(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, reinterpret_cast<void*>(base), dims, strides, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200_ERR_INVALID_ARG, "cuTensorMapEncodeTiled (scales) failed: %s", cu_err(r));
@@ -1238,10 +1236,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (rc) return rc;
     rc = encode_sf_tmap(c, &tb_lo, g.sfb, g.sf_atoms, tiles_b * bb, mx_atoms(g.mx_kind), (v.block_n + 127) / 128);
     if (rc) return rc;
-    {  // A/B switches: scale copies issued by the MMA thread (round-2 scheme), or by the copy thread one atom at a time
-      const std::string sfc = opt(c, "gemm.sf_copy", "thread");
-      p.pad_ = sfc == "mma" ? 1u : sfc == "thread_x4" ? 2u : 0u;
-    }
+    p.pad_ = opt(c, "gemm.sf_copy", "thread") == "mma" ? 1u : 0u;   // A/B switch: scale copies issued by the MMA thread (round-2 scheme)
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }

@@ -199,13 +199,12 @@ __device__ __forceinline__ bool next_unit(UnitIter& it, const GemmParams& p, Wor
 // How the atoms get to TMEM (round 3, measured with tools/microbench/tmem_cp_probe.cu, profiles/r03_tmem_cp_probe.log):
 // a tcgen05.cp blocks the issuing thread's tensor-core queue for 150-190 cycles, so three 32x128b.warpx4 copies issued by
 // the MMA thread in front of the four MMAs of a k-block (512 cycles of tensor work) made the k-block 770-840 cycles, six
-// 1260-1360, twelve 2050.  Copies issued by ANOTHER warp run beside the MMAs: two per k-block are free, three 128x256b
-// copies are free, six cost 690.  So (a) a dedicated scale-copy thread (warp 2) feeds a ring of TMEM scale buffers,
-// synchronised with the MMA thread by two mbarriers per buffer (tcgen05.commit of the copies -> sf_full, tcgen05.commit of the
-// MMAs -> sf_empty), and (b) atoms go two per copy with the 128x256b shape (each lane takes its own 32-byte row: 16 B of one
-// atom image + 16 B of another).  That shape does not broadcast over the lane quarters, so the shared-memory image of an atom
-// is the 512-byte chunk four times over (2 KB) -- written by the TMA load itself through a ZERO-STRIDE dimension of the
-// scale tensor map (dims: 256 B, 2 halves of the atom, 4 replicas with stride 0, k atoms, row tiles): no extra global bytes, no extra pass.
+// 1260-1360, twelve 2050.  Copies issued by ANOTHER warp run beside the MMAs.  So a dedicated scale-copy thread (warp 2)
+// feeds a ring of TMEM scale buffers, synchronised with the MMA thread by two mbarriers per buffer (tcgen05.commit of the
+// copies -> sf_full, tcgen05.commit of the MMAs -> sf_empty).  Measured on 8192^3 (profiles/r03_scaled_ab.log, same box, copies
+// by the MMA thread -> by the copy thread): mxfp8 2437 -> 2589 TFLOP/s, mxfp4 3417 -> 4100, nvfp4 2832 -> 3500.  Two atoms per
+// 128x256b copy (from four-times replicated images written by the TMA load through a zero-stride tensor-map dimension, which
+// works) measured the SAME as one broadcast copy per atom once the copies left the MMA thread, so the plain form stays.
 // ACC = accumulator stages in TMEM: 256-wide scaled tiles have room for one only (512 columns - scale columns).
 // MT = 128-row sub-tiles of M per CTA.  MT = 2 (CG = 2, BLOCK_N = 256, ACC = 1) is the 512 x 256 pair tile: each CTA stages
 // 256 rows of A and half of B per k-block (48 KB, 4 stages) and holds two 128 x 256 accumulators -- all 512 TMEM columns.
@@ -228,9 +227,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   // groups are never spread over unaligned chunks.  224 columns are what lets TWO accumulator stages (448 columns) and the
   // scale columns (12 / 24 / 48) share the 512 TMEM columns -- the 256-wide scaled tiles have one stage and an exposed drain.
   constexpr int SF_TILES_B = (BLOCK_N + 127) / 128;
-  constexpr uint32_t SF_IMG = 2048;   // one atom in shared memory: the 512-byte chunk replicated over the four lane quarters
+  constexpr uint32_t SF_IMG = 512;    // one atom in shared memory, as packed
   constexpr uint32_t SFA_BYTES = SF_IMG * SF_ATOMS, SFB_BYTES = SF_IMG * SF_ATOMS * SF_TILES_B;
-  constexpr uint32_t SF_BYTES = SFA_BYTES + SFB_BYTES;
+  constexpr uint32_t SF_BYTES = (SFA_BYTES + SFB_BYTES + 1023u) / 1024u * 1024u;
   constexpr uint32_t SF_COLS = 4u * SF_ATOMS * (1 + SF_TILES_B);   // TMEM columns of one scale buffer: A atoms, then B atoms (atom-major, tile-minor)
   constexpr int ESZ = (KIND == KIND_TF32) ? 4 : (KIND >= KIND_E4M3) ? 1 : 2;
   // operand format field of the instruction descriptor (meaning depends on the MMA kind)
@@ -400,17 +399,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             }
           }
           if constexpr (SCALED) {
-            // scale atoms of this k-block as replicated images: A rows of this CTA (one 128-row tile), B rows of the whole BLOCK_N
-            // (the MMA of each CTA of a pair needs the scales of all N columns); box = (256 B, 2 halves, 4 replicas, atoms, tiles)
+            // scale atoms of this k-block: A rows of this CTA (one 128-row tile), B rows of the whole BLOCK_N (the MMA of each CTA
+            // of a pair needs the scales of all N columns); box = (one 512-byte atom, atoms, tiles) -> smem [tile][atom][512 B]
             const int atom0 = static_cast<int>(kk * SF_ATOMS);
             if (who == 0) {
               const int tile = static_cast<int>(tc.b * p.a_bmul * p.sf_tiles_a + tc.m_blk * CG + rank);
-              if constexpr (CG == 1) tma_load_5d(sb + B_BYTES, tma_a_lo, fb, 0, 0, 0, atom0, tile);
-              else tma_load_5d_2sm(sb + B_BYTES, tma_a_lo, fb, 0, 0, 0, atom0, tile);
+              if constexpr (CG == 1) tma_load_3d(sb + B_BYTES, tma_a_lo, fb, 0, atom0, tile);
+              else tma_load_3d_2sm(sb + B_BYTES, tma_a_lo, fb, 0, atom0, tile);
             } else {
               const int tile = static_cast<int>(tc.b * p.b_bmul * p.sf_tiles_b + tc.n_blk * SF_TILES_B);
-              if constexpr (CG == 1) tma_load_5d(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, 0, 0, atom0, tile);
-              else tma_load_5d_2sm(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, 0, 0, atom0, tile);
+              if constexpr (CG == 1) tma_load_3d(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, atom0, tile);
+              else tma_load_3d_2sm(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, atom0, tile);
             }
           }
           if (++kk == (seg == 0 ? seg_kb : seg_kb1)) { kk = 0; ++seg; }
@@ -472,8 +471,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           if constexpr (SCALED) {
             const uint32_t sf_t = tmem_base + sfb_i * SF_COLS;
             if (p.pad_ & 1u) {
-              // gemm.sf_copy=mma (A/B switch): the MMA thread copies the atoms itself, one broadcast copy per atom from the first
-              // replica of its image, in front of the MMAs that read them (the round-2 scheme)
+              // gemm.sf_copy=mma (A/B switch): the MMA thread copies the atoms itself, one broadcast copy per atom, in front of
+              // the MMAs that read them (the round-2 scheme)
               const uint32_t sfa_s = sb + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
 #pragma unroll
               for (int atom = 0; atom < SF_ATOMS; ++atom)
@@ -539,9 +538,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     // ===================================================================== scale-copy thread (block-scaled kinds, leader CTA)
     if constexpr (SCALED) {
       if (leader && lane == 0 && !(p.pad_ & 1u)) {
-        // 128-row source of a 128x256b copy: row R = 32 q + r of an atom image at R * 16 B (8-row groups 128 B apart: SBO), the
-        // second 16 bytes of each lane's row from another image `lbo` bytes further (LBO)
-        auto wide_desc = [&](uint32_t addr, uint32_t lbo) { return make_smem_desc(addr, lbo, 128, 0); };
         uint32_t s = 0, ph = 0, bi = 0, bph = 0;
         UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
         WorkUnit wu;
@@ -552,34 +548,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             tcgen05_fence_after();
             const uint32_t sfa_s = smem_base + s * STAGE_BYTES + A_BYTES + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
             const uint32_t sfa_t = tmem_base + bi * SF_COLS + SFA_COL, sfb_t = tmem_base + bi * SF_COLS + SFB_COL;
-            if (p.pad_ & 2u) {
-              // gemm.sf_copy=thread_x4 (A/B switch): one broadcast copy per atom from this thread
+            // one broadcast copy per atom (32 rows x 16 B, 8-row groups 128 B apart): A atoms to TMEM columns 4 a, B atoms to
+            // 4 (a T + t); smem atoms are [tile][atom]
 #pragma unroll
-              for (int a = 0; a < SF_ATOMS; ++a) tmem_cp_32x128b_warpx4<CG>(sfa_t + 4u * a, make_smem_desc(sfa_s + SF_IMG * a, 0, 128, 0));
+            for (int a = 0; a < SF_ATOMS; ++a) tmem_cp_32x128b_warpx4<CG>(sfa_t + 4u * a, make_smem_desc(sfa_s + SF_IMG * a, 0, 128, 0));
 #pragma unroll
-              for (int t = 0; t < SF_TILES_B; ++t)
+            for (int t = 0; t < SF_TILES_B; ++t)
 #pragma unroll
-                for (int a = 0; a < SF_ATOMS; ++a)
-                  tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * (a * SF_TILES_B + t), make_smem_desc(sfb_s + SF_IMG * (t * SF_ATOMS + a), 0, 128, 0));
-            } else {
-            // A atoms (TMEM columns 4 a): consecutive atoms in pairs, a last odd one as a broadcast copy of its first replica
-#pragma unroll
-            for (int a = 0; a < SF_ATOMS; a += 2) {
-              if (a + 1 < SF_ATOMS) tmem_cp_128x256b<CG>(sfa_t + 4u * a, wide_desc(sfa_s + SF_IMG * a, SF_IMG));
-              else tmem_cp_32x128b_warpx4<CG>(sfa_t + 4u * a, make_smem_desc(sfa_s + SF_IMG * a, 0, 128, 0));
-            }
-            if constexpr (SF_TILES_B == 2) {
-              // B atoms (TMEM columns 4 (2 a + t)): the two row tiles of one atom per copy; smem images are [tile][atom]
-#pragma unroll
-              for (int a = 0; a < SF_ATOMS; ++a) tmem_cp_128x256b<CG>(sfb_t + 8u * a, wide_desc(sfb_s + SF_IMG * a, SF_IMG * SF_ATOMS));
-            } else {
-#pragma unroll
-              for (int a = 0; a < SF_ATOMS; a += 2) {
-                if (a + 1 < SF_ATOMS) tmem_cp_128x256b<CG>(sfb_t + 4u * a, wide_desc(sfb_s + SF_IMG * a, SF_IMG));
-                else tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * a, make_smem_desc(sfb_s + SF_IMG * a, 0, 128, 0));
-              }
-            }
-            }
+              for (int a = 0; a < SF_ATOMS; ++a)
+                tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * (a * SF_TILES_B + t), make_smem_desc(sfb_s + SF_IMG * (t * SF_ATOMS + a), 0, 128, 0));
             umma_commit<CG>(sf_full_bar(bi));      // arrives when the copies have completed
             if (++s == STAGES) { s = 0; ph ^= 1; }
             if (++bi == SF_NB) { bi = 0; bph ^= 1; }
@@ -988,11 +965,11 @@ extern "C" __global__ void __launch_bounds__(kNumThreads, 1) umma_probe_bf16_2sm
 #endif  // GEMM_PART == 0
 
 #if GEMM_PART == 1
-// Block-scaled (MX) kinds: K-major operands only (lhs [M,K], rhs [N,K]); stage = operands + replicated scale images (2 KB per atom).
+// Block-scaled (MX) kinds: K-major operands only (lhs [M,K], rhs [N,K]); stage = operands + scale atoms (512 B each).
 //   gemm_mxf8_<out>_<tile>_kk: e4m3 / e5m2 (either per operand), gemm_mxf4_<out>_<tile>_kk: packed e2m1
 // Stages: as many as fit 227 KB beside the barrier block and the epilogue staging, eight at most (host mirror: gemm_stages()).
 __host__ __device__ constexpr int mx_stages(int cg, int block_n, int atoms) {
-  const int stage = 16384 + (block_n / cg) * 128 + 2048 * atoms * (1 + (block_n + 127) / 128);
+  const int stage = 16384 + (block_n / cg) * 128 + (512 * atoms * (1 + (block_n + 127) / 128) + 1023) / 1024 * 1024;
   const int fit = (232448 - 1024 - 1024 - 16384) / stage;
   return fit > 8 ? 8 : fit;
 }

@@ -150,24 +150,6 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
       : "memory");
 }
 
-// 5-D tiled loads (scale-factor images: 256 B, 2 halves of the 512-byte atom, 4 zero-stride replicas, k atoms, row tiles)
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      :
-      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1, int c2, int c3,
-                                                int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      :
-      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
 // Multicast 3-D load: the box lands at the same smem offset in every CTA of `mask`, each CTA's own barrier
 // (same offset) receives the complete_tx.
 __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, uint16_t mask, int c0,
@@ -303,16 +285,6 @@ __device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t 
     asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(smem_desc) : "memory");
   else
     asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(smem_desc) : "memory");
-}
-
-// 128 lanes x 256 bits: every lane receives its own 32-byte source row (no broadcast) -- two scale-factor atoms per copy when
-// the source holds each 32-row chunk replicated four times (lanes 32 q + r equal for q = 0..3), see gemm_tcgen05.cu.
-template <int CG>
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t smem_desc) {
-  if constexpr (CG == 1)
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(smem_desc) : "memory");
-  else
-    asm volatile("tcgen05.cp.cta_group::2.128x256b [%0], %1;" ::"r"(taddr), "l"(smem_desc) : "memory");
 }
 
 // Instruction descriptor of the block-scaled kinds (f32 accumulate, K-major operands); the scale-factor byte ids (bits

@@ -165,23 +165,22 @@ def test_block_scaled_plans(plan):
     launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
     assert launches == ["pack_scales", "pack_scales", "gemm_mxf8_bf16_2sm_n256_kk"]
     assert t.count(f"alloc {64 * 64 * 512}") == 2                           # 64 row tiles x 64 k-atoms x 512 B each
-    # operands as bytes, K-major, 128B swizzle; scale atoms: (256 B, 2 halves, 4 zero-stride replicas, k atoms, tiles) -- the TMA load
-    # itself writes every 512-byte atom as the four-times replicated 2 KB image the 128x256b TMEM copies read; B: 2 tiles per box
+    # operands as bytes, K-major, 128B swizzle; scale atoms: (512-byte atom, k atoms, tiles) boxes, one k-block's atoms per box; B: 2 tiles
     assert "tmap esz=1 dims=(8192,8192,1) strides=(8192,67108864) box=(128,128) swizzle=3" in t
-    assert "tmap scales esz=4 dims=(64,2,4,64,64) strides=(256,0,512,32768) box=(64,2,4,1,1)" in t
-    assert "tmap scales esz=4 dims=(64,2,4,64,64) strides=(256,0,512,32768) box=(64,2,4,1,2)" in t
-    assert "smem=212992 cluster=2" in t                                              # 5 x (16K + 16K + 6K) + 1K + 1K + 16K staging
+    assert "tmap scales esz=4 dims=(128,64,64) strides=(512,32768) box=(128,1,1)" in t
+    assert "tmap scales esz=4 dims=(128,64,64) strides=(512,32768) box=(128,1,2)" in t
+    assert "smem=227328 cluster=2" in t                                     # 6 x (16K + 16K + 2K) + 1K + 1K + 16K staging
     rc, t = plan.matmul_scaled(FP4, FP4, F32, 2, 4096, 4096, 8192)          # packed e2m1: 4096 bytes of K per row
     assert rc == 0 and "gemm_mxf4_f32_" in t
     assert "tmap esz=1 dims=(4096,4096,2) strides=(4096,16777216) box=(128,128) swizzle=3" in t
-    assert "box=(64,2,4,2,1)" in t and "box=(64,2,4,2,2)" in t             # two atoms per k-block (256 elements of K)
-    rc, t = plan.matmul_scaled(FP4, FP4, BF16, 1, 8192, 8192, 8192, block=16)   # NVFP4: four atoms per k-block, 3 stages of 56 KB
-    assert rc == 0 and "gemm_nvf4_bf16_2sm_n256_kk" in t and "box=(64,2,4,4,2)" in t and f"smem={1024 + 3 * 57344 + 1024 + 16384} cluster=2" in t
+    assert "box=(128,2,1)" in t and "box=(128,2,2)" in t             # two atoms per k-block (256 elements of K)
+    rc, t = plan.matmul_scaled(FP4, FP4, BF16, 1, 8192, 8192, 8192, block=16)   # NVFP4: four atoms per k-block, 5 stages of 38 KB
+    assert rc == 0 and "gemm_nvf4_bf16_2sm_n256_kk" in t and "box=(128,4,2)" in t and "smem=212992 cluster=2" in t
     assert t.count(f"alloc {64 * 128 * 512}") == 2                          # 64 row tiles x 128 k-atoms (K / 16 / 4) x 512 B
     plan.option("gemm.variant", "2sm_n224")                                 # opt-in 256 x 224 tile: two accumulator stages fit TMEM;
     rc, t = plan.matmul_scaled(E4M3, E5M2, BF16, 1, 8192, 8192, 8192)       # rhs scales packed per 224-row tile (37 tiles x 2 chunks)
     assert rc == 0 and "gemm_mxf8_bf16_2sm_n224_kk grid=(148,1,1)" in t and f"alloc {74 * 64 * 512}" in t
-    assert "tmap scales esz=4 dims=(64,2,4,64,74) strides=(256,0,512,32768) box=(64,2,4,1,2)" in t and "box=(128,112) swizzle=3" in t
+    assert "tmap scales esz=4 dims=(128,64,74) strides=(512,32768) box=(128,1,2)" in t and "box=(128,112) swizzle=3" in t
     assert plan.matmul_scaled(E4M3, E4M3, F32, 1, 256, 256, 128, packed=1)[0] != 0   # pre-packed scales are in the plain layout
     plan.option("gemm.variant", "auto")
     rc, t = plan.matmul_scaled(E4M3, E4M3, F32, 1, 16, 8, 32)               # the reference's m16 n8 k32 test shape

@@ -174,7 +174,7 @@ if "scaledab" in what:
         pa = TensorHandle.from_numpy(c, np.full((tiles, atoms, 512), 127 if blk == 32 else 0x38, np.uint8), "ue8m0" if blk == 32 else "f8e4m3")
         flops = 2.0 * n * n * k
         res = []
-        for mode in ("thread", "mma", "thread_x4", "thread"):
+        for mode in ("thread", "mma", "thread"):
             c.set_option("gemm.sf_copy", mode)
             ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scale_block=blk, scales_packed=True), iters=10, warm=2) for _ in range(3))
             res.append(f"{mode}: {ms * 1e3:7.1f} us {flops / ms / 1e9:6.0f} TF/s")
