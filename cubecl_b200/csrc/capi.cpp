@@ -880,7 +880,7 @@ static bool variant_has_dtype(const GemmVariant& v, int in_dtype) {
   if (!strcmp(v.tag, "2sm_n224")) return false;   // block-scaled kinds only
   const bool bits8 = (in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2 || in_dtype == B200_U8 || in_dtype == B200_I8);
   if (!strcmp(v.tag, "2sm_m512")) return in_dtype == B200_BF16 || in_dtype == B200_F16 || in_dtype == B200_F8E4M3 || in_dtype == B200_F8E5M2;
-  if (!strcmp(v.tag, "2sm_n256a1")) return in_dtype == B200_BF16;
+  if (!strcmp(v.tag, "2sm_n256a1")) return in_dtype == B200_BF16 || in_dtype == B200_F8E4M3;
   if (bits8) return !strcmp(v.tag, "2sm_n256") || !strcmp(v.tag, "1sm_n128");
   return true;
 }

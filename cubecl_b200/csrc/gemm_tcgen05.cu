@@ -242,15 +242,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   constexpr uint32_t A_SUB_BYTES = 128 * 128;       // one 128-row sub-tile of A: 128 rows x 128 B
   constexpr uint32_t A_BYTES = MT * A_SUB_BYTES;
   constexpr uint32_t B_BYTES = N_LOCAL * 128;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + SF_BYTES;
-  constexpr uint32_t STAGE_TX = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;  // bytes one CTA's copies deliver per stage
+  // operand stages keep their power-of-two-friendly stride; the scale atoms of stage s live in their own array behind the ring
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int CHUNK_N = 128 / ESZ;                 // MN-major operand: M/N elements per 128-byte row
   constexpr uint32_t CHUNK_BYTES = BLOCK_K * 128;    // MN-major operand: one [BLOCK_K x 128 B] chunk
   constexpr int NUM_CHUNKS = N_LOCAL / CHUNK_N;      // B chunks per CTA
   constexpr int NUM_CHUNKS_A = MT * 128 / CHUNK_N;   // A chunks per CTA (128 * MT rows of M)
   constexpr uint32_t ACC_COLS = ACC * MT * BLOCK_N;
-  // ring of TMEM scale buffers behind the accumulators: as many as fit, four at most (the copy thread runs that far ahead)
-  constexpr uint32_t SF_NB = !SCALED ? 0u : ((512u - ACC_COLS) / SF_COLS >= 4u ? 4u : (512u - ACC_COLS) / SF_COLS);
+  // ring of TMEM scale buffers behind the accumulators: as many as fit, six at most (the copy thread runs that far ahead)
+  constexpr uint32_t SF_NB = !SCALED ? 0u : ((512u - ACC_COLS) / SF_COLS >= 6u ? 6u : (512u - ACC_COLS) / SF_COLS);
   static_assert(!SCALED || SF_NB >= 2, "block-scaled kinds need two TMEM scale buffers");
   constexpr uint32_t TMEM_NEED = ACC_COLS + SF_NB * SF_COLS;
   constexpr uint32_t TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 : (TMEM_NEED <= 128) ? 128 : (TMEM_NEED <= 256) ? 256 : 512;
@@ -264,7 +264,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t sf_base = smem_base + STAGES * STAGE_BYTES;   // [STAGES][SF_BYTES]: A atoms, then B atoms ([tile][atom])
+  const uint32_t bar_base = sf_base + STAGES * SF_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -273,6 +274,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   const uint32_t split_flag = tmem_slot + 4;  // "this CTA reduces the slabs" broadcast among the epilogue warps
   auto sf_full_bar = [&](uint32_t b) { return bar_base + 256u + 8u * b; };    // scale copies of buffer b have landed in TMEM
   auto sf_empty_bar = [&](uint32_t b) { return bar_base + 320u + 8u * b; };   // the MMAs that read buffer b have retired
+  // the scale atoms of stage s have landed in shared memory: their (small) loads are issued BEFORE the stage's operands and
+  // signal this barrier of their own, so the copies to TMEM finish while the 32 KB of operands are still in flight -- waiting
+  // for the whole stage put the copy latency (~600 cycles) between "stage landed" and "MMAs issued" (measured: 7 % of the run)
+  auto sf_ld_bar = [&](uint32_t st) { return bar_base + 384u + 8u * st; };
   // epilogue staging: one [32 rows x 128 B] tile per epilogue warp (4 * MT of them), 128B-swizzled like the tensor map that stores it
   const uint32_t epi_base = bar_base + 1024u;
 
@@ -302,6 +307,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       mbar_init(sf_full_bar(b), 1);       // one tcgen05.commit (scale-copy thread)
       mbar_init(sf_empty_bar(b), 1);      // one tcgen05.commit (MMA thread)
     }
+    if constexpr (SCALED)
+      for (int st = 0; st < STAGES; ++st) mbar_init(sf_ld_bar(st), 1);  // one arrive.expect_tx; scale bytes of both CTAs
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -340,6 +347,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
     if (lane == 0) {
       const uint32_t who = (warp == 0) ? 0u : 1u;
       const uint32_t leader_full0 = (CG == 2) ? mapa_shared(full_bar(0), 0) : full_bar(0);
+      [[maybe_unused]] const uint32_t leader_sfld0 = (CG == 2) ? mapa_shared(sf_ld_bar(0), 0) : sf_ld_bar(0);
       constexpr int kAItems = A_MN ? NUM_CHUNKS_A : MT, kBItems = B_MN ? NUM_CHUNKS : 1;
       uint32_t s = 0, ph = 0;
       UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
@@ -356,7 +364,26 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           const uint32_t fb = (CG == 2) ? leader_full0 + 8u * s : full_bar(s);
-          if (who == 0 && leader) mbar_arrive_expect_tx(full_bar(s), CG * STAGE_TX);
+          if constexpr (SCALED) {
+            // scale atoms of this k-block first, on their own barrier: A rows of this CTA (one 128-row tile), B rows of the whole
+            // BLOCK_N (the MMA of each CTA of a pair needs the scales of all N columns); box = (one 512-byte atom, atoms, tiles)
+            // -> smem [tile][atom][512 B]
+            {
+              const uint32_t fsf = (CG == 2) ? leader_sfld0 + 8u * s : sf_ld_bar(s);
+              const int atom0 = static_cast<int>(kk * SF_ATOMS);
+              if (who == 0) {
+                if (leader) mbar_arrive_expect_tx(sf_ld_bar(s), CG * (SFA_BYTES + SFB_BYTES));
+                const int tile = static_cast<int>(tc.b * p.a_bmul * p.sf_tiles_a + tc.m_blk * CG + rank);
+                if constexpr (CG == 1) tma_load_3d(sf_base + s * SF_BYTES, tma_a_lo, fsf, 0, atom0, tile);
+                else tma_load_3d_2sm(sf_base + s * SF_BYTES, tma_a_lo, fsf, 0, atom0, tile);
+              } else {
+                const int tile = static_cast<int>(tc.b * p.b_bmul * p.sf_tiles_b + tc.n_blk * SF_TILES_B);
+                if constexpr (CG == 1) tma_load_3d(sf_base + s * SF_BYTES + SFA_BYTES, tma_b_lo, fsf, 0, atom0, tile);
+                else tma_load_3d_2sm(sf_base + s * SF_BYTES + SFA_BYTES, tma_b_lo, fsf, 0, atom0, tile);
+              }
+            }
+          }
+          if (who == 0 && leader) mbar_arrive_expect_tx(full_bar(s), CG * (A_BYTES + B_BYTES));
           bool h16 = false;
           if constexpr (KIND == KIND_TF32) h16 = hyb && seg != 0;
           if (h16) {
@@ -396,20 +423,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                 const int c0 = B_MN ? n0 + c * CHUNK_N : k0, c1 = B_MN ? k0 : n0;
                 if constexpr (CG == 1) tma_load_3d(dst, tma_b, fb, c0, c1, bb); else tma_load_3d_2sm(dst, tma_b, fb, c0, c1, bb);
               }
-            }
-          }
-          if constexpr (SCALED) {
-            // scale atoms of this k-block: A rows of this CTA (one 128-row tile), B rows of the whole BLOCK_N (the MMA of each CTA
-            // of a pair needs the scales of all N columns); box = (one 512-byte atom, atoms, tiles) -> smem [tile][atom][512 B]
-            const int atom0 = static_cast<int>(kk * SF_ATOMS);
-            if (who == 0) {
-              const int tile = static_cast<int>(tc.b * p.a_bmul * p.sf_tiles_a + tc.m_blk * CG + rank);
-              if constexpr (CG == 1) tma_load_3d(sb + B_BYTES, tma_a_lo, fb, 0, atom0, tile);
-              else tma_load_3d_2sm(sb + B_BYTES, tma_a_lo, fb, 0, atom0, tile);
-            } else {
-              const int tile = static_cast<int>(tc.b * p.b_bmul * p.sf_tiles_b + tc.n_blk * SF_TILES_B);
-              if constexpr (CG == 1) tma_load_3d(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, atom0, tile);
-              else tma_load_3d_2sm(sb + B_BYTES + SFA_BYTES, tma_b_lo, fb, 0, atom0, tile);
             }
           }
           if (++kk == (seg == 0 ? seg_kb : seg_kb1)) { kk = 0; ++seg; }
@@ -473,7 +486,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             if (p.pad_ & 1u) {
               // gemm.sf_copy=mma (A/B switch): the MMA thread copies the atoms itself, one broadcast copy per atom, in front of
               // the MMAs that read them (the round-2 scheme)
-              const uint32_t sfa_s = sb + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
+              const uint32_t sfa_s = sf_base + s * SF_BYTES, sfb_s = sfa_s + SFA_BYTES;
+              mbar_wait(sf_ld_bar(s), ph);
 #pragma unroll
               for (int atom = 0; atom < SF_ATOMS; ++atom)
                 tmem_cp_32x128b_warpx4<CG>(sf_t + SFA_COL + 4u * atom, make_smem_desc(sfa_s + SF_IMG * atom, 0, 128, 0));
@@ -543,10 +557,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         WorkUnit wu;
         while (next_unit(it, p, wu)) {
           for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
-            mbar_wait(full_bar(s), ph);            // the stage's scale images (and operands) have landed, both CTAs
+            mbar_wait(sf_ld_bar(s), ph);           // the stage's scale atoms have landed, both CTAs
             mbar_wait(sf_empty_bar(bi), bph ^ 1);  // the MMAs that read this TMEM scale buffer have retired
             tcgen05_fence_after();
-            const uint32_t sfa_s = smem_base + s * STAGE_BYTES + A_BYTES + B_BYTES, sfb_s = sfa_s + SFA_BYTES;
+            const uint32_t sfa_s = sf_base + s * SF_BYTES, sfb_s = sfa_s + SFA_BYTES;
             const uint32_t sfa_t = tmem_base + bi * SF_COLS + SFA_COL, sfb_t = tmem_base + bi * SF_COLS + SFB_COL;
             // one broadcast copy per atom (32 rows x 16 B, 8-row groups 128 B apart): A atoms to TMEM columns 4 a, B atoms to
             // 4 (a T + t); smem atoms are [tile][atom]
@@ -910,6 +924,7 @@ GEMM_M512(gemm_e5m2_f16, KIND_E5M2, OUT_F16)
 // diagnostic: the 256x256 tile with ONE accumulator stage (what an un-hidden epilogue costs per tile); gemm.variant=2sm_n256a1
 GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kn, 2, 256, false, true, KIND_BF16, OUT_BF16, 6, 1)
 GEMM_KERNEL_ACC(gemm_bf16_bf16_2sm_n256a1_kk, 2, 256, false, false, KIND_BF16, OUT_BF16, 6, 1)
+GEMM_KERNEL_ACC(gemm_e4m3_bf16_2sm_n256a1_kk, 2, 256, false, false, KIND_E4M3, OUT_BF16, 6, 1)   // the same for fp8 (tile time halves)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 peak probe: the accounting of compute_cmma_throughput (crates/cubecl-std/src/throughput/runners/

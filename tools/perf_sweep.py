@@ -161,26 +161,45 @@ if "scaled" in what:
 
 if "scaledab" in what:
     # block-scaled GEMM, 256 x 256 tile, pre-packed scales: scale atoms copied by the dedicated thread (default) vs by the MMA thread
-    print("block-scaled matmul 8192^3 -> bf16, pre-packed scales, CUDA events; gemm.sf_copy = thread | mma:")
+    # (round-2 scheme), next to the unscaled fp8 kernel with two / one accumulator stages.  The part is power-capped and a sample
+    # inherits the power state of what ran before it: 2 s pause before every 10-launch sample, configurations walked round-robin.
+    import time as _time
+    print("block-scaled matmul 8192^3 -> bf16, pre-packed scales; 2 s pause before every 10-launch sample, round-robin x3: min / median us, TFLOP/s of the min")
     n = k = 8192
-    for (dt, blk) in (("f8e4m3", 32), ("f4e2m1x2", 32), ("f4e2m1x2", 16)):
+    ops = {}
+    for (tag, dt, blk) in (("mxfp8", "f8e4m3", 32), ("mxfp4", "f4e2m1x2", 32), ("nvfp4", "f4e2m1x2", 16)):
         kb = k // 2 if dt == "f4e2m1x2" else k
         a = TensorHandle.empty_contiguous(c, [n, kb], dt)
         b = TensorHandle.empty_contiguous(c, [n, kb], dt)
-        o = TensorHandle.empty_contiguous(c, [n, n], "bf16")
         c.fill_uniform(a.handle, "f8e4m3", n * kb, 3, -1.0, 1.0)
         c.fill_uniform(b.handle, "f8e4m3", n * kb, 4, -1.0, 1.0)
-        tiles, atoms = n // 128, k // (4 * blk)
-        pa = TensorHandle.from_numpy(c, np.full((tiles, atoms, 512), 127 if blk == 32 else 0x38, np.uint8), "ue8m0" if blk == 32 else "f8e4m3")
-        flops = 2.0 * n * n * k
-        res = []
-        for mode in ("thread", "mma", "thread"):
-            c.set_option("gemm.sf_copy", mode)
-            ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scale_block=blk, scales_packed=True), iters=10, warm=2) for _ in range(3))
-            res.append(f"{mode}: {ms * 1e3:7.1f} us {flops / ms / 1e9:6.0f} TF/s")
-        print(f"  {dt:9s} scale/{blk}: " + " | ".join(res) + f"  [{c.last_kernel()}]", flush=True)
-        del a, b, o
-    c.set_option("gemm.sf_copy", "thread")
+        pa = TensorHandle.from_numpy(c, np.full((n // 128, k // (4 * blk), 512), 127 if blk == 32 else 0x38, np.uint8), "ue8m0" if blk == 32 else "f8e4m3")
+        ops[tag] = (a, b, pa, blk)
+    o = TensorHandle.empty_contiguous(c, [n, n], "bf16")
+    a8, b8 = ops["mxfp8"][0], ops["mxfp8"][1]
+    bt = TensorHandle(b8.handle, [k, n], [1, k], "f8e4m3")
+    configs = [(f"{tag} copies by {who}", ("scaled", tag, who)) for tag in ops for who in ("thread", "mma")]
+    configs += [("plain fp8 2sm_n256 (two accumulators)", ("plain", "2sm_n256", "")), ("plain fp8 2sm_n256a1 (one accumulator)", ("plain", "2sm_n256a1", ""))]
+    samples = {name: [] for name, _ in configs}
+    for rnd in range(3):
+        for name, (kind, x, who) in configs:
+            if kind == "scaled":
+                a, b, pa, blk = ops[x]
+                c.set_option("gemm.variant", "auto")
+                c.set_option("gemm.sf_copy", who)
+                fn = lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scale_block=blk, scales_packed=True)
+            else:
+                c.set_option("gemm.variant", x)
+                fn = lambda: matmul.launch(c, a8, bt, o)
+            fn(); c.sync()
+            _time.sleep(2.0)
+            samples[name].append(time_ms(c, fn, iters=10, warm=1))
+    c.set_option("gemm.variant", "auto"); c.set_option("gemm.sf_copy", "thread")
+    flops = 2.0 * n * n * k
+    for name, _ in configs:
+        v = sorted(samples[name])
+        print(f"  {name:40s}: {v[0] * 1e3:7.1f} / {v[1] * 1e3:7.1f} us   {flops / v[0] / 1e9:6.0f} TFLOP/s", flush=True)
+    del ops, o
 
 if "split" in what:
     # tail split (deterministic split-K of the last partial wave): off vs forced S vs the auto policy
