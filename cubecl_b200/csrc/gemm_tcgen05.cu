@@ -249,8 +249,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   constexpr int NUM_CHUNKS = N_LOCAL / CHUNK_N;      // B chunks per CTA
   constexpr int NUM_CHUNKS_A = MT * 128 / CHUNK_N;   // A chunks per CTA (128 * MT rows of M)
   constexpr uint32_t ACC_COLS = ACC * MT * BLOCK_N;
-  // ring of TMEM scale buffers behind the accumulators: as many as fit, six at most (the copy thread runs that far ahead)
-  constexpr uint32_t SF_NB = !SCALED ? 0u : ((512u - ACC_COLS) / SF_COLS >= 6u ? 6u : (512u - ACC_COLS) / SF_COLS);
+  // TMEM scale buffers behind the accumulators.  One per pipeline stage when they fit (buffer index = stage index): the stage's
+  // scale loads are only issued once the MMAs of the stage's previous round have retired (empty barrier), so "atoms landed"
+  // already implies "the buffer is free" and the copy thread needs no second handshake.  Otherwise (256 x 224 tiles: 448
+  // accumulator columns) a shorter ring with its own empty barriers.
+  constexpr uint32_t SF_FIT = !SCALED ? 0u : (512u - ACC_COLS) / SF_COLS;
+  constexpr uint32_t SF_NB = !SCALED ? 0u : (SF_FIT >= static_cast<uint32_t>(STAGES) ? static_cast<uint32_t>(STAGES) : SF_FIT);
+  constexpr bool SF_PER_STAGE = SCALED && SF_NB == static_cast<uint32_t>(STAGES);
   static_assert(!SCALED || SF_NB >= 2, "block-scaled kinds need two TMEM scale buffers");
   constexpr uint32_t TMEM_NEED = ACC_COLS + SF_NB * SF_COLS;
   constexpr uint32_t TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 : (TMEM_NEED <= 128) ? 128 : (TMEM_NEED <= 256) ? 256 : 512;
@@ -482,7 +487,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           const uint64_t a_desc = A_MN ? mn_desc(sa) : make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t b_desc = B_MN ? mn_desc(sb) : make_smem_desc_sw128(sb, 16, 1024);
           if constexpr (SCALED) {
-            const uint32_t sf_t = tmem_base + sfb_i * SF_COLS;
+            const uint32_t sf_buf = SF_PER_STAGE ? s : sfb_i;
+            const uint32_t sf_t = tmem_base + sf_buf * SF_COLS;
             if (p.pad_ & 1u) {
               // gemm.sf_copy=mma (A/B switch): the MMA thread copies the atoms itself, one broadcast copy per atom, in front of
               // the MMAs that read them (the round-2 scheme)
@@ -499,7 +505,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                                              make_smem_desc(sfb_s + SF_IMG * (tile * SF_ATOMS + atom), 0, 128, 0));
             } else {
               // the scale-copy thread (warp 2) has put this k-block's atoms into TMEM scale buffer sfb_i
-              mbar_wait(sf_full_bar(sfb_i), sfb_ph);
+              mbar_wait(sf_full_bar(sf_buf), SF_PER_STAGE ? ph : sfb_ph);
               tcgen05_fence_after();
             }
             const uint32_t idesc_base = make_idesc_scaled(p.sf_fmt_a, p.sf_fmt_b, UMMA_M, BLOCK_N, KIND == KIND_NVF4 ? 0u : 1u);
@@ -511,8 +517,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                                                               idesc_base | (sf_id << 29) | (sf_id << 4), sf_t + SFA_COL + 4u * atom,
                                                               sf_t + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
-            if (!(p.pad_ & 1u)) umma_commit<CG>(sf_empty_bar(sfb_i));  // buffer reusable once these MMAs retire
-            if (++sfb_i == SF_NB) { sfb_i = 0; sfb_ph ^= 1; }
+            if constexpr (!SF_PER_STAGE) {
+              if (!(p.pad_ & 1u)) umma_commit<CG>(sf_empty_bar(sfb_i));  // buffer reusable once these MMAs retire
+              if (++sfb_i == SF_NB) { sfb_i = 0; sfb_ph ^= 1; }
+            }
           } else if constexpr (MT == 1) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -558,10 +566,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
         while (next_unit(it, p, wu)) {
           for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
             mbar_wait(sf_ld_bar(s), ph);           // the stage's scale atoms have landed, both CTAs
-            mbar_wait(sf_empty_bar(bi), bph ^ 1);  // the MMAs that read this TMEM scale buffer have retired
+            if constexpr (!SF_PER_STAGE) mbar_wait(sf_empty_bar(bi), bph ^ 1);  // the MMAs that read this TMEM scale buffer have retired
             tcgen05_fence_after();
+            const uint32_t buf = SF_PER_STAGE ? s : bi;
             const uint32_t sfa_s = sf_base + s * SF_BYTES, sfb_s = sfa_s + SFA_BYTES;
-            const uint32_t sfa_t = tmem_base + bi * SF_COLS + SFA_COL, sfb_t = tmem_base + bi * SF_COLS + SFB_COL;
+            const uint32_t sfa_t = tmem_base + buf * SF_COLS + SFA_COL, sfb_t = tmem_base + buf * SF_COLS + SFB_COL;
             // one broadcast copy per atom (32 rows x 16 B, 8-row groups 128 B apart): A atoms to TMEM columns 4 a, B atoms to
             // 4 (a T + t); smem atoms are [tile][atom]
 #pragma unroll
@@ -571,7 +580,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 #pragma unroll
               for (int a = 0; a < SF_ATOMS; ++a)
                 tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * (a * SF_TILES_B + t), make_smem_desc(sfb_s + SF_IMG * (t * SF_ATOMS + a), 0, 128, 0));
-            umma_commit<CG>(sf_full_bar(bi));      // arrives when the copies have completed
+            umma_commit<CG>(sf_full_bar(buf));     // arrives when the copies have completed
             if (++s == STAGES) { s = 0; ph ^= 1; }
             if (++bi == SF_NB) { bi = 0; bph ^= 1; }
           }
