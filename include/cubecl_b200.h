@@ -95,7 +95,9 @@ int b200_get_props(b200_ctx* ctx, b200_props* out);
 int b200_plan_begin(int num_sms, b200_ctx** out);
 int b200_plan_text(b200_ctx* ctx, char* buf, size_t capacity, size_t* needed);
 /* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
- * (auto|2sm_m512|2sm_n256|2sm_n128|1sm_n128|simt; 2sm_n256a1 = single-accumulator diagnostic), "gemm.f32" (3xtf32|tf32), "gemm.group_m",
+ * (auto|2sm_m512|2sm_n256|2sm_n128|1sm_n128|simt; 2sm_n256a1 = single-accumulator diagnostic), "gemm.f32" (hybrid|3xtf32|tf32: f32 inputs as one
+ * tf32 pass + two bf16 cross-term passes in ONE launch (default, ~2^-20 of the product), three tf32 passes, or one), "gemm.sf_copy" (thread|mma:
+ * block-scaled kinds, who issues the scale-factor copies to TMEM -- the dedicated copy thread, or the MMA thread for an A/B), "gemm.group_m",
  * "gemm.l2_promotion" (256|128|64|0: TMA L2 promotion bytes of the operand tensor maps), "gemm.split_k" (auto|off|on|1..8:
  * deterministic stream-K head -- the tiles of a partial last wave are cut along K into equal ranges that run FIRST, slabs
  * added in k order; N = ranges per tile), "gemm.epilogue" (tma|direct), "gemm.stage" (on|off: operands TMA cannot describe --
@@ -150,7 +152,7 @@ int b200_event_destroy(b200_ctx* ctx, b200_event e);
  * `out_dtype` = the input dtype or F32; fp8 inputs (F8E4M3 / F8E5M2, both operands the same format, kind::f8f6f4) with
  * `out_dtype` BF16, F16 or F32; U8 / I8 inputs (kind::i8) with exact I32 accumulation and `out_dtype` I32.  Row strides may be pitched (allocator.rs:21-72); rhs may be given transposed
  * (stride_k == 1, MatrixBatchLayout::MildlyPermuted{transposed}, matrix_batch_layout.rs:8-19).  f32 inputs run on the tf32
- * tensor pipe, by default with a 3-way split that restores ~f32 accuracy (see "gemm.f32").
+ * tensor pipe, by default with the hybrid split (tf32 main product + bf16 cross terms, f32-grade accuracy; see "gemm.f32").
  * Returns B200_ERR_INVALID_ARG on shape mismatch -- the MatmulShapeError of shape.rs:489-517. */
 int b200_matmul(b200_ctx* ctx, b200_stream s, b200_dtype in_dtype, b200_dtype out_dtype,
                 b200_dptr lhs, b200_dptr rhs, b200_dptr out, int rank,
