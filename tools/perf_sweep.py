@@ -152,6 +152,7 @@ if "scaled" in what:
                 continue
             msp = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, pa, pa, o, scales_packed=True), iters=10, warm=2) for _ in range(3))
             print(f"  {dt:9s} {n}x{n}x{k} {variant}: {ms * 1e3:8.1f} us {flops / ms / 1e9:7.0f} TF/s | pre-packed scales {msp * 1e3:8.1f} us {flops / msp / 1e9:7.0f} TF/s  [{picked}]", flush=True)
+        c.set_option("gemm.variant", "auto")   # (rounds 1-2 left the loop's last variant, 1sm_n128, set for the nvfp4 row below)
         if dt == "f4e2m1x2":
             s16 = TensorHandle.from_numpy(c, np.full((n, k // 16), 0x38, np.uint8), "f8e4m3")
             ms = min(time_ms(c, lambda: matmul.launch_scaled(c, a, b, s16, s16, o, scale_block=16), iters=10, warm=2) for _ in range(3))
