@@ -759,11 +759,17 @@ def main():
             a4 = TensorHandle(a8.handle, [N_MM, N_MM // 2], [N_MM // 2, 1], "f4e2m1x2")   # the same bytes read as packed e2m1
             b4 = TensorHandle(b8.handle, [N_MM, N_MM // 2], [N_MM // 2, 1], "f4e2m1x2")
             ms_m4, _ = timed(lambda: matmul.launch_scaled(c, a4, b4, sc, sc, o), extra_steps, 3)
+            # NVFP4: the same packed e2m1 operands with an e4m3 scale byte per 16 elements of K (kind::mxf4nvf4)
+            sc16 = TensorHandle.from_numpy(c, _np.full((N_MM, N_MM // 16), 0x38, _np.uint8), "f8e4m3")
+            ms_nv, _ = timed(lambda: matmul.launch_scaled(c, a4, b4, sc16, sc16, o, scale_block=16), extra_steps, 3)
             line["matmul_block_scaled_8192"] = {
                 "unit": "TFLOP/s", "mxfp8_e4m3": world * FLOPS_MM * extra_steps / (ms_m8 * 1e-3) / 1e12,
                 "mxfp4_e2m1": world * FLOPS_MM * extra_steps / (ms_m4 * 1e-3) / 1e12,
-                "config": "8192^3 per GPU -> bf16, ue8m0 scale per 32 elements of K for both operands, scale packing included"}
-            del a8, b8, a4, b4, sc
+                "nvfp4_e2m1": world * FLOPS_MM * extra_steps / (ms_nv * 1e-3) / 1e12,
+                "kernel": c.last_kernel(),
+                "config": "8192^3 per GPU -> bf16, row-major scales for both operands (ue8m0 per 32 elements of K; nvfp4: e4m3 per 16), the two "
+                          "scale-packing passes run inside the timed call; scale atoms reach TMEM through the dedicated copy thread"}
+            del a8, b8, a4, b4, sc, sc16
             # what CubeCL's own kernels reach on this GPU (hand-written from its emit rules)
             if world == 1:
                 scratch = c.empty(1024)
