@@ -222,7 +222,8 @@ struct GemmParams {
   uint64_t split_ws, split_tickets;
   uint32_t sf_fmt_a, sf_fmt_b, sf_tiles_a, sf_tiles_b;  // block-scaled kinds; operand formats of a mixed 8-bit pair
   uint32_t tma_store, fmt_mixed;
-  uint32_t hyb, hyb_nba, hyb_nbb, pad_;  // hybrid f32 schedule: tf32 main product + two bf16 cross terms (gemm_tcgen05.cu)
+  uint32_t hyb, hyb_nba, hyb_nbb;  // hybrid f32 schedule: tf32 main product + two bf16 cross terms (gemm_tcgen05.cu)
+  uint32_t sf_flags;               // block-scaled kinds: bit 0 = scale copies by the MMA thread (gemm.sf_copy=mma)
 };
 struct PackScalesParams {
   uint64_t in, out;
@@ -1236,7 +1237,7 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (rc) return rc;
     rc = encode_sf_tmap(c, &tb_lo, g.sfb, g.sf_atoms, tiles_b * bb, mx_atoms(g.mx_kind), (v.block_n + 127) / 128);
     if (rc) return rc;
-    p.pad_ = opt(c, "gemm.sf_copy", "thread") == "mma" ? 1u : 0u;   // A/B switch: scale copies issued by the MMA thread (round-2 scheme)
+    p.sf_flags = opt(c, "gemm.sf_copy", "thread") == "mma" ? 1u : 0u;   // A/B switch: scale copies issued by the MMA thread (round-2 scheme)
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }

@@ -54,7 +54,8 @@ struct GemmParams {
   // instructions into the same f32 accumulators, 64 elements of K per stage instead of 32.  tma_a_lo / tma_b_lo then describe
   // bf16 PAIR buffers [2 * entries][rows][pitch]: entries [0, hyb_nba) hold bf16(x), entries [hyb_nba, 2 hyb_nba) hold
   // bf16(x - trunc_tf32(x)).  Two tensor passes' worth of time instead of 3xTF32's three.
-  uint32_t hyb, hyb_nba, hyb_nbb, pad_;
+  uint32_t hyb, hyb_nba, hyb_nbb;
+  uint32_t sf_flags;   // block-scaled kinds, bit 0: the MMA thread issues the scale copies itself (gemm.sf_copy=mma, the A/B reference)
 };
 
 enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M2 = 4, KIND_U8 = 5, KIND_S8 = 6,
@@ -489,7 +490,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
           if constexpr (SCALED) {
             const uint32_t sf_buf = SF_PER_STAGE ? s : sfb_i;
             const uint32_t sf_t = tmem_base + sf_buf * SF_COLS;
-            if (p.pad_ & 1u) {
+            if (p.sf_flags & 1u) {
               // gemm.sf_copy=mma (A/B switch): the MMA thread copies the atoms itself, one broadcast copy per atom, in front of
               // the MMAs that read them (the round-2 scheme)
               const uint32_t sfa_s = sf_base + s * SF_BYTES, sfb_s = sfa_s + SFA_BYTES;
@@ -518,7 +519,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
                                                               sf_t + SFB_COL + 4u * atom * SF_TILES_B, (kb != wu.kb0 || k != 0) ? 1u : 0u);
             }
             if constexpr (!SF_PER_STAGE) {
-              if (!(p.pad_ & 1u)) umma_commit<CG>(sf_empty_bar(sfb_i));  // buffer reusable once these MMAs retire
+              if (!(p.sf_flags & 1u)) umma_commit<CG>(sf_empty_bar(sfb_i));  // buffer reusable once these MMAs retire
               if (++sfb_i == SF_NB) { sfb_i = 0; sfb_ph ^= 1; }
             }
           } else if constexpr (MT == 1) {
@@ -559,7 +560,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
   } else if (warp == 2) {
     // ===================================================================== scale-copy thread (block-scaled kinds, leader CTA)
     if constexpr (SCALED) {
-      if (leader && lane == 0 && !(p.pad_ & 1u)) {
+      if (leader && lane == 0 && !(p.sf_flags & 1u)) {
         uint32_t s = 0, ph = 0, bi = 0, bph = 0;
         UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
         WorkUnit wu;
