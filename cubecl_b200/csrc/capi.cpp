@@ -1237,7 +1237,11 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     if (rc) return rc;
     rc = encode_sf_tmap(c, &tb_lo, g.sfb, g.sf_atoms, tiles_b * bb, mx_atoms(g.mx_kind), (v.block_n + 127) / 128);
     if (rc) return rc;
-    p.sf_flags = opt(c, "gemm.sf_copy", "thread") == "mma" ? 1u : 0u;   // A/B switch: scale copies issued by the MMA thread (round-2 scheme)
+    {  // who issues the scale copies: one copy thread (default), two copy threads in different warps, or the MMA thread (A/B reference)
+      const std::string sfc = opt(c, "gemm.sf_copy", "thread");
+      if (sfc != "thread" && sfc != "thread2" && sfc != "mma") return fail(B200_ERR_INVALID_ARG, "gemm.sf_copy must be thread, thread2 or mma");
+      p.sf_flags = sfc == "mma" ? 1u : sfc == "thread2" ? 2u : 0u;
+    }
     p.sf_fmt_a = g.fmt_a; p.sf_fmt_b = g.fmt_b;
     p.sf_tiles_a = (uint32_t)tiles_a; p.sf_tiles_b = (uint32_t)tiles_b;
   }
@@ -1308,7 +1312,8 @@ static int launch_tcgen05(b200_ctx* c, CUstream st, const GemmProblem& g, bool a
     }
   }
   void* args[] = {&ta, &tb, &ta_lo, &tb_lo, &tout, &p};
-  rc = launch(c, f, clusters * v.cg, 1, 1, 256 + 128 * (v.mt - 1), smem, v.cg, st, args);
+  // block-scaled kernels carry one more warp (the optional second scale-copy thread)
+  rc = launch(c, f, clusters * v.cg, 1, 1, 256 + 128 * (v.mt - 1) + (g.mx_kind ? 32 : 0), smem, v.cg, st, args);
   if (slabs) pool_free(c, slabs, st);  // stream-ordered: reusable by later work once this launch has drained
   return rc;
 }

@@ -64,7 +64,8 @@ enum : int { KIND_F16 = 0, KIND_BF16 = 1, KIND_TF32 = 2, KIND_E4M3 = 3, KIND_E5M
              KIND_NVF4 = 9 };  // kind::mxf4nvf4.block_scale.scale_vec::4X: packed e2m1, ue4m3 scale per 16 K (NVFP4)
 enum : int { OUT_F16 = 0, OUT_BF16 = 1, OUT_F32 = 2 };  // OUT_F32 is a raw 32-bit store: it also carries the s32 accumulators of kind::i8
 
-constexpr int kNumThreads = 256;  // warps 0 and 3 TMA producers, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int kNumThreads = 256;  // warps 0 and 3 TMA producers, warp 1 MMA, warp 2 TMEM alloc (+ scale copies), warps 4-7 epilogue
+constexpr int kSecondCopyWarp = 8;  // block-scaled kernels are launched with one more warp (288 threads): the optional second copy thread
 
 template <int OUT>
 __device__ __forceinline__ void store_chunk32(uint64_t row_ptr, uint32_t n0, uint32_t N, bool vec, const uint32_t (&v)[32]) {
@@ -310,7 +311,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       mbar_init(tempty_bar(a), 4 * CG);   // one elected lane per epilogue warp, both CTAs
     }
     for (uint32_t b = 0; b < SF_NB; ++b) {
-      mbar_init(sf_full_bar(b), 1);       // one tcgen05.commit (scale-copy thread)
+      mbar_init(sf_full_bar(b), (p.sf_flags & 2u) ? 2 : 1);   // one tcgen05.commit per scale-copy thread
       mbar_init(sf_empty_bar(b), 1);      // one tcgen05.commit (MMA thread)
     }
     if constexpr (SCALED)
@@ -557,10 +558,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
       }
     }
     __syncwarp();
-  } else if (warp == 2) {
-    // ===================================================================== scale-copy thread (block-scaled kinds, leader CTA)
+  } else if (warp == 2 || (SCALED && warp == kSecondCopyWarp)) {
+    // ===================================================================== scale-copy thread(s) (block-scaled kinds, leader CTA)
+    // gemm.sf_copy=thread2: the atoms of a k-block are dealt alternately to TWO copy threads in different warps (warp 2 and the
+    // extra warp 8 the block-scaled kernels are launched with), each committing to sf_full (count 2)
     if constexpr (SCALED) {
-      if (leader && lane == 0 && !(p.sf_flags & 1u)) {
+      const uint32_t me = (warp == 2) ? 0u : 1u;
+      const bool two = (p.sf_flags & 2u) != 0;
+      if (leader && lane == 0 && !(p.sf_flags & 1u) && (me == 0 || two)) {
         uint32_t s = 0, ph = 0, bi = 0, bph = 0;
         UnitIter it = unit_iter(cluster_id, n_clusters, num_kb);
         WorkUnit wu;
@@ -574,14 +579,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
             const uint32_t sfa_t = tmem_base + buf * SF_COLS + SFA_COL, sfb_t = tmem_base + buf * SF_COLS + SFB_COL;
             // one broadcast copy per atom (32 rows x 16 B, 8-row groups 128 B apart): A atoms to TMEM columns 4 a, B atoms to
             // 4 (a T + t); smem atoms are [tile][atom]
+            uint32_t idx = 0;   // running copy index of the k-block (compile-time after unrolling)
 #pragma unroll
-            for (int a = 0; a < SF_ATOMS; ++a) tmem_cp_32x128b_warpx4<CG>(sfa_t + 4u * a, make_smem_desc(sfa_s + SF_IMG * a, 0, 128, 0));
+            for (int a = 0; a < SF_ATOMS; ++a, ++idx)
+              if (!two || (idx & 1u) == me) tmem_cp_32x128b_warpx4<CG>(sfa_t + 4u * a, make_smem_desc(sfa_s + SF_IMG * a, 0, 128, 0));
 #pragma unroll
             for (int t = 0; t < SF_TILES_B; ++t)
 #pragma unroll
-              for (int a = 0; a < SF_ATOMS; ++a)
-                tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * (a * SF_TILES_B + t), make_smem_desc(sfb_s + SF_IMG * (t * SF_ATOMS + a), 0, 128, 0));
-            umma_commit<CG>(sf_full_bar(buf));     // arrives when the copies have completed
+              for (int a = 0; a < SF_ATOMS; ++a, ++idx)
+                if (!two || (idx & 1u) == me)
+                  tmem_cp_32x128b_warpx4<CG>(sfb_t + 4u * (a * SF_TILES_B + t), make_smem_desc(sfb_s + SF_IMG * (t * SF_ATOMS + a), 0, 128, 0));
+            umma_commit<CG>(sf_full_bar(buf));     // arrives when this thread's copies have completed
             if (++s == STAGES) { s = 0; ph ^= 1; }
             if (++bi == SF_NB) { bi = 0; bph ^= 1; }
           }
@@ -855,7 +863,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tma_a_hi, const CUt
 
 // threads: 256 = warps 0-7; MT = 2 adds the second epilogue warpgroup (warps 8-11): 384
 #define GEMM_KERNEL_MT(NAME, CG, BN, AMN, BMN, KIND, OUT, STAGES, ACC, MT)                                       \
-  extern "C" __global__ void __launch_bounds__(kNumThreads + 128 * (MT - 1), 1)                                  \
+  extern "C" __global__ void __launch_bounds__(kNumThreads + 128 * (MT - 1) + 32 * ((KIND) >= KIND_MXF8), 1)     \
       NAME(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,                 \
            const __grid_constant__ CUtensorMap tma_a_lo, const __grid_constant__ CUtensorMap tma_b_lo,           \
            const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ GemmParams p) {                  \

@@ -169,7 +169,12 @@ def test_block_scaled_plans(plan):
     assert "tmap esz=1 dims=(8192,8192,1) strides=(8192,67108864) box=(128,128) swizzle=3" in t
     assert "tmap scales esz=4 dims=(128,64,64) strides=(512,32768) box=(128,1,1)" in t
     assert "tmap scales esz=4 dims=(128,64,64) strides=(512,32768) box=(128,1,2)" in t
-    assert "smem=227328 cluster=2" in t                                     # 6 x (16K + 16K + 2K) + 1K + 1K + 16K staging
+    assert "block=288 smem=227328 cluster=2" in t                           # 6 x (16K + 16K + 2K) + 1K + 1K + 16K staging; 9th warp = second copy thread
+    plan.option("gemm.sf_copy", "thread2")
+    assert plan.matmul_scaled(E4M3, E5M2, BF16, 1, 8192, 8192, 8192)[0] == 0
+    plan.option("gemm.sf_copy", "bogus")
+    assert plan.matmul_scaled(E4M3, E5M2, BF16, 1, 8192, 8192, 8192)[0] != 0
+    plan.option("gemm.sf_copy", "thread")
     rc, t = plan.matmul_scaled(FP4, FP4, F32, 2, 4096, 4096, 8192)          # packed e2m1: 4096 bytes of K per row
     assert rc == 0 and "gemm_mxf4_f32_" in t
     assert "tmap esz=1 dims=(4096,4096,2) strides=(4096,16777216) box=(128,128) swizzle=3" in t

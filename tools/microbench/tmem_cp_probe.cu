@@ -114,7 +114,7 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sa = smem_base, sb = smem_base + 16384, sf = smem_base + 32768;
-  const uint32_t done_bar = sf + 16384, done2_bar = done_bar + 8, tmem_slot = done_bar + 16;
+  const uint32_t done_bar = sf + 16384, done2_bar = done_bar + 8, done3_bar = done_bar + 16, tmem_slot = done_bar + 24;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool leader = cluster_ctarank() == 0;
   for (uint32_t i = threadIdx.x; i < 32768 / 4; i += blockDim.x)
@@ -125,6 +125,7 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   if (warp == 1 && lane == 0) {
     mbar_init(done_bar, 1);
     mbar_init(done2_bar, 1);
+    mbar_init(done3_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -168,17 +169,21 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     }
     umma_commit<2>(done_bar);
     mbar_wait(done_bar, 1);
-    if (mode == 2) mbar_wait(done2_bar, 0);
+    if (mode >= 2) mbar_wait(done2_bar, 0);
+    if (mode == 3) mbar_wait(done3_bar, 0);
     tcgen05_fence_after();
     const long long t1 = clock64();
     out[0] = static_cast<unsigned long long>(t1 - t0);
-  } else if (warp == 3 && leader && lane == 0) {
-    if (mode == 2) {
+  } else if ((warp == 3 || warp == 5) && leader && lane == 0) {
+    // mode 2: every copy from warp 3; mode 3: even copies from warp 3, odd copies from warp 5 (two issuing warps)
+    const int me = (warp == 3) ? 0 : 1;
+    if ((mode == 2 && me == 0) || mode == 3) {
       for (int g = 0; g < groups; ++g) {
         const uint32_t nxt = tmem_base + 256 + ((g + 1) & 1) * 128u;
-        for (int i = 0; i < n_cp; ++i) one_cp(i, nxt);
+        for (int i = 0; i < n_cp; ++i)
+          if (mode == 2 || (i & 1) == me) one_cp(i, nxt);
       }
-      umma_commit<2>(done2_bar);
+      umma_commit<2>(me == 0 ? done2_bar : done3_bar);
     }
   }
   __syncwarp();
@@ -241,9 +246,9 @@ int main() {
   printf("\nmixes per group of four MMAs (cycles per group; 512 = copies fully hidden):\n");
   const int mixes[][3] = {{3, 0, 0}, {1, 1, 0}, {0, 2, 0}, {0, 1, 1}, {6, 0, 0}, {2, 2, 0}, {0, 3, 0}, {12, 0, 0}, {0, 6, 0}, {0, 0, 3}, {0, 0, 2}, {2, 0, 0}};
   for (const auto& m : mixes) {
-    printf("  %2d x warpx4 + %d x 128x256b + %d x 128x128b: burst-then-MMAs %7.1f | spread between MMAs %7.1f | from another warp %7.1f\n", m[0], m[1], m[2],
+    printf("  %2d x warpx4 + %d x 128x256b + %d x 128x128b: burst-then-MMAs %7.1f | spread between MMAs %7.1f | from another warp %7.1f | from two other warps %7.1f\n", m[0], m[1], m[2],
            double(run_mix(d_out, m[0], m[1], m[2], 0, groups)) / groups, double(run_mix(d_out, m[0], m[1], m[2], 1, groups)) / groups,
-           double(run_mix(d_out, m[0], m[1], m[2], 2, groups)) / groups);
+           double(run_mix(d_out, m[0], m[1], m[2], 2, groups)) / groups, double(run_mix(d_out, m[0], m[1], m[2], 3, groups)) / groups);
   }
   return 0;
 }
