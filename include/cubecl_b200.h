@@ -96,8 +96,8 @@ int b200_plan_begin(int num_sms, b200_ctx** out);
 int b200_plan_text(b200_ctx* ctx, char* buf, size_t capacity, size_t* needed);
 /* Runtime knobs, string-typed like cubecl.toml keys (config/base.rs:18-120).  Keys: "gemm.variant"
  * (auto|2sm_m512|2sm_n256|2sm_n128|1sm_n128|simt; 2sm_n256a1 = single-accumulator diagnostic), "gemm.f32" (hybrid|3xtf32|tf32: f32 inputs as one
- * tf32 pass + two bf16 cross-term passes in ONE launch (default, ~2^-20 of the product), three tf32 passes, or one), "gemm.sf_copy" (thread|mma:
- * block-scaled kinds, who issues the scale-factor copies to TMEM -- the dedicated copy thread, or the MMA thread for an A/B), "gemm.group_m",
+ * tf32 pass + two bf16 cross-term passes in ONE launch (default, ~2^-20 of the product), three tf32 passes, or one), "gemm.sf_copy" (thread|thread2|mma:
+ * block-scaled kinds, who issues the scale-factor copies to TMEM -- the dedicated copy thread, two of them, or the MMA thread for an A/B), "gemm.group_m",
  * "gemm.l2_promotion" (256|128|64|0: TMA L2 promotion bytes of the operand tensor maps), "gemm.split_k" (auto|off|on|1..8:
  * deterministic stream-K head -- the tiles of a partial last wave are cut along K into equal ranges that run FIRST, slabs
  * added in k order; N = ranges per tile), "gemm.epilogue" (tma|direct), "gemm.stage" (on|off: operands TMA cannot describe --
