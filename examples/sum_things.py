@@ -32,7 +32,7 @@ def launch(device: int = 0) -> None:
         matmul.launch(client, lhs, rhs, out)
         output = out.to_numpy(client).ravel()
         print(f"[{name!r} - {kind}]\n {output.tolist()}")
-    client.set_option("gemm.f32", "3xtf32")
+    client.set_option("gemm.f32", "hybrid")                                  # back to the default
 
 
 if __name__ == "__main__":
