@@ -119,6 +119,28 @@ def test_f32_defaults_to_the_hybrid_schedule_with_two_split_passes(plan):
     assert rc != 0
 
 
+def test_hybrid_f32_pair_buffers_follow_operand_major_and_batch(plan):
+    """pair buffers [2 planes][entries][rows][pitch]: one entry per batch element, a single one for a broadcast operand; the
+    buffer keeps the operand's own major (K-major: rows of K, MN-major: rows of M / N), rows pitched to 8 bf16 elements"""
+    M, N, K, Bt = 256, 384, 200, 3
+    rc, t = plan.matmul(F32, F32, [Bt, M, K], cs([Bt, M, K]), [1, K, N], cs([1, K, N]), [Bt, M, N], cs([Bt, M, N]))
+    assert rc == 0
+    launches = [ln.split()[1] for ln in t.splitlines() if ln.startswith("launch")]
+    assert launches[:2] == ["split_f32_bf16_pair", "split_f32_bf16_pair"] and launches[2].startswith("gemm_tf32_f32_") and len(launches) == 3
+    assert f"alloc {2 * Bt * M * 200 * 2}" in t            # lhs: 2 planes x 3 entries x [M, pad8(K) = 200] bf16
+    assert f"alloc {2 * 1 * K * N * 2}" in t                # rhs broadcast: 2 planes x ONE entry x [K, N] bf16 (row-major rhs = MN-major)
+    assert f"tmap esz=2 dims=({K},{M},{2 * Bt}) strides=({2 * 200},{2 * 200 * M}) box=(64,128) swizzle=3" in t
+    assert f"tmap esz=2 dims=({N},{K},2) strides=({2 * N},{2 * N * K}) box=(64,64) swizzle=3" in t
+    # transposed views on both sides: lhs MN-major ([K, M] buffer), rhs K-major ([N, K] buffer)
+    rc, t = plan.matmul(F32, F32, [M, K], [1, M], [K, N], [1, K], [M, N], [N, 1])
+    assert rc == 0 and "gemm_tf32_f32_" in t and "_mk grid" in t
+    assert f"tmap esz=2 dims=({M},{K},2) strides=({2 * M},{2 * M * K}) box=(64,64) swizzle=3" in t
+    assert f"tmap esz=2 dims=({K},{N},2) strides=({2 * 200},{2 * 200 * N})" in t
+    # K not a multiple of 8: rows pitched to pad8(K)
+    rc, t = plan.matmul(F32, F32, [M, 100], [100, 1], [100, N], [N, 1], [M, N], [N, 1])
+    assert rc == 0 and f"alloc {2 * M * 104 * 2}" in t and f"dims=(100,{M},2) strides=({2 * 104},{2 * 104 * M})" in t
+
+
 def test_stream_k_head_policy(plan):
     """Deterministic stream-K head instead of a partial last wave (launch_tcgen05 / sk_plan): only when the model gains,
     never for integer accumulators or the pair tile; it also feeds the tile choice."""
