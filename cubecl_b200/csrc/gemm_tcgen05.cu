@@ -198,15 +198,19 @@ __device__ __forceinline__ bool next_unit(UnitIter& it, const GemmParams& p, Wor
 // quarters (row group g of the atom in column g, byte s of the word is scale s).  kind::mxf8f6f4: one atom per k-block, MMA k
 // uses byte k.  kind::mxf4: K = 64 elements per MMA and two scales per row per MMA -> two atoms per k-block, MMA k uses
 // atom k / 2, bytes 2 (k % 2) and +1.  kind::mxf4nvf4 (NVFP4): a scale per 16 elements -> four atoms per k-block, MMA k uses atom k.
-// How the atoms get to TMEM (round 2, second session, measured with tools/microbench/tmem_cp_probe.cu, profiles/r02b_tmem_cp_probe.log):
+// How the atoms get to TMEM (round 2, second session; tools/microbench/tmem_cp_probe.cu, profiles/r02b_tmem_cp_probe*.log):
 // a tcgen05.cp blocks the issuing thread's tensor-core queue for 150-190 cycles, so three 32x128b.warpx4 copies issued by
 // the MMA thread in front of the four MMAs of a k-block (512 cycles of tensor work) made the k-block 770-840 cycles, six
-// 1260-1360, twelve 2050.  Copies issued by ANOTHER warp run beside the MMAs.  So a dedicated scale-copy thread (warp 2)
-// feeds a ring of TMEM scale buffers, synchronised with the MMA thread by two mbarriers per buffer (tcgen05.commit of the
-// copies -> sf_full, tcgen05.commit of the MMAs -> sf_empty).  Measured on 8192^3 (profiles/r02b_scaled_ab.log, same box, copies
-// by the MMA thread -> by the copy thread): mxfp8 2437 -> 2589 TFLOP/s, mxfp4 3417 -> 4100, nvfp4 2832 -> 3500.  Two atoms per
-// 128x256b copy (from four-times replicated images written by the TMA load through a zero-stride tensor-map dimension, which
-// works) measured the SAME as one broadcast copy per atom once the copies left the MMA thread, so the plain form stays.
+// 1260-1360, twelve 2050.  Copies issued by ANOTHER warp run beside the MMAs.  So:
+//   * the producers issue the stage's scale loads FIRST, on a barrier of their own (sf_ld[stage]; 512-byte box rows);
+//   * a dedicated scale-copy thread (warp 2) waits for sf_ld[stage], copies the atoms into the stage's own TMEM scale buffer
+//     (buffer = stage: the loads were only issued after the MMAs of the stage's previous round retired, so "atoms landed"
+//     implies "buffer free") and commits to sf_full[stage];
+//   * the MMA thread waits for sf_full[stage] next to the operands' full barrier.
+// Measured at 8192^3 -> bf16, same box, paused round-robin (profiles/r02b_scaled_ab.log), copies by the MMA thread -> this scheme:
+// mxfp8 2346 -> 2641 TFLOP/s, mxfp4 3878 -> 5438, nvfp4 2957 -> 4159.  Tried and measured equal or worse once the copies had left
+// the MMA thread: two atoms per 128x256b copy from four-times replicated images (which the TMA load can write itself through a
+// zero-stride tensor-map dimension), and a second copy thread in a ninth warp (gemm.sf_copy=thread2, kept as an option).
 // ACC = accumulator stages in TMEM: 256-wide scaled tiles have room for one only (512 columns - scale columns).
 // MT = 128-row sub-tiles of M per CTA.  MT = 2 (CG = 2, BLOCK_N = 256, ACC = 1) is the 512 x 256 pair tile: each CTA stages
 // 256 rows of A and half of B per k-block (48 KB, 4 stages) and holds two 128 x 256 accumulators -- all 512 TMEM columns.
