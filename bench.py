@@ -167,29 +167,50 @@ def host_threads() -> int:
         return max(1, min(256, os.cpu_count() or 1))
 
 
+_CPU_OPERANDS = {}
+
+
 def cpu_matmul_sample(seconds_target=12.0):
-    """Reference-order CPU matmul (oracle port, all host threads) on a bounded row-slab of the 8192^3 problem."""
+    """Reference-order CPU matmul (oracle port, all host threads) on a bounded block of C of the 8192^3 problem: every output is
+    one serial f32 sum over k (the reference's arithmetic), 4 x 4 outputs carried at once, rhs walked in L2-sized panels."""
     import oracle
     from cubecl_b200 import synth
     threads = host_threads()
     K = N_MM
-    b_nk = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(4, 512 * K, -1.0, 1.0))).reshape(512, K)  # 512 rhs columns
-    rows = 2 * threads
-    a = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(3, rows * K, -1.0, 1.0))).reshape(rows, K)
+
+    def operand(seed, rows):   # bf16-rounded rows of the seeded operand; kept across steps (generating 8192 x 8192 takes seconds)
+        have = _CPU_OPERANDS.get(seed)
+        if have is None or have.shape[0] < rows:
+            have = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(seed, rows * K, -1.0, 1.0))).reshape(rows, K)
+            _CPU_OPERANDS[seed] = have
+        return have[:rows]
+
+    b_nk = operand(4, 512)                                 # 512 rhs columns
+    rows = 4 * threads
+    a = operand(3, rows)
+    oracle.matmul_blocked_f32(a[:threads], b_nk, threads)  # thread pool up, pages touched
     t0 = time.perf_counter()
     oracle.matmul_blocked_f32(a, b_nk, threads)
     dt = time.perf_counter() - t0
     rate = 2.0 * rows * 512 * K / dt                       # FLOP/s on the probe
-    # size the sample: `rows_s` rows x 512 columns x K, ~seconds_target of work
-    rows_s = int(max(rows, min(8192, seconds_target * rate / (2.0 * 512 * K))))
-    rows_s = max(threads, rows_s // threads * threads)
-    a = synth.bf16_bits_to_f32(synth.f32_to_bf16_bits(synth.uniform_f32(3, rows_s * K, -1.0, 1.0))).reshape(rows_s, K)
+    # size the sample to ~seconds_target of work: rows first (up to the full 8192), then more rhs columns (up to the full 8192)
+    want = seconds_target * rate
+    rows_s = int(max(rows, min(N_MM, want / (2.0 * 512 * K))))
+    rows_s = max(4 * threads, rows_s // (4 * threads) * (4 * threads))
+    cols_s = 512
+    if rows_s >= N_MM:
+        rows_s = N_MM
+        cols_s = int(max(512, min(N_MM, want / (2.0 * N_MM * K)) // 512 * 512))
+    a = operand(3, rows_s)
+    if cols_s != 512:
+        b_nk = operand(4, cols_s)
     t0 = time.perf_counter()
     oracle.matmul_blocked_f32(a, b_nk, threads)
     dt = time.perf_counter() - t0
-    flops = 2.0 * rows_s * 512 * K
+    flops = 2.0 * rows_s * cols_s * K
     return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": "port",
-            "sample": f"{rows_s}x512 block of C of the bf16 8192^3 matmul (K=8192 full), reference-order f32 loops, {threads} threads, {dt:.1f} s",
+            "sample": f"{rows_s}x{cols_s} block of C of the bf16 8192^3 matmul (K=8192 full), reference-order f32 sums (4x4 outputs in flight, "
+                      f"64-column rhs panels), {threads} threads, {dt:.1f} s",
             "seconds": dt, "flops": flops}
 
 
