@@ -17,6 +17,7 @@ def _reset_options(client):
     yield
     client.set_option("gemm.variant", "auto")
     client.set_option("gemm.split_k", "auto")
+    client.set_option("gemm.sf_copy", "thread")
 
 
 def quantise(vals, dtype):
@@ -140,6 +141,20 @@ def test_prepacked_scales_and_batches(client, dtype):
     assert np.array_equal(plain, packed)
     for i in range(batch[0]):
         check(plain[i], a[i], b[i], sa[i], sb[i], 2e-6)
+
+
+@pytest.mark.parametrize("dtype,K", [("f8e4m3", 1024), ("f4e2m1x2", 2048)])
+def test_scale_copy_schemes_agree_bit_for_bit(client, dtype, K):
+    # who copies the scale atoms to TMEM (the dedicated copy thread, two of them, the MMA thread) changes the schedule, never the
+    # arithmetic: identical bits, and parity with the oracle, on a multi-tile problem with ragged edges
+    M, N = 300, 520
+    a_dev, a, b_dev, b, sa, sb = random_problem(M, N, K, dtype, dtype, seed=31)
+    outs = {}
+    for scheme in ("thread", "thread2", "mma"):
+        client.set_option("gemm.sf_copy", scheme)
+        outs[scheme] = run_scaled(client, a_dev, b_dev, sa, sb, dtype, dtype, "f32")
+    check(outs["thread"], a, b, sa, sb, 2e-6)
+    assert np.array_equal(outs["thread"], outs["thread2"]) and np.array_equal(outs["thread"], outs["mma"])
 
 
 # ------------------------------------------------------------------------------------------------ NVFP4 (ue4m3 scale per 16)
