@@ -145,16 +145,17 @@ def test_prepacked_scales_and_batches(client, dtype):
 
 @pytest.mark.parametrize("dtype,K", [("f8e4m3", 1024), ("f4e2m1x2", 2048)])
 def test_scale_copy_schemes_agree_bit_for_bit(client, dtype, K):
-    # who copies the scale atoms to TMEM (the dedicated copy thread, two of them, the MMA thread) changes the schedule, never the
-    # arithmetic: identical bits, and parity with the oracle, on a multi-tile problem with ragged edges
+    # who copies the scale atoms to TMEM (the dedicated copy thread, or two of them) changes the schedule, never the arithmetic:
+    # identical bits, and parity with the oracle, on a multi-tile problem with ragged edges.  (gemm.sf_copy=mma, the round-2 scheme,
+    # is kept as a TIMING reference for tools/perf_sweep.py scaledab only.)
     M, N = 300, 520
     a_dev, a, b_dev, b, sa, sb = random_problem(M, N, K, dtype, dtype, seed=31)
     outs = {}
-    for scheme in ("thread", "thread2", "mma"):
+    for scheme in ("thread", "thread2"):
         client.set_option("gemm.sf_copy", scheme)
         outs[scheme] = run_scaled(client, a_dev, b_dev, sa, sb, dtype, dtype, "f32")
     check(outs["thread"], a, b, sa, sb, 2e-6)
-    assert np.array_equal(outs["thread"], outs["thread2"]) and np.array_equal(outs["thread"], outs["mma"])
+    assert np.array_equal(outs["thread"], outs["thread2"])
 
 
 # ------------------------------------------------------------------------------------------------ NVFP4 (ue4m3 scale per 16)
